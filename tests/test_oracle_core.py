@@ -1,0 +1,256 @@
+"""Pins the CPU oracle (oracle/vfo.cpp) against independent numpy/scipy mathematics.
+
+The reference ships no tests or golden vectors for this path, so
+the pins are the analytic invariants listed there plus an independent assembly.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import npref
+from oracle import OracleMG, OracleSim
+
+RNG = np.random.default_rng(0)
+
+
+def make_sim(ne, dom=None, nu=0.3, bc=None, data_dir=None, emin=1e-4):
+    ne = np.array(ne)
+    N = len(ne)
+    if dom is None:
+        dom = (np.zeros(N), ne.astype(float))
+    s = OracleSim(ne, dom[0], dom[1])
+    s.set_isotropic(1.0, nu)
+    s.set_interp(0, 1.0, emin, 3.0, 3.0)
+    if bc is not None:
+        s.apply_bc_file(os.path.join(data_dir, "bcs", bc))
+    return s
+
+
+@pytest.mark.parametrize("N,h", [(2, (1.0, 1.0)), (2, (0.5, 0.25)), (3, (1.0, 1.0, 1.0)), (3, (0.25, 0.5, 0.125))])
+@pytest.mark.parametrize("nu", [0.0, 0.3])
+def test_K0_matches_textbook(N, h, nu):
+    ne = np.array([2] * N)
+    s = OracleSim(ne, np.zeros(N), ne * np.array(h))
+    s.set_isotropic(1.0, nu)
+    K0 = s.K0()
+    Kref = npref.k0_reference(N, h, 1.0, nu)
+    assert np.allclose(K0, K0.T, atol=1e-15)
+    assert np.abs(K0 - Kref).max() < 1e-13 * np.abs(Kref).max()
+    # rigid-body null space: 3 (2D) / 6 (3D) zero eigenvalues  (SURVEY section 4 invariant 1)
+    ev = np.linalg.eigvalsh(K0)
+    nz = 3 if N == 2 else 6
+    assert np.all(np.abs(ev[:nz]) < 1e-12) and ev[nz] > 1e-6
+    # scaling h^(N-2)
+    s2 = OracleSim(ne, np.zeros(N), 2 * ne * np.array(h)); s2.set_isotropic(1.0, nu)
+    assert np.allclose(s2.K0(), K0 * 2.0 ** (N - 2), rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("ne", [(6, 4), (5, 3, 4), (4, 4, 9)])
+def test_applyK_matches_assembled(ne):
+    s = make_sim(ne)
+    rho = RNG.uniform(0, 1, s.num_elements)
+    s.set_densities(rho)
+    E = s.E()
+    assert np.allclose(E, 1e-4 + rho ** 3 * (1 - 1e-4))
+    K = npref.assemble_K(ne, s.K0(), E)
+    u = RNG.normal(size=(s.num_nodes, len(ne)))
+    f = s.apply_K(u)
+    fref = npref.dof_to_field(K @ npref.field_to_dof(u), len(ne))
+    assert np.abs(f - fref).max() < 1e-13 * np.abs(fref).max()
+    # accumulate / negate variants (applyK<ZeroInit=false, Negate=true>)
+    b = RNG.normal(size=u.shape)
+    r = s.apply_K(u, out=b, zero_init=False, negate=True)
+    assert np.abs(r - (b - fref)).max() < 1e-12 * np.abs(fref).max()
+    # rigid translations are in the null space (invariant 3)
+    t = np.ones_like(u) * np.array([1.0, -2.0, 0.5][:len(ne)])
+    assert np.abs(s.apply_K(t)).max() < 1e-12
+
+
+def test_bc_mbb_2d(data_dir):
+    s = make_sim((8, 4), dom=(np.zeros(2), np.array([2.0, 1.0])), bc="mbb_N.bc", data_dir=data_dir)
+    m = s.dirichlet_mask().reshape(9, 5)
+    assert m[0, 0] == 3 and m[8, 0] == 2 and m.sum() == 5
+    f = s.build_load().reshape(9, 5, 2)
+    assert f[4, 4, 1] == -1 and np.count_nonzero(f) == 1
+
+
+def test_bc_cantilever_3d(data_dir):
+    s = make_sim((8, 4, 4), dom=(np.zeros(3), np.array([2.0, 1.0, 1.0])), bc="3D/cantilever_flexion_E.bc", data_dir=data_dir)
+    m = s.dirichlet_mask().reshape(9, 5, 5)
+    assert np.all(m[0] == 7) and np.all(m[1:] == 0)
+    f = s.build_load().reshape(9, 5, 5, 3)
+    assert f[8, 2, 2, 2] == -1 and np.count_nonzero(f) == 1
+
+
+def test_direct_solve_matches_scipy(data_dir):
+    ne = (8, 4, 4)
+    s = make_sim(ne, dom=(np.zeros(3), np.array([2.0, 1.0, 1.0])), bc="3D/cantilever_flexion_E.bc", data_dir=data_dir)
+    s.set_densities(RNG.uniform(0.2, 1, s.num_elements))
+    f = s.build_load()
+    u = s.solve(f)
+    K = npref.assemble_K(ne, s.K0(), s.E())
+    uref = npref.direct_solve(K, f, s.dirichlet_mask(), 3)
+    assert np.linalg.norm(u - uref) < 1e-9 * np.linalg.norm(uref)
+
+
+@pytest.mark.parametrize("ne,levels", [((8, 8), 2), ((8, 4, 4), 2)])
+def test_transfer_operators(ne, levels):
+    s = make_sim(ne)
+    mg = OracleMG(s, levels)
+    N = len(ne)
+    for l in range(levels):
+        nec = np.array(ne) // 2 ** (l + 1)
+        P = npref.prolongation(nec, N)
+        xc = RNG.normal(size=(mg.nn(l + 1), N))
+        xf = mg.interpolate(l, xc)
+        assert np.abs(npref.field_to_dof(xf) - P @ npref.field_to_dof(xc)).max() < 1e-14
+        acc = RNG.normal(size=xf.shape)
+        assert np.abs(mg.interpolate(l, xc, fine=acc) - (acc + xf)).max() < 1e-14
+        rf = RNG.normal(size=xf.shape)
+        rc = mg.restrict(l, rf)   # restriction == interpolation^T (invariant 5)
+        assert np.abs(npref.field_to_dof(rc) - P.T @ npref.field_to_dof(rf)).max() < 1e-13
+
+
+@pytest.mark.parametrize("ne,levels", [((16, 8), 3), ((8, 8, 8), 3), ((8, 4, 4), 2)])
+def test_galerkin_hierarchy(ne, levels):
+    """applyK(l) == P^T K_{l-1} P (invariant 4) for on-the-fly level 1, blockK levels and the cached coarsest Ke."""
+    s = make_sim(ne)
+    s.set_densities(RNG.uniform(0, 1, s.num_elements))
+    mg = OracleMG(s, levels)
+    mg.update_stiffness()
+    N = len(ne)
+    K = npref.assemble_K(ne, s.K0(), s.E())
+    for l in range(1, levels + 1):
+        P = npref.prolongation(np.array(ne) // 2 ** l, N)
+        K = (P.T @ K @ P).tocsr()
+        u = RNG.normal(size=(mg.nn(l), N))
+        f = mg.apply_K(l, u)
+        fref = npref.dof_to_field(K @ npref.field_to_dof(u), N)
+        assert np.abs(f - fref).max() < 1e-12 * np.abs(fref).max(), l
+        # stencil export agrees with the Galerkin matrix rows
+        S = mg.stencil(l)
+        nn = np.array(ne) // 2 ** l + 1
+        n = int(np.ravel_multi_index(tuple(nn // 2), nn))
+        row = K[N * n:N * n + N].toarray()
+        dense = np.zeros_like(row)
+        for sidx in range(3 ** N):
+            d = np.array(np.unravel_index(sidx, (3,) * N)) - 1
+            m = np.array(np.unravel_index(n, nn)) + d
+            if np.any(m < 0) or np.any(m >= nn):
+                continue
+            mm = int(np.ravel_multi_index(tuple(m), nn))
+            dense[:, N * mm:N * mm + N] = S[n, sidx]
+        assert np.abs(dense - row).max() < 1e-12 * np.abs(row).max()
+
+
+@pytest.mark.parametrize("case", ["2d_mbb", "3d_cant"])
+def test_multicolor_gs_matches_explicit(case, data_dir):
+    if case == "2d_mbb":
+        ne, dom, bc, levels = (16, 8), (np.zeros(2), np.array([2.0, 1.0])), "mbb_N.bc", 3
+    else:
+        ne, dom, bc, levels = (8, 4, 4), (np.zeros(3), np.array([2.0, 1.0, 1.0])), "3D/mbb_N.bc", 2
+    N = len(ne)
+    s = make_sim(ne, dom=dom, bc=bc, data_dir=data_dir)
+    s.set_densities(RNG.uniform(0.1, 1, s.num_elements))
+    mg = OracleMG(s, levels)
+    mg.update_stiffness()
+    K = npref.assemble_K(ne, s.K0(), s.E())
+    for l in range(levels):
+        sim_l = mg.get_sim(l)
+        nn = np.array(ne) // 2 ** l + 1
+        if l > 0:
+            P = npref.prolongation(np.array(ne) // 2 ** l, N)
+            K = (P.T @ K @ P).tocsr()
+        dm = sim_l.dirichlet_mask()
+        u = RNG.normal(size=(mg.nn(l), N))
+        bits = (dm[:, None] >> np.arange(N)[None, :]) & 1
+        u[bits == 1] = 0
+        b = RNG.normal(size=u.shape)
+        for fwd in (True, False):
+            got = mg.smooth(l, u, b, forward=fwd)
+            ref = npref.colored_gauss_seidel(K, u, b, nn, dm, forward=fwd)
+            assert np.abs(got - ref).max() < 1e-11 * max(1.0, np.abs(ref).max()), (l, fwd)
+
+
+def test_dirichlet_coarsening(data_dir):
+    s = make_sim((16, 8), dom=(np.zeros(2), np.array([2.0, 1.0])), bc="mbb_N.bc", data_dir=data_dir)
+    mg = OracleMG(s, 3)
+    for l in range(4):
+        m = mg.get_sim(l).dirichlet_mask().reshape(16 // 2 ** l + 1, 8 // 2 ** l + 1)
+        assert m[0, 0] == 3 and m[-1, 0] == 2 and np.count_nonzero(m) == 2
+    # an odd fine Dirichlet node constrains both coarse neighbours along that axis
+    s2 = make_sim((8, 8))
+    s2.add_dirichlet([0, 0], [3, 0], [3, 0], 1)
+    mg2 = OracleMG(s2, 1)
+    m = mg2.get_sim(1).dirichlet_mask().reshape(5, 5)
+    assert m[1, 0] == 1 and m[2, 0] == 1 and np.count_nonzero(m) == 2
+
+
+def test_multicolor_visit_order():
+    s = make_sim((4, 2, 2))
+    mg = OracleMG(s, 1)
+    order = mg.debug_multicolor_visit().reshape(5, 3, 3)
+    # colour c <-> parity bits (row-major), forward 0 -> 7 (SURVEY section 4 invariant 9)
+    pos = 0
+    for c in range(8):
+        off = [(c >> 2) & 1, (c >> 1) & 1, c & 1]
+        blk = order[off[0]::2, off[1]::2, off[2]::2]
+        assert blk.min() == pos and blk.max() == pos + blk.size - 1
+        assert np.all(np.diff(blk.ravel()) == 1)
+        pos += blk.size
+
+
+@pytest.mark.parametrize("case", ["2d", "3d"])
+@pytest.mark.parametrize("fmg", [True, False])
+def test_pcg_converges_to_direct_solution(case, fmg, data_dir):
+    if case == "2d":
+        ne, dom, bc, levels = (32, 16), (np.zeros(2), np.array([2.0, 1.0])), "mbb_N.bc", 2
+    else:
+        ne, dom, bc, levels = (16, 8, 8), (np.zeros(3), np.array([2.0, 1.0, 1.0])), "3D/cantilever_flexion_E.bc", 2
+    N = len(ne)
+    s = make_sim(ne, dom=dom, bc=bc, data_dir=data_dir, emin=1e-5)
+    s.set_uniform_density(0.5)
+    mg = OracleMG(s, levels)
+    f = s.build_load()
+    u, iters, res = mg.pcg(np.zeros_like(f), f, 100, 1e-10, 1, 1, fmg)
+    K = npref.assemble_K(ne, s.K0(), s.E())
+    uref = npref.direct_solve(K, f, s.dirichlet_mask(), N)
+    assert iters < 40
+    assert np.linalg.norm(u - uref) < 1e-8 * np.linalg.norm(uref)
+    assert res[-1] <= 1e-10 * np.linalg.norm(f)
+    # residual reported == b - K u with Dirichlet rows zeroed
+    r = npref.dof_to_field(npref.field_to_dof(f) - K @ npref.field_to_dof(u), N)
+    bits = (s.dirichlet_mask()[:, None] >> np.arange(N)[None, :]) & 1
+    r[bits == 1] = 0
+    assert abs(np.linalg.norm(r) - res[-1]) < 1e-6 * res[-1] + 1e-14
+    assert np.abs(mg.pcg_residual() - r).max() < 1e-12
+
+
+def test_pcg_heterogeneous_density_3d(data_dir):
+    ne = (16, 8, 8)
+    s = make_sim(ne, dom=(np.zeros(3), np.array([2.0, 1.0, 1.0])), bc="3D/cantilever_flexion_E.bc", data_dir=data_dir)
+    s.set_densities(RNG.uniform(0.05, 1, s.num_elements))
+    mg = OracleMG(s, 2)
+    f = s.build_load()
+    u, iters, res = mg.pcg(np.zeros_like(f), f, 200, 1e-9, 1, 2, True)
+    K = npref.assemble_K(ne, s.K0(), s.E())
+    uref = npref.direct_solve(K, f, s.dirichlet_mask(), 3)
+    assert np.linalg.norm(u - uref) < 1e-7 * np.linalg.norm(uref)
+
+
+def test_vcycle_is_symmetric_operator(data_dir):
+    """One symmetric-GS V-cycle from zero is a symmetric linear operator (needed for PCG)."""
+    ne = (8, 4, 4)
+    s = make_sim(ne, dom=(np.zeros(3), np.array([2.0, 1.0, 1.0])), bc="3D/cantilever_flexion_E.bc", data_dir=data_dir)
+    s.set_densities(RNG.uniform(0.1, 1, s.num_elements))
+    mg = OracleMG(s, 2)
+    mg.update_stiffness()
+    bits = (s.dirichlet_mask()[:, None] >> np.arange(3)[None, :]) & 1
+    a = RNG.normal(size=(s.num_nodes, 3)); a[bits == 1] = 0
+    b = RNG.normal(size=(s.num_nodes, 3)); b[bits == 1] = 0
+    z = np.zeros_like(a)
+    Ma = mg.solve(z, a, 1, 1, True, True, False)
+    Mb = mg.solve(z, b, 1, 1, True, True, False)
+    assert abs((Ma * b).sum() - (Mb * a).sum()) < 1e-10 * abs((Ma * b).sum())
