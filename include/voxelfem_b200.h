@@ -1,0 +1,199 @@
+/* voxelfem_b200.h -- C ABI of the B200-native VoxelFEM hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The C++
+ * host classes in voxelfem_b200/host/ (TensorProductSimulator, MultigridSolver,
+ * TopologyOptimizationProblem, ...) and the pyVoxelFEM pybind11 module are thin veneers
+ * over these entry points; tests/ call them directly through ctypes.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * VoxelFEM reference tree).  All functions return 0 on success and a non-zero status on
+ * failure; vf_last_error() then holds the message (the host wrappers rethrow it as the
+ * std::runtime_error / std::logic_error the reference would have thrown).
+ *
+ * Conventions (identical to the reference):
+ *   - grids are flattened row-major, axis 0 slowest;  nodes per dim = elements + 1 (Q1)
+ *   - nodal vector fields cross this boundary as VField = (numNodes x N) column-major,
+ *     i.e. component c of node n at data[c * numNodes + n]   (TensorProductSimulator.hh:180)
+ *   - per-element scalar fields are flat arrays of numElements doubles
+ *   - the build direction for fabrication masks is axis 1   (TensorProductSimulator.hh:1851)
+ * Host pointers are pageable or pinned host memory unless the name ends in _dev.
+ * There is no CPU fallback: every compute entry point runs CUDA kernels on the current
+ * device and fails with an error status if no device is usable.
+ */
+#ifndef VOXELFEM_B200_H
+#define VOXELFEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vf_sim vf_sim; /* TensorProductSimulator<double,1,1[,1]>  (TensorProductSimulator.hh:170-2182) */
+typedef struct vf_mg  vf_mg;  /* MultigridSolver<double,1,1[,1]>         (MultigridSolver.hh:23-1176)         */
+typedef struct vf_top vf_top; /* TopologyOptimizationProblem + MultigridComplianceObjective + FilterChain +
+                                 TotalVolumeConstraint + OCOptimizer state (TopologyOptimizationProblem.hh,
+                                 TopologyOptimizationObjective.hh:72-105, OptimalityCriterion.hh:38-149)   */
+typedef struct vf_lbl vf_lbl; /* LayerByLayerEvaluator (LayerByLayer.hh:25-309) */
+
+#define VF_LAW_SIMP 0
+#define VF_LAW_RAMP 1
+#define VF_FILTER_SMOOTH 0   /* SmoothingFilter  (TopologyOptimizationFilter.hh:285-400) */
+#define VF_FILTER_PROJECT 1  /* ProjectionFilter (TopologyOptimizationFilter.hh:189-245) */
+#define VF_SMOOTH_CONST 0
+#define VF_SMOOTH_LINEAR 1
+
+/* ---- library / device ------------------------------------------------------------ */
+const char *vf_last_error(void);
+int vf_device_count(int *count);
+int vf_set_device(int device);
+int vf_version(void);
+/* Number of kernels this library has launched since load / since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t vf_kernel_launch_count(void);
+void vf_reset_kernel_launch_count(void);
+
+/* ---- TensorProductSimulator ------------------------------------------------------ */
+/* ctor, TensorProductSimulator.hh:209-279.  dim = 2 or 3. */
+int vf_sim_create(int dim, const int64_t *ne, const double *domain_min, const double *domain_max, vf_sim **out);
+int vf_sim_destroy(vf_sim *s);
+int64_t vf_sim_num_nodes(const vf_sim *s);
+int64_t vf_sim_num_elements(const vf_sim *s);
+/* setETensor (:343-347) with the flattened tensor D (3x3 in 2D, 6x6 in 3D, row-major, MeshFEM
+ * Voigt order xx,yy[,zz,yz,xz],xy); recomputes K0 by 2-point Gauss quadrature (:67-80, :2078-2086). */
+int vf_sim_set_elasticity_tensor(vf_sim *s, const double *D);
+/* ElasticityTensor::setIsotropic (MeshFEM ElasticityTensor.hh:100-115; 2D = plane stress). */
+int vf_sim_set_isotropic(vf_sim *s, double young, double poisson);
+/* fullDensityElementStiffnessMatrix (:1077): (N*2^N)^2 doubles, row-major. */
+int vf_sim_get_K0(const vf_sim *s, double *out);
+/* setInterpolationLaw / setE_0 / setE_min / setSIMPExponent / setRAMPFactor (:1719-1723). */
+int vf_sim_set_interpolation(vf_sim *s, int law, double E_0, double E_min, double gamma, double q);
+int vf_sim_set_gravity(vf_sim *s, const double *g);                      /* setGravity (:1775) */
+int vf_sim_set_densities(vf_sim *s, const double *rho);                  /* setDensities (:785-790) */
+int vf_sim_set_uniform_density(vf_sim *s, double rho);                   /* setUniformDensities (:715-720) */
+int vf_sim_get_densities(const vf_sim *s, double *rho);                  /* getDensities (:780-783) */
+int vf_sim_get_young_moduli(const vf_sim *s, double *E);                 /* getYoungModulusScaleFactor (:969) */
+/* applyDisplacementsAndLoads (:600-652) for axis-aligned box regions given in absolute coordinates
+ * (3 doubles per corner / value, unused trailing entries ignored).  kind[r]: 0 = dirichlet with
+ * component bit-mask cmask[r] (bit c = component c), 1 = force (total force split evenly over the nodes
+ * in the box, :629-630). */
+int vf_sim_apply_bc_regions(vf_sim *s, int nregions, const int32_t *kind, const int32_t *cmask,
+                            const double *values, const double *box_min, const double *box_max);
+/* addDirichletCondition (:660-671). */
+int vf_sim_add_dirichlet_box(vf_sim *s, const double *u, const double *box_min, const double *box_max, int cmask);
+/* applySymmetryConditions (:2042-2053): axes / minMaxFace are bit-masks over the N axes. */
+int vf_sim_apply_symmetry_conditions(vf_sim *s, int axes_mask, int max_face_mask);
+int vf_sim_get_dirichlet_mask(const vf_sim *s, uint8_t *mask_per_node);  /* getDirichletMask (:675-682), bit c = component c */
+int64_t vf_sim_num_force_nodes(const vf_sim *s);
+int vf_sim_build_load_vector(vf_sim *s, double *f);                      /* buildLoadVector (:1269-1288) */
+/* applyK<ZeroInit,Negate> (:1410-1438 -> TPSStencils.hh:231-396, 431-728).
+ * zero_init=1: out = K u; zero_init=0: out +=/-= K u (out is read). */
+int vf_sim_apply_K(vf_sim *s, const double *u, double *out, int zero_init, int negate);
+int vf_sim_set_mask_layer(vf_sim *s, int64_t layer);                     /* setFabricationMaskHeightByLayer (:327-329) */
+int vf_sim_get_mask_info(const vf_sim *s, int64_t *first_masked_elem_layer, int64_t *first_detached_node_layer, double *height);
+/* complianceGradientFlattened (:1051-1055) / accumulateComplianceGradient (:1008-1040). */
+int vf_sim_compliance_gradient(vf_sim *s, const double *u, double *g, int accumulate);
+int vf_sim_element_energy_density(vf_sim *s, const double *u, double *out); /* elementEnergyDensity (:1057-1073) */
+/* TPS::solve (:1198-1230): direct solve with a dense GPU Cholesky; intended for coarse grids only
+ * (fails for more than VF_MAX_DIRECT_DOFS free variables). */
+#define VF_MAX_DIRECT_DOFS 20000
+int vf_sim_solve(vf_sim *s, const double *f, double *u);
+
+/* ---- MultigridSolver --------------------------------------------------------------- */
+/* ctor (MultigridSolver.hh:35-121): builds the hierarchy, coarsens the Dirichlet conditions (:58-103)
+ * and the 2^N coarsened full-density matrices (:116-120).  The simulator must outlive the solver and
+ * is mutated by it (mask height), exactly as in the reference. */
+int vf_mg_create(vf_sim *fine, int num_coarsening_levels, vf_mg **out);
+int vf_mg_destroy(vf_mg *mg);
+int vf_mg_num_levels(const vf_mg *mg);
+int64_t vf_mg_level_num_nodes(const vf_mg *mg, int level);
+int vf_mg_level_grid(const vf_mg *mg, int level, int64_t *ne);
+int vf_mg_level_dirichlet_mask(const vf_mg *mg, int level, uint8_t *mask_per_node);
+int vf_mg_get_coarsened_fine_K0(const vf_mg *mg, int fi, double *out);   /* coarsenedFineK0s (:1161) */
+int vf_mg_update_stiffness_matrices(vf_mg *mg);                           /* updateStiffnessMatrices (:846-905), banded variant (:907-1017) */
+int vf_mg_apply_K(vf_mg *mg, int level, const double *u, double *out);    /* applyK(l, u) (:464-504) */
+int vf_mg_compute_residual(vf_mg *mg, int level, const double *u, const double *b, double *r); /* computeResidual (:527-541) */
+int vf_mg_smooth(vf_mg *mg, int level, double *u, const double *b, int forward);  /* smoothingMulticoloredGS (:452-458) */
+int vf_mg_restrict(vf_mg *mg, int fine_level, const double *fine, double *coarse);            /* restriction (:216-262) */
+int vf_mg_interpolate(vf_mg *mg, int fine_level, const double *coarse, double *fine, int accumulate); /* interpolation / accum_interpolation (:178-212) */
+/* Assembled 3^N-point block stencil of a coarse level: [node][3^N][N][N] doubles (the reference's
+ * blockK, TensorProductSimulator.hh:885-966, in dense-slot form).  level >= 1. */
+int vf_mg_get_stencil(vf_mg *mg, int level, double *out);
+int vf_mg_coarse_solve(vf_mg *mg, const double *f, double *x);            /* coarsest TPS::solve, (:622-624) */
+/* solve (:546-573): numSteps V-cycles (first one a full-multigrid cycle if fmg). */
+int vf_mg_solve(vf_mg *mg, const double *u, const double *f, int num_steps, int num_smoothing_steps,
+                int stiffness_updated, int zero_dirichlet, int fmg, double *out);
+/* preconditionedConjugateGradient (:1047-1152).  x is updated in place.  residual_norms (may be NULL)
+ * receives ||r|| after every iteration (what the reference's it_callback would compute), at most max_iter
+ * entries.  cb (may be NULL) is invoked after every iteration with (iteration, ||r||, user). */
+typedef void (*vf_pcg_callback)(int iteration, double residual_norm, void *user);
+int vf_mg_pcg(vf_mg *mg, double *x, const double *b, int max_iter, double tol, int mg_iterations,
+              int mg_smoothing_iterations, int fmg, int dirichlet_already_satisfied,
+              int *out_iterations, double *residual_norms, vf_pcg_callback cb, void *user);
+int vf_mg_get_pcg_residual(vf_mg *mg, double *r);                         /* pcgResidual (:1156) */
+int vf_mg_set_symmetric_gauss_seidel(vf_mg *mg, int symmetric);           /* setSymmetricGaussSeidel (:123-125) */
+int vf_mg_set_mask_layer(vf_mg *mg, int64_t fine_layer);                  /* setFabricationMaskHeightByLayer (:1022-1028) */
+int vf_mg_decrement_mask(vf_mg *mg, int fine_layer_increment);            /* decrementFabricationMaskHeightByLayer (:1030-1036) */
+int vf_mg_debug_get(vf_mg *mg, int which /*0 x, 1 b, 2 r*/, int level, double *out); /* debug_get_x/b (:1158-1159) */
+int vf_mg_debug_multicolor_visit(vf_mg *mg, int32_t *order_per_node);     /* debugMulticolorVisit (:444-450) */
+
+/* Device-resident variants used by the optimization layer and by bench.py's HBM-resident timing:
+ * x_dev / b_dev are device pointers to VFields allocated with vf_dev_alloc. */
+int vf_dev_alloc(size_t num_doubles, double **out_dev);
+int vf_dev_free(double *dev);
+int vf_dev_upload(double *dev, const double *host, size_t num_doubles);
+int vf_dev_download(double *host, const double *dev, size_t num_doubles);
+int vf_dev_memset_zero(double *dev, size_t num_doubles);
+int vf_mg_pcg_dev(vf_mg *mg, double *x_dev, const double *b_dev, int max_iter, double tol, int mg_iterations,
+                  int mg_smoothing_iterations, int fmg, int dirichlet_already_satisfied,
+                  int *out_iterations, double *residual_norms, vf_pcg_callback cb, void *user);
+int vf_sim_build_load_vector_dev(vf_sim *s, double *f_dev);
+/* The CUDA stream all kernels of this solver are launched on (as a cudaStream_t). */
+void *vf_mg_stream(vf_mg *mg);
+int vf_mg_synchronize(vf_mg *mg);
+
+/* Per-kernel device timing (CUDA events on the solver's stream), for the roofline report.
+ * Categories: see vf_prof_name().  Enabling adds two event records per launch. */
+int vf_prof_enable(vf_mg *mg, int enable);
+int vf_prof_reset(vf_mg *mg);
+int vf_prof_num_categories(void);
+const char *vf_prof_name(int category);
+int vf_prof_get(vf_mg *mg, int category, int64_t *launches, double *total_ms, double *units);
+
+/* ---- Filters (stand-alone) -------------------------------------------------------- */
+int vf_filter_smooth(int dim, const int64_t *sizes, int radius, int type, const double *in, double *out); /* SmoothingFilter::apply == backprop (:297-310) */
+int vf_filter_project(int64_t n, double beta, const double *in, double *out);                                 /* ProjectionFilter::apply (:199-210) */
+int vf_filter_project_backprop(int64_t n, double beta, const double *in, const double *vars, double *out);  /* ProjectionFilter::backprop (:212-225) */
+
+/* ---- Topology optimization problem ------------------------------------------------ */
+/* filter_spec: 4 doubles per filter (kind, radius, smoothing type, beta). */
+int vf_top_create(vf_mg *mg, int num_filters, const double *filter_spec, double volume_fraction, vf_top **out);
+int vf_top_destroy(vf_top *t);
+/* MultigridComplianceObjective attributes (TopologyOptimizationObjective.hh:99-103). */
+int vf_top_set_solver(vf_top *t, int cg_iter, double tol, int mg_iterations, int mg_smoothing_iterations, int fmg, int zero_init);
+int vf_top_set_vars(vf_top *t, const double *x);                 /* setVars (TopologyOptimizationProblem.hh:41-50) */
+int vf_top_get_vars(vf_top *t, int which /*0 design, 1 physical*/, double *out);
+int vf_top_compliance(vf_top *t, double *out);                    /* ComplianceObjective::compliance (:41-43) */
+int vf_top_constraint(vf_top *t, double *out);                    /* TotalVolumeConstraint::evaluate (TopologyOptimizationConstraint.hh:30-32) */
+int vf_top_objective_gradient(vf_top *t, double *g);              /* evaluateObjectiveGradient (:77-84) */
+int vf_top_constraint_jacobian(vf_top *t, double *g);             /* evaluateConstraintsJacobian (:106-121), single row */
+int vf_top_get_u(vf_top *t, double *u);
+int vf_top_last_pcg_iterations(vf_top *t);
+int vf_top_oc_step(vf_top *t, double m, double p, double ctol, int *num_constraint_evals); /* OCOptimizer::step (OptimalityCriterion.hh:51-134) */
+int vf_top_get_lambda_bracket(vf_top *t, double *lo, double *hi);
+
+/* ---- Layer-by-layer evaluator ------------------------------------------------------ */
+int vf_lbl_create(vf_mg *mg, vf_lbl **out);                       /* LayerByLayerEvaluator(lblSim) (LayerByLayer.hh:33-36) */
+int vf_lbl_destroy(vf_lbl *l);
+int vf_lbl_select_init_method(vf_lbl *l, const char *method);    /* selectInitMethod (:214-220): "zero", "constant", "fd", "N=k" */
+typedef void (*vf_lbl_callback)(int64_t layer, double compliance, int pcg_iterations, void *user);
+int vf_lbl_run(vf_lbl *l, int zero_init, int64_t layer_increment, int max_iter, double tol, int mg_iterations,
+               int mg_smoothing_iterations, int fmg, vf_lbl_callback cb, void *user); /* run (:223-296) */
+int vf_lbl_objective(vf_lbl *l, double *out);                     /* objective (:299) */
+int vf_lbl_gradient(vf_lbl *l, double *g);                        /* gradient (:300) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXELFEM_B200_H */

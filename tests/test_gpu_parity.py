@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): indexing / level layout bit-exact; a single operator
+application agrees to rounding (1e-12 relative here); converged displacements <= 1e-6 relative L2;
+compliance and sensitivities <= 1e-8 relative; CG iteration counts compared side by side.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import OracleMG, OracleProblem, OracleSim
+
+pytestmark = pytest.mark.gpu
+
+RNG = np.random.default_rng(1234)
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from voxelfem_b200 import capi as c
+    assert c.device_count() > 0
+    return c
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def make_pair(capi, ne, dom=None, nu=0.3, bc=None, data_dir=None, emin=1e-4, rho=None):
+    ne = np.array(ne)
+    N = len(ne)
+    if dom is None:
+        dom = (np.zeros(N), ne.astype(float))
+    sims = []
+    for cls in (capi.Sim, OracleSim):
+        s = cls(ne, dom[0], dom[1])
+        s.set_isotropic(1.0, nu)
+        s.set_interp(0, 1.0, emin, 3.0, 3.0)
+        if bc is not None:
+            s.apply_bc_file(os.path.join(data_dir, "bcs", bc))
+        if rho is not None:
+            if np.isscalar(rho):
+                s.set_uniform_density(rho)
+            else:
+                s.set_densities(rho)
+        sims.append(s)
+    return sims
+
+
+@pytest.mark.parametrize("N,h,nu", [(2, (1.0, 1.0), 0.3), (2, (0.5, 0.25), 0.0), (3, (1.0, 1.0, 1.0), 0.3), (3, (0.25, 0.5, 0.125), 0.2)])
+def test_K0(capi, N, h, nu):
+    ne = np.array([2] * N)
+    g, o = make_pair(capi, ne, dom=(np.zeros(N), ne * np.array(h)), nu=nu)
+    assert rel(g.K0(), o.K0()) < 1e-14
+
+
+@pytest.mark.parametrize("ne", [(6, 4), (33, 17), (5, 3, 4), (4, 4, 9), (17, 9, 35)])
+def test_applyK_level0(capi, ne):
+    rho = RNG.uniform(0, 1, int(np.prod(ne)))
+    g, o = make_pair(capi, ne, rho=rho)
+    assert rel(g.E(), o.E()) < 1e-15
+    u = RNG.normal(size=(o.num_nodes, len(ne)))
+    assert rel(g.apply_K(u), o.apply_K(u)) < 1e-12
+    b = RNG.normal(size=u.shape)
+    assert rel(g.apply_K(u, out=b, zero_init=False, negate=True), o.apply_K(u, out=b, zero_init=False, negate=True)) < 1e-12
+    assert rel(g.apply_K(u, out=b, zero_init=False, negate=False), o.apply_K(u, out=b, zero_init=False, negate=False)) < 1e-12
+
+
+@pytest.mark.parametrize("bc,ne,dom", [("mbb_N.bc", (16, 8), (2.0, 1.0)), ("cantilever_flexion_E.bc", (16, 8), (2.0, 1.0)),
+                                       ("3D/cantilever_flexion_E.bc", (8, 4, 4), (2.0, 1.0, 1.0)), ("3D/mbb_N.bc", (8, 4, 6), (2.0, 1.0, 1.0))])
+def test_boundary_conditions_bit_exact(capi, bc, ne, dom, data_dir):
+    g, o = make_pair(capi, ne, dom=(np.zeros(len(ne)), np.array(dom)), bc=bc, data_dir=data_dir, rho=1.0)
+    assert np.array_equal(g.dirichlet_mask(), o.dirichlet_mask())
+    assert np.array_equal(g.build_load(), o.build_load())
+
+
+def test_self_weight_load(capi):
+    ne = (6, 5, 4)
+    rho = RNG.uniform(0, 1, int(np.prod(ne)))
+    g, o = make_pair(capi, ne, rho=rho)
+    for s in (g, o):
+        s.set_gravity([0.0, -1.0, 0.0])
+    assert rel(g.build_load(), o.build_load()) < 1e-14
+
+
+HIER = [((16, 8), (2.0, 1.0), "mbb_N.bc", 3), ((16, 16, 8), (2.0, 2.0, 1.0), "3D/cantilever_flexion_E.bc", 3),
+        ((8, 4, 4), (2.0, 1.0, 1.0), "3D/mbb_N.bc", 2)]
+
+
+@pytest.mark.parametrize("ne,dom,bc,levels", HIER)
+def test_hierarchy_operators(capi, ne, dom, bc, levels, data_dir):
+    """Level layout + Dirichlet coarsening bit-exact; applyK / residual / GS / transfers per level to rounding."""
+    N = len(ne)
+    rho = RNG.uniform(0.05, 1, int(np.prod(ne)))
+    g, o = make_pair(capi, ne, dom=(np.zeros(N), np.array(dom)), bc=bc, data_dir=data_dir, rho=rho)
+    gm, om = capi.MG(g, levels), OracleMG(o, levels)
+    gm.update_stiffness(); om.update_stiffness()
+    for fi in range(2 ** N):
+        assert rel(gm.coarsened_fine_K0(fi), om.coarsened_fine_K0(fi)) < 1e-14
+    for l in range(levels + 1):
+        assert gm.nn(l) == om.nn(l)
+        dm = om.get_sim(l).dirichlet_mask()
+        assert np.array_equal(gm.get_sim(l).dirichlet_mask(), dm)
+        u = RNG.normal(size=(om.nn(l), N))
+        b = RNG.normal(size=u.shape)
+        assert rel(gm.apply_K(l, u), om.apply_K(l, u)) < 1e-12, l
+        assert rel(gm.residual(l, u, b), om.residual(l, u, b)) < 1e-12, l
+        if l >= 1:
+            assert rel(gm.stencil(l), om.stencil(l)) < 1e-12, l
+        if l < levels:
+            bits = (dm[:, None] >> np.arange(N)[None, :]) & 1
+            u0 = u.copy(); u0[bits == 1] = 0
+            for fwd in (True, False):
+                assert rel(gm.smooth(l, u0, b, fwd), om.smooth(l, u0, b, fwd)) < 1e-11, (l, fwd)
+            xc = RNG.normal(size=(om.nn(l + 1), N))
+            assert rel(gm.interpolate(l, xc), om.interpolate(l, xc)) < 1e-14
+            assert rel(gm.interpolate(l, xc, fine=u), om.interpolate(l, xc, fine=u)) < 1e-14
+            assert rel(gm.restrict(l, u), om.restrict(l, u)) < 1e-13
+    f = RNG.normal(size=(om.nn(levels), N))
+    assert rel_l2(gm.coarse_solve(f), om.coarse_solve(f)) < 1e-9
+    assert np.array_equal(gm.debug_multicolor_visit(), om.debug_multicolor_visit())
+
+
+@pytest.mark.parametrize("ne,dom,bc,levels", HIER)
+@pytest.mark.parametrize("fmg", [True, False])
+def test_vcycle_matches_oracle(capi, ne, dom, bc, levels, fmg, data_dir):
+    N = len(ne)
+    rho = RNG.uniform(0.05, 1, int(np.prod(ne)))
+    g, o = make_pair(capi, ne, dom=(np.zeros(N), np.array(dom)), bc=bc, data_dir=data_dir, rho=rho)
+    gm, om = capi.MG(g, levels), OracleMG(o, levels)
+    dm = o.dirichlet_mask()
+    bits = (dm[:, None] >> np.arange(N)[None, :]) & 1
+    r = RNG.normal(size=(o.num_nodes, N)); r[bits == 1] = 0
+    z = np.zeros_like(r)
+    for nsm in (1, 2):
+        a = gm.solve(z, r, 1, nsm, False, True, fmg)
+        b = om.solve(z, r, 1, nsm, False, True, fmg)
+        assert rel_l2(a, b) < 1e-10, nsm
+    for l in range(levels + 1):
+        assert rel_l2(gm.debug_get("x", l), om.debug_get("x", l)) < 1e-9
+
+
+PCG_CASES = [
+    ("C1-small", (64, 32), (2.0, 1.0), "mbb_N.bc", 2, 0.5, 1e-5),
+    ("C3-small", (32, 32, 32), (1.0, 1.0, 1.0), "3D/cantilever_flexion_E.bc", 2, 0.5, 1e-5),
+    ("C3-hetero", (32, 16, 16), (2.0, 1.0, 1.0), "3D/cantilever_flexion_E.bc", 2, None, 1e-4),
+]
+
+
+@pytest.mark.parametrize("name,ne,dom,bc,levels,rho,emin", PCG_CASES)
+def test_pcg_parity(capi, name, ne, dom, bc, levels, rho, emin, data_dir):
+    N = len(ne)
+    if rho is None:
+        rho = RNG.uniform(0.05, 1, int(np.prod(ne)))
+    g, o = make_pair(capi, ne, dom=(np.zeros(N), np.array(dom)), bc=bc, data_dir=data_dir, rho=rho, emin=emin)
+    gm, om = capi.MG(g, levels), OracleMG(o, levels)
+    f = o.build_load()
+    ug, itg, resg = gm.pcg(np.zeros_like(f), f, 100, 1e-10, 1, 1, True)
+    uo, ito, reso = om.pcg(np.zeros_like(f), f, 100, 1e-10, 1, 1, True)
+    print(f"[{name}] PCG iterations GPU {itg} vs oracle {ito}")
+    assert abs(itg - ito) <= 1
+    assert rel_l2(ug, uo) < 1e-6
+    k = min(itg, ito) - 1
+    assert np.allclose(resg[:k], reso[:k], rtol=1e-5)
+    cg = 0.5 * (f * ug).sum(); co = 0.5 * (f * uo).sum()
+    assert abs(cg - co) < 1e-8 * abs(co)
+    sg, so = g.compliance_gradient(ug), o.compliance_gradient(uo)
+    assert rel(sg, so) < 1e-7
+    assert rel(g.compliance_gradient(uo), so) < 1e-12   # same displacement -> sensitivities to rounding
+    assert rel(g.energy_density(uo), o.energy_density(uo)) < 1e-12
+    assert rel(gm.pcg_residual(), om.pcg_residual()) < 1e-3 or np.abs(om.pcg_residual()).max() < 1e-9
+
+
+def test_pcg_plain_vcycle_and_callback(capi, data_dir):
+    ne, dom = (32, 16, 16), (2.0, 1.0, 1.0)
+    g, o = make_pair(capi, ne, dom=(np.zeros(3), np.array(dom)), bc="3D/cantilever_flexion_E.bc", data_dir=data_dir, rho=0.6)
+    gm, om = capi.MG(g, 2), OracleMG(o, 2)
+    f = o.build_load()
+    seen = []
+    ug, itg, resg = gm.pcg(np.zeros_like(f), f, 50, 1e-8, 1, 2, False, callback=lambda i, r: seen.append((i, r)))
+    uo, ito, reso = om.pcg(np.zeros_like(f), f, 50, 1e-8, 1, 2, False)
+    assert abs(itg - ito) <= 1 and rel_l2(ug, uo) < 1e-6
+    assert [i for i, _ in seen] == list(range(1, itg + 1)) and np.allclose([r for _, r in seen], resg)
+
+
+def test_direct_solve_single_level(capi, data_dir):
+    ne, dom = (8, 4, 4), (2.0, 1.0, 1.0)
+    rho = RNG.uniform(0.2, 1, int(np.prod(ne)))
+    g, o = make_pair(capi, ne, dom=(np.zeros(3), np.array(dom)), bc="3D/cantilever_flexion_E.bc", data_dir=data_dir, rho=rho)
+    f = o.build_load()
+    assert rel_l2(g.solve(f), o.solve(f)) < 1e-9
+    gm = capi.MG(g, 0)
+    u, it, _ = gm.pcg(np.zeros_like(f), f, 10, 1e-8)
+    assert it == 1 and rel_l2(u, o.solve(f)) < 1e-9
+
+
+def test_odd_grid_rejected(capi):
+    g, _ = make_pair(capi, (6, 4), rho=1.0)
+    with pytest.raises(RuntimeError, match="divisible"):
+        capi.MG(g, 2)
+
+
+def test_masked_operators(capi, data_dir):
+    """Fabrication mask (layer-by-layer): mask arithmetic bit-exact, masked applyK / residual / smoothing / transfer parity."""
+    ne, levels = (8, 16, 8), 2
+    rho = RNG.uniform(0.3, 1, int(np.prod(ne)))
+    g, o = make_pair(capi, ne, rho=rho)
+    for s in (g, o):
+        s.add_dirichlet([0, 0, 0], [-1, -0.01, -1], [100, 0.01, 100], 7)
+    gm, om = capi.MG(g, levels), OracleMG(o, levels)
+    for layer in (16, 11, 10, 3):
+        gm.set_mask_layer(layer); om.set_mask_layer(layer)
+        assert g.mask_info() == o.mask_info()
+        assert rel(g.E(), o.E()) < 1e-15
+        gm.update_stiffness(); om.update_stiffness()
+        nn = np.array(ne) + 1
+        u = RNG.normal(size=(o.num_nodes, 3)).reshape(*nn, 3)
+        det = o.mask_info()[1]
+        u[:, det:, :, :] = 0      # detached entries: defined as zero here
+        u = u.reshape(-1, 3)
+        b = RNG.normal(size=u.shape).reshape(*nn, 3); b[:, det:] = 0; b = b.reshape(-1, 3)
+        ag, ao = g.apply_K(u).reshape(*nn, 3), o.apply_K(u).reshape(*nn, 3)
+        assert rel(ag[:, :det], ao[:, :det]) < 1e-12
+        assert np.all(ag[:, det:] == 0)
+        rg, ro = gm.residual(0, u, b).reshape(*nn, 3), om.residual(0, u, b).reshape(*nn, 3)
+        assert rel(rg[:, :det], ro[:, :det]) < 1e-12
+        dm = o.dirichlet_mask(); bits = (dm[:, None] >> np.arange(3)[None, :]) & 1
+        u0 = u.copy(); u0[bits == 1] = 0
+        sg, so = gm.smooth(0, u0, b, True).reshape(*nn, 3), om.smooth(0, u0, b, True).reshape(*nn, 3)
+        assert rel(sg[:, :det], so[:, :det]) < 1e-11
+        rcg, rco = gm.restrict(0, rg.reshape(-1, 3)), om.restrict(0, ro.reshape(-1, 3))
+        nnc = np.array(ne) // 2 + 1
+        detc = int(np.ceil(layer / 2 - 1e-10)) + 1
+        assert rel(rcg.reshape(*nnc, 3)[:, :min(detc + 1, nnc[1])], rco.reshape(*nnc, 3)[:, :min(detc + 1, nnc[1])]) < 1e-12
+        for l in (1, 2):
+            uc = RNG.normal(size=(om.nn(l), 3))
+            nl = np.array(ne) // 2 ** l + 1
+            dl = int(np.ceil(layer / 2 ** l - 1e-10)) + 1
+            uc = uc.reshape(*nl, 3); uc[:, dl:] = 0; uc = uc.reshape(-1, 3)
+            a1, a2 = gm.apply_K(l, uc).reshape(*nl, 3), om.apply_K(l, uc).reshape(*nl, 3)
+            assert rel(a1[:, :dl], a2[:, :dl]) < 1e-11, (layer, l)
+
+
+def test_masked_pcg(capi):
+    ne, levels = (8, 16, 8), 2
+    g, o = make_pair(capi, ne, rho=0.7)
+    for s in (g, o):
+        s.add_dirichlet([0, 0, 0], [-1, -0.01, -1], [100, 0.01, 100], 7)
+        s.set_gravity([0.0, -1.0, 0.0])
+    gm, om = capi.MG(g, levels), OracleMG(o, levels)
+    for layer in (16, 9):
+        gm.set_mask_layer(layer); om.set_mask_layer(layer)
+        f = o.build_load()
+        assert rel(g.build_load(), f) < 1e-14
+        ug, itg, _ = gm.pcg(np.zeros_like(f), f, 50, 1e-8, 1, 1, False, dirichlet_ok=True)
+        uo, ito, _ = om.pcg(np.zeros_like(f), f, 50, 1e-8, 1, 1, False, dirichlet_ok=True)
+        det = o.mask_info()[1]
+        nn = np.array(ne) + 1
+        assert abs(itg - ito) <= 1
+        assert rel_l2(ug.reshape(*nn, 3)[:, :det], uo.reshape(*nn, 3)[:, :det]) < 1e-6
+
+
+@pytest.mark.parametrize("shape,radius,ftype", [((12, 9), 2, 1), ((7, 5, 6), 3, 1), ((7, 5, 6), 1, 0), ((3, 2, 4), 3, 1), ((40, 33, 37), 3, 1)])
+def test_smoothing_filter(capi, shape, radius, ftype):
+    x = RNG.uniform(0, 1, int(np.prod(shape)))
+    a = capi.smoothing_filter(x, shape, radius, ftype)
+    b = oracle.smoothing_filter(x, shape, radius, ftype)
+    assert rel(a, b) < 1e-13
+    # symmetric operator (apply == backprop, SURVEY section 4 invariant 6)
+    y = RNG.uniform(0, 1, x.size)
+    assert abs(a @ y - x @ capi.smoothing_filter(y, shape, radius, ftype)) < 1e-10
+
+
+def test_projection_filter(capi):
+    x = RNG.uniform(0, 1, 1001)
+    for beta in (1.0, 4.0):
+        assert rel(capi.projection_apply(x, beta), oracle.projection_apply(x, beta)) < 1e-14
+        g = RNG.normal(size=x.size)
+        assert rel(capi.projection_backprop(g, x, beta), oracle.projection_backprop(g, x, beta)) < 1e-13
+
+
+@pytest.mark.parametrize("ne,dom,bc", [((32, 16), (2.0, 1.0), "cantilever_flexion_E.bc"), ((16, 8, 8), (2.0, 1.0, 1.0), "3D/cantilever_flexion_E.bc")])
+def test_topopt_oc_iterations(capi, ne, dom, bc, data_dir):
+    """Config-2 style loop at reduced size: filters + MG-PCG compliance + OC, three iterations side by side."""
+    N = len(ne)
+    V = 0.3
+    x0 = np.full(int(np.prod(ne)), 0.5 + np.arctanh((2 * V - 1) * np.tanh(0.5)) / 1.0)   # ProjectionFilter(1).invert(V)
+    g, o = make_pair(capi, ne, dom=(np.zeros(N), np.array(dom)), bc=bc, data_dir=data_dir, rho=1.0)
+    gm, om = capi.MG(g, 2), OracleMG(o, 2)
+    filters = [("smooth", 2, 1), ("project", 1.0)]
+    gp, op = capi.Problem(gm, filters, V), OracleProblem(om, filters, V)
+    for p in (gp, op):
+        p.set_solver(100, 1e-9, 1, 2, True, False)
+        p.set_vars(x0)
+    for it in range(3):
+        assert abs(gp.compliance() - op.compliance()) < 1e-8 * abs(op.compliance()), it
+        assert abs(gp.constraint() - op.constraint()) < 1e-12
+        assert rel(gp.objective_gradient(), op.objective_gradient()) < 1e-7
+        assert rel(gp.constraint_jacobian(), op.constraint_jacobian()) < 1e-12
+        ng, no = gp.oc_step(), op.oc_step()
+        print(f"OC it {it}: evals GPU {ng} oracle {no}; PCG its GPU {gp.last_pcg_iters()} oracle {op.last_pcg_iters()}")
+        assert ng == no
+        assert abs(gp.last_pcg_iters() - op.last_pcg_iters()) <= 1
+        assert rel(gp.design_vars(), op.design_vars()) < 1e-6
+        assert abs(gp.constraint()) <= 1e-6 + 1e-9            # OC postcondition (invariant 8)
+    assert rel_l2(gp.u(), op.u()) < 1e-6

@@ -1,0 +1,533 @@
+"""ctypes binding of the C ABI in include/voxelfem_b200.h (libvoxelfem_b200.so).
+
+This is plumbing for tests/ and bench.py; the reference-facing Python module is the
+pybind11 `pyVoxelFEM` built from voxelfem_b200/host/.  Nothing here computes on the CPU:
+every numeric call goes to the CUDA library and raises if it (or a GPU) is missing.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvoxelfem_b200.so")
+DATA_DIR = os.path.join(_HERE, "data")
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+PCG_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_void_p)
+LBL_CALLBACK = C.CFUNCTYPE(None, C.c_int64, C.c_double, C.c_int, C.c_void_p)
+
+_lib = None
+
+
+class VoxelFEMError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libvoxelfem_b200.so; fails loudly if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VoxelFEMError("libvoxelfem_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cd, i64, sz = C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_size_t
+    pvp = C.POINTER(C.c_void_p)
+    sig = {
+        "vf_last_error": (C.c_char_p, []),
+        "vf_device_count": (ci, [C.POINTER(ci)]),
+        "vf_set_device": (ci, [ci]),
+        "vf_version": (ci, []),
+        "vf_kernel_launch_count": (i64, []),
+        "vf_reset_kernel_launch_count": (None, []),
+        "vf_sim_create": (ci, [ci, _ip, _dp, _dp, pvp]),
+        "vf_sim_destroy": (ci, [vp]),
+        "vf_sim_num_nodes": (i64, [vp]),
+        "vf_sim_num_elements": (i64, [vp]),
+        "vf_sim_set_elasticity_tensor": (ci, [vp, _dp]),
+        "vf_sim_set_isotropic": (ci, [vp, cd, cd]),
+        "vf_sim_get_K0": (ci, [vp, _dp]),
+        "vf_sim_set_interpolation": (ci, [vp, ci, cd, cd, cd, cd]),
+        "vf_sim_set_gravity": (ci, [vp, _dp]),
+        "vf_sim_set_densities": (ci, [vp, _dp]),
+        "vf_sim_set_uniform_density": (ci, [vp, cd]),
+        "vf_sim_get_densities": (ci, [vp, _dp]),
+        "vf_sim_get_young_moduli": (ci, [vp, _dp]),
+        "vf_sim_apply_bc_regions": (ci, [vp, ci, _i32p, _i32p, _dp, _dp, _dp]),
+        "vf_sim_add_dirichlet_box": (ci, [vp, _dp, _dp, _dp, ci]),
+        "vf_sim_apply_symmetry_conditions": (ci, [vp, ci, ci]),
+        "vf_sim_get_dirichlet_mask": (ci, [vp, _u8p]),
+        "vf_sim_num_force_nodes": (i64, [vp]),
+        "vf_sim_build_load_vector": (ci, [vp, _dp]),
+        "vf_sim_build_load_vector_dev": (ci, [vp, vp]),
+        "vf_sim_apply_K": (ci, [vp, _dp, _dp, ci, ci]),
+        "vf_sim_set_mask_layer": (ci, [vp, i64]),
+        "vf_sim_get_mask_info": (ci, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(cd)]),
+        "vf_sim_compliance_gradient": (ci, [vp, _dp, _dp, ci]),
+        "vf_sim_element_energy_density": (ci, [vp, _dp, _dp]),
+        "vf_sim_solve": (ci, [vp, _dp, _dp]),
+        "vf_mg_create": (ci, [vp, ci, pvp]),
+        "vf_mg_destroy": (ci, [vp]),
+        "vf_mg_num_levels": (ci, [vp]),
+        "vf_mg_level_num_nodes": (i64, [vp, ci]),
+        "vf_mg_level_grid": (ci, [vp, ci, _ip]),
+        "vf_mg_level_dirichlet_mask": (ci, [vp, ci, _u8p]),
+        "vf_mg_get_coarsened_fine_K0": (ci, [vp, ci, _dp]),
+        "vf_mg_update_stiffness_matrices": (ci, [vp]),
+        "vf_mg_apply_K": (ci, [vp, ci, _dp, _dp]),
+        "vf_mg_compute_residual": (ci, [vp, ci, _dp, _dp, _dp]),
+        "vf_mg_smooth": (ci, [vp, ci, _dp, _dp, ci]),
+        "vf_mg_restrict": (ci, [vp, ci, _dp, _dp]),
+        "vf_mg_interpolate": (ci, [vp, ci, _dp, _dp, ci]),
+        "vf_mg_get_stencil": (ci, [vp, ci, _dp]),
+        "vf_mg_coarse_solve": (ci, [vp, _dp, _dp]),
+        "vf_mg_solve": (ci, [vp, _dp, _dp, ci, ci, ci, ci, ci, _dp]),
+        "vf_mg_pcg": (ci, [vp, _dp, _dp, ci, cd, ci, ci, ci, ci, C.POINTER(ci), _dp, PCG_CALLBACK, vp]),
+        "vf_mg_pcg_dev": (ci, [vp, vp, vp, ci, cd, ci, ci, ci, ci, C.POINTER(ci), _dp, PCG_CALLBACK, vp]),
+        "vf_mg_get_pcg_residual": (ci, [vp, _dp]),
+        "vf_mg_set_symmetric_gauss_seidel": (ci, [vp, ci]),
+        "vf_mg_set_mask_layer": (ci, [vp, i64]),
+        "vf_mg_decrement_mask": (ci, [vp, ci]),
+        "vf_mg_debug_get": (ci, [vp, ci, ci, _dp]),
+        "vf_mg_debug_multicolor_visit": (ci, [vp, _i32p]),
+        "vf_dev_alloc": (ci, [sz, pvp]),
+        "vf_dev_free": (ci, [vp]),
+        "vf_dev_upload": (ci, [vp, _dp, sz]),
+        "vf_dev_download": (ci, [_dp, vp, sz]),
+        "vf_dev_memset_zero": (ci, [vp, sz]),
+        "vf_mg_stream": (vp, [vp]),
+        "vf_mg_synchronize": (ci, [vp]),
+        "vf_prof_enable": (ci, [vp, ci]),
+        "vf_prof_reset": (ci, [vp]),
+        "vf_prof_num_categories": (ci, []),
+        "vf_prof_name": (C.c_char_p, [ci]),
+        "vf_prof_get": (ci, [vp, ci, C.POINTER(i64), C.POINTER(cd), C.POINTER(cd)]),
+        "vf_filter_smooth": (ci, [ci, _ip, ci, ci, _dp, _dp]),
+        "vf_filter_project": (ci, [i64, cd, _dp, _dp]),
+        "vf_filter_project_backprop": (ci, [i64, cd, _dp, _dp, _dp]),
+        "vf_top_create": (ci, [vp, ci, _dp, cd, pvp]),
+        "vf_top_destroy": (ci, [vp]),
+        "vf_top_set_solver": (ci, [vp, ci, cd, ci, ci, ci, ci]),
+        "vf_top_set_vars": (ci, [vp, _dp]),
+        "vf_top_get_vars": (ci, [vp, ci, _dp]),
+        "vf_top_compliance": (ci, [vp, C.POINTER(cd)]),
+        "vf_top_constraint": (ci, [vp, C.POINTER(cd)]),
+        "vf_top_objective_gradient": (ci, [vp, _dp]),
+        "vf_top_constraint_jacobian": (ci, [vp, _dp]),
+        "vf_top_get_u": (ci, [vp, _dp]),
+        "vf_top_last_pcg_iterations": (ci, [vp]),
+        "vf_top_oc_step": (ci, [vp, cd, cd, cd, C.POINTER(ci)]),
+        "vf_top_get_lambda_bracket": (ci, [vp, C.POINTER(cd), C.POINTER(cd)]),
+        "vf_lbl_create": (ci, [vp, pvp]),
+        "vf_lbl_destroy": (ci, [vp]),
+        "vf_lbl_select_init_method": (ci, [vp, C.c_char_p]),
+        "vf_lbl_run": (ci, [vp, ci, i64, ci, cd, ci, ci, ci, LBL_CALLBACK, vp]),
+        "vf_lbl_objective": (ci, [vp, C.POINTER(cd)]),
+        "vf_lbl_gradient": (ci, [vp, _dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = None  # filled lazily by exported_symbols()
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib().vf_last_error().decode()
+        if rc == 2:
+            raise VoxelFEMError(msg)  # std::logic_error in the reference
+        raise VoxelFEMError(msg)
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(lib().vf_device_count(C.byref(n)))
+    return n.value
+
+
+def parse_bc(path_or_dict, dmin, dmax):
+    """Parse a VoxelFEM/MeshFEM .bc JSON file into box regions in absolute coordinates
+    (rules of MeshFEM BoundaryConditions.cc:219-380 restricted to the `dirichlet[xyz]*` / `force`
+    box regions the voxel simulator accepts, TensorProductSimulator.hh:600-652)."""
+    cfg = path_or_dict
+    if not isinstance(cfg, dict):
+        with open(path_or_dict) as f:
+            cfg = json.load(f)
+    dmin = np.asarray(dmin, dtype=float)
+    dmax = np.asarray(dmax, dtype=float)
+    N = len(dmin)
+    kinds, masks, vals, los, his = [], [], [], [], []
+
+    def pad(v):
+        v = [float(x) for x in v][:3]
+        return v + [0.0] * (3 - len(v))
+
+    for reg in cfg["regions"]:
+        t = reg["type"]
+        cm = 7
+        if t.startswith("dirichlet"):
+            rest = t[9:]
+            comp = ""
+            for ch in rest:
+                if ch < "x" or ch > "z":
+                    break
+                comp += ch
+            if len(comp) > 3:
+                raise VoxelFEMError("invalid mask")
+            if comp:
+                cm = sum(1 << "xyz".index(c) for c in set(comp))
+            if rest[len(comp):] != "":
+                raise VoxelFEMError("Invalid type '%s'" % t)
+            kind = 0
+        elif t == "force":
+            kind = 1
+        else:
+            raise VoxelFEMError("Illegal constraint type, only \"dirichlet\" and \"force\" accepted")
+        if "box%" in reg:
+            lo = np.array(pad(reg["box%"]["minCorner"]))
+            hi = np.array(pad(reg["box%"]["maxCorner"]))
+            lo[:N] = dmin + lo[:N] * (dmax - dmin)
+            hi[:N] = dmin + hi[:N] * (dmax - dmin)
+        elif "box" in reg:
+            lo = np.array(pad(reg["box"]["minCorner"]))
+            hi = np.array(pad(reg["box"]["maxCorner"]))
+        else:
+            raise VoxelFEMError("only box / box% regions are supported")
+        kinds.append(kind)
+        masks.append(cm)
+        vals.append(pad(reg["value"]))
+        los.append(lo)
+        his.append(hi)
+    return (np.array(kinds, dtype=np.int32), np.array(masks, dtype=np.int32),
+            np.ascontiguousarray(vals, dtype=np.float64), np.ascontiguousarray(los, dtype=np.float64),
+            np.ascontiguousarray(his, dtype=np.float64))
+
+
+def to_soa(u):
+    """(numNodes, N) -> flat component-major VField storage."""
+    return np.ascontiguousarray(np.asarray(u, dtype=np.float64).T).ravel()
+
+
+def from_soa(flat, N):
+    return np.ascontiguousarray(flat.reshape(N, -1).T)
+
+
+class DeviceArray:
+    """A device-resident array of doubles (vf_dev_alloc)."""
+
+    def __init__(self, n):
+        self.L = lib()
+        p = C.c_void_p()
+        _check(self.L.vf_dev_alloc(int(n), C.byref(p)))
+        self.ptr, self.n = p, int(n)
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=np.float64).ravel()
+        assert host.size == self.n
+        _check(self.L.vf_dev_upload(self.ptr, host, self.n))
+
+    def download(self):
+        out = np.empty(self.n)
+        _check(self.L.vf_dev_download(out, self.ptr, self.n))
+        return out
+
+    def zero(self):
+        _check(self.L.vf_dev_memset_zero(self.ptr, self.n))
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.L.vf_dev_free(self.ptr)
+            self.ptr = None
+
+
+class Sim:
+    """TensorProductSimulator<double,1,1[,1]> device state (vf_sim)."""
+
+    def __init__(self, ne, dmin=None, dmax=None):
+        self.L = lib()
+        ne = np.ascontiguousarray(ne, dtype=np.int64)
+        self.N = len(ne)
+        if dmin is None:
+            dmin = np.zeros(self.N)
+            dmax = ne.astype(float)
+        self.ne = ne
+        self.dmin = np.ascontiguousarray(dmin, dtype=np.float64)
+        self.dmax = np.ascontiguousarray(dmax, dtype=np.float64)
+        h = C.c_void_p()
+        _check(self.L.vf_sim_create(self.N, ne, self.dmin, self.dmax, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.vf_sim_destroy(self.h)
+            self.h = None
+
+    @property
+    def num_nodes(self): return self.L.vf_sim_num_nodes(self.h)
+    @property
+    def num_elements(self): return self.L.vf_sim_num_elements(self.h)
+    @property
+    def nn(self): return self.ne + 1
+
+    def set_isotropic(self, E, nu): _check(self.L.vf_sim_set_isotropic(self.h, E, nu))
+    def set_elasticity_tensor(self, D): _check(self.L.vf_sim_set_elasticity_tensor(self.h, np.ascontiguousarray(D, dtype=np.float64)))
+
+    def K0(self):
+        ke = self.N * 2 ** self.N
+        out = np.zeros((ke, ke))
+        _check(self.L.vf_sim_get_K0(self.h, out))
+        return out
+
+    def set_interp(self, law=0, E0=1.0, Emin=1e-4, gamma=3.0, q=3.0): _check(self.L.vf_sim_set_interpolation(self.h, law, E0, Emin, gamma, q))
+
+    def set_gravity(self, g):
+        g = list(g) + [0.0] * (3 - len(g))
+        _check(self.L.vf_sim_set_gravity(self.h, np.ascontiguousarray(g, dtype=np.float64)))
+
+    def set_densities(self, rho): _check(self.L.vf_sim_set_densities(self.h, np.ascontiguousarray(rho, dtype=np.float64).ravel()))
+    def set_uniform_density(self, v): _check(self.L.vf_sim_set_uniform_density(self.h, v))
+
+    def densities(self):
+        out = np.zeros(self.num_elements); _check(self.L.vf_sim_get_densities(self.h, out)); return out
+
+    def E(self):
+        out = np.zeros(self.num_elements); _check(self.L.vf_sim_get_young_moduli(self.h, out)); return out
+
+    def apply_bc_file(self, path):
+        k, m, v, lo, hi = parse_bc(path, self.dmin, self.dmax)
+        _check(self.L.vf_sim_apply_bc_regions(self.h, len(k), k, m, v, lo, hi))
+
+    def add_dirichlet(self, u, lo, hi, cmask=7):
+        pad = lambda a: np.ascontiguousarray(list(a) + [0.0] * (3 - len(a)), dtype=np.float64)
+        _check(self.L.vf_sim_add_dirichlet_box(self.h, pad(u), pad(lo), pad(hi), cmask))
+
+    def apply_symmetry_conditions(self, axes_mask, max_face_mask=0): _check(self.L.vf_sim_apply_symmetry_conditions(self.h, axes_mask, max_face_mask))
+
+    def dirichlet_mask(self):
+        out = np.zeros(self.num_nodes, dtype=np.uint8); _check(self.L.vf_sim_get_dirichlet_mask(self.h, out)); return out
+
+    def build_load(self):
+        f = np.zeros(self.num_nodes * self.N); _check(self.L.vf_sim_build_load_vector(self.h, f)); return from_soa(f, self.N)
+
+    def apply_K(self, u, out=None, zero_init=True, negate=False):
+        o = np.zeros(self.num_nodes * self.N) if out is None else to_soa(out)
+        _check(self.L.vf_sim_apply_K(self.h, to_soa(u), o, int(zero_init), int(negate)))
+        return from_soa(o, self.N)
+
+    def set_mask_layer(self, l): _check(self.L.vf_sim_set_mask_layer(self.h, l))
+
+    def mask_info(self):
+        a, b, h = C.c_int64(), C.c_int64(), C.c_double()
+        _check(self.L.vf_sim_get_mask_info(self.h, C.byref(a), C.byref(b), C.byref(h)))
+        return a.value, b.value
+
+    def compliance_gradient(self, u, g=None):
+        out = np.zeros(self.num_elements) if g is None else np.ascontiguousarray(g, dtype=np.float64).copy()
+        _check(self.L.vf_sim_compliance_gradient(self.h, to_soa(u), out, int(g is not None)))
+        return out
+
+    def energy_density(self, u):
+        out = np.zeros(self.num_elements); _check(self.L.vf_sim_element_energy_density(self.h, to_soa(u), out)); return out
+
+    def solve(self, f):
+        u = np.zeros(self.num_nodes * self.N); _check(self.L.vf_sim_solve(self.h, to_soa(f), u)); return from_soa(u, self.N)
+
+
+class _LevelView:
+    def __init__(self, mg, l):
+        self.mg, self.l = mg, l
+
+    @property
+    def num_nodes(self): return self.mg.nn(self.l)
+
+    def dirichlet_mask(self):
+        out = np.zeros(self.num_nodes, dtype=np.uint8)
+        _check(self.mg.L.vf_mg_level_dirichlet_mask(self.mg.h, self.l, out))
+        return out
+
+
+class MG:
+    """MultigridSolver (vf_mg)."""
+
+    def __init__(self, sim, levels):
+        self.L = lib()
+        self.sim, self.N, self.levels = sim, sim.N, levels
+        h = C.c_void_p()
+        _check(self.L.vf_mg_create(sim.h, levels, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.vf_mg_destroy(self.h)
+            self.h = None
+
+    def get_sim(self, l): return _LevelView(self, l)
+    def nn(self, l): return self.L.vf_mg_level_num_nodes(self.h, l)
+
+    def coarsened_fine_K0(self, fi):
+        ke = self.N * 2 ** self.N
+        out = np.zeros((ke, ke)); _check(self.L.vf_mg_get_coarsened_fine_K0(self.h, fi, out)); return out
+
+    def update_stiffness(self): _check(self.L.vf_mg_update_stiffness_matrices(self.h))
+
+    def apply_K(self, l, u):
+        out = np.zeros(self.nn(l) * self.N); _check(self.L.vf_mg_apply_K(self.h, l, to_soa(u), out)); return from_soa(out, self.N)
+
+    def residual(self, l, u, b):
+        out = np.zeros(self.nn(l) * self.N); _check(self.L.vf_mg_compute_residual(self.h, l, to_soa(u), to_soa(b), out)); return from_soa(out, self.N)
+
+    def smooth(self, l, u, b, forward=True):
+        uu = to_soa(u); _check(self.L.vf_mg_smooth(self.h, l, uu, to_soa(b), int(forward))); return from_soa(uu, self.N)
+
+    def restrict(self, lf, fine):
+        out = np.zeros(self.nn(lf + 1) * self.N); _check(self.L.vf_mg_restrict(self.h, lf, to_soa(fine), out)); return from_soa(out, self.N)
+
+    def interpolate(self, lf, coarse, fine=None):
+        out = np.zeros(self.nn(lf) * self.N) if fine is None else to_soa(fine)
+        _check(self.L.vf_mg_interpolate(self.h, lf, to_soa(coarse), out, int(fine is not None)))
+        return from_soa(out, self.N)
+
+    def stencil(self, l):
+        ns = 3 ** self.N
+        out = np.zeros(self.nn(l) * ns * self.N * self.N)
+        _check(self.L.vf_mg_get_stencil(self.h, l, out))
+        return out.reshape(self.nn(l), ns, self.N, self.N)
+
+    def coarse_solve(self, f):
+        out = np.zeros(self.nn(self.levels) * self.N); _check(self.L.vf_mg_coarse_solve(self.h, to_soa(f), out)); return from_soa(out, self.N)
+
+    def solve(self, u, f, num_steps, num_smooth, stiffness_updated=False, zero_dirichlet=False, fmg=False):
+        out = np.zeros(self.nn(0) * self.N)
+        _check(self.L.vf_mg_solve(self.h, to_soa(u), to_soa(f), num_steps, num_smooth, int(stiffness_updated), int(zero_dirichlet), int(fmg), out))
+        return from_soa(out, self.N)
+
+    def pcg(self, u, b, max_iter, tol, mg_iterations=1, mg_smoothing=1, fmg=False, dirichlet_ok=False, callback=None):
+        x = to_soa(u)
+        it = C.c_int(0)
+        res = np.zeros(max(max_iter, 1) + 1)
+        cb = PCG_CALLBACK(lambda i, r, _u: callback(i, r)) if callback else PCG_CALLBACK()
+        _check(self.L.vf_mg_pcg(self.h, x, to_soa(b), max_iter, tol, mg_iterations, mg_smoothing, int(fmg), int(dirichlet_ok), C.byref(it), res, cb, None))
+        return from_soa(x, self.N), it.value, res[:it.value]
+
+    def pcg_dev(self, x_dev, b_dev, max_iter, tol, mg_iterations=1, mg_smoothing=1, fmg=False, dirichlet_ok=False):
+        it = C.c_int(0)
+        res = np.zeros(max(max_iter, 1) + 1)
+        _check(self.L.vf_mg_pcg_dev(self.h, x_dev.ptr, b_dev.ptr, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), int(dirichlet_ok), C.byref(it), res, PCG_CALLBACK(), None))
+        return it.value, res[:it.value]
+
+    def pcg_residual(self):
+        out = np.zeros(self.nn(0) * self.N); _check(self.L.vf_mg_get_pcg_residual(self.h, out)); return from_soa(out, self.N)
+
+    def set_symmetric_gs(self, s): _check(self.L.vf_mg_set_symmetric_gauss_seidel(self.h, int(s)))
+    def set_mask_layer(self, l): _check(self.L.vf_mg_set_mask_layer(self.h, l))
+    def decrement_mask(self, inc): _check(self.L.vf_mg_decrement_mask(self.h, inc))
+
+    def debug_get(self, which, l):
+        out = np.zeros(self.nn(l) * self.N)
+        _check(self.L.vf_mg_debug_get(self.h, {"x": 0, "b": 1, "r": 2}[which], l, out))
+        return from_soa(out, self.N)
+
+    def debug_multicolor_visit(self):
+        out = np.zeros(self.nn(0), dtype=np.int32); _check(self.L.vf_mg_debug_multicolor_visit(self.h, out)); return out
+
+    def stream(self): return self.L.vf_mg_stream(self.h)
+    def synchronize(self): _check(self.L.vf_mg_synchronize(self.h))
+
+    def prof_enable(self, on=True): _check(self.L.vf_prof_enable(self.h, int(on)))
+    def prof_reset(self): _check(self.L.vf_prof_reset(self.h))
+
+    def prof_report(self):
+        out = {}
+        for c in range(self.L.vf_prof_num_categories()):
+            n, ms, un = C.c_int64(), C.c_double(), C.c_double()
+            _check(self.L.vf_prof_get(self.h, c, C.byref(n), C.byref(ms), C.byref(un)))
+            if n.value:
+                out[self.L.vf_prof_name(c).decode()] = {"launches": n.value, "ms": ms.value, "units": un.value}
+        return out
+
+
+class Problem:
+    """TopologyOptimizationProblem + MultigridComplianceObjective + TotalVolumeConstraint + OCOptimizer (vf_top)."""
+
+    def __init__(self, mg, filters, vol_frac):
+        self.L = lib()
+        self.mg = mg
+        spec = []
+        for f in filters:
+            if f[0] == "smooth":
+                spec += [0, f[1], f[2], 0.0]
+            else:
+                spec += [1, 0, 0, f[1]]
+        spec = np.ascontiguousarray(spec if spec else [0.0], dtype=np.float64)
+        h = C.c_void_p()
+        _check(self.L.vf_top_create(mg.h, len(filters), spec, vol_frac, C.byref(h)))
+        self.h = h
+        self.ne = mg.sim.num_elements
+        self.N = mg.N
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.vf_top_destroy(self.h)
+            self.h = None
+
+    def set_solver(self, cg_iter=100, tol=1e-5, mg_it=1, mg_smooth=2, fmg=True, zero_init=False):
+        _check(self.L.vf_top_set_solver(self.h, cg_iter, tol, mg_it, mg_smooth, int(fmg), int(zero_init)))
+
+    def set_vars(self, x): _check(self.L.vf_top_set_vars(self.h, np.ascontiguousarray(x, dtype=np.float64)))
+
+    def design_vars(self):
+        o = np.zeros(self.ne); _check(self.L.vf_top_get_vars(self.h, 0, o)); return o
+
+    def physical_vars(self):
+        o = np.zeros(self.ne); _check(self.L.vf_top_get_vars(self.h, 1, o)); return o
+
+    def compliance(self):
+        v = C.c_double(); _check(self.L.vf_top_compliance(self.h, C.byref(v))); return v.value
+
+    def constraint(self):
+        v = C.c_double(); _check(self.L.vf_top_constraint(self.h, C.byref(v))); return v.value
+
+    def objective_gradient(self):
+        o = np.zeros(self.ne); _check(self.L.vf_top_objective_gradient(self.h, o)); return o
+
+    def constraint_jacobian(self):
+        o = np.zeros(self.ne); _check(self.L.vf_top_constraint_jacobian(self.h, o)); return o
+
+    def u(self):
+        o = np.zeros(self.mg.nn(0) * self.N); _check(self.L.vf_top_get_u(self.h, o)); return from_soa(o, self.N)
+
+    def last_pcg_iters(self): return self.L.vf_top_last_pcg_iterations(self.h)
+
+    def oc_step(self, m=0.2, p=0.5, ctol=1e-6):
+        n = C.c_int(0); _check(self.L.vf_top_oc_step(self.h, m, p, ctol, C.byref(n))); return n.value
+
+    def lambda_bracket(self):
+        a, b = C.c_double(), C.c_double(); _check(self.L.vf_top_get_lambda_bracket(self.h, C.byref(a), C.byref(b))); return a.value, b.value
+
+
+def smoothing_filter(x, shape, radius, ftype):
+    shape = np.ascontiguousarray(shape, dtype=np.int64)
+    out = np.zeros(int(np.prod(shape)))
+    _check(lib().vf_filter_smooth(len(shape), shape, radius, ftype, np.ascontiguousarray(x, dtype=np.float64).ravel(), out))
+    return out
+
+
+def projection_apply(x, beta):
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel(); out = np.zeros_like(x)
+    _check(lib().vf_filter_project(len(x), beta, x, out)); return out
+
+
+def projection_backprop(g, vars_, beta):
+    g = np.ascontiguousarray(g, dtype=np.float64).ravel(); out = np.zeros_like(g)
+    _check(lib().vf_filter_project_backprop(len(g), beta, g, np.ascontiguousarray(vars_, dtype=np.float64).ravel(), out)); return out

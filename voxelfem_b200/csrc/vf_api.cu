@@ -1,0 +1,1275 @@
+// vf_api.cu -- host side of libvoxelfem_b200: the C ABI of include/voxelfem_b200.h.
+//
+// Owns all device state (densities, moduli, per-level fields and stencils, the dense coarse
+// inverse) and drives the kernels of vf_l0.cu / vf_stencil.cu / vf_vec.cu / vf_top.cu on one CUDA
+// stream per simulator.  Control flow follows MultigridSolver.hh (vcycle :617-658, fullMultigrid
+// :587-609, solve :546-573, preconditionedConjugateGradient :1047-1152) and
+// TensorProductSimulator.hh; each function cites the lines it restates.
+#include "vf_internal.cuh"
+#include "../../include/voxelfem_b200.h"
+
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <vector>
+
+namespace vf {
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------
+// Profiler: CUDA-event pairs around each launch, resolved lazily
+// ---------------------------------------------------------------------------
+struct Profiler {
+    bool enabled = false;
+    struct Pending { int cat; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+    long long launches[PC_COUNT] = {0};
+    double ms[PC_COUNT] = {0}, units[PC_COUNT] = {0};
+    cudaEvent_t curStart = nullptr;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; VF_CUDA(cudaEventCreate(&e)); return e;
+    }
+    void resolve() {
+        for (auto &p : pending) {
+            cudaEventSynchronize(p.b);
+            float t = 0; cudaEventElapsedTime(&t, p.a, p.b);
+            ms[p.cat] += t; pool.push_back(p.a); pool.push_back(p.b);
+        }
+        pending.clear();
+    }
+    void reset() { resolve(); for (int i = 0; i < PC_COUNT; ++i) { launches[i] = 0; ms[i] = 0; units[i] = 0; } }
+    ~Profiler() { for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); } for (auto e : pool) cudaEventDestroy(e); }
+};
+void prof_begin(const LaunchCtx &ctx, int cat, double units) {
+    Profiler *p = ctx.prof;
+    if (!p || !p->enabled) return;
+    p->curStart = p->get();
+    cudaEventRecord(p->curStart, ctx.stream);
+    p->launches[cat]++; p->units[cat] += units;
+}
+void prof_end(const LaunchCtx &ctx, int cat) {
+    Profiler *p = ctx.prof;
+    if (!p || !p->enabled || !p->curStart) return;
+    cudaEvent_t b = p->get();
+    cudaEventRecord(b, ctx.stream);
+    p->pending.push_back({cat, p->curStart, b});
+    p->curStart = nullptr;
+    if (p->pending.size() > 8192) p->resolve();
+}
+static const char *kProfNames[PC_COUNT] = {"apply_l0", "residual_l0", "gs_l0", "apply_stencil", "residual_stencil", "gs_stencil",
+                                           "restrict", "prolong", "coarse_solve", "vector_ops", "coarsen", "topopt", "other"};
+
+// ---------------------------------------------------------------------------
+// Small RAII device buffer
+// ---------------------------------------------------------------------------
+template<class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete; DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count, bool zero = true) {
+        if (count == n && p) { if (zero) VF_CUDA(cudaMemset(p, 0, n * sizeof(T))); return; }
+        release();
+        if (count == 0) return;
+        VF_CUDA(cudaMalloc(&p, count * sizeof(T))); n = count;
+        if (zero) VF_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    }
+    void upload(const T *h, size_t count, cudaStream_t s) { VF_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }
+    void download(T *h, size_t count, cudaStream_t s) const { VF_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s)); VF_CUDA(cudaStreamSynchronize(s)); }
+};
+
+static void ensure_device() {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) throw std::runtime_error("voxelfem_b200: no usable CUDA device (this library has no CPU fallback)");
+}
+
+static GridDesc make_grid(int N, const int64_t *ne) {
+    GridDesc g; std::memset(&g, 0, sizeof(g));
+    g.N = N;
+    if (N == 3) { for (int d = 0; d < 3; ++d) { g.ne[d] = (int)ne[d]; g.nn[d] = (int)ne[d] + 1; } g.bd = 1; }
+    else { g.ne[0] = 1; g.nn[0] = 1; g.ne[1] = (int)ne[0]; g.nn[1] = (int)ne[0] + 1; g.ne[2] = (int)ne[1]; g.nn[2] = (int)ne[1] + 1; g.bd = 2; }
+    g.ns[2] = 1; g.ns[1] = g.nn[2]; g.ns[0] = (long long)g.nn[1] * g.nn[2];
+    g.es[2] = 1; g.es[1] = g.ne[2]; g.es[0] = (long long)g.ne[1] * g.ne[2];
+    g.numNodes = (long long)g.nn[0] * g.nn[1] * g.nn[2];
+    g.numElems = (long long)g.ne[0] * g.ne[1] * g.ne[2];
+    g.nActive = g.nn[g.bd]; g.neActive = g.ne[g.bd];
+    return g;
+}
+static void set_mask_limits(GridDesc &g, int firstMasked, int firstDetached) {
+    g.nActive = std::min<long long>(firstDetached, g.nn[g.bd]);
+    g.neActive = std::min<long long>(firstMasked, g.ne[g.bd]);
+}
+
+// ---------------------------------------------------------------------------
+// Dense SPD solver on the GPU (stands in for CHOLMOD): A^-1 via cuSOLVER potrf + potri, applied as a
+// bandwidth-bound symmetric mat-vec so that the coarse solve on the V-cycle's critical path is one kernel.
+// ---------------------------------------------------------------------------
+struct DenseSolver {
+    cusolverDnHandle_t handle = nullptr;
+    DevBuf<double> A, work, rhs, y; DevBuf<int> info, red, freeDofs;
+    int nfree = 0; bool ok = false;
+    ~DenseSolver() { if (handle) cusolverDnDestroy(handle); }
+    void init_handle(cudaStream_t s) {
+        if (!handle) {
+            if (cusolverDnCreate(&handle) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("cusolverDnCreate failed");
+        }
+        cusolverDnSetStream(handle, s);
+    }
+    // fixed: per-DOF flags in (node*N + c) order
+    void factor(const LaunchCtx &ctx, const GridDesc &g, const double *S, const std::vector<uint8_t> &fixed) {
+        init_handle(ctx.stream);
+        const long long ndof = g.numNodes * g.N;
+        std::vector<int> redH(ndof, -1), freeH;
+        for (long long i = 0; i < ndof; ++i) if (!fixed[i]) { redH[i] = (int)freeH.size(); freeH.push_back((int)i); }
+        nfree = (int)freeH.size();
+        red.alloc(ndof, false); red.upload(redH.data(), ndof, ctx.stream);
+        freeDofs.alloc(std::max(nfree, 1), false); if (nfree) freeDofs.upload(freeH.data(), nfree, ctx.stream);
+        VF_CUDA(cudaStreamSynchronize(ctx.stream)); // redH / freeH are stack-owned
+        if (nfree == 0) { ok = true; return; }
+        A.alloc((size_t)nfree * nfree, true);
+        rhs.alloc(nfree, true); y.alloc(nfree, true); info.alloc(1, true);
+        launch_stencil_to_dense(ctx, g, S, red.p, nfree, A.p);
+        int lwork1 = 0, lwork2 = 0;
+        // Row-major symmetric == column-major symmetric; factor the "lower" triangle in cuSOLVER's column-major view.
+        if (cusolverDnDpotrf_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, &lwork1) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf_bufferSize failed");
+        if (cusolverDnDpotri_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, &lwork2) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potri_bufferSize failed");
+        const int lwork = std::max(lwork1, lwork2);
+        if ((size_t)lwork > work.n) work.alloc(lwork, false);
+        count_launch();
+        if (cusolverDnDpotrf(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, work.p, lwork, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf failed");
+        int hinfo = 0; info.download(&hinfo, 1, ctx.stream);
+        if (hinfo != 0) throw std::runtime_error("Cholesky factorization failed: coarse stiffness matrix is not positive definite (info = " + std::to_string(hinfo) + ")");
+        count_launch();
+        if (cusolverDnDpotri(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, work.p, lwork, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potri failed");
+        info.download(&hinfo, 1, ctx.stream);
+        if (hinfo != 0) throw std::runtime_error("potri failed (info = " + std::to_string(hinfo) + ")");
+        // column-major lower triangle == row-major upper triangle: mirror it so that rows are complete
+        launch_symmetrize_lower_from_colmajor(ctx);
+        ok = true;
+    }
+    void launch_symmetrize_lower_from_colmajor(const LaunchCtx &ctx) {
+        // In row-major terms cuSOLVER wrote entries A[j][i] for i >= j (i.e. the upper triangle, row j col i).
+        // launch_symmetrize_lower copies lower -> upper, so transpose roles by treating the buffer as column-major:
+        // element (i, j) column-major is at A[j * n + i]; "lower" there is what launch_symmetrize_lower calls "upper"
+        // of the transposed view.  Copy valid part onto the other half:
+        launch_symmetrize_upper_to_lower(ctx);
+    }
+    void launch_symmetrize_upper_to_lower(const LaunchCtx &ctx);
+    // x = A^-1 f on free DOFs, zero on fixed DOFs (TensorProductSimulator.hh:1227-1229, 1243-1252)
+    void solve(const LaunchCtx &ctx, const GridDesc &g, const double *f, double *x) {
+        VF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * g.numNodes * g.N, ctx.stream));
+        if (nfree == 0) return;
+        launch_gather_free(ctx, f, freeDofs.p, nfree, g.numNodes, g.N, rhs.p);
+        launch_dense_symv(ctx, A.p, nfree, rhs.p, y.p);
+        launch_scatter_free(ctx, y.p, freeDofs.p, nfree, g.numNodes, g.N, x);
+    }
+};
+
+} // namespace vf
+
+// kernels local to this file ----------------------------------------------------------------
+__global__ void k_sym_upper_to_lower(double *A, int n) { // row-major: copy A[i][j] (j > i) into A[j][i]
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i < n && j < n && j > i) A[(size_t)j * n + i] = A[(size_t)i * n + j];
+}
+namespace vf {
+void DenseSolver::launch_symmetrize_upper_to_lower(const LaunchCtx &ctx) {
+    // cuSOLVER (column-major, FILL_MODE_LOWER) holds element (r, c), r >= c, at A[c * n + r]; in our row-major reading
+    // that is row c, column r >= c: the upper triangle.  Mirror it into the lower triangle.
+    ProfScope ps(ctx, PC_COARSEN, (double)nfree * nfree);
+    dim3 block(32, 8), grid((nfree + 31) / 32, (nfree + 7) / 8);
+    k_sym_upper_to_lower<<<grid, block, 0, ctx.stream>>>(A.p, nfree);
+    VF_KERNEL_CHECK();
+}
+} // namespace vf
+
+using namespace vf;
+
+// ---------------------------------------------------------------------------
+// vf_sim
+// ---------------------------------------------------------------------------
+struct vf_sim {
+    int N = 3;
+    int64_t ne[3] = {1, 1, 1}, nn[3] = {1, 1, 1};
+    double dmin[3] = {0, 0, 0}, dmax[3] = {1, 1, 1}, stretch[3] = {1, 1, 1}, spacing[3] = {1, 1, 1};
+    GridDesc g;
+    double D[6][6];
+    std::vector<double> K0; K0Param K0p; DevBuf<double> K0dev;
+    int law = VF_LAW_SIMP; double E0 = 1, Emin = 1e-4, gamma = 3, q = 3;
+    double gravity[3] = {0, 0, 0};
+    std::vector<int64_t> dirNodes; std::vector<uint8_t> dirMask; std::vector<double> dirVals; std::vector<uint8_t> nodeMask;
+    std::vector<int64_t> forceNodes; std::vector<double> forceVals;
+    DevBuf<double> rho, E, dirValsDev, scratch, scalars, tmpU, tmpV;
+    DevBuf<uint8_t> dmaskDev, dirMaskDev; DevBuf<long long> dirNodesDev;
+    double maskHeight = std::numeric_limits<double>::infinity();
+    int firstMasked = INT_MAX, firstDetached = INT_MAX;
+    cudaStream_t stream = nullptr; LaunchCtx ctx; Profiler prof;
+    uint64_t version = 1; // bumped whenever E, the mask, K0 or the Dirichlet set changes
+    DenseSolver direct; uint64_t directVersion = 0; DevBuf<double> directStencil;
+
+    long long numNodes() const { return g.numNodes; }
+    long long numElems() const { return g.numElems; }
+    double elemVolume() const { double v = 1; for (int d = 0; d < N; ++d) v *= stretch[d]; return v; }
+    bool maskActive() const { return maskHeight < dmax[1]; }
+    void touch() { ++version; }
+
+    int symIdx(int i, int j) const { if (i == j) return i; if (N == 2) return 2; return 6 - i - j; }
+    // Element_T::Stiffness (:67-80) with Strains::getStrains (TensorProductPolynomialInterpolant.hh:204-231) and the
+    // 2-point Gauss rule on [0,1] (TensorProductQuadrature.hh:134-143); m_updateK0 (:2078-2086)
+    void updateK0() {
+        const int npe = 1 << N, ke = N * npe, fl = (N == 3) ? 6 : 3, nq = 1 << N;
+        K0.assign((size_t)ke * ke, 0.0);
+        const double gp[2] = {0.5 - 0.5 / std::sqrt(3.0), 0.5 + 0.5 / std::sqrt(3.0)};
+        std::vector<double> strain((size_t)ke * fl);
+        for (int qi = 0; qi < nq; ++qi) {
+            double xi[3] = {0, 0, 0};
+            for (int d = 0; d < N; ++d) xi[d] = gp[(qi >> (N - 1 - d)) & 1];
+            const double w = 1.0 / nq;
+            for (int j = 0; j < npe; ++j) {
+                double gr[3] = {0, 0, 0};
+                for (int c = 0; c < N; ++c) {
+                    double v = 1;
+                    for (int d = 0; d < N; ++d) {
+                        const int bit = (j >> (N - 1 - d)) & 1;
+                        v *= (d == c) ? ((bit ? 1.0 : -1.0) / stretch[d]) : (bit ? xi[d] : 1.0 - xi[d]);
+                    }
+                    gr[c] = v;
+                }
+                for (int c = 0; c < N; ++c) {
+                    double *s = &strain[(size_t)(j * N + c) * fl];
+                    for (int t = 0; t < fl; ++t) s[t] = 0;
+                    for (int i = 0; i < N; ++i) s[symIdx(c, i)] = 0.5 * gr[i];
+                    s[symIdx(c, c)] = gr[c];
+                }
+            }
+            for (int a = 0; a < ke; ++a) for (int b = a; b < ke; ++b) {
+                const double *sa = &strain[(size_t)a * fl], *sb = &strain[(size_t)b * fl];
+                double acc = 0;
+                for (int i = 0; i < fl; ++i) {
+                    double sig = 0;
+                    for (int j = 0; j < fl; ++j) sig += D[i][j] * (j >= N ? 2.0 : 1.0) * sb[j]; // doubleContract with shear doubling
+                    acc += (i >= N ? 2.0 : 1.0) * sa[i] * sig;
+                }
+                K0[(size_t)a * ke + b] += w * acc;
+            }
+        }
+        const double vol = elemVolume();
+        for (int a = 0; a < ke; ++a) for (int b = a; b < ke; ++b) { K0[(size_t)a * ke + b] *= vol; K0[(size_t)b * ke + a] = K0[(size_t)a * ke + b]; }
+        std::memset(&K0p, 0, sizeof(K0p));
+        std::copy(K0.begin(), K0.end(), K0p.v);
+        K0dev.alloc(K0.size(), false); K0dev.upload(K0.data(), K0.size(), stream);
+        VF_CUDA(cudaStreamSynchronize(stream));
+        touch();
+    }
+    void setIsotropic(double Ey, double nu) {
+        double lambda = (nu * Ey) / ((1.0 + nu) * (1.0 - 2.0 * nu));
+        const double mu = Ey / (2.0 + 2.0 * nu);
+        if (N == 2) lambda = (nu * Ey) / (1.0 - nu * nu);
+        std::memset(D, 0, sizeof(D));
+        if (N == 3) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) D[i][j] = lambda; for (int i = 0; i < 3; ++i) D[i][i] = lambda + 2 * mu; D[3][3] = D[4][4] = D[5][5] = mu; }
+        else { D[0][0] = D[1][1] = lambda + 2 * mu; D[0][1] = D[1][0] = lambda; D[2][2] = mu; }
+        updateK0();
+    }
+    void refreshGridMask() { set_mask_limits(g, firstMasked, firstDetached); }
+    void updateModuli() { // m_updateYoungModuli (:2088-2102)
+        launch_update_moduli(ctx, g, rho.p, E.p, law, E0, Emin, gamma, q, maskActive());
+        touch();
+    }
+    void uploadBCs() {
+        dmaskDev.alloc(g.numNodes, false); dmaskDev.upload(nodeMask.data(), g.numNodes, stream);
+        const size_t nd = dirNodes.size();
+        dirNodesDev.alloc(std::max<size_t>(nd, 1), false); dirMaskDev.alloc(std::max<size_t>(nd, 1), false); dirValsDev.alloc(std::max<size_t>(nd * N, 1), false);
+        if (nd) {
+            std::vector<long long> tmp(dirNodes.begin(), dirNodes.end());
+            dirNodesDev.upload(tmp.data(), nd, stream); dirMaskDev.upload(dirMask.data(), nd, stream); dirValsDev.upload(dirVals.data(), nd * N, stream);
+            VF_CUDA(cudaStreamSynchronize(stream));
+        }
+        VF_CUDA(cudaStreamSynchronize(stream));
+        touch();
+    }
+    // node index ranges per axis covered by an inclusive box (Geometry.hh:276-279 applied to nodePosition, :349-351)
+    bool boxRanges(const double *lo, const double *hi, std::vector<int64_t> (&idx)[3]) const {
+        for (int d = 0; d < N; ++d) {
+            idx[d].clear();
+            for (int64_t i = 0; i < nn[d]; ++i) { const double p = dmin[d] + double(i) * spacing[d]; if (p >= lo[d] && p <= hi[d]) idx[d].push_back(i); }
+            if (idx[d].empty()) return false;
+        }
+        for (int d = N; d < 3; ++d) idx[d].assign(1, 0);
+        return true;
+    }
+    int64_t flatNode(int64_t i, int64_t j, int64_t k) const { return N == 3 ? (i * nn[1] + j) * nn[2] + k : i * nn[1] + j; }
+};
+
+// BCBuilder (TensorProductSimulator.hh:464-566): dense staging of the sparse BC lists
+struct BCBuilder {
+    vf_sim &s; std::vector<double> forces, dvals; std::vector<uint8_t> dmask;
+    explicit BCBuilder(vf_sim &s_) : s(s_), forces((size_t)s_.g.numNodes * s_.N, 0.0), dvals((size_t)s_.g.numNodes * s_.N, 0.0), dmask(s_.g.numNodes, 0) {
+        for (size_t f = 0; f < s.forceNodes.size(); ++f) for (int c = 0; c < s.N; ++c) forces[s.forceNodes[f] * s.N + c] = s.forceVals[f * s.N + c];
+        for (size_t k = 0; k < s.dirNodes.size(); ++k) { for (int c = 0; c < s.N; ++c) dvals[s.dirNodes[k] * s.N + c] = s.dirVals[k * s.N + c]; dmask[s.dirNodes[k]] = s.dirMask[k]; }
+    }
+    void setDirichlet(int64_t ni, const double *val, unsigned cm) {
+        for (int c = 0; c < s.N; ++c) {
+            if (!((cm >> c) & 1u)) continue;
+            if (!((dmask[ni] >> c) & 1u)) { dmask[ni] |= uint8_t(1u << c); dvals[ni * s.N + c] = val[c]; }
+            else if (std::abs(dvals[ni * s.N + c] - val[c]) > 1e-10) throw std::runtime_error("Conflicting dirichlet displacements.");
+        }
+    }
+    void setDirichletComponent(int64_t ni, int d, double v) { dmask[ni] |= uint8_t(1u << d); dvals[ni * s.N + d] = v; }
+    void setForce(int64_t ni, const double *f) { for (int c = 0; c < s.N; ++c) forces[ni * s.N + c] = f[c]; }
+    void apply() {
+        s.dirNodes.clear(); s.dirMask.clear(); s.dirVals.clear();
+        const uint8_t full = uint8_t((1u << s.N) - 1u);
+        s.nodeMask.assign(s.g.numNodes, 0);
+        for (int64_t ni = 0; ni < s.g.numNodes; ++ni) {
+            const uint8_t m = dmask[ni] & full;
+            if (m) { s.dirNodes.push_back(ni); s.dirMask.push_back(m); for (int c = 0; c < s.N; ++c) s.dirVals.push_back(dvals[ni * s.N + c]); s.nodeMask[ni] = m; }
+        }
+        s.forceNodes.clear(); s.forceVals.clear();
+        for (int64_t ni = 0; ni < s.g.numNodes; ++ni) {
+            double sq = 0; for (int c = 0; c < s.N; ++c) sq += forces[ni * s.N + c] * forces[ni * s.N + c];
+            if (sq != 0.0) { s.forceNodes.push_back(ni); for (int c = 0; c < s.N; ++c) s.forceVals.push_back(forces[ni * s.N + c]); }
+        }
+        s.uploadBCs();
+    }
+};
+
+// ---------------------------------------------------------------------------
+// vf_mg
+// ---------------------------------------------------------------------------
+struct MGLevel {
+    GridDesc g; int64_t ne[3]; double stretchBD = 1;
+    std::vector<uint8_t> nodeMask; DevBuf<uint8_t> dmask;
+    DevBuf<double> x, b, r, S;
+    int firstMasked = INT_MAX, firstDetached = INT_MAX;
+};
+struct vf_mg {
+    vf_sim *sim = nullptr; int N = 3;
+    std::vector<std::unique_ptr<MGLevel>> lv;
+    std::vector<double> cK0; DevBuf<double> cK0dev; // [fi][KE][KE]
+    bool symmetricGS = true;
+    DenseSolver coarse;
+    uint64_t stiffnessVersion = 0; // sim->version the coarse operators were built for
+    DevBuf<double> Ad, d, scalars, scratch, tmpA, tmpB, tmpC;
+    double *hostScalars = nullptr; // pinned
+    std::vector<double> lastResiduals; int lastIters = 0;
+    LaunchCtx ctx;
+    ~vf_mg() { if (hostScalars) cudaFreeHost(hostScalars); }
+    int numLevels() const { return (int)lv.size(); }
+    const uint8_t *dmask(int l) const { return l == 0 ? sim->dmaskDev.p : lv[l]->dmask.p; }
+    const GridDesc &grid(int l) const { return l == 0 ? sim->g : lv[l]->g; }
+};
+
+namespace {
+
+enum Scalar { SC_RMR_A = 0, SC_RMR_B, SC_DAD, SC_RSQ, SC_BSQ, SC_TMP, SC_COUNT = 8 };
+
+void mg_sync_level_masks(vf_mg &mg) {
+    // coarse simulators share the physical mask height (MultigridSolver.hh:1022-1036)
+    for (int l = 1; l < mg.numLevels(); ++l) {
+        MGLevel &L = *mg.lv[l];
+        if (std::isinf(mg.sim->maskHeight)) { L.firstMasked = INT_MAX; L.firstDetached = INT_MAX; }
+        else { L.firstMasked = (int)std::ceil(mg.sim->maskHeight / L.stretchBD - 1e-10); L.firstDetached = L.firstMasked + 1; } // TensorProductSimulator.hh:297-301
+        set_mask_limits(L.g, L.firstMasked, L.firstDetached);
+    }
+}
+
+// updateStiffnessMatrices (MultigridSolver.hh:846-905): rebuild all coarse operators for the current moduli/mask.
+// The reference's banded partial update (:907-1017) yields the same operators; here the (cheap) full rebuild is
+// always used and is skipped only when nothing changed since the last build.
+void mg_update_stiffness(vf_mg &mg, bool force = false) {
+    mg_sync_level_masks(mg);
+    if (!force && mg.stiffnessVersion == mg.sim->version) return;
+    const int nl = mg.numLevels();
+    for (int l = 1; l < nl; ++l) {
+        MGLevel &L = *mg.lv[l];
+        const size_t len = (size_t)L.g.numNodes * (mg.N == 3 ? 27 : 9) * mg.N * mg.N;
+        if (L.S.n != len) L.S.alloc(len, false);
+        if (l == 1) launch_coarsen_from_moduli(mg.ctx, L.g, mg.sim->g, mg.sim->E.p, mg.cK0dev.p, L.S.p);
+        else        launch_coarsen_stencil(mg.ctx, L.g, mg.lv[l - 1]->g, mg.lv[l - 1]->S.p, L.S.p);
+    }
+    if (nl > 1) {
+        MGLevel &C = *mg.lv[nl - 1];
+        // findFixedVars (TensorProductSimulator.hh:1181-1195): Dirichlet components and detached nodes
+        std::vector<uint8_t> fixed((size_t)C.g.numNodes * mg.N, 0);
+        for (long long n = 0; n < C.g.numNodes; ++n) {
+            const int cbd = (C.g.bd == 2) ? (int)(n % C.g.nn[2]) : (int)((n / C.g.nn[2]) % C.g.nn[1]);
+            const bool det = cbd >= C.g.nActive;
+            for (int c = 0; c < mg.N; ++c) if (det || ((C.nodeMask[n] >> c) & 1)) fixed[n * mg.N + c] = 1;
+        }
+        mg.coarse.factor(mg.ctx, C.g, C.S.p, fixed);
+    }
+    mg.stiffnessVersion = mg.sim->version;
+}
+
+void mg_apply_K(vf_mg &mg, int l, const double *u, const double *b, double *out, int mode, bool zeroDirichlet, double *dotOut = nullptr) {
+    if (l == 0) launch_apply_l0(mg.ctx, mg.sim->g, mg.sim->K0p, u, mg.sim->E.p, b, zeroDirichlet ? mg.dmask(0) : nullptr, out, mode, dotOut, mg.scratch.p);
+    else {
+        mg_update_stiffness(mg);
+        launch_apply_stencil(mg.ctx, mg.lv[l]->g, mg.lv[l]->S.p, u, b, zeroDirichlet ? mg.dmask(l) : nullptr, out, mode);
+    }
+}
+// computeResidual (:527-541): r = b - K u on non-detached nodes, Dirichlet components zeroed
+void mg_residual(vf_mg &mg, int l, const double *u, const double *b, double *r) { mg_apply_K(mg, l, u, b, r, APPLY_RESIDUAL, true); }
+
+// smoothingMulticoloredGS (:452-458): 2^N colour passes, colours reversed for backward sweeps (:417)
+void mg_smooth(vf_mg &mg, int l, double *u, const double *b, bool forward) {
+    const int nc = 1 << mg.N;
+    if (l > 0) mg_update_stiffness(mg);
+    for (int i = 0; i < nc; ++i) {
+        const int color = forward ? i : (nc - 1 - i);
+        if (l == 0) launch_gs_l0(mg.ctx, mg.sim->g, mg.sim->K0p, u, b, mg.sim->E.p, mg.dmask(0), color, forward);
+        else        launch_gs_stencil(mg.ctx, mg.lv[l]->g, mg.lv[l]->S.p, u, b, mg.dmask(l), color, forward);
+    }
+}
+void mg_coarse_solve(vf_mg &mg, const double *f, double *x) {
+    mg_update_stiffness(mg);
+    mg.coarse.solve(mg.ctx, mg.grid(mg.numLevels() - 1), f, x);
+}
+void mg_enforce_dirichlet(vf_mg &mg, int l, double *u, bool zero) { // (:521-524)
+    if (zero || l > 0) launch_zero_dirichlet(mg.ctx, mg.grid(l), mg.dmask(l), u);
+    else launch_enforce_dirichlet(mg.ctx, mg.sim->g.numNodes, mg.N, (int)mg.sim->dirNodes.size(), mg.sim->dirNodesDev.p, mg.sim->dirMaskDev.p, mg.sim->dirValsDev.p, u);
+}
+double *lx(vf_mg &mg, int l) { return mg.lv[l]->x.p; }
+double *lb(vf_mg &mg, int l) { return mg.lv[l]->b.p; }
+double *lr(vf_mg &mg, int l) { return mg.lv[l]->r.p; }
+
+// vcycle (:617-658)
+void mg_vcycle(vf_mg &mg, int l, int nsmooth, bool residualSystem) {
+    const int coarsest = mg.numLevels() - 1;
+    if (l == coarsest) { mg_coarse_solve(mg, lb(mg, l), lx(mg, l)); return; }
+    mg_enforce_dirichlet(mg, l, lx(mg, l), residualSystem);
+    for (int i = 0; i < nsmooth; ++i) mg_smooth(mg, l, lx(mg, l), lb(mg, l), true);
+    mg_residual(mg, l, lx(mg, l), lb(mg, l), lr(mg, l));
+    launch_restrict(mg.ctx, mg.grid(l), mg.grid(l + 1), lr(mg, l), lb(mg, l + 1));
+    launch_masked_zero(mg.ctx, mg.grid(l + 1), lx(mg, l + 1), 4 /* VOXELFEM_SIMD_WIDTH margin (:644) */);
+    mg_vcycle(mg, l + 1, nsmooth, true);
+    launch_prolong(mg.ctx, mg.grid(l), mg.grid(l + 1), lx(mg, l + 1), lx(mg, l), true);
+    for (int i = 0; i < nsmooth; ++i) mg_smooth(mg, l, lx(mg, l), lb(mg, l), !mg.symmetricGS);
+}
+// fullMultigrid (:587-609)
+void mg_fmg(vf_mg &mg, int l, int nsmooth, bool residualSystem) {
+    const int coarsest = mg.numLevels() - 1;
+    if (l == coarsest) { mg_coarse_solve(mg, lb(mg, l), lx(mg, l)); return; }
+    launch_restrict(mg.ctx, mg.grid(l), mg.grid(l + 1), lb(mg, l), lb(mg, l + 1));
+    mg_fmg(mg, l + 1, nsmooth, residualSystem);
+    launch_prolong(mg.ctx, mg.grid(l), mg.grid(l + 1), lx(mg, l + 1), lx(mg, l), false);
+    mg_vcycle(mg, l, nsmooth, residualSystem);
+}
+// solve (:546-573) operating on lv[0].x (initial guess already there) and lv[0].b
+void mg_solve_inplace(vf_mg &mg, int numSteps, int nsmooth, bool zeroDirichlet, bool fmg) {
+    if (numSteps == 0) return;
+    int start = 0;
+    if (fmg) { mg_fmg(mg, 0, nsmooth, zeroDirichlet); start = 1; }
+    for (int i = start; i < numSteps; ++i) mg_vcycle(mg, 0, nsmooth, zeroDirichlet);
+}
+
+double read_scalar(vf_mg &mg, int slot) {
+    VF_CUDA(cudaMemcpyAsync(mg.hostScalars + slot, mg.scalars.p + slot, sizeof(double), cudaMemcpyDeviceToHost, mg.ctx.stream));
+    VF_CUDA(cudaStreamSynchronize(mg.ctx.stream));
+    return mg.hostScalars[slot];
+}
+
+void sim_direct_solve(vf_sim &s, const double *fDev, double *xDev); // below
+
+// preconditionedConjugateGradient (:1047-1152), device-resident x and b
+void mg_pcg(vf_mg &mg, double *x, const double *b, int maxIter, double tol, int mgIterations, int mgSmoothing, bool fmg, bool dirichletOK,
+            vf_pcg_callback cb, void *user) {
+    vf_sim &sim = *mg.sim; const GridDesc &g = sim.g;
+    mg.lastResiduals.clear(); mg.lastIters = 0;
+    mg_sync_level_masks(mg);
+    double *r = lb(mg, 0), *s = lx(mg, 0);
+    double *sc = mg.scalars.p;
+    if (mg.numLevels() == 1) { // (:1057-1065)
+        mg_residual(mg, 0, x, b, r);
+        launch_dot_plain(mg.ctx, g.numNodes * mg.N, r, r, sc + SC_RSQ, mg.scratch.p);
+        launch_dot_plain(mg.ctx, g.numNodes * mg.N, b, b, sc + SC_BSQ, mg.scratch.p);
+        const double rs = read_scalar(mg, SC_RSQ), bs = read_scalar(mg, SC_BSQ);
+        if (rs < tol * tol * bs) return;
+        sim_direct_solve(sim, b, x);
+        mg_residual(mg, 0, x, b, r);
+        launch_dot_plain(mg.ctx, g.numNodes * mg.N, r, r, sc + SC_RSQ, mg.scratch.p);
+        const double rn = std::sqrt(read_scalar(mg, SC_RSQ));
+        mg.lastIters = 1; mg.lastResiduals.push_back(rn);
+        if (cb) cb(1, rn, user);
+        return;
+    }
+    if (!dirichletOK) mg_enforce_dirichlet(mg, 0, x, false);
+    launch_masked_dot(mg.ctx, g, b, b, sc + SC_BSQ, mg.scratch.p);
+    mg_residual(mg, 0, x, b, r);
+    launch_masked_dot(mg.ctx, g, r, r, sc + SC_RSQ, mg.scratch.p);
+    const double bsq = read_scalar(mg, SC_BSQ);
+    double rsq = read_scalar(mg, SC_RSQ);
+    if (std::isnan(rsq)) throw std::logic_error("NaN encountered");
+    int i = 0; bool first = true; int cur = SC_RMR_A, old = SC_RMR_B;
+    while ((i++ < maxIter) && (rsq > tol * tol * bsq)) {
+        if (mgIterations > 0 && mgSmoothing > 0) {
+            mg_update_stiffness(mg); // lazily, first iteration (:1104-1107)
+            VF_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * g.numNodes * mg.N, mg.ctx.stream)); // applyPreconditionerInv: zero initial guess (:577-580)
+            mg_solve_inplace(mg, mgIterations, mgSmoothing, true, fmg);
+        } else {
+            VF_CUDA(cudaMemcpyAsync(s, r, sizeof(double) * g.numNodes * mg.N, cudaMemcpyDeviceToDevice, mg.ctx.stream)); // s = r (:578, :1118)
+        }
+        launch_zero_dirichlet(mg.ctx, g, mg.dmask(0), s);                                 // (:1122)
+        std::swap(cur, old);
+        launch_masked_dot(mg.ctx, g, r, s, sc + cur, mg.scratch.p);                      // r_Minv_r (:1124)
+        launch_cg_direction(mg.ctx, g, s, mg.d.p, sc + cur, sc + old, first);           // d = s + beta d (:1125-1126)
+        first = false;
+        mg_apply_K(mg, 0, mg.d.p, nullptr, mg.Ad.p, APPLY_SET, true, sc + SC_DAD);      // Ad = K d, zero Dirichlet, d.Ad (:1129-1134)
+        launch_cg_update(mg.ctx, g, x, mg.d.p, r, mg.Ad.p, sc + cur, sc + SC_DAD, sc + SC_RSQ, mg.scratch.p); // (:1134-1143)
+        rsq = read_scalar(mg, SC_RSQ);
+        if (std::isnan(rsq)) throw std::logic_error("NaN encountered at iteration" + std::to_string(i));
+        mg.lastIters = i; mg.lastResiduals.push_back(std::sqrt(rsq));
+        if (cb) cb(i, std::sqrt(rsq), user);
+    }
+}
+
+// TPS::solve at level 0 (TensorProductSimulator.hh:1198-1230) through the dense GPU solver
+void sim_direct_solve(vf_sim &s, const double *fDev, double *xDev) {
+    if (s.directVersion != s.version || !s.direct.ok) {
+        std::vector<uint8_t> fixed((size_t)s.g.numNodes * s.N, 0);
+        long long nfree = 0;
+        for (long long n = 0; n < s.g.numNodes; ++n) {
+            const int cbd = (s.g.bd == 2) ? (int)(n % s.g.nn[2]) : (int)((n / s.g.nn[2]) % s.g.nn[1]);
+            const bool det = cbd >= s.g.nActive;
+            for (int c = 0; c < s.N; ++c) { if (det || ((s.nodeMask[n] >> c) & 1)) fixed[n * s.N + c] = 1; else ++nfree; }
+        }
+        for (size_t k = 0; k < s.dirNodes.size(); ++k) for (int c = 0; c < s.N; ++c)
+            if (((s.dirMask[k] >> c) & 1) && s.dirVals[k * s.N + c] != 0) throw std::runtime_error("Nonzero Dirichlet constraints currently unsupported");
+        if (nfree > VF_MAX_DIRECT_DOFS) throw std::runtime_error("direct solve requested for " + std::to_string(nfree) + " free variables; use the multigrid solver (limit " + std::to_string(VF_MAX_DIRECT_DOFS) + ")");
+        const size_t len = (size_t)s.g.numNodes * (s.N == 3 ? 27 : 9) * s.N * s.N;
+        s.directStencil.alloc(len, false);
+        launch_stencil_from_moduli_l0(s.ctx, s.g, s.E.p, s.K0dev.p, s.directStencil.p);
+        s.direct.factor(s.ctx, s.g, s.directStencil.p, fixed);
+        s.directVersion = s.version;
+    }
+    s.direct.solve(s.ctx, s.g, fDev, xDev);
+}
+
+void sim_build_load_dev(vf_sim &s, double *f) { // buildLoadVector (:1269-1288)
+    VF_CUDA(cudaMemsetAsync(f, 0, sizeof(double) * s.g.numNodes * s.N, s.stream));
+    const size_t nf = s.forceNodes.size();
+    if (nf) { // scatter the point loads: reuse the Dirichlet "set value" kernel with a full component mask
+        DevBuf<long long> nodes; DevBuf<uint8_t> masks; DevBuf<double> vals;
+        std::vector<long long> hn(s.forceNodes.begin(), s.forceNodes.end()); std::vector<uint8_t> hm(nf, uint8_t((1u << s.N) - 1u));
+        nodes.alloc(nf, false); masks.alloc(nf, false); vals.alloc(nf * s.N, false);
+        nodes.upload(hn.data(), nf, s.stream); masks.upload(hm.data(), nf, s.stream); vals.upload(s.forceVals.data(), nf * s.N, s.stream);
+        launch_enforce_dirichlet(s.ctx, s.g.numNodes, s.N, (int)nf, nodes.p, masks.p, vals.p, f);
+        VF_CUDA(cudaStreamSynchronize(s.stream));
+    }
+    if (s.gravity[0] != 0 || s.gravity[1] != 0 || s.gravity[2] != 0)
+        launch_self_weight_load(s.ctx, s.g, s.rho.p, s.gravity, s.elemVolume(), f, 0, s.g.neActive, 1.0);
+}
+
+} // namespace
+
+#define VF_TRY try {
+#define VF_CATCH } catch (const std::logic_error &e) { vf::g_err = std::string("logic_error: ") + e.what(); return 2; } \
+                   catch (const std::exception &e) { vf::g_err = e.what(); return 1; } return 0;
+
+// scratch VField (device) of the simulator for host-pointer entry points
+static double *sim_tmp(vf_sim *s, int which) {
+    DevBuf<double> &b = which == 0 ? s->tmpU : s->tmpV;
+    const size_t len = (size_t)s->g.numNodes * s->N;
+    if (b.n != len) b.alloc(len, true);
+    return b.p;
+}
+static double *mg_tmp(vf_mg *mg, int which, size_t len) {
+    DevBuf<double> &b = which == 0 ? mg->tmpA : (which == 1 ? mg->tmpB : mg->tmpC);
+    if (b.n < len) b.alloc(len, true);
+    return b.p;
+}
+static void h2d(double *dev, const double *host, size_t n, cudaStream_t s) { VF_CUDA(cudaMemcpyAsync(dev, host, n * sizeof(double), cudaMemcpyHostToDevice, s)); }
+static void d2h(double *host, const double *dev, size_t n, cudaStream_t s) { VF_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, s)); VF_CUDA(cudaStreamSynchronize(s)); }
+
+extern "C" {
+
+const char *vf_last_error(void) { return vf::g_err.c_str(); }
+int vf_version(void) { return 100; }
+int vf_device_count(int *count) { VF_TRY VF_CUDA(cudaGetDeviceCount(count)); VF_CATCH }
+int vf_set_device(int device) { VF_TRY VF_CUDA(cudaSetDevice(device)); VF_CATCH }
+int64_t vf_kernel_launch_count(void) { return vf::g_launches.load(); }
+void vf_reset_kernel_launch_count(void) { vf::g_launches.store(0); }
+
+// ---- simulator ----------------------------------------------------------------------------
+int vf_sim_create(int dim, const int64_t *ne, const double *dmin, const double *dmax, vf_sim **out) {
+    VF_TRY
+    if (dim != 2 && dim != 3) throw std::runtime_error("dim must be 2 or 3");
+    ensure_device();
+    auto s = std::make_unique<vf_sim>();
+    s->N = dim;
+    for (int d = 0; d < dim; ++d) {
+        if (ne[d] < 1) throw std::runtime_error("grid must have at least one element per dimension");
+        s->ne[d] = ne[d]; s->nn[d] = ne[d] + 1; s->dmin[d] = dmin[d]; s->dmax[d] = dmax[d];
+        s->spacing[d] = (dmax[d] - dmin[d]) / (double(s->nn[d]) - 1.0);
+        s->stretch[d] = (dmax[d] - dmin[d]) / double(ne[d]);
+    }
+    s->g = make_grid(dim, ne);
+    VF_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->ctx.stream = s->stream; s->ctx.prof = &s->prof;
+    s->rho.alloc(s->g.numElems, true); s->E.alloc(s->g.numElems, true);
+    s->scratch.alloc(reduce_scratch_doubles(), true); s->scalars.alloc(SC_COUNT, true);
+    s->nodeMask.assign(s->g.numNodes, 0);
+    s->uploadBCs();
+    s->setIsotropic(1.0, 0.0);  // TensorProductSimulator.hh:2114
+    s->updateModuli();
+    *out = s.release();
+    VF_CATCH
+}
+int vf_sim_destroy(vf_sim *s) { VF_TRY if (s) { if (s->stream) { cudaStreamSynchronize(s->stream); } cudaStream_t st = s->stream; delete s; if (st) cudaStreamDestroy(st); } VF_CATCH }
+int64_t vf_sim_num_nodes(const vf_sim *s) { return s->g.numNodes; }
+int64_t vf_sim_num_elements(const vf_sim *s) { return s->g.numElems; }
+int vf_sim_set_elasticity_tensor(vf_sim *s, const double *D) {
+    VF_TRY const int fl = s->N == 3 ? 6 : 3; std::memset(s->D, 0, sizeof(s->D));
+    for (int i = 0; i < fl; ++i) for (int j = 0; j < fl; ++j) s->D[i][j] = D[i * fl + j];
+    s->updateK0(); VF_CATCH
+}
+int vf_sim_set_isotropic(vf_sim *s, double young, double poisson) { VF_TRY s->setIsotropic(young, poisson); VF_CATCH }
+int vf_sim_get_K0(const vf_sim *s, double *out) { VF_TRY std::copy(s->K0.begin(), s->K0.end(), out); VF_CATCH }
+int vf_sim_set_interpolation(vf_sim *s, int law, double E_0, double E_min, double gamma, double q) {
+    VF_TRY s->law = law; s->E0 = E_0; s->Emin = E_min; s->gamma = gamma; s->q = q; s->updateModuli(); VF_CATCH
+}
+int vf_sim_set_gravity(vf_sim *s, const double *g) { VF_TRY for (int c = 0; c < s->N; ++c) s->gravity[c] = g[c]; VF_CATCH }
+int vf_sim_set_densities(vf_sim *s, const double *rho) {
+    VF_TRY h2d(s->rho.p, rho, s->g.numElems, s->stream); s->updateModuli(); VF_CUDA(cudaStreamSynchronize(s->stream)); VF_CATCH
+}
+int vf_sim_set_uniform_density(vf_sim *s, double rho) {
+    VF_TRY if (rho > 1.0 || rho < 0) throw std::runtime_error("Density value (" + std::to_string(rho) + ") has to be in between 0 and 1");
+    launch_fill(s->ctx, s->g.numElems, rho, s->rho.p); s->updateModuli(); VF_CATCH
+}
+int vf_sim_get_densities(const vf_sim *s, double *rho) { VF_TRY d2h(rho, s->rho.p, s->g.numElems, s->stream); VF_CATCH }
+int vf_sim_get_young_moduli(const vf_sim *s, double *E) { VF_TRY d2h(E, s->E.p, s->g.numElems, s->stream); VF_CATCH }
+
+int vf_sim_apply_bc_regions(vf_sim *s, int nreg, const int32_t *kind, const int32_t *cmask, const double *values, const double *bmin, const double *bmax) {
+    VF_TRY
+    if (s->dirNodes.size() + s->forceNodes.size() > 0) throw std::runtime_error("Boundary condition updates unsupported");
+    BCBuilder b(*s);
+    for (int r = 0; r < nreg; ++r) {
+        std::vector<int64_t> idx[3];
+        const bool any = s->boxRanges(bmin + 3 * r, bmax + 3 * r, idx);
+        const double *val = values + 3 * r;
+        if (kind[r] == 1) {
+            if (!any) throw std::runtime_error("Force constraint region unmatched");
+            const double cnt = double(idx[0].size() * idx[1].size() * idx[2].size());
+            double f[3]; for (int c = 0; c < s->N; ++c) f[c] = val[c] / cnt;
+            for (int64_t i : idx[0]) for (int64_t j : idx[1]) for (int64_t k : idx[2]) b.setForce(s->flatNode(i, j, k), f);
+        } else if (kind[r] == 0) {
+            if (!any) throw std::runtime_error("Dirichlet region unmatched");
+            for (int64_t i : idx[0]) for (int64_t j : idx[1]) for (int64_t k : idx[2]) b.setDirichlet(s->flatNode(i, j, k), val, (unsigned)cmask[r]);
+        } else throw std::runtime_error("Illegal constraint type, only \"dirichlet\" and \"force\" accepted");
+    }
+    b.apply();
+    VF_CATCH
+}
+int vf_sim_add_dirichlet_box(vf_sim *s, const double *u, const double *bmin, const double *bmax, int cmask) {
+    VF_TRY BCBuilder b(*s); std::vector<int64_t> idx[3];
+    if (s->boxRanges(bmin, bmax, idx)) for (int64_t i : idx[0]) for (int64_t j : idx[1]) for (int64_t k : idx[2]) b.setDirichlet(s->flatNode(i, j, k), u, (unsigned)cmask);
+    b.apply(); VF_CATCH
+}
+int vf_sim_apply_symmetry_conditions(vf_sim *s, int axes_mask, int max_face_mask) {
+    VF_TRY BCBuilder b(*s);
+    for (int d = 0; d < s->N; ++d) {
+        if (!((axes_mask >> d) & 1)) continue;
+        const double target = ((max_face_mask >> d) & 1) ? s->dmax[d] : s->dmin[d];
+        for (int64_t n = 0; n < s->g.numNodes; ++n) {
+            int64_t c[3]; int64_t r = n; for (int a = s->N - 1; a >= 0; --a) { c[a] = r % s->nn[a]; r /= s->nn[a]; }
+            if (std::abs(s->dmin[d] + double(c[d]) * s->spacing[d] - target) < 1e-10) b.setDirichletComponent(n, d, 0.0);
+        }
+    }
+    b.apply(); VF_CATCH
+}
+int vf_sim_get_dirichlet_mask(const vf_sim *s, uint8_t *m) { VF_TRY std::copy(s->nodeMask.begin(), s->nodeMask.end(), m); VF_CATCH }
+int64_t vf_sim_num_force_nodes(const vf_sim *s) { return (int64_t)s->forceNodes.size(); }
+int vf_sim_build_load_vector_dev(vf_sim *s, double *f_dev) { VF_TRY sim_build_load_dev(*s, f_dev); VF_CATCH }
+int vf_sim_build_load_vector(vf_sim *s, double *f) {
+    VF_TRY double *t = sim_tmp(s, 0); sim_build_load_dev(*s, t); d2h(f, t, (size_t)s->g.numNodes * s->N, s->stream); VF_CATCH
+}
+int vf_sim_apply_K(vf_sim *s, const double *u, double *out, int zero_init, int negate) {
+    VF_TRY
+    const size_t len = (size_t)s->g.numNodes * s->N;
+    double *du = sim_tmp(s, 0), *dout = sim_tmp(s, 1);
+    h2d(du, u, len, s->stream);
+    if (!zero_init) h2d(dout, out, len, s->stream);
+    launch_apply_l0(s->ctx, s->g, s->K0p, du, s->E.p, nullptr, nullptr, dout, zero_init ? APPLY_SET : (negate ? APPLY_SUB : APPLY_ADD), nullptr, nullptr);
+    if (zero_init && negate) launch_scale(s->ctx, (long long)len, -1.0, dout);
+    d2h(out, dout, len, s->stream);
+    VF_CATCH
+}
+int vf_sim_set_mask_layer(vf_sim *s, int64_t layer) {
+    VF_TRY // setFabricationMaskHeightByLayer -> setFabricationMaskHeight (:290-309, 327-329)
+    const double h = s->spacing[1] * double(layer);
+    if (h < 0 || h > s->dmax[1]) throw std::runtime_error("Fabrication height (" + std::to_string(h) + ") has to be in between 0 and " + std::to_string(s->dmax[1]));
+    s->maskHeight = h;
+    s->firstMasked = (int)std::ceil(h / s->stretch[1] - 1e-10);
+    s->firstDetached = s->firstMasked + 1;
+    s->refreshGridMask(); s->updateModuli();
+    VF_CATCH
+}
+int vf_sim_get_mask_info(const vf_sim *s, int64_t *fm, int64_t *fd, double *h) { VF_TRY if (fm) *fm = s->firstMasked; if (fd) *fd = s->firstDetached; if (h) *h = s->maskHeight; VF_CATCH }
+int vf_sim_compliance_gradient(vf_sim *s, const double *u, double *g, int accumulate) {
+    VF_TRY
+    const size_t len = (size_t)s->g.numNodes * s->N;
+    double *du = sim_tmp(s, 0); h2d(du, u, len, s->stream);
+    DevBuf<double> dg; dg.alloc(s->g.numElems, !accumulate);
+    if (accumulate) h2d(dg.p, g, s->g.numElems, s->stream);
+    launch_compliance_gradient(s->ctx, s->g, s->K0p, du, s->rho.p, dg.p, s->law, s->E0, s->Emin, s->gamma, s->q, s->gravity, s->elemVolume(), accumulate != 0);
+    d2h(g, dg.p, s->g.numElems, s->stream);
+    VF_CATCH
+}
+int vf_sim_element_energy_density(vf_sim *s, const double *u, double *out) {
+    VF_TRY
+    double *du = sim_tmp(s, 0); h2d(du, u, (size_t)s->g.numNodes * s->N, s->stream);
+    DevBuf<double> dg; dg.alloc(s->g.numElems, false);
+    launch_energy_density(s->ctx, s->g, s->K0p, du, s->E.p, dg.p);
+    d2h(out, dg.p, s->g.numElems, s->stream);
+    VF_CATCH
+}
+int vf_sim_solve(vf_sim *s, const double *f, double *u) {
+    VF_TRY
+    const size_t len = (size_t)s->g.numNodes * s->N;
+    double *df = sim_tmp(s, 0), *du = sim_tmp(s, 1);
+    h2d(df, f, len, s->stream);
+    sim_direct_solve(*s, df, du);
+    d2h(u, du, len, s->stream);
+    VF_CATCH
+}
+
+// ---- multigrid -----------------------------------------------------------------------------
+int vf_mg_create(vf_sim *fine, int levels, vf_mg **out) {
+    VF_TRY
+    if (levels < 0) throw std::runtime_error("numCoarseningLevels must be >= 0");
+    auto mg = std::make_unique<vf_mg>();
+    mg->sim = fine; mg->N = fine->N; mg->ctx = fine->ctx;
+    const int N = fine->N;
+    int64_t ne[3] = {fine->ne[0], fine->ne[1], fine->ne[2]};
+    for (int l = 0; l <= levels; ++l) {
+        auto L = std::make_unique<MGLevel>();
+        if (l > 0) {
+            for (int d = 0; d < N; ++d) {
+                if (ne[d] % 2 == 1) throw std::runtime_error("Grid size currently must be divisible by 2^numCoarseningLevels (nonuniform coarsening not yet implemented)");
+                ne[d] /= 2;
+            }
+        }
+        for (int d = 0; d < 3; ++d) L->ne[d] = ne[d];
+        L->g = make_grid(N, ne);
+        L->stretchBD = (fine->dmax[1] - fine->dmin[1]) / double(ne[1]);
+        const size_t len = (size_t)L->g.numNodes * N;
+        L->x.alloc(len, true); L->b.alloc(len, true); L->r.alloc(len, true);
+        if (l == 0) L->nodeMask = fine->nodeMask;
+        else {
+            // Dirichlet coarsening (MultigridSolver.hh:58-103): a fine Dirichlet node constrains, with the same component
+            // mask and zero value, every coarse node on the vertex/edge/face/cell of the coarse element it lies on.
+            const MGLevel &F = *mg->lv.back();
+            L->nodeMask.assign(L->g.numNodes, 0);
+            int64_t fnn[3] = {1, 1, 1}, cnn[3] = {1, 1, 1};
+            for (int d = 0; d < N; ++d) { fnn[d] = F.ne[d] + 1; cnn[d] = ne[d] + 1; }
+            for (int64_t fn = 0; fn < F.g.numNodes; ++fn) {
+                const uint8_t m = F.nodeMask[fn]; if (!m) continue;
+                int64_t c[3] = {0, 0, 0}; { int64_t r = fn; for (int d = N - 1; d >= 0; --d) { c[d] = r % fnn[d]; r /= fnn[d]; } }
+                for (int k = 0; k < (1 << N); ++k) {
+                    int64_t cn = 0; bool ok = true;
+                    for (int d = 0; d < N; ++d) {
+                        const int bit = (k >> d) & 1;
+                        if ((c[d] & 1) == 0 && bit) { ok = false; break; }
+                        const int64_t q = (c[d] >> 1) + bit;
+                        cn = cn * cnn[d] + q;
+                    }
+                    if (ok) L->nodeMask[cn] |= m;
+                }
+            }
+            L->dmask.alloc(L->g.numNodes, false); L->dmask.upload(L->nodeMask.data(), L->g.numNodes, fine->stream);
+            VF_CUDA(cudaStreamSynchronize(fine->stream));
+        }
+        mg->lv.push_back(std::move(L));
+    }
+    // coarsenedFineK0s[fi] = Phi_fi^T K0 Phi_fi (MultigridSolver.hh:116-120, 664-687, 711-722)
+    const int npe = 1 << N, ke = N * npe;
+    mg->cK0.assign((size_t)npe * ke * ke, 0.0);
+    for (int fi = 0; fi < npe; ++fi) {
+        std::vector<double> phi((size_t)npe * npe);
+        for (int fn = 0; fn < npe; ++fn) for (int cn = 0; cn < npe; ++cn) {
+            double v = 1;
+            for (int d = 0; d < N; ++d) {
+                const double pos = 0.5 * ((fn >> (N - 1 - d)) & 1) + 0.5 * ((fi >> (N - 1 - d)) & 1);
+                v *= ((cn >> (N - 1 - d)) & 1) ? pos : (1.0 - pos);
+            }
+            phi[fn * npe + cn] = v;
+        }
+        std::vector<double> T((size_t)ke * ke, 0.0);
+        for (int a = 0; a < ke; ++a) for (int j = 0; j < npe; ++j) for (int dc = 0; dc < N; ++dc) {
+            double sacc = 0; for (int i = 0; i < npe; ++i) sacc += fine->K0[(size_t)a * ke + (N * i + dc)] * phi[i * npe + j];
+            T[(size_t)a * ke + (N * j + dc)] = sacc;
+        }
+        double *Kc = &mg->cK0[(size_t)fi * ke * ke];
+        for (int j = 0; j < npe; ++j) for (int c = 0; c < N; ++c) for (int bcol = 0; bcol < ke; ++bcol) {
+            double sacc = 0; for (int i = 0; i < npe; ++i) sacc += phi[i * npe + j] * T[(size_t)(N * i + c) * ke + bcol];
+            Kc[(size_t)(N * j + c) * ke + bcol] = sacc;
+        }
+    }
+    mg->cK0dev.alloc(mg->cK0.size(), false); mg->cK0dev.upload(mg->cK0.data(), mg->cK0.size(), fine->stream);
+    VF_CUDA(cudaStreamSynchronize(fine->stream));
+    const size_t len0 = (size_t)fine->g.numNodes * N;
+    mg->Ad.alloc(len0, true); mg->d.alloc(len0, true);
+    mg->scalars.alloc(SC_COUNT, true); mg->scratch.alloc(reduce_scratch_doubles(), true);
+    VF_CUDA(cudaMallocHost(&mg->hostScalars, SC_COUNT * sizeof(double)));
+    mg_sync_level_masks(*mg);
+    *out = mg.release();
+    VF_CATCH
+}
+int vf_mg_destroy(vf_mg *mg) { VF_TRY if (mg) { cudaStreamSynchronize(mg->ctx.stream); delete mg; } VF_CATCH }
+int vf_mg_num_levels(const vf_mg *mg) { return mg->numLevels(); }
+int64_t vf_mg_level_num_nodes(const vf_mg *mg, int l) { return mg->grid(l).numNodes; }
+int vf_mg_level_grid(const vf_mg *mg, int l, int64_t *ne) { VF_TRY for (int d = 0; d < mg->N; ++d) ne[d] = mg->lv.at(l)->ne[d]; VF_CATCH }
+int vf_mg_level_dirichlet_mask(const vf_mg *mg, int l, uint8_t *m) {
+    VF_TRY const std::vector<uint8_t> &src = (l == 0) ? mg->sim->nodeMask : mg->lv.at(l)->nodeMask; std::copy(src.begin(), src.end(), m); VF_CATCH
+}
+int vf_mg_get_coarsened_fine_K0(const vf_mg *mg, int fi, double *out) {
+    VF_TRY const int ke = mg->N * (1 << mg->N); std::copy(mg->cK0.begin() + (size_t)fi * ke * ke, mg->cK0.begin() + (size_t)(fi + 1) * ke * ke, out); VF_CATCH
+}
+int vf_mg_update_stiffness_matrices(vf_mg *mg) { VF_TRY mg_update_stiffness(*mg, true); VF_CUDA(cudaStreamSynchronize(mg->ctx.stream)); VF_CATCH }
+int vf_mg_apply_K(vf_mg *mg, int l, const double *u, double *out) {
+    VF_TRY const size_t len = (size_t)mg->grid(l).numNodes * mg->N;
+    double *du = mg_tmp(mg, 0, len), *dout = mg_tmp(mg, 1, len);
+    h2d(du, u, len, mg->ctx.stream); mg_sync_level_masks(*mg);
+    mg_apply_K(*mg, l, du, nullptr, dout, APPLY_SET, false);
+    d2h(out, dout, len, mg->ctx.stream); VF_CATCH
+}
+int vf_mg_compute_residual(vf_mg *mg, int l, const double *u, const double *b, double *r) {
+    VF_TRY const size_t len = (size_t)mg->grid(l).numNodes * mg->N;
+    double *du = mg_tmp(mg, 0, len), *db = mg_tmp(mg, 1, len), *dr = mg_tmp(mg, 2, len);
+    h2d(du, u, len, mg->ctx.stream); h2d(db, b, len, mg->ctx.stream); mg_sync_level_masks(*mg);
+    VF_CUDA(cudaMemsetAsync(dr, 0, len * sizeof(double), mg->ctx.stream));
+    mg_residual(*mg, l, du, db, dr);
+    d2h(r, dr, len, mg->ctx.stream); VF_CATCH
+}
+int vf_mg_smooth(vf_mg *mg, int l, double *u, const double *b, int forward) {
+    VF_TRY const size_t len = (size_t)mg->grid(l).numNodes * mg->N;
+    double *du = mg_tmp(mg, 0, len), *db = mg_tmp(mg, 1, len);
+    h2d(du, u, len, mg->ctx.stream); h2d(db, b, len, mg->ctx.stream); mg_sync_level_masks(*mg);
+    mg_smooth(*mg, l, du, db, forward != 0);
+    d2h(u, du, len, mg->ctx.stream); VF_CATCH
+}
+int vf_mg_restrict(vf_mg *mg, int lf, const double *fine, double *coarse) {
+    VF_TRY const size_t lenF = (size_t)mg->grid(lf).numNodes * mg->N, lenC = (size_t)mg->grid(lf + 1).numNodes * mg->N;
+    double *df = mg_tmp(mg, 0, lenF), *dc = mg_tmp(mg, 1, lenC);
+    h2d(df, fine, lenF, mg->ctx.stream); h2d(dc, coarse, lenC, mg->ctx.stream); mg_sync_level_masks(*mg);
+    launch_restrict(mg->ctx, mg->grid(lf), mg->grid(lf + 1), df, dc);
+    d2h(coarse, dc, lenC, mg->ctx.stream); VF_CATCH
+}
+int vf_mg_interpolate(vf_mg *mg, int lf, const double *coarse, double *fine, int accumulate) {
+    VF_TRY const size_t lenF = (size_t)mg->grid(lf).numNodes * mg->N, lenC = (size_t)mg->grid(lf + 1).numNodes * mg->N;
+    double *df = mg_tmp(mg, 0, lenF), *dc = mg_tmp(mg, 1, lenC);
+    h2d(dc, coarse, lenC, mg->ctx.stream); h2d(df, fine, lenF, mg->ctx.stream); mg_sync_level_masks(*mg);
+    launch_prolong(mg->ctx, mg->grid(lf), mg->grid(lf + 1), dc, df, accumulate != 0);
+    d2h(fine, df, lenF, mg->ctx.stream); VF_CATCH
+}
+int vf_mg_get_stencil(vf_mg *mg, int l, double *out) {
+    VF_TRY if (l < 1 || l >= mg->numLevels()) throw std::runtime_error("stencils are stored for levels 1..numLevels-1");
+    mg_update_stiffness(*mg);
+    const GridDesc &g = mg->grid(l); const int ns = mg->N == 3 ? 27 : 9, NN = mg->N * mg->N;
+    std::vector<double> h((size_t)g.numNodes * ns * NN);
+    d2h(h.data(), mg->lv[l]->S.p, h.size(), mg->ctx.stream);
+    for (long long n = 0; n < g.numNodes; ++n) for (int s = 0; s < ns; ++s) for (int i = 0; i < NN; ++i)
+        out[((size_t)n * ns + s) * NN + i] = h[(size_t)(s * NN + i) * g.numNodes + n];
+    VF_CATCH
+}
+int vf_mg_coarse_solve(vf_mg *mg, const double *f, double *x) {
+    VF_TRY const int l = mg->numLevels() - 1; const size_t len = (size_t)mg->grid(l).numNodes * mg->N;
+    double *df = mg_tmp(mg, 0, len), *dx = mg_tmp(mg, 1, len);
+    h2d(df, f, len, mg->ctx.stream); mg_sync_level_masks(*mg);
+    if (l == 0) sim_direct_solve(*mg->sim, df, dx); else mg_coarse_solve(*mg, df, dx);
+    d2h(x, dx, len, mg->ctx.stream); VF_CATCH
+}
+int vf_mg_solve(vf_mg *mg, const double *u, const double *f, int numSteps, int nsmooth, int stiffnessUpdated, int zeroDirichlet, int fmg, double *out) {
+    VF_TRY (void)stiffnessUpdated; // coarse operators are version-tracked; stale ones are always rebuilt
+    const size_t len = (size_t)mg->grid(0).numNodes * mg->N;
+    mg_sync_level_masks(*mg);
+    h2d(lx(*mg, 0), u, len, mg->ctx.stream);
+    if (numSteps > 0) {
+        h2d(lb(*mg, 0), f, len, mg->ctx.stream);
+        if (mg->numLevels() == 1) sim_direct_solve(*mg->sim, lb(*mg, 0), lx(*mg, 0));
+        else { mg_update_stiffness(*mg); mg_solve_inplace(*mg, numSteps, nsmooth, zeroDirichlet != 0, fmg != 0); }
+    }
+    d2h(out, lx(*mg, 0), len, mg->ctx.stream); VF_CATCH
+}
+int vf_mg_pcg_dev(vf_mg *mg, double *x, const double *b, int maxIter, double tol, int mgIt, int mgSmooth, int fmg, int dirichletOK,
+                  int *outIters, double *resNorms, vf_pcg_callback cb, void *user) {
+    VF_TRY mg_pcg(*mg, x, b, maxIter, tol, mgIt, mgSmooth, fmg != 0, dirichletOK != 0, cb, user);
+    VF_CUDA(cudaStreamSynchronize(mg->ctx.stream));
+    if (outIters) *outIters = mg->lastIters;
+    if (resNorms) std::copy(mg->lastResiduals.begin(), mg->lastResiduals.end(), resNorms);
+    VF_CATCH
+}
+int vf_mg_pcg(vf_mg *mg, double *x, const double *b, int maxIter, double tol, int mgIt, int mgSmooth, int fmg, int dirichletOK,
+              int *outIters, double *resNorms, vf_pcg_callback cb, void *user) {
+    VF_TRY const size_t len = (size_t)mg->grid(0).numNodes * mg->N;
+    double *dx = mg_tmp(mg, 0, len), *db = mg_tmp(mg, 1, len);
+    h2d(dx, x, len, mg->ctx.stream); h2d(db, b, len, mg->ctx.stream);
+    mg_pcg(*mg, dx, db, maxIter, tol, mgIt, mgSmooth, fmg != 0, dirichletOK != 0, cb, user);
+    d2h(x, dx, len, mg->ctx.stream);
+    if (outIters) *outIters = mg->lastIters;
+    if (resNorms) std::copy(mg->lastResiduals.begin(), mg->lastResiduals.end(), resNorms);
+    VF_CATCH
+}
+int vf_mg_get_pcg_residual(vf_mg *mg, double *r) { VF_TRY d2h(r, lb(*mg, 0), (size_t)mg->grid(0).numNodes * mg->N, mg->ctx.stream); VF_CATCH }
+int vf_mg_set_symmetric_gauss_seidel(vf_mg *mg, int s) { mg->symmetricGS = s != 0; return 0; }
+int vf_mg_set_mask_layer(vf_mg *mg, int64_t layer) { if (int rc = vf_sim_set_mask_layer(mg->sim, layer)) return rc; VF_TRY mg_sync_level_masks(*mg); VF_CATCH }
+int vf_mg_decrement_mask(vf_mg *mg, int inc) {
+    VF_TRY // decrementFabricationMaskHeightByLayer (TensorProductSimulator.hh:311-324; MultigridSolver.hh:1030-1036)
+    vf_sim &s = *mg->sim;
+    if ((int64_t)s.firstMasked > s.ne[1]) throw std::runtime_error("Mask must already be applied");
+    if (s.firstMasked < inc) throw std::runtime_error("Mask decrement of bounds");
+    s.maskHeight -= inc * s.spacing[1];
+    s.firstMasked -= inc; s.firstDetached = s.firstMasked + 1;
+    s.refreshGridMask();
+    launch_zero_moduli_layers(s.ctx, s.g, s.E.p, s.firstMasked, s.firstMasked + inc);
+    s.touch(); mg_sync_level_masks(*mg);
+    VF_CATCH
+}
+int vf_mg_debug_get(vf_mg *mg, int which, int l, double *out) {
+    VF_TRY MGLevel &L = *mg->lv.at(l); const double *p = which == 0 ? L.x.p : (which == 1 ? L.b.p : L.r.p);
+    d2h(out, p, (size_t)L.g.numNodes * mg->N, mg->ctx.stream); VF_CATCH
+}
+int vf_mg_debug_multicolor_visit(vf_mg *mg, int32_t *order) {
+    VF_TRY // host restatement of the visit order for the debug exposer (:444-450); colour-major, row-major within a colour
+    const GridDesc &g = mg->sim->g; int32_t i = 0;
+    for (int color = 0; color < (1 << mg->N); ++color) {
+        ColorDesc col; if (!make_color(g, color, col)) continue;
+        for (int i0 = 0; i0 < col.cnt[0]; ++i0) for (int i1 = 0; i1 < col.cnt[1]; ++i1) for (int i2 = 0; i2 < col.cnt[2]; ++i2)
+            order[(long long)(col.off[0] + 2 * i0) * g.ns[0] + (long long)(col.off[1] + 2 * i1) * g.ns[1] + (col.off[2] + 2 * i2)] = i++;
+    }
+    VF_CATCH
+}
+
+int vf_dev_alloc(size_t n, double **out) { VF_TRY ensure_device(); VF_CUDA(cudaMalloc(out, n * sizeof(double))); VF_CUDA(cudaMemset(*out, 0, n * sizeof(double))); VF_CATCH }
+int vf_dev_free(double *p) { VF_TRY VF_CUDA(cudaFree(p)); VF_CATCH }
+int vf_dev_upload(double *dev, const double *host, size_t n) { VF_TRY VF_CUDA(cudaMemcpy(dev, host, n * sizeof(double), cudaMemcpyHostToDevice)); VF_CATCH }
+int vf_dev_download(double *host, const double *dev, size_t n) { VF_TRY VF_CUDA(cudaMemcpy(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost)); VF_CATCH }
+int vf_dev_memset_zero(double *dev, size_t n) { VF_TRY VF_CUDA(cudaMemset(dev, 0, n * sizeof(double))); VF_CATCH }
+void *vf_mg_stream(vf_mg *mg) { return (void *)mg->ctx.stream; }
+int vf_mg_synchronize(vf_mg *mg) { VF_TRY VF_CUDA(cudaStreamSynchronize(mg->ctx.stream)); VF_CATCH }
+
+int vf_prof_enable(vf_mg *mg, int enable) { mg->sim->prof.enabled = enable != 0; return 0; }
+int vf_prof_reset(vf_mg *mg) { VF_TRY mg->sim->prof.reset(); VF_CATCH }
+int vf_prof_num_categories(void) { return PC_COUNT; }
+const char *vf_prof_name(int c) { return (c >= 0 && c < PC_COUNT) ? kProfNames[c] : ""; }
+int vf_prof_get(vf_mg *mg, int c, int64_t *launches, double *ms, double *units) {
+    VF_TRY Profiler &p = mg->sim->prof; VF_CUDA(cudaStreamSynchronize(mg->ctx.stream)); p.resolve();
+    if (c < 0 || c >= PC_COUNT) throw std::runtime_error("bad profiling category");
+    if (launches) *launches = p.launches[c]; if (ms) *ms = p.ms[c]; if (units) *units = p.units[c];
+    VF_CATCH
+}
+
+// ---- stand-alone filters --------------------------------------------------------------------
+static LaunchCtx default_ctx() { LaunchCtx c; c.stream = nullptr; c.prof = nullptr; return c; }
+int vf_filter_smooth(int dim, const int64_t *sizes, int radius, int type, const double *in, double *out) {
+    VF_TRY ensure_device(); long long n = 1; int sz[3] = {1, 1, 1}; for (int d = 0; d < dim; ++d) { sz[d] = (int)sizes[d]; n *= sizes[d]; }
+    DevBuf<double> a, b; a.alloc(n, false); b.alloc(n, false); LaunchCtx c = default_ctx();
+    h2d(a.p, in, n, c.stream); launch_filter_smooth(c, dim, sz, radius, type, a.p, b.p); d2h(out, b.p, n, c.stream); VF_CATCH
+}
+int vf_filter_project(int64_t n, double beta, const double *in, double *out) {
+    VF_TRY ensure_device(); DevBuf<double> a, b; a.alloc(n, false); b.alloc(n, false); LaunchCtx c = default_ctx();
+    h2d(a.p, in, n, c.stream); launch_filter_project(c, n, beta, a.p, b.p); d2h(out, b.p, n, c.stream); VF_CATCH
+}
+int vf_filter_project_backprop(int64_t n, double beta, const double *in, const double *vars, double *out) {
+    VF_TRY ensure_device(); DevBuf<double> a, v, b; a.alloc(n, false); v.alloc(n, false); b.alloc(n, false); LaunchCtx c = default_ctx();
+    h2d(a.p, in, n, c.stream); h2d(v.p, vars, n, c.stream); launch_filter_project_backprop(c, n, beta, a.p, v.p, b.p); d2h(out, b.p, n, c.stream); VF_CATCH
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------
+// Topology optimization problem
+// ---------------------------------------------------------------------------
+struct FilterSpec { int kind, radius, type; double beta; };
+struct vf_top {
+    vf_mg *mg; vf_sim *sim;
+    std::vector<FilterSpec> filters; double volFrac;
+    std::vector<std::unique_ptr<DevBuf<double>>> vars; // m_vars of FilterChain (TopologyOptimizationFilter.hh:111-132)
+    DevBuf<double> u, f, dJ, dc, stepped, xv, tmp, scalar, scratch;
+    int cgIter = 100; double tol = 1e-5; int mgIt = 1, mgSmooth = 2; bool fmg = true, zeroInit = false; // TopologyOptimizationObjective.hh:99-103
+    double lamMin = 1, lamMax = 2; // OptimalityCriterion.hh:46-49
+    int lastPcgIters = 0;
+    double *hostScalar = nullptr;
+    ~vf_top() { if (hostScalar) cudaFreeHost(hostScalar); }
+    long long ne() const { return sim->g.numElems; }
+    int sizes3[3];
+    void applyFilter(const FilterSpec &fs, const double *in, double *out) {
+        int sz[3] = {(int)sim->ne[0], (int)sim->ne[1], (int)sim->ne[2]};
+        if (fs.kind == VF_FILTER_SMOOTH) launch_filter_smooth(mg->ctx, sim->N, sz, fs.radius, fs.type, in, out);
+        else launch_filter_project(mg->ctx, ne(), fs.beta, in, out);
+    }
+    double readScalar() {
+        VF_CUDA(cudaMemcpyAsync(hostScalar, scalar.p, sizeof(double), cudaMemcpyDeviceToHost, mg->ctx.stream));
+        VF_CUDA(cudaStreamSynchronize(mg->ctx.stream));
+        return *hostScalar;
+    }
+    // MultigridComplianceObjective::updateCache (TopologyOptimizationObjective.hh:88-96)
+    void updateCache(const double *xPhysDev) {
+        if (xPhysDev != sim->rho.p) VF_CUDA(cudaMemcpyAsync(sim->rho.p, xPhysDev, sizeof(double) * ne(), cudaMemcpyDeviceToDevice, mg->ctx.stream));
+        sim->updateModuli();
+        if (zeroInit) VF_CUDA(cudaMemsetAsync(u.p, 0, sizeof(double) * u.n, mg->ctx.stream));
+        mg_pcg(*mg, u.p, f.p, cgIter, tol, mgIt, mgSmooth, fmg, false, nullptr, nullptr);
+        lastPcgIters = mg->lastIters;
+    }
+    void setVarsDev() { // FilterChain::setDesignVars (:142-152) + updateCache
+        for (size_t i = 0; i < filters.size(); ++i) applyFilter(filters[i], vars[i]->p, vars[i + 1]->p);
+        updateCache(vars.back()->p);
+    }
+    void backprop(DevBuf<double> &g, DevBuf<double> &scr) { // FilterChain::backprop (:162-170); result left in g
+        double *a = g.p, *b = scr.p;
+        for (size_t i = filters.size(); i-- > 0;) {
+            if (filters[i].kind == VF_FILTER_SMOOTH) { int sz[3] = {(int)sim->ne[0], (int)sim->ne[1], (int)sim->ne[2]}; launch_filter_smooth(mg->ctx, sim->N, sz, filters[i].radius, filters[i].type, a, b); }
+            else launch_filter_project_backprop(mg->ctx, ne(), filters[i].beta, a, vars[i]->p, b);
+            std::swap(a, b);
+        }
+        if (a != g.p) VF_CUDA(cudaMemcpyAsync(g.p, a, sizeof(double) * ne(), cudaMemcpyDeviceToDevice, mg->ctx.stream));
+    }
+    void objectiveGradient() { // into dJ
+        launch_compliance_gradient(mg->ctx, sim->g, sim->K0p, u.p, sim->rho.p, dJ.p, sim->law, sim->E0, sim->Emin, sim->gamma, sim->q, sim->gravity, sim->elemVolume(), false);
+        backprop(dJ, tmp);
+    }
+    void constraintJacobian() { // into dc (TopologyOptimizationConstraint.hh:34-36)
+        launch_fill(mg->ctx, ne(), -1.0 / (volFrac * double(ne())), dc.p);
+        backprop(dc, tmp);
+    }
+    double constraintOf(const double *xPhys) { // :30-32
+        launch_sum(mg->ctx, ne(), xPhys, scalar.p, scratch.p);
+        return 1.0 - (readScalar() / double(ne())) / volFrac;
+    }
+    double ceval(double lambda, double m, double p) { // OptimalityCriterion.hh:64-83 + TopologyOptimizationProblem.hh:58-66
+        launch_oc_update(mg->ctx, ne(), vars[0]->p, dJ.p, dc.p, lambda, m, p, stepped.p);
+        const double *cur = stepped.p; double *a = xv.p, *b = tmp.p;
+        for (const auto &fs : filters) { applyFilter(fs, cur, a); cur = a; std::swap(a, b); }
+        return constraintOf(cur);
+    }
+};
+
+extern "C" {
+int vf_top_create(vf_mg *mg, int nf, const double *spec, double volFrac, vf_top **out) {
+    VF_TRY
+    auto t = std::make_unique<vf_top>();
+    t->mg = mg; t->sim = mg->sim; t->volFrac = volFrac;
+    for (int i = 0; i < nf; ++i) t->filters.push_back({(int)spec[4 * i], (int)spec[4 * i + 1], (int)spec[4 * i + 2], spec[4 * i + 3]});
+    const long long ne = t->ne(); const size_t len = (size_t)t->sim->g.numNodes * t->sim->N;
+    for (int i = 0; i <= nf; ++i) { t->vars.push_back(std::make_unique<DevBuf<double>>()); t->vars.back()->alloc(ne, true); }
+    t->u.alloc(len, true); t->f.alloc(len, true);
+    t->dJ.alloc(ne, true); t->dc.alloc(ne, true); t->stepped.alloc(ne, true); t->xv.alloc(ne, true); t->tmp.alloc(ne, true);
+    t->scalar.alloc(1, true); t->scratch.alloc(reduce_scratch_doubles(), true);
+    VF_CUDA(cudaMallocHost(&t->hostScalar, sizeof(double)));
+    sim_build_load_dev(*t->sim, t->f.p);      // ComplianceObjective ctor (TopologyOptimizationObjective.hh:32-35)
+    t->updateCache(t->sim->rho.p);            // MultigridComplianceObjective ctor (:82-86)
+    VF_CUDA(cudaStreamSynchronize(mg->ctx.stream));
+    *out = t.release();
+    VF_CATCH
+}
+int vf_top_destroy(vf_top *t) { VF_TRY if (t) { cudaStreamSynchronize(t->mg->ctx.stream); delete t; } VF_CATCH }
+int vf_top_set_solver(vf_top *t, int cgIter, double tol, int mgIt, int mgSmooth, int fmg, int zeroInit) { t->cgIter = cgIter; t->tol = tol; t->mgIt = mgIt; t->mgSmooth = mgSmooth; t->fmg = fmg != 0; t->zeroInit = zeroInit != 0; return 0; }
+int vf_top_set_vars(vf_top *t, const double *x) { VF_TRY h2d(t->vars[0]->p, x, t->ne(), t->mg->ctx.stream); t->setVarsDev(); VF_CUDA(cudaStreamSynchronize(t->mg->ctx.stream)); VF_CATCH }
+int vf_top_get_vars(vf_top *t, int which, double *out) { VF_TRY d2h(out, which == 0 ? t->vars.front()->p : t->vars.back()->p, t->ne(), t->mg->ctx.stream); VF_CATCH }
+int vf_top_compliance(vf_top *t, double *out) {
+    VF_TRY launch_dot_plain(t->mg->ctx, (long long)t->u.n, t->f.p, t->u.p, t->scalar.p, t->scratch.p); *out = 0.5 * t->readScalar(); VF_CATCH
+}
+int vf_top_constraint(vf_top *t, double *out) { VF_TRY *out = t->constraintOf(t->vars.back()->p); VF_CATCH }
+int vf_top_objective_gradient(vf_top *t, double *g) { VF_TRY t->objectiveGradient(); d2h(g, t->dJ.p, t->ne(), t->mg->ctx.stream); VF_CATCH }
+int vf_top_constraint_jacobian(vf_top *t, double *g) { VF_TRY t->constraintJacobian(); d2h(g, t->dc.p, t->ne(), t->mg->ctx.stream); VF_CATCH }
+int vf_top_get_u(vf_top *t, double *u) { VF_TRY d2h(u, t->u.p, t->u.n, t->mg->ctx.stream); VF_CATCH }
+int vf_top_last_pcg_iterations(vf_top *t) { return t->lastPcgIters; }
+int vf_top_get_lambda_bracket(vf_top *t, double *lo, double *hi) { *lo = t->lamMin; *hi = t->lamMax; return 0; }
+// OCOptimizer::step (OptimalityCriterion.hh:51-134)
+int vf_top_oc_step(vf_top *t, double m, double p, double ctol, int *nevalsOut) {
+    VF_TRY
+    t->objectiveGradient(); t->constraintJacobian();
+    int nevals = 0;
+    auto ceval = [&](double lam) { ++nevals; return t->ceval(lam, m, p); };
+    const double dilation = 32;
+    double mid = 0.5 * (t->lamMin + t->lamMax);
+    t->lamMax = dilation * t->lamMax + (1 - dilation) * mid;
+    t->lamMin = std::max(dilation * t->lamMin + (1 - dilation) * mid, 0.01);
+    const int guard = 100; int nit = 0;
+    for (; nit < guard; ++nit) { if (ceval(t->lamMin) < 0) break; t->lamMax = t->lamMin; t->lamMin /= 2; }
+    if (nit == guard) throw std::runtime_error("Bracketing constraint(lambda_min) < 0 failed (100 times).");
+    if (nit == 0) for (; nit < guard; ++nit) { if (ceval(t->lamMax) > 0) break; t->lamMin = t->lamMax; t->lamMax *= 2; }
+    if (nit == guard) throw std::runtime_error("Bracketing constraint(lambda_max) > 0 failed (100 times).");
+    double violation;
+    do {
+        mid = 0.5 * (t->lamMin + t->lamMax);
+        violation = ceval(mid);
+        if (std::abs(violation) <= ctol) break;
+        ++nit;
+        if (violation < 0) t->lamMin = mid;
+        if (violation > 0) t->lamMax = mid;
+    } while (true);
+    // m_p.setVars(m_steppedVars) (:133)
+    VF_CUDA(cudaMemcpyAsync(t->vars[0]->p, t->stepped.p, sizeof(double) * t->ne(), cudaMemcpyDeviceToDevice, t->mg->ctx.stream));
+    t->setVarsDev();
+    VF_CUDA(cudaStreamSynchronize(t->mg->ctx.stream));
+    if (nevalsOut) *nevalsOut = nevals;
+    VF_CATCH
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------
+// Layer-by-layer evaluator (LayerByLayer.hh:25-309)
+// ---------------------------------------------------------------------------
+// Initial-guess generators: Zero (:56-61), FD with history 1 ("constant") or 2 ("fd") (:89-101) and
+// Subspace N=k (:103-209).  The reference maintains the k x k subspace system  A = U^T K U, b = U^T f  with
+// band-limited recurrences (:149-202, TensorProductSimulator.hh:1309-1406) that are exact identities for
+// A and b *of the next layer's system*; here A and b are evaluated directly for the current (next) system at
+// constructGuess time with k stiffness applies and k(k+3)/2 masked dot products -- same values up to rounding.
+struct vf_lbl {
+    vf_mg *mg; vf_sim *sim;
+    int method = 2; // 0 zero, 1 FD, 2 subspace
+    size_t maxHist = 3;
+    std::vector<std::unique_ptr<DevBuf<double>>> hist; // front = most recent
+    DevBuf<double> f, u, uFull, w, totalGrad, scalar, scratch;
+    bool uValid = false, uFullValid = false;
+    double totalCompliance = 0; long long layersAccumulated = 0;
+    double *hostScalar = nullptr;
+    std::vector<int> layerIters;
+    ~vf_lbl() { if (hostScalar) cudaFreeHost(hostScalar); }
+    size_t len() const { return (size_t)sim->g.numNodes * sim->N; }
+    double maskedDot(const double *a, const double *b) {
+        launch_masked_dot(mg->ctx, sim->g, a, b, scalar.p, scratch.p);
+        VF_CUDA(cudaMemcpyAsync(hostScalar, scalar.p, sizeof(double), cudaMemcpyDeviceToHost, mg->ctx.stream));
+        VF_CUDA(cudaStreamSynchronize(mg->ctx.stream));
+        return *hostScalar;
+    }
+    void addToHistory() { // m_addToHistory (:72-84): the solved field moves to the front, the stalest buffer is recycled as `u`
+        if (maxHist == 0) return;
+        std::unique_ptr<DevBuf<double>> slot;
+        if (hist.size() == maxHist) { slot = std::move(hist.back()); hist.pop_back(); }
+        else { slot = std::make_unique<DevBuf<double>>(); slot->alloc(len(), true); }
+        std::swap(slot->p, u.p); std::swap(slot->n, u.n);
+        hist.insert(hist.begin(), std::move(slot));
+        uValid = false;
+    }
+    // pseudo-inverse solve of the symmetric k x k system (Eigen::JacobiSVD::solve semantics, :120-121)
+    static std::vector<double> solveSymmetricPinv(std::vector<double> A, const std::vector<double> &b, int k) {
+        std::vector<double> V((size_t)k * k, 0.0);
+        for (int i = 0; i < k; ++i) V[i * k + i] = 1;
+        for (int sweep = 0; sweep < 64; ++sweep) {
+            double off = 0; for (int i = 0; i < k; ++i) for (int j = i + 1; j < k; ++j) off += A[i * k + j] * A[i * k + j];
+            if (off < 1e-300) break;
+            for (int p = 0; p < k; ++p) for (int q = p + 1; q < k; ++q) {
+                if (A[p * k + q] == 0) continue;
+                const double theta = (A[q * k + q] - A[p * k + p]) / (2 * A[p * k + q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::abs(theta) + std::sqrt(theta * theta + 1));
+                const double c = 1 / std::sqrt(t * t + 1), sn = t * c;
+                for (int r = 0; r < k; ++r) { const double arp = A[r * k + p], arq = A[r * k + q]; A[r * k + p] = c * arp - sn * arq; A[r * k + q] = sn * arp + c * arq; }
+                for (int r = 0; r < k; ++r) { const double apr = A[p * k + r], aqr = A[q * k + r]; A[p * k + r] = c * apr - sn * aqr; A[q * k + r] = sn * apr + c * aqr; }
+                for (int r = 0; r < k; ++r) { const double vrp = V[r * k + p], vrq = V[r * k + q]; V[r * k + p] = c * vrp - sn * vrq; V[r * k + q] = sn * vrp + c * vrq; }
+            }
+        }
+        double smax = 0; for (int i = 0; i < k; ++i) smax = std::max(smax, std::abs(A[i * k + i]));
+        const double thresh = std::numeric_limits<double>::epsilon() * k * smax;
+        std::vector<double> x(k, 0.0);
+        for (int i = 0; i < k; ++i) {
+            const double lam = A[i * k + i];
+            if (std::abs(lam) <= thresh) continue;
+            double proj = 0; for (int r = 0; r < k; ++r) proj += V[r * k + i] * b[r];
+            for (int r = 0; r < k; ++r) x[r] += V[r * k + i] * proj / lam;
+        }
+        return x;
+    }
+    void constructGuess() {
+        const size_t s = hist.size();
+        if (u.n != len()) u.alloc(len(), true);
+        if (method == 0 || s == 0) { VF_CUDA(cudaMemsetAsync(u.p, 0, sizeof(double) * len(), mg->ctx.stream)); uValid = true; return; }
+        if (method == 1) { // InitGenFD (:95-100)
+            VF_CUDA(cudaMemcpyAsync(u.p, hist[0]->p, sizeof(double) * len(), cudaMemcpyDeviceToDevice, mg->ctx.stream));
+            if (s == 2) { launch_scale(mg->ctx, (long long)len(), 2.0, u.p); launch_axpy(mg->ctx, (long long)len(), -1.0, hist[1]->p, u.p); }
+            if (s > 2) throw std::runtime_error("Unimplemented");
+            uValid = true; return;
+        }
+        // InitGenSubspace (:110-147): solve A c = b, g = sum c_i u_i on the attached nodes, zero above
+        const int k = (int)s;
+        std::vector<double> A((size_t)k * k, 0.0), b(k, 0.0);
+        if (w.n != len()) w.alloc(len(), true);
+        for (int j = 0; j < k; ++j) {
+            b[j] = maskedDot(hist[j]->p, f.p);
+            launch_apply_l0(mg->ctx, sim->g, sim->K0p, hist[j]->p, sim->E.p, nullptr, nullptr, w.p, APPLY_SET, nullptr, nullptr);
+            for (int i = j; i < k; ++i) A[i * k + j] = A[j * k + i] = maskedDot(hist[i]->p, w.p);
+        }
+        const std::vector<double> c = solveSymmetricPinv(A, b, k);
+        VF_CUDA(cudaMemsetAsync(u.p, 0, sizeof(double) * len(), mg->ctx.stream));
+        for (int i = 0; i < k; ++i) launch_axpy(mg->ctx, (long long)len(), c[i], hist[i]->p, u.p);
+        launch_detached_zero(mg->ctx, sim->g, u.p);
+        uValid = true;
+    }
+};
+
+extern "C" {
+int vf_lbl_create(vf_mg *mg, vf_lbl **out) {
+    VF_TRY auto l = std::make_unique<vf_lbl>(); l->mg = mg; l->sim = mg->sim;
+    l->scalar.alloc(1, true); l->scratch.alloc(reduce_scratch_doubles(), true);
+    VF_CUDA(cudaMallocHost(&l->hostScalar, sizeof(double)));
+    *out = l.release(); VF_CATCH
+}
+int vf_lbl_destroy(vf_lbl *l) { VF_TRY if (l) { cudaStreamSynchronize(l->mg->ctx.stream); delete l; } VF_CATCH }
+int vf_lbl_select_init_method(vf_lbl *l, const char *method) { // selectInitMethod (:214-220)
+    VF_TRY const std::string m(method);
+    if (m == "zero") { l->method = 0; l->maxHist = 0; }
+    else if (m == "constant") { l->method = 1; l->maxHist = 1; }
+    else if (m == "fd") { l->method = 1; l->maxHist = 2; }
+    else if (m.substr(0, 2) == "N=") { l->method = 2; l->maxHist = (size_t)std::stoi(m.substr(2)); }
+    else throw std::runtime_error("Unrecognized method " + m);
+    l->hist.clear(); VF_CATCH
+}
+// LayerByLayerEvaluator::run (:223-296)
+int vf_lbl_run(vf_lbl *l, int zeroInit, int64_t layerIncrement, int maxIter, double tol, int mgIt, int mgSmooth, int fmg, vf_lbl_callback cb, void *user) {
+    VF_TRY
+    vf_mg &mg = *l->mg; vf_sim &sim = *l->sim;
+    const int64_t numLayers = sim.ne[1];
+    const size_t len = l->len();
+    if (layerIncrement < 1) throw std::runtime_error("layerIncrement must be positive");
+    l->uValid = false;
+    if (!zeroInit && l->uFullValid) { if (l->u.n != len) l->u.alloc(len, false); VF_CUDA(cudaMemcpyAsync(l->u.p, l->uFull.p, sizeof(double) * len, cudaMemcpyDeviceToDevice, mg.ctx.stream)); l->uValid = true; }
+    l->hist.clear();                                           // m_initGen->reset() (:237)
+    l->layersAccumulated = 0; l->totalCompliance = 0; l->layerIters.clear();
+    l->totalGrad.alloc(sim.g.numElems, true);
+    if (int rc = vf_mg_set_mask_layer(&mg, numLayers)) return rc; // (:244)
+    if (l->f.n != len) l->f.alloc(len, true);
+    sim_build_load_dev(sim, l->f.p);                           // (:245)
+    for (int64_t layer = numLayers; layer > 0; layer -= std::min(layerIncrement, layer)) {
+        if (layer < numLayers) {
+            if (int rc = vf_mg_decrement_mask(&mg, (int)layerIncrement)) return rc;               // (:250)
+            const double g2 = sim.gravity[0] * sim.gravity[0] + sim.gravity[1] * sim.gravity[1] + sim.gravity[2] * sim.gravity[2];
+            if (g2 == 0 || std::abs(g2 - sim.gravity[1] * sim.gravity[1]) > 1e-10) throw std::runtime_error("Unexpected gravity vector");
+            launch_self_weight_load(mg.ctx, sim.g, sim.rho.p, sim.gravity, sim.elemVolume(), l->f.p, (int)layer, (int)(layer + layerIncrement), -1.0); // (:252)
+        }
+        if (layer < numLayers || !l->uValid) l->constructGuess();                                  // (:259-260)
+        try {
+            mg_pcg(mg, l->u.p, l->f.p, maxIter, tol, mgIt, mgSmooth, fmg != 0, /* dirichletAlreadySatisfied */ true, nullptr, nullptr); // (:265)
+        } catch (const std::exception &e) { throw std::runtime_error(std::string("PCG exception ") + e.what() + " at l = " + std::to_string(layer)); }
+        l->layerIters.push_back(mg.lastIters);
+        const double compliance = l->maskedDot(l->f.p, l->u.p);                                    // (:273)
+        if (cb) cb(layer, compliance, mg.lastIters, user);
+        l->totalCompliance += compliance;
+        launch_compliance_gradient(mg.ctx, sim.g, sim.K0p, l->u.p, sim.rho.p, l->totalGrad.p, sim.law, sim.E0, sim.Emin, sim.gamma, sim.q, sim.gravity, sim.elemVolume(), true); // (:283)
+        ++l->layersAccumulated;
+        if (layer == numLayers) { if (l->uFull.n != len) l->uFull.alloc(len, false); VF_CUDA(cudaMemcpyAsync(l->uFull.p, l->u.p, sizeof(double) * len, cudaMemcpyDeviceToDevice, mg.ctx.stream)); l->uFullValid = true; }
+        if (layer >= layerIncrement) l->addToHistory();                                            // finalizeLayer (:290-294)
+    }
+    VF_CUDA(cudaStreamSynchronize(mg.ctx.stream));
+    VF_CATCH
+}
+int vf_lbl_objective(vf_lbl *l, double *out) { *out = 0.5 * l->totalCompliance / double(l->layersAccumulated); return 0; } // (:299)
+int vf_lbl_gradient(vf_lbl *l, double *g) { // (:300)
+    VF_TRY std::vector<double> h(l->sim->g.numElems); d2h(h.data(), l->totalGrad.p, h.size(), l->mg->ctx.stream);
+    for (size_t i = 0; i < h.size(); ++i) g[i] = h[i] / double(l->layersAccumulated); VF_CATCH
+}
+}

@@ -1,0 +1,191 @@
+// vf_internal.cuh -- shared declarations for the CUDA side of libvoxelfem_b200.
+// Internal to the library; the public surface is include/voxelfem_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace vf {
+
+// ---------------------------------------------------------------------------
+// Grid descriptor, passed to kernels by value.
+// 2D grids are embedded with a leading dummy axis: nn = {1, nx, ny}, so node (x, y) has
+// flat index x*ny + y exactly as in the reference (NDVector.hh:256-264) and the fastest
+// axis is always embedded axis 2.
+// ---------------------------------------------------------------------------
+struct GridDesc {
+    int N;              // 2 or 3
+    int nn[3];          // nodes per embedded axis
+    int ne[3];          // elements per embedded axis (1 along the dummy axis in 2D)
+    long long ns[3];    // node strides
+    long long es[3];    // element strides
+    long long numNodes, numElems;
+    int bd;             // embedded build-direction axis (reference axis 1): 1 in 3D, 2 in 2D
+    int nActive;        // non-detached node layers along bd (nondetachedNodesPerDim, TensorProductSimulator.hh:371-375)
+    int neActive;       // non-masked element layers along bd (nonmaskedElementsPerDim, :377-381)
+};
+
+template<int N> struct Dims {
+    static constexpr int NPE = 1 << N;       // nodes per element
+    static constexpr int KE  = N * NPE;      // element matrix size
+    static constexpr int NS  = (N == 3) ? 27 : 9; // stencil slots
+    static constexpr int A0  = 3 - N;        // first active embedded axis
+};
+
+// Full-density element stiffness matrix, passed by value (__grid_constant__) so that its
+// entries become constant-bank operands of the DFMAs.
+struct K0Param { double v[24 * 24]; };
+
+
+// Colour (parity class) description for one pass of the multicoloured smoother
+// (visitNodesMulticolored, MultigridSolver.hh:408-442): nodes off + 2*i, i < cnt, per embedded axis.
+struct ColorDesc { int off[3]; int cnt[3]; };
+inline bool make_color(const GridDesc &g, int color, ColorDesc &col) {
+    const int A0 = 3 - g.N;
+    for (int a = 0; a < 3; ++a) { col.off[a] = 0; col.cnt[a] = 1; }
+    for (int a = A0; a < 3; ++a) {
+        col.off[a] = (color >> (2 - a)) & 1;
+        const int lim = (a == g.bd) ? g.nActive : g.nn[a];
+        if (lim - 1 - col.off[a] < 0) return false;
+        col.cnt[a] = (lim - 1 - col.off[a]) / 2 + 1;
+    }
+    return true;
+}
+
+#ifdef __CUDACC__
+template<int N> __device__ __forceinline__ void solve_block(const double (&M)[N][N], const double (&rhs)[N], double (&du)[N]);
+// Closed-form cofactor inverse, as Eigen's fixed-size Matrix::inverse() (MultigridSolver.hh:370)
+template<> __device__ __forceinline__ void solve_block<3>(const double (&M)[3][3], const double (&r)[3], double (&du)[3]) {
+    const double c00 = M[1][1] * M[2][2] - M[1][2] * M[2][1];
+    const double c01 = M[1][2] * M[2][0] - M[1][0] * M[2][2];
+    const double c02 = M[1][0] * M[2][1] - M[1][1] * M[2][0];
+    const double det = M[0][0] * c00 + M[0][1] * c01 + M[0][2] * c02;
+    const double id = 1.0 / det;
+    du[0] = (c00 * r[0] + (M[0][2] * M[2][1] - M[0][1] * M[2][2]) * r[1] + (M[0][1] * M[1][2] - M[0][2] * M[1][1]) * r[2]) * id;
+    du[1] = (c01 * r[0] + (M[0][0] * M[2][2] - M[0][2] * M[2][0]) * r[1] + (M[0][2] * M[1][0] - M[0][0] * M[1][2]) * r[2]) * id;
+    du[2] = (c02 * r[0] + (M[0][1] * M[2][0] - M[0][0] * M[2][1]) * r[1] + (M[0][0] * M[1][1] - M[0][1] * M[1][0]) * r[2]) * id;
+}
+template<> __device__ __forceinline__ void solve_block<2>(const double (&M)[2][2], const double (&r)[2], double (&du)[2]) {
+    const double id = 1.0 / (M[0][0] * M[1][1] - M[0][1] * M[1][0]);
+    du[0] = (M[1][1] * r[0] - M[0][1] * r[1]) * id;
+    du[1] = (M[0][0] * r[1] - M[1][0] * r[0]) * id;
+}
+// u_n += M^-1 (b - S') for free nodes; point Gauss-Seidel on the free components of partially
+// constrained nodes, direction following the sweep (MultigridSolver.hh:358-365).
+template<int N>
+__device__ __forceinline__ void gs_node_update(const double (&M)[N][N], const double (&rhs)[N], unsigned dm, bool forward, double (&du)[N]) {
+    if (dm == 0u) { solve_block<N>(M, rhs, du); return; }
+    #pragma unroll
+    for (int c = 0; c < N; ++c) du[c] = 0.0;
+    #pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int i = forward ? k : (N - 1 - k);
+        double s = rhs[i];
+        #pragma unroll
+        for (int j = 0; j < N; ++j) s -= M[i][j] * du[j];
+        du[i] = s * ((((dm >> i) & 1u) ? 0.0 : 1.0) / M[i][i]);
+    }
+}
+#endif
+
+// ---------------------------------------------------------------------------
+// Profiling categories (device time per kernel family; vf_prof_* in the C ABI)
+// ---------------------------------------------------------------------------
+enum ProfCat {
+    PC_APPLY_L0 = 0, PC_RESIDUAL_L0, PC_GS_L0, PC_APPLY_ST, PC_RESIDUAL_ST, PC_GS_ST, PC_RESTRICT, PC_PROLONG,
+    PC_COARSE_SOLVE, PC_VEC, PC_COARSEN, PC_TOPOPT, PC_OTHER, PC_COUNT
+};
+
+struct Profiler;
+struct LaunchCtx {
+    cudaStream_t stream = nullptr;
+    Profiler *prof = nullptr;
+};
+void prof_begin(const LaunchCtx &ctx, int cat, double units);
+void prof_end(const LaunchCtx &ctx, int cat);
+void count_launch();
+
+struct ProfScope {
+    const LaunchCtx &c; int cat;
+    ProfScope(const LaunchCtx &ctx, int cat_, double units) : c(ctx), cat(cat_) { prof_begin(c, cat, units); count_launch(); }
+    ~ProfScope() { prof_end(c, cat); }
+};
+
+inline void cuda_check(cudaError_t e, const char *what, const char *file, int line) {
+    if (e != cudaSuccess) {
+        throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" + std::to_string(line) + ")");
+    }
+}
+#define VF_CUDA(x) ::vf::cuda_check((x), #x, __FILE__, __LINE__)
+#define VF_KERNEL_CHECK() ::vf::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+
+// ---------------------------------------------------------------------------
+// Kernel launchers (defined in the .cu files named in the comments)
+// ---------------------------------------------------------------------------
+// --- vf_l0.cu: matrix-free level-0 operator (TPSStencils.hh:231-396, 431-728; MultigridSolver.hh:277-292, 347-378)
+enum ApplyMode { APPLY_SET = 0, APPLY_ADD = 1, APPLY_SUB = 2, APPLY_RESIDUAL = 3 };
+// out (=, +=, -=) K u   or   out = b - K u (APPLY_RESIDUAL);  dmask != nullptr zeroes Dirichlet components of out.
+// dotOut != nullptr additionally accumulates sum(u . out) over the non-detached nodes (deterministic two-stage reduction).
+void launch_apply_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
+                     const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch);
+// One colour pass of the block Gauss-Seidel smoother at level 0.
+void launch_gs_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, double *u, const double *b, const double *E,
+                  const uint8_t *dmask, int color, bool forward);
+
+// --- vf_stencil.cu: 3^N-point block-stencil levels (MultigridSolver.hh:323-334; TensorProductSimulator.hh:1500-1504)
+// Stencil layout: S[(slot * N*N + a*N + b) * numNodes + node]
+void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
+                          const uint8_t *dmask, double *out, int mode);
+void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
+                       const uint8_t *dmask, int color, bool forward);
+// Galerkin coarsening (MultigridSolver.hh:711-819): level-1 stencil from the fine Young's moduli and the 2^N
+// coarsened full-density matrices cK0[fi] (device, [fi][KE][KE]); level l >= 2 stencil as P^T A_{l-1} P.
+void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc);
+void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc);
+// Level-0 stencil straight from moduli (used for single-level direct solves): S = sum_e E_e K0 blocks.
+void launch_stencil_from_moduli_l0(const LaunchCtx &ctx, const GridDesc &g, const double *E, const double *K0dev, double *S);
+// Dense matrix of the free DOFs from a stencil: A[red(i)][red(j)], row-major n x n; redIdx[dof] = -1 for fixed DOFs.
+void launch_stencil_to_dense(const LaunchCtx &ctx, const GridDesc &g, const double *S, const int *redIdx, int nfree, double *A);
+void launch_symmetrize_lower(const LaunchCtx &ctx, double *A, int n);   // copy lower (row-major) triangle to upper
+void launch_dense_symv(const LaunchCtx &ctx, const double *A, int n, const double *x, double *y);
+void launch_gather_free(const LaunchCtx &ctx, const double *f, const int *freeDofs, int nfree, long long numNodes, int N, double *rhs);
+void launch_scatter_free(const LaunchCtx &ctx, const double *y, const int *freeDofs, int nfree, long long numNodes, int N, double *x);
+
+// --- vf_vec.cu: transfers and PCG vector kernels
+void launch_restrict(const LaunchCtx &ctx, const GridDesc &gf, const GridDesc &gc, const double *fine, double *coarse);
+void launch_prolong(const LaunchCtx &ctx, const GridDesc &gf, const GridDesc &gc, const double *coarse, double *fine, bool accumulate);
+void launch_zero_dirichlet(const LaunchCtx &ctx, const GridDesc &g, const uint8_t *dmask, double *u);
+void launch_enforce_dirichlet(const LaunchCtx &ctx, long long numNodes, int N, int ndir, const long long *nodes, const uint8_t *masks, const double *vals, double *u);
+void launch_masked_zero(const LaunchCtx &ctx, const GridDesc &g, double *u, int margin);
+void launch_detached_zero(const LaunchCtx &ctx, const GridDesc &g, double *u); // zero the detached node layers
+void launch_masked_copy(const LaunchCtx &ctx, const GridDesc &g, const double *in, double *out, int margin);
+// result[slot] = sum over non-detached nodes of a . b   (deterministic)
+void launch_masked_dot(const LaunchCtx &ctx, const GridDesc &g, const double *a, const double *b, double *result, double *scratch);
+// d = s + (num/den) d   (first == true: d = s)           (scaleAndAddInPlace, ParallelVectorOps.hh:76-84)
+void launch_cg_direction(const LaunchCtx &ctx, const GridDesc &g, const double *s, double *d, const double *num, const double *den, bool first);
+// alpha = rMr / dAd;  x += alpha d;  r -= alpha Ad;  rsq = ||r||^2      (MultigridSolver.hh:1134-1143)
+void launch_cg_update(const LaunchCtx &ctx, const GridDesc &g, double *x, const double *d, double *r, const double *Ad,
+                      const double *rMr, const double *dAd, double *rsq, double *scratch);
+size_t reduce_scratch_doubles();
+
+// --- vf_top.cu: optimization-layer kernels
+void launch_update_moduli(const LaunchCtx &ctx, const GridDesc &g, const double *rho, double *E, int law, double E0, double Emin, double gamma, double q, bool maskActive);
+void launch_zero_moduli_layers(const LaunchCtx &ctx, const GridDesc &g, double *E, int layerBegin, int layerEnd);
+void launch_compliance_gradient(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *rho, double *out,
+                                int law, double E0, double Emin, double gamma, double q, const double *gravity, double elemVol, bool accumulate);
+void launch_energy_density(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E, double *out);
+void launch_self_weight_load(const LaunchCtx &ctx, const GridDesc &g, const double *rho, const double *gravity, double elemVol, double *f, int layerBegin, int layerEnd, double sign);
+void launch_filter_smooth(const LaunchCtx &ctx, int N, const int *sizes, int radius, int type, const double *in, double *out);
+void launch_filter_project(const LaunchCtx &ctx, long long n, double beta, const double *in, double *out);
+void launch_filter_project_backprop(const LaunchCtx &ctx, long long n, double beta, const double *in, const double *vars, double *out);
+// OC update (OptimalityCriterion.hh:64-83): out = clamp(x0 * (dJ / (dc*lambda))^p, x0 -+ m, [0,1]); non-finite -> x0
+void launch_oc_update(const LaunchCtx &ctx, long long n, const double *x0, const double *dJ, const double *dc, double lambda, double m, double p, double *out);
+void launch_sum(const LaunchCtx &ctx, long long n, const double *x, double *result, double *scratch);
+void launch_fill(const LaunchCtx &ctx, long long n, double v, double *x);
+void launch_dot_plain(const LaunchCtx &ctx, long long n, const double *a, const double *b, double *result, double *scratch);
+void launch_axpy(const LaunchCtx &ctx, long long n, double a, const double *x, double *y); // y += a x
+void launch_scale(const LaunchCtx &ctx, long long n, double a, double *x);
+
+} // namespace vf

@@ -1,0 +1,391 @@
+// vf_stencil.cu -- coarse-level operators stored as 3^N-point block stencils (sm_100a).
+//
+// The reference keeps levels >= 2 as a block-CSC matrix ("blockK", TensorProductSimulator.hh:
+// 885-966; applied by CSCMatrix::applyTransposeParallel, MeshFEM SparseMatrices.hh:1613-1677,
+// smoothed with NodeSmoothStencilBlockK, MultigridSolver.hh:323-334), rebuilds the level-1 operator
+// on the fly from the fine moduli (MultigridSolver.hh:294-321, 475-499) and caches per-element
+// matrices at the coarsest level (:815-817).  On a structured grid all three are the same object: a
+// 3^N-point stencil of N x N blocks per node.  Here every level >= 1 stores that stencil in a
+// slot-major SoA layout  S[(slot*N*N + a*N + b) * numNodes + node]  so that warp lanes (consecutive
+// nodes along the fastest axis) read consecutive addresses.
+//
+// Galerkin coarsening (MultigridSolver.hh:711-819) is done directly on stencils: level 1 from the
+// fine moduli and the 2^N matrices coarsenedFineK0s[fi]; level l >= 2 as P^T A_{l-1} P.  Both are
+// algebraically identical to the reference's per-element recursion (sum over coarse elements of
+// Phi^T Ke Phi), differing only in floating-point summation order.
+#include "vf_internal.cuh"
+#include "vf_reduce.cuh"
+
+namespace vf {
+
+// acc[a] = sum_slot sum_b S[slot][a][b](n) * u_b(n + delta(slot));  Mdiag receives the centre block.
+template<int N, bool WANT_DIAG>
+__device__ __forceinline__ void stencil_row(const GridDesc &g, const double *__restrict__ S, const double *__restrict__ u,
+                                            int c0, int c1, int c2, long long n, double (&acc)[N], double (&Md)[N][N], double (&uself)[N]) {
+    constexpr int NS = Dims<N>::NS, A0 = Dims<N>::A0, NN = N * N;
+    const int cc[3] = {c0, c1, c2};
+    #pragma unroll
+    for (int a = 0; a < N; ++a) acc[a] = 0.0;
+    #pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        int d[3] = {0, 0, 0};
+        { int r = s;
+          #pragma unroll
+          for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+        bool valid = true; long long off = 0;
+        #pragma unroll
+        for (int a = A0; a < 3; ++a) {
+            const int q = cc[a] + d[a];
+            valid = valid && (q >= 0) && (q < g.nn[a]);
+            off += (long long)d[a] * g.ns[a];
+        }
+        double un[N];
+        #pragma unroll
+        for (int b = 0; b < N; ++b) un[b] = valid ? u[b * g.numNodes + n + off] : 0.0;
+        if (s == NS / 2) {
+            #pragma unroll
+            for (int b = 0; b < N; ++b) uself[b] = un[b];
+        }
+        if (valid) {
+            #pragma unroll
+            for (int a = 0; a < N; ++a) {
+                #pragma unroll
+                for (int b = 0; b < N; ++b) {
+                    const double sv = __ldg(S + (long long)(s * NN + a * N + b) * g.numNodes + n);
+                    acc[a] = fma(sv, un[b], acc[a]);
+                    if (WANT_DIAG && s == NS / 2) Md[a][b] = sv;
+                }
+            }
+        }
+    }
+}
+
+template<int N, int MODE>
+__global__ void __launch_bounds__(256)
+k_apply_stencil(const __grid_constant__ GridDesc g, const double *__restrict__ S, const double *__restrict__ u,
+                const double *__restrict__ b, const uint8_t *__restrict__ dmask, double *__restrict__ out) {
+    const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c1 = blockIdx.y * blockDim.y + threadIdx.y;
+    const int c0 = blockIdx.z * blockDim.z + threadIdx.z;
+    if (c2 >= g.nn[2] || c1 >= g.nn[1] || c0 >= g.nn[0]) return;
+    const long long n = (long long)c0 * g.ns[0] + (long long)c1 * g.ns[1] + c2;
+    const bool detached = ((g.bd == 1) ? c1 : c2) >= g.nActive;
+    if (detached) {
+        if (MODE == APPLY_SET) {
+            #pragma unroll
+            for (int c = 0; c < N; ++c) out[c * g.numNodes + n] = 0.0;
+        }
+        return;
+    }
+    double acc[N], Md[N][N], uself[N];
+    stencil_row<N, false>(g, S, u, c0, c1, c2, n, acc, Md, uself);
+    const unsigned dm = dmask ? dmask[n] : 0u;
+    #pragma unroll
+    for (int c = 0; c < N; ++c) {
+        double res;
+        if (MODE == APPLY_SET) res = acc[c];
+        else if (MODE == APPLY_ADD) res = out[c * g.numNodes + n] + acc[c];
+        else if (MODE == APPLY_SUB) res = out[c * g.numNodes + n] - acc[c];
+        else res = b[c * g.numNodes + n] - acc[c];
+        if ((dm >> c) & 1u) res = 0.0;
+        out[c * g.numNodes + n] = res;
+    }
+}
+
+void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
+                          const uint8_t *dmask, double *out, int mode) {
+    ProfScope ps(ctx, mode == APPLY_RESIDUAL ? PC_RESIDUAL_ST : PC_APPLY_ST, (double)g.numNodes);
+    dim3 block = (g.N == 3) ? dim3(32, 4, 2) : dim3(32, 8, 1);
+    dim3 grid((g.nn[2] + block.x - 1) / block.x, (g.nn[1] + block.y - 1) / block.y, (g.nn[0] + block.z - 1) / block.z);
+#define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) k_apply_stencil<NN_, M><<<grid, block, 0, ctx.stream>>>(g, S, u, b, dmask, out);
+    VF_CASE(3, APPLY_SET) VF_CASE(3, APPLY_ADD) VF_CASE(3, APPLY_SUB) VF_CASE(3, APPLY_RESIDUAL)
+    VF_CASE(2, APPLY_SET) VF_CASE(2, APPLY_ADD) VF_CASE(2, APPLY_SUB) VF_CASE(2, APPLY_RESIDUAL)
+#undef VF_CASE
+    VF_KERNEL_CHECK();
+}
+
+
+template<int N>
+__global__ void __launch_bounds__(256)
+k_gs_stencil(const __grid_constant__ GridDesc g, const __grid_constant__ ColorDesc col, const double *__restrict__ S,
+             double *__restrict__ u, const double *__restrict__ b, const uint8_t *__restrict__ dmask, int forward) {
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i1 = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i0 = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i2 >= col.cnt[2] || i1 >= col.cnt[1] || i0 >= col.cnt[0]) return;
+    const int c0 = col.off[0] + 2 * i0, c1 = col.off[1] + 2 * i1, c2 = col.off[2] + 2 * i2;
+    const long long n = (long long)c0 * g.ns[0] + (long long)c1 * g.ns[1] + c2;
+    const unsigned dm = dmask[n];
+    if (dm == (unsigned)((1 << N) - 1)) return;
+    double acc[N], M[N][N], uself[N], rhs[N], du[N];
+    stencil_row<N, true>(g, S, u, c0, c1, c2, n, acc, M, uself);
+    #pragma unroll
+    for (int c = 0; c < N; ++c) rhs[c] = b[c * g.numNodes + n] - acc[c];
+    gs_node_update<N>(M, rhs, dm, forward != 0, du);
+    #pragma unroll
+    for (int c = 0; c < N; ++c) u[c * g.numNodes + n] = uself[c] + du[c];
+}
+
+void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
+                       const uint8_t *dmask, int color, bool forward) {
+    ColorDesc col;
+    if (!make_color(g, color, col)) return;
+    ProfScope ps(ctx, PC_GS_ST, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
+    dim3 block = (g.N == 3) ? dim3(32, 4, 2) : dim3(32, 8, 1);
+    dim3 grid((col.cnt[2] + block.x - 1) / block.x, (col.cnt[1] + block.y - 1) / block.y, (col.cnt[0] + block.z - 1) / block.z);
+    if (g.N == 3) k_gs_stencil<3><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, forward ? 1 : 0);
+    else          k_gs_stencil<2><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, forward ? 1 : 0);
+    VF_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------
+// Galerkin coarsening
+// ---------------------------------------------------------------------------
+// Level-1 stencil from the fine moduli:  A_delta(n) = sum_{coarse e containing n and n+delta}
+//   sum_{fi} E_{child(e, fi)} * cK0[fi][ln_e(n) rows, ln_e(n+delta) cols]
+// (m_firstLevelCoarsenedStiffnessMatrix, MultigridSolver.hh:724-732, assembled as in :782-814).
+// One thread per (coarse node, slot); blockIdx.y = slot so (e, ln, m) are warp-uniform.
+template<int N>
+__global__ void __launch_bounds__(128)
+k_coarsen_from_moduli(const __grid_constant__ GridDesc gc, const __grid_constant__ GridDesc gf,
+                      const double *__restrict__ E, const double *__restrict__ cK0, double *__restrict__ Sc) {
+    constexpr int NPE = Dims<N>::NPE, KE = Dims<N>::KE, A0 = Dims<N>::A0, NN = N * N;
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (n >= gc.numNodes) return;
+    int c[3]; { long long r = n; c[2] = (int)(r % gc.nn[2]); r /= gc.nn[2]; c[1] = (int)(r % gc.nn[1]); c[0] = (int)(r / gc.nn[1]); }
+    int d[3] = {0, 0, 0};
+    { int r = s; for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+    double acc[NN];
+    #pragma unroll
+    for (int i = 0; i < NN; ++i) acc[i] = 0.0;
+    bool nbValid = true;
+    for (int a = A0; a < 3; ++a) { const int q = c[a] + d[a]; nbValid = nbValid && q >= 0 && q < gc.nn[a]; }
+    if (nbValid) {
+        for (int e = 0; e < NPE; ++e) { // incident coarse elements; node is local node ln == e
+            bool ok = true; int m = 0; int ec[3] = {0, 0, 0};
+            for (int a = A0; a < 3; ++a) {
+                const int ob = (e >> (2 - a)) & 1;
+                ec[a] = c[a] - ob;
+                ok = ok && ec[a] >= 0 && ec[a] < gc.ne[a];
+                const int mb = d[a] + ob;
+                ok = ok && (mb == 0 || mb == 1);
+                m |= (mb & 1) << (2 - a);
+            }
+            if (!ok) continue;
+            for (int fi = 0; fi < NPE; ++fi) {
+                long long ef = 0;
+                for (int a = A0; a < 3; ++a) ef += (long long)(2 * ec[a] + ((fi >> (2 - a)) & 1)) * gf.es[a];
+                const double Ef = __ldg(E + ef);
+                const double *Kb = cK0 + (size_t)fi * KE * KE;
+                #pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    #pragma unroll
+                    for (int b = 0; b < N; ++b) acc[a * N + b] = fma(Ef, __ldg(Kb + (N * e + a) * KE + (N * m + b)), acc[a * N + b]);
+                }
+            }
+        }
+    }
+    #pragma unroll
+    for (int i = 0; i < NN; ++i) Sc[(long long)(s * NN + i) * gc.numNodes + n] = acc[i];
+}
+
+void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc) {
+    ProfScope ps(ctx, PC_COARSEN, (double)gc.numNodes);
+    dim3 block(128), grid((unsigned)((gc.numNodes + 127) / 128), gc.N == 3 ? 27 : 9);
+    if (gc.N == 3) k_coarsen_from_moduli<3><<<grid, block, 0, ctx.stream>>>(gc, gf, E, cK0, Sc);
+    else           k_coarsen_from_moduli<2><<<grid, block, 0, ctx.stream>>>(gc, gf, E, cK0, Sc);
+    VF_KERNEL_CHECK();
+}
+
+// A^c_delta(n) = sum_{a, a' in {-1,0,1}^N} w(a) w(a') A^f_{eps}(2n + a),  eps = 2 delta + a' - a in {-1,0,1}^N,
+// w(a) = prod_d (1 - |a_d| / 2)   (= P^T A^f P with the multilinear P of MultigridSolver.hh:130-176).
+template<int N>
+__global__ void __launch_bounds__(128)
+k_coarsen_stencil(const __grid_constant__ GridDesc gc, const __grid_constant__ GridDesc gf,
+                  const double *__restrict__ Sf, double *__restrict__ Sc) {
+    constexpr int A0 = Dims<N>::A0, NN = N * N, NS = Dims<N>::NS;
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (n >= gc.numNodes) return;
+    int c[3]; { long long r = n; c[2] = (int)(r % gc.nn[2]); r /= gc.nn[2]; c[1] = (int)(r % gc.nn[1]); c[0] = (int)(r / gc.nn[1]); }
+    int d[3] = {0, 0, 0};
+    { int r = s; for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+    double acc[NN];
+    #pragma unroll
+    for (int i = 0; i < NN; ++i) acc[i] = 0.0;
+    bool nbValid = true;
+    for (int a = A0; a < 3; ++a) { const int q = c[a] + d[a]; nbValid = nbValid && q >= 0 && q < gc.nn[a]; }
+    if (nbValid) {
+        for (int sa = 0; sa < NS; ++sa) {          // a: fine node i = 2n + a
+            int av[3] = {0, 0, 0};
+            { int r = sa; for (int a = 2; a >= A0; --a) { av[a] = r % 3 - 1; r /= 3; } }
+            bool ok = true; long long fi = 0; double wa = 1.0;
+            for (int a = A0; a < 3; ++a) {
+                const int q = 2 * c[a] + av[a];
+                ok = ok && q >= 0 && q < gf.nn[a];
+                fi += (long long)q * gf.ns[a];
+                wa *= av[a] == 0 ? 1.0 : 0.5;
+            }
+            if (!ok) continue;
+            for (int sb = 0; sb < NS; ++sb) {      // a': fine node j = 2(n + delta) + a'
+                int bv[3] = {0, 0, 0};
+                { int r = sb; for (int a = 2; a >= A0; --a) { bv[a] = r % 3 - 1; r /= 3; } }
+                bool ok2 = true; int se = 0; double w = wa;
+                for (int a = A0; a < 3; ++a) {
+                    const int eps = 2 * d[a] + bv[a] - av[a];
+                    ok2 = ok2 && eps >= -1 && eps <= 1;
+                    const int qj = 2 * (c[a] + d[a]) + bv[a];
+                    ok2 = ok2 && qj >= 0 && qj < gf.nn[a];
+                    se = se * 3 + (eps + 1);
+                    w *= bv[a] == 0 ? 1.0 : 0.5;
+                }
+                if (!ok2) continue;
+                #pragma unroll
+                for (int i = 0; i < NN; ++i) acc[i] = fma(w, __ldg(Sf + (long long)(se * NN + i) * gf.numNodes + fi), acc[i]);
+            }
+        }
+    }
+    #pragma unroll
+    for (int i = 0; i < NN; ++i) Sc[(long long)(s * NN + i) * gc.numNodes + n] = acc[i];
+}
+
+void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc) {
+    ProfScope ps(ctx, PC_COARSEN, (double)gc.numNodes);
+    dim3 block(128), grid((unsigned)((gc.numNodes + 127) / 128), gc.N == 3 ? 27 : 9);
+    if (gc.N == 3) k_coarsen_stencil<3><<<grid, block, 0, ctx.stream>>>(gc, gf, Sf, Sc);
+    else           k_coarsen_stencil<2><<<grid, block, 0, ctx.stream>>>(gc, gf, Sf, Sc);
+    VF_KERNEL_CHECK();
+}
+
+// Level-0 stencil S = sum_e E_e * K0 blocks (assembled K in stencil form; used by the single-level
+// direct solve TPS::solve, TensorProductSimulator.hh:1198-1230).
+template<int N>
+__global__ void __launch_bounds__(128)
+k_stencil_from_moduli_l0(const __grid_constant__ GridDesc g, const double *__restrict__ E, const double *__restrict__ K0, double *__restrict__ S) {
+    constexpr int NPE = Dims<N>::NPE, KE = Dims<N>::KE, A0 = Dims<N>::A0, NN = N * N;
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (n >= g.numNodes) return;
+    int c[3]; { long long r = n; c[2] = (int)(r % g.nn[2]); r /= g.nn[2]; c[1] = (int)(r % g.nn[1]); c[0] = (int)(r / g.nn[1]); }
+    int d[3] = {0, 0, 0};
+    { int r = s; for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+    double acc[NN];
+    #pragma unroll
+    for (int i = 0; i < NN; ++i) acc[i] = 0.0;
+    for (int e = 0; e < NPE; ++e) {
+        bool ok = true; int m = 0; long long ei = 0;
+        for (int a = A0; a < 3; ++a) {
+            const int ob = (e >> (2 - a)) & 1;
+            const int ec = c[a] - ob;
+            ok = ok && ec >= 0 && ec < g.ne[a];
+            ei += (long long)ec * g.es[a];
+            const int mb = d[a] + ob;
+            ok = ok && (mb == 0 || mb == 1);
+            m |= (mb & 1) << (2 - a);
+        }
+        if (!ok) continue;
+        const double Ee = __ldg(E + ei);
+        #pragma unroll
+        for (int a = 0; a < N; ++a) {
+            #pragma unroll
+            for (int b = 0; b < N; ++b) acc[a * N + b] = fma(Ee, __ldg(K0 + (N * e + a) * KE + (N * m + b)), acc[a * N + b]);
+        }
+    }
+    #pragma unroll
+    for (int i = 0; i < NN; ++i) S[(long long)(s * NN + i) * g.numNodes + n] = acc[i];
+}
+
+void launch_stencil_from_moduli_l0(const LaunchCtx &ctx, const GridDesc &g, const double *E, const double *K0dev, double *S) {
+    ProfScope ps(ctx, PC_COARSEN, (double)g.numNodes);
+    dim3 block(128), grid((unsigned)((g.numNodes + 127) / 128), g.N == 3 ? 27 : 9);
+    if (g.N == 3) k_stencil_from_moduli_l0<3><<<grid, block, 0, ctx.stream>>>(g, E, K0dev, S);
+    else          k_stencil_from_moduli_l0<2><<<grid, block, 0, ctx.stream>>>(g, E, K0dev, S);
+    VF_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------
+// Coarsest-level dense system (replaces m_assembleStiffnessMatrix + rowColRemoval + CHOLMOD,
+// TensorProductSimulator.hh:834-865, 1198-1230)
+// ---------------------------------------------------------------------------
+__global__ void k_stencil_to_dense(const __grid_constant__ GridDesc g, const double *__restrict__ S, const int *__restrict__ red, int nfree, double *__restrict__ A) {
+    const int N = g.N, NN = N * N, NS = (N == 3) ? 27 : 9, A0 = 3 - N;
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (n >= g.numNodes) return;
+    int c[3]; { long long r = n; c[2] = (int)(r % g.nn[2]); r /= g.nn[2]; c[1] = (int)(r % g.nn[1]); c[0] = (int)(r / g.nn[1]); }
+    int d[3] = {0, 0, 0};
+    { int r = s; for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+    long long m = 0;
+    for (int a = 0; a < 3; ++a) { const int q = c[a] + d[a]; if (q < 0 || q >= g.nn[a]) return; m += (long long)q * g.ns[a]; }
+    (void)NS;
+    for (int a = 0; a < N; ++a) {
+        const int ri = red[n * N + a]; if (ri < 0) continue;
+        for (int b = 0; b < N; ++b) {
+            const int rj = red[m * N + b]; if (rj < 0) continue;
+            A[(size_t)ri * nfree + rj] = S[(long long)(s * NN + a * N + b) * g.numNodes + n];
+        }
+    }
+}
+void launch_stencil_to_dense(const LaunchCtx &ctx, const GridDesc &g, const double *S, const int *redIdx, int nfree, double *A) {
+    ProfScope ps(ctx, PC_COARSEN, (double)g.numNodes);
+    dim3 block(128), grid((unsigned)((g.numNodes + 127) / 128), g.N == 3 ? 27 : 9);
+    k_stencil_to_dense<<<grid, block, 0, ctx.stream>>>(g, S, redIdx, nfree, A);
+    VF_KERNEL_CHECK();
+}
+
+__global__ void k_symmetrize_lower(double *A, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i < n && j < n && j > i) A[(size_t)i * n + j] = A[(size_t)j * n + i];
+}
+void launch_symmetrize_lower(const LaunchCtx &ctx, double *A, int n) {
+    ProfScope ps(ctx, PC_COARSEN, (double)n * n);
+    dim3 block(32, 8), grid((n + 31) / 32, (n + 7) / 8);
+    k_symmetrize_lower<<<grid, block, 0, ctx.stream>>>(A, n);
+    VF_KERNEL_CHECK();
+}
+
+// y = A x for a dense symmetric row-major A: one warp per row, coalesced along the row.
+__global__ void __launch_bounds__(256) k_dense_symv(const double *__restrict__ A, int n, const double *__restrict__ x, double *__restrict__ y) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const double *row = A + (size_t)warp * n;
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32) s = fma(__ldg(row + j), x[j], s);
+    s = warp_sum(s);
+    if (lane == 0) y[warp] = s;
+}
+void launch_dense_symv(const LaunchCtx &ctx, const double *A, int n, const double *x, double *y) {
+    ProfScope ps(ctx, PC_COARSE_SOLVE, (double)n * n);
+    if (n == 0) return;
+    dim3 block(256), grid((unsigned)(((size_t)n * 32 + 255) / 256));
+    k_dense_symv<<<grid, block, 0, ctx.stream>>>(A, n, x, y);
+    VF_KERNEL_CHECK();
+}
+
+__global__ void k_gather_free(const double *__restrict__ f, const int *__restrict__ freeDofs, int nfree, long long numNodes, int N, double *__restrict__ rhs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nfree) return;
+    const int dof = freeDofs[i];
+    rhs[i] = f[(long long)(dof % N) * numNodes + dof / N];
+}
+void launch_gather_free(const LaunchCtx &ctx, const double *f, const int *freeDofs, int nfree, long long numNodes, int N, double *rhs) {
+    ProfScope ps(ctx, PC_COARSE_SOLVE, (double)nfree);
+    if (nfree == 0) return;
+    k_gather_free<<<(nfree + 255) / 256, 256, 0, ctx.stream>>>(f, freeDofs, nfree, numNodes, N, rhs);
+    VF_KERNEL_CHECK();
+}
+__global__ void k_scatter_free(const double *__restrict__ y, const int *__restrict__ freeDofs, int nfree, long long numNodes, int N, double *__restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nfree) return;
+    const int dof = freeDofs[i];
+    x[(long long)(dof % N) * numNodes + dof / N] = y[i];
+}
+void launch_scatter_free(const LaunchCtx &ctx, const double *y, const int *freeDofs, int nfree, long long numNodes, int N, double *x) {
+    ProfScope ps(ctx, PC_COARSE_SOLVE, (double)nfree);
+    if (nfree == 0) return;
+    k_scatter_free<<<(nfree + 255) / 256, 256, 0, ctx.stream>>>(y, freeDofs, nfree, numNodes, N, x);
+    VF_KERNEL_CHECK();
+}
+
+} // namespace vf
