@@ -108,6 +108,7 @@ def lib():
         "vf_prof_num_categories": (ci, []),
         "vf_prof_name": (C.c_char_p, [ci]),
         "vf_prof_get": (ci, [vp, ci, C.POINTER(i64), C.POINTER(cd), C.POINTER(cd)]),
+        "vf_mg_time_op": (ci, [vp, ci, ci, ci, ci, C.POINTER(cd)]),
         "vf_filter_smooth": (ci, [ci, _ip, ci, ci, _dp, _dp]),
         "vf_filter_project": (ci, [i64, cd, _dp, _dp]),
         "vf_filter_project_backprop": (ci, [i64, cd, _dp, _dp, _dp]),
@@ -443,6 +444,13 @@ class MG:
 
     def stream(self): return self.L.vf_mg_stream(self.h)
     def synchronize(self): _check(self.L.vf_mg_synchronize(self.h))
+
+    OPS = {"smooth": 0, "residual": 1, "apply": 2, "restrict": 3, "prolong": 4, "coarse_solve": 5, "vcycle": 6, "fmg": 7}
+
+    def time_op(self, op, level=0, reps=10, nsmooth=1):
+        ms = C.c_double()
+        _check(self.L.vf_mg_time_op(self.h, self.OPS[op], level, reps, nsmooth, C.byref(ms)))
+        return ms.value
 
     def prof_enable(self, on=True): _check(self.L.vf_prof_enable(self.h, int(on)))
     def prof_reset(self): _check(self.L.vf_prof_reset(self.h))

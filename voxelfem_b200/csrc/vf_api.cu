@@ -106,6 +106,16 @@ static GridDesc make_grid(int N, const int64_t *ne) {
     g.numNodes = (long long)g.nn[0] * g.nn[1] * g.nn[2];
     g.numElems = (long long)g.ne[0] * g.ne[1] * g.ne[2];
     g.nActive = g.nn[g.bd]; g.neActive = g.ne[g.bd];
+    long long base = 0;
+    for (int c = 0; c < 8; ++c) {
+        long long cnt = 1;
+        for (int a = 0; a < 3; ++a) {
+            const int off = (c >> (2 - a)) & 1;
+            g.ccnt[c][a] = (g.nn[a] - 1 - off >= 0) ? (g.nn[a] - 1 - off) / 2 + 1 : 0;
+            cnt *= g.ccnt[c][a];
+        }
+        g.cbase[c] = base; base += cnt;
+    }
     return g;
 }
 static void set_mask_limits(GridDesc &g, int firstMasked, int firstDetached) {
@@ -527,7 +537,8 @@ void mg_pcg(vf_mg &mg, double *x, const double *b, int maxIter, double tol, int 
         launch_masked_dot(mg.ctx, g, r, s, sc + cur, mg.scratch.p);                      // r_Minv_r (:1124)
         launch_cg_direction(mg.ctx, g, s, mg.d.p, sc + cur, sc + old, first);           // d = s + beta d (:1125-1126)
         first = false;
-        mg_apply_K(mg, 0, mg.d.p, nullptr, mg.Ad.p, APPLY_SET, true, sc + SC_DAD);      // Ad = K d, zero Dirichlet, d.Ad (:1129-1134)
+        mg_apply_K(mg, 0, mg.d.p, nullptr, mg.Ad.p, APPLY_SET, true);                   // Ad = K d, zero Dirichlet (:1129-1130)
+        launch_masked_dot(mg.ctx, g, mg.d.p, mg.Ad.p, sc + SC_DAD, mg.scratch.p);        // d . Ad (:1134)
         launch_cg_update(mg.ctx, g, x, mg.d.p, r, mg.Ad.p, sc + cur, sc + SC_DAD, sc + SC_RSQ, mg.scratch.p); // (:1134-1143)
         rsq = read_scalar(mg, SC_RSQ);
         if (std::isnan(rsq)) throw std::logic_error("NaN encountered at iteration" + std::to_string(i));
@@ -881,8 +892,10 @@ int vf_mg_get_stencil(vf_mg *mg, int l, double *out) {
     const GridDesc &g = mg->grid(l); const int ns = mg->N == 3 ? 27 : 9, NN = mg->N * mg->N;
     std::vector<double> h((size_t)g.numNodes * ns * NN);
     d2h(h.data(), mg->lv[l]->S.p, h.size(), mg->ctx.stream);
-    for (long long n = 0; n < g.numNodes; ++n) for (int s = 0; s < ns; ++s) for (int i = 0; i < NN; ++i)
-        out[((size_t)n * ns + s) * NN + i] = h[(size_t)(s * NN + i) * g.numNodes + n];
+    for (int c0 = 0; c0 < g.nn[0]; ++c0) for (int c1 = 0; c1 < g.nn[1]; ++c1) for (int c2 = 0; c2 < g.nn[2]; ++c2) {
+        const long long n = (long long)c0 * g.ns[0] + (long long)c1 * g.ns[1] + c2, p = stencil_pos(g, c0, c1, c2);
+        for (int s = 0; s < ns; ++s) for (int i = 0; i < NN; ++i) out[((size_t)n * ns + s) * NN + i] = h[(size_t)(s * NN + i) * g.numNodes + p];
+    }
     VF_CATCH
 }
 int vf_mg_coarse_solve(vf_mg *mg, const double *f, double *x) {
@@ -961,6 +974,38 @@ int vf_dev_memset_zero(double *dev, size_t n) { VF_TRY VF_CUDA(cudaMemset(dev, 0
 void *vf_mg_stream(vf_mg *mg) { return (void *)mg->ctx.stream; }
 int vf_mg_synchronize(vf_mg *mg) { VF_TRY VF_CUDA(cudaStreamSynchronize(mg->ctx.stream)); VF_CATCH }
 
+// Device time of `reps` back-to-back repetitions of one multigrid operation on the level's own x/b/r fields
+// (CUDA events on the solver's stream).  op: 0 one smoothing sweep (2^N colour passes), 1 residual, 2 applyK,
+// 3 restrict (level -> level+1), 4 prolong-add (level+1 -> level), 5 coarse solve, 6 V-cycle from `level`, 7 FMG cycle.
+int vf_mg_time_op(vf_mg *mg, int op, int level, int reps, int nsmooth, double *ms_per_rep) {
+    VF_TRY
+    mg_sync_level_masks(*mg); mg_update_stiffness(*mg);
+    cudaEvent_t e0, e1; VF_CUDA(cudaEventCreate(&e0)); VF_CUDA(cudaEventCreate(&e1));
+    const bool profWas = mg->sim->prof.enabled; mg->sim->prof.enabled = false;
+    auto body = [&]() {
+        switch (op) {
+            case 0: mg_smooth(*mg, level, lx(*mg, level), lb(*mg, level), true); break;
+            case 1: mg_residual(*mg, level, lx(*mg, level), lb(*mg, level), lr(*mg, level)); break;
+            case 2: mg_apply_K(*mg, level, lx(*mg, level), nullptr, lr(*mg, level), APPLY_SET, true); break;
+            case 3: launch_restrict(mg->ctx, mg->grid(level), mg->grid(level + 1), lr(*mg, level), lb(*mg, level + 1)); break;
+            case 4: launch_prolong(mg->ctx, mg->grid(level), mg->grid(level + 1), lx(*mg, level + 1), lx(*mg, level), true); break;
+            case 5: mg_coarse_solve(*mg, lb(*mg, mg->numLevels() - 1), lx(*mg, mg->numLevels() - 1)); break;
+            case 6: mg_vcycle(*mg, level, nsmooth, true); break;
+            case 7: mg_fmg(*mg, 0, nsmooth, true); break;
+            default: throw std::runtime_error("unknown op");
+        }
+    };
+    body(); // warm-up
+    VF_CUDA(cudaEventRecord(e0, mg->ctx.stream));
+    for (int i = 0; i < reps; ++i) body();
+    VF_CUDA(cudaEventRecord(e1, mg->ctx.stream));
+    VF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; VF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_rep = ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    mg->sim->prof.enabled = profWas;
+    VF_CATCH
+}
 int vf_prof_enable(vf_mg *mg, int enable) { mg->sim->prof.enabled = enable != 0; return 0; }
 int vf_prof_reset(vf_mg *mg) { VF_TRY mg->sim->prof.reset(); VF_CATCH }
 int vf_prof_num_categories(void) { return PC_COUNT; }

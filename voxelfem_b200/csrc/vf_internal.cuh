@@ -25,7 +25,23 @@ struct GridDesc {
     int bd;             // embedded build-direction axis (reference axis 1): 1 in 3D, 2 in 2D
     int nActive;        // non-detached node layers along bd (nondetachedNodesPerDim, TensorProductSimulator.hh:371-375)
     int neActive;       // non-masked element layers along bd (nonmaskedElementsPerDim, :377-381)
+    // Colour-major node numbering used by the stored stencils of the coarse levels: the nodes of parity class
+    // (colour) c occupy positions cbase[c] .. cbase[c] + prod(ccnt[c]) in row-major order of (i_a >> 1).  A colour
+    // pass of the smoother then streams its stencil rows from contiguous memory.
+    long long cbase[8];
+    int ccnt[8][3];
 };
+
+#if defined(__CUDACC__)
+#define VF_HD __host__ __device__ __forceinline__
+#else
+#define VF_HD inline
+#endif
+// position of node (c0, c1, c2) in the colour-major numbering
+VF_HD long long stencil_pos(const GridDesc &g, int c0, int c1, int c2) {
+    const int col = ((c0 & 1) << 2) | ((c1 & 1) << 1) | (c2 & 1);
+    return g.cbase[col] + ((long long)(c0 >> 1) * g.ccnt[col][1] + (c1 >> 1)) * g.ccnt[col][2] + (c2 >> 1);
+}
 
 template<int N> struct Dims {
     static constexpr int NPE = 1 << N;       // nodes per element

@@ -6,8 +6,8 @@
 // on the fly from the fine moduli (MultigridSolver.hh:294-321, 475-499) and caches per-element
 // matrices at the coarsest level (:815-817).  On a structured grid all three are the same object: a
 // 3^N-point stencil of N x N blocks per node.  Here every level >= 1 stores that stencil in a
-// slot-major SoA layout  S[(slot*N*N + a*N + b) * numNodes + node]  so that warp lanes (consecutive
-// nodes along the fastest axis) read consecutive addresses.
+// slot-major SoA layout  S[(slot*N*N + a*N + b) * numNodes + pos(node)]  where pos() is the colour-major node
+// numbering of GridDesc (stencil_pos): a colour pass of the smoother streams its rows contiguously.
 //
 // Galerkin coarsening (MultigridSolver.hh:711-819) is done directly on stencils: level 1 from the
 // fine moduli and the 2^N matrices coarsenedFineK0s[fi]; level l >= 2 as P^T A_{l-1} P.  Both are
@@ -18,123 +18,158 @@
 
 namespace vf {
 
-// acc[a] = sum_slot sum_b S[slot][a][b](n) * u_b(n + delta(slot));  Mdiag receives the centre block.
-template<int N, bool WANT_DIAG>
-__device__ __forceinline__ void stencil_row(const GridDesc &g, const double *__restrict__ S, const double *__restrict__ u,
-                                            int c0, int c1, int c2, long long n, double (&acc)[N], double (&Md)[N][N], double (&uself)[N]) {
+// Slot-parallel stencil row evaluation.  A thread block handles 32 consecutive nodes (in colour-major order)
+// with one warp-row per stencil slot: thread (tx, s) loads the N x N block S[s](node tx) (coalesced across tx)
+// and the neighbour displacement, and contributes S u to a shared-memory reduction over the 3^N slots.  Every
+// thread issues a single batch of independent loads, so the latency chain of a row is one memory round trip
+// instead of 3^N dependent ones -- this is what matters on the small coarse levels that sit on the critical
+// path of every V-cycle, while the large level 1 streams its 1944 B/node of stencil at HBM rate.
+constexpr int kSlotNodes = 16; // nodes per block (16 consecutive doubles = 128 B = 4 full sectors per load)
+template<int N>
+struct SlotShared {
+    double red[N][Dims<N>::NS][kSlotNodes];
+    double Md[N * N][kSlotNodes];
+    double us[N][kSlotNodes];
+    double bs[N][kSlotNodes];
+    unsigned dm[kSlotNodes];
+};
+
+// coordinates of the q-th node: either of one colour pass (col != nullptr) or of the whole grid in colour-major order
+template<int N>
+__device__ __forceinline__ bool slot_node_coords(const GridDesc &g, const ColorDesc *col, long long q, int (&c)[3]) {
+    if (col) {
+        const long long tot = (long long)col->cnt[0] * col->cnt[1] * col->cnt[2];
+        if (q >= tot) return false;
+        const int i2 = (int)(q % col->cnt[2]); q /= col->cnt[2];
+        const int i1 = (int)(q % col->cnt[1]); const int i0 = (int)(q / col->cnt[1]);
+        c[0] = col->off[0] + 2 * i0; c[1] = col->off[1] + 2 * i1; c[2] = col->off[2] + 2 * i2;
+        return true;
+    }
+    if (q >= g.numNodes) return false;
+    int cc = 0;
+    #pragma unroll
+    for (int k = 1; k < 8; ++k) cc += (q >= g.cbase[k]) ? 1 : 0;   // cbase is non-decreasing
+    long long idx = q - g.cbase[cc];
+    const int i2 = (int)(idx % g.ccnt[cc][2]); idx /= g.ccnt[cc][2];
+    const int i1 = (int)(idx % g.ccnt[cc][1]); const int i0 = (int)(idx / g.ccnt[cc][1]);
+    c[0] = 2 * i0 + ((cc >> 2) & 1); c[1] = 2 * i1 + ((cc >> 1) & 1); c[2] = 2 * i2 + (cc & 1);
+    return true;
+}
+
+template<int N, bool GS, int MODE>
+__global__ void __launch_bounds__(kSlotNodes * Dims<N>::NS)
+k_stencil_slots(const __grid_constant__ GridDesc g, const __grid_constant__ ColorDesc col, const double *__restrict__ S,
+                const double *uin, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
+                double *out, int forward) {
     constexpr int NS = Dims<N>::NS, A0 = Dims<N>::A0, NN = N * N;
-    const int cc[3] = {c0, c1, c2};
+    __shared__ SlotShared<N> sh;
+    const int tx = threadIdx.x, s = threadIdx.y;
+    const long long q = (long long)blockIdx.x * kSlotNodes + tx;
+    int c[3] = {0, 0, 0};
+    const bool inRange = slot_node_coords<N>(g, GS ? &col : nullptr, q, c);
+    const long long n = (long long)c[0] * g.ns[0] + (long long)c[1] * g.ns[1] + c[2];
+    const bool detached = inRange && (((g.bd == 1) ? c[1] : c[2]) >= g.nActive);
+    double acc[N];
     #pragma unroll
     for (int a = 0; a < N; ++a) acc[a] = 0.0;
-    #pragma unroll
-    for (int s = 0; s < NS; ++s) {
+    if (inRange && !detached) {
+        // stage b and the Dirichlet mask alongside the stencil loads so that the finalising warp has no global loads left
+        if (s < N && (GS || MODE == APPLY_RESIDUAL)) sh.bs[s][tx] = b[s * g.numNodes + n];
+        if (s == N) sh.dm[tx] = dmask ? dmask[n] : 0u;
         int d[3] = {0, 0, 0};
         { int r = s;
           #pragma unroll
           for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
         bool valid = true; long long off = 0;
         #pragma unroll
-        for (int a = A0; a < 3; ++a) {
-            const int q = cc[a] + d[a];
-            valid = valid && (q >= 0) && (q < g.nn[a]);
-            off += (long long)d[a] * g.ns[a];
-        }
-        double un[N];
-        #pragma unroll
-        for (int b = 0; b < N; ++b) un[b] = valid ? u[b * g.numNodes + n + off] : 0.0;
-        if (s == NS / 2) {
-            #pragma unroll
-            for (int b = 0; b < N; ++b) uself[b] = un[b];
-        }
+        for (int a = A0; a < 3; ++a) { const int qq = c[a] + d[a]; valid = valid && qq >= 0 && qq < g.nn[a]; off += (long long)d[a] * g.ns[a]; }
         if (valid) {
+            const long long p = stencil_pos(g, c[0], c[1], c[2]);
+            double un[N], sv[NN];
+            #pragma unroll
+            for (int k = 0; k < N; ++k) un[k] = uin[k * g.numNodes + n + off];
+            #pragma unroll
+            for (int k = 0; k < NN; ++k) sv[k] = __ldg(S + (long long)(s * NN + k) * g.numNodes + p);
             #pragma unroll
             for (int a = 0; a < N; ++a) {
                 #pragma unroll
-                for (int b = 0; b < N; ++b) {
-                    const double sv = __ldg(S + (long long)(s * NN + a * N + b) * g.numNodes + n);
-                    acc[a] = fma(sv, un[b], acc[a]);
-                    if (WANT_DIAG && s == NS / 2) Md[a][b] = sv;
-                }
+                for (int k = 0; k < N; ++k) acc[a] = fma(sv[a * N + k], un[k], acc[a]);
+            }
+            if (s == NS / 2) {
+                #pragma unroll
+                for (int k = 0; k < NN; ++k) sh.Md[k][tx] = sv[k];
+                #pragma unroll
+                for (int k = 0; k < N; ++k) sh.us[k][tx] = un[k];
             }
         }
     }
-}
-
-template<int N, int MODE>
-__global__ void __launch_bounds__(256)
-k_apply_stencil(const __grid_constant__ GridDesc g, const double *__restrict__ S, const double *__restrict__ u,
-                const double *__restrict__ b, const uint8_t *__restrict__ dmask, double *__restrict__ out) {
-    const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c1 = blockIdx.y * blockDim.y + threadIdx.y;
-    const int c0 = blockIdx.z * blockDim.z + threadIdx.z;
-    if (c2 >= g.nn[2] || c1 >= g.nn[1] || c0 >= g.nn[0]) return;
-    const long long n = (long long)c0 * g.ns[0] + (long long)c1 * g.ns[1] + c2;
-    const bool detached = ((g.bd == 1) ? c1 : c2) >= g.nActive;
+    #pragma unroll
+    for (int a = 0; a < N; ++a) sh.red[a][s][tx] = acc[a];
+    __syncthreads();
+    if (s < N) { // warp-row a = s sums the slot contributions of component a (fixed order -> deterministic)
+        double t = 0.0;
+        #pragma unroll
+        for (int k = 0; k < NS; ++k) t += sh.red[s][k][tx];
+        sh.red[s][0][tx] = t;
+    }
+    __syncthreads();
+    if (s != 0 || !inRange) return;
     if (detached) {
-        if (MODE == APPLY_SET) {
+        if (!GS && MODE == APPLY_SET) {
             #pragma unroll
-            for (int c = 0; c < N; ++c) out[c * g.numNodes + n] = 0.0;
+            for (int a = 0; a < N; ++a) out[a * g.numNodes + n] = 0.0;
         }
         return;
     }
-    double acc[N], Md[N][N], uself[N];
-    stencil_row<N, false>(g, S, u, c0, c1, c2, n, acc, Md, uself);
-    const unsigned dm = dmask ? dmask[n] : 0u;
-    #pragma unroll
-    for (int c = 0; c < N; ++c) {
-        double res;
-        if (MODE == APPLY_SET) res = acc[c];
-        else if (MODE == APPLY_ADD) res = out[c * g.numNodes + n] + acc[c];
-        else if (MODE == APPLY_SUB) res = out[c * g.numNodes + n] - acc[c];
-        else res = b[c * g.numNodes + n] - acc[c];
-        if ((dm >> c) & 1u) res = 0.0;
-        out[c * g.numNodes + n] = res;
+    const unsigned dm = sh.dm[tx];
+    if (GS) {
+        if (dm == (unsigned)((1 << N) - 1)) return; // hasFullDirichlet (MultigridSolver.hh:350)
+        double rhs[N], M[N][N], du[N];
+        #pragma unroll
+        for (int a = 0; a < N; ++a) {
+            rhs[a] = sh.bs[a][tx] - sh.red[a][0][tx];
+            #pragma unroll
+            for (int k = 0; k < N; ++k) M[a][k] = sh.Md[a * N + k][tx];
+        }
+        gs_node_update<N>(M, rhs, dm, forward != 0, du);
+        #pragma unroll
+        for (int a = 0; a < N; ++a) out[a * g.numNodes + n] = sh.us[a][tx] + du[a];
+    } else {
+        #pragma unroll
+        for (int a = 0; a < N; ++a) {
+            const double av = sh.red[a][0][tx];
+            double res;
+            if (MODE == APPLY_SET) res = av;
+            else if (MODE == APPLY_ADD) res = out[a * g.numNodes + n] + av;
+            else if (MODE == APPLY_SUB) res = out[a * g.numNodes + n] - av;
+            else res = sh.bs[a][tx] - av;
+            if ((dm >> a) & 1u) res = 0.0;
+            out[a * g.numNodes + n] = res;
+        }
     }
 }
 
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
                           const uint8_t *dmask, double *out, int mode) {
     ProfScope ps(ctx, mode == APPLY_RESIDUAL ? PC_RESIDUAL_ST : PC_APPLY_ST, (double)g.numNodes);
-    dim3 block = (g.N == 3) ? dim3(32, 4, 2) : dim3(32, 8, 1);
-    dim3 grid((g.nn[2] + block.x - 1) / block.x, (g.nn[1] + block.y - 1) / block.y, (g.nn[0] + block.z - 1) / block.z);
-#define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) k_apply_stencil<NN_, M><<<grid, block, 0, ctx.stream>>>(g, S, u, b, dmask, out);
+    ColorDesc col; make_color(g, 0, col);
+    dim3 block(kSlotNodes, g.N == 3 ? 27 : 9), grid((unsigned)((g.numNodes + kSlotNodes - 1) / kSlotNodes));
+#define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) k_stencil_slots<NN_, false, M><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, out, 1);
     VF_CASE(3, APPLY_SET) VF_CASE(3, APPLY_ADD) VF_CASE(3, APPLY_SUB) VF_CASE(3, APPLY_RESIDUAL)
     VF_CASE(2, APPLY_SET) VF_CASE(2, APPLY_ADD) VF_CASE(2, APPLY_SUB) VF_CASE(2, APPLY_RESIDUAL)
 #undef VF_CASE
     VF_KERNEL_CHECK();
 }
 
-
-template<int N>
-__global__ void __launch_bounds__(256)
-k_gs_stencil(const __grid_constant__ GridDesc g, const __grid_constant__ ColorDesc col, const double *__restrict__ S,
-             double *__restrict__ u, const double *__restrict__ b, const uint8_t *__restrict__ dmask, int forward) {
-    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i1 = blockIdx.y * blockDim.y + threadIdx.y;
-    const int i0 = blockIdx.z * blockDim.z + threadIdx.z;
-    if (i2 >= col.cnt[2] || i1 >= col.cnt[1] || i0 >= col.cnt[0]) return;
-    const int c0 = col.off[0] + 2 * i0, c1 = col.off[1] + 2 * i1, c2 = col.off[2] + 2 * i2;
-    const long long n = (long long)c0 * g.ns[0] + (long long)c1 * g.ns[1] + c2;
-    const unsigned dm = dmask[n];
-    if (dm == (unsigned)((1 << N) - 1)) return;
-    double acc[N], M[N][N], uself[N], rhs[N], du[N];
-    stencil_row<N, true>(g, S, u, c0, c1, c2, n, acc, M, uself);
-    #pragma unroll
-    for (int c = 0; c < N; ++c) rhs[c] = b[c * g.numNodes + n] - acc[c];
-    gs_node_update<N>(M, rhs, dm, forward != 0, du);
-    #pragma unroll
-    for (int c = 0; c < N; ++c) u[c * g.numNodes + n] = uself[c] + du[c];
-}
-
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
                        const uint8_t *dmask, int color, bool forward) {
     ColorDesc col;
     if (!make_color(g, color, col)) return;
-    ProfScope ps(ctx, PC_GS_ST, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
-    dim3 block = (g.N == 3) ? dim3(32, 4, 2) : dim3(32, 8, 1);
-    dim3 grid((col.cnt[2] + block.x - 1) / block.x, (col.cnt[1] + block.y - 1) / block.y, (col.cnt[0] + block.z - 1) / block.z);
-    if (g.N == 3) k_gs_stencil<3><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, forward ? 1 : 0);
-    else          k_gs_stencil<2><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, forward ? 1 : 0);
+    const long long tot = (long long)col.cnt[0] * col.cnt[1] * col.cnt[2];
+    ProfScope ps(ctx, PC_GS_ST, (double)tot);
+    dim3 block(kSlotNodes, g.N == 3 ? 27 : 9), grid((unsigned)((tot + kSlotNodes - 1) / kSlotNodes));
+    if (g.N == 3) k_stencil_slots<3, true, APPLY_SET><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, u, forward ? 1 : 0);
+    else          k_stencil_slots<2, true, APPLY_SET><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, u, forward ? 1 : 0);
     VF_KERNEL_CHECK();
 }
 
@@ -186,8 +221,9 @@ k_coarsen_from_moduli(const __grid_constant__ GridDesc gc, const __grid_constant
             }
         }
     }
+    const long long p = stencil_pos(gc, c[0], c[1], c[2]);
     #pragma unroll
-    for (int i = 0; i < NN; ++i) Sc[(long long)(s * NN + i) * gc.numNodes + n] = acc[i];
+    for (int i = 0; i < NN; ++i) Sc[(long long)(s * NN + i) * gc.numNodes + p] = acc[i];
 }
 
 void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc) {
@@ -220,14 +256,15 @@ k_coarsen_stencil(const __grid_constant__ GridDesc gc, const __grid_constant__ G
         for (int sa = 0; sa < NS; ++sa) {          // a: fine node i = 2n + a
             int av[3] = {0, 0, 0};
             { int r = sa; for (int a = 2; a >= A0; --a) { av[a] = r % 3 - 1; r /= 3; } }
-            bool ok = true; long long fi = 0; double wa = 1.0;
+            bool ok = true; double wa = 1.0; int fq[3] = {0, 0, 0};
             for (int a = A0; a < 3; ++a) {
                 const int q = 2 * c[a] + av[a];
                 ok = ok && q >= 0 && q < gf.nn[a];
-                fi += (long long)q * gf.ns[a];
+                fq[a] = q;
                 wa *= av[a] == 0 ? 1.0 : 0.5;
             }
             if (!ok) continue;
+            const long long fi = stencil_pos(gf, fq[0], fq[1], fq[2]);
             for (int sb = 0; sb < NS; ++sb) {      // a': fine node j = 2(n + delta) + a'
                 int bv[3] = {0, 0, 0};
                 { int r = sb; for (int a = 2; a >= A0; --a) { bv[a] = r % 3 - 1; r /= 3; } }
@@ -246,8 +283,9 @@ k_coarsen_stencil(const __grid_constant__ GridDesc gc, const __grid_constant__ G
             }
         }
     }
+    const long long p = stencil_pos(gc, c[0], c[1], c[2]);
     #pragma unroll
-    for (int i = 0; i < NN; ++i) Sc[(long long)(s * NN + i) * gc.numNodes + n] = acc[i];
+    for (int i = 0; i < NN; ++i) Sc[(long long)(s * NN + i) * gc.numNodes + p] = acc[i];
 }
 
 void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc) {
@@ -292,8 +330,9 @@ k_stencil_from_moduli_l0(const __grid_constant__ GridDesc g, const double *__res
             for (int b = 0; b < N; ++b) acc[a * N + b] = fma(Ee, __ldg(K0 + (N * e + a) * KE + (N * m + b)), acc[a * N + b]);
         }
     }
+    const long long p = stencil_pos(g, c[0], c[1], c[2]);
     #pragma unroll
-    for (int i = 0; i < NN; ++i) S[(long long)(s * NN + i) * g.numNodes + n] = acc[i];
+    for (int i = 0; i < NN; ++i) S[(long long)(s * NN + i) * g.numNodes + p] = acc[i];
 }
 
 void launch_stencil_from_moduli_l0(const LaunchCtx &ctx, const GridDesc &g, const double *E, const double *K0dev, double *S) {
@@ -323,7 +362,7 @@ __global__ void k_stencil_to_dense(const __grid_constant__ GridDesc g, const dou
         const int ri = red[n * N + a]; if (ri < 0) continue;
         for (int b = 0; b < N; ++b) {
             const int rj = red[m * N + b]; if (rj < 0) continue;
-            A[(size_t)ri * nfree + rj] = S[(long long)(s * NN + a * N + b) * g.numNodes + n];
+            A[(size_t)ri * nfree + rj] = S[(long long)(s * NN + a * N + b) * g.numNodes + stencil_pos(g, c[0], c[1], c[2])];
         }
     }
 }
