@@ -1,14 +1,18 @@
 #!/bin/bash
 # Runs on the GPU box under gpurun: launch list + full captures of the hot kernels (B200_PROFILING.md recipe).
-# usage: profiles/run_ncu.sh <tag>
-TAG=${1:-r01}
+# usage: profiles/run_ncu.sh <tag> [what...]   what in: launches gs_l0 apply_l0 stencil
+TAG=${1:-r01}; shift
+WHAT=${@:-launches gs_l0 apply_l0 stencil}
 OUT=gpurun_out
 mkdir -p $OUT
 NCU="ncu --clock-control none"
-# 1) every launch of one capped solve with its device time
-$NCU --metrics gpu__time_duration.sum -c 1200 --csv --log-file $OUT/${TAG}_launches.csv python tools/profile_driver.py "C3_pcg_256^3" 1 > $OUT/${TAG}_launches.log 2>&1
-# 2) full captures: level-0 GS colour pass, level-0 apply/residual, level-1 stencil GS pass (launch 96.. of the first FMG cycle)
-$NCU --set full --import-source on -k regex:k_gs_l0 -s 2 -c 2 -o $OUT/${TAG}_gs_l0 -f python tools/profile_driver.py "C3_pcg_256^3" 1 > $OUT/${TAG}_gs_l0.log 2>&1
-$NCU --set full --import-source on -k regex:k_apply_l0 -s 1 -c 2 -o $OUT/${TAG}_apply_l0 -f python tools/profile_driver.py "C3_pcg_256^3" 1 > $OUT/${TAG}_apply_l0.log 2>&1
-$NCU --set full --import-source on -k regex:k_gs_stencil -s 96 -c 2 -o $OUT/${TAG}_gs_stencil_l1 -f python tools/profile_driver.py "C3_pcg_256^3" 1 > $OUT/${TAG}_gs_stencil.log 2>&1
+DRV="python tools/profile_driver.py C3_pcg_256^3 1"
+for w in $WHAT; do case $w in
+  launches) # every launch of one capped solve with its device time
+    $NCU --metrics gpu__time_duration.sum -c 1200 --csv --log-file $OUT/${TAG}_launches.csv $DRV > $OUT/${TAG}_launches.log 2>&1 ;;
+  gs_l0)    $NCU --set full --import-source on -k regex:k_gs -s 2 -c 2 -o $OUT/${TAG}_gs_l0 -f $DRV > $OUT/${TAG}_gs_l0.log 2>&1 ;;
+  apply_l0) $NCU --set full --import-source on -k regex:k_apply -s 1 -c 2 -o $OUT/${TAG}_apply_l0 -f $DRV > $OUT/${TAG}_apply_l0.log 2>&1 ;;
+  stencil)  # level-1 colour passes (launches 51..58 of k_stencil_tile in the first FMG cycle) and the level-1 residual (59)
+    $NCU --set full --import-source on -k regex:k_stencil_tile -s 56 -c 4 -o $OUT/${TAG}_stencil_l1 -f $DRV > $OUT/${TAG}_stencil_l1.log 2>&1 ;;
+esac; done
 ls -la $OUT

@@ -114,8 +114,9 @@ static GridDesc make_grid(int N, const int64_t *ne) {
             g.ccnt[c][a] = (g.nn[a] - 1 - off >= 0) ? (g.nn[a] - 1 - off) / 2 + 1 : 0;
             cnt *= g.ccnt[c][a];
         }
-        g.cbase[c] = base; base += cnt;
+        g.cbase[c] = base; base += (cnt + kStencilTile - 1) / kStencilTile * kStencilTile;
     }
+    g.numPos = base;
     return g;
 }
 static void set_mask_limits(GridDesc &g, int firstMasked, int firstDetached) {
@@ -405,8 +406,8 @@ void mg_update_stiffness(vf_mg &mg, bool force = false) {
     const int nl = mg.numLevels();
     for (int l = 1; l < nl; ++l) {
         MGLevel &L = *mg.lv[l];
-        const size_t len = (size_t)L.g.numNodes * (mg.N == 3 ? 27 : 9) * mg.N * mg.N;
-        if (L.S.n != len) L.S.alloc(len, false);
+        const size_t len = (size_t)L.g.numPos * (mg.N == 3 ? 27 : 9) * mg.N * mg.N;
+        if (L.S.n != len) L.S.alloc(len, true);
         if (l == 1) launch_coarsen_from_moduli(mg.ctx, L.g, mg.sim->g, mg.sim->E.p, mg.cK0dev.p, L.S.p);
         else        launch_coarsen_stencil(mg.ctx, L.g, mg.lv[l - 1]->g, mg.lv[l - 1]->S.p, L.S.p);
     }
@@ -560,8 +561,8 @@ void sim_direct_solve(vf_sim &s, const double *fDev, double *xDev) {
         for (size_t k = 0; k < s.dirNodes.size(); ++k) for (int c = 0; c < s.N; ++c)
             if (((s.dirMask[k] >> c) & 1) && s.dirVals[k * s.N + c] != 0) throw std::runtime_error("Nonzero Dirichlet constraints currently unsupported");
         if (nfree > VF_MAX_DIRECT_DOFS) throw std::runtime_error("direct solve requested for " + std::to_string(nfree) + " free variables; use the multigrid solver (limit " + std::to_string(VF_MAX_DIRECT_DOFS) + ")");
-        const size_t len = (size_t)s.g.numNodes * (s.N == 3 ? 27 : 9) * s.N * s.N;
-        s.directStencil.alloc(len, false);
+        const size_t len = (size_t)s.g.numPos * (s.N == 3 ? 27 : 9) * s.N * s.N;
+        s.directStencil.alloc(len, true);
         launch_stencil_from_moduli_l0(s.ctx, s.g, s.E.p, s.K0dev.p, s.directStencil.p);
         s.direct.factor(s.ctx, s.g, s.directStencil.p, fixed);
         s.directVersion = s.version;
@@ -890,11 +891,11 @@ int vf_mg_get_stencil(vf_mg *mg, int l, double *out) {
     VF_TRY if (l < 1 || l >= mg->numLevels()) throw std::runtime_error("stencils are stored for levels 1..numLevels-1");
     mg_update_stiffness(*mg);
     const GridDesc &g = mg->grid(l); const int ns = mg->N == 3 ? 27 : 9, NN = mg->N * mg->N;
-    std::vector<double> h((size_t)g.numNodes * ns * NN);
+    std::vector<double> h((size_t)g.numPos * ns * NN);
     d2h(h.data(), mg->lv[l]->S.p, h.size(), mg->ctx.stream);
     for (int c0 = 0; c0 < g.nn[0]; ++c0) for (int c1 = 0; c1 < g.nn[1]; ++c1) for (int c2 = 0; c2 < g.nn[2]; ++c2) {
         const long long n = (long long)c0 * g.ns[0] + (long long)c1 * g.ns[1] + c2, p = stencil_pos(g, c0, c1, c2);
-        for (int s = 0; s < ns; ++s) for (int i = 0; i < NN; ++i) out[((size_t)n * ns + s) * NN + i] = h[(size_t)(s * NN + i) * g.numNodes + p];
+        for (int s = 0; s < ns; ++s) for (int i = 0; i < NN; ++i) out[((size_t)n * ns + s) * NN + i] = h[(size_t)stencil_addr(p, s * NN + i, ns * NN)];
     }
     VF_CATCH
 }

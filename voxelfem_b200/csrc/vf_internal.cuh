@@ -28,9 +28,16 @@ struct GridDesc {
     // Colour-major node numbering used by the stored stencils of the coarse levels: the nodes of parity class
     // (colour) c occupy positions cbase[c] .. cbase[c] + prod(ccnt[c]) in row-major order of (i_a >> 1).  A colour
     // pass of the smoother then streams its stencil rows from contiguous memory.
+    // Colour bases are padded to multiples of kStencilTile so that every tile of kStencilTile consecutive positions belongs
+    // to one colour; numPos = padded number of positions (>= numNodes).
     long long cbase[8];
     int ccnt[8][3];
+    long long numPos;
 };
+
+// Stored stencils are tiled: the NE = 3^N * N * N entries of kStencilTile consecutive positions form one contiguous
+// block  S[tile][entry][lane]  (31,104 B in 3D), which one cp.async.bulk (TMA) copy stages into shared memory.
+constexpr int kStencilTile = 16;
 
 #if defined(__CUDACC__)
 #define VF_HD __host__ __device__ __forceinline__
@@ -43,10 +50,16 @@ VF_HD long long stencil_pos(const GridDesc &g, int c0, int c1, int c2) {
     return g.cbase[col] + ((long long)(c0 >> 1) * g.ccnt[col][1] + (c1 >> 1)) * g.ccnt[col][2] + (c2 >> 1);
 }
 
+// offset of stencil entry `entry` (= slot * N*N + a*N + b) of position pos; NE = entries per node
+VF_HD long long stencil_addr(long long pos, int entry, int NE) {
+    return ((pos / kStencilTile) * NE + entry) * kStencilTile + (pos % kStencilTile);
+}
+
 template<int N> struct Dims {
     static constexpr int NPE = 1 << N;       // nodes per element
     static constexpr int KE  = N * NPE;      // element matrix size
     static constexpr int NS  = (N == 3) ? 27 : 9; // stencil slots
+    static constexpr int NE  = NS * N * N;        // stencil entries per node
     static constexpr int A0  = 3 - N;        // first active embedded axis
 };
 
@@ -151,7 +164,7 @@ void launch_gs_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, dou
                   const uint8_t *dmask, int color, bool forward);
 
 // --- vf_stencil.cu: 3^N-point block-stencil levels (MultigridSolver.hh:323-334; TensorProductSimulator.hh:1500-1504)
-// Stencil layout: S[(slot * N*N + a*N + b) * numNodes + node]
+// Stencil layout: S[stencil_addr(stencil_pos(node), slot * N*N + a*N + b, NE)], numPos * NE doubles per level
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
                           const uint8_t *dmask, double *out, int mode);
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,

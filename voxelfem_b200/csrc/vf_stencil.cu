@@ -6,8 +6,8 @@
 // on the fly from the fine moduli (MultigridSolver.hh:294-321, 475-499) and caches per-element
 // matrices at the coarsest level (:815-817).  On a structured grid all three are the same object: a
 // 3^N-point stencil of N x N blocks per node.  Here every level >= 1 stores that stencil in a
-// slot-major SoA layout  S[(slot*N*N + a*N + b) * numNodes + pos(node)]  where pos() is the colour-major node
-// numbering of GridDesc (stencil_pos): a colour pass of the smoother streams its rows contiguously.
+// tiled layout  S[tile][slot*N*N + a*N + b][lane]  (stencil_addr) over the colour-major node numbering of GridDesc
+// (stencil_pos): the rows of 16 consecutive same-colour nodes are one contiguous block, fetched by one TMA bulk copy.
 //
 // Galerkin coarsening (MultigridSolver.hh:711-819) is done directly on stencils: level 1 from the
 // fine moduli and the 2^N matrices coarsenedFineK0s[fi]; level l >= 2 as P^T A_{l-1} P.  Both are
@@ -18,95 +18,116 @@
 
 namespace vf {
 
-// Slot-parallel stencil row evaluation.  A thread block handles 32 consecutive nodes (in colour-major order)
-// with one warp-row per stencil slot: thread (tx, s) loads the N x N block S[s](node tx) (coalesced across tx)
-// and the neighbour displacement, and contributes S u to a shared-memory reduction over the 3^N slots.  Every
-// thread issues a single batch of independent loads, so the latency chain of a row is one memory round trip
-// instead of 3^N dependent ones -- this is what matters on the small coarse levels that sit on the critical
-// path of every V-cycle, while the large level 1 streams its 1944 B/node of stencil at HBM rate.
-constexpr int kSlotNodes = 16; // nodes per block (16 consecutive doubles = 128 B = 4 full sectors per load)
+// Tile kernel for the stored-stencil levels.  A thread block handles one tile of kStencilTile consecutive positions
+// (same colour, colour-major order) with one thread row per stencil slot.  Thread 0 stages the tile's contiguous
+// NE x 16 block of stencil entries into shared memory with a single TMA bulk copy (cp.async.bulk + mbarrier) while all
+// threads resolve their node coordinates and gather the neighbour displacements; thread (tx, s) then multiplies the
+// N x N block of slot s with u(neighbour s) and the 3^N slot contributions are reduced in shared memory in a fixed
+// order (deterministic).  The level-1 stencil (1944 B per node in 3D) therefore streams from HBM as contiguous 31 KB
+// blocks; the small coarse levels cost one memory round trip per colour pass.
 template<int N>
-struct SlotShared {
-    double red[N][Dims<N>::NS][kSlotNodes];
-    double Md[N * N][kSlotNodes];
-    double us[N][kSlotNodes];
-    double bs[N][kSlotNodes];
-    unsigned dm[kSlotNodes];
+struct TileShared {
+    alignas(128) double S[Dims<N>::NE * kStencilTile];
+    double red[N][Dims<N>::NS][kStencilTile];
+    double bs[N][kStencilTile];
+    double us[N][kStencilTile];
+    unsigned dm[kStencilTile];
+    alignas(8) unsigned long long mbar;
 };
 
-// coordinates of the q-th node: either of one colour pass (col != nullptr) or of the whole grid in colour-major order
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one thread: arm the barrier with the byte count and start the bulk copy global -> shared
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// coordinates of position pos (colour-major numbering); false for the padding lanes of a colour's last tile
 template<int N>
-__device__ __forceinline__ bool slot_node_coords(const GridDesc &g, const ColorDesc *col, long long q, int (&c)[3]) {
-    if (col) {
-        const long long tot = (long long)col->cnt[0] * col->cnt[1] * col->cnt[2];
-        if (q >= tot) return false;
-        const int i2 = (int)(q % col->cnt[2]); q /= col->cnt[2];
-        const int i1 = (int)(q % col->cnt[1]); const int i0 = (int)(q / col->cnt[1]);
-        c[0] = col->off[0] + 2 * i0; c[1] = col->off[1] + 2 * i1; c[2] = col->off[2] + 2 * i2;
-        return true;
-    }
-    if (q >= g.numNodes) return false;
+__device__ __forceinline__ bool pos_coords(const GridDesc &g, long long pos, int (&c)[3]) {
     int cc = 0;
     #pragma unroll
-    for (int k = 1; k < 8; ++k) cc += (q >= g.cbase[k]) ? 1 : 0;   // cbase is non-decreasing
-    long long idx = q - g.cbase[cc];
-    const int i2 = (int)(idx % g.ccnt[cc][2]); idx /= g.ccnt[cc][2];
-    const int i1 = (int)(idx % g.ccnt[cc][1]); const int i0 = (int)(idx / g.ccnt[cc][1]);
-    c[0] = 2 * i0 + ((cc >> 2) & 1); c[1] = 2 * i1 + ((cc >> 1) & 1); c[2] = 2 * i2 + (cc & 1);
+    for (int k = 1; k < 8; ++k) cc += (pos >= g.cbase[k]) ? 1 : 0;   // cbase is non-decreasing
+    const unsigned idx = (unsigned)(pos - g.cbase[cc]);
+    const unsigned n2 = (unsigned)g.ccnt[cc][2], n1 = (unsigned)g.ccnt[cc][1], n0 = (unsigned)g.ccnt[cc][0];
+    if (idx >= n0 * n1 * n2) return false;
+    const unsigned i2 = idx % n2, r = idx / n2, i1 = r % n1, i0 = r / n1;
+    c[0] = 2 * (int)i0 + ((cc >> 2) & 1); c[1] = 2 * (int)i1 + ((cc >> 1) & 1); c[2] = 2 * (int)i2 + (cc & 1);
     return true;
 }
 
 template<int N, bool GS, int MODE>
-__global__ void __launch_bounds__(kSlotNodes * Dims<N>::NS)
-k_stencil_slots(const __grid_constant__ GridDesc g, const __grid_constant__ ColorDesc col, const double *__restrict__ S,
-                const double *uin, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
-                double *out, int forward) {
-    constexpr int NS = Dims<N>::NS, A0 = Dims<N>::A0, NN = N * N;
-    __shared__ SlotShared<N> sh;
+__global__ void __launch_bounds__(kStencilTile * Dims<N>::NS)
+k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double *__restrict__ S,
+               const double *uin, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
+               double *out, int forward) {
+    constexpr int NS = Dims<N>::NS, A0 = Dims<N>::A0, NN = N * N, NE = Dims<N>::NE;
+    __shared__ TileShared<N> sh;
     const int tx = threadIdx.x, s = threadIdx.y;
-    const long long q = (long long)blockIdx.x * kSlotNodes + tx;
+    const long long tile = tile0 + blockIdx.x;
+    const long long pos = tile * kStencilTile + tx;
     int c[3] = {0, 0, 0};
-    const bool inRange = slot_node_coords<N>(g, GS ? &col : nullptr, q, c);
+    const bool inRange = pos_coords<N>(g, pos, c);
     const long long n = (long long)c[0] * g.ns[0] + (long long)c[1] * g.ns[1] + c[2];
     const bool detached = inRange && (((g.bd == 1) ? c[1] : c[2]) >= g.nActive);
-    double acc[N];
-    #pragma unroll
-    for (int a = 0; a < N; ++a) acc[a] = 0.0;
-    if (inRange && !detached) {
-        // stage b and the Dirichlet mask alongside the stencil loads so that the finalising warp has no global loads left
-        if (s < N && (GS || MODE == APPLY_RESIDUAL)) sh.bs[s][tx] = b[s * g.numNodes + n];
-        if (s == N) sh.dm[tx] = dmask ? dmask[n] : 0u;
-        int d[3] = {0, 0, 0};
-        { int r = s;
-          #pragma unroll
-          for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
-        bool valid = true; long long off = 0;
+    const bool active = inRange && !detached;
+    if (tx == 0 && s == 0) mbar_init(&sh.mbar, 1);
+    const int anyActive = __syncthreads_or(active ? 1 : 0);     // also publishes the barrier initialisation
+    if (anyActive) {
+        if (tx == 0 && s == 0) tma_load_1d(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+        double acc[N], un[N];
         #pragma unroll
-        for (int a = A0; a < 3; ++a) { const int qq = c[a] + d[a]; valid = valid && qq >= 0 && qq < g.nn[a]; off += (long long)d[a] * g.ns[a]; }
+        for (int a = 0; a < N; ++a) { acc[a] = 0.0; un[a] = 0.0; }
+        bool valid = false;
+        if (active) {
+            // stage b and the Dirichlet mask alongside so that the finalising threads have no global loads left
+            if (s < N && (GS || MODE == APPLY_RESIDUAL)) sh.bs[s][tx] = b[s * g.numNodes + n];
+            if (s == N) sh.dm[tx] = dmask ? dmask[n] : 0u;
+            int d[3] = {0, 0, 0};
+            { int r = s;
+              #pragma unroll
+              for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+            valid = true; long long off = 0;
+            #pragma unroll
+            for (int a = A0; a < 3; ++a) { const int qq = c[a] + d[a]; valid = valid && qq >= 0 && qq < g.nn[a]; off += (long long)d[a] * g.ns[a]; }
+            if (valid) {
+                #pragma unroll
+                for (int k = 0; k < N; ++k) un[k] = uin[k * g.numNodes + n + off];
+                if (GS && s == NS / 2) {
+                    #pragma unroll
+                    for (int k = 0; k < N; ++k) sh.us[k][tx] = un[k];
+                }
+            }
+        }
+        mbar_wait(&sh.mbar, 0);
         if (valid) {
-            const long long p = stencil_pos(g, c[0], c[1], c[2]);
-            double un[N], sv[NN];
-            #pragma unroll
-            for (int k = 0; k < N; ++k) un[k] = uin[k * g.numNodes + n + off];
-            #pragma unroll
-            for (int k = 0; k < NN; ++k) sv[k] = __ldg(S + (long long)(s * NN + k) * g.numNodes + p);
             #pragma unroll
             for (int a = 0; a < N; ++a) {
                 #pragma unroll
-                for (int k = 0; k < N; ++k) acc[a] = fma(sv[a * N + k], un[k], acc[a]);
-            }
-            if (s == NS / 2) {
-                #pragma unroll
-                for (int k = 0; k < NN; ++k) sh.Md[k][tx] = sv[k];
-                #pragma unroll
-                for (int k = 0; k < N; ++k) sh.us[k][tx] = un[k];
+                for (int k = 0; k < N; ++k) acc[a] = fma(sh.S[(s * NN + a * N + k) * kStencilTile + tx], un[k], acc[a]);
             }
         }
+        #pragma unroll
+        for (int a = 0; a < N; ++a) sh.red[a][s][tx] = acc[a];
     }
-    #pragma unroll
-    for (int a = 0; a < N; ++a) sh.red[a][s][tx] = acc[a];
     __syncthreads();
-    if (s < N) { // warp-row a = s sums the slot contributions of component a (fixed order -> deterministic)
+    if (!anyActive) {
+        if (!GS && MODE == APPLY_SET && s == 0 && inRange) {   // applyK<ZeroInit> zero-fills the detached margin
+            #pragma unroll
+            for (int a = 0; a < N; ++a) out[a * g.numNodes + n] = 0.0;
+        }
+        return;
+    }
+    if (s < N) { // thread row a = s sums the slot contributions of component a (fixed order -> deterministic)
         double t = 0.0;
         #pragma unroll
         for (int k = 0; k < NS; ++k) t += sh.red[s][k][tx];
@@ -129,7 +150,7 @@ k_stencil_slots(const __grid_constant__ GridDesc g, const __grid_constant__ Colo
         for (int a = 0; a < N; ++a) {
             rhs[a] = sh.bs[a][tx] - sh.red[a][0][tx];
             #pragma unroll
-            for (int k = 0; k < N; ++k) M[a][k] = sh.Md[a * N + k][tx];
+            for (int k = 0; k < N; ++k) M[a][k] = sh.S[((NS / 2) * NN + a * N + k) * kStencilTile + tx];
         }
         gs_node_update<N>(M, rhs, dm, forward != 0, du);
         #pragma unroll
@@ -152,9 +173,8 @@ k_stencil_slots(const __grid_constant__ GridDesc g, const __grid_constant__ Colo
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
                           const uint8_t *dmask, double *out, int mode) {
     ProfScope ps(ctx, mode == APPLY_RESIDUAL ? PC_RESIDUAL_ST : PC_APPLY_ST, (double)g.numNodes);
-    ColorDesc col; make_color(g, 0, col);
-    dim3 block(kSlotNodes, g.N == 3 ? 27 : 9), grid((unsigned)((g.numNodes + kSlotNodes - 1) / kSlotNodes));
-#define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) k_stencil_slots<NN_, false, M><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, out, 1);
+    dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)(g.numPos / kStencilTile));
+#define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) k_stencil_tile<NN_, false, M><<<grid, block, 0, ctx.stream>>>(g, 0, S, u, b, dmask, out, 1);
     VF_CASE(3, APPLY_SET) VF_CASE(3, APPLY_ADD) VF_CASE(3, APPLY_SUB) VF_CASE(3, APPLY_RESIDUAL)
     VF_CASE(2, APPLY_SET) VF_CASE(2, APPLY_ADD) VF_CASE(2, APPLY_SUB) VF_CASE(2, APPLY_RESIDUAL)
 #undef VF_CASE
@@ -165,11 +185,12 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
                        const uint8_t *dmask, int color, bool forward) {
     ColorDesc col;
     if (!make_color(g, color, col)) return;
-    const long long tot = (long long)col.cnt[0] * col.cnt[1] * col.cnt[2];
-    ProfScope ps(ctx, PC_GS_ST, (double)tot);
-    dim3 block(kSlotNodes, g.N == 3 ? 27 : 9), grid((unsigned)((tot + kSlotNodes - 1) / kSlotNodes));
-    if (g.N == 3) k_stencil_slots<3, true, APPLY_SET><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, u, forward ? 1 : 0);
-    else          k_stencil_slots<2, true, APPLY_SET><<<grid, block, 0, ctx.stream>>>(g, col, S, u, b, dmask, u, forward ? 1 : 0);
+    const long long tot = (long long)g.ccnt[color][0] * g.ccnt[color][1] * g.ccnt[color][2];
+    ProfScope ps(ctx, PC_GS_ST, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
+    dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)((tot + kStencilTile - 1) / kStencilTile));
+    const long long tile0 = g.cbase[color] / kStencilTile;
+    if (g.N == 3) k_stencil_tile<3, true, APPLY_SET><<<grid, block, 0, ctx.stream>>>(g, tile0, S, u, b, dmask, u, forward ? 1 : 0);
+    else          k_stencil_tile<2, true, APPLY_SET><<<grid, block, 0, ctx.stream>>>(g, tile0, S, u, b, dmask, u, forward ? 1 : 0);
     VF_KERNEL_CHECK();
 }
 
@@ -223,7 +244,7 @@ k_coarsen_from_moduli(const __grid_constant__ GridDesc gc, const __grid_constant
     }
     const long long p = stencil_pos(gc, c[0], c[1], c[2]);
     #pragma unroll
-    for (int i = 0; i < NN; ++i) Sc[(long long)(s * NN + i) * gc.numNodes + p] = acc[i];
+    for (int i = 0; i < NN; ++i) Sc[stencil_addr(p, s * NN + i, Dims<N>::NE)] = acc[i];
 }
 
 void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc) {
@@ -279,13 +300,13 @@ k_coarsen_stencil(const __grid_constant__ GridDesc gc, const __grid_constant__ G
                 }
                 if (!ok2) continue;
                 #pragma unroll
-                for (int i = 0; i < NN; ++i) acc[i] = fma(w, __ldg(Sf + (long long)(se * NN + i) * gf.numNodes + fi), acc[i]);
+                for (int i = 0; i < NN; ++i) acc[i] = fma(w, __ldg(Sf + stencil_addr(fi, se * NN + i, Dims<N>::NE)), acc[i]);
             }
         }
     }
     const long long p = stencil_pos(gc, c[0], c[1], c[2]);
     #pragma unroll
-    for (int i = 0; i < NN; ++i) Sc[(long long)(s * NN + i) * gc.numNodes + p] = acc[i];
+    for (int i = 0; i < NN; ++i) Sc[stencil_addr(p, s * NN + i, Dims<N>::NE)] = acc[i];
 }
 
 void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc) {
@@ -332,7 +353,7 @@ k_stencil_from_moduli_l0(const __grid_constant__ GridDesc g, const double *__res
     }
     const long long p = stencil_pos(g, c[0], c[1], c[2]);
     #pragma unroll
-    for (int i = 0; i < NN; ++i) S[(long long)(s * NN + i) * g.numNodes + p] = acc[i];
+    for (int i = 0; i < NN; ++i) S[stencil_addr(p, s * NN + i, Dims<N>::NE)] = acc[i];
 }
 
 void launch_stencil_from_moduli_l0(const LaunchCtx &ctx, const GridDesc &g, const double *E, const double *K0dev, double *S) {
@@ -357,12 +378,11 @@ __global__ void k_stencil_to_dense(const __grid_constant__ GridDesc g, const dou
     { int r = s; for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
     long long m = 0;
     for (int a = 0; a < 3; ++a) { const int q = c[a] + d[a]; if (q < 0 || q >= g.nn[a]) return; m += (long long)q * g.ns[a]; }
-    (void)NS;
     for (int a = 0; a < N; ++a) {
         const int ri = red[n * N + a]; if (ri < 0) continue;
         for (int b = 0; b < N; ++b) {
             const int rj = red[m * N + b]; if (rj < 0) continue;
-            A[(size_t)ri * nfree + rj] = S[(long long)(s * NN + a * N + b) * g.numNodes + stencil_pos(g, c[0], c[1], c[2])];
+            A[(size_t)ri * nfree + rj] = S[stencil_addr(stencil_pos(g, c[0], c[1], c[2]), s * NN + a * N + b, NS * NN)];
         }
     }
 }
