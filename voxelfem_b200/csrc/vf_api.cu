@@ -439,6 +439,10 @@ void mg_residual(vf_mg &mg, int l, const double *u, const double *b, double *r) 
 void mg_smooth(vf_mg &mg, int l, double *u, const double *b, bool forward) {
     const int nc = 1 << mg.N;
     if (l > 0) mg_update_stiffness(mg);
+    if (l == 0 && mg.N == 3) { // 3D level 0: two same-colour nodes per thread
+        for (int i = 0; i < nc; ++i) launch_gs3_color_l0(mg.ctx, mg.sim->g, mg.sim->K0p, u, b, mg.sim->E.p, mg.dmask(0), forward ? i : (nc - 1 - i), forward);
+        return;
+    }
     for (int i = 0; i < nc; ++i) {
         const int color = forward ? i : (nc - 1 - i);
         if (l == 0) launch_gs_l0(mg.ctx, mg.sim->g, mg.sim->K0p, u, b, mg.sim->E.p, mg.dmask(0), color, forward);

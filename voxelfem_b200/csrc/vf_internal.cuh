@@ -163,6 +163,10 @@ void launch_apply_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, 
 void launch_gs_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, double *u, const double *b, const double *E,
                   const uint8_t *dmask, int color, bool forward);
 
+// One colour pass, two nodes per thread (3D only).
+void launch_gs3_color_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, double *u, const double *b, const double *E,
+                         const uint8_t *dmask, int color, bool forward);
+
 // --- vf_stencil.cu: 3^N-point block-stencil levels (MultigridSolver.hh:323-334; TensorProductSimulator.hh:1500-1504)
 // Stencil layout: S[stencil_addr(stencil_pos(node), slot * N*N + a*N + b, NE)], numPos * NE doubles per level
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,

@@ -12,6 +12,7 @@
 // kernel parameter, so every K0 entry is a constant-bank operand of a DFMA.
 #include "vf_internal.cuh"
 #include "vf_reduce.cuh"
+#include <cstdlib>
 
 namespace vf {
 
@@ -137,6 +138,143 @@ k_apply_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K
     if (DOT) grid_sum(dotv, scratch, dotOut);
 }
 
+// ---------------------------------------------------------------------------
+// 3D apply, two nodes per thread.
+//
+// Every K0 entry is used exactly once per node (8 incident elements x 3 rows x 24 columns = 24 x 24), so with one
+// node per thread each DFMA needs its own constant fetch (LDCU) and the kernel is issue-bound at ~40% of the FP64
+// pipe.  Here a thread owns the two nodes (x, y, z), (x, y+1, z) -- lanes along the fastest axis -- so every constant
+// feeds two DFMAs and the 4 x 3 neighbour rows of an x-plane are loaded once for both nodes.  There are no
+// boundary branches: neighbour addresses are clamped into the grid and the moduli of elements outside the grid are
+// zero, so whatever a clamped load returns is multiplied by zero (an element inside the grid has all 8 nodes inside).
+// ---------------------------------------------------------------------------
+template<int MODE, bool DOT>
+__global__ void __launch_bounds__(128, 3)
+k_apply3_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K, const double *__restrict__ u,
+            const double *__restrict__ E, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
+            double *__restrict__ out, double *dotOut, double *scratch) {
+    const int c2 = blockIdx.x * 32 + threadIdx.x;
+    const int c1 = 2 * (blockIdx.y * 4 + threadIdx.y);
+    const int c0 = blockIdx.z;
+    double dotv = 0.0;
+    const bool inGrid = c2 < g.nn[2] && c1 < g.nn[1];
+    if (inGrid) {
+        const int nx = g.nn[0], ny = g.nn[1], nz = g.nn[2];
+        // clamped neighbour offsets
+        long long xo[3], yo[4]; int zo[3];
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) { xo[i] = (long long)min(max(c0 + i - 1, 0), nx - 1) * g.ns[0]; zo[i] = min(max(c2 + i - 1, 0), nz - 1); }
+        #pragma unroll
+        for (int r = 0; r < 4; ++r) yo[r] = (long long)min(max(c1 + r - 1, 0), ny - 1) * g.ns[1];
+        // moduli of the 2 x 3 x 2 elements around the node pair (zero outside the grid)
+        double Ee[2][3][2];
+        #pragma unroll
+        for (int ix = 0; ix < 2; ++ix) {
+            #pragma unroll
+            for (int iy = 0; iy < 3; ++iy) {
+                #pragma unroll
+                for (int iz = 0; iz < 2; ++iz) {
+                    const int ex = c0 - 1 + ix, ey = c1 - 1 + iy, ez = c2 - 1 + iz;
+                    const bool ok = ex >= 0 && ex < g.ne[0] && ey >= 0 && ey < g.ne[1] && ez >= 0 && ez < g.ne[2];
+                    Ee[ix][iy][iz] = ok ? __ldg(E + ((long long)ex * g.es[0] + (long long)ey * g.es[1] + ez)) : 0.0;
+                }
+            }
+        }
+        double t[2][8][3];
+        #pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            #pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                #pragma unroll
+                for (int c = 0; c < 3; ++c) t[j][e][c] = 0.0;
+            }
+        }
+        double uself[2][3];
+        #pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            #pragma unroll
+            for (int dz = 0; dz < 3; ++dz) {
+                double uu[4][3];
+                #pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    #pragma unroll
+                    for (int dc = 0; dc < 3; ++dc) uu[r][dc] = u[dc * g.numNodes + xo[dx] + yo[r] + zo[dz]];
+                }
+                if (dx == 1 && dz == 1) {
+                    #pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        #pragma unroll
+                        for (int dc = 0; dc < 3; ++dc) uself[j][dc] = uu[j + 1][dc];
+                    }
+                }
+                #pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    #pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        // local index m of neighbour (dx-1, dy-1, dz-1) in incident element e (bit (2-a) of e: element at offset -1 along axis a)
+                        const int m0 = (dx - 1) + ((e >> 2) & 1), m1 = (dy - 1) + ((e >> 1) & 1), m2 = (dz - 1) + (e & 1);
+                        if (m0 < 0 || m0 > 1 || m1 < 0 || m1 > 1 || m2 < 0 || m2 > 1) continue;
+                        const int m = (m0 << 2) | (m1 << 1) | m2;
+                        #pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            #pragma unroll
+                            for (int dc = 0; dc < 3; ++dc) {
+                                const double k = K.v[(3 * e + c) * 24 + (3 * m + dc)];
+                                t[0][e][c] = fma(k, uu[dy][dc], t[0][e][c]);
+                                t[1][e][c] = fma(k, uu[dy + 1][dc], t[1][e][c]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        #pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int y = c1 + j;
+            if (y >= ny) break;
+            const long long n = (long long)c0 * g.ns[0] + (long long)y * g.ns[1] + c2;
+            if (y >= g.nActive) { // detached layer: applyK<ZeroInit = true> zero-fills it (TPSStencils.hh:717-727)
+                if (MODE == APPLY_SET) {
+                    #pragma unroll
+                    for (int c = 0; c < 3; ++c) out[c * g.numNodes + n] = 0.0;
+                }
+                continue;
+            }
+            const unsigned dm = dmask ? dmask[n] : 0u;
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double acc = 0.0;
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) acc = fma(Ee[1 - ((e >> 2) & 1)][j + 1 - ((e >> 1) & 1)][1 - (e & 1)], t[j][e][c], acc);
+                double res;
+                if (MODE == APPLY_SET) res = acc;
+                else if (MODE == APPLY_ADD) res = out[c * g.numNodes + n] + acc;
+                else if (MODE == APPLY_SUB) res = out[c * g.numNodes + n] - acc;
+                else res = b[c * g.numNodes + n] - acc;
+                if ((dm >> c) & 1u) res = 0.0;
+                out[c * g.numNodes + n] = res;
+                if (DOT) dotv = fma(uself[j][c], res, dotv);
+            }
+        }
+    }
+    if (DOT) grid_sum(dotv, scratch, dotOut);
+}
+
+static void apply3_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
+                               const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
+    dim3 block(32, 4, 1);
+    dim3 grid((g.nn[2] + 31) / 32, ((g.nn[1] + 1) / 2 + 3) / 4, g.nn[0]);
+    if (dotOut && (size_t)grid.x * grid.y * grid.z > (size_t)kReduceMaxBlocks) throw std::runtime_error("apply_l0: grid too large for fused reduction");
+#define VF_APPLY_CASE(M) \
+    if (mode == M) { \
+        if (dotOut) k_apply3_l0<M, true><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, dotOut, scratch); \
+        else        k_apply3_l0<M, false><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, nullptr, nullptr); \
+    }
+    VF_APPLY_CASE(APPLY_SET) VF_APPLY_CASE(APPLY_ADD) VF_APPLY_CASE(APPLY_SUB) VF_APPLY_CASE(APPLY_RESIDUAL)
+#undef VF_APPLY_CASE
+    VF_KERNEL_CHECK();
+}
+
 template<int N>
 static void apply_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
                               const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
@@ -156,7 +294,7 @@ static void apply_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0P
 void launch_apply_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
                      const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
     ProfScope ps(ctx, mode == APPLY_RESIDUAL ? PC_RESIDUAL_L0 : PC_APPLY_L0, (double)g.numNodes);
-    if (g.N == 3) apply_l0_dispatch<3>(ctx, g, K, u, E, b, dmask, out, mode, dotOut, scratch);
+    if (g.N == 3) apply3_l0_dispatch(ctx, g, K, u, E, b, dmask, out, mode, dotOut, scratch);
     else          apply_l0_dispatch<2>(ctx, g, K, u, E, b, dmask, out, mode, dotOut, scratch);
 }
 
@@ -199,6 +337,119 @@ k_gs_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K, c
     gs_node_update<N>(M, rhs, dm, forward != 0, du);
     #pragma unroll
     for (int c = 0; c < N; ++c) u[c * g.numNodes + x.n] = uself[c] + du[c];
+}
+
+// ---------------------------------------------------------------------------
+// 3D single-colour Gauss-Seidel pass, two same-colour nodes (y, y+2) per thread: every K0 constant feeds two DFMAs and
+// there are no boundary branches (clamped addresses, zero moduli outside the grid), as in k_apply3_l0.
+// ---------------------------------------------------------------------------
+template<bool FWD>
+__global__ void __launch_bounds__(128, 3)
+k_gs3_color(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K, const __grid_constant__ ColorDesc col,
+            double *u, const double *__restrict__ b, const double *__restrict__ E, const uint8_t *__restrict__ dmask) {
+    const int i2 = blockIdx.x * 32 + threadIdx.x;
+    const int i1 = 2 * (blockIdx.y * 4 + threadIdx.y);   // first of the two colour-local y indices
+    const int i0 = blockIdx.z;
+    if (i2 >= col.cnt[2] || i1 >= col.cnt[1]) return;
+    const int c0 = col.off[0] + 2 * i0, c1 = col.off[1] + 2 * i1, c2 = col.off[2] + 2 * i2;
+    const int nx = g.nn[0], ny = g.nn[1], nz = g.nn[2];
+    const long long NN = g.numNodes;
+    long long xo[3], yo[5]; int zo[3];
+    #pragma unroll
+    for (int i = 0; i < 3; ++i) { xo[i] = (long long)min(max(c0 + i - 1, 0), nx - 1) * g.ns[0]; zo[i] = min(max(c2 + i - 1, 0), nz - 1); }
+    #pragma unroll
+    for (int r = 0; r < 5; ++r) yo[r] = (long long)min(max(c1 + r - 1, 0), ny - 1) * g.ns[1];
+    double t[2][8][3];
+    #pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        #pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) t[j][e][c] = 0.0;
+        }
+    }
+    double uself[2][3];
+    #pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+        #pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+            double uu[5][3];
+            #pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                #pragma unroll
+                for (int dc = 0; dc < 3; ++dc) uu[r][dc] = u[dc * NN + xo[dx] + yo[r] + zo[dz]];
+            }
+            if (dx == 1 && dz == 1) {
+                #pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    #pragma unroll
+                    for (int dc = 0; dc < 3; ++dc) uself[j][dc] = uu[2 * j + 1][dc];
+                }
+            }
+            #pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int m0 = (dx - 1) + ((e >> 2) & 1), m1 = (dy - 1) + ((e >> 1) & 1), m2 = (dz - 1) + (e & 1);
+                    if (m0 < 0 || m0 > 1 || m1 < 0 || m1 > 1 || m2 < 0 || m2 > 1) continue;
+                    const int m = (m0 << 2) | (m1 << 1) | m2;
+                    #pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        #pragma unroll
+                        for (int dc = 0; dc < 3; ++dc) {
+                            const double k = K.v[(3 * e + c) * 24 + (3 * m + dc)];
+                            t[0][e][c] = fma(k, uu[dy][dc], t[0][e][c]);
+                            t[1][e][c] = fma(k, uu[dy + 2][dc], t[1][e][c]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    #pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (i1 + j >= col.cnt[1]) break;
+        const int y = c1 + 2 * j;
+        const long long n = (long long)c0 * g.ns[0] + (long long)y * g.ns[1] + c2;
+        const unsigned dm = dmask[n];
+        if (dm == 7u) continue; // hasFullDirichlet (MultigridSolver.hh:350)
+        double Ee[8];
+        #pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ex = c0 - ((e >> 2) & 1), ey = y - ((e >> 1) & 1), ez = c2 - (e & 1);
+            const bool ok = ex >= 0 && ex < g.ne[0] && ey >= 0 && ey < g.ne[1] && ez >= 0 && ez < g.ne[2];
+            Ee[e] = ok ? __ldg(E + ((long long)ex * g.es[0] + (long long)ey * g.es[1] + ez)) : 0.0;
+        }
+        double rhs[3], M[3][3], du[3];
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double acc = 0.0;
+            #pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fma(Ee[e], t[j][e][c], acc);
+            rhs[c] = b[c * NN + n] - acc;
+            #pragma unroll
+            for (int c2_ = 0; c2_ < 3; ++c2_) {
+                double mm = 0.0;
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) mm = fma(Ee[e], K.v[(3 * e + c) * 24 + (3 * e + c2_)], mm);
+                M[c][c2_] = mm;
+            }
+        }
+        gs_node_update<3>(M, rhs, dm, FWD, du);
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) u[c * NN + n] = uself[j][c] + du[c];
+    }
+}
+
+void launch_gs3_color_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, double *u, const double *b, const double *E,
+                         const uint8_t *dmask, int color, bool forward) {
+    ColorDesc col;
+    if (!make_color(g, color, col)) return;
+    ProfScope ps(ctx, PC_GS_L0, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
+    dim3 block(32, 4, 1), grid((col.cnt[2] + 31) / 32, ((col.cnt[1] + 1) / 2 + 3) / 4, col.cnt[0]);
+    if (forward) k_gs3_color<true><<<grid, block, 0, ctx.stream>>>(g, K, col, u, b, E, dmask);
+    else         k_gs3_color<false><<<grid, block, 0, ctx.stream>>>(g, K, col, u, b, E, dmask);
+    VF_KERNEL_CHECK();
 }
 
 void launch_gs_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, double *u, const double *b, const double *E,

@@ -66,7 +66,7 @@ __device__ __forceinline__ bool pos_coords(const GridDesc &g, long long pos, int
 }
 
 template<int N, bool GS, int MODE>
-__global__ void __launch_bounds__(kStencilTile * Dims<N>::NS)
+__global__ void __launch_bounds__(kStencilTile * Dims<N>::NS, N == 3 ? 4 : 8)
 k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double *__restrict__ S,
                const double *uin, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
                double *out, int forward) {
@@ -170,8 +170,24 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     }
 }
 
+// the tile kernels want the largest shared-memory carve-out (4 resident blocks x 42 KB in 3D)
+template<typename Kern> static void prefer_shared(Kern k) {
+    VF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+}
+static void stencil_kernel_attributes() {
+    static bool done = false;
+    if (done) return;
+#define VF_ATTR(NN_, M) prefer_shared(k_stencil_tile<NN_, false, M>);
+    VF_ATTR(3, APPLY_SET) VF_ATTR(3, APPLY_ADD) VF_ATTR(3, APPLY_SUB) VF_ATTR(3, APPLY_RESIDUAL)
+    VF_ATTR(2, APPLY_SET) VF_ATTR(2, APPLY_ADD) VF_ATTR(2, APPLY_SUB) VF_ATTR(2, APPLY_RESIDUAL)
+#undef VF_ATTR
+    prefer_shared(k_stencil_tile<3, true, APPLY_SET>); prefer_shared(k_stencil_tile<2, true, APPLY_SET>);
+    done = true;
+}
+
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
                           const uint8_t *dmask, double *out, int mode) {
+    stencil_kernel_attributes();
     ProfScope ps(ctx, mode == APPLY_RESIDUAL ? PC_RESIDUAL_ST : PC_APPLY_ST, (double)g.numNodes);
     dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)(g.numPos / kStencilTile));
 #define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) k_stencil_tile<NN_, false, M><<<grid, block, 0, ctx.stream>>>(g, 0, S, u, b, dmask, out, 1);
@@ -185,6 +201,7 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
                        const uint8_t *dmask, int color, bool forward) {
     ColorDesc col;
     if (!make_color(g, color, col)) return;
+    stencil_kernel_attributes();
     const long long tot = (long long)g.ccnt[color][0] * g.ccnt[color][1] * g.ccnt[color][2];
     ProfScope ps(ctx, PC_GS_ST, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
     dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)((tot + kStencilTile - 1) / kStencilTile));
