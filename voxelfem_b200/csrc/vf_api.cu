@@ -532,7 +532,7 @@ void mg_pcg(vf_mg &mg, double *x, const double *b, int maxIter, double tol, int 
     while ((i++ < maxIter) && (rsq > tol * tol * bsq)) {
         if (mgIterations > 0 && mgSmoothing > 0) {
             mg_update_stiffness(mg); // lazily, first iteration (:1104-1107)
-            VF_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * g.numNodes * mg.N, mg.ctx.stream)); // applyPreconditionerInv: zero initial guess (:577-580)
+            if (!fmg) VF_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * g.numNodes * mg.N, mg.ctx.stream)); // applyPreconditionerInv: zero initial guess (:577-580); the FMG cycle overwrites s by interpolation (:600)
             mg_solve_inplace(mg, mgIterations, mgSmoothing, true, fmg);
         } else {
             VF_CUDA(cudaMemcpyAsync(s, r, sizeof(double) * g.numNodes * mg.N, cudaMemcpyDeviceToDevice, mg.ctx.stream)); // s = r (:578, :1118)
@@ -542,8 +542,7 @@ void mg_pcg(vf_mg &mg, double *x, const double *b, int maxIter, double tol, int 
         launch_masked_dot(mg.ctx, g, r, s, sc + cur, mg.scratch.p);                      // r_Minv_r (:1124)
         launch_cg_direction(mg.ctx, g, s, mg.d.p, sc + cur, sc + old, first);           // d = s + beta d (:1125-1126)
         first = false;
-        mg_apply_K(mg, 0, mg.d.p, nullptr, mg.Ad.p, APPLY_SET, true);                   // Ad = K d, zero Dirichlet (:1129-1130)
-        launch_masked_dot(mg.ctx, g, mg.d.p, mg.Ad.p, sc + SC_DAD, mg.scratch.p);        // d . Ad (:1134)
+        mg_apply_K(mg, 0, mg.d.p, nullptr, mg.Ad.p, APPLY_SET, true, sc + SC_DAD);      // Ad = K d, zero Dirichlet (:1129-1130), fused d . Ad (:1134)
         launch_cg_update(mg.ctx, g, x, mg.d.p, r, mg.Ad.p, sc + cur, sc + SC_DAD, sc + SC_RSQ, mg.scratch.p); // (:1134-1143)
         rsq = read_scalar(mg, SC_RSQ);
         if (std::isnan(rsq)) throw std::logic_error("NaN encountered at iteration" + std::to_string(i));

@@ -264,31 +264,17 @@ static void apply3_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0
                                const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
     dim3 block(32, 4, 1);
     dim3 grid((g.nn[2] + 31) / 32, ((g.nn[1] + 1) / 2 + 3) / 4, g.nn[0]);
-    if (dotOut && (size_t)grid.x * grid.y * grid.z > (size_t)kReduceMaxBlocks) throw std::runtime_error("apply_l0: grid too large for fused reduction");
+    // the fused u . out reduction keeps one partial per block; beyond the scratch capacity fall back to a separate dot
+    const bool fused = dotOut && (size_t)grid.x * grid.y * grid.z <= (size_t)kReduceMaxBlocks;
 #define VF_APPLY_CASE(M) \
     if (mode == M) { \
-        if (dotOut) k_apply3_l0<M, true><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, dotOut, scratch); \
-        else        k_apply3_l0<M, false><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, nullptr, nullptr); \
+        if (fused) k_apply3_l0<M, true><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, dotOut, scratch); \
+        else       k_apply3_l0<M, false><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, nullptr, nullptr); \
     }
     VF_APPLY_CASE(APPLY_SET) VF_APPLY_CASE(APPLY_ADD) VF_APPLY_CASE(APPLY_SUB) VF_APPLY_CASE(APPLY_RESIDUAL)
 #undef VF_APPLY_CASE
     VF_KERNEL_CHECK();
-}
-
-template<int N>
-static void apply_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
-                              const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
-    dim3 block = (N == 3) ? dim3(32, 4, 2) : dim3(32, 8, 1);
-    dim3 grid((g.nn[2] + block.x - 1) / block.x, (g.nn[1] + block.y - 1) / block.y, (g.nn[0] + block.z - 1) / block.z);
-    if (dotOut && (size_t)grid.x * grid.y * grid.z > (size_t)kReduceMaxBlocks) throw std::runtime_error("apply_l0: grid too large for fused reduction");
-#define VF_APPLY_CASE(M) \
-    if (mode == M) { \
-        if (dotOut) k_apply_l0<N, M, true><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, dotOut, scratch); \
-        else        k_apply_l0<N, M, false><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, nullptr, nullptr); \
-    }
-    VF_APPLY_CASE(APPLY_SET) VF_APPLY_CASE(APPLY_ADD) VF_APPLY_CASE(APPLY_SUB) VF_APPLY_CASE(APPLY_RESIDUAL)
-#undef VF_APPLY_CASE
-    VF_KERNEL_CHECK();
+    if (dotOut && !fused) launch_masked_dot(ctx, g, u, out, dotOut, scratch);
 }
 
 void launch_apply_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
