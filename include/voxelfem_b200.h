@@ -36,6 +36,7 @@ typedef struct vf_top vf_top; /* TopologyOptimizationProblem + MultigridComplian
                                  TotalVolumeConstraint + OCOptimizer state (TopologyOptimizationProblem.hh,
                                  TopologyOptimizationObjective.hh:72-105, OptimalityCriterion.hh:38-149)   */
 typedef struct vf_lbl vf_lbl; /* LayerByLayerEvaluator (LayerByLayer.hh:25-309) */
+typedef struct vf_group vf_group; /* a MultigridSolver partitioned into slabs along axis 0, one part per GPU (no reference equivalent: the reference is single-address-space) */
 
 #define VF_LAW_SIMP 0
 #define VF_LAW_RAMP 1
@@ -164,6 +165,30 @@ int vf_prof_get(vf_mg *mg, int category, int64_t *launches, double *total_ms, do
  * repetitions on the level's own fields.  op: 0 smoothing sweep (smoothingMulticoloredGS, :452-458), 1 computeResidual,
  * 2 applyK, 3 restriction, 4 accum_interpolation, 5 coarsest solve, 6 vcycle(level) (:617-658), 7 fullMultigrid(0) (:587-609). */
 int vf_mg_time_op(vf_mg *mg, int op, int level, int reps, int num_smoothing_steps, double *ms_per_rep);
+
+/* ---- Slab-partitioned solver (multi-GPU) -------------------------------------------------
+ * The grid is cut into slabs of element layers [slab_begin, slab_end) along axis 0 (the slowest axis: a slab and its halo
+ * planes are contiguous in every field).  Each part is an ordinary simulator / solver over the slab's WINDOW: the node planes
+ * [max(slab_begin - 1, 0), min(slab_end + 1, ne[0])] -- the slab plus one ghost plane per neighbour; per-element and nodal
+ * arrays passed to a part (densities, u, f) are the window's slice of the global arrays.  BC regions are matched against the
+ * global grid (a force is split over all nodes of the grid inside its box).  Levels < first_replicated_level are windowed
+ * per part, the others are held by every part for the whole grid; slab boundaries must be multiples of
+ * 2^first_replicated_level.  One process per GPU joins an NCCL group (halo planes by ncclSend/ncclRecv, PCG scalars and
+ * the replicated coarse data by ncclAllReduce); a local group drives several parts from one process on one device. */
+int vf_sim_create_slab(int dim, const int64_t *ne_global, const double *domain_min, const double *domain_max,
+                       int64_t slab_begin, int64_t slab_end, vf_sim *share_stream_with /* may be NULL */, vf_sim **out);
+/* node planes stored [plane_lo, plane_hi] and owned [own_lo, own_hi] (global indices along axis 0) */
+int vf_sim_window(const vf_sim *s, int64_t *plane_lo, int64_t *plane_hi, int64_t *own_lo, int64_t *own_hi);
+int vf_mg_create_slab(vf_sim *fine, int num_coarsening_levels, int first_replicated_level, vf_mg **out);
+int vf_group_create_local(int nparts, vf_mg **parts, vf_group **out);
+int vf_nccl_unique_id(void *out128);  /* rank 0: ncclGetUniqueId; the caller broadcasts the 128 bytes (torch.distributed) */
+int vf_group_create_nccl(vf_mg *part, int rank, int world, const void *unique_id128, vf_group **out);
+int vf_group_destroy(vf_group *g);
+/* preconditionedConjugateGradient (MultigridSolver.hh:1047-1152) over the whole grid; x_dev / b_dev: one device VField of the
+ * part's window per local part.  Every part returns the same iteration count and residual history. */
+int vf_group_pcg_dev(vf_group *g, double *const *x_dev, const double *const *b_dev, int max_iter, double tol, int mg_iterations,
+                     int mg_smoothing_iterations, int fmg, int dirichlet_already_satisfied,
+                     int *out_iterations, double *residual_norms, vf_pcg_callback cb, void *user);
 
 /* ---- Filters (stand-alone) -------------------------------------------------------- */
 int vf_filter_smooth(int dim, const int64_t *sizes, int radius, int type, const double *in, double *out); /* SmoothingFilter::apply == backprop (:297-310) */

@@ -125,6 +125,14 @@ def lib():
         "vf_top_last_pcg_iterations": (ci, [vp]),
         "vf_top_oc_step": (ci, [vp, cd, cd, cd, C.POINTER(ci)]),
         "vf_top_get_lambda_bracket": (ci, [vp, C.POINTER(cd), C.POINTER(cd)]),
+        "vf_sim_create_slab": (ci, [ci, _ip, _dp, _dp, i64, i64, vp, pvp]),
+        "vf_sim_window": (ci, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        "vf_mg_create_slab": (ci, [vp, ci, ci, pvp]),
+        "vf_group_create_local": (ci, [ci, pvp, pvp]),
+        "vf_nccl_unique_id": (ci, [vp]),
+        "vf_group_create_nccl": (ci, [vp, ci, ci, vp, pvp]),
+        "vf_group_destroy": (ci, [vp]),
+        "vf_group_pcg_dev": (ci, [vp, pvp, pvp, ci, cd, ci, ci, ci, ci, C.POINTER(ci), _dp, PCG_CALLBACK, vp]),
         "vf_lbl_create": (ci, [vp, pvp]),
         "vf_lbl_destroy": (ci, [vp]),
         "vf_lbl_select_init_method": (ci, [vp, C.c_char_p]),
@@ -463,6 +471,94 @@ class MG:
             if n.value:
                 out[self.L.vf_prof_name(c).decode()] = {"launches": n.value, "ms": ms.value, "units": un.value}
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Slab-partitioned solver (multi-GPU)
+# ---------------------------------------------------------------------------------------------
+def slab_ranges(ne0, nparts, align):
+    """Even split of ne0 element layers into nparts slabs whose boundaries are multiples of `align`."""
+    units = ne0 // align
+    assert units * align == ne0 and units >= nparts, "grid not divisible into %d slabs aligned to %d" % (nparts, align)
+    cuts = [align * ((units * i) // nparts) for i in range(nparts + 1)]
+    return [(cuts[i], cuts[i + 1]) for i in range(nparts)]
+
+
+class SlabSim(Sim):
+    """One slab of a TensorProductSimulator: stores the window of node planes [plane_lo, plane_hi] of the global grid."""
+
+    def __init__(self, ne_global, dmin, dmax, slab_begin, slab_end, share_stream_with=None):
+        self.L = lib()
+        self.ne_global = np.ascontiguousarray(ne_global, dtype=np.int64)
+        self.N = len(self.ne_global)
+        self.dmin = np.ascontiguousarray(dmin, dtype=np.float64)
+        self.dmax = np.ascontiguousarray(dmax, dtype=np.float64)
+        h = C.c_void_p()
+        _check(self.L.vf_sim_create_slab(self.N, self.ne_global, self.dmin, self.dmax, int(slab_begin), int(slab_end),
+                                         share_stream_with.h if share_stream_with is not None else None, C.byref(h)))
+        self.h = h
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _check(self.L.vf_sim_window(h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        self.plane_lo, self.plane_hi, self.own_lo, self.own_hi = a.value, b.value, c.value, d.value
+        self.slab = (int(slab_begin), int(slab_end))
+        self.ne = self.ne_global.copy()
+        self.ne[0] = self.plane_hi - self.plane_lo
+
+    def window_of_nodal(self, field):
+        """Slice of a global (numNodes, N) nodal field stored by this part."""
+        nn = self.ne_global + 1
+        return np.ascontiguousarray(field.reshape(tuple(nn) + (self.N,))[self.plane_lo:self.plane_hi + 1]).reshape(-1, self.N)
+
+    def window_of_elements(self, values):
+        return np.ascontiguousarray(np.asarray(values).reshape(tuple(self.ne_global))[self.plane_lo:self.plane_hi]).ravel()
+
+
+class SlabMG(MG):
+    def __init__(self, sim, levels, first_replicated_level):
+        self.L = lib()
+        self.sim, self.N, self.levels = sim, sim.N, levels
+        h = C.c_void_p()
+        _check(self.L.vf_mg_create_slab(sim.h, levels, first_replicated_level, C.byref(h)))
+        self.h = h
+
+
+class SlabGroup:
+    """A MultigridSolver cut into slabs along axis 0: a local group (all parts in this process, one device) or one NCCL rank."""
+
+    def __init__(self, parts, rank=None, world=None, unique_id=None):
+        self.L = lib()
+        self.parts = list(parts)
+        h = C.c_void_p()
+        if unique_id is None:
+            arr = (C.c_void_p * len(self.parts))(*[p.h for p in self.parts])
+            _check(self.L.vf_group_create_local(len(self.parts), arr, C.byref(h)))
+        else:
+            assert len(self.parts) == 1
+            buf = C.create_string_buffer(bytes(unique_id), 128)
+            _check(self.L.vf_group_create_nccl(self.parts[0].h, rank, world, buf, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = C.create_string_buffer(128)
+        _check(lib().vf_nccl_unique_id(buf))
+        return buf.raw
+
+    def pcg_dev(self, xs, bs, max_iter, tol, mg_iterations=1, mg_smoothing=1, fmg=False, dirichlet_ok=False):
+        it = C.c_int(0)
+        res = np.zeros(max(max_iter, 1) + 1)
+        xa = (C.c_void_p * len(xs))(*[x.ptr for x in xs])
+        ba = (C.c_void_p * len(bs))(*[b.ptr for b in bs])
+        _check(self.L.vf_group_pcg_dev(self.h, xa, ba, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), int(dirichlet_ok), C.byref(it), res, PCG_CALLBACK(), None))
+        return it.value, res[:it.value]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vf_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 class Problem:

@@ -9,6 +9,7 @@
 #include "../../include/voxelfem_b200.h"
 
 #include <cusolverDn.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -117,6 +118,7 @@ static GridDesc make_grid(int N, const int64_t *ne) {
         g.cbase[c] = base; base += (cnt + kStencilTile - 1) / kStencilTile * kStencilTile;
     }
     g.numPos = base;
+    g.xoff = 0; g.ownLo = 0; g.ownHi = g.nn[0]; g.cmpLo = 0; g.cmpHi = g.nn[0]; g.oeLo = 0; g.oeHi = g.ne[0];
     return g;
 }
 static void set_mask_limits(GridDesc &g, int firstMasked, int firstDetached) {
@@ -230,6 +232,9 @@ struct vf_sim {
     cudaStream_t stream = nullptr; LaunchCtx ctx; Profiler prof;
     uint64_t version = 1; // bumped whenever E, the mask, K0 or the Dirichlet set changes
     DenseSolver direct; uint64_t directVersion = 0; DevBuf<double> directStencil;
+    // Slab window (multi-GPU): this simulator stores node planes [xoff, xoff + nn[0] - 1] of a grid with gne0 element layers
+    // along axis 0, of which element layers [slabBegin, slabEnd) are owned.  dmin/dmax/spacing/stretch are the global ones.
+    bool window = false, ownsStream = true; int64_t gne0 = 0, xoff = 0, slabBegin = 0, slabEnd = 0;
 
     long long numNodes() const { return g.numNodes; }
     long long numElems() const { return g.numElems; }
@@ -312,13 +317,22 @@ struct vf_sim {
         touch();
     }
     // node index ranges per axis covered by an inclusive box (Geometry.hh:276-279 applied to nodePosition, :349-351)
-    bool boxRanges(const double *lo, const double *hi, std::vector<int64_t> (&idx)[3]) const {
+    // idx: local indices inside this simulator's window; *globalCount (optional): number of nodes of the whole grid in the box
+    bool boxRanges(const double *lo, const double *hi, std::vector<int64_t> (&idx)[3], double *globalCount = nullptr) const {
+        double cnt = 1;
         for (int d = 0; d < N; ++d) {
             idx[d].clear();
-            for (int64_t i = 0; i < nn[d]; ++i) { const double p = dmin[d] + double(i) * spacing[d]; if (p >= lo[d] && p <= hi[d]) idx[d].push_back(i); }
-            if (idx[d].empty()) return false;
+            const int64_t gn = (d == 0 && window) ? gne0 + 1 : nn[d], off = (d == 0 && window) ? xoff : 0;
+            int64_t c = 0;
+            for (int64_t i = 0; i < gn; ++i) {
+                const double p = dmin[d] + double(i) * spacing[d];
+                if (p >= lo[d] && p <= hi[d]) { ++c; if (i - off >= 0 && i - off < nn[d]) idx[d].push_back(i - off); }
+            }
+            if (c == 0) return false;
+            cnt *= double(c);
         }
         for (int d = N; d < 3; ++d) idx[d].assign(1, 0);
+        if (globalCount) *globalCount = cnt;
         return true;
     }
     int64_t flatNode(int64_t i, int64_t j, int64_t k) const { return N == 3 ? (i * nn[1] + j) * nn[2] + k : i * nn[1] + j; }
@@ -360,8 +374,11 @@ struct BCBuilder {
 // ---------------------------------------------------------------------------
 // vf_mg
 // ---------------------------------------------------------------------------
+struct vf_group;
 struct MGLevel {
     GridDesc g; int64_t ne[3]; double stretchBD = 1;
+    // slab windows: this part owns global element layers [sb, se) of the level (node planes sb..se); replicated levels hold the whole grid
+    int64_t sb = 0, se = 0, gne0 = 0; bool windowed = false;
     std::vector<uint8_t> nodeMask; DevBuf<uint8_t> dmask;
     DevBuf<double> x, b, r, S;
     int firstMasked = INT_MAX, firstDetached = INT_MAX;
@@ -377,10 +394,58 @@ struct vf_mg {
     double *hostScalars = nullptr; // pinned
     std::vector<double> lastResiduals; int lastIters = 0;
     LaunchCtx ctx;
+    vf_group *grp = nullptr; int firstRep = INT_MAX; // slab group this solver is a part of; first replicated (non-windowed) level
+    std::vector<vf_mg *> self;
+    DevBuf<double> stage[2];                          // staging buffers of the slab exchanges
     ~vf_mg() { if (hostScalars) cudaFreeHost(hostScalars); }
     int numLevels() const { return (int)lv.size(); }
     const uint8_t *dmask(int l) const { return l == 0 ? sim->dmaskDev.p : lv[l]->dmask.p; }
     const GridDesc &grid(int l) const { return l == 0 ? sim->g : lv[l]->g; }
+};
+
+// ---------------------------------------------------------------------------
+// Slab groups: the grid is cut into slabs along axis 0, one vf_mg "part" per slab.  A group is either
+//   - local: all parts live in this process on one device and one stream (exchanges are device copies) -- used to test the
+//     partitioned algorithm on a single GPU and to drive several slabs from one process, or
+//   - NCCL:  one part per process / GPU; halo planes travel with ncclSend/ncclRecv, scalars and the replicated coarse
+//     data with ncclAllReduce, all enqueued on the solver's stream.
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy torch already loaded, else the system one).
+// ---------------------------------------------------------------------------
+struct NcclUniqueId { char internal[128]; };   // ncclUniqueId (nccl.h)
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    static NcclApi &get() {
+        static NcclApi api;
+        if (!api.lib) {
+            api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (!api.lib) throw std::runtime_error(std::string("cannot load NCCL: ") + dlerror());
+#define VF_NCCL_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name)); if (!api.field) throw std::runtime_error("NCCL symbol missing: " name);
+            VF_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") VF_NCCL_SYM(CommInitRank, "ncclCommInitRank") VF_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+            VF_NCCL_SYM(Send, "ncclSend") VF_NCCL_SYM(Recv, "ncclRecv") VF_NCCL_SYM(AllReduce, "ncclAllReduce")
+            VF_NCCL_SYM(GroupStart, "ncclGroupStart") VF_NCCL_SYM(GroupEnd, "ncclGroupEnd") VF_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef VF_NCCL_SYM
+        }
+        return api;
+    }
+    void check(int rc, const char *what) { if (rc != 0) throw std::runtime_error(std::string("NCCL error in ") + what + ": " + (GetErrorString ? GetErrorString(rc) : "?")); }
+};
+constexpr int kNcclDouble = 8, kNcclSum = 0; // ncclFloat64, ncclSum (nccl.h)
+
+struct vf_group {
+    std::vector<vf_mg *> parts;   // local parts, ordered by slab
+    int rank = 0, world = 1;      // NCCL mode: this process' slab index and the number of slabs
+    void *comm = nullptr;         // ncclComm_t
+    ~vf_group() { if (comm) NcclApi::get().CommDestroy(comm); }
 };
 
 namespace {
@@ -397,98 +462,270 @@ void mg_sync_level_masks(vf_mg &mg) {
     }
 }
 
+std::vector<vf_mg *> &parts_of(vf_mg &mg) {
+    if (mg.grp) return mg.grp->parts;
+    if (mg.self.empty()) mg.self.assign(1, &mg);
+    return mg.self;
+}
+MGLevel &level(vf_mg &mg, int l) { return *mg.lv[l]; }
+bool level_windowed(vf_mg &mg, int l) { return mg.grp && l < mg.firstRep; }
+double *stage_buf(vf_mg &mg, int which, size_t n) { if (mg.stage[which].n < n) mg.stage[which].alloc(n, false); return mg.stage[which].p; }
+
+__global__ void k_sum_into_all(int np, double *p0, double *p1, double *p2, double *p3, double *p4, double *p5, double *p6, double *p7, long long n) {
+    double *p[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < np; ++k) s += p[k][i];
+        for (int k = 0; k < np; ++k) p[k][i] = s;
+    }
+}
+// Sum a buffer (same length on every part) over all parts of the group; every part ends up with the total.
+template<class Sel> void grp_allreduce(vf_mg &lead, Sel sel, size_t n) {
+    if (!lead.grp || n == 0) return;
+    vf_group &G = *lead.grp;
+    if (G.comm) {
+        NcclApi &A = NcclApi::get(); double *p = sel(*G.parts[0]);
+        count_launch();
+        A.check(A.AllReduce(p, p, n, kNcclDouble, kNcclSum, G.comm, lead.ctx.stream), "ncclAllReduce");
+        return;
+    }
+    const int np = (int)G.parts.size();
+    if (np < 2) return;
+    if (np > 8) throw std::runtime_error("a local slab group holds at most 8 parts");
+    double *p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < np; ++k) p[k] = sel(*G.parts[k]);
+    count_launch();
+    const long long blocks = std::min<long long>((long long)(n + 255) / 256, 148LL * 8);
+    k_sum_into_all<<<(unsigned)blocks, 256, 0, lead.ctx.stream>>>(np, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], (long long)n);
+    VF_KERNEL_CHECK();
+}
+// Ghost-plane exchange of a nodal field of level l: every part receives its ghost planes (global planes sb - 1 and se + 1)
+// from the neighbour that owns them.  parity >= 0: only ghost planes whose global index has that parity (after a colour pass).
+template<class Sel> void grp_exchange(vf_mg &lead, int l, Sel sel, int parity = -1) {
+    if (!level_windowed(lead, l)) return;
+    vf_group &G = *lead.grp;
+    const int N = lead.N;
+    auto planePtr = [&](vf_mg &m, int c, int64_t globalPlane) {
+        const GridDesc &g = m.grid(l);
+        return sel(m) + (size_t)c * g.numNodes + (size_t)(globalPlane - g.xoff) * g.ns[0];
+    };
+    if (G.comm) {
+        vf_mg &m = *G.parts[0]; MGLevel &L = level(m, l); const GridDesc &g = m.grid(l);
+        const bool hasLeft = g.xoff < L.sb, hasRight = g.xoff + g.nn[0] - 1 > L.se;
+        const bool doLeft = hasLeft && (parity < 0 || ((L.sb - 1) & 1) == parity), doRight = hasRight && (parity < 0 || ((L.se + 1) & 1) == parity);
+        if (!doLeft && !doRight) return;
+        NcclApi &A = NcclApi::get();
+        count_launch();
+        A.check(A.GroupStart(), "ncclGroupStart");
+        for (int c = 0; c < N; ++c) {
+            if (doLeft)  { A.check(A.Send(planePtr(m, c, L.sb + 1), g.ns[0], kNcclDouble, G.rank - 1, G.comm, lead.ctx.stream), "ncclSend");
+                           A.check(A.Recv(planePtr(m, c, L.sb - 1), g.ns[0], kNcclDouble, G.rank - 1, G.comm, lead.ctx.stream), "ncclRecv"); }
+            if (doRight) { A.check(A.Send(planePtr(m, c, L.se - 1), g.ns[0], kNcclDouble, G.rank + 1, G.comm, lead.ctx.stream), "ncclSend");
+                           A.check(A.Recv(planePtr(m, c, L.se + 1), g.ns[0], kNcclDouble, G.rank + 1, G.comm, lead.ctx.stream), "ncclRecv"); }
+        }
+        A.check(A.GroupEnd(), "ncclGroupEnd");
+        return;
+    }
+    for (size_t i = 0; i + 1 < G.parts.size(); ++i) {
+        vf_mg &a = *G.parts[i], &b = *G.parts[i + 1];
+        MGLevel &La = level(a, l); const size_t bytes = (size_t)a.grid(l).ns[0] * sizeof(double);
+        const int64_t shared = La.se;              // == level(b, l).sb
+        if (parity >= 0 && ((shared + 1) & 1) != parity) continue;   // shared - 1 and shared + 1 have the same parity
+        for (int c = 0; c < N; ++c) {
+            count_launch();
+            VF_CUDA(cudaMemcpyAsync(planePtr(a, c, shared + 1), planePtr(b, c, shared + 1), bytes, cudaMemcpyDeviceToDevice, lead.ctx.stream));
+            VF_CUDA(cudaMemcpyAsync(planePtr(b, c, shared - 1), planePtr(a, c, shared - 1), bytes, cudaMemcpyDeviceToDevice, lead.ctx.stream));
+        }
+    }
+}
+// Completion of the sub-assembled stencil of a windowed level: the rows of a plane shared by two slabs are the sum of
+// both parts' sub-assemblies (each part assembled only the element layers it owns).
+void grp_complete_stencil(vf_mg &lead, int l) {
+    vf_group &G = *lead.grp;
+    const int NE = (lead.N == 3 ? 27 : 9) * lead.N * lead.N;
+    if (G.comm) {
+        vf_mg &m = *G.parts[0]; MGLevel &L = level(m, l); const GridDesc &g = L.g;
+        const bool hasLeft = g.xoff < L.sb, hasRight = g.xoff + g.nn[0] - 1 > L.se;
+        const size_t n = (size_t)stencil_plane_rows(g, 0) * NE;
+        NcclApi &A = NcclApi::get();
+        double *sendL = stage_buf(m, 0, 4 * n), *sendR = sendL + n, *recvL = sendR + n, *recvR = recvL + n;
+        if (hasLeft) launch_stencil_plane_pack(m.ctx, g, L.S.p, (int)(L.sb - g.xoff), sendL);
+        if (hasRight) launch_stencil_plane_pack(m.ctx, g, L.S.p, (int)(L.se - g.xoff), sendR);
+        A.check(A.GroupStart(), "ncclGroupStart");
+        if (hasLeft)  { A.check(A.Send(sendL, n, kNcclDouble, G.rank - 1, G.comm, m.ctx.stream), "ncclSend"); A.check(A.Recv(recvL, n, kNcclDouble, G.rank - 1, G.comm, m.ctx.stream), "ncclRecv"); }
+        if (hasRight) { A.check(A.Send(sendR, n, kNcclDouble, G.rank + 1, G.comm, m.ctx.stream), "ncclSend"); A.check(A.Recv(recvR, n, kNcclDouble, G.rank + 1, G.comm, m.ctx.stream), "ncclRecv"); }
+        A.check(A.GroupEnd(), "ncclGroupEnd");
+        if (hasLeft) launch_stencil_plane_add(m.ctx, g, L.S.p, (int)(L.sb - g.xoff), recvL);
+        if (hasRight) launch_stencil_plane_add(m.ctx, g, L.S.p, (int)(L.se - g.xoff), recvR);
+        return;
+    }
+    for (size_t i = 0; i + 1 < G.parts.size(); ++i) {
+        vf_mg &a = *G.parts[i], &b = *G.parts[i + 1];
+        MGLevel &La = level(a, l), &Lb = level(b, l);
+        const size_t n = (size_t)stencil_plane_rows(La.g, 0) * NE;
+        double *bufA = stage_buf(a, 0, n), *bufB = stage_buf(b, 0, n);
+        const int pa = (int)(La.se - La.g.xoff), pb = (int)(Lb.sb - Lb.g.xoff);
+        launch_stencil_plane_pack(a.ctx, La.g, La.S.p, pa, bufA);
+        launch_stencil_plane_pack(b.ctx, Lb.g, Lb.S.p, pb, bufB);
+        launch_stencil_plane_add(a.ctx, La.g, La.S.p, pa, bufB);
+        launch_stencil_plane_add(b.ctx, Lb.g, Lb.S.p, pb, bufA);
+    }
+}
+// zero the node planes of a replicated-level field that this part does not own (before summing the parts' contributions)
+void zero_unowned_planes(vf_mg &m, int l, double *f) {
+    const GridDesc &g = m.grid(l);
+    for (int c = 0; c < m.N; ++c) {
+        double *p = f + (size_t)c * g.numNodes;
+        if (g.ownLo > 0) VF_CUDA(cudaMemsetAsync(p, 0, (size_t)g.ownLo * g.ns[0] * sizeof(double), m.ctx.stream));
+        if (g.ownHi < g.nn[0]) VF_CUDA(cudaMemsetAsync(p + (size_t)g.ownHi * g.ns[0], 0, (size_t)(g.nn[0] - g.ownHi) * g.ns[0] * sizeof(double), m.ctx.stream));
+    }
+}
+
 // updateStiffnessMatrices (MultigridSolver.hh:846-905): rebuild all coarse operators for the current moduli/mask.
 // The reference's banded partial update (:907-1017) yields the same operators; here the (cheap) full rebuild is
 // always used and is skipped only when nothing changed since the last build.
-void mg_update_stiffness(vf_mg &mg, bool force = false) {
-    mg_sync_level_masks(mg);
-    if (!force && mg.stiffnessVersion == mg.sim->version) return;
-    const int nl = mg.numLevels();
-    for (int l = 1; l < nl; ++l) {
+// Slab groups: every part sub-assembles the windowed levels from the element layers it owns (Galerkin coarsening is
+// additive over elements), the rows on planes shared by two slabs are then completed by one exchange-add per level, and
+// the first replicated level is the all-reduced sum of the parts' sub-assemblies; deeper levels are coarsened redundantly.
+void mg_update_stiffness(vf_mg &lead, bool force = false) {
+    std::vector<vf_mg *> &P = parts_of(lead);
+    bool stale = force;
+    for (vf_mg *m : P) { mg_sync_level_masks(*m); stale = stale || m->stiffnessVersion != m->sim->version; }
+    if (!stale) return;
+    const int nl = lead.numLevels();
+    const int T = lead.grp ? lead.firstRep : 0;   // levels 1..T are sub-assembled per part, then completed
+    auto coarsen = [&](vf_mg &mg, int l) {
         MGLevel &L = *mg.lv[l];
         const size_t len = (size_t)L.g.numPos * (mg.N == 3 ? 27 : 9) * mg.N * mg.N;
         if (L.S.n != len) L.S.alloc(len, true);
         if (l == 1) launch_coarsen_from_moduli(mg.ctx, L.g, mg.sim->g, mg.sim->E.p, mg.cK0dev.p, L.S.p);
         else        launch_coarsen_stencil(mg.ctx, L.g, mg.lv[l - 1]->g, mg.lv[l - 1]->S.p, L.S.p);
+    };
+    for (int l = 1; l < nl && l <= T; ++l) for (vf_mg *m : P) coarsen(*m, l);
+    if (lead.grp) {
+        for (int l = 1; l < nl && l < T; ++l) grp_complete_stencil(lead, l);
+        if (T < nl) grp_allreduce(lead, [&](vf_mg &m) { return m.lv[T]->S.p; }, lead.lv[T]->S.n);
     }
+    for (int l = std::max(T + 1, 1); l < nl; ++l) for (vf_mg *m : P) coarsen(*m, l);
     if (nl > 1) {
-        MGLevel &C = *mg.lv[nl - 1];
-        // findFixedVars (TensorProductSimulator.hh:1181-1195): Dirichlet components and detached nodes
-        std::vector<uint8_t> fixed((size_t)C.g.numNodes * mg.N, 0);
-        for (long long n = 0; n < C.g.numNodes; ++n) {
-            const int cbd = (C.g.bd == 2) ? (int)(n % C.g.nn[2]) : (int)((n / C.g.nn[2]) % C.g.nn[1]);
-            const bool det = cbd >= C.g.nActive;
-            for (int c = 0; c < mg.N; ++c) if (det || ((C.nodeMask[n] >> c) & 1)) fixed[n * mg.N + c] = 1;
+        for (vf_mg *m : P) {
+            vf_mg &mg = *m; MGLevel &C = *mg.lv[nl - 1];
+            // findFixedVars (TensorProductSimulator.hh:1181-1195): Dirichlet components and detached nodes
+            std::vector<uint8_t> fixed((size_t)C.g.numNodes * mg.N, 0);
+            for (long long n = 0; n < C.g.numNodes; ++n) {
+                const int cbd = (C.g.bd == 2) ? (int)(n % C.g.nn[2]) : (int)((n / C.g.nn[2]) % C.g.nn[1]);
+                const bool det = cbd >= C.g.nActive;
+                for (int c = 0; c < mg.N; ++c) if (det || ((C.nodeMask[n] >> c) & 1)) fixed[n * mg.N + c] = 1;
+            }
+            mg.coarse.factor(mg.ctx, C.g, C.S.p, fixed);
         }
-        mg.coarse.factor(mg.ctx, C.g, C.S.p, fixed);
     }
-    mg.stiffnessVersion = mg.sim->version;
+    for (vf_mg *m : P) m->stiffnessVersion = m->sim->version;
 }
 
-void mg_apply_K(vf_mg &mg, int l, const double *u, const double *b, double *out, int mode, bool zeroDirichlet, double *dotOut = nullptr) {
-    if (l == 0) launch_apply_l0(mg.ctx, mg.sim->g, mg.sim->K0p, u, mg.sim->E.p, b, zeroDirichlet ? mg.dmask(0) : nullptr, out, mode, dotOut, mg.scratch.p);
-    else {
-        mg_update_stiffness(mg);
-        launch_apply_stencil(mg.ctx, mg.lv[l]->g, mg.lv[l]->S.p, u, b, zeroDirichlet ? mg.dmask(l) : nullptr, out, mode);
-    }
-}
-// computeResidual (:527-541): r = b - K u on non-detached nodes, Dirichlet components zeroed
-void mg_residual(vf_mg &mg, int l, const double *u, const double *b, double *r) { mg_apply_K(mg, l, u, b, r, APPLY_RESIDUAL, true); }
-
-// smoothingMulticoloredGS (:452-458): 2^N colour passes, colours reversed for backward sweeps (:417)
-void mg_smooth(vf_mg &mg, int l, double *u, const double *b, bool forward) {
-    const int nc = 1 << mg.N;
-    if (l > 0) mg_update_stiffness(mg);
-    if (l == 0 && mg.N == 3) { // 3D level 0: two same-colour nodes per thread
-        for (int i = 0; i < nc; ++i) launch_gs3_color_l0(mg.ctx, mg.sim->g, mg.sim->K0p, u, b, mg.sim->E.p, mg.dmask(0), forward ? i : (nc - 1 - i), forward);
-        return;
-    }
-    for (int i = 0; i < nc; ++i) {
-        const int color = forward ? i : (nc - 1 - i);
-        if (l == 0) launch_gs_l0(mg.ctx, mg.sim->g, mg.sim->K0p, u, b, mg.sim->E.p, mg.dmask(0), color, forward);
-        else        launch_gs_stencil(mg.ctx, mg.lv[l]->g, mg.lv[l]->S.p, u, b, mg.dmask(l), color, forward);
-    }
-}
-void mg_coarse_solve(vf_mg &mg, const double *f, double *x) {
-    mg_update_stiffness(mg);
-    mg.coarse.solve(mg.ctx, mg.grid(mg.numLevels() - 1), f, x);
-}
-void mg_enforce_dirichlet(vf_mg &mg, int l, double *u, bool zero) { // (:521-524)
-    if (zero || l > 0) launch_zero_dirichlet(mg.ctx, mg.grid(l), mg.dmask(l), u);
-    else launch_enforce_dirichlet(mg.ctx, mg.sim->g.numNodes, mg.N, (int)mg.sim->dirNodes.size(), mg.sim->dirNodesDev.p, mg.sim->dirMaskDev.p, mg.sim->dirValsDev.p, u);
-}
 double *lx(vf_mg &mg, int l) { return mg.lv[l]->x.p; }
 double *lb(vf_mg &mg, int l) { return mg.lv[l]->b.p; }
 double *lr(vf_mg &mg, int l) { return mg.lv[l]->r.p; }
+enum FieldId { F_X = 0, F_B, F_R, F_D, F_AD, F_USER };
+// Field selector shared by all parts of a group ("the same field on every part")
+struct Field {
+    int id, l; double *user0 = nullptr; // user pointer: only valid for single-part calls
+    double *operator()(vf_mg &m) const {
+        switch (id) { case F_X: return lx(m, l); case F_B: return lb(m, l); case F_R: return lr(m, l); case F_D: return m.d.p; case F_AD: return m.Ad.p; default: return user0; }
+    }
+};
+Field fu(const double *p) { return Field{F_USER, 0, const_cast<double *>(p)}; }
+Field fx(int l) { return Field{F_X, l}; } Field fb(int l) { return Field{F_B, l}; } Field fr(int l) { return Field{F_R, l}; }
+
+// out (=, +=, -=) K u  or  out = b - K u  on one part
+void part_apply_K(vf_mg &mg, int l, const double *u, const double *b, double *out, int mode, bool zeroDirichlet, double *dotOut = nullptr) {
+    if (l == 0) launch_apply_l0(mg.ctx, mg.sim->g, mg.sim->K0p, u, mg.sim->E.p, b, zeroDirichlet ? mg.dmask(0) : nullptr, out, mode, dotOut, mg.scratch.p);
+    else launch_apply_stencil(mg.ctx, mg.lv[l]->g, mg.lv[l]->S.p, u, b, zeroDirichlet ? mg.dmask(l) : nullptr, out, mode);
+}
+void mg_apply_K(vf_mg &lead, int l, Field u, Field b, Field out, int mode, bool zeroDirichlet, int dotSlot = -1) {
+    if (l > 0) mg_update_stiffness(lead);
+    for (vf_mg *m : parts_of(lead)) part_apply_K(*m, l, u(*m), mode == APPLY_RESIDUAL ? b(*m) : nullptr, out(*m), mode, zeroDirichlet, dotSlot >= 0 ? m->scalars.p + dotSlot : nullptr);
+    if (dotSlot >= 0) grp_allreduce(lead, [&](vf_mg &m) { return m.scalars.p + dotSlot; }, 1);
+}
+// computeResidual (:527-541): r = b - K u on non-detached nodes, Dirichlet components zeroed.  The ghost planes of r are
+// refreshed because the restriction that follows reads them.
+void mg_residual(vf_mg &lead, int l, Field u, Field b, Field r) {
+    mg_apply_K(lead, l, u, b, r, APPLY_RESIDUAL, true);
+    grp_exchange(lead, l, r);
+}
+
+// smoothingMulticoloredGS (:452-458): 2^N colour passes, colours reversed for backward sweeps (:417).  In a slab window the
+// colour of a node is the parity class of its GLOBAL index; after a pass that updated the parity of the ghost planes those
+// planes are received from the neighbours.
+void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward) {
+    const int nc = 1 << lead.N;
+    if (l > 0) mg_update_stiffness(lead);
+    for (int i = 0; i < nc; ++i) {
+        const int color = forward ? i : (nc - 1 - i);
+        for (vf_mg *mp : parts_of(lead)) {
+            vf_mg &mg = *mp; const GridDesc &g = mg.grid(l);
+            const int lc = (lead.N == 3) ? (color ^ ((g.xoff & 1) << 2)) : color;   // local parity class of this global colour
+            if (l == 0 && mg.N == 3) launch_gs3_color_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), lc, forward);
+            else if (l == 0)         launch_gs_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), lc, forward);
+            else                     launch_gs_stencil(mg.ctx, g, mg.lv[l]->S.p, u(mg), b(mg), mg.dmask(l), lc, forward);
+        }
+        if (lead.N == 3) grp_exchange(lead, l, u, (color >> 2) & 1);
+    }
+}
+// coarsest-level solve on the replicated coarsest grid
+void mg_coarse_solve(vf_mg &lead, Field f, Field x) {
+    mg_update_stiffness(lead);
+    for (vf_mg *m : parts_of(lead)) m->coarse.solve(m->ctx, m->grid(m->numLevels() - 1), f(*m), x(*m));
+}
+void mg_enforce_dirichlet(vf_mg &lead, int l, Field u, bool zero) { // (:521-524)
+    for (vf_mg *mp : parts_of(lead)) {
+        vf_mg &mg = *mp;
+        if (zero || l > 0) launch_zero_dirichlet(mg.ctx, mg.grid(l), mg.dmask(l), u(mg));
+        else launch_enforce_dirichlet(mg.ctx, mg.sim->g.numNodes, mg.N, (int)mg.sim->dirNodes.size(), mg.sim->dirNodesDev.p, mg.sim->dirMaskDev.p, mg.sim->dirValsDev.p, u(mg));
+    }
+}
+// restriction (:216-262) onto level l + 1.  Onto the first replicated level every part restricts the coarse planes it owns
+// and the parts' contributions are summed; between windowed levels the coarse ghost planes are received.
+void mg_restrict(vf_mg &lead, int l, Field fine, Field coarse) {
+    for (vf_mg *m : parts_of(lead)) launch_restrict(m->ctx, m->grid(l), m->grid(l + 1), fine(*m), coarse(*m));
+    if (!lead.grp) return;
+    if (l + 1 == lead.firstRep) {
+        for (vf_mg *m : parts_of(lead)) zero_unowned_planes(*m, l + 1, coarse(*m));
+        grp_allreduce(lead, coarse, (size_t)lead.grid(l + 1).numNodes * lead.N);
+    } else grp_exchange(lead, l + 1, coarse);
+}
+void mg_prolong(vf_mg &lead, int l, Field coarse, Field fine, bool accumulate) { // interpolation / accum_interpolation (:178-212), level l + 1 -> l
+    for (vf_mg *m : parts_of(lead)) launch_prolong(m->ctx, m->grid(l), m->grid(l + 1), coarse(*m), fine(*m), accumulate);
+}
 
 // vcycle (:617-658)
-void mg_vcycle(vf_mg &mg, int l, int nsmooth, bool residualSystem) {
-    const int coarsest = mg.numLevels() - 1;
-    if (l == coarsest) { mg_coarse_solve(mg, lb(mg, l), lx(mg, l)); return; }
-    mg_enforce_dirichlet(mg, l, lx(mg, l), residualSystem);
-    for (int i = 0; i < nsmooth; ++i) mg_smooth(mg, l, lx(mg, l), lb(mg, l), true);
-    mg_residual(mg, l, lx(mg, l), lb(mg, l), lr(mg, l));
-    launch_restrict(mg.ctx, mg.grid(l), mg.grid(l + 1), lr(mg, l), lb(mg, l + 1));
-    launch_masked_zero(mg.ctx, mg.grid(l + 1), lx(mg, l + 1), 4 /* VOXELFEM_SIMD_WIDTH margin (:644) */);
-    mg_vcycle(mg, l + 1, nsmooth, true);
-    launch_prolong(mg.ctx, mg.grid(l), mg.grid(l + 1), lx(mg, l + 1), lx(mg, l), true);
-    for (int i = 0; i < nsmooth; ++i) mg_smooth(mg, l, lx(mg, l), lb(mg, l), !mg.symmetricGS);
+void mg_vcycle(vf_mg &lead, int l, int nsmooth, bool residualSystem) {
+    const int coarsest = lead.numLevels() - 1;
+    if (l == coarsest) { mg_coarse_solve(lead, fb(l), fx(l)); return; }
+    mg_enforce_dirichlet(lead, l, fx(l), residualSystem);
+    for (int i = 0; i < nsmooth; ++i) mg_smooth(lead, l, fx(l), fb(l), true);
+    mg_residual(lead, l, fx(l), fb(l), fr(l));
+    mg_restrict(lead, l, fr(l), fb(l + 1));
+    for (vf_mg *m : parts_of(lead)) launch_masked_zero(m->ctx, m->grid(l + 1), lx(*m, l + 1), 4 /* VOXELFEM_SIMD_WIDTH margin (:644) */);
+    mg_vcycle(lead, l + 1, nsmooth, true);
+    mg_prolong(lead, l, fx(l + 1), fx(l), true);
+    for (int i = 0; i < nsmooth; ++i) mg_smooth(lead, l, fx(l), fb(l), !lead.symmetricGS);
 }
 // fullMultigrid (:587-609)
-void mg_fmg(vf_mg &mg, int l, int nsmooth, bool residualSystem) {
-    const int coarsest = mg.numLevels() - 1;
-    if (l == coarsest) { mg_coarse_solve(mg, lb(mg, l), lx(mg, l)); return; }
-    launch_restrict(mg.ctx, mg.grid(l), mg.grid(l + 1), lb(mg, l), lb(mg, l + 1));
-    mg_fmg(mg, l + 1, nsmooth, residualSystem);
-    launch_prolong(mg.ctx, mg.grid(l), mg.grid(l + 1), lx(mg, l + 1), lx(mg, l), false);
-    mg_vcycle(mg, l, nsmooth, residualSystem);
+void mg_fmg(vf_mg &lead, int l, int nsmooth, bool residualSystem) {
+    const int coarsest = lead.numLevels() - 1;
+    if (l == coarsest) { mg_coarse_solve(lead, fb(l), fx(l)); return; }
+    mg_restrict(lead, l, fb(l), fb(l + 1));
+    mg_fmg(lead, l + 1, nsmooth, residualSystem);
+    mg_prolong(lead, l, fx(l + 1), fx(l), false);
+    mg_vcycle(lead, l, nsmooth, residualSystem);
 }
 // solve (:546-573) operating on lv[0].x (initial guess already there) and lv[0].b
-void mg_solve_inplace(vf_mg &mg, int numSteps, int nsmooth, bool zeroDirichlet, bool fmg) {
+void mg_solve_inplace(vf_mg &lead, int numSteps, int nsmooth, bool zeroDirichlet, bool fmg) {
     if (numSteps == 0) return;
     int start = 0;
-    if (fmg) { mg_fmg(mg, 0, nsmooth, zeroDirichlet); start = 1; }
-    for (int i = start; i < numSteps; ++i) mg_vcycle(mg, 0, nsmooth, zeroDirichlet);
+    if (fmg) { mg_fmg(lead, 0, nsmooth, zeroDirichlet); start = 1; }
+    for (int i = start; i < numSteps; ++i) mg_vcycle(lead, 0, nsmooth, zeroDirichlet);
 }
 
 double read_scalar(vf_mg &mg, int slot) {
@@ -496,59 +733,80 @@ double read_scalar(vf_mg &mg, int slot) {
     VF_CUDA(cudaStreamSynchronize(mg.ctx.stream));
     return mg.hostScalars[slot];
 }
+// masked dot product over the owned nodes of all parts -> scalar slot (every part gets the total)
+void mg_dot(vf_mg &lead, Field a, Field b, int slot) {
+    for (vf_mg *m : parts_of(lead)) launch_masked_dot(m->ctx, m->sim->g, a(*m), b(*m), m->scalars.p + slot, m->scratch.p);
+    grp_allreduce(lead, [&](vf_mg &m) { return m.scalars.p + slot; }, 1);
+}
 
 void sim_direct_solve(vf_sim &s, const double *fDev, double *xDev); // below
 
-// preconditionedConjugateGradient (:1047-1152), device-resident x and b
-void mg_pcg(vf_mg &mg, double *x, const double *b, int maxIter, double tol, int mgIterations, int mgSmoothing, bool fmg, bool dirichletOK,
+// preconditionedConjugateGradient (:1047-1152), device-resident x and b (one pointer per part of the group)
+void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter, double tol, int mgIterations, int mgSmoothing, bool fmg, bool dirichletOK,
             vf_pcg_callback cb, void *user) {
-    vf_sim &sim = *mg.sim; const GridDesc &g = sim.g;
-    mg.lastResiduals.clear(); mg.lastIters = 0;
-    mg_sync_level_masks(mg);
-    double *r = lb(mg, 0), *s = lx(mg, 0);
-    double *sc = mg.scalars.p;
-    if (mg.numLevels() == 1) { // (:1057-1065)
-        mg_residual(mg, 0, x, b, r);
-        launch_dot_plain(mg.ctx, g.numNodes * mg.N, r, r, sc + SC_RSQ, mg.scratch.p);
-        launch_dot_plain(mg.ctx, g.numNodes * mg.N, b, b, sc + SC_BSQ, mg.scratch.p);
-        const double rs = read_scalar(mg, SC_RSQ), bs = read_scalar(mg, SC_BSQ);
-        if (rs < tol * tol * bs) return;
-        sim_direct_solve(sim, b, x);
-        mg_residual(mg, 0, x, b, r);
-        launch_dot_plain(mg.ctx, g.numNodes * mg.N, r, r, sc + SC_RSQ, mg.scratch.p);
-        const double rn = std::sqrt(read_scalar(mg, SC_RSQ));
-        mg.lastIters = 1; mg.lastResiduals.push_back(rn);
+    std::vector<vf_mg *> &P = parts_of(lead);
+    const int N = lead.N;
+    lead.lastResiduals.clear(); lead.lastIters = 0;
+    for (vf_mg *m : P) mg_sync_level_masks(*m);
+    const Field r = fb(0), s = fx(0), d{F_D, 0}, Ad{F_AD, 0};
+    auto X = [&](vf_mg &m) { for (size_t i = 0; i < P.size(); ++i) if (P[i] == &m) return xs[i]; return (double *)nullptr; };
+    auto B = [&](vf_mg &m) { for (size_t i = 0; i < P.size(); ++i) if (P[i] == &m) return const_cast<double *>(bs[i]); return (double *)nullptr; };
+    if (lead.numLevels() == 1) { // (:1057-1065)
+        vf_sim &sim = *lead.sim; const GridDesc &g = sim.g; double *sc = lead.scalars.p;
+        part_apply_K(lead, 0, xs[0], bs[0], lb(lead, 0), APPLY_RESIDUAL, true);
+        launch_dot_plain(lead.ctx, g.numNodes * N, lb(lead, 0), lb(lead, 0), sc + SC_RSQ, lead.scratch.p);
+        launch_dot_plain(lead.ctx, g.numNodes * N, bs[0], bs[0], sc + SC_BSQ, lead.scratch.p);
+        const double rs = read_scalar(lead, SC_RSQ), bsq1 = read_scalar(lead, SC_BSQ);
+        if (rs < tol * tol * bsq1) return;
+        sim_direct_solve(sim, bs[0], xs[0]);
+        part_apply_K(lead, 0, xs[0], bs[0], lb(lead, 0), APPLY_RESIDUAL, true);
+        launch_dot_plain(lead.ctx, g.numNodes * N, lb(lead, 0), lb(lead, 0), sc + SC_RSQ, lead.scratch.p);
+        const double rn = std::sqrt(read_scalar(lead, SC_RSQ));
+        lead.lastIters = 1; lead.lastResiduals.push_back(rn);
         if (cb) cb(1, rn, user);
         return;
     }
-    if (!dirichletOK) mg_enforce_dirichlet(mg, 0, x, false);
-    launch_masked_dot(mg.ctx, g, b, b, sc + SC_BSQ, mg.scratch.p);
-    mg_residual(mg, 0, x, b, r);
-    launch_masked_dot(mg.ctx, g, r, r, sc + SC_RSQ, mg.scratch.p);
-    const double bsq = read_scalar(mg, SC_BSQ);
-    double rsq = read_scalar(mg, SC_RSQ);
+    for (vf_mg *m : P) {
+        if (!dirichletOK) launch_enforce_dirichlet(m->ctx, m->sim->g.numNodes, N, (int)m->sim->dirNodes.size(), m->sim->dirNodesDev.p, m->sim->dirMaskDev.p, m->sim->dirValsDev.p, X(*m));
+        launch_masked_dot(m->ctx, m->sim->g, B(*m), B(*m), m->scalars.p + SC_BSQ, m->scratch.p);
+        part_apply_K(*m, 0, X(*m), B(*m), r(*m), APPLY_RESIDUAL, true);       // computeResidual(0, x, b, r) (:1080)
+    }
+    grp_allreduce(lead, [&](vf_mg &m) { return m.scalars.p + SC_BSQ; }, 1);
+    grp_exchange(lead, 0, r);
+    mg_dot(lead, r, r, SC_RSQ);
+    const double bsq = read_scalar(lead, SC_BSQ);
+    double rsq = read_scalar(lead, SC_RSQ);
     if (std::isnan(rsq)) throw std::logic_error("NaN encountered");
     int i = 0; bool first = true; int cur = SC_RMR_A, old = SC_RMR_B;
     while ((i++ < maxIter) && (rsq > tol * tol * bsq)) {
         if (mgIterations > 0 && mgSmoothing > 0) {
-            mg_update_stiffness(mg); // lazily, first iteration (:1104-1107)
-            if (!fmg) VF_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * g.numNodes * mg.N, mg.ctx.stream)); // applyPreconditionerInv: zero initial guess (:577-580); the FMG cycle overwrites s by interpolation (:600)
-            mg_solve_inplace(mg, mgIterations, mgSmoothing, true, fmg);
+            mg_update_stiffness(lead); // lazily, first iteration (:1104-1107)
+            // applyPreconditionerInv: zero initial guess (:577-580); the FMG cycle overwrites s by interpolation (:600)
+            if (!fmg) for (vf_mg *m : P) VF_CUDA(cudaMemsetAsync(s(*m), 0, sizeof(double) * m->sim->g.numNodes * N, m->ctx.stream));
+            mg_solve_inplace(lead, mgIterations, mgSmoothing, true, fmg);
         } else {
-            VF_CUDA(cudaMemcpyAsync(s, r, sizeof(double) * g.numNodes * mg.N, cudaMemcpyDeviceToDevice, mg.ctx.stream)); // s = r (:578, :1118)
+            for (vf_mg *m : P) VF_CUDA(cudaMemcpyAsync(s(*m), r(*m), sizeof(double) * m->sim->g.numNodes * N, cudaMemcpyDeviceToDevice, m->ctx.stream)); // s = r (:578, :1118)
         }
-        launch_zero_dirichlet(mg.ctx, g, mg.dmask(0), s);                                 // (:1122)
+        for (vf_mg *m : P) launch_zero_dirichlet(m->ctx, m->sim->g, m->dmask(0), s(*m));            // (:1122)
         std::swap(cur, old);
-        launch_masked_dot(mg.ctx, g, r, s, sc + cur, mg.scratch.p);                      // r_Minv_r (:1124)
-        launch_cg_direction(mg.ctx, g, s, mg.d.p, sc + cur, sc + old, first);           // d = s + beta d (:1125-1126)
+        mg_dot(lead, r, s, cur);                                                                    // r_Minv_r (:1124)
+        for (vf_mg *m : P) launch_cg_direction(m->ctx, m->sim->g, s(*m), m->d.p, m->scalars.p + cur, m->scalars.p + old, first); // d = s + beta d (:1125-1126)
         first = false;
-        mg_apply_K(mg, 0, mg.d.p, nullptr, mg.Ad.p, APPLY_SET, true, sc + SC_DAD);      // Ad = K d, zero Dirichlet (:1129-1130), fused d . Ad (:1134)
-        launch_cg_update(mg.ctx, g, x, mg.d.p, r, mg.Ad.p, sc + cur, sc + SC_DAD, sc + SC_RSQ, mg.scratch.p); // (:1134-1143)
-        rsq = read_scalar(mg, SC_RSQ);
+        mg_apply_K(lead, 0, d, d, Ad, APPLY_SET, true, SC_DAD);                                     // Ad = K d, zero Dirichlet (:1129-1130), fused d . Ad (:1134)
+        grp_exchange(lead, 0, Ad);                                                                  // keeps r consistent on the ghost planes (r feeds the next restriction)
+        for (vf_mg *m : P) launch_cg_update(m->ctx, m->sim->g, X(*m), m->d.p, r(*m), m->Ad.p, m->scalars.p + cur, m->scalars.p + SC_DAD, m->scalars.p + SC_RSQ, m->scratch.p); // (:1134-1143)
+        grp_allreduce(lead, [&](vf_mg &m) { return m.scalars.p + SC_RSQ; }, 1);
+        rsq = read_scalar(lead, SC_RSQ);
         if (std::isnan(rsq)) throw std::logic_error("NaN encountered at iteration" + std::to_string(i));
-        mg.lastIters = i; mg.lastResiduals.push_back(std::sqrt(rsq));
+        lead.lastIters = i; lead.lastResiduals.push_back(std::sqrt(rsq));
         if (cb) cb(i, std::sqrt(rsq), user);
     }
+}
+void mg_pcg(vf_mg &mg, double *x, const double *b, int maxIter, double tol, int mgIterations, int mgSmoothing, bool fmg, bool dirichletOK,
+            vf_pcg_callback cb, void *user) {
+    if (mg.grp && mg.grp->parts.size() != 1) throw std::runtime_error("use vf_group_pcg_dev for a multi-part slab group");
+    double *xs[1] = {x}; const double *bs[1] = {b};
+    mg_pcg(mg, xs, bs, maxIter, tol, mgIterations, mgSmoothing, fmg, dirichletOK, cb, user);
 }
 
 // TPS::solve at level 0 (TensorProductSimulator.hh:1198-1230) through the dense GPU solver
@@ -619,20 +877,38 @@ int64_t vf_kernel_launch_count(void) { return vf::g_launches.load(); }
 void vf_reset_kernel_launch_count(void) { vf::g_launches.store(0); }
 
 // ---- simulator ----------------------------------------------------------------------------
-int vf_sim_create(int dim, const int64_t *ne, const double *dmin, const double *dmax, vf_sim **out) {
-    VF_TRY
+static vf_sim *sim_create_common(int dim, const int64_t *gne, const double *dmin, const double *dmax, bool window, int64_t slabBegin, int64_t slabEnd, vf_sim *share) {
     if (dim != 2 && dim != 3) throw std::runtime_error("dim must be 2 or 3");
     ensure_device();
     auto s = std::make_unique<vf_sim>();
     s->N = dim;
+    int64_t ne[3] = {1, 1, 1};
     for (int d = 0; d < dim; ++d) {
-        if (ne[d] < 1) throw std::runtime_error("grid must have at least one element per dimension");
-        s->ne[d] = ne[d]; s->nn[d] = ne[d] + 1; s->dmin[d] = dmin[d]; s->dmax[d] = dmax[d];
-        s->spacing[d] = (dmax[d] - dmin[d]) / (double(s->nn[d]) - 1.0);
-        s->stretch[d] = (dmax[d] - dmin[d]) / double(ne[d]);
+        if (gne[d] < 1) throw std::runtime_error("grid must have at least one element per dimension");
+        ne[d] = gne[d]; s->dmin[d] = dmin[d]; s->dmax[d] = dmax[d];
+        s->spacing[d] = (dmax[d] - dmin[d]) / (double(gne[d] + 1) - 1.0);
+        s->stretch[d] = (dmax[d] - dmin[d]) / double(gne[d]);
     }
+    int64_t wlo = 0;
+    if (window) {
+        if (dim != 3) throw std::runtime_error("slab windows are implemented for 3D grids");
+        if (slabBegin < 0 || slabEnd > gne[0] || slabEnd - slabBegin < 2) throw std::runtime_error("slab must hold at least two element layers inside the grid");
+        wlo = std::max<int64_t>(slabBegin - 1, 0);
+        const int64_t whi = std::min<int64_t>(slabEnd + 1, gne[0]);
+        ne[0] = whi - wlo;
+        s->window = true; s->gne0 = gne[0]; s->xoff = wlo; s->slabBegin = slabBegin; s->slabEnd = slabEnd;
+    }
+    for (int d = 0; d < dim; ++d) { s->ne[d] = ne[d]; s->nn[d] = ne[d] + 1; }
     s->g = make_grid(dim, ne);
-    VF_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    if (window) {
+        GridDesc &g = s->g;
+        g.xoff = (int)wlo;
+        g.ownLo = (int)(slabBegin - wlo); g.ownHi = (int)((slabEnd == gne[0] ? slabEnd + 1 : slabEnd) - wlo);
+        g.cmpLo = (int)(slabBegin - wlo); g.cmpHi = (int)(slabEnd + 1 - wlo);
+        g.oeLo = (int)(slabBegin - wlo);  g.oeHi = (int)(slabEnd - wlo);
+    }
+    if (share) { s->stream = share->stream; s->ownsStream = false; }
+    else VF_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->ctx.stream = s->stream; s->ctx.prof = &s->prof;
     s->rho.alloc(s->g.numElems, true); s->E.alloc(s->g.numElems, true);
     s->scratch.alloc(reduce_scratch_doubles(), true); s->scalars.alloc(SC_COUNT, true);
@@ -640,10 +916,19 @@ int vf_sim_create(int dim, const int64_t *ne, const double *dmin, const double *
     s->uploadBCs();
     s->setIsotropic(1.0, 0.0);  // TensorProductSimulator.hh:2114
     s->updateModuli();
-    *out = s.release();
-    VF_CATCH
+    return s.release();
 }
-int vf_sim_destroy(vf_sim *s) { VF_TRY if (s) { if (s->stream) { cudaStreamSynchronize(s->stream); } cudaStream_t st = s->stream; delete s; if (st) cudaStreamDestroy(st); } VF_CATCH }
+int vf_sim_create(int dim, const int64_t *ne, const double *dmin, const double *dmax, vf_sim **out) {
+    VF_TRY *out = sim_create_common(dim, ne, dmin, dmax, false, 0, 0, nullptr); VF_CATCH
+}
+int vf_sim_create_slab(int dim, const int64_t *ne_global, const double *dmin, const double *dmax, int64_t slab_begin, int64_t slab_end,
+                       vf_sim *share_stream_with, vf_sim **out) {
+    VF_TRY *out = sim_create_common(dim, ne_global, dmin, dmax, true, slab_begin, slab_end, share_stream_with); VF_CATCH
+}
+int vf_sim_window(const vf_sim *s, int64_t *plane_lo, int64_t *plane_hi, int64_t *own_lo, int64_t *own_hi) {
+    VF_TRY *plane_lo = s->xoff; *plane_hi = s->xoff + s->nn[0] - 1; *own_lo = s->xoff + s->g.ownLo; *own_hi = s->xoff + s->g.ownHi - 1; VF_CATCH
+}
+int vf_sim_destroy(vf_sim *s) { VF_TRY if (s) { if (s->stream) { cudaStreamSynchronize(s->stream); } cudaStream_t st = s->ownsStream ? s->stream : nullptr; delete s; if (st) cudaStreamDestroy(st); } VF_CATCH }
 int64_t vf_sim_num_nodes(const vf_sim *s) { return s->g.numNodes; }
 int64_t vf_sim_num_elements(const vf_sim *s) { return s->g.numElems; }
 int vf_sim_set_elasticity_tensor(vf_sim *s, const double *D) {
@@ -673,11 +958,11 @@ int vf_sim_apply_bc_regions(vf_sim *s, int nreg, const int32_t *kind, const int3
     BCBuilder b(*s);
     for (int r = 0; r < nreg; ++r) {
         std::vector<int64_t> idx[3];
-        const bool any = s->boxRanges(bmin + 3 * r, bmax + 3 * r, idx);
+        double cnt = 0;
+        const bool any = s->boxRanges(bmin + 3 * r, bmax + 3 * r, idx, &cnt);
         const double *val = values + 3 * r;
         if (kind[r] == 1) {
             if (!any) throw std::runtime_error("Force constraint region unmatched");
-            const double cnt = double(idx[0].size() * idx[1].size() * idx[2].size());
             double f[3]; for (int c = 0; c < s->N; ++c) f[c] = val[c] / cnt;
             for (int64_t i : idx[0]) for (int64_t j : idx[1]) for (int64_t k : idx[2]) b.setForce(s->flatNode(i, j, k), f);
         } else if (kind[r] == 0) {
@@ -700,7 +985,7 @@ int vf_sim_apply_symmetry_conditions(vf_sim *s, int axes_mask, int max_face_mask
         const double target = ((max_face_mask >> d) & 1) ? s->dmax[d] : s->dmin[d];
         for (int64_t n = 0; n < s->g.numNodes; ++n) {
             int64_t c[3]; int64_t r = n; for (int a = s->N - 1; a >= 0; --a) { c[a] = r % s->nn[a]; r /= s->nn[a]; }
-            if (std::abs(s->dmin[d] + double(c[d]) * s->spacing[d] - target) < 1e-10) b.setDirichletComponent(n, d, 0.0);
+            if (std::abs(s->dmin[d] + double(c[d] + (d == 0 ? s->xoff : 0)) * s->spacing[d] - target) < 1e-10) b.setDirichletComponent(n, d, 0.0);
         }
     }
     b.apply(); VF_CATCH
@@ -762,48 +1047,79 @@ int vf_sim_solve(vf_sim *s, const double *f, double *u) {
 }
 
 // ---- multigrid -----------------------------------------------------------------------------
-int vf_mg_create(vf_sim *fine, int levels, vf_mg **out) {
-    VF_TRY
+// Dirichlet coarsening (MultigridSolver.hh:58-103): a fine Dirichlet node constrains, with the same component mask and
+// zero value, every coarse node on the vertex/edge/face/cell of the coarse element it lies on.  Index arithmetic is done
+// on global plane indices so that it also serves slab windows (coarse nodes outside the window are skipped).
+static void coarsen_dirichlet_mask(int N, const MGLevel &F, const std::vector<uint8_t> &fineMask, MGLevel &L) {
+    L.nodeMask.assign(L.g.numNodes, 0);
+    int64_t fnn[3] = {1, 1, 1}, cnn[3] = {1, 1, 1};
+    for (int d = 0; d < N; ++d) { fnn[d] = F.ne[d] + 1; cnn[d] = L.ne[d] + 1; }
+    const int64_t fo = F.g.xoff, co = L.g.xoff;
+    for (int64_t fn = 0; fn < F.g.numNodes; ++fn) {
+        const uint8_t m = fineMask[fn]; if (!m) continue;
+        int64_t c[3] = {0, 0, 0}; { int64_t r = fn; for (int d = N - 1; d >= 0; --d) { c[d] = r % fnn[d]; r /= fnn[d]; } }
+        if (N == 3) c[0] += fo;
+        for (int k = 0; k < (1 << N); ++k) {
+            int64_t cn = 0; bool ok = true;
+            for (int d = 0; d < N; ++d) {
+                const int bit = (k >> d) & 1;
+                if ((c[d] & 1) == 0 && bit) { ok = false; break; }
+                int64_t q = (c[d] >> 1) + bit;
+                if (N == 3 && d == 0) q -= co;
+                if (q < 0 || q >= cnn[d]) { ok = false; break; }
+                cn = cn * cnn[d] + q;
+            }
+            if (ok) L.nodeMask[cn] |= m;
+        }
+    }
+}
+
+static vf_mg *mg_create_common(vf_sim *fine, int levels, int firstRep) {
     if (levels < 0) throw std::runtime_error("numCoarseningLevels must be >= 0");
     auto mg = std::make_unique<vf_mg>();
     mg->sim = fine; mg->N = fine->N; mg->ctx = fine->ctx;
     const int N = fine->N;
-    int64_t ne[3] = {fine->ne[0], fine->ne[1], fine->ne[2]};
+    const bool slab = fine->window;
+    if (slab) {
+        if (levels < 1) throw std::runtime_error("a slab-partitioned solver needs at least one coarsening level");
+        firstRep = std::min(std::max(firstRep, 1), levels);     // the coarsest level is always replicated
+        mg->firstRep = firstRep;
+    }
+    int64_t gne[3] = {slab ? fine->gne0 : fine->ne[0], fine->ne[1], fine->ne[2]};
     for (int l = 0; l <= levels; ++l) {
         auto L = std::make_unique<MGLevel>();
         if (l > 0) {
             for (int d = 0; d < N; ++d) {
-                if (ne[d] % 2 == 1) throw std::runtime_error("Grid size currently must be divisible by 2^numCoarseningLevels (nonuniform coarsening not yet implemented)");
-                ne[d] /= 2;
+                if (gne[d] % 2 == 1) throw std::runtime_error("Grid size currently must be divisible by 2^numCoarseningLevels (nonuniform coarsening not yet implemented)");
+                gne[d] /= 2;
             }
         }
+        int64_t ne[3] = {gne[0], gne[1], gne[2]};
+        L->gne0 = gne[0];
+        if (slab) {
+            const int64_t div = int64_t(1) << l;
+            const bool win = l < firstRep;
+            if (l <= firstRep && (fine->slabBegin % div || fine->slabEnd % div)) throw std::runtime_error("slab boundaries must be multiples of 2^(first replicated level)");
+            L->sb = fine->slabBegin / div; L->se = fine->slabEnd / div; L->windowed = win;
+            if (win && L->se - L->sb < 1) throw std::runtime_error("slab too thin for the requested number of windowed levels");
+            const int64_t wlo = win ? std::max<int64_t>(L->sb - 1, 0) : 0, whi = win ? std::min<int64_t>(L->se + 1, gne[0]) : gne[0];
+            ne[0] = whi - wlo;
+            L->g = make_grid(N, ne);
+            GridDesc &g = L->g;
+            g.xoff = (int)wlo;
+            if (l <= firstRep) { g.ownLo = (int)(L->sb - wlo); g.ownHi = (int)((L->se == gne[0] ? L->se + 1 : L->se) - wlo); }
+            if (win) { g.cmpLo = (int)(L->sb - wlo); g.cmpHi = (int)(L->se + 1 - wlo); g.oeLo = (int)(L->sb - wlo); g.oeHi = (int)(L->se - wlo); }
+            if (l == 0 && (g.xoff != fine->g.xoff || g.nn[0] != fine->g.nn[0])) throw std::logic_error("slab window mismatch");
+        } else {
+            L->g = make_grid(N, ne);
+        }
         for (int d = 0; d < 3; ++d) L->ne[d] = ne[d];
-        L->g = make_grid(N, ne);
         L->stretchBD = (fine->dmax[1] - fine->dmin[1]) / double(ne[1]);
         const size_t len = (size_t)L->g.numNodes * N;
         L->x.alloc(len, true); L->b.alloc(len, true); L->r.alloc(len, true);
         if (l == 0) L->nodeMask = fine->nodeMask;
         else {
-            // Dirichlet coarsening (MultigridSolver.hh:58-103): a fine Dirichlet node constrains, with the same component
-            // mask and zero value, every coarse node on the vertex/edge/face/cell of the coarse element it lies on.
-            const MGLevel &F = *mg->lv.back();
-            L->nodeMask.assign(L->g.numNodes, 0);
-            int64_t fnn[3] = {1, 1, 1}, cnn[3] = {1, 1, 1};
-            for (int d = 0; d < N; ++d) { fnn[d] = F.ne[d] + 1; cnn[d] = ne[d] + 1; }
-            for (int64_t fn = 0; fn < F.g.numNodes; ++fn) {
-                const uint8_t m = F.nodeMask[fn]; if (!m) continue;
-                int64_t c[3] = {0, 0, 0}; { int64_t r = fn; for (int d = N - 1; d >= 0; --d) { c[d] = r % fnn[d]; r /= fnn[d]; } }
-                for (int k = 0; k < (1 << N); ++k) {
-                    int64_t cn = 0; bool ok = true;
-                    for (int d = 0; d < N; ++d) {
-                        const int bit = (k >> d) & 1;
-                        if ((c[d] & 1) == 0 && bit) { ok = false; break; }
-                        const int64_t q = (c[d] >> 1) + bit;
-                        cn = cn * cnn[d] + q;
-                    }
-                    if (ok) L->nodeMask[cn] |= m;
-                }
-            }
+            coarsen_dirichlet_mask(N, *mg->lv.back(), mg->lv.back()->nodeMask, *L);
             L->dmask.alloc(L->g.numNodes, false); L->dmask.upload(L->nodeMask.data(), L->g.numNodes, fine->stream);
             VF_CUDA(cudaStreamSynchronize(fine->stream));
         }
@@ -840,9 +1156,107 @@ int vf_mg_create(vf_sim *fine, int levels, vf_mg **out) {
     mg->scalars.alloc(SC_COUNT, true); mg->scratch.alloc(reduce_scratch_doubles(), true);
     VF_CUDA(cudaMallocHost(&mg->hostScalars, SC_COUNT * sizeof(double)));
     mg_sync_level_masks(*mg);
-    *out = mg.release();
+    return mg.release();
+}
+int vf_mg_create(vf_sim *fine, int levels, vf_mg **out) {
+    VF_TRY if (fine->window) throw std::runtime_error("use vf_mg_create_slab for a slab-window simulator");
+    *out = mg_create_common(fine, levels, INT_MAX); VF_CATCH
+}
+int vf_mg_create_slab(vf_sim *fine, int levels, int first_replicated_level, vf_mg **out) {
+    VF_TRY if (!fine->window) throw std::runtime_error("vf_mg_create_slab needs a simulator created with vf_sim_create_slab");
+    *out = mg_create_common(fine, levels, first_replicated_level); VF_CATCH
+}
+// ---- slab groups ---------------------------------------------------------------------------
+namespace {
+// Dirichlet masks of the coarse levels must also be right on the ghost planes (they are applied pointwise to fields whose
+// ghost copies have to stay identical to the owner's values) and on the replicated levels (every part only saw its own
+// window).  Done once at group creation through the ordinary field exchanges: bit c of the mask travels as component c.
+__global__ void k_mask_to_field(long long nn, int N, const uint8_t *__restrict__ m, double *__restrict__ f) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < nn) for (int c = 0; c < N; ++c) f[c * nn + n] = ((m[n] >> c) & 1) ? 1.0 : 0.0;
+}
+__global__ void k_field_to_mask(long long nn, int N, const double *__restrict__ f, uint8_t *__restrict__ m) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < nn) { unsigned v = 0; for (int c = 0; c < N; ++c) if (f[c * nn + n] > 0.5) v |= 1u << c; m[n] = (uint8_t)v; }
+}
+void group_complete_masks(vf_mg &lead) {
+    std::vector<vf_mg *> &P = parts_of(lead);
+    const int nl = lead.numLevels(), N = lead.N;
+    for (int l = 1; l < nl; ++l) {
+        for (vf_mg *m : P) {
+            MGLevel &L = *m->lv[l];
+            coarsen_dirichlet_mask(N, *m->lv[l - 1], m->lv[l - 1]->nodeMask, L);   // from the (now complete) finer mask
+            L.dmask.upload(L.nodeMask.data(), L.g.numNodes, m->ctx.stream);
+            k_mask_to_field<<<(unsigned)((L.g.numNodes + 255) / 256), 256, 0, m->ctx.stream>>>(L.g.numNodes, N, L.dmask.p, L.x.p);
+            VF_KERNEL_CHECK();
+        }
+        if (l < lead.firstRep) grp_exchange(lead, l, fx(l));
+        else if (l == lead.firstRep) {
+            for (vf_mg *m : P) zero_unowned_planes(*m, l, lx(*m, l));
+            grp_allreduce(lead, fx(l), (size_t)lead.grid(l).numNodes * N);
+        }
+        for (vf_mg *m : P) {
+            MGLevel &L = *m->lv[l];
+            k_field_to_mask<<<(unsigned)((L.g.numNodes + 255) / 256), 256, 0, m->ctx.stream>>>(L.g.numNodes, N, L.x.p, L.dmask.p);
+            VF_KERNEL_CHECK();
+            L.dmask.download(L.nodeMask.data(), L.g.numNodes, m->ctx.stream);
+            VF_CUDA(cudaMemsetAsync(L.x.p, 0, sizeof(double) * L.g.numNodes * N, m->ctx.stream));
+        }
+    }
+    for (vf_mg *m : P) VF_CUDA(cudaStreamSynchronize(m->ctx.stream));
+}
+void group_validate(vf_group &G) {
+    if (G.parts.empty()) throw std::runtime_error("empty slab group");
+    for (vf_mg *m : G.parts) {
+        if (!m->sim->window) throw std::runtime_error("slab groups are made of solvers created with vf_mg_create_slab");
+        if (m->numLevels() != G.parts[0]->numLevels() || m->firstRep != G.parts[0]->firstRep) throw std::runtime_error("all parts of a slab group need the same hierarchy");
+        if (m->grp) throw std::runtime_error("solver already belongs to a slab group");
+    }
+}
+} // namespace
+
+int vf_group_create_local(int nparts, vf_mg **parts, vf_group **out) {
+    VF_TRY
+    auto G = std::make_unique<vf_group>();
+    G->parts.assign(parts, parts + nparts); G->world = nparts;
+    group_validate(*G);
+    for (int i = 0; i < nparts; ++i) {
+        if (parts[i]->ctx.stream != parts[0]->ctx.stream) throw std::runtime_error("the parts of a local slab group must share one stream (vf_sim_create_slab share_stream_with)");
+        if (i > 0 && parts[i]->sim->slabBegin != parts[i - 1]->sim->slabEnd) throw std::runtime_error("parts must be consecutive slabs");
+    }
+    if (parts[0]->sim->slabBegin != 0 || parts[nparts - 1]->sim->slabEnd != parts[0]->sim->gne0) throw std::runtime_error("the slabs must cover the grid");
+    for (int i = 0; i < nparts; ++i) parts[i]->grp = G.get();
+    group_complete_masks(*parts[0]);
+    *out = G.release();
     VF_CATCH
 }
+int vf_nccl_unique_id(void *out128) { VF_TRY NcclApi &A = NcclApi::get(); A.check(A.GetUniqueId(reinterpret_cast<NcclUniqueId *>(out128)), "ncclGetUniqueId"); VF_CATCH }
+int vf_group_create_nccl(vf_mg *part, int rank, int world, const void *unique_id128, vf_group **out) {
+    VF_TRY
+    auto G = std::make_unique<vf_group>();
+    G->parts.assign(1, part); G->rank = rank; G->world = world;
+    group_validate(*G);
+    if ((rank == 0) != (part->sim->slabBegin == 0) || (rank == world - 1) != (part->sim->slabEnd == part->sim->gne0)) throw std::runtime_error("slab does not match the rank's position");
+    NcclApi &A = NcclApi::get();
+    NcclUniqueId id; std::memcpy(&id, unique_id128, sizeof(id));
+    A.check(A.CommInitRank(&G->comm, world, id, rank), "ncclCommInitRank");
+    part->grp = G.get();
+    group_complete_masks(*part);
+    *out = G.release();
+    VF_CATCH
+}
+int vf_group_destroy(vf_group *g) {
+    VF_TRY if (g) { for (vf_mg *m : g->parts) { cudaStreamSynchronize(m->ctx.stream); m->grp = nullptr; } delete g; } VF_CATCH
+}
+int vf_group_pcg_dev(vf_group *g, double *const *x_dev, const double *const *b_dev, int maxIter, double tol, int mgIt, int mgSmooth, int fmg,
+                     int dirichletOK, int *iters, double *residualNorms, vf_pcg_callback cb, void *user) {
+    VF_TRY vf_mg &lead = *g->parts[0];
+    mg_pcg(lead, x_dev, b_dev, maxIter, tol, mgIt, mgSmooth, fmg != 0, dirichletOK != 0, cb, user);
+    if (iters) *iters = lead.lastIters;
+    if (residualNorms) std::copy(lead.lastResiduals.begin(), lead.lastResiduals.end(), residualNorms);
+    VF_CATCH
+}
+
 int vf_mg_destroy(vf_mg *mg) { VF_TRY if (mg) { cudaStreamSynchronize(mg->ctx.stream); delete mg; } VF_CATCH }
 int vf_mg_num_levels(const vf_mg *mg) { return mg->numLevels(); }
 int64_t vf_mg_level_num_nodes(const vf_mg *mg, int l) { return mg->grid(l).numNodes; }
@@ -858,7 +1272,7 @@ int vf_mg_apply_K(vf_mg *mg, int l, const double *u, double *out) {
     VF_TRY const size_t len = (size_t)mg->grid(l).numNodes * mg->N;
     double *du = mg_tmp(mg, 0, len), *dout = mg_tmp(mg, 1, len);
     h2d(du, u, len, mg->ctx.stream); mg_sync_level_masks(*mg);
-    mg_apply_K(*mg, l, du, nullptr, dout, APPLY_SET, false);
+    mg_apply_K(*mg, l, fu(du), fu(du), fu(dout), APPLY_SET, false);
     d2h(out, dout, len, mg->ctx.stream); VF_CATCH
 }
 int vf_mg_compute_residual(vf_mg *mg, int l, const double *u, const double *b, double *r) {
@@ -866,14 +1280,14 @@ int vf_mg_compute_residual(vf_mg *mg, int l, const double *u, const double *b, d
     double *du = mg_tmp(mg, 0, len), *db = mg_tmp(mg, 1, len), *dr = mg_tmp(mg, 2, len);
     h2d(du, u, len, mg->ctx.stream); h2d(db, b, len, mg->ctx.stream); mg_sync_level_masks(*mg);
     VF_CUDA(cudaMemsetAsync(dr, 0, len * sizeof(double), mg->ctx.stream));
-    mg_residual(*mg, l, du, db, dr);
+    mg_residual(*mg, l, fu(du), fu(db), fu(dr));
     d2h(r, dr, len, mg->ctx.stream); VF_CATCH
 }
 int vf_mg_smooth(vf_mg *mg, int l, double *u, const double *b, int forward) {
     VF_TRY const size_t len = (size_t)mg->grid(l).numNodes * mg->N;
     double *du = mg_tmp(mg, 0, len), *db = mg_tmp(mg, 1, len);
     h2d(du, u, len, mg->ctx.stream); h2d(db, b, len, mg->ctx.stream); mg_sync_level_masks(*mg);
-    mg_smooth(*mg, l, du, db, forward != 0);
+    mg_smooth(*mg, l, fu(du), fu(db), forward != 0);
     d2h(u, du, len, mg->ctx.stream); VF_CATCH
 }
 int vf_mg_restrict(vf_mg *mg, int lf, const double *fine, double *coarse) {
@@ -906,7 +1320,7 @@ int vf_mg_coarse_solve(vf_mg *mg, const double *f, double *x) {
     VF_TRY const int l = mg->numLevels() - 1; const size_t len = (size_t)mg->grid(l).numNodes * mg->N;
     double *df = mg_tmp(mg, 0, len), *dx = mg_tmp(mg, 1, len);
     h2d(df, f, len, mg->ctx.stream); mg_sync_level_masks(*mg);
-    if (l == 0) sim_direct_solve(*mg->sim, df, dx); else mg_coarse_solve(*mg, df, dx);
+    if (l == 0) sim_direct_solve(*mg->sim, df, dx); else mg_coarse_solve(*mg, fu(df), fu(dx));
     d2h(x, dx, len, mg->ctx.stream); VF_CATCH
 }
 int vf_mg_solve(vf_mg *mg, const double *u, const double *f, int numSteps, int nsmooth, int stiffnessUpdated, int zeroDirichlet, int fmg, double *out) {
@@ -988,12 +1402,12 @@ int vf_mg_time_op(vf_mg *mg, int op, int level, int reps, int nsmooth, double *m
     const bool profWas = mg->sim->prof.enabled; mg->sim->prof.enabled = false;
     auto body = [&]() {
         switch (op) {
-            case 0: mg_smooth(*mg, level, lx(*mg, level), lb(*mg, level), true); break;
-            case 1: mg_residual(*mg, level, lx(*mg, level), lb(*mg, level), lr(*mg, level)); break;
-            case 2: mg_apply_K(*mg, level, lx(*mg, level), nullptr, lr(*mg, level), APPLY_SET, true); break;
+            case 0: mg_smooth(*mg, level, fx(level), fb(level), true); break;
+            case 1: mg_residual(*mg, level, fx(level), fb(level), fr(level)); break;
+            case 2: mg_apply_K(*mg, level, fx(level), fx(level), fr(level), APPLY_SET, true); break;
             case 3: launch_restrict(mg->ctx, mg->grid(level), mg->grid(level + 1), lr(*mg, level), lb(*mg, level + 1)); break;
             case 4: launch_prolong(mg->ctx, mg->grid(level), mg->grid(level + 1), lx(*mg, level + 1), lx(*mg, level), true); break;
-            case 5: mg_coarse_solve(*mg, lb(*mg, mg->numLevels() - 1), lx(*mg, mg->numLevels() - 1)); break;
+            case 5: mg_coarse_solve(*mg, fb(mg->numLevels() - 1), fx(mg->numLevels() - 1)); break;
             case 6: mg_vcycle(*mg, level, nsmooth, true); break;
             case 7: mg_fmg(*mg, 0, nsmooth, true); break;
             default: throw std::runtime_error("unknown op");

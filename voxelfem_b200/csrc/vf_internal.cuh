@@ -33,6 +33,12 @@ struct GridDesc {
     long long cbase[8];
     int ccnt[8][3];
     long long numPos;
+    // Slab windows (multi-GPU).  A level of a slab-partitioned solver stores a window of the global grid:
+    // local plane i along embedded axis 0 is global plane xoff + i.  Defaults describe an undivided grid.
+    int xoff;           // global index of local node plane 0 (and of local element layer 0)
+    int ownLo, ownHi;   // local node planes [ownLo, ownHi) this part owns: reductions count exactly these
+    int cmpLo, cmpHi;   // local node planes [cmpLo, cmpHi) the smoother updates (owned + shared planes; ghost planes are received)
+    int oeLo, oeHi;     // local element layers [oeLo, oeHi) this part owns: Galerkin coarsening sub-assembles exactly these
 };
 
 // Stored stencils are tiled: the NE = 3^N * N * N entries of kStencilTile consecutive positions form one contiguous
@@ -180,6 +186,10 @@ void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const Grid
 // Level-0 stencil straight from moduli (used for single-level direct solves): S = sum_e E_e K0 blocks.
 void launch_stencil_from_moduli_l0(const LaunchCtx &ctx, const GridDesc &g, const double *E, const double *K0dev, double *S);
 // Dense matrix of the free DOFs from a stencil: A[red(i)][red(j)], row-major n x n; redIdx[dof] = -1 for fixed DOFs.
+// Slab completion of a sub-assembled stencil: rows of local node plane `plane` <-> contiguous buffer [position in plane][entry]
+long long stencil_plane_rows(const GridDesc &g, int plane);   // number of nodes in a plane
+void launch_stencil_plane_pack(const LaunchCtx &ctx, const GridDesc &g, const double *S, int plane, double *buf);
+void launch_stencil_plane_add(const LaunchCtx &ctx, const GridDesc &g, double *S, int plane, const double *buf);
 void launch_stencil_to_dense(const LaunchCtx &ctx, const GridDesc &g, const double *S, const int *redIdx, int nfree, double *A);
 void launch_symmetrize_lower(const LaunchCtx &ctx, double *A, int n);   // copy lower (row-major) triangle to upper
 void launch_dense_symv(const LaunchCtx &ctx, const double *A, int n, const double *x, double *y);
@@ -187,6 +197,8 @@ void launch_gather_free(const LaunchCtx &ctx, const double *f, const int *freeDo
 void launch_scatter_free(const LaunchCtx &ctx, const double *y, const int *freeDofs, int nfree, long long numNodes, int N, double *x);
 
 // --- vf_vec.cu: transfers and PCG vector kernels
+// Grid transfers between two windows: fine plane index = 2 * coarse plane index + xshift(gf, gc) along embedded axis 0.
+VF_HD int xshift(const GridDesc &gf, const GridDesc &gc) { return 2 * gc.xoff - gf.xoff; }
 void launch_restrict(const LaunchCtx &ctx, const GridDesc &gf, const GridDesc &gc, const double *fine, double *coarse);
 void launch_prolong(const LaunchCtx &ctx, const GridDesc &gf, const GridDesc &gc, const double *coarse, double *fine, bool accumulate);
 void launch_zero_dirichlet(const LaunchCtx &ctx, const GridDesc &g, const uint8_t *dmask, double *u);

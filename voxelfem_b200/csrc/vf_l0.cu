@@ -131,7 +131,7 @@ k_apply_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K
                 else res = b[c * g.numNodes + x.n] - acc;
                 if ((dm >> c) & 1u) res = 0.0;
                 out[c * g.numNodes + x.n] = res;
-                if (DOT) dotv = fma(uself[c], res, dotv);
+                if (DOT && c0 >= g.ownLo && c0 < g.ownHi) dotv = fma(uself[c], res, dotv);
             }
         }
     }
@@ -253,7 +253,7 @@ k_apply3_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param 
                 else res = b[c * g.numNodes + n] - acc;
                 if ((dm >> c) & 1u) res = 0.0;
                 out[c * g.numNodes + n] = res;
-                if (DOT) dotv = fma(uself[j][c], res, dotv);
+                if (DOT && c0 >= g.ownLo && c0 < g.ownHi) dotv = fma(uself[j][c], res, dotv);
             }
         }
     }
@@ -270,6 +270,23 @@ static void apply3_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0
     if (mode == M) { \
         if (fused) k_apply3_l0<M, true><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, dotOut, scratch); \
         else       k_apply3_l0<M, false><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, nullptr, nullptr); \
+    }
+    VF_APPLY_CASE(APPLY_SET) VF_APPLY_CASE(APPLY_ADD) VF_APPLY_CASE(APPLY_SUB) VF_APPLY_CASE(APPLY_RESIDUAL)
+#undef VF_APPLY_CASE
+    VF_KERNEL_CHECK();
+    if (dotOut && !fused) launch_masked_dot(ctx, g, u, out, dotOut, scratch);
+}
+
+template<int N>
+static void apply_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
+                              const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
+    dim3 block = (N == 3) ? dim3(32, 4, 2) : dim3(32, 8, 1);
+    dim3 grid((g.nn[2] + block.x - 1) / block.x, (g.nn[1] + block.y - 1) / block.y, (g.nn[0] + block.z - 1) / block.z);
+    const bool fused = dotOut && (size_t)grid.x * grid.y * grid.z <= (size_t)kReduceMaxBlocks;
+#define VF_APPLY_CASE(M) \
+    if (mode == M) { \
+        if (fused) k_apply_l0<N, M, true><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, dotOut, scratch); \
+        else       k_apply_l0<N, M, false><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, nullptr, nullptr); \
     }
     VF_APPLY_CASE(APPLY_SET) VF_APPLY_CASE(APPLY_ADD) VF_APPLY_CASE(APPLY_SUB) VF_APPLY_CASE(APPLY_RESIDUAL)
 #undef VF_APPLY_CASE
@@ -300,6 +317,7 @@ k_gs_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K, c
     const int i0 = blockIdx.z * blockDim.z + threadIdx.z;
     if (i2 >= col.cnt[2] || i1 >= col.cnt[1] || i0 >= col.cnt[0]) return;
     NodeCtx<N> x; make_ctx<N>(g, col.off[0] + 2 * i0, col.off[1] + 2 * i1, col.off[2] + 2 * i2, x);
+    if (x.c[0] < g.cmpLo || x.c[0] >= g.cmpHi) return;   // ghost planes of a slab window are received, not computed
     const unsigned dm = dmask[x.n];
     if (dm == (unsigned)((1 << N) - 1)) return; // hasFullDirichlet (:350)
     double t[NPE][N], Ee[NPE], uself[N];
@@ -338,6 +356,7 @@ k_gs3_color(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param 
     const int i0 = blockIdx.z;
     if (i2 >= col.cnt[2] || i1 >= col.cnt[1]) return;
     const int c0 = col.off[0] + 2 * i0, c1 = col.off[1] + 2 * i1, c2 = col.off[2] + 2 * i2;
+    if (c0 < g.cmpLo || c0 >= g.cmpHi) return;           // ghost planes of a slab window are received, not computed
     const int nx = g.nn[0], ny = g.nn[1], nz = g.nn[2];
     const long long NN = g.numNodes;
     long long xo[3], yo[5]; int zo[3];

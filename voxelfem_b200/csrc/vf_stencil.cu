@@ -79,7 +79,7 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     const bool inRange = pos_coords<N>(g, pos, c);
     const long long n = (long long)c[0] * g.ns[0] + (long long)c[1] * g.ns[1] + c[2];
     const bool detached = inRange && (((g.bd == 1) ? c[1] : c[2]) >= g.nActive);
-    const bool active = inRange && !detached;
+    const bool active = inRange && !detached && !(GS && (c[0] < g.cmpLo || c[0] >= g.cmpHi)); // ghost planes of a slab window are not smoothed
     if (tx == 0 && s == 0) mbar_init(&sh.mbar, 1);
     const int anyActive = __syncthreads_or(active ? 1 : 0);     // also publishes the barrier initialisation
     if (anyActive) {
@@ -135,6 +135,7 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     }
     __syncthreads();
     if (s != 0 || !inRange) return;
+    if (GS && !active) return;
     if (detached) {
         if (!GS && MODE == APPLY_SET) {
             #pragma unroll
@@ -247,8 +248,13 @@ k_coarsen_from_moduli(const __grid_constant__ GridDesc gc, const __grid_constant
             }
             if (!ok) continue;
             for (int fi = 0; fi < NPE; ++fi) {
-                long long ef = 0;
-                for (int a = A0; a < 3; ++a) ef += (long long)(2 * ec[a] + ((fi >> (2 - a)) & 1)) * gf.es[a];
+                long long ef = 0; bool owned = true;
+                for (int a = A0; a < 3; ++a) {
+                    const int q = 2 * ec[a] + ((fi >> (2 - a)) & 1) + (a == 0 ? xshift(gf, gc) : 0);
+                    if (a == 0) owned = q >= gf.oeLo && q < gf.oeHi;   // sub-assembly over the fine element layers this part owns
+                    ef += (long long)q * gf.es[a];
+                }
+                if (!owned) continue;
                 const double Ef = __ldg(E + ef);
                 const double *Kb = cK0 + (size_t)fi * KE * KE;
                 #pragma unroll
@@ -296,7 +302,7 @@ k_coarsen_stencil(const __grid_constant__ GridDesc gc, const __grid_constant__ G
             { int r = sa; for (int a = 2; a >= A0; --a) { av[a] = r % 3 - 1; r /= 3; } }
             bool ok = true; double wa = 1.0; int fq[3] = {0, 0, 0};
             for (int a = A0; a < 3; ++a) {
-                const int q = 2 * c[a] + av[a];
+                const int q = 2 * c[a] + av[a] + (a == 0 ? xshift(gf, gc) : 0);
                 ok = ok && q >= 0 && q < gf.nn[a];
                 fq[a] = q;
                 wa *= av[a] == 0 ? 1.0 : 0.5;
@@ -310,7 +316,7 @@ k_coarsen_stencil(const __grid_constant__ GridDesc gc, const __grid_constant__ G
                 for (int a = A0; a < 3; ++a) {
                     const int eps = 2 * d[a] + bv[a] - av[a];
                     ok2 = ok2 && eps >= -1 && eps <= 1;
-                    const int qj = 2 * (c[a] + d[a]) + bv[a];
+                    const int qj = 2 * (c[a] + d[a]) + bv[a] + (a == 0 ? xshift(gf, gc) : 0);
                     ok2 = ok2 && qj >= 0 && qj < gf.nn[a];
                     se = se * 3 + (eps + 1);
                     w *= bv[a] == 0 ? 1.0 : 0.5;
@@ -378,6 +384,33 @@ void launch_stencil_from_moduli_l0(const LaunchCtx &ctx, const GridDesc &g, cons
     dim3 block(128), grid((unsigned)((g.numNodes + 127) / 128), g.N == 3 ? 27 : 9);
     if (g.N == 3) k_stencil_from_moduli_l0<3><<<grid, block, 0, ctx.stream>>>(g, E, K0dev, S);
     else          k_stencil_from_moduli_l0<2><<<grid, block, 0, ctx.stream>>>(g, E, K0dev, S);
+    VF_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------
+// Slab completion: rows of one node plane <-> contiguous buffer [node in plane (row-major y, z)][entry]
+// ---------------------------------------------------------------------------
+long long stencil_plane_rows(const GridDesc &g, int plane) { (void)plane; return (long long)g.nn[1] * g.nn[2]; }
+template<bool ADD>
+__global__ void __launch_bounds__(256) k_stencil_plane(const __grid_constant__ GridDesc g, double *S, int plane, double *buf, int NE) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rows = (long long)g.nn[1] * g.nn[2];
+    if (i >= rows * NE) return;
+    const int entry = (int)(i % NE); const long long r = i / NE;
+    const int c2 = (int)(r % g.nn[2]), c1 = (int)(r / g.nn[2]);
+    const long long a = stencil_addr(stencil_pos(g, plane, c1, c2), entry, NE);
+    if (ADD) S[a] += buf[i]; else buf[i] = S[a];
+}
+void launch_stencil_plane_pack(const LaunchCtx &ctx, const GridDesc &g, const double *S, int plane, double *buf) {
+    const int NE = (g.N == 3 ? 27 : 9) * g.N * g.N; const long long tot = stencil_plane_rows(g, plane) * NE;
+    ProfScope ps(ctx, PC_COARSEN, (double)tot);
+    k_stencil_plane<false><<<(unsigned)((tot + 255) / 256), 256, 0, ctx.stream>>>(g, const_cast<double *>(S), plane, buf, NE);
+    VF_KERNEL_CHECK();
+}
+void launch_stencil_plane_add(const LaunchCtx &ctx, const GridDesc &g, double *S, int plane, const double *buf) {
+    const int NE = (g.N == 3 ? 27 : 9) * g.N * g.N; const long long tot = stencil_plane_rows(g, plane) * NE;
+    ProfScope ps(ctx, PC_COARSEN, (double)tot);
+    k_stencil_plane<true><<<(unsigned)((tot + 255) / 256), 256, 0, ctx.stream>>>(g, S, plane, const_cast<double *>(buf), NE);
     VF_KERNEL_CHECK();
 }
 

@@ -38,7 +38,7 @@ k_restrict(const __grid_constant__ GridDesc gf, const __grid_constant__ GridDesc
             bool valid = true; long long fi = 0; double w = 1.0;
             #pragma unroll
             for (int a = A0; a < 3; ++a) {
-                const int q = 2 * cc[a] + d[a];
+                const int q = 2 * cc[a] + d[a] + (a == 0 ? xshift(gf, gc) : 0);
                 const int lim = (a == gf.bd) ? gf.nActive : gf.nn[a];
                 valid = valid && q >= 0 && q < lim;
                 fi += (long long)q * gf.ns[a];
@@ -83,10 +83,13 @@ k_prolong(const __grid_constant__ GridDesc gf, const __grid_constant__ GridDesc 
         #pragma unroll
         for (int a = A0; a < 3; ++a) {
             const int bit = (k >> (2 - a)) & 1;
-            const int odd = cc[a] & 1;
+            const int fa = cc[a] - (a == 0 ? xshift(gf, gc) : 0);   // fine index relative to coarse plane 0 (may be negative in a window)
+            const int odd = fa & 1;
             // even fine index: single coarse node (bit 0 only); odd: both neighbours with weight 1/2
             use = use && (odd || bit == 0);
-            ci += (long long)((cc[a] >> 1) + bit) * gc.ns[a];
+            const int q = (fa >> 1) + bit;                          // arithmetic shift = floor division
+            use = use && q >= 0 && q < gc.nn[a];                    // outside the coarse window: only for ghost planes, which are received
+            ci += (long long)q * gc.ns[a];
             w *= odd ? 0.5 : 1.0;
         }
         if (use) {
@@ -111,6 +114,12 @@ void launch_prolong(const LaunchCtx &ctx, const GridDesc &gf, const GridDesc &gc
 // ---------------------------------------------------------------------------
 // Flat masked loops: index i over all nodes; active iff coordinate along bd < limit
 // ---------------------------------------------------------------------------
+// node belongs to the planes this part owns (slab windows; always true for an undivided grid)
+__device__ __forceinline__ bool node_owned(const GridDesc &g, long long n) {
+    if (g.ownLo <= 0 && g.ownHi >= g.nn[0]) return true;
+    const int p = (int)(n / g.ns[0]);
+    return p >= g.ownLo && p < g.ownHi;
+}
 __device__ __forceinline__ bool node_active(const GridDesc &g, long long n, int limit) {
     if (limit >= g.nn[g.bd]) return true;
     const int cbd = (g.bd == 2) ? (int)(n % g.nn[2]) : (int)((n / g.nn[2]) % g.nn[1]);
@@ -175,7 +184,7 @@ void launch_masked_copy(const LaunchCtx &ctx, const GridDesc &g, const double *i
 __global__ void __launch_bounds__(256) k_masked_dot(const __grid_constant__ GridDesc g, const double *__restrict__ a, const double *__restrict__ b, double *result, double *scratch) {
     double s = 0.0;
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < g.numNodes; n += (long long)gridDim.x * blockDim.x)
-        if (node_active(g, n, g.nActive)) for (int c = 0; c < g.N; ++c) s = fma(a[c * g.numNodes + n], b[c * g.numNodes + n], s);
+        if (node_active(g, n, g.nActive) && node_owned(g, n)) for (int c = 0; c < g.N; ++c) s = fma(a[c * g.numNodes + n], b[c * g.numNodes + n], s);
     grid_sum(s, scratch, result);
 }
 void launch_masked_dot(const LaunchCtx &ctx, const GridDesc &g, const double *a, const double *b, double *result, double *scratch) {
@@ -206,12 +215,13 @@ __global__ void __launch_bounds__(256) k_cg_update(const __grid_constant__ GridD
     double s = 0.0;
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < g.numNodes; n += (long long)gridDim.x * blockDim.x) {
         if (!node_active(g, n, g.nActive)) continue;
+        const bool own = node_owned(g, n);
         for (int c = 0; c < g.N; ++c) {
             const long long i = c * g.numNodes + n;
             x[i] = fma(alpha, d[i], x[i]);
             const double rn = fma(-alpha, Ad[i], r[i]);
             r[i] = rn;
-            s = fma(rn, rn, s);
+            if (own) s = fma(rn, rn, s);
         }
     }
     grid_sum(s, scratch, rsq);
