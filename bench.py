@@ -9,6 +9,10 @@ reference's own single-solve benchmark (python/CoarseningLevelBenchmark.py) on t
 FMG-preconditioned PCG with 1 smoothing sweep, zero initial guess.
 metric = DOF*iterations / s = N * numNodes * PCG iterations / solve time.
 
+With --gpus W > 1 (torchrun, one rank per GPU) ONE solve is partitioned over the W GPUs: the grid is (256 W) x 256 x 256
+(domain W x 1 x 1, weak scaling: a 256^3 slab per GPU), cut into slabs along axis 0 with NCCL ghost-plane exchange and
+all-reduced PCG scalars (BASELINE.json configs[3] style); value = global DOF * iterations / max-over-ranks time.
+
 Emits ONE JSON line (rank 0).  Timing: CUDA events on the solver's stream, max over ranks; inputs are
 re-zeroed on the device before every step; the working set (>4 GB) is far larger than L2.
 """
@@ -122,6 +126,22 @@ def cpu_sample(workload, steps, warmup, threads=None):
             "ms_per_step": t * 1e3, "iters": iters}
 
 
+def setup_slab(capi, rank, world, data_dir):
+    """This rank's slab of the weak-scaling grid (256 * world) x 256 x 256."""
+    ne = np.array([256 * world, 256, 256])
+    dmax = np.array([float(world), 1.0, 1.0])
+    levels = 5 if world <= 2 else 6          # keeps the replicated coarsest grid at <= 4,131 DOF
+    first_rep = 4                            # levels 0..3 are windowed per GPU, the rest is replicated
+    a, b = capi.slab_ranges(int(ne[0]), world, 2 ** first_rep)[rank]
+    s = capi.SlabSim(ne, np.zeros(3), dmax, a, b)
+    s.set_isotropic(MATERIAL["E"], MATERIAL["nu"])
+    s.set_interp(0, 1.0, 1e-5, 3.0, 3.0)
+    s.apply_bc_file(os.path.join(data_dir, "bcs", "3D/cantilever_flexion_E.bc"))
+    s.set_uniform_density(0.5)
+    mg = capi.SlabMG(s, levels, first_rep)
+    return s, mg, ne, levels, first_rep
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,9 +183,20 @@ def main():
     torch.cuda.set_device(local_rank)
     capi._check(capi.lib().vf_set_device(local_rank))
     L = capi.lib()
-    s, mg = setup(capi.Sim, capi.MG, workload, capi.DATA_DIR)
+    grp = None
+    if world > 1:
+        s, mg, gne, levels, first_rep = setup_slab(capi, rank, world, capi.DATA_DIR)
+        workload = "C3w_pcg_%dx256x256_slabs%d" % (256 * world, world)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.SlabGroup.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        grp = capi.SlabGroup([mg], rank=rank, world=world, unique_id=bytes(uid.cpu().numpy().tobytes()))
+        global_dof = 3 * int(np.prod(gne + 1))
     N = s.N
     ndof = N * s.num_nodes
+    if world == 1:
+        global_dof = ndof
     x = capi.DeviceArray(ndof)
     b = capi.DeviceArray(ndof)
     capi._check(L.vf_sim_build_load_vector_dev(s.h, b.ptr))
@@ -178,6 +209,8 @@ def main():
 
     def step():
         x.zero()
+        if grp is not None:
+            return grp.pcg_dev([x], [b], **PCG)
         return mg.pcg_dev(x, b, **PCG)
 
     for _ in range(args.warmup):
@@ -201,7 +234,13 @@ def main():
     launches = L.vf_kernel_launch_count()
     prof = mg.prof_report()
     clocks = sampler.stop() if rank == 0 else None
-    relres = float(res[-1] / np.linalg.norm(s.build_load())) if len(res) else None
+    if world > 1:
+        sl = s.build_load().reshape((s.plane_hi - s.plane_lo + 1, -1))
+        bnorm2 = torch.tensor([float((sl[s.own_lo - s.plane_lo:s.own_hi - s.plane_lo + 1] ** 2).sum())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(bnorm2)
+        relres = float(res[-1] / np.sqrt(bnorm2.item())) if len(res) else None
+    else:
+        relres = float(res[-1] / np.linalg.norm(s.build_load())) if len(res) else None
 
     # end-to-end through the host-pointer C ABI call (what the reference's binding does: copy u and f in, x out)
     xh = torch.zeros(ndof, dtype=torch.float64).pin_memory().numpy()
@@ -211,6 +250,11 @@ def main():
 
     def e2e_step():
         xh[:] = 0.0
+        if grp is not None:  # this rank's window: host -> device, partitioned solve, device -> host
+            capi._check(L.vf_dev_upload(x.ptr, xh, ndof)); capi._check(L.vf_dev_upload(b.ptr, bh, ndof))
+            it_, _ = grp.pcg_dev([x], [b], **PCG)
+            capi._check(L.vf_dev_download(xh, x.ptr, ndof))
+            return it_
         itc = C.c_int(0)
         capi._check(L.vf_mg_pcg(mg.h, xh, bh, PCG["max_iter"], PCG["tol"], PCG["mg_iterations"], PCG["mg_smoothing"], int(PCG["fmg"]), 0, C.byref(itc), np.zeros(PCG["max_iter"] + 1), capi.PCG_CALLBACK(), None))
         return itc.value
@@ -227,15 +271,15 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(iters) * ndof, float(e2e_iters) * ndof], dtype=torch.float64, device="cuda")
+    # one partitioned solve: every rank ran the same iterations over the GLOBAL grid
+    tot = torch.tensor([float(iters) * global_dof, float(e2e_iters) * global_dof], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms, ms_e2e = t.tolist()
     work, work_e2e = tot.tolist()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        grp.close()
+        dist.destroy_process_group()
         return
 
     peaks = {}
@@ -274,17 +318,20 @@ def main():
         "metric": "MG-PCG DOF*iterations per second (3D Q1, FMG-PCG, tol 1e-10)", "value": value, "unit": "DOF*iters/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "grid": list(WORKLOADS[workload][0]), "levels": WORKLOADS[workload][3], "pcg": PCG,
+        "config": {"workload": workload, "grid": [int(v) for v in gne] if world > 1 else list(WORKLOADS[workload][0]),
+                   "levels": levels if world > 1 else WORKLOADS[workload][3], "pcg": PCG,
                    "pcg_iterations_per_solve": iters / args.steps, "final_relative_residual": relres,
-                   "solve_time_s": ms * 1e-3 / args.steps, "parallelism": "1 solve per GPU (replicas)" if world > 1 else "single GPU",
+                   "solve_time_s": ms * 1e-3 / args.steps,
+                   "parallelism": ("one solve partitioned into %d slabs along axis 0 (256 element layers per GPU), levels 0-%d windowed with NCCL ghost-plane exchange, coarser levels replicated, PCG scalars all-reduced" % (world, first_rep - 1)) if world > 1 else "single GPU",
                    "l2": "working set >> 126 MB L2 (x,b,r,d,Ad = 5 x 407 MB + 4.7 GB of coarse stencils); inputs re-zeroed every step"},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "e2e": {"value": work_e2e / (ms_e2e * 1e-3), "unit": "DOF*iters/s", "h2d_bytes_per_step": 2 * ndof * 8, "d2h_bytes_per_step": ndof * 8,
+        "e2e": {"value": work_e2e / (ms_e2e * 1e-3), "unit": "DOF*iters/s", "h2d_bytes_per_step": 2 * ndof * 8 * world, "d2h_bytes_per_step": ndof * 8 * world,
                 "ms_per_step": ms_e2e / n_e2e, "steps": n_e2e},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:
+        grp.close()
         dist.destroy_process_group()
 
 

@@ -484,6 +484,15 @@ def slab_ranges(ne0, nparts, align):
     return [(cuts[i], cuts[i + 1]) for i in range(nparts)]
 
 
+def slab_window(ne0, slab_begin, slab_end):
+    """Node planes stored (plane_lo, plane_hi) and owned (own_lo, own_hi) by the part holding element layers
+    [slab_begin, slab_end) of ne0 (mirrors vf_sim_create_slab): one ghost plane per neighbour; a plane shared by two
+    slabs is owned by the lower one."""
+    plane_lo, plane_hi = max(slab_begin - 1, 0), min(slab_end + 1, ne0)
+    own_hi = slab_end if slab_end == ne0 else slab_end - 1
+    return plane_lo, plane_hi, slab_begin, own_hi
+
+
 class SlabSim(Sim):
     """One slab of a TensorProductSimulator: stores the window of node planes [plane_lo, plane_hi] of the global grid."""
 
