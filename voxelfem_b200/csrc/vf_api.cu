@@ -127,12 +127,14 @@ static void set_mask_limits(GridDesc &g, int firstMasked, int firstDetached) {
 }
 
 // ---------------------------------------------------------------------------
-// Dense SPD solver on the GPU (stands in for CHOLMOD): A^-1 via cuSOLVER potrf + potri, applied as a
-// bandwidth-bound symmetric mat-vec so that the coarse solve on the V-cycle's critical path is one kernel.
+// Dense SPD solver on the GPU (stands in for CHOLMOD): Cholesky factor by cuSOLVER potrf, then the explicit inverse of
+// the triangular factor (trtri) -- NOT the full inverse (potri's lauum/trmm stage costs as much as everything else
+// together).  A solve is two bandwidth-bound triangular mat-vecs  x = L^-T (L^-1 b)  on a matrix that stays L2-resident,
+// so the coarse solve on the V-cycle's critical path is two small kernels with no dependent-block latency chain.
 // ---------------------------------------------------------------------------
 struct DenseSolver {
     cusolverDnHandle_t handle = nullptr;
-    DevBuf<double> A, work, rhs, y; DevBuf<int> info, red, freeDofs;
+    DevBuf<double> A, work, rhs, y; DevBuf<int> info, red, freeDofs; std::vector<char> hostWork;
     int nfree = 0; bool ok = false;
     ~DenseSolver() { if (handle) cusolverDnDestroy(handle); }
     void init_handle(cudaStream_t s) {
@@ -152,33 +154,27 @@ struct DenseSolver {
         freeDofs.alloc(std::max(nfree, 1), false); if (nfree) freeDofs.upload(freeH.data(), nfree, ctx.stream);
         VF_CUDA(cudaStreamSynchronize(ctx.stream)); // redH / freeH are stack-owned
         if (nfree == 0) { ok = true; return; }
-        A.alloc((size_t)nfree * nfree, true);
+        if (A.n != (size_t)nfree * nfree) A.alloc((size_t)nfree * nfree, false);
+        VF_CUDA(cudaMemsetAsync(A.p, 0, sizeof(double) * A.n, ctx.stream));
         rhs.alloc(nfree, true); y.alloc(nfree, true); info.alloc(1, true);
         launch_stencil_to_dense(ctx, g, S, red.p, nfree, A.p);
-        int lwork1 = 0, lwork2 = 0;
+        int lwork1 = 0; size_t wdev = 0, whost = 0;
         // Row-major symmetric == column-major symmetric; factor the "lower" triangle in cuSOLVER's column-major view.
         if (cusolverDnDpotrf_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, &lwork1) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf_bufferSize failed");
-        if (cusolverDnDpotri_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, &lwork2) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potri_bufferSize failed");
-        const int lwork = std::max(lwork1, lwork2);
-        if ((size_t)lwork > work.n) work.alloc(lwork, false);
+        if (cusolverDnXtrtri_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, nfree, CUDA_R_64F, A.p, nfree, &wdev, &whost) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("trtri_bufferSize failed");
+        const size_t lwork = std::max((size_t)lwork1, (wdev + sizeof(double) - 1) / sizeof(double));
+        if (lwork > work.n) work.alloc(lwork, false);
+        if (whost > hostWork.size()) hostWork.resize(whost);
         count_launch();
-        if (cusolverDnDpotrf(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, work.p, lwork, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf failed");
+        if (cusolverDnDpotrf(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, work.p, lwork1, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf failed");
         int hinfo = 0; info.download(&hinfo, 1, ctx.stream);
         if (hinfo != 0) throw std::runtime_error("Cholesky factorization failed: coarse stiffness matrix is not positive definite (info = " + std::to_string(hinfo) + ")");
         count_launch();
-        if (cusolverDnDpotri(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, work.p, lwork, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potri failed");
-        info.download(&hinfo, 1, ctx.stream);
-        if (hinfo != 0) throw std::runtime_error("potri failed (info = " + std::to_string(hinfo) + ")");
-        // column-major lower triangle == row-major upper triangle: mirror it so that rows are complete
-        launch_symmetrize_lower_from_colmajor(ctx);
-        ok = true;
-    }
-    void launch_symmetrize_lower_from_colmajor(const LaunchCtx &ctx) {
-        // In row-major terms cuSOLVER wrote entries A[j][i] for i >= j (i.e. the upper triangle, row j col i).
-        // launch_symmetrize_lower copies lower -> upper, so transpose roles by treating the buffer as column-major:
-        // element (i, j) column-major is at A[j * n + i]; "lower" there is what launch_symmetrize_lower calls "upper"
-        // of the transposed view.  Copy valid part onto the other half:
+        if (cusolverDnXtrtri(handle, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, nfree, CUDA_R_64F, A.p, nfree, work.p, wdev, hostWork.data(), whost, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("trtri failed");
+        // cuSOLVER (column-major, lower) holds L^-1(r, c), r >= c, at A[c * n + r]: in our row-major reading that is row c,
+        // column r -- the upper triangle, i.e. L^-T.  Mirror it so that the lower triangle holds L^-1 row by row.
         launch_symmetrize_upper_to_lower(ctx);
+        ok = true;
     }
     void launch_symmetrize_upper_to_lower(const LaunchCtx &ctx);
     // x = A^-1 f on free DOFs, zero on fixed DOFs (TensorProductSimulator.hh:1227-1229, 1243-1252)
@@ -186,8 +182,9 @@ struct DenseSolver {
         VF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * g.numNodes * g.N, ctx.stream));
         if (nfree == 0) return;
         launch_gather_free(ctx, f, freeDofs.p, nfree, g.numNodes, g.N, rhs.p);
-        launch_dense_symv(ctx, A.p, nfree, rhs.p, y.p);
-        launch_scatter_free(ctx, y.p, freeDofs.p, nfree, g.numNodes, g.N, x);
+        launch_dense_trmv(ctx, A.p, nfree, rhs.p, y.p, true);    // y = L^-1 rhs   (rows of the lower triangle)
+        launch_dense_trmv(ctx, A.p, nfree, y.p, rhs.p, false);   // z = L^-T y     (rows of the upper triangle)
+        launch_scatter_free(ctx, rhs.p, freeDofs.p, nfree, g.numNodes, g.N, x);
     }
 };
 
@@ -231,6 +228,7 @@ struct vf_sim {
     int firstMasked = INT_MAX, firstDetached = INT_MAX;
     cudaStream_t stream = nullptr; LaunchCtx ctx; Profiler prof;
     uint64_t version = 1; // bumped whenever E, the mask, K0 or the Dirichlet set changes
+    uint64_t structVersion = 1; // bumped when K0, the Dirichlet set or the mask change (not on density updates): keys captured CUDA graphs
     DenseSolver direct; uint64_t directVersion = 0; DevBuf<double> directStencil;
     // Slab window (multi-GPU): this simulator stores node planes [xoff, xoff + nn[0] - 1] of a grid with gne0 element layers
     // along axis 0, of which element layers [slabBegin, slabEnd) are owned.  dmin/dmax/spacing/stretch are the global ones.
@@ -288,7 +286,7 @@ struct vf_sim {
         std::copy(K0.begin(), K0.end(), K0p.v);
         K0dev.alloc(K0.size(), false); K0dev.upload(K0.data(), K0.size(), stream);
         VF_CUDA(cudaStreamSynchronize(stream));
-        touch();
+        touch(); ++structVersion;
     }
     void setIsotropic(double Ey, double nu) {
         double lambda = (nu * Ey) / ((1.0 + nu) * (1.0 - 2.0 * nu));
@@ -314,7 +312,7 @@ struct vf_sim {
             VF_CUDA(cudaStreamSynchronize(stream));
         }
         VF_CUDA(cudaStreamSynchronize(stream));
-        touch();
+        touch(); ++structVersion;
     }
     // node index ranges per axis covered by an inclusive box (Geometry.hh:276-279 applied to nodePosition, :349-351)
     // idx: local indices inside this simulator's window; *globalCount (optional): number of nodes of the whole grid in the box
@@ -397,7 +395,11 @@ struct vf_mg {
     vf_group *grp = nullptr; int firstRep = INT_MAX; // slab group this solver is a part of; first replicated (non-windowed) level
     std::vector<vf_mg *> self;
     DevBuf<double> stage[2];                          // staging buffers of the slab exchanges
-    ~vf_mg() { if (hostScalars) cudaFreeHost(hostScalars); }
+    // The preconditioner application (one FMG / V-cycle: a fixed sequence of ~350 launches, most of them tiny coarse-level
+    // kernels) is captured once into a CUDA graph and replayed every PCG iteration.
+    struct PrecondGraph { cudaGraphExec_t exec = nullptr; uint64_t version = 0; int nActive = -1, mgIt = 0, nsmooth = 0; bool fmg = false, sym = true; long long launches = 0; } pg;
+    bool useGraphs = true;
+    ~vf_mg() { if (hostScalars) cudaFreeHost(hostScalars); if (pg.exec) cudaGraphExecDestroy(pg.exec); }
     int numLevels() const { return (int)lv.size(); }
     const uint8_t *dmask(int l) const { return l == 0 ? sim->dmaskDev.p : lv[l]->dmask.p; }
     const GridDesc &grid(int l) const { return l == 0 ? sim->g : lv[l]->g; }
@@ -782,8 +784,31 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
         if (mgIterations > 0 && mgSmoothing > 0) {
             mg_update_stiffness(lead); // lazily, first iteration (:1104-1107)
             // applyPreconditionerInv: zero initial guess (:577-580); the FMG cycle overwrites s by interpolation (:600)
-            if (!fmg) for (vf_mg *m : P) VF_CUDA(cudaMemsetAsync(s(*m), 0, sizeof(double) * m->sim->g.numNodes * N, m->ctx.stream));
-            mg_solve_inplace(lead, mgIterations, mgSmoothing, true, fmg);
+            auto precond = [&]() {
+                if (!fmg) for (vf_mg *m : P) VF_CUDA(cudaMemsetAsync(s(*m), 0, sizeof(double) * m->sim->g.numNodes * N, m->ctx.stream));
+                mg_solve_inplace(lead, mgIterations, mgSmoothing, true, fmg);
+            };
+            const bool graphable = lead.useGraphs && !lead.grp && !(lead.ctx.prof && lead.ctx.prof->enabled);
+            if (!graphable) precond();
+            else {
+                vf_mg::PrecondGraph &pg = lead.pg;
+                const bool valid = pg.exec && pg.version == lead.sim->structVersion && pg.nActive == lead.sim->g.nActive && pg.mgIt == mgIterations &&
+                                   pg.nsmooth == mgSmoothing && pg.fmg == fmg && pg.sym == lead.symmetricGS;
+                if (!valid) {
+                    if (pg.exec) { cudaGraphExecDestroy(pg.exec); pg.exec = nullptr; }
+                    const long long before = g_launches.load();
+                    cudaGraph_t graph = nullptr;
+                    VF_CUDA(cudaStreamBeginCapture(lead.ctx.stream, cudaStreamCaptureModeThreadLocal));
+                    try { precond(); } catch (...) { cudaStreamEndCapture(lead.ctx.stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+                    VF_CUDA(cudaStreamEndCapture(lead.ctx.stream, &graph));
+                    VF_CUDA(cudaGraphInstantiate(&pg.exec, graph, 0));
+                    cudaGraphDestroy(graph);
+                    pg.launches = g_launches.load() - before; g_launches.fetch_sub(pg.launches);
+                    pg.version = lead.sim->structVersion; pg.nActive = lead.sim->g.nActive; pg.mgIt = mgIterations; pg.nsmooth = mgSmoothing; pg.fmg = fmg; pg.sym = lead.symmetricGS;
+                }
+                VF_CUDA(cudaGraphLaunch(pg.exec, lead.ctx.stream));
+                g_launches.fetch_add(pg.launches);
+            }
         } else {
             for (vf_mg *m : P) VF_CUDA(cudaMemcpyAsync(s(*m), r(*m), sizeof(double) * m->sim->g.numNodes * N, cudaMemcpyDeviceToDevice, m->ctx.stream)); // s = r (:578, :1118)
         }
@@ -792,7 +817,8 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
         mg_dot(lead, r, s, cur);                                                                    // r_Minv_r (:1124)
         for (vf_mg *m : P) launch_cg_direction(m->ctx, m->sim->g, s(*m), m->d.p, m->scalars.p + cur, m->scalars.p + old, first); // d = s + beta d (:1125-1126)
         first = false;
-        mg_apply_K(lead, 0, d, d, Ad, APPLY_SET, true, SC_DAD);                                     // Ad = K d, zero Dirichlet (:1129-1130), fused d . Ad (:1134)
+        mg_apply_K(lead, 0, d, d, Ad, APPLY_SET, true);                                             // Ad = K d, zero Dirichlet (:1129-1130)
+        mg_dot(lead, d, Ad, SC_DAD);                                                                // d . Ad (:1134); a reduction fused into the apply kernel measured slower (1.79 vs 1.10 + 0.11 ms at 256^3)
         grp_exchange(lead, 0, Ad);                                                                  // keeps r consistent on the ghost planes (r feeds the next restriction)
         for (vf_mg *m : P) launch_cg_update(m->ctx, m->sim->g, X(*m), m->d.p, r(*m), m->Ad.p, m->scalars.p + cur, m->scalars.p + SC_DAD, m->scalars.p + SC_RSQ, m->scratch.p); // (:1134-1143)
         grp_allreduce(lead, [&](vf_mg &m) { return m.scalars.p + SC_RSQ; }, 1);
@@ -1014,7 +1040,7 @@ int vf_sim_set_mask_layer(vf_sim *s, int64_t layer) {
     s->maskHeight = h;
     s->firstMasked = (int)std::ceil(h / s->stretch[1] - 1e-10);
     s->firstDetached = s->firstMasked + 1;
-    s->refreshGridMask(); s->updateModuli();
+    s->refreshGridMask(); s->updateModuli(); ++s->structVersion;
     VF_CATCH
 }
 int vf_sim_get_mask_info(const vf_sim *s, int64_t *fm, int64_t *fd, double *h) { VF_TRY if (fm) *fm = s->firstMasked; if (fd) *fd = s->firstDetached; if (h) *h = s->maskHeight; VF_CATCH }

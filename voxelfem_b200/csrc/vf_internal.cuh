@@ -193,6 +193,8 @@ void launch_stencil_plane_add(const LaunchCtx &ctx, const GridDesc &g, double *S
 void launch_stencil_to_dense(const LaunchCtx &ctx, const GridDesc &g, const double *S, const int *redIdx, int nfree, double *A);
 void launch_symmetrize_lower(const LaunchCtx &ctx, double *A, int n);   // copy lower (row-major) triangle to upper
 void launch_dense_symv(const LaunchCtx &ctx, const double *A, int n, const double *x, double *y);
+// y = tril(A) x (lower = true) or y = triu(A) x (lower = false), diagonal included; row-major A
+void launch_dense_trmv(const LaunchCtx &ctx, const double *A, int n, const double *x, double *y, bool lower);
 void launch_gather_free(const LaunchCtx &ctx, const double *f, const int *freeDofs, int nfree, long long numNodes, int N, double *rhs);
 void launch_scatter_free(const LaunchCtx &ctx, const double *y, const int *freeDofs, int nfree, long long numNodes, int N, double *x);
 

@@ -472,6 +472,27 @@ void launch_dense_symv(const LaunchCtx &ctx, const double *A, int n, const doubl
     VF_KERNEL_CHECK();
 }
 
+// y = tril(A) x or triu(A) x for a row-major matrix: one warp per row over the row's triangular part only
+template<bool LOWER>
+__global__ void __launch_bounds__(256) k_dense_trmv(const double *__restrict__ A, int n, const double *__restrict__ x, double *__restrict__ y) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double *a = A + (size_t)row * n;
+    const int j0 = LOWER ? 0 : row, j1 = LOWER ? row + 1 : n;
+    double s = 0.0;
+    for (int j = (j0 & ~31) + lane; j < j1; j += 32) if (j >= j0) s = fma(__ldg(a + j), x[j], s);
+    s = warp_sum(s);
+    if (lane == 0) y[row] = s;
+}
+void launch_dense_trmv(const LaunchCtx &ctx, const double *A, int n, const double *x, double *y, bool lower) {
+    ProfScope ps(ctx, PC_COARSE_SOLVE, (double)n * n / 2);
+    if (n == 0) return;
+    dim3 block(256), grid((unsigned)(((size_t)n * 32 + 255) / 256));
+    if (lower) k_dense_trmv<true><<<grid, block, 0, ctx.stream>>>(A, n, x, y);
+    else       k_dense_trmv<false><<<grid, block, 0, ctx.stream>>>(A, n, x, y);
+    VF_KERNEL_CHECK();
+}
+
 __global__ void k_gather_free(const double *__restrict__ f, const int *__restrict__ freeDofs, int nfree, long long numNodes, int N, double *__restrict__ rhs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nfree) return;

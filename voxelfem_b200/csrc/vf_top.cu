@@ -6,6 +6,8 @@
 // OC update (OptimalityCriterion.hh:64-83).
 #include "vf_internal.cuh"
 #include "vf_reduce.cuh"
+#include <vector>
+#include <cmath>
 
 namespace vf {
 
@@ -216,6 +218,64 @@ k_filter_smooth(const __grid_constant__ FilterDesc fd, const double *__restrict_
     }
     out[((long long)c0 * fd.sz[1] + c1) * fd.sz[2] + c2] = acc * fd.invTotalWeight;
 }
+// 3D tiled variant: a block stages the (8 + 2r) x (4 + 2r) x (32 + 2r) neighbourhood of its 8 x 4 x 32 element tile in
+// shared memory (reflection applied while loading, TopologyOptimizationFilter.hh:339-345) and every thread then sums the
+// non-zero taps for 4 elements with immediate tile offsets: one LDS + one FMA per tap instead of three reflections,
+// a weight test and a global load.  taps: [offset in tile | weight] pairs in the reference's row-major offset order.
+constexpr int kFtX = 8, kFtY = 4, kFtZ = 32;
+struct FilterTap { int off; int pad; double w; };
+__global__ void __launch_bounds__(256)
+k_filter_smooth3_tiled(const __grid_constant__ FilterDesc fd, const FilterTap *__restrict__ taps, int ntaps,
+                       const double *__restrict__ in, double *__restrict__ out) {
+    extern __shared__ double s_t[];
+    const int r = fd.radius, uy = kFtY + 2 * r, uz = kFtZ + 2 * r, ux = kFtX + 2 * r;
+    const int tid = threadIdx.x + 32 * (threadIdx.y + 4 * threadIdx.z);
+    const int x0 = blockIdx.z * kFtX, y0 = blockIdx.y * kFtY, z0 = blockIdx.x * kFtZ;
+    for (int i = tid; i < ux * uy * uz; i += 256) {
+        const int zi = i % uz; const int q = i / uz; const int yi = q % uy, xi = q / uy;
+        const int gx = reflect_index(x0 - r + xi, fd.sz[0]), gy = reflect_index(y0 - r + yi, fd.sz[1]), gz = reflect_index(z0 - r + zi, fd.sz[2]);
+        s_t[i] = in[((long long)gx * fd.sz[1] + gy) * fd.sz[2] + gz];
+    }
+    __syncthreads();
+    const int cz = z0 + threadIdx.x, cy = y0 + threadIdx.y;
+    if (cz >= fd.sz[2] || cy >= fd.sz[1]) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // element (x0 + tz + 2k, cy, cz), k = 0..3 -> tile centre ((tz + 2k + r) * uy + ty + r) * uz + tx + r
+    const double *base = s_t + ((threadIdx.z + r) * uy + threadIdx.y + r) * uz + threadIdx.x + r;
+    const int kstride = 2 * uy * uz;
+    for (int t = 0; t < ntaps; ++t) {
+        const int off = taps[t].off; const double w = taps[t].w;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = fma(w, base[off + k * kstride], acc[k]);
+    }
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int cx = x0 + threadIdx.z + 2 * k;
+        if (cx < fd.sz[0]) out[((long long)cx * fd.sz[1] + cy) * fd.sz[2] + cz] = acc[k] * fd.invTotalWeight;
+    }
+}
+struct FilterTapCache { int radius = -1, type = -1, n = 0; FilterTap *dev = nullptr; };
+static const FilterTap *filter_taps3(int radius, int type, int &ntaps, cudaStream_t stream) {
+    static FilterTapCache cache[8];
+    for (auto &c : cache) if (c.radius == radius && c.type == type) { ntaps = c.n; return c.dev; }
+    FilterTapCache *slot = nullptr;
+    for (auto &c : cache) if (c.radius < 0) { slot = &c; break; }
+    if (!slot) return nullptr;
+    const int w1 = 2 * radius + 1, uy = kFtY + 2 * radius, uz = kFtZ + 2 * radius;
+    std::vector<FilterTap> h;
+    for (int d0 = -radius; d0 <= radius; ++d0) for (int d1 = -radius; d1 <= radius; ++d1) for (int d2 = -radius; d2 <= radius; ++d2) {
+        const double w = (type == 1) ? ((double)(radius + 1) - std::sqrt((double)(d0 * d0 + d1 * d1 + d2 * d2))) : 1.0;
+        if (w > 0.0) h.push_back(FilterTap{(d0 * uy + d1) * uz + d2, 0, w});
+    }
+    (void)w1;
+    VF_CUDA(cudaMalloc(&slot->dev, h.size() * sizeof(FilterTap)));
+    VF_CUDA(cudaMemcpyAsync(slot->dev, h.data(), h.size() * sizeof(FilterTap), cudaMemcpyHostToDevice, stream));
+    VF_CUDA(cudaStreamSynchronize(stream));
+    slot->radius = radius; slot->type = type; slot->n = (int)h.size();
+    ntaps = slot->n;
+    return slot->dev;
+}
+
 void launch_filter_smooth(const LaunchCtx &ctx, int N, const int *sizes, int radius, int type, const double *in, double *out) {
     FilterDesc fd; fd.N = N; fd.radius = radius; fd.type = type;
     fd.sz[0] = (N == 3) ? sizes[0] : 1; fd.sz[1] = sizes[N - 2]; fd.sz[2] = sizes[N - 1];
@@ -231,6 +291,19 @@ void launch_filter_smooth(const LaunchCtx &ctx, int N, const int *sizes, int rad
     // NOTE: the reference divides by the accumulated weight; multiplying by its reciprocal differs by <= 1 ulp.
     fd.invTotalWeight = 1.0 / tot;
     ProfScope ps(ctx, PC_TOPOPT, (double)fd.sz[0] * fd.sz[1] * fd.sz[2]);
+    if (N == 3 && radius >= 1 && radius <= 4) {
+        int ntaps = 0;
+        const FilterTap *taps = filter_taps3(radius, type, ntaps, ctx.stream);
+        if (taps) {
+            const size_t tile = (size_t)(kFtX + 2 * radius) * (kFtY + 2 * radius) * (kFtZ + 2 * radius) * sizeof(double);
+            static bool attr = false;
+            if (!attr) { VF_CUDA(cudaFuncSetAttribute(k_filter_smooth3_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+            dim3 bt(32, 4, 2), gt((fd.sz[2] + kFtZ - 1) / kFtZ, (fd.sz[1] + kFtY - 1) / kFtY, (fd.sz[0] + kFtX - 1) / kFtX);
+            k_filter_smooth3_tiled<<<gt, bt, tile, ctx.stream>>>(fd, taps, ntaps, in, out);
+            VF_KERNEL_CHECK();
+            return;
+        }
+    }
     dim3 b = (N == 3) ? dim3(32, 4, 2) : dim3(32, 8, 1);
     dim3 gr((fd.sz[2] + b.x - 1) / b.x, (fd.sz[1] + b.y - 1) / b.y, (fd.sz[0] + b.z - 1) / b.z);
     const size_t smem = (size_t)nOff * sizeof(double);
