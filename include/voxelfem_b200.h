@@ -222,6 +222,24 @@ int vf_lbl_run(vf_lbl *l, int zero_init, int64_t layer_increment, int max_iter, 
 int vf_lbl_objective(vf_lbl *l, double *out);                     /* objective (:299) */
 int vf_lbl_gradient(vf_lbl *l, double *g);                        /* gradient (:300) */
 
+/* ---- Method of Moving Asymptotes (pyOptimizer.MMA, python_bindings/Optimizer.cc:11-23) ----------------------
+ * MMA(numVars, numConstr, xmin, xmax, f, df_dx) (MethodOfMovingAsymptotes.hh:34-52).  f writes the m + 1 values
+ * (objective, constraints f_i(x) <= 0) and df_dx the (m + 1) x n row-major gradients; both return 0 on success.
+ * With callbacks_take_device_pointers != 0 the callbacks receive / fill DEVICE arrays (x, df), so an objective that
+ * lives on the GPU (vf_top / vf_lbl) never crosses the bus; otherwise they are host arrays as in the reference. */
+#define VF_MMA_MAX_CONSTRAINTS 8
+typedef struct vf_mma vf_mma;
+typedef int (*vf_mma_f_callback)(const double *x, double *f_out, void *user);
+typedef int (*vf_mma_df_callback)(const double *x, double *df_out, void *user);
+int vf_mma_create(int64_t num_vars, int num_constr, const double *xmin, const double *xmax, vf_mma **out);
+int vf_mma_destroy(vf_mma *mma);
+int vf_mma_enable_gcmma(vf_mma *mma, int enable);                 /* enableGCMMA (:53) */
+int vf_mma_set_initial_var(vf_mma *mma, const double *x);         /* setInitialVar (:54-56) */
+int vf_mma_step(vf_mma *mma, vf_mma_f_callback f, vf_mma_df_callback df_dx, void *user, int callbacks_take_device_pointers); /* step (:63-133) */
+int vf_mma_get_optimal_var(vf_mma *mma, double *x);               /* getOptimalVar (:134) */
+int vf_mma_get_optimal_var_dev(vf_mma *mma, const double **x_dev);
+int64_t vf_mma_newton_iterations(const vf_mma *mma);              /* interior-point Newton directions computed so far */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1293,6 +1293,414 @@ struct Problem { // TopologyOptimizationProblem + MultigridComplianceObjective +
     }
 };
 
+
+// ---------------------------------------------------------------------------
+// LayerByLayerEvaluator (LayerByLayer.hh:25-309) with the Zero / FD / Subspace(N=k) initial-guess
+// generators (:56-209) and the band-limited recurrences for A = U^T K U, b = U^T f (:149-202,
+// TensorProductSimulator.hh:1292-1406).
+// ---------------------------------------------------------------------------
+// Eigen::JacobiSVD(A).solve(b) for a small symmetric matrix (LayerByLayer.hh:120-121): minimum-norm least-squares
+// solution, singular values below eps * k * sigma_max dropped.  One-sided Jacobi on the columns of A.
+static std::vector<double> svdSolveSmall(const std::vector<double> &Ain, const std::vector<double> &b, int k) {
+    std::vector<double> U = Ain, V(size_t(k) * k, 0.0);     // U (k x k, row-major) converges to U * Sigma
+    for (int i = 0; i < k; ++i) V[i * k + i] = 1.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < k; ++p) for (int q = p + 1; q < k; ++q) {
+            double app = 0, aqq = 0, apq = 0;
+            for (int r = 0; r < k; ++r) { app += U[r * k + p] * U[r * k + p]; aqq += U[r * k + q] * U[r * k + q]; apq += U[r * k + p] * U[r * k + q]; }
+            if (std::abs(apq) <= 1e-300 || std::abs(apq) <= 1e-16 * std::sqrt(app * aqq)) continue;
+            rotated = true;
+            const double zeta = (aqq - app) / (2 * apq);
+            const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::abs(zeta) + std::sqrt(1 + zeta * zeta));
+            const double c = 1 / std::sqrt(1 + t * t), sn = c * t;
+            for (int r = 0; r < k; ++r) {
+                const double up = U[r * k + p], uq = U[r * k + q]; U[r * k + p] = c * up - sn * uq; U[r * k + q] = sn * up + c * uq;
+                const double vp = V[r * k + p], vq = V[r * k + q]; V[r * k + p] = c * vp - sn * vq; V[r * k + q] = sn * vp + c * vq;
+            }
+        }
+        if (!rotated) break;
+    }
+    std::vector<double> sig(k), x(k, 0.0);
+    double smax = 0;
+    for (int j = 0; j < k; ++j) { double s = 0; for (int r = 0; r < k; ++r) s += U[r * k + j] * U[r * k + j]; sig[j] = std::sqrt(s); smax = std::max(smax, sig[j]); }
+    const double thresh = std::numeric_limits<double>::epsilon() * k * smax;
+    for (int j = 0; j < k; ++j) {
+        if (sig[j] <= thresh) continue;
+        double proj = 0; for (int r = 0; r < k; ++r) proj += (U[r * k + j] / sig[j]) * b[r];
+        for (int r = 0; r < k; ++r) x[r] += V[r * k + j] * proj / sig[j];
+    }
+    return x;
+}
+
+struct LBL {
+    std::shared_ptr<MG> mg; Sim *sim;
+    int method = 2; size_t maxHist = 3;                  // selectInitMethod("N=3") (:33-36)
+    std::vector<std::vector<double>> hist;               // front = most recent (m_storage, :86)
+    std::vector<double> A, b;                            // subspace system (:205-206); A is s x s row-major
+    std::vector<double> uFull, totalGrad;
+    double totalCompliance = 0; idx layersAccumulated = 0;
+    std::vector<int> layerIters; std::vector<double> layerCompliance;
+    explicit LBL(std::shared_ptr<MG> m) : mg(std::move(m)), sim(mg->sims[0].get()) {}
+
+    void selectInitMethod(const std::string &m) { // :214-220
+        if (m == "zero") { method = 0; maxHist = 0; }
+        else if (m == "constant") { method = 1; maxHist = 1; }
+        else if (m == "fd") { method = 1; maxHist = 2; }
+        else if (m.substr(0, 2) == "N=") { method = 2; maxHist = size_t(std::stoi(m.substr(2))); }
+        else throw std::runtime_error("Unrecognized method " + m);
+        hist.clear(); A.clear(); b.clear();
+    }
+    void checkGravity() const { // TensorProductSimulator.hh:1293-1294
+        double g2 = 0; for (int c = 0; c < sim->N; ++c) g2 += sim->gravity[c] * sim->gravity[c];
+        if (g2 == 0 || std::abs(g2 - sim->gravity[BUILD_DIRECTION] * sim->gravity[BUILD_DIRECTION]) > 1e-10) throw std::runtime_error("Unexpected gravity vector");
+    }
+    template<class F> void visitLayerElements(idx lbegin, idx lend, const F &f) const {
+        for (idx e = 0; e < sim->numElems; ++e) { idx nd[3] = {0, 0, 0}; sim->ndElem(e, nd); if (nd[BUILD_DIRECTION] >= lbegin && nd[BUILD_DIRECTION] < lend) f(e, nd); }
+    }
+    // addLayerRemovalDeltaLoadVector (TensorProductSimulator.hh:1292-1305)
+    void addLayerRemovalDeltaLoad(idx lbegin, idx lend, double *f) const {
+        checkGravity();
+        double vol = 1; for (int d = 0; d < sim->N; ++d) vol *= sim->stretch[d];
+        const double intPhi = 1.0 / double(sim->npe);
+        visitLayerElements(lbegin, lend, [&](idx e, const idx *nd) {
+            const idx off = sim->firstNodeOfElem(nd);
+            const double w = sim->gravity[BUILD_DIRECTION] * (sim->rho[e] * vol);
+            for (int l = 0; l < sim->npe; ++l) f[BUILD_DIRECTION * sim->numNodes + sim->refNodes[l] + off] -= w * intPhi;
+        });
+    }
+    // dotLayerRemovalDeltaLoadVector (:1309-1341)
+    std::vector<double> dotLayerRemovalDeltaLoad(idx lbegin, idx lend) const {
+        checkGravity();
+        double vol = 1; for (int d = 0; d < sim->N; ++d) vol *= sim->stretch[d];
+        const double intPhi = 1.0 / double(sim->npe);
+        std::vector<double> out(hist.size(), 0.0);
+        visitLayerElements(lbegin, lend, [&](idx e, const idx *nd) {
+            const idx off = sim->firstNodeOfElem(nd);
+            const double w = sim->gravity[BUILD_DIRECTION] * (sim->rho[e] * vol);
+            for (size_t i = 0; i < hist.size(); ++i) {
+                double dot = 0; for (int l = 0; l < sim->npe; ++l) dot += hist[i][BUILD_DIRECTION * sim->numNodes + sim->refNodes[l] + off] * intPhi;
+                out[i] -= w * dot;
+            }
+        });
+        return out;
+    }
+    // layerRemovalDeltaUKU (:1346-1406): lower triangle of  result(i, j) += u_i . (delta K) u_j  for voiding [lbegin, lend)
+    void layerRemovalDeltaUKU(idx lbegin, idx lend, std::vector<double> &result, int s) const {
+        const int N = sim->N, ke = sim->ke, npe = sim->npe;
+        std::vector<double> dKu(size_t(sim->numNodes) * N);
+        for (int i = 0; i < s; ++i) {
+            std::fill(dKu.begin(), dKu.end(), 0.0);
+            const std::vector<double> &u = hist[i];
+            visitLayerElements(lbegin, lend, [&](idx e, const idx *nd) {
+                const idx off = sim->firstNodeOfElem(nd);
+                double ue[24], Ku[24];
+                for (int l = 0; l < npe; ++l) for (int c = 0; c < N; ++c) ue[l * N + c] = u[c * sim->numNodes + sim->refNodes[l] + off];
+                for (int a = 0; a < ke; ++a) { double t = 0; for (int bb = 0; bb < ke; ++bb) t += sim->k0(a, bb) * ue[bb]; Ku[a] = t * sim->E[e]; }
+                for (int l = 0; l < npe; ++l) for (int c = 0; c < N; ++c) dKu[c * sim->numNodes + sim->refNodes[l] + off] -= Ku[l * N + c];
+            });
+            for (int j = 0; j <= i; ++j) { double t = 0; for (size_t k = 0; k < dKu.size(); ++k) t += dKu[k] * hist[j][k]; result[i * s + j] += t; }
+        }
+    }
+    void addToHistory(std::vector<double> &u) { // m_addToHistory (:72-84)
+        if (maxHist == 0) return;
+        if (hist.size() == maxHist) hist.pop_back();
+        hist.insert(hist.begin(), std::vector<double>());
+        std::swap(u, hist.front());
+    }
+    void constructGuess(std::vector<double> &g) const {
+        const size_t len = size_t(sim->numNodes) * sim->N, s = hist.size();
+        g.assign(len, 0.0);
+        if (method == 0 || s == 0) return;                               // :56-61, :96, :115-118
+        if (method == 1) {                                                // InitGenFD (:95-100)
+            if (s == 1) g = hist[0];
+            else if (s == 2) for (size_t k = 0; k < len; ++k) g[k] = 2 * hist[0][k] - hist[1][k];
+            else throw std::runtime_error("Unimplemented");
+            return;
+        }
+        const std::vector<double> c = svdSolveSmall(A, b, int(s));       // :120-121
+        sim->maskedVisit([&](idx start, idx n) {                          // :124-128 (detached rows stay zero, :129-146)
+            for (int comp = 0; comp < sim->N; ++comp) for (idx k = 0; k < n; ++k) {
+                const size_t at = size_t(comp) * sim->numNodes + start + k;
+                double t = c[0] * hist[0][at]; for (size_t i = 1; i < s; ++i) t += c[i] * hist[i][at]; g[at] = t;
+            }
+        });
+    }
+    // InitGenSubspace::finalizeLayer (:149-202) / InitializationGenerator::finalizeLayer (:44-46)
+    void finalizeLayer(idx lbegin, idx lend, std::vector<double> &u, const double *r, double compliance) {
+        addToHistory(u);
+        if (method != 2) return;
+        const int s = int(hist.size());
+        const std::vector<double> bOld = b, AOld = A; const int so = int(bOld.size());
+        b.assign(s, 0.0); b[0] = compliance;
+        for (int i = 1; i < s; ++i) b[i] = bOld[i - 1];
+        const std::vector<double> db = dotLayerRemovalDeltaLoad(lbegin, lend);
+        for (int i = 0; i < s; ++i) b[i] += db[i];
+        A.assign(size_t(s) * s, 0.0);
+        A[0] = compliance;
+        for (int i = 1; i < s; ++i) A[i * s] = bOld[i - 1];
+        for (int i = 0; i < s; ++i) A[i * s] -= sim->maskedDot(r, hist[i].data());   // U^T r (:182-197)
+        for (int i = 1; i < s; ++i) for (int j = 1; j < s; ++j) A[i * s + j] = AOld[(i - 1) * so + (j - 1)];
+        layerRemovalDeltaUKU(lbegin, lend, A, s);
+        for (int i = 0; i < s; ++i) for (int j = i + 1; j < s; ++j) A[i * s + j] = A[j * s + i];
+    }
+    // run (:223-296)
+    void run(bool zeroInit, idx layerIncrement, int maxIter, double tol, int mgIterations, int mgSmoothing, bool fmg) {
+        const idx numLayers = sim->ne[BUILD_DIRECTION];
+        const size_t len = size_t(sim->numNodes) * sim->N;
+        std::vector<double> f(len), u;
+        if (!zeroInit) u = uFull;
+        hist.clear(); A.clear(); b.clear();
+        layersAccumulated = 0; totalCompliance = 0; totalGrad.assign(sim->numElems, 0.0); layerIters.clear(); layerCompliance.clear();
+        mg->setMaskByLayer(numLayers);
+        sim->buildLoadVector(f.data());
+        for (idx l = numLayers; l > 0; l -= std::min(layerIncrement, l)) {
+            if (l < numLayers) { mg->decrementMaskByLayer(int(layerIncrement)); addLayerRemovalDeltaLoad(l, l + layerIncrement, f.data()); }
+            if (l < numLayers || u.size() != len) constructGuess(u);
+            mg->pcg(u.data(), f.data(), maxIter, tol, mgIterations, mgSmoothing, fmg, true);
+            layerIters.push_back(mg->lastIters);
+            const double compliance = sim->maskedDot(f.data(), u.data());
+            layerCompliance.push_back(compliance);
+            totalCompliance += compliance;
+            sim->complianceGradient(u.data(), totalGrad.data(), true);
+            ++layersAccumulated;
+            if (l == numLayers) uFull = u;
+            if (l >= layerIncrement) finalizeLayer(l - layerIncrement, l, u, mg->b[0].data(), compliance);
+        }
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// MMA / GCMMA (MethodOfMovingAsymptotes.hh:28-469): Svanberg's method of moving asymptotes with the primal-dual
+// interior-point subproblem solver.  Row i of the (m+1) x n arrays is function i (0 = objective).
+// ---------------------------------------------------------------------------
+typedef void (*mma_f_cb)(const double *x, double *f, void *user);          // f: m + 1 values
+typedef void (*mma_df_cb)(const double *x, double *df, void *user);        // df: (m + 1) x n, row-major
+// Solve the small dense system M sol = rhs (MethodOfMovingAsymptotes.hh:351 uses colPivHouseholderQr; any backward-stable
+// solve agrees to rounding): Gaussian elimination with partial pivoting.
+static std::vector<double> solveDense(std::vector<double> M, std::vector<double> rhs, int k) {
+    for (int c = 0; c < k; ++c) {
+        int piv = c; for (int r = c + 1; r < k; ++r) if (std::abs(M[r * k + c]) > std::abs(M[piv * k + c])) piv = r;
+        if (piv != c) { for (int j = 0; j < k; ++j) std::swap(M[c * k + j], M[piv * k + j]); std::swap(rhs[c], rhs[piv]); }
+        for (int r = c + 1; r < k; ++r) {
+            const double fct = M[r * k + c] / M[c * k + c];
+            for (int j = c; j < k; ++j) M[r * k + j] -= fct * M[c * k + j];
+            rhs[r] -= fct * rhs[c];
+        }
+    }
+    std::vector<double> x(k);
+    for (int r = k - 1; r >= 0; --r) { double t = rhs[r]; for (int j = r + 1; j < k; ++j) t -= M[r * k + j] * x[j]; x[r] = t / M[r * k + r]; }
+    return x;
+}
+struct MMA {
+    using V = std::vector<double>;
+    int m, n; V xmin, xmax, xdiff, a, d, c; const double a0 = 1;
+    mma_f_cb f; mma_df_cb df; void *user;
+    bool enableInner = false; int outerIter = 0, innerIter = 0;
+    std::vector<V> xhist;                         // front = x^k (FixedSizeDeque<AXd>{3})
+    V l, u, alpha, beta, xInner, rho, p, q, r, fcur, dfp, dfm, diffFSubf;
+    struct IV { V umx, xml, umx2, xml2; } cur, old;
+    const double raa0 = 1e-5, albefa = 0.1, move = 0.5, asyinit = 0.5; // :196
+    // subproblem state (:452-465)
+    struct Vars { double z, zeta; V x, xi, eta, y, lam, mu, s; } data, delta;
+    V Dx, G, dpsi, plam, qlam, gvec;
+    long subsolveNewtonIters = 0;
+
+    MMA(int n_, int m_, const double *xmin_, const double *xmax_, mma_f_cb f_, mma_df_cb df_, void *user_)
+        : m(m_), n(n_), xmin(xmin_, xmin_ + n_), xmax(xmax_, xmax_ + n_), xdiff(n_), a(m_, 0.0), d(m_, 1.0), c(m_, 1000.0), f(f_), df(df_), user(user_) {
+        for (int j = 0; j < n; ++j) xdiff[j] = xmax[j] - xmin[j];
+        l.assign(n, 0); u.assign(n, 0); alpha.assign(n, 0); beta.assign(n, 0);
+        p.assign(size_t(m + 1) * n, 0); q.assign(size_t(m + 1) * n, 0); dfp.assign(size_t(m + 1) * n, 0); dfm.assign(size_t(m + 1) * n, 0);
+        cur.umx.assign(n, 0); cur.xml.assign(n, 0); cur.umx2.assign(n, 0); cur.xml2.assign(n, 0);
+    }
+    void setInitialVar(const double *x) { addToHistory(V(x, x + n)); }   // :54-56
+    void addToHistory(V x) { xhist.insert(xhist.begin(), std::move(x)); if (xhist.size() > 3) xhist.pop_back(); }
+    const V &xcur() const { return xhist[0]; }
+    // g_i(x) = sum_j p_ij / (u_j - x_j) + q_ij / (x_j - l_j)   (:160-180); rows [first, m]
+    V subG(bool allRows, bool useOld = false) const {
+        const IV &v = useOld ? old : cur; const int first = allRows ? 0 : 1;
+        V res(m + 1 - first);
+        for (int i = first; i <= m; ++i) { double t = 0; for (int j = 0; j < n; ++j) t += p[size_t(i) * n + j] / v.umx[j] + q[size_t(i) * n + j] / v.xml[j]; res[i - first] = t; }
+        return res;
+    }
+    void refreshCur(const V &x) { for (int j = 0; j < n; ++j) { cur.umx[j] = u[j] - x[j]; cur.umx2[j] = cur.umx[j] * cur.umx[j]; cur.xml[j] = x[j] - l[j]; cur.xml2[j] = cur.xml[j] * cur.xml[j]; } }
+    void buildPQ(const V &rhoRow, const IV &v) { // :108-114 / :123-129
+        for (int i = 0; i <= m; ++i) for (int j = 0; j < n; ++j) {
+            const double rod = rhoRow[i] / xdiff[j], dp = dfp[size_t(i) * n + j], dm = dfm[size_t(i) * n + j];
+            p[size_t(i) * n + j] = v.umx2[j] * (1.001 * dp + 0.001 * dm + rod);
+            q[size_t(i) * n + j] = v.xml2[j] * (0.001 * dp + 1.001 * dm + rod);
+        }
+    }
+    V nextRho() const { // :136-156
+        V res(m + 1);
+        if (innerIter == 0) {
+            for (int i = 0; i <= m; ++i) { double t = 0; for (int j = 0; j < n; ++j) t += 0.1 / n * (dfp[size_t(i) * n + j] + dfm[size_t(i) * n + j]) * xdiff[j]; res[i] = std::max(t, 1e-6); }
+            return res;
+        }
+        double dd = 0;
+        for (int j = 0; j < n; ++j) { const double dx = xInner[j] - xcur()[j]; dd += (u[j] - l[j]) * dx * dx / (cur.umx[j] * cur.xml[j] * xdiff[j]); }
+        for (int i = 0; i <= m; ++i) { const double del = diffFSubf[i] / dd; res[i] = del < 0 ? rho[i] : std::min(1.1 * (rho[i] + del), 10 * rho[i]); }
+        return res;
+    }
+    bool isFeasible() { // :190-193
+        V fx(m + 1); f(xInner.data(), fx.data(), user);
+        const V g = subG(true); diffFSubf.assign(m + 1, 0.0);
+        double mx = -std::numeric_limits<double>::infinity();
+        for (int i = 0; i <= m; ++i) { diffFSubf[i] = fx[i] - (g[i] + r[i]); mx = std::max(mx, diffFSubf[i]); }
+        return mx < 0;
+    }
+    void step() { // :63-133
+        if (xhist.empty()) throw std::runtime_error("Must specify an initial value");
+        ++outerIter;
+        const V &x = xcur();
+        if (outerIter <= 2) for (int j = 0; j < n; ++j) { l[j] = x[j] - asyinit * xdiff[j]; u[j] = x[j] + asyinit * xdiff[j]; }
+        else for (int j = 0; j < n; ++j) {
+            const double diff = (xhist[0][j] - xhist[1][j]) * (xhist[1][j] - xhist[2][j]);
+            const double gam = diff > 0 ? 1.2 : 0.7;
+            l[j] = std::max(std::min(xhist[0][j] - gam * (xhist[1][j] - l[j]), x[j] - 0.01 * xdiff[j]), x[j] - 10 * xdiff[j]);
+            u[j] = std::min(std::max(xhist[0][j] + gam * (u[j] - xhist[1][j]), x[j] + 0.01 * xdiff[j]), x[j] + 10 * xdiff[j]);
+        }
+        for (int j = 0; j < n; ++j) {
+            alpha[j] = std::max(std::max(xmin[j], l[j] + albefa * (x[j] - l[j])), x[j] - move * xdiff[j]);
+            beta[j]  = std::min(std::min(xmax[j], u[j] - albefa * (u[j] - x[j])), x[j] + move * xdiff[j]);
+        }
+        fcur.assign(m + 1, 0.0); f(x.data(), fcur.data(), user);
+        df(x.data(), dfp.data(), user);
+        for (size_t k = 0; k < dfp.size(); ++k) { dfm[k] = std::max(-dfp[k], 0.0); dfp[k] = std::max(dfp[k], 0.0); }
+        refreshCur(x);
+        if (enableInner) {
+            old = cur;
+            do {
+                rho = nextRho();
+                buildPQ(rho, old);
+                const V g = subG(true, true); r.assign(m + 1, 0.0); for (int i = 0; i <= m; ++i) r[i] = fcur[i] - g[i];
+                xInner = subsolve();
+                ++innerIter;
+            } while (!isFeasible());
+            addToHistory(xInner); innerIter = 0;
+        } else {
+            buildPQ(V(m + 1, raa0), cur);
+            const V g = subG(true); r.assign(m + 1, 0.0); for (int i = 0; i <= m; ++i) r[i] = fcur[i] - g[i];
+            addToHistory(subsolve());
+        }
+    }
+    // ---- Subproblem (:240-466) ----
+    void refreshDual() { // the recomputation block of init_vars (:303-312) and squared_residual (:401-411)
+        refreshCur(data.x);
+        for (int j = 0; j < n; ++j) {
+            double pl = p[j], ql = q[j];
+            for (int i = 0; i < m; ++i) { pl += p[size_t(i + 1) * n + j] * data.lam[i]; ql += q[size_t(i + 1) * n + j] * data.lam[i]; }
+            plam[j] = pl; qlam[j] = ql; dpsi[j] = pl / cur.umx2[j] - ql / cur.xml2[j];
+        }
+        gvec = subG(false);
+    }
+    void initVars() { // :281-313
+        data.x.assign(n, 0); data.xi.assign(n, 0); data.eta.assign(n, 0);
+        data.y.assign(m, 1.0); data.z = 1; data.zeta = 1; data.lam.assign(m, 1.0); data.s.assign(m, 1.0); data.mu.assign(m, 0.0);
+        for (int i = 0; i < m; ++i) data.mu[i] = std::max(c[i] / 2, 1.0);
+        Dx.assign(n, 0); G.assign(size_t(m) * n, 0); delta.x.assign(n, 0); delta.xi.assign(n, 0); delta.eta.assign(n, 0);
+        dpsi.assign(n, 0); plam.assign(n, 0); qlam.assign(n, 0);
+        for (int j = 0; j < n; ++j) {
+            data.x[j] = 0.5 * (alpha[j] + beta[j]);
+            data.xi[j] = std::max(1.0 / (data.x[j] - alpha[j]), 1.0);
+            data.eta[j] = std::max(1.0 / (beta[j] - data.x[j]), 1.0);
+        }
+        refreshDual();
+    }
+    void newtonDirection(double eps) { // :315-363
+        for (int j = 0; j < n; ++j) {
+            const double xa = data.x[j] - alpha[j], bx = beta[j] - data.x[j];
+            delta.x[j] = dpsi[j] - eps / xa + eps / bx;
+            Dx[j] = 2 * plam[j] / (cur.umx[j] * cur.umx2[j]) + 2 * qlam[j] / (cur.xml[j] * cur.xml2[j]) + data.xi[j] / xa + data.eta[j] / bx;
+            for (int i = 0; i < m; ++i) G[size_t(i) * n + j] = p[size_t(i + 1) * n + j] / cur.umx2[j] - q[size_t(i + 1) * n + j] / cur.xml2[j];
+        }
+        V Dy(m), dy(m);
+        for (int i = 0; i < m; ++i) { Dy[i] = d[i] + data.mu[i] / data.y[i]; dy[i] = c[i] + d[i] * data.y[i] - data.lam[i] - eps / data.y[i]; }
+        const int k = m + 1; V M(size_t(k) * k, 0.0), rhs(k, 0.0);
+        for (int ci = 0; ci < m; ++ci) for (int cj = ci; cj < m; ++cj) { double t = 0; for (int j = 0; j < n; ++j) t += G[size_t(ci) * n + j] * G[size_t(cj) * n + j] / Dx[j]; M[ci * k + cj] = t; }
+        for (int i = 0; i < m; ++i) { M[i * k + i] += data.s[i] / data.lam[i] + 1 / Dy[i]; M[i * k + m] = a[i]; }
+        M[m * k + m] = -data.zeta / data.z;
+        for (int i = 0; i < k; ++i) for (int j = i + 1; j < k; ++j) M[j * k + i] = M[i * k + j];
+        for (int i = 0; i < m; ++i) {
+            rhs[i] = gvec[i] - a[i] * data.z - data.y[i] + r[i + 1] + eps / data.lam[i] + dy[i] / Dy[i];
+            double t = 0; for (int j = 0; j < n; ++j) t += G[size_t(i) * n + j] * (delta.x[j] / Dx[j]);
+            rhs[i] -= t;
+        }
+        double la = 0; for (int i = 0; i < m; ++i) la += data.lam[i] * a[i];
+        rhs[m] = a0 - la - eps / data.z;
+        const V sol = solveDense(M, rhs, k);
+        delta.lam.assign(sol.begin(), sol.begin() + m); delta.z = sol[m];
+        for (int j = 0; j < n; ++j) {
+            const double xa = data.x[j] - alpha[j], bx = beta[j] - data.x[j];
+            double gl = 0; for (int i = 0; i < m; ++i) gl += G[size_t(i) * n + j] * delta.lam[i];
+            delta.x[j] = -(delta.x[j] + gl) / Dx[j];
+            delta.xi[j] = -data.xi[j] + eps / xa - data.xi[j] * delta.x[j] / xa;
+            delta.eta[j] = -data.eta[j] + eps / bx + data.eta[j] * delta.x[j] / bx;
+        }
+        delta.y.assign(m, 0); delta.mu.assign(m, 0); delta.s.assign(m, 0);
+        for (int i = 0; i < m; ++i) {
+            delta.y[i] = delta.lam[i] / Dy[i] - dy[i] / Dy[i];
+            delta.mu[i] = (eps - data.mu[i] * delta.y[i]) / data.y[i] - data.mu[i];
+            delta.s[i] = (eps - data.s[i] * delta.lam[i]) / data.lam[i] - data.s[i];
+        }
+        delta.zeta = (eps - data.zeta * delta.z) / data.z - data.zeta;
+    }
+    double stepSatisfyKKT() const { // :384-397
+        double mn = std::numeric_limits<double>::infinity();
+        for (int j = 0; j < n; ++j) {
+            mn = std::min(mn, delta.x[j] / (data.x[j] - alpha[j])); mn = std::min(mn, delta.x[j] / (data.x[j] - beta[j]));
+            mn = std::min(mn, delta.xi[j] / data.xi[j]); mn = std::min(mn, delta.eta[j] / data.eta[j]);
+        }
+        for (int i = 0; i < m; ++i) { mn = std::min(mn, delta.y[i] / data.y[i]); mn = std::min(mn, delta.s[i] / data.s[i]); mn = std::min(mn, delta.mu[i] / data.mu[i]); mn = std::min(mn, delta.lam[i] / data.lam[i]); }
+        mn = std::min(mn, delta.z / data.z); mn = std::min(mn, delta.zeta / data.zeta);
+        return 1 / std::max(-1.01 * mn, 1.0);
+    }
+    void newtonStep(double t) { // :426-438
+        for (int j = 0; j < n; ++j) { data.x[j] += t * delta.x[j]; data.xi[j] += t * delta.xi[j]; data.eta[j] += t * delta.eta[j]; }
+        for (int i = 0; i < m; ++i) { data.y[i] += t * delta.y[i]; data.lam[i] += t * delta.lam[i]; data.mu[i] += t * delta.mu[i]; data.s[i] += t * delta.s[i]; }
+        data.z += t * delta.z; data.zeta += t * delta.zeta;
+    }
+    // eq_a .. eq_i (:440-450): squared norm and max-norm of the perturbed KKT residual
+    void kktResidual(double eps, const V &g, double &sq, double &mx) const {
+        sq = 0; mx = 0;
+        auto acc = [&](double v) { sq += v * v; mx = std::max(mx, std::abs(v)); };
+        for (int j = 0; j < n; ++j) { acc(dpsi[j] - data.xi[j] + data.eta[j]); acc(data.xi[j] * (data.x[j] - alpha[j]) - eps); acc(data.eta[j] * (beta[j] - data.x[j]) - eps); }
+        double la = 0;
+        for (int i = 0; i < m; ++i) {
+            acc(c[i] + d[i] * data.y[i] - data.lam[i] - data.mu[i]);
+            acc(g[i] - a[i] * data.z - data.y[i] + data.s[i] + r[i + 1]);
+            acc(data.mu[i] * data.y[i] - eps); acc(data.lam[i] * data.s[i] - eps);
+            la += data.lam[i] * a[i];
+        }
+        acc(a0 - data.zeta - la); acc(data.zeta * data.z - eps);
+    }
+    double squaredResidual(double eps, bool init = false) { if (!init) refreshDual(); double sq, mx; kktResidual(eps, gvec, sq, mx); return sq; } // :399-424
+    double kktInfNorm(double eps) const { double sq, mx; kktResidual(eps, subG(false), sq, mx); return mx; }                               // :261-279
+    double backtrack(double eps, double resOld) { // :365-376
+        double t = stepSatisfyKKT();
+        newtonStep(t);
+        double res = squaredResidual(eps);
+        while (res > resOld) { t /= 2; newtonStep(-t); res = squaredResidual(eps); }
+        return res;
+    }
+    V subsolve() { // :242-258
+        initVars();
+        double eps = 1;
+        while (eps > 1e-7) {
+            double resOld = 0;
+            for (int i = 0; i < 10; ++i) {
+                newtonDirection(eps); ++subsolveNewtonIters;
+                if (i == 0) resOld = squaredResidual(eps, true);
+                resOld = backtrack(eps, resOld);
+                if (kktInfNorm(eps) <= 0.9 * eps) break;
+            }
+            eps *= 0.1;
+        }
+        return data.x;
+    }
+};
+
 } // namespace vfo
 
 // ---------------------------------------------------------------------------
@@ -1422,4 +1830,26 @@ void vfo_problem_get_u(void *h, double *u) { std::copy(P(h).u.begin(), P(h).u.en
 int vfo_problem_last_pcg_iters(void *h) { return P(h).lastPcgIters; }
 int vfo_problem_oc_step(void *h, double m, double p, double ctol, int *nevals) { VFO_TRY int n = P(h).ocStep(m, p, ctol); if (nevals) *nevals = n; VFO_CATCH }
 void vfo_problem_get_lambda(void *h, double *lo, double *hi) { *lo = P(h).lamMin; *hi = P(h).lamMax; }
+}
+
+// ---- layer-by-layer evaluator ----
+struct LBLHandle { std::unique_ptr<LBL> l; };
+static LBL &LB(void *h) { return *static_cast<LBLHandle *>(h)->l; }
+extern "C" {
+void *vfo_lbl_create(void *mgh) { auto *h = new LBLHandle; h->l = std::make_unique<LBL>(static_cast<MGHandle *>(mgh)->m); return h; }
+void vfo_lbl_destroy(void *h) { delete static_cast<LBLHandle *>(h); }
+int vfo_lbl_select_init_method(void *h, const char *m) { VFO_TRY LB(h).selectInitMethod(m); VFO_CATCH }
+int vfo_lbl_run(void *h, int zeroInit, int64_t inc, int maxIter, double tol, int mgIt, int mgSmooth, int fmg) { VFO_TRY LB(h).run(zeroInit != 0, inc, maxIter, tol, mgIt, mgSmooth, fmg != 0); VFO_CATCH }
+double vfo_lbl_objective(void *h) { return 0.5 * LB(h).totalCompliance / double(LB(h).layersAccumulated); }
+void vfo_lbl_gradient(void *h, double *g) { LBL &l = LB(h); for (size_t i = 0; i < l.totalGrad.size(); ++i) g[i] = l.totalGrad[i] / double(l.layersAccumulated); }
+int vfo_lbl_num_layers_run(void *h) { return int(LB(h).layerIters.size()); }
+void vfo_lbl_layer_info(void *h, int32_t *iters, double *compliance) { LBL &l = LB(h); for (size_t i = 0; i < l.layerIters.size(); ++i) { iters[i] = l.layerIters[i]; compliance[i] = l.layerCompliance[i]; } }
+// ---- MMA ----
+void *vfo_mma_create(int n, int m, const double *xmin, const double *xmax, mma_f_cb f, mma_df_cb df, void *user) { return new MMA(n, m, xmin, xmax, f, df, user); }
+void vfo_mma_destroy(void *h) { delete static_cast<MMA *>(h); }
+void vfo_mma_enable_gcmma(void *h, int e) { static_cast<MMA *>(h)->enableInner = e != 0; }
+void vfo_mma_set_initial_var(void *h, const double *x) { static_cast<MMA *>(h)->setInitialVar(x); }
+int vfo_mma_step(void *h) { VFO_TRY static_cast<MMA *>(h)->step(); VFO_CATCH }
+void vfo_mma_get_optimal_var(void *h, double *x) { MMA &M_ = *static_cast<MMA *>(h); std::copy(M_.xhist[0].begin(), M_.xhist[0].end(), x); }
+int64_t vfo_mma_newton_iterations(void *h) { return static_cast<MMA *>(h)->subsolveNewtonIters; }
 }

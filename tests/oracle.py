@@ -27,6 +27,9 @@ def build_oracle(force=False):
     return _LIB_PATH
 
 
+MMA_F_CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+MMA_DF_CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
 _lib = None
 
 
@@ -104,6 +107,21 @@ def lib():
         "vfo_problem_last_pcg_iters": (ci, [vp]),
         "vfo_problem_oc_step": (ci, [vp, cd, cd, cd, C.POINTER(ci)]),
         "vfo_problem_get_lambda": (None, [vp, C.POINTER(cd), C.POINTER(cd)]),
+        "vfo_lbl_create": (vp, [vp]),
+        "vfo_lbl_destroy": (None, [vp]),
+        "vfo_lbl_select_init_method": (ci, [vp, C.c_char_p]),
+        "vfo_lbl_run": (ci, [vp, ci, i64, ci, cd, ci, ci, ci]),
+        "vfo_lbl_objective": (cd, [vp]),
+        "vfo_lbl_gradient": (None, [vp, _dp]),
+        "vfo_lbl_num_layers_run": (ci, [vp]),
+        "vfo_lbl_layer_info": (None, [vp, _i32p, _dp]),
+        "vfo_mma_create": (vp, [ci, ci, _dp, _dp, MMA_F_CB, MMA_DF_CB, vp]),
+        "vfo_mma_destroy": (None, [vp]),
+        "vfo_mma_enable_gcmma": (None, [vp, ci]),
+        "vfo_mma_set_initial_var": (None, [vp, _dp]),
+        "vfo_mma_step": (ci, [vp]),
+        "vfo_mma_get_optimal_var": (None, [vp, _dp]),
+        "vfo_mma_newton_iterations": (i64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -452,3 +470,59 @@ def projection_apply(x, beta):
 def projection_backprop(g, vars_, beta):
     g = np.ascontiguousarray(g, dtype=np.float64).ravel(); out = np.zeros_like(g)
     lib().vfo_projection_backprop(len(g), beta, g, np.ascontiguousarray(vars_, dtype=np.float64).ravel(), out); return out
+
+
+class OracleLBL:
+    """LayerByLayerEvaluator (LayerByLayer.hh:25-309)."""
+
+    def __init__(self, mg):
+        self.L = lib(); self.mg = mg
+        self.h = self.L.vfo_lbl_create(mg.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.vfo_lbl_destroy(self.h); self.h = None
+
+    def select_init_method(self, m): _check(self.L.vfo_lbl_select_init_method(self.h, m.encode()))
+
+    def run(self, zero_init=True, layer_increment=1, max_iter=50, tol=1e-5, mg_iterations=1, mg_smoothing=1, fmg=False):
+        _check(self.L.vfo_lbl_run(self.h, int(zero_init), layer_increment, max_iter, tol, mg_iterations, mg_smoothing, int(fmg)))
+        n = self.L.vfo_lbl_num_layers_run(self.h)
+        it = np.zeros(n, dtype=np.int32); c = np.zeros(n)
+        self.L.vfo_lbl_layer_info(self.h, it, c)
+        return it, c
+
+    def objective(self): return self.L.vfo_lbl_objective(self.h)
+
+    def gradient(self):
+        g = np.zeros(self.mg.sim.num_elements); self.L.vfo_lbl_gradient(self.h, g); return g
+
+
+class OracleMMA:
+    """MMA (MethodOfMovingAsymptotes.hh:28-469); f(x) -> (m+1,), df_dx(x) -> (m+1, n)."""
+
+    def __init__(self, n, m, xmin, xmax, f, df_dx):
+        self.L = lib(); self.n, self.m = n, m
+
+        def _f(xp, out, _):
+            x = np.ctypeslib.as_array(xp, shape=(n,))
+            np.ctypeslib.as_array(out, shape=(m + 1,))[:] = np.asarray(f(x.copy()), dtype=np.float64).ravel()
+
+        def _df(xp, out, _):
+            x = np.ctypeslib.as_array(xp, shape=(n,))
+            np.ctypeslib.as_array(out, shape=(m + 1, n))[:] = np.asarray(df_dx(x.copy()), dtype=np.float64).reshape(m + 1, n)
+        self._cbs = (MMA_F_CB(_f), MMA_DF_CB(_df))
+        self.h = self.L.vfo_mma_create(n, m, np.ascontiguousarray(xmin, dtype=np.float64), np.ascontiguousarray(xmax, dtype=np.float64), self._cbs[0], self._cbs[1], None)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.vfo_mma_destroy(self.h); self.h = None
+
+    def enableGCMMA(self, e): self.L.vfo_mma_enable_gcmma(self.h, int(e))
+    def setInitialVar(self, x): self.L.vfo_mma_set_initial_var(self.h, np.ascontiguousarray(x, dtype=np.float64))
+    def step(self): _check(self.L.vfo_mma_step(self.h))
+
+    def getOptimalVar(self):
+        x = np.zeros(self.n); self.L.vfo_mma_get_optimal_var(self.h, x); return x
+
+    def newton_iterations(self): return self.L.vfo_mma_newton_iterations(self.h)

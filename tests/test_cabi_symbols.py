@@ -13,7 +13,7 @@ def declared_symbols():
     text = open(os.path.join(ROOT, "include", "voxelfem_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = set(re.findall(r"\b(vf_[a-z0-9_]+)\s*\(", text))
-    names -= {"vf_pcg_callback", "vf_lbl_callback"}
+    names -= {"vf_pcg_callback", "vf_lbl_callback", "vf_mma_f_callback", "vf_mma_df_callback"}
     return sorted(names)
 
 

@@ -20,6 +20,8 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 PCG_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_void_p)
 LBL_CALLBACK = C.CFUNCTYPE(None, C.c_int64, C.c_double, C.c_int, C.c_void_p)
+MMA_F_CALLBACK = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+MMA_DF_CALLBACK = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
 
 _lib = None
 
@@ -139,6 +141,14 @@ def lib():
         "vf_lbl_run": (ci, [vp, ci, i64, ci, cd, ci, ci, ci, LBL_CALLBACK, vp]),
         "vf_lbl_objective": (ci, [vp, C.POINTER(cd)]),
         "vf_lbl_gradient": (ci, [vp, _dp]),
+        "vf_mma_create": (ci, [i64, ci, _dp, _dp, pvp]),
+        "vf_mma_destroy": (ci, [vp]),
+        "vf_mma_enable_gcmma": (ci, [vp, ci]),
+        "vf_mma_set_initial_var": (ci, [vp, _dp]),
+        "vf_mma_step": (ci, [vp, MMA_F_CALLBACK, MMA_DF_CALLBACK, vp, ci]),
+        "vf_mma_get_optimal_var": (ci, [vp, _dp]),
+        "vf_mma_get_optimal_var_dev": (ci, [vp, pvp]),
+        "vf_mma_newton_iterations": (i64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here == header/library mismatch
@@ -644,3 +654,86 @@ def projection_apply(x, beta):
 def projection_backprop(g, vars_, beta):
     g = np.ascontiguousarray(g, dtype=np.float64).ravel(); out = np.zeros_like(g)
     _check(lib().vf_filter_project_backprop(len(g), beta, g, np.ascontiguousarray(vars_, dtype=np.float64).ravel(), out)); return out
+
+
+class LBL:
+    """LayerByLayerEvaluator (LayerByLayer.hh:25-309) on the GPU."""
+
+    def __init__(self, mg):
+        self.L = lib(); self.mg = mg
+        h = C.c_void_p()
+        _check(self.L.vf_lbl_create(mg.h, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.vf_lbl_destroy(self.h); self.h = None
+
+    def select_init_method(self, m): _check(self.L.vf_lbl_select_init_method(self.h, m.encode()))
+
+    def run(self, zero_init=True, layer_increment=1, max_iter=50, tol=1e-5, mg_iterations=1, mg_smoothing=1, fmg=False, callback=None):
+        its, cs = [], []
+
+        def _cb(layer, compliance, iters, _):
+            its.append(iters); cs.append(compliance)
+            if callback is not None:
+                callback(layer, compliance, iters)
+        cb = LBL_CALLBACK(_cb)
+        _check(self.L.vf_lbl_run(self.h, int(zero_init), layer_increment, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), cb, None))
+        return np.array(its, dtype=np.int32), np.array(cs)
+
+    def objective(self):
+        v = C.c_double(0); _check(self.L.vf_lbl_objective(self.h, C.byref(v))); return v.value
+
+    def gradient(self):
+        g = np.zeros(self.mg.sim.num_elements); _check(self.L.vf_lbl_gradient(self.h, g)); return g
+
+
+class MMA:
+    """pyOptimizer.MMA (python_bindings/Optimizer.cc:11-23): MMA(numVars, numConstr, xmin, xmax, f, df_dx)."""
+
+    def __init__(self, numVars, numConstr, xmin, xmax, f, df_dx):
+        self.L = lib(); self.n, self.m = int(numVars), int(numConstr)
+        n, m = self.n, self.m
+        self._err = None
+
+        def _f(xp, out, _):
+            try:
+                x = np.ctypeslib.as_array(xp, shape=(n,)).copy()
+                np.ctypeslib.as_array(out, shape=(m + 1,))[:] = np.asarray(f(x), dtype=np.float64).ravel()
+                return 0
+            except Exception as e:  # surfaced by step()
+                self._err = e
+                return 1
+
+        def _df(xp, out, _):
+            try:
+                x = np.ctypeslib.as_array(xp, shape=(n,)).copy()
+                np.ctypeslib.as_array(out, shape=(m + 1, n))[:] = np.asarray(df_dx(x), dtype=np.float64).reshape(m + 1, n)
+                return 0
+            except Exception as e:
+                self._err = e
+                return 1
+        self._cbs = (MMA_F_CALLBACK(_f), MMA_DF_CALLBACK(_df))
+        h = C.c_void_p()
+        _check(self.L.vf_mma_create(n, m, np.ascontiguousarray(xmin, dtype=np.float64), np.ascontiguousarray(xmax, dtype=np.float64), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.vf_mma_destroy(self.h); self.h = None
+
+    def enableGCMMA(self, enable): _check(self.L.vf_mma_enable_gcmma(self.h, int(enable)))
+    def setInitialVar(self, x): _check(self.L.vf_mma_set_initial_var(self.h, np.ascontiguousarray(x, dtype=np.float64)))
+
+    def step(self):
+        self._err = None
+        rc = self.L.vf_mma_step(self.h, self._cbs[0], self._cbs[1], None, 0)
+        if self._err is not None:
+            raise self._err
+        _check(rc)
+
+    def getOptimalVar(self):
+        x = np.zeros(self.n); _check(self.L.vf_mma_get_optimal_var(self.h, x)); return x
+
+    def newton_iterations(self): return self.L.vf_mma_newton_iterations(self.h)

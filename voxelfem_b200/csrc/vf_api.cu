@@ -25,6 +25,7 @@ namespace vf {
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void set_last_error(const std::string &msg) { g_err = msg; }
 
 // ---------------------------------------------------------------------------
 // Profiler: CUDA-event pairs around each launch, resolved lazily

@@ -141,6 +141,7 @@ struct LaunchCtx {
 void prof_begin(const LaunchCtx &ctx, int cat, double units);
 void prof_end(const LaunchCtx &ctx, int cat);
 void count_launch();
+void set_last_error(const std::string &msg);   // message returned by vf_last_error() on this thread
 
 struct ProfScope {
     const LaunchCtx &c; int cat;
