@@ -133,6 +133,9 @@ int vf_mg_pcg(vf_mg *mg, double *x, const double *b, int max_iter, double tol, i
               int mg_smoothing_iterations, int fmg, int dirichlet_already_satisfied,
               int *out_iterations, double *residual_norms, vf_pcg_callback cb, void *user);
 int vf_mg_get_pcg_residual(vf_mg *mg, double *r);                         /* pcgResidual (:1156) */
+/* Current iterate x of the running PCG: valid inside cb (the reference's it_callback receives (it, x, r),
+ * MultigridSolver.hh:1043-1045, 1146-1147) and until the buffers passed to the last solve are released. */
+int vf_mg_get_pcg_iterate(vf_mg *mg, double *x);
 int vf_mg_set_symmetric_gauss_seidel(vf_mg *mg, int symmetric);           /* setSymmetricGaussSeidel (:123-125) */
 int vf_mg_set_mask_layer(vf_mg *mg, int64_t fine_layer);                  /* setFabricationMaskHeightByLayer (:1022-1028) */
 int vf_mg_decrement_mask(vf_mg *mg, int fine_layer_increment);            /* decrementFabricationMaskHeightByLayer (:1030-1036) */

@@ -12,7 +12,7 @@ for w in $WHAT; do case $w in
     $NCU --metrics gpu__time_duration.sum -c 1200 --csv --log-file $OUT/${TAG}_launches.csv $DRV > $OUT/${TAG}_launches.log 2>&1 ;;
   gs_l0)    $NCU --set full --import-source on -k regex:k_gs -s 2 -c 2 -o $OUT/${TAG}_gs_l0 -f $DRV > $OUT/${TAG}_gs_l0.log 2>&1 ;;
   apply_l0) $NCU --set full --import-source on -k regex:k_apply -s 1 -c 2 -o $OUT/${TAG}_apply_l0 -f $DRV > $OUT/${TAG}_apply_l0.log 2>&1 ;;
-  stencil)  # level-1 colour passes (launches 51..58 of k_stencil_tile in the first FMG cycle) and the level-1 residual (59)
-    $NCU --set full --import-source on -k regex:k_stencil_tile -s 56 -c 4 -o $OUT/${TAG}_stencil_l1 -f $DRV > $OUT/${TAG}_stencil_l1.log 2>&1 ;;
+  stencil)  # level-1 colour passes (launches 102..109 of k_stencil_tile* in the first FMG cycle) and the level-1 residual (110)
+    $NCU --set full --import-source on -k regex:k_stencil_tile -s 102 -c 9 -o $OUT/${TAG}_stencil_l1 -f $DRV > $OUT/${TAG}_stencil_l1.log 2>&1 ;;
 esac; done
 ls -la $OUT

@@ -1,0 +1,137 @@
+"""The reference's Python workflows, written against the reference's own names (pyVoxelFEM / pyOptimizer), run on the
+GPU through voxelfem_b200/compat and are checked against the CPU oracle:
+  * python/CoarseningLevelBenchmark.py:76-100 (single MG-PCG solve with it_callback),
+  * python/3DTopoptDemo.ipynb cells 1,5 (filters + MultigridComplianceObjective + TotalVolumeConstraint + OCOptimizer),
+  * python/LayerByLayerObjective.py:75-124 (getIntermediateFabricationShape + LayerByLayerEvaluator)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import OracleLBL, OracleMG, OracleProblem, OracleSim
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "voxelfem_b200", "compat"))
+
+
+@pytest.fixture(scope="module")
+def vf():
+    import pyVoxelFEM
+    return pyVoxelFEM
+
+
+def rel_l2(a, b): return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("dim,grid,levels", [(2, [64, 32], 2), (3, [32, 16, 16], 2)])
+def test_coarsening_level_benchmark_flow(vf, data_dir, dim, grid, levels):
+    bc = os.path.join(data_dir, "bcs", "3D" if dim == 3 else "", "cantilever_flexion_E.bc")
+    corners = [[0, 0], [2, 1]] if dim == 2 else [[0, 0, 0], [2, 1, 1]]
+    tps = vf.TensorProductSimulator([1] * dim, corners, grid)
+    tps.readMaterial(os.path.join(data_dir, "materials", "B9Creator.material"))
+    tps.applyDisplacementsAndLoadsFromFile(bc)
+    tps.E_min = 1e-5
+    tps.setUniformDensities(0.5)
+    assert list(tps.NbElementsPerDimension) == grid and tps.numNodes() == int(np.prod(np.array(grid) + 1))
+    f = tps.buildLoadVector()
+    mg = tps.multigridSolver(levels)
+    seen = []
+
+    def it_callback(it, u_curr, residual):
+        assert u_curr.shape == f.shape and residual.shape == f.shape
+        seen.append((it, np.linalg.norm(residual), u_curr.copy()))
+    u = mg.preconditionedConjugateGradient(np.zeros_like(f), f, maxIter=100, tol=1e-10, it_callback=it_callback, mgIterations=1,
+                                           mgSmoothingIterations=1, fullMultigrid=True)
+    o = OracleSim(np.array(grid), np.zeros(dim), np.array(corners[1], dtype=float))
+    o.set_isotropic(1.0, 0.3); o.set_interp(0, 1.0, 1e-5, 3.0, 3.0); o.apply_bc_file(bc); o.set_uniform_density(0.5)
+    uo, ito, reso = OracleMG(o, levels).pcg(np.zeros_like(f), f, 100, 1e-10, 1, 1, True)
+    assert abs(len(seen) - ito) <= 1 and [s[0] for s in seen] == list(range(1, len(seen) + 1))
+    assert rel_l2(u, uo) < 1e-6
+    k = min(len(seen), ito)
+    assert np.allclose([s[1] for s in seen][:k], reso[:k], rtol=1e-5)
+    assert rel_l2(seen[-1][2], u) < 1e-14                         # the callback's iterate of the last iteration is the result
+    r = mg.computeResidual(0, u, f)
+    assert np.linalg.norm(r) <= 1e-10 * np.linalg.norm(f) * 1.01
+    assert np.all(mg.zeroOutDirichletComponents(0, np.ones_like(f))[tps.getDirichletMask()] == 0)
+    assert rel_l2(tps.applyK(u), mg.applyK(0, u)) < 1e-13
+
+
+def test_topopt_demo_flow(vf, data_dir):
+    grid, V = [16, 8, 8], 0.3
+    bc = os.path.join(data_dir, "bcs", "3D", "cantilever_flexion_E.bc")
+    tps = vf.TensorProductSimulator([1, 1, 1], [[0, 0, 0], [2, 1, 1]], grid)
+    tps.readMaterial(os.path.join(data_dir, "materials", "B9Creator.material"))
+    tps.applyDisplacementsAndLoadsFromFile(bc)
+    pf = vf.ProjectionFilter(); pf.beta = 1
+    filters = [vf.SmoothingFilter(2, vf.SmoothingFilter.Type.Linear), pf]
+    objective = vf.MultigridComplianceObjective(tps.multigridSolver(2))
+    objective.tol = 1e-9
+    top = vf.TopologyOptimizationProblem(tps, objective, [vf.TotalVolumeConstraint(V)], filters)
+    x0 = pf.invert(V) * np.ones(tps.numElements())
+    top.setVars(x0)
+    oc = vf.OCOptimizer(top)
+
+    o = OracleSim(np.array(grid), np.zeros(3), np.array([2.0, 1.0, 1.0]))
+    o.set_isotropic(1.0, 0.3); o.set_interp(0, 1.0, 1e-4, 3.0, 3.0); o.apply_bc_file(bc); o.set_uniform_density(1.0)
+    op = OracleProblem(OracleMG(o, 2), [("smooth", 2, 1), ("project", 1.0)], V)
+    op.set_solver(100, 1e-9, 1, 2, True, False); op.set_vars(x0)
+    for it in range(3):
+        assert abs(top.evaluateObjective() - op.compliance()) < 1e-8 * abs(op.compliance())
+        assert abs(top.evaluateConstraints()[0] - op.constraint()) < 1e-9      # after an OC step both sit within ctol = 1e-6 of zero
+        g = top.evaluateObjectiveGradient()
+        assert np.abs(g - op.objective_gradient()).max() < 1e-7 * np.abs(g).max()
+        assert top.evaluateConstraintsJacobian().shape == (1, top.numVars())
+        oc.step(); op.oc_step()
+        assert np.abs(top.getVars() - op.design_vars()).max() < 1e-6
+    assert np.abs(top.getDensities() - op.physical_vars()).max() < 1e-6
+    assert np.abs(tps.getDensities() - top.getDensities()).max() == 0           # the simulator carries the physical densities
+    # filterChain view: backprop of a physical-space gradient equals the problem's own chain rule
+    dJ = objective.gradient()
+    assert np.abs(top.filterChain.backprop(dJ) - top.evaluateObjectiveGradient()).max() < 1e-12 * np.abs(dJ).max()
+    assert abs(objective.compliance() - 0.5 * float((objective.f() * objective.u()).sum())) < 1e-12 * abs(objective.compliance())
+
+
+def test_layer_by_layer_flow(vf):
+    ne = [8, 8, 4]
+    rho = np.random.default_rng(3).uniform(0.3, 1.0, int(np.prod(ne)))
+    tps = vf.TensorProductSimulator([1, 1, 1], [[0, 0, 0], [1.0, 1.0, 0.5]], ne)
+    tps.setDensities(rho)
+    lbl_sim = tps.getIntermediateFabricationShape(1, False, vf.InterpolationLaw.RAMP)
+    lbl_sim.q = 3
+    assert np.allclose(lbl_sim.gravity, [0, -1, 0]) and lbl_sim.interpolationLaw == vf.InterpolationLaw.RAMP
+    mask = lbl_sim.getDirichletMask().reshape(9, 9, 5, 3)
+    assert mask[:, 0].all() and not mask[:, 1:].any()                           # build platform clamped, nothing else
+    mg = lbl_sim.multigridSolver(1)
+    ev = vf.LayerByLayerEvaluator(lbl_sim)
+    ev.selectInitMethod("N=3")
+    layers = []
+    ev.run(mg, True, 1, maxIter=50, tol=1e-8, it_callback=None, mgIterations=1, mgSmoothingIterations=1, fullMultigrid=False,
+           lblCallback=lambda layer, c, its: layers.append((layer, c, its)))
+    o = OracleSim(np.array(ne), np.zeros(3), np.array([1.0, 1.0, 0.5]))
+    o.set_isotropic(1.0, 0.0); o.set_interp(1, 1.0, 1e-4, 3.0, 3.0)    # default material ETensor(1, 0)
+    o.add_dirichlet([0, 0, 0], [-1, -1e-9, -1], [100, 1e-9, 100], 7); o.set_gravity(np.array([0, -1.0, 0])); o.set_densities(rho)
+    oe = OracleLBL(OracleMG(o, 1)); oe.select_init_method("N=3")
+    its, comps = oe.run(True, 1, 50, 1e-8, 1, 1, False)
+    assert len(layers) == len(its) == 8
+    assert np.allclose([c for _, c, _ in layers], comps, rtol=1e-6)
+    assert abs(ev.objective() - oe.objective()) < 1e-6 * abs(oe.objective())
+    assert np.abs(ev.gradient() - oe.gradient()).max() < 1e-5 * np.abs(oe.gradient()).max()
+    # downsampling helpers (TensorProductSimulator.hh:1926-1992)
+    coarse = tps.downsample(1)
+    tps.downsampleDensityFieldTo(rho, coarse)
+    assert np.allclose(coarse.getDensities().reshape(4, 4, 2), rho.reshape(4, 2, 4, 2, 2, 2).mean(axis=(1, 3, 5)))
+    gc = np.arange(coarse.numElements(), dtype=float)
+    assert abs(tps.upsampleDensityGradientFrom(coarse, gc).sum() - gc.sum()) < 1e-12 * gc.sum()
+
+
+def test_mma_module(vf):
+    import pyOptimizer
+    from mma_problems import svanberg_toy
+    n, m, lo, hi, f, df, x0, xstar = svanberg_toy()
+    opt = pyOptimizer.MMA(n, m, lo, hi, f, df)
+    opt.setInitialVar(x0)
+    for _ in range(12):
+        opt.step()
+    assert np.abs(opt.getOptimalVar() - xstar).max() < 2e-6

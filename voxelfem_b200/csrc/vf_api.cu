@@ -285,6 +285,7 @@ struct vf_sim {
         for (int a = 0; a < ke; ++a) for (int b = a; b < ke; ++b) { K0[(size_t)a * ke + b] *= vol; K0[(size_t)b * ke + a] = K0[(size_t)a * ke + b]; }
         std::memset(&K0p, 0, sizeof(K0p));
         std::copy(K0.begin(), K0.end(), K0p.v);
+        finalize_k0_param(K0p, N);
         K0dev.alloc(K0.size(), false); K0dev.upload(K0.data(), K0.size(), stream);
         VF_CUDA(cudaStreamSynchronize(stream));
         touch(); ++structVersion;
@@ -391,7 +392,7 @@ struct vf_mg {
     uint64_t stiffnessVersion = 0; // sim->version the coarse operators were built for
     DevBuf<double> Ad, d, scalars, scratch, tmpA, tmpB, tmpC;
     double *hostScalars = nullptr; // pinned
-    std::vector<double> lastResiduals; int lastIters = 0;
+    std::vector<double> lastResiduals; int lastIters = 0; const double *pcgX = nullptr; // device iterate of the running / last PCG
     LaunchCtx ctx;
     vf_group *grp = nullptr; int firstRep = INT_MAX; // slab group this solver is a part of; first replicated (non-windowed) level
     std::vector<vf_mg *> self;
@@ -833,6 +834,7 @@ void mg_pcg(vf_mg &mg, double *x, const double *b, int maxIter, double tol, int 
             vf_pcg_callback cb, void *user) {
     if (mg.grp && mg.grp->parts.size() != 1) throw std::runtime_error("use vf_group_pcg_dev for a multi-part slab group");
     double *xs[1] = {x}; const double *bs[1] = {b};
+    mg.pcgX = x;
     mg_pcg(mg, xs, bs, maxIter, tol, mgIterations, mgSmoothing, fmg, dirichletOK, cb, user);
 }
 
@@ -1382,6 +1384,10 @@ int vf_mg_pcg(vf_mg *mg, double *x, const double *b, int maxIter, double tol, in
     VF_CATCH
 }
 int vf_mg_get_pcg_residual(vf_mg *mg, double *r) { VF_TRY d2h(r, lb(*mg, 0), (size_t)mg->grid(0).numNodes * mg->N, mg->ctx.stream); VF_CATCH }
+int vf_mg_get_pcg_iterate(vf_mg *mg, double *x) {
+    VF_TRY if (!mg->pcgX) throw std::runtime_error("no PCG solve has run on this solver");
+    d2h(x, mg->pcgX, (size_t)mg->grid(0).numNodes * mg->N, mg->ctx.stream); VF_CATCH
+}
 int vf_mg_set_symmetric_gauss_seidel(vf_mg *mg, int s) { mg->symmetricGS = s != 0; return 0; }
 int vf_mg_set_mask_layer(vf_mg *mg, int64_t layer) { if (int rc = vf_sim_set_mask_layer(mg->sim, layer)) return rc; VF_TRY mg_sync_level_masks(*mg); VF_CATCH }
 int vf_mg_decrement_mask(vf_mg *mg, int inc) {

@@ -71,7 +71,17 @@ template<int N> struct Dims {
 
 // Full-density element stiffness matrix, passed by value (__grid_constant__) so that its
 // entries become constant-bank operands of the DFMAs.
-struct K0Param { double v[24 * 24]; };
+struct K0Param {
+    double v[24 * 24];
+    // 3D only: K0 in the symmetry-adapted (Walsh) basis of the voxel's mirror group, filled by finalize_k0_param().
+    // kh[p][c][c'] couples the modes (component c, sign pattern s = p ^ (4 >> c)) of irreducible representation p.
+    double kh[8][3][3];
+    int walsh;      // 1 if K0 is block diagonal in that basis (orthotropic material aligned with the grid)
+    int sparse7;    // 1 if additionally the trilinear mode (s = 7) of a component only couples with itself
+};
+// Passed by value to the Walsh-basis kernels (constant-bank operands).
+struct KhatParam { double v[8][3][3]; };
+void finalize_k0_param(K0Param &K, int N);   // vf_l0.cu
 
 
 // Colour (parity class) description for one pass of the multicoloured smoother
@@ -109,19 +119,25 @@ template<> __device__ __forceinline__ void solve_block<2>(const double (&M)[2][2
 }
 // u_n += M^-1 (b - S') for free nodes; point Gauss-Seidel on the free components of partially
 // constrained nodes, direction following the sweep (MultigridSolver.hh:358-365).
-template<int N>
-__device__ __forceinline__ void gs_node_update(const double (&M)[N][N], const double (&rhs)[N], unsigned dm, bool forward, double (&du)[N]) {
-    if (dm == 0u) { solve_block<N>(M, rhs, du); return; }
-    #pragma unroll
-    for (int c = 0; c < N; ++c) du[c] = 0.0;
+template<int N, bool FWD>
+__device__ __forceinline__ void gs_point_sweep(const double (&M)[N][N], const double (&rhs)[N], unsigned dm, double (&du)[N]) {
     #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const int i = forward ? k : (N - 1 - k);
+        constexpr int dummy = 0; (void)dummy;
+        const int i = FWD ? k : (N - 1 - k);   // compile-time after unrolling: M, rhs, du stay in registers
         double s = rhs[i];
         #pragma unroll
         for (int j = 0; j < N; ++j) s -= M[i][j] * du[j];
         du[i] = s * ((((dm >> i) & 1u) ? 0.0 : 1.0) / M[i][i]);
     }
+}
+template<int N>
+__device__ __forceinline__ void gs_node_update(const double (&M)[N][N], const double (&rhs)[N], unsigned dm, bool forward, double (&du)[N]) {
+    if (dm == 0u) { solve_block<N>(M, rhs, du); return; }
+    #pragma unroll
+    for (int c = 0; c < N; ++c) du[c] = 0.0;
+    if (forward) gs_point_sweep<N, true>(M, rhs, dm, du);
+    else         gs_point_sweep<N, false>(M, rhs, dm, du);
 }
 #endif
 

@@ -13,6 +13,9 @@
 #include "vf_internal.cuh"
 #include "vf_reduce.cuh"
 #include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
 
 namespace vf {
 
@@ -260,6 +263,254 @@ k_apply3_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param 
     if (DOT) grid_sum(dotv, scratch, dotOut);
 }
 
+// ---------------------------------------------------------------------------
+// 3D apply in the symmetry-adapted basis ("Walsh" kernel).
+//
+// The dense formulation above spends 576 DFMA per node and is FP64-pipe bound at 4x the HBM floor.  A voxel has three
+// mirror planes, and for a material whose symmetry planes are those of the grid (isotropic, orthotropic) K0 commutes
+// with the mirror group Z2^3 acting on node positions and displacement components.  In the basis of the 2x2x2 Walsh
+// functions w_s(m) = (-1)^(s.m), K0 therefore splits into 8 blocks of 3x3 -- one per irreducible representation p,
+// coupling the modes (component c, s = p ^ e_c) -- of which the 3 rigid translations vanish: 45..57 multiplies per
+// ELEMENT instead of 576.  finalize_k0_param() verifies the block structure numerically; other materials keep the
+// dense kernel.
+//
+// Mapping: one thread per element column (y, z), lanes along z, marching along x.  Per step (one element):
+//   * load the 4 nodes of the next node plane, 2D Walsh transform (shared by the elements on either side of the plane)
+//   * x butterfly -> 24 mode amplitudes, 8 blocks -> 24 mode forces
+//   * inverse x butterfly fused with the modulus scaling and with the carry from the previous element of the column
+//   * inverse 2D transform -> contributions to the 4 nodes of the finished node plane
+//   * the thread owns node (y, z): contributions of the columns (y, z-1), (y-1, z), (y-1, z-1) arrive by warp shuffle
+//     (z) and through shared memory (y); lane 0 and warp 0 of a block are halo columns.
+// About 175 FP64 instructions per element including the node accumulation.  The loads of step ex + 1 are issued before
+// the arithmetic of step ex (software pipeline) and two blocks are resident per SM (128 registers): measured at 256^3
+// 0.45 ms (SET) / 0.58 ms (RESIDUAL) against 1.10 / 1.15 ms for the dense kernel; without the prefetch 0.56 ms, with one
+// resident block 0.68 ms, with the carry in shared memory 0.50 ms (profiles/r01o_time_ab.log).
+// ---------------------------------------------------------------------------
+constexpr int kWalshBY = 8;      // warps (element rows) per block, one of them halo
+constexpr int kWalshXC = 32;     // node planes per block along x (one extra element step to prime the carry)
+
+__device__ __forceinline__ void wht2(const double (&r)[2][2], double (&P)[2][2]) {
+    const double t0 = r[0][0] + r[0][1], t1 = r[0][0] - r[0][1], t2 = r[1][0] + r[1][1], t3 = r[1][0] - r[1][1];
+    P[0][0] = t0 + t2; P[0][1] = t1 + t3; P[1][0] = t0 - t2; P[1][1] = t1 - t3;
+}
+
+template<int MODE, bool DOT, bool S7>
+__global__ void __launch_bounds__(32 * kWalshBY, 2)
+k_apply3w_l0(const __grid_constant__ GridDesc g, const __grid_constant__ KhatParam Kh, const double *__restrict__ u,
+             const double *__restrict__ E, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
+             double *__restrict__ out, double *dotOut, double *scratch) {
+    __shared__ double s_up[2][kWalshBY][3][32];
+    const int lane = threadIdx.x, wy = threadIdx.y;
+    const int cz = blockIdx.x * 31 + lane - 1;                 // element column / owned node coordinates (halo: lane 0, warp 0)
+    const int cy = blockIdx.y * (kWalshBY - 1) + wy - 1;
+    const int xs = blockIdx.z * kWalshXC, xe = min(xs + kWalshXC, g.nn[0]);
+    const int nx = g.nn[0], ny = g.nn[1], nz = g.nn[2];
+    const long long NN = g.numNodes;
+    const bool colValid = cz >= 0 && cz < g.ne[2] && cy >= 0 && cy < g.ne[1];
+    const bool owner = lane >= 1 && wy >= 1 && cz < nz && cy < ny;
+    // clamped in-plane node offsets of the column's 4 nodes
+    long long no[2][2];
+    #pragma unroll
+    for (int m1 = 0; m1 < 2; ++m1) {
+        #pragma unroll
+        for (int m2 = 0; m2 < 2; ++m2)
+            no[m1][m2] = (long long)min(max(cy + m1, 0), ny - 1) * g.ns[1] + min(max(cz + m2, 0), nz - 1);
+    }
+    const long long eo = (long long)min(max(cy, 0), g.ne[1] - 1) * g.es[1] + min(max(cz, 0), g.ne[2] - 1);
+    double Pp[3][2][2], carry[3][2][2], uown[3];
+    {
+        const long long xo = (long long)min(max(xs - 1, 0), nx - 1) * g.ns[0];
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double r[2][2];
+            #pragma unroll
+            for (int m1 = 0; m1 < 2; ++m1) {
+                #pragma unroll
+                for (int m2 = 0; m2 < 2; ++m2) r[m1][m2] = u[c * NN + xo + no[m1][m2]];
+            }
+            wht2(r, Pp[c]);
+            uown[c] = r[0][0];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) carry[c][i >> 1][i & 1] = 0.0;
+        }
+    }
+    // software pipeline: the node plane and modulus of step ex + 1 are requested before the arithmetic of step ex
+    double rawN[3][2][2], EeN;
+    {
+        const long long xo = (long long)min(xs, nx - 1) * g.ns[0];
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            #pragma unroll
+            for (int m1 = 0; m1 < 2; ++m1) {
+                #pragma unroll
+                for (int m2 = 0; m2 < 2; ++m2) rawN[c][m1][m2] = u[c * NN + xo + no[m1][m2]];
+            }
+        }
+        const bool ev = colValid && xs - 1 >= 0 && xs - 1 < g.ne[0];
+        EeN = ev ? __ldg(E + ((long long)max(xs - 1, 0) * g.es[0] + eo)) : 0.0;
+    }
+    double dotv = 0.0;
+    for (int ex = xs - 1; ex < xe; ++ex) {
+        double raw[3][2][2];
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) raw[c][i >> 1][i & 1] = rawN[c][i >> 1][i & 1];
+        }
+        const double Ee = EeN;
+        if (ex + 1 < xe) {   // next node plane (clamped: beyond the grid the element is void and its modulus zero)
+            const long long xo = (long long)min(ex + 2, nx - 1) * g.ns[0];
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                #pragma unroll
+                for (int m1 = 0; m1 < 2; ++m1) {
+                    #pragma unroll
+                    for (int m2 = 0; m2 < 2; ++m2) rawN[c][m1][m2] = u[c * NN + xo + no[m1][m2]];
+                }
+            }
+            const bool evn = colValid && ex + 1 < g.ne[0];
+            EeN = evn ? __ldg(E + ((long long)(ex + 1) * g.es[0] + eo)) : 0.0;
+        }
+        // mode amplitudes uh[c][s], s = (s0 << 2) | (s1 << 1) | s2
+        double uh[3][8];
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double Pn[2][2];
+            wht2(raw[c], Pn);
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double a = Pp[c][i >> 1][i & 1], bb = Pn[i >> 1][i & 1];
+                uh[c][i] = a + bb; uh[c][4 + i] = a - bb;
+                Pp[c][i >> 1][i & 1] = bb;
+            }
+        }
+        // mode forces wh[c][s]: 8 blocks of 3x3, rigid translations (s = 0) vanish
+        double wh[3][8];
+        #pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int sc = p ^ (4 >> c);
+                double acc = 0.0;
+                if (sc != 0) {
+                    #pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const int sd = p ^ (4 >> d);
+                        if (sd == 0) continue;
+                        if (S7 && c != d && (sc == 7 || sd == 7)) continue;
+                        acc = fma(Kh.v[p][c][d], uh[d][sd], acc);
+                    }
+                }
+                wh[c][sc] = acc;
+            }
+        }
+        // inverse x butterfly + modulus + carry: plane ex is complete, the m0 = 1 half is carried to plane ex + 1
+        double gq[3][2][2];
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double Q[2][2];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double a = wh[c][i] + wh[c][4 + i], bb = wh[c][i] - wh[c][4 + i];
+                Q[i >> 1][i & 1] = fma(Ee, a, carry[c][i >> 1][i & 1]);
+                carry[c][i >> 1][i & 1] = Ee * bb;
+            }
+            wht2(Q, gq[c]);   // gq[c][m1][m2]: contribution of this column to node (ex, cy + m1, cz + m2)
+        }
+        if (ex >= xs) {
+            const int buf = ex & 1;
+            double acc[3];
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                acc[c] = gq[c][0][0] + __shfl_up_sync(0xffffffffu, gq[c][0][1], 1);
+                s_up[buf][wy][c][lane] = gq[c][1][0] + __shfl_up_sync(0xffffffffu, gq[c][1][1], 1);
+            }
+            __syncthreads();
+            if (owner) {
+                const long long n = (long long)ex * g.ns[0] + (long long)cy * g.ns[1] + cz;
+                if (cy >= g.nActive) { // detached layer: applyK<ZeroInit = true> zero-fills it (TPSStencils.hh:717-727)
+                    if (MODE == APPLY_SET) {
+                        #pragma unroll
+                        for (int c = 0; c < 3; ++c) out[c * NN + n] = 0.0;
+                    }
+                } else {
+                    const unsigned dm = dmask ? dmask[n] : 0u;
+                    #pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const double a = acc[c] + s_up[buf][wy - 1][c][lane];
+                        double res;
+                        if (MODE == APPLY_SET) res = a;
+                        else if (MODE == APPLY_ADD) res = out[c * NN + n] + a;
+                        else if (MODE == APPLY_SUB) res = out[c * NN + n] - a;
+                        else res = b[c * NN + n] - a;
+                        if ((dm >> c) & 1u) res = 0.0;
+                        out[c * NN + n] = res;
+                        if (DOT && ex >= g.ownLo && ex < g.ownHi) dotv = fma(uown[c], res, dotv);
+                    }
+                }
+            }
+        }
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) uown[c] = raw[c][0][0];
+    }
+    if (DOT) grid_sum(dotv, scratch, dotOut);
+}
+
+// K0 in the Walsh basis: Khat = T K0 T^T / 64 with T = H (x) I3, H[s][m] = (-1)^popcount(s & m) over the local node index
+// m = (m0 << 2) | (m1 << 1) | m2 (TensorProductSimulator.hh:1532-1651 node ordering, axis 0 slowest).
+void finalize_k0_param(K0Param &K, int N) {
+    K.walsh = 0; K.sparse7 = 0;
+    std::memset(K.kh, 0, sizeof(K.kh));
+    if (N != 3) return;
+    static double Kt[24][24], Kh[24][24];
+    auto sgn = [](int s, int m) { return (__builtin_popcount(s & m) & 1) ? -1.0 : 1.0; };
+    for (int s = 0; s < 8; ++s) for (int c = 0; c < 3; ++c) for (int j = 0; j < 24; ++j) {
+        double a = 0; for (int m = 0; m < 8; ++m) a += sgn(s, m) * K.v[(3 * m + c) * 24 + j];
+        Kt[3 * s + c][j] = a;
+    }
+    double kmax = 0;
+    for (int i = 0; i < 24; ++i) for (int s = 0; s < 8; ++s) for (int c = 0; c < 3; ++c) {
+        double a = 0; for (int m = 0; m < 8; ++m) a += sgn(s, m) * Kt[i][3 * m + c];
+        Kh[i][3 * s + c] = a / 64.0; kmax = std::max(kmax, std::fabs(a / 64.0));
+    }
+    bool blockDiag = true, s7 = true;
+    const double tol = 1e-13 * kmax;
+    for (int s1 = 0; s1 < 8; ++s1) for (int c1 = 0; c1 < 3; ++c1) for (int s2 = 0; s2 < 8; ++s2) for (int c2 = 0; c2 < 3; ++c2) {
+        const double v = Kh[3 * s1 + c1][3 * s2 + c2];
+        const bool same = (s1 ^ (4 >> c1)) == (s2 ^ (4 >> c2));
+        if (!same || s1 == 0 || s2 == 0) { if (std::fabs(v) > tol) blockDiag = false; continue; }
+        K.kh[s1 ^ (4 >> c1)][c1][c2] = v;
+        if (c1 != c2 && (s1 == 7 || s2 == 7) && std::fabs(v) > tol) s7 = false;
+    }
+    const char *env = std::getenv("VF_L0_DENSE");
+    K.walsh = blockDiag && !(env && env[0] == '1');
+    K.sparse7 = s7;
+}
+
+template<bool DOT>
+static void apply3w_launch(const LaunchCtx &ctx, dim3 grid, dim3 block, const GridDesc &g, const K0Param &K, const double *u, const double *E,
+                           const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
+    KhatParam Kh; std::memcpy(Kh.v, K.kh, sizeof(Kh.v));
+#define VF_W_CASE(M) \
+    if (mode == M) { \
+        if (K.sparse7) k_apply3w_l0<M, DOT, true><<<grid, block, 0, ctx.stream>>>(g, Kh, u, E, b, dmask, out, dotOut, scratch); \
+        else           k_apply3w_l0<M, DOT, false><<<grid, block, 0, ctx.stream>>>(g, Kh, u, E, b, dmask, out, dotOut, scratch); \
+    }
+    VF_W_CASE(APPLY_SET) VF_W_CASE(APPLY_ADD) VF_W_CASE(APPLY_SUB) VF_W_CASE(APPLY_RESIDUAL)
+#undef VF_W_CASE
+}
+
+static void apply3w_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
+                                const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
+    dim3 block(32, kWalshBY, 1);
+    dim3 grid((g.nn[2] + 30) / 31, (g.nn[1] + kWalshBY - 2) / (kWalshBY - 1), (g.nn[0] + kWalshXC - 1) / kWalshXC);
+    const bool fused = dotOut && (size_t)grid.x * grid.y * grid.z <= (size_t)kReduceMaxBlocks;
+    if (fused) apply3w_launch<true>(ctx, grid, block, g, K, u, E, b, dmask, out, mode, dotOut, scratch);
+    else       apply3w_launch<false>(ctx, grid, block, g, K, u, E, b, dmask, out, mode, nullptr, nullptr);
+    VF_KERNEL_CHECK();
+    if (dotOut && !fused) launch_masked_dot(ctx, g, u, out, dotOut, scratch);
+}
+
 static void apply3_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
                                const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
     dim3 block(32, 4, 1);
@@ -297,7 +548,8 @@ static void apply_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0P
 void launch_apply_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, const double *u, const double *E,
                      const double *b, const uint8_t *dmask, double *out, int mode, double *dotOut, double *scratch) {
     ProfScope ps(ctx, mode == APPLY_RESIDUAL ? PC_RESIDUAL_L0 : PC_APPLY_L0, (double)g.numNodes);
-    if (g.N == 3) apply3_l0_dispatch(ctx, g, K, u, E, b, dmask, out, mode, dotOut, scratch);
+    if (g.N == 3 && K.walsh) apply3w_l0_dispatch(ctx, g, K, u, E, b, dmask, out, mode, dotOut, scratch);
+    else if (g.N == 3) apply3_l0_dispatch(ctx, g, K, u, E, b, dmask, out, mode, dotOut, scratch);
     else          apply_l0_dispatch<2>(ctx, g, K, u, E, b, dmask, out, mode, dotOut, scratch);
 }
 

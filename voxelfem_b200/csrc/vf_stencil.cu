@@ -15,6 +15,8 @@
 // Phi^T Ke Phi), differing only in floating-point summation order.
 #include "vf_internal.cuh"
 #include "vf_reduce.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace vf {
 
