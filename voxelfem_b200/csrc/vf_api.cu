@@ -134,32 +134,71 @@ static void set_mask_limits(GridDesc &g, int firstMasked, int firstDetached) {
 // so the coarse solve on the V-cycle's critical path is two small kernels with no dependent-block latency chain.
 // ---------------------------------------------------------------------------
 struct DenseSolver {
-    cusolverDnHandle_t handle = nullptr;
-    DevBuf<double> A, work, rhs, y; DevBuf<int> info, red, freeDofs; std::vector<char> hostWork;
+    cusolverDnHandle_t handle = nullptr; cublasHandle_t blas = nullptr;
+    DevBuf<double> A, W, Lip, Tbuf, work, rhs, y; DevBuf<int> info, red, freeDofs; std::vector<char> hostWork;
     int nfree = 0; bool ok = false;
-    ~DenseSolver() { if (handle) cusolverDnDestroy(handle); }
+    ~DenseSolver() { if (handle) cusolverDnDestroy(handle); if (blas) cublasDestroy(blas); }
     void init_handle(cudaStream_t s) {
         if (!handle) {
             if (cusolverDnCreate(&handle) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("cusolverDnCreate failed");
         }
         cusolverDnSetStream(handle, s);
+        if (!blas) {
+            if (cublasCreate(&blas) != CUBLAS_STATUS_SUCCESS) throw std::runtime_error("cublasCreate failed");
+        }
+        cublasSetStream(blas, s);
     }
     // fixed: per-DOF flags in (node*N + c) order
     void factor(const LaunchCtx &ctx, const GridDesc &g, const double *S, const std::vector<uint8_t> &fixed) {
         init_handle(ctx.stream);
         const long long ndof = g.numNodes * g.N;
-        std::vector<int> redH(ndof, -1), freeH;
-        for (long long i = 0; i < ndof; ++i) if (!fixed[i]) { redH[i] = (int)freeH.size(); freeH.push_back((int)i); }
+        // Free DOFs are numbered plane by plane along the longest grid axis: nodes of non-adjacent planes do not couple, so the
+        // matrix of the free DOFs is block tridiagonal with one block per node plane (blockOff).
+        int ax = 3 - g.N;
+        for (int a = 3 - g.N; a < 3; ++a) if (g.nn[a] > g.nn[ax]) ax = a;
+        std::vector<int> redH(ndof, -1), freeH, blockOff(1, 0);
+        for (int p = 0; p < g.nn[ax]; ++p) {
+            for (long long n = 0; n < g.numNodes; ++n) {
+                const int c = (int)((n / g.ns[ax]) % g.nn[ax]);
+                if (c != p) continue;
+                for (int k = 0; k < g.N; ++k) { const long long i = n * g.N + k; if (!fixed[i]) { redH[i] = (int)freeH.size(); freeH.push_back((int)i); } }
+            }
+            blockOff.push_back((int)freeH.size());
+        }
         nfree = (int)freeH.size();
         red.alloc(ndof, false); red.upload(redH.data(), ndof, ctx.stream);
         freeDofs.alloc(std::max(nfree, 1), false); if (nfree) freeDofs.upload(freeH.data(), nfree, ctx.stream);
         VF_CUDA(cudaStreamSynchronize(ctx.stream)); // redH / freeH are stack-owned
         if (nfree == 0) { ok = true; return; }
-        if (A.n != (size_t)nfree * nfree) A.alloc((size_t)nfree * nfree, false);
+        if (A.n != (size_t)nfree * nfree) A.alloc((size_t)nfree * nfree, false);   // A.p stays put: captured CUDA graphs hold it
         VF_CUDA(cudaMemsetAsync(A.p, 0, sizeof(double) * A.n, ctx.stream));
-        rhs.alloc(nfree, true); y.alloc(nfree, true); info.alloc(1, true);
-        launch_stencil_to_dense(ctx, g, S, red.p, nfree, A.p);
+        rhs.alloc(nfree, true); y.alloc(nfree, true);
+        int maxBlock = 0, nBlocks = 0;
+        for (size_t b = 0; b + 1 < blockOff.size(); ++b) { const int m = blockOff[b + 1] - blockOff[b]; maxBlock = std::max(maxBlock, m); nBlocks += m > 0; }
+        static const bool noBlockTri = [] { const char *e = std::getenv("VF_COARSE_DENSE"); return e && e[0] == '1'; }();
+        if (!noBlockTri && nBlocks >= 3 && maxBlock >= 96) {
+            if (W.n != (size_t)nfree * nfree) W.alloc((size_t)nfree * nfree, false);
+            VF_CUDA(cudaMemsetAsync(W.p, 0, sizeof(double) * W.n, ctx.stream));
+            launch_stencil_to_dense(ctx, g, S, red.p, nfree, W.p);
+            factor_block_tridiagonal(ctx, blockOff, maxBlock);
+        } else {
+            launch_stencil_to_dense(ctx, g, S, red.p, nfree, A.p);
+            factor_dense(ctx);
+        }
+        // cuSOLVER / cuBLAS (column-major, lower) hold L^-1(r, c), r >= c, at A[c * n + r]: in our row-major reading that is row c,
+        // column r -- the upper triangle, i.e. L^-T.  Mirror it so that the lower triangle holds L^-1 row by row.
+        launch_symmetrize_upper_to_lower(ctx);
+        ok = true;
+    }
+    void check_info(const LaunchCtx &ctx, int count) {
+        std::vector<int> h(count, 0); info.download(h.data(), count, ctx.stream);
+        for (int i = 0; i < count; ++i)
+            if (h[i] != 0) throw std::runtime_error("Cholesky factorization failed: coarse stiffness matrix is not positive definite (info = " + std::to_string(h[i]) + ")");
+    }
+    // Dense path: potrf + trtri on the whole matrix (small or unstructured coarse grids).
+    void factor_dense(const LaunchCtx &ctx) {
         int lwork1 = 0; size_t wdev = 0, whost = 0;
+        info.alloc(1, true);
         // Row-major symmetric == column-major symmetric; factor the "lower" triangle in cuSOLVER's column-major view.
         if (cusolverDnDpotrf_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, &lwork1) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf_bufferSize failed");
         if (cusolverDnXtrtri_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, nfree, CUDA_R_64F, A.p, nfree, &wdev, &whost) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("trtri_bufferSize failed");
@@ -168,15 +207,55 @@ struct DenseSolver {
         if (whost > hostWork.size()) hostWork.resize(whost);
         count_launch();
         if (cusolverDnDpotrf(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, work.p, lwork1, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf failed");
-        int hinfo = 0; info.download(&hinfo, 1, ctx.stream);
-        if (hinfo != 0) throw std::runtime_error("Cholesky factorization failed: coarse stiffness matrix is not positive definite (info = " + std::to_string(hinfo) + ")");
+        check_info(ctx, 1);
         count_launch();
         if (cusolverDnXtrtri(handle, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, nfree, CUDA_R_64F, A.p, nfree, work.p, wdev, hostWork.data(), whost, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("trtri failed");
-        // cuSOLVER (column-major, lower) holds L^-1(r, c), r >= c, at A[c * n + r]: in our row-major reading that is row c,
-        // column r -- the upper triangle, i.e. L^-T.  Mirror it so that the lower triangle holds L^-1 row by row.
-        launch_symmetrize_upper_to_lower(ctx);
-        ok = true;
     }
+    // Block-tridiagonal path (stands in for CHOLMOD's sparse factorization, TensorProductSimulator.hh:1198-1230): block Cholesky
+    //   L_ii L_ii^T = A_ii - L_ip L_ip^T,  L_ip = A_ip L_pp^-T   (p = i - 1)
+    // followed by the block forward substitution L X = I, X_ii = L_ii^-1, X_i,: = -L_ii^-1 L_ip X_p,: , which leaves the dense
+    // lower-triangular L^-1 that solve() applies as two bandwidth-bound triangular mat-vecs.  n bw^2 + n^2 bw flops in
+    // GEMM-shaped calls instead of the 2/3 n^3 of a dense potrf + trtri.  All in cuBLAS column-major terms on the symmetric A.
+    void factor_block_tridiagonal(const LaunchCtx &ctx, const std::vector<int> &off, int maxBlock) {
+        const int n = nfree, nb = (int)off.size() - 1;   // W: the matrix, overwritten by its block factor; A: receives L^-1
+        info.alloc(nb, true);
+        int lwork = 0;
+        if (cusolverDnDpotrf_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, maxBlock, W.p, n, &lwork) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf_bufferSize failed");
+        if ((size_t)lwork > work.n) work.alloc(lwork, false);
+        auto M = [&](int i, int j) { return W.p + (size_t)off[j] * n + off[i]; };   // block (i, j), leading dimension n
+        auto X = [&](int i, int j) { return A.p + (size_t)off[j] * n + off[i]; };
+        const double one = 1.0, mone = -1.0, zero = 0.0;
+        auto chk = [](cublasStatus_t st, const char *what) { if (st != CUBLAS_STATUS_SUCCESS) throw std::runtime_error(std::string("cuBLAS ") + what + " failed"); };
+        // Triangular solves against wide right-hand sides are replaced by products with the explicit L_ii^-1 (GEMM-shaped).
+        if (Lip.n < (size_t)maxBlock * maxBlock) Lip.alloc((size_t)maxBlock * maxBlock, false);
+        if (Tbuf.n < (size_t)maxBlock * n) Tbuf.alloc((size_t)maxBlock * n, false);
+        int prev = -1;
+        for (int i = 0; i < nb; ++i) {
+            const int m = off[i + 1] - off[i];
+            if (m == 0) continue;
+            const bool coupled = prev == i - 1 && prev >= 0;
+            const int mp = coupled ? off[prev + 1] - off[prev] : 0;
+            if (coupled) {   // L_ip = A_ip L_pp^-T = A_ip X_pp^T;  A_ii -= L_ip L_ip^T
+                count_launch();
+                chk(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, m, mp, mp, &one, M(i, prev), n, X(prev, prev), n, &zero, Lip.p, m), "gemm");
+                chk(cublasDsyrk(blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, m, mp, &mone, Lip.p, m, &one, M(i, i), n), "syrk");
+            }
+            count_launch();
+            if (cusolverDnDpotrf(handle, CUBLAS_FILL_MODE_LOWER, m, M(i, i), n, work.p, lwork, info.p + i) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf failed");
+            // X_ii = L_ii^-1 (solve against the identity), then the block row left of the diagonal: X_i,: = -X_ii (L_ip X_p,:)
+            launch_set_identity(ctx, X(i, i), m, n);
+            chk(cublasDtrsm(blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, m, m, &one, M(i, i), n, X(i, i), n), "trsm");
+            if (coupled && off[i] > 0) {
+                const int w = off[i];   // all columns left of block i
+                count_launch();
+                chk(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, m, w, mp, &one, Lip.p, m, X(prev, 0), n, &zero, Tbuf.p, m), "gemm");
+                chk(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, m, w, m, &mone, X(i, i), n, Tbuf.p, m, &zero, X(i, 0), n), "gemm");
+            }
+            prev = i;
+        }
+        check_info(ctx, nb);
+    }
+    void launch_set_identity(const LaunchCtx &ctx, double *B, int m, int ld);
     void launch_symmetrize_upper_to_lower(const LaunchCtx &ctx);
     // x = A^-1 f on free DOFs, zero on fixed DOFs (TensorProductSimulator.hh:1227-1229, 1243-1252)
     void solve(const LaunchCtx &ctx, const GridDesc &g, const double *f, double *x) {
@@ -196,7 +275,16 @@ __global__ void k_sym_upper_to_lower(double *A, int n) { // row-major: copy A[i]
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i < n && j < n && j > i) A[(size_t)j * n + i] = A[(size_t)i * n + j];
 }
+__global__ void k_set_identity(double *B, int m, int ld) { // column-major block, leading dimension ld
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i < m && j < m) B[(size_t)j * ld + i] = i == j ? 1.0 : 0.0;
+}
 namespace vf {
+void DenseSolver::launch_set_identity(const LaunchCtx &ctx, double *B, int m, int ld) {
+    dim3 block(32, 8), grid((m + 31) / 32, (m + 7) / 8);
+    k_set_identity<<<grid, block, 0, ctx.stream>>>(B, m, ld);
+    VF_KERNEL_CHECK();
+}
 void DenseSolver::launch_symmetrize_upper_to_lower(const LaunchCtx &ctx) {
     // cuSOLVER (column-major, FILL_MODE_LOWER) holds element (r, c), r >= c, at A[c * n + r]; in our row-major reading
     // that is row c, column r >= c: the upper triangle.  Mirror it into the lower triangle.
@@ -390,6 +478,9 @@ struct vf_mg {
     bool symmetricGS = true;
     DenseSolver coarse;
     uint64_t stiffnessVersion = 0; // sim->version the coarse operators were built for
+    // Pending banded update: since the hierarchy was last built, only the moduli of fine element layers [bandLo, bandHi) along
+    // the build direction changed (mask decrements), and sim->version == bandVersion (MultigridSolver.hh:907-1017).
+    bool bandActive = false; int bandLo = 0, bandHi = 0; uint64_t bandVersion = 0;
     DevBuf<double> Ad, d, scalars, scratch, tmpA, tmpB, tmpC;
     double *hostScalars = nullptr; // pinned
     std::vector<double> lastResiduals; int lastIters = 0; const double *pcgX = nullptr; // device iterate of the running / last PCG
@@ -598,12 +689,21 @@ void mg_update_stiffness(vf_mg &lead, bool force = false) {
     if (!stale) return;
     const int nl = lead.numLevels();
     const int T = lead.grp ? lead.firstRep : 0;   // levels 1..T are sub-assembled per part, then completed
+    // A pending banded update recomputes only the coarse rows whose support meets the changed fine element layers: the range
+    // of affected node layers halves (and widens by one node on either side) from level to level.
+    const bool banded = !force && !lead.grp && lead.bandActive && lead.bandVersion == lead.sim->version;
+    std::vector<int> bLo(nl, 0), bHi(nl, 0x7fffffff);
+    if (banded) {
+        int lo = lead.bandLo, hi = lead.bandHi;             // fine node layers lo .. hi touch the changed elements [lo, hi)
+        for (int l = 1; l < nl; ++l) { lo = std::max(lo / 2 - 1, 0); hi = (hi + 1) / 2 + 1; bLo[l] = lo; bHi[l] = hi; }
+    }
+    lead.bandActive = false;
     auto coarsen = [&](vf_mg &mg, int l) {
         MGLevel &L = *mg.lv[l];
         const size_t len = (size_t)L.g.numPos * (mg.N == 3 ? 27 : 9) * mg.N * mg.N;
         if (L.S.n != len) L.S.alloc(len, true);
-        if (l == 1) launch_coarsen_from_moduli(mg.ctx, L.g, mg.sim->g, mg.sim->E.p, mg.cK0dev.p, L.S.p);
-        else        launch_coarsen_stencil(mg.ctx, L.g, mg.lv[l - 1]->g, mg.lv[l - 1]->S.p, L.S.p);
+        if (l == 1) launch_coarsen_from_moduli(mg.ctx, L.g, mg.sim->g, mg.sim->E.p, mg.cK0dev.p, L.S.p, bLo[l], bHi[l]);
+        else        launch_coarsen_stencil(mg.ctx, L.g, mg.lv[l - 1]->g, mg.lv[l - 1]->S.p, L.S.p, bLo[l], bHi[l]);
     };
     for (int l = 1; l < nl && l <= T; ++l) for (vf_mg *m : P) coarsen(*m, l);
     if (lead.grp) {
@@ -1395,11 +1495,18 @@ int vf_mg_decrement_mask(vf_mg *mg, int inc) {
     vf_sim &s = *mg->sim;
     if ((int64_t)s.firstMasked > s.ne[1]) throw std::runtime_error("Mask must already be applied");
     if (s.firstMasked < inc) throw std::runtime_error("Mask decrement of bounds");
+    const bool pendingBand = mg->bandActive && mg->bandVersion == s.version;
+    const bool upToDate = mg->stiffnessVersion == s.version || pendingBand;
     s.maskHeight -= inc * s.spacing[1];
     s.firstMasked -= inc; s.firstDetached = s.firstMasked + 1;
     s.refreshGridMask();
     launch_zero_moduli_layers(s.ctx, s.g, s.E.p, s.firstMasked, s.firstMasked + inc);
     s.touch(); mg_sync_level_masks(*mg);
+    if (upToDate && !mg->grp && mg->numLevels() > 1 && mg->lv[1]->S.n) {   // only these element layers changed since the hierarchy was built
+        mg->bandLo = pendingBand ? std::min(mg->bandLo, s.firstMasked) : s.firstMasked;
+        mg->bandHi = pendingBand ? std::max(mg->bandHi, s.firstMasked + inc) : s.firstMasked + inc;
+        mg->bandActive = true; mg->bandVersion = s.version;
+    } else mg->bandActive = false;
     VF_CATCH
 }
 int vf_mg_debug_get(vf_mg *mg, int which, int l, double *out) {

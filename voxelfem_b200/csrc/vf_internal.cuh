@@ -198,8 +198,10 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
                        const uint8_t *dmask, int color, bool forward);
 // Galerkin coarsening (MultigridSolver.hh:711-819): level-1 stencil from the fine Young's moduli and the 2^N
 // coarsened full-density matrices cK0[fi] (device, [fi][KE][KE]); level l >= 2 stencil as P^T A_{l-1} P.
-void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc);
-void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc);
+// bandLo..bandHi (inclusive, coarse node layers along the build direction): only those rows are recomputed -- the banded update of
+// updateStiffnessMatrices after a change of the fabrication mask (MultigridSolver.hh:907-1017); default: every row.
+void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc, int bandLo = 0, int bandHi = 0x7fffffff);
+void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc, int bandLo = 0, int bandHi = 0x7fffffff);
 // Level-0 stencil straight from moduli (used for single-level direct solves): S = sum_e E_e K0 blocks.
 void launch_stencil_from_moduli_l0(const LaunchCtx &ctx, const GridDesc &g, const double *E, const double *K0dev, double *S);
 // Dense matrix of the free DOFs from a stencil: A[red(i)][red(j)], row-major n x n; redIdx[dof] = -1 for fixed DOFs.

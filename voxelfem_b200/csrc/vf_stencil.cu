@@ -224,12 +224,13 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
 template<int N>
 __global__ void __launch_bounds__(128)
 k_coarsen_from_moduli(const __grid_constant__ GridDesc gc, const __grid_constant__ GridDesc gf,
-                      const double *__restrict__ E, const double *__restrict__ cK0, double *__restrict__ Sc) {
+                      const double *__restrict__ E, const double *__restrict__ cK0, double *__restrict__ Sc, int bandLo, int bandHi) {
     constexpr int NPE = Dims<N>::NPE, KE = Dims<N>::KE, A0 = Dims<N>::A0, NN = N * N;
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y;
     if (n >= gc.numNodes) return;
     int c[3]; { long long r = n; c[2] = (int)(r % gc.nn[2]); r /= gc.nn[2]; c[1] = (int)(r % gc.nn[1]); c[0] = (int)(r / gc.nn[1]); }
+    { const int cb = (gc.bd == 1) ? c[1] : c[2]; if (cb < bandLo || cb > bandHi) return; }   // banded update: rows outside keep their values
     int d[3] = {0, 0, 0};
     { int r = s; for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
     double acc[NN];
@@ -272,11 +273,11 @@ k_coarsen_from_moduli(const __grid_constant__ GridDesc gc, const __grid_constant
     for (int i = 0; i < NN; ++i) Sc[stencil_addr(p, s * NN + i, Dims<N>::NE)] = acc[i];
 }
 
-void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc) {
+void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc, int bandLo, int bandHi) {
     ProfScope ps(ctx, PC_COARSEN, (double)gc.numNodes);
     dim3 block(128), grid((unsigned)((gc.numNodes + 127) / 128), gc.N == 3 ? 27 : 9);
-    if (gc.N == 3) k_coarsen_from_moduli<3><<<grid, block, 0, ctx.stream>>>(gc, gf, E, cK0, Sc);
-    else           k_coarsen_from_moduli<2><<<grid, block, 0, ctx.stream>>>(gc, gf, E, cK0, Sc);
+    if (gc.N == 3) k_coarsen_from_moduli<3><<<grid, block, 0, ctx.stream>>>(gc, gf, E, cK0, Sc, bandLo, bandHi);
+    else           k_coarsen_from_moduli<2><<<grid, block, 0, ctx.stream>>>(gc, gf, E, cK0, Sc, bandLo, bandHi);
     VF_KERNEL_CHECK();
 }
 
@@ -285,12 +286,13 @@ void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const 
 template<int N>
 __global__ void __launch_bounds__(128)
 k_coarsen_stencil(const __grid_constant__ GridDesc gc, const __grid_constant__ GridDesc gf,
-                  const double *__restrict__ Sf, double *__restrict__ Sc) {
+                  const double *__restrict__ Sf, double *__restrict__ Sc, int bandLo, int bandHi) {
     constexpr int A0 = Dims<N>::A0, NN = N * N, NS = Dims<N>::NS;
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y;
     if (n >= gc.numNodes) return;
     int c[3]; { long long r = n; c[2] = (int)(r % gc.nn[2]); r /= gc.nn[2]; c[1] = (int)(r % gc.nn[1]); c[0] = (int)(r / gc.nn[1]); }
+    { const int cb = (gc.bd == 1) ? c[1] : c[2]; if (cb < bandLo || cb > bandHi) return; }   // banded update: rows outside keep their values
     int d[3] = {0, 0, 0};
     { int r = s; for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
     double acc[NN];
@@ -334,11 +336,11 @@ k_coarsen_stencil(const __grid_constant__ GridDesc gc, const __grid_constant__ G
     for (int i = 0; i < NN; ++i) Sc[stencil_addr(p, s * NN + i, Dims<N>::NE)] = acc[i];
 }
 
-void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc) {
+void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc, int bandLo, int bandHi) {
     ProfScope ps(ctx, PC_COARSEN, (double)gc.numNodes);
     dim3 block(128), grid((unsigned)((gc.numNodes + 127) / 128), gc.N == 3 ? 27 : 9);
-    if (gc.N == 3) k_coarsen_stencil<3><<<grid, block, 0, ctx.stream>>>(gc, gf, Sf, Sc);
-    else           k_coarsen_stencil<2><<<grid, block, 0, ctx.stream>>>(gc, gf, Sf, Sc);
+    if (gc.N == 3) k_coarsen_stencil<3><<<grid, block, 0, ctx.stream>>>(gc, gf, Sf, Sc, bandLo, bandHi);
+    else           k_coarsen_stencil<2><<<grid, block, 0, ctx.stream>>>(gc, gf, Sf, Sc, bandLo, bandHi);
     VF_KERNEL_CHECK();
 }
 
