@@ -11,4 +11,11 @@ for l in (0, 1, 2):
     for op in ("smooth", "residual", "apply"):
         row.append("L%d %s %.4f" % (l, op, mg.time_op(op, l, reps=5 if l == 0 else 20)))
 row.append("fmg %.4f" % mg.time_op("fmg", 0, reps=5))
+import time
+mg.update_stiffness(); mg.synchronize()
+t0 = time.perf_counter()
+for _ in range(3):
+    mg.update_stiffness()
+mg.synchronize()
+row.append("update_stiffness %.3f" % (1e3 * (time.perf_counter() - t0) / 3))
 print("%-28s %s" % (tag, " | ".join(row)))

@@ -481,6 +481,7 @@ struct vf_mg {
     // Pending banded update: since the hierarchy was last built, only the moduli of fine element layers [bandLo, bandHi) along
     // the build direction changed (mask decrements), and sim->version == bandVersion (MultigridSolver.hh:907-1017).
     bool bandActive = false; int bandLo = 0, bandHi = 0; uint64_t bandVersion = 0;
+    DevBuf<double> coarsenScratch;   // intermediates of the separable Galerkin product
     DevBuf<double> Ad, d, scalars, scratch, tmpA, tmpB, tmpC;
     double *hostScalars = nullptr; // pinned
     std::vector<double> lastResiduals; int lastIters = 0; const double *pcgX = nullptr; // device iterate of the running / last PCG
@@ -698,11 +699,18 @@ void mg_update_stiffness(vf_mg &lead, bool force = false) {
         for (int l = 1; l < nl; ++l) { lo = std::max(lo / 2 - 1, 0); hi = (hi + 1) / 2 + 1; bLo[l] = lo; bHi[l] = hi; }
     }
     lead.bandActive = false;
+    static const bool noSeparable = [] { const char *e = std::getenv("VF_COARSEN_ONESHOT"); return e && e[0] == '1'; }();
     auto coarsen = [&](vf_mg &mg, int l) {
         MGLevel &L = *mg.lv[l];
         const size_t len = (size_t)L.g.numPos * (mg.N == 3 ? 27 : 9) * mg.N * mg.N;
         if (L.S.n != len) L.S.alloc(len, true);
         if (l == 1) launch_coarsen_from_moduli(mg.ctx, L.g, mg.sim->g, mg.sim->E.p, mg.cK0dev.p, L.S.p, bLo[l], bHi[l]);
+        else if (mg.N == 3 && !banded && !mg.grp && !mg.sim->window && !noSeparable) {
+            const GridDesc &gf = mg.lv[l - 1]->g;
+            const size_t need = coarsen_separable_scratch(L.g, gf);
+            if (mg.coarsenScratch.n < need) mg.coarsenScratch.alloc(need, false);
+            launch_coarsen_stencil_separable(mg.ctx, L.g, gf, mg.lv[l - 1]->S.p, L.S.p, mg.coarsenScratch.p);
+        }
         else        launch_coarsen_stencil(mg.ctx, L.g, mg.lv[l - 1]->g, mg.lv[l - 1]->S.p, L.S.p, bLo[l], bHi[l]);
     };
     for (int l = 1; l < nl && l <= T; ++l) for (vf_mg *m : P) coarsen(*m, l);

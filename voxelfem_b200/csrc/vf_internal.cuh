@@ -202,6 +202,9 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
 // updateStiffnessMatrices after a change of the fabrication mask (MultigridSolver.hh:907-1017); default: every row.
 void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc, int bandLo = 0, int bandHi = 0x7fffffff);
 void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc, int bandLo = 0, int bandHi = 0x7fffffff);
+// P^T A P one axis at a time (3D, undivided grids, full rebuilds); scratch holds the two intermediate operators
+size_t coarsen_separable_scratch(const GridDesc &gc, const GridDesc &gf);
+void launch_coarsen_stencil_separable(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc, double *scratch);
 // Level-0 stencil straight from moduli (used for single-level direct solves): S = sum_e E_e K0 blocks.
 void launch_stencil_from_moduli_l0(const LaunchCtx &ctx, const GridDesc &g, const double *E, const double *K0dev, double *S);
 // Dense matrix of the free DOFs from a stencil: A[red(i)][red(j)], row-major n x n; redIdx[dof] = -1 for fixed DOFs.
