@@ -308,13 +308,16 @@ def main():
         sec_per_launch = p["ms"] * 1e-3 / p["launches"]
         achieved = bytes_per_launch / sec_per_launch / 1e9
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom, {}).get("bytes_per_launch")
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": peak_src, "launches": p["launches"], "avg_launch_us": sec_per_launch * 1e6,
-                    "share_of_step": p["ms"] / ms_prof, "note": "algorithmic bytes = %g B per node updated (DESIGN.md); fp64 FMA-bound kernel, see DESIGN.md for the FP64-pipe view" % ALG_BYTES[dom]}
+                    "share_of_step": p["ms"] / ms_prof,
+                    "note": "algorithmic bytes = %g B per node updated (DESIGN.md section 3); families: *_stencil = stored-stencil levels streaming from HBM (level 1), *_stencil_small = L2-resident coarse levels (launch-latency bound), *_l0 = matrix-free level 0 (FP64-pipe bound, DESIGN.md)" % ALG_BYTES[dom],
+                    "families": {k: {"ms_per_launch": v["ms"] / v["launches"], "launches": v["launches"], "share": v["ms"] / ms_prof,
+                                     "achieved_GBs": (ALG_BYTES[k] * v["units"] / (v["ms"] * 1e-3) / 1e9) if k in ALG_BYTES else None} for k, v in prof.items() if v["launches"]}}
     if args.profile:
         for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
             print("  %-18s launches %6d  ms %9.3f  share %5.1f%%  ms/launch %8.4f" % (k, v["launches"], v["ms"], 100 * v["ms"] / ms_prof, v["ms"] / v["launches"]), file=sys.stderr)

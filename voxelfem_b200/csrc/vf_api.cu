@@ -70,7 +70,8 @@ void prof_end(const LaunchCtx &ctx, int cat) {
     if (p->pending.size() > 8192) p->resolve();
 }
 static const char *kProfNames[PC_COUNT] = {"apply_l0", "residual_l0", "gs_l0", "apply_stencil", "residual_stencil", "gs_stencil",
-                                           "restrict", "prolong", "coarse_solve", "vector_ops", "coarsen", "topopt", "other"};
+                                           "restrict", "prolong", "coarse_solve", "vector_ops", "coarsen", "topopt", "other",
+                                           "apply_stencil_small", "residual_stencil_small", "gs_stencil_small"};
 
 // ---------------------------------------------------------------------------
 // Small RAII device buffer

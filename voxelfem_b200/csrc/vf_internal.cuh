@@ -146,9 +146,13 @@ __device__ __forceinline__ void gs_node_update(const double (&M)[N][N], const do
 // ---------------------------------------------------------------------------
 enum ProfCat {
     PC_APPLY_L0 = 0, PC_RESIDUAL_L0, PC_GS_L0, PC_APPLY_ST, PC_RESIDUAL_ST, PC_GS_ST, PC_RESTRICT, PC_PROLONG,
-    PC_COARSE_SOLVE, PC_VEC, PC_COARSEN, PC_TOPOPT, PC_OTHER, PC_COUNT
+    PC_COARSE_SOLVE, PC_VEC, PC_COARSEN, PC_TOPOPT, PC_OTHER,
+    // stored-stencil levels whose stencil fits the 126 MB L2 several times over are launch-latency bound, not HBM bound: own families
+    PC_APPLY_ST_SMALL, PC_RESIDUAL_ST_SMALL, PC_GS_ST_SMALL, PC_COUNT
 };
 
+// a stencil level streams from HBM when its stencil (1944 B per node in 3D) is larger than 256 MB
+inline bool stencil_level_streams(const GridDesc &g) { return (double)g.numNodes * (g.N == 3 ? 1944.0 : 288.0) > 256.0 * 1048576.0; }
 struct Profiler;
 struct LaunchCtx {
     cudaStream_t stream = nullptr;

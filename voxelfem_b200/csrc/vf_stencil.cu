@@ -191,7 +191,8 @@ static void stencil_kernel_attributes() {
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
                           const uint8_t *dmask, double *out, int mode) {
     stencil_kernel_attributes();
-    ProfScope ps(ctx, mode == APPLY_RESIDUAL ? PC_RESIDUAL_ST : PC_APPLY_ST, (double)g.numNodes);
+    const bool big = stencil_level_streams(g);
+    ProfScope ps(ctx, mode == APPLY_RESIDUAL ? (big ? PC_RESIDUAL_ST : PC_RESIDUAL_ST_SMALL) : (big ? PC_APPLY_ST : PC_APPLY_ST_SMALL), (double)g.numNodes);
     dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)(g.numPos / kStencilTile));
 #define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) k_stencil_tile<NN_, false, M><<<grid, block, 0, ctx.stream>>>(g, 0, S, u, b, dmask, out, 1);
     VF_CASE(3, APPLY_SET) VF_CASE(3, APPLY_ADD) VF_CASE(3, APPLY_SUB) VF_CASE(3, APPLY_RESIDUAL)
@@ -206,7 +207,7 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
     if (!make_color(g, color, col)) return;
     stencil_kernel_attributes();
     const long long tot = (long long)g.ccnt[color][0] * g.ccnt[color][1] * g.ccnt[color][2];
-    ProfScope ps(ctx, PC_GS_ST, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
+    ProfScope ps(ctx, stencil_level_streams(g) ? PC_GS_ST : PC_GS_ST_SMALL, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
     dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)((tot + kStencilTile - 1) / kStencilTile));
     const long long tile0 = g.cbase[color] / kStencilTile;
     if (g.N == 3) k_stencil_tile<3, true, APPLY_SET><<<grid, block, 0, ctx.stream>>>(g, tile0, S, u, b, dmask, u, forward ? 1 : 0);
