@@ -899,12 +899,14 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
                 if (!fmg) for (vf_mg *m : P) VF_CUDA(cudaMemsetAsync(s(*m), 0, sizeof(double) * m->sim->g.numNodes * N, m->ctx.stream));
                 mg_solve_inplace(lead, mgIterations, mgSmoothing, true, fmg);
             };
+            // Slab groups stay eager: capturing the NCCL ghost-plane send/recv pairs of one rank into the graph deadlocked on
+            // 2 GPUs (round 1), so the partitioned solve pays the launch latency of the small levels.
             const bool graphable = lead.useGraphs && !lead.grp && !(lead.ctx.prof && lead.ctx.prof->enabled);
+            vf_mg::PrecondGraph &pg = lead.pg;
+            const bool valid = pg.exec && pg.version == lead.sim->structVersion && pg.nActive == lead.sim->g.nActive && pg.mgIt == mgIterations &&
+                               pg.nsmooth == mgSmoothing && pg.fmg == fmg && pg.sym == lead.symmetricGS;
             if (!graphable) precond();
             else {
-                vf_mg::PrecondGraph &pg = lead.pg;
-                const bool valid = pg.exec && pg.version == lead.sim->structVersion && pg.nActive == lead.sim->g.nActive && pg.mgIt == mgIterations &&
-                                   pg.nsmooth == mgSmoothing && pg.fmg == fmg && pg.sym == lead.symmetricGS;
                 if (!valid) {
                     if (pg.exec) { cudaGraphExecDestroy(pg.exec); pg.exec = nullptr; }
                     const long long before = g_launches.load();

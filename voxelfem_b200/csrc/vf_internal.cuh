@@ -151,8 +151,8 @@ enum ProfCat {
     PC_APPLY_ST_SMALL, PC_RESIDUAL_ST_SMALL, PC_GS_ST_SMALL, PC_COUNT
 };
 
-// a stencil level streams from HBM when its stencil (1944 B per node in 3D) is larger than 256 MB
-inline bool stencil_level_streams(const GridDesc &g) { return (double)g.numNodes * (g.N == 3 ? 1944.0 : 288.0) > 256.0 * 1048576.0; }
+// a stencil level streams from HBM when its stencil (1944 B per node in 3D) is larger than 1 GiB (level 1 of the 256^3 grid: 4.2 GB; level 2: 0.5 GB, a few L2 sizes, latency-dominated)
+inline bool stencil_level_streams(const GridDesc &g) { return (double)g.numNodes * (g.N == 3 ? 1944.0 : 288.0) > 1024.0 * 1048576.0; }
 struct Profiler;
 struct LaunchCtx {
     cudaStream_t stream = nullptr;
