@@ -780,7 +780,7 @@ void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward) {
             const int lc = (lead.N == 3) ? (color ^ ((g.xoff & 1) << 2)) : color;   // local parity class of this global colour
             if (l == 0 && mg.N == 3) launch_gs3_color_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), lc, forward);
             else if (l == 0)         launch_gs_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), lc, forward);
-            else                     launch_gs_stencil(mg.ctx, g, mg.lv[l]->S.p, u(mg), b(mg), mg.dmask(l), lc, forward);
+            else                     launch_gs_stencil(mg.ctx, g, mg.lv[l]->S.p, u(mg), b(mg), mg.dmask(l), lc, forward, /* chained */ i > 0 && !lead.grp);
         }
         if (lead.N == 3) grp_exchange(lead, l, u, (color >> 2) & 1);
     }

@@ -178,6 +178,35 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
 #define VF_KERNEL_CHECK() ::vf::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Kernels of the solve path start with pdl_prologue(): griddepcontrol.launch_dependents
+// lets a NEXT kernel launched with the programmatic-stream-serialization attribute be scheduled as soon as this grid's blocks
+// have all started, griddepcontrol.wait holds its blocks until the PREVIOUS grid has completed and its writes are visible.
+// The attribute is set on the colour passes 2..8 of a stored-stencil smoothing sweep only, whose blocks request their stencil
+// tile (TMA) before the wait: the HBM round trip of a pass's first wave overlaps the tail of the previous pass (level-1
+// sweep 0.914 -> 0.891 ms, level-2 sweep 0.156 -> 0.132 ms).  Setting it on every launch of the captured preconditioner
+// graph made the FMG cycle slower (14.4 vs 13.5 ms, profiles/r02b_time_ab.log).  VF_PDL=0 disables the attribute.
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+bool pdl_enabled();   // vf_vec.cu
+template<class... KArgs, class... Args>
+inline void launch_pdl(bool programmatic, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (programmatic && pdl_enabled()) ? 1 : 0;
+    cuda_check(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...), "cudaLaunchKernelEx", __FILE__, __LINE__);
+}
+// VF_LAUNCH: ordinary stream-ordered launch; VF_LAUNCH_PDL: may start before its predecessor has drained (see above)
+#define VF_LAUNCH(kernel, grid, block, smem, stream, ...) ::vf::launch_pdl(false, kernel, grid, block, smem, stream, __VA_ARGS__)
+#define VF_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, ...) ::vf::launch_pdl(pdl, kernel, grid, block, smem, stream, __VA_ARGS__)
+#endif
+
+// ---------------------------------------------------------------------------
 // Kernel launchers (defined in the .cu files named in the comments)
 // ---------------------------------------------------------------------------
 // --- vf_l0.cu: matrix-free level-0 operator (TPSStencils.hh:231-396, 431-728; MultigridSolver.hh:277-292, 347-378)
@@ -198,8 +227,9 @@ void launch_gs3_color_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param 
 // Stencil layout: S[stencil_addr(stencil_pos(node), slot * N*N + a*N + b, NE)], numPos * NE doubles per level
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
                           const uint8_t *dmask, double *out, int mode);
+// chained: the previous kernel on the stream is a colour pass of the same sweep (nothing in flight writes S)
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
-                       const uint8_t *dmask, int color, bool forward);
+                       const uint8_t *dmask, int color, bool forward, bool chained = false);
 // Galerkin coarsening (MultigridSolver.hh:711-819): level-1 stencil from the fine Young's moduli and the 2^N
 // coarsened full-density matrices cK0[fi] (device, [fi][KE][KE]); level l >= 2 stencil as P^T A_{l-1} P.
 // bandLo..bandHi (inclusive, coarse node layers along the build direction): only those rows are recomputed -- the banded update of

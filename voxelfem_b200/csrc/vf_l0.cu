@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256)
 k_apply_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K, const double *__restrict__ u,
            const double *__restrict__ E, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
            double *__restrict__ out, double *dotOut, double *scratch) {
+    pdl_prologue();
     constexpr int NPE = Dims<N>::NPE;
     const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
     const int c1 = blockIdx.y * blockDim.y + threadIdx.y;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(128, 3)
 k_apply3_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K, const double *__restrict__ u,
             const double *__restrict__ E, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
             double *__restrict__ out, double *dotOut, double *scratch) {
+    pdl_prologue();
     const int c2 = blockIdx.x * 32 + threadIdx.x;
     const int c1 = 2 * (blockIdx.y * 4 + threadIdx.y);
     const int c0 = blockIdx.z;
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(32 * kWalshBY, 2)
 k_apply3w_l0(const __grid_constant__ GridDesc g, const __grid_constant__ KhatParam Kh, const double *__restrict__ u,
              const double *__restrict__ E, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
              double *__restrict__ out, double *dotOut, double *scratch) {
+    pdl_prologue();
     __shared__ double s_up[2][kWalshBY][3][32];
     const int lane = threadIdx.x, wy = threadIdx.y;
     const int cz = blockIdx.x * 31 + lane - 1;                 // element column / owned node coordinates (halo: lane 0, warp 0)
@@ -493,8 +496,8 @@ static void apply3w_launch(const LaunchCtx &ctx, dim3 grid, dim3 block, const Gr
     KhatParam Kh; std::memcpy(Kh.v, K.kh, sizeof(Kh.v));
 #define VF_W_CASE(M) \
     if (mode == M) { \
-        if (K.sparse7) k_apply3w_l0<M, DOT, true><<<grid, block, 0, ctx.stream>>>(g, Kh, u, E, b, dmask, out, dotOut, scratch); \
-        else           k_apply3w_l0<M, DOT, false><<<grid, block, 0, ctx.stream>>>(g, Kh, u, E, b, dmask, out, dotOut, scratch); \
+        if (K.sparse7) VF_LAUNCH((k_apply3w_l0<M, DOT, true>), grid, block, 0, ctx.stream, g, Kh, u, E, b, dmask, out, dotOut, scratch); \
+        else           VF_LAUNCH((k_apply3w_l0<M, DOT, false>), grid, block, 0, ctx.stream, g, Kh, u, E, b, dmask, out, dotOut, scratch); \
     }
     VF_W_CASE(APPLY_SET) VF_W_CASE(APPLY_ADD) VF_W_CASE(APPLY_SUB) VF_W_CASE(APPLY_RESIDUAL)
 #undef VF_W_CASE
@@ -519,8 +522,8 @@ static void apply3_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0
     const bool fused = dotOut && (size_t)grid.x * grid.y * grid.z <= (size_t)kReduceMaxBlocks;
 #define VF_APPLY_CASE(M) \
     if (mode == M) { \
-        if (fused) k_apply3_l0<M, true><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, dotOut, scratch); \
-        else       k_apply3_l0<M, false><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, nullptr, nullptr); \
+        if (fused) VF_LAUNCH((k_apply3_l0<M, true>), grid, block, 0, ctx.stream, g, K, u, E, b, dmask, out, dotOut, scratch); \
+        else       VF_LAUNCH((k_apply3_l0<M, false>), grid, block, 0, ctx.stream, g, K, u, E, b, dmask, out, nullptr, nullptr); \
     }
     VF_APPLY_CASE(APPLY_SET) VF_APPLY_CASE(APPLY_ADD) VF_APPLY_CASE(APPLY_SUB) VF_APPLY_CASE(APPLY_RESIDUAL)
 #undef VF_APPLY_CASE
@@ -536,8 +539,8 @@ static void apply_l0_dispatch(const LaunchCtx &ctx, const GridDesc &g, const K0P
     const bool fused = dotOut && (size_t)grid.x * grid.y * grid.z <= (size_t)kReduceMaxBlocks;
 #define VF_APPLY_CASE(M) \
     if (mode == M) { \
-        if (fused) k_apply_l0<N, M, true><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, dotOut, scratch); \
-        else       k_apply_l0<N, M, false><<<grid, block, 0, ctx.stream>>>(g, K, u, E, b, dmask, out, nullptr, nullptr); \
+        if (fused) VF_LAUNCH((k_apply_l0<N, M, true>), grid, block, 0, ctx.stream, g, K, u, E, b, dmask, out, dotOut, scratch); \
+        else       VF_LAUNCH((k_apply_l0<N, M, false>), grid, block, 0, ctx.stream, g, K, u, E, b, dmask, out, nullptr, nullptr); \
     }
     VF_APPLY_CASE(APPLY_SET) VF_APPLY_CASE(APPLY_ADD) VF_APPLY_CASE(APPLY_SUB) VF_APPLY_CASE(APPLY_RESIDUAL)
 #undef VF_APPLY_CASE
@@ -563,6 +566,7 @@ __global__ void __launch_bounds__(256)
 k_gs_l0(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K, const __grid_constant__ ColorDesc col,
         double *__restrict__ u, const double *__restrict__ b, const double *__restrict__ E,
         const uint8_t *__restrict__ dmask, int forward) {
+    pdl_prologue();
     constexpr int NPE = Dims<N>::NPE, KE = Dims<N>::KE;
     const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
     const int i1 = blockIdx.y * blockDim.y + threadIdx.y;
@@ -603,6 +607,7 @@ template<bool FWD>
 __global__ void __launch_bounds__(128, 3)
 k_gs3_color(const __grid_constant__ GridDesc g, const __grid_constant__ K0Param K, const __grid_constant__ ColorDesc col,
             double *u, const double *__restrict__ b, const double *__restrict__ E, const uint8_t *__restrict__ dmask) {
+    pdl_prologue();
     const int i2 = blockIdx.x * 32 + threadIdx.x;
     const int i1 = 2 * (blockIdx.y * 4 + threadIdx.y);   // first of the two colour-local y indices
     const int i0 = blockIdx.z;
@@ -704,8 +709,8 @@ void launch_gs3_color_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param 
     if (!make_color(g, color, col)) return;
     ProfScope ps(ctx, PC_GS_L0, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
     dim3 block(32, 4, 1), grid((col.cnt[2] + 31) / 32, ((col.cnt[1] + 1) / 2 + 3) / 4, col.cnt[0]);
-    if (forward) k_gs3_color<true><<<grid, block, 0, ctx.stream>>>(g, K, col, u, b, E, dmask);
-    else         k_gs3_color<false><<<grid, block, 0, ctx.stream>>>(g, K, col, u, b, E, dmask);
+    if (forward) VF_LAUNCH((k_gs3_color<true>), grid, block, 0, ctx.stream, g, K, col, u, b, E, dmask);
+    else         VF_LAUNCH((k_gs3_color<false>), grid, block, 0, ctx.stream, g, K, col, u, b, E, dmask);
     VF_KERNEL_CHECK();
 }
 
@@ -716,8 +721,8 @@ void launch_gs_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, dou
     ProfScope ps(ctx, PC_GS_L0, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
     dim3 block = (g.N == 3) ? dim3(32, 4, 2) : dim3(32, 8, 1);
     dim3 grid((col.cnt[2] + block.x - 1) / block.x, (col.cnt[1] + block.y - 1) / block.y, (col.cnt[0] + block.z - 1) / block.z);
-    if (g.N == 3) k_gs_l0<3><<<grid, block, 0, ctx.stream>>>(g, K, col, u, b, E, dmask, forward ? 1 : 0);
-    else          k_gs_l0<2><<<grid, block, 0, ctx.stream>>>(g, K, col, u, b, E, dmask, forward ? 1 : 0);
+    if (g.N == 3) VF_LAUNCH((k_gs_l0<3>), grid, block, 0, ctx.stream, g, K, col, u, b, E, dmask, forward ? 1 : 0);
+    else          VF_LAUNCH((k_gs_l0<2>), grid, block, 0, ctx.stream, g, K, col, u, b, E, dmask, forward ? 1 : 0);
     VF_KERNEL_CHECK();
 }
 

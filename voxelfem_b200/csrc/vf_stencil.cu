@@ -27,10 +27,10 @@ namespace vf {
 // N x N block of slot s with u(neighbour s) and the 3^N slot contributions are reduced in shared memory in a fixed
 // order (deterministic).  The level-1 stencil (1944 B per node in 3D) therefore streams from HBM as contiguous 31 KB
 // blocks; the small coarse levels cost one memory round trip per colour pass.
-template<int N>
+template<int N, int SPT>
 struct TileShared {
     alignas(128) double S[Dims<N>::NE * kStencilTile];
-    double red[N][Dims<N>::NS][kStencilTile];
+    double red[N][Dims<N>::NS / SPT][kStencilTile];
     double bs[N][kStencilTile];
     double us[N][kStencilTile];
     unsigned dm[kStencilTile];
@@ -67,14 +67,22 @@ __device__ __forceinline__ bool pos_coords(const GridDesc &g, long long pos, int
     return true;
 }
 
-template<int N, bool GS, int MODE>
-__global__ void __launch_bounds__(kStencilTile * Dims<N>::NS, N == 3 ? 4 : 8)
+// SPT = stencil slots per thread: 1 (one thread row per slot, 432 threads, 4 blocks per SM in 3D) or 3 (one thread row per
+// (dx, dy) pair handling its three z-neighbours, 144 threads, 6 blocks per SM: more tiles in flight per SM).
+template<int N, bool GS, int MODE, int SPT>
+__global__ void __launch_bounds__(kStencilTile * Dims<N>::NS / SPT, (N == 3 ? 4 : 8) * (SPT == 3 ? 3 : 2) / 2)
 k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double *__restrict__ S,
                const double *uin, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
-               double *out, int forward) {
-    constexpr int NS = Dims<N>::NS, A0 = Dims<N>::A0, NN = N * N, NE = Dims<N>::NE;
-    __shared__ TileShared<N> sh;
-    const int tx = threadIdx.x, s = threadIdx.y;
+               double *out, int flags) {
+    // flags bit 0: forward sweep; bit 1: the previous kernel on the stream does not write S (a colour pass of the same sweep),
+    // so the stencil tile may be requested BEFORE waiting for it -- the HBM round trip of this kernel's first wave then
+    // overlaps the tail of the previous colour pass.
+    pdl_trigger();
+    const int forward = flags & 1;
+    const bool earlyTile = (flags & 2) != 0;
+    constexpr int NS = Dims<N>::NS, A0 = Dims<N>::A0, NN = N * N, NE = Dims<N>::NE, ROWS = NS / SPT;
+    __shared__ TileShared<N, SPT> sh;
+    const int tx = threadIdx.x, s = threadIdx.y;   // s: thread row, slots s * SPT .. s * SPT + SPT - 1
     const long long tile = tile0 + blockIdx.x;
     const long long pos = tile * kStencilTile + tx;
     int c[3] = {0, 0, 0};
@@ -84,38 +92,55 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     const bool active = inRange && !detached && !(GS && (c[0] < g.cmpLo || c[0] >= g.cmpHi)); // ghost planes of a slab window are not smoothed
     if (tx == 0 && s == 0) mbar_init(&sh.mbar, 1);
     const int anyActive = __syncthreads_or(active ? 1 : 0);     // also publishes the barrier initialisation
+    if (!earlyTile) pdl_wait();
+    if (anyActive && tx == 0 && s == 0) tma_load_1d(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+    if (earlyTile) pdl_wait();
     if (anyActive) {
-        if (tx == 0 && s == 0) tma_load_1d(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
-        double acc[N], un[N];
+        double acc[N], un[SPT][N];
         #pragma unroll
-        for (int a = 0; a < N; ++a) { acc[a] = 0.0; un[a] = 0.0; }
-        bool valid = false;
+        for (int a = 0; a < N; ++a) acc[a] = 0.0;
+        bool valid[SPT];
+        #pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+            valid[j] = false;
+            #pragma unroll
+            for (int k = 0; k < N; ++k) un[j][k] = 0.0;
+        }
         if (active) {
             // stage b and the Dirichlet mask alongside so that the finalising threads have no global loads left
             if (s < N && (GS || MODE == APPLY_RESIDUAL)) sh.bs[s][tx] = b[s * g.numNodes + n];
             if (s == N) sh.dm[tx] = dmask ? dmask[n] : 0u;
-            int d[3] = {0, 0, 0};
-            { int r = s;
-              #pragma unroll
-              for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
-            valid = true; long long off = 0;
             #pragma unroll
-            for (int a = A0; a < 3; ++a) { const int qq = c[a] + d[a]; valid = valid && qq >= 0 && qq < g.nn[a]; off += (long long)d[a] * g.ns[a]; }
-            if (valid) {
+            for (int j = 0; j < SPT; ++j) {
+                const int slot = s * SPT + j;
+                int d[3] = {0, 0, 0};
+                { int r = slot;
+                  #pragma unroll
+                  for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+                bool v = true; long long off = 0;
                 #pragma unroll
-                for (int k = 0; k < N; ++k) un[k] = uin[k * g.numNodes + n + off];
-                if (GS && s == NS / 2) {
+                for (int a = A0; a < 3; ++a) { const int qq = c[a] + d[a]; v = v && qq >= 0 && qq < g.nn[a]; off += (long long)d[a] * g.ns[a]; }
+                valid[j] = v;
+                if (v) {
                     #pragma unroll
-                    for (int k = 0; k < N; ++k) sh.us[k][tx] = un[k];
+                    for (int k = 0; k < N; ++k) un[j][k] = uin[k * g.numNodes + n + off];
+                    if (GS && slot == NS / 2) {
+                        #pragma unroll
+                        for (int k = 0; k < N; ++k) sh.us[k][tx] = un[j][k];
+                    }
                 }
             }
         }
         mbar_wait(&sh.mbar, 0);
-        if (valid) {
-            #pragma unroll
-            for (int a = 0; a < N; ++a) {
+        #pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+            if (valid[j]) {
+                const int slot = s * SPT + j;
                 #pragma unroll
-                for (int k = 0; k < N; ++k) acc[a] = fma(sh.S[(s * NN + a * N + k) * kStencilTile + tx], un[k], acc[a]);
+                for (int a = 0; a < N; ++a) {
+                    #pragma unroll
+                    for (int k = 0; k < N; ++k) acc[a] = fma(sh.S[(slot * NN + a * N + k) * kStencilTile + tx], un[j][k], acc[a]);
+                }
             }
         }
         #pragma unroll
@@ -132,7 +157,7 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     if (s < N) { // thread row a = s sums the slot contributions of component a (fixed order -> deterministic)
         double t = 0.0;
         #pragma unroll
-        for (int k = 0; k < NS; ++k) t += sh.red[s][k][tx];
+        for (int k = 0; k < ROWS; ++k) t += sh.red[s][k][tx];
         sh.red[s][0][tx] = t;
     }
     __syncthreads();
@@ -173,6 +198,10 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     }
 }
 
+static int stencil_slots_per_thread() {
+    static const int v = [] { const char *e = std::getenv("VF_ST_SPT"); return (e && std::atoi(e) == 3) ? 3 : 1; }();
+    return v;
+}
 // the tile kernels want the largest shared-memory carve-out (4 resident blocks x 42 KB in 3D)
 template<typename Kern> static void prefer_shared(Kern k) {
     VF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -180,11 +209,12 @@ template<typename Kern> static void prefer_shared(Kern k) {
 static void stencil_kernel_attributes() {
     static bool done = false;
     if (done) return;
-#define VF_ATTR(NN_, M) prefer_shared(k_stencil_tile<NN_, false, M>);
+#define VF_ATTR(NN_, M) prefer_shared(k_stencil_tile<NN_, false, M, 1>); prefer_shared(k_stencil_tile<NN_, false, M, 3>);
     VF_ATTR(3, APPLY_SET) VF_ATTR(3, APPLY_ADD) VF_ATTR(3, APPLY_SUB) VF_ATTR(3, APPLY_RESIDUAL)
     VF_ATTR(2, APPLY_SET) VF_ATTR(2, APPLY_ADD) VF_ATTR(2, APPLY_SUB) VF_ATTR(2, APPLY_RESIDUAL)
 #undef VF_ATTR
-    prefer_shared(k_stencil_tile<3, true, APPLY_SET>); prefer_shared(k_stencil_tile<2, true, APPLY_SET>);
+    prefer_shared(k_stencil_tile<3, true, APPLY_SET, 1>); prefer_shared(k_stencil_tile<2, true, APPLY_SET, 1>);
+    prefer_shared(k_stencil_tile<3, true, APPLY_SET, 3>); prefer_shared(k_stencil_tile<2, true, APPLY_SET, 3>);
     done = true;
 }
 
@@ -193,8 +223,11 @@ void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double 
     stencil_kernel_attributes();
     const bool big = stencil_level_streams(g);
     ProfScope ps(ctx, mode == APPLY_RESIDUAL ? (big ? PC_RESIDUAL_ST : PC_RESIDUAL_ST_SMALL) : (big ? PC_APPLY_ST : PC_APPLY_ST_SMALL), (double)g.numNodes);
-    dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)(g.numPos / kStencilTile));
-#define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) k_stencil_tile<NN_, false, M><<<grid, block, 0, ctx.stream>>>(g, 0, S, u, b, dmask, out, 1);
+    const int spt = stencil_slots_per_thread();
+    dim3 block(kStencilTile, (g.N == 3 ? 27 : 9) / spt), grid((unsigned)(g.numPos / kStencilTile));
+#define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) { \
+        if (spt == 3) VF_LAUNCH((k_stencil_tile<NN_, false, M, 3>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1); \
+        else          VF_LAUNCH((k_stencil_tile<NN_, false, M, 1>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1); }
     VF_CASE(3, APPLY_SET) VF_CASE(3, APPLY_ADD) VF_CASE(3, APPLY_SUB) VF_CASE(3, APPLY_RESIDUAL)
     VF_CASE(2, APPLY_SET) VF_CASE(2, APPLY_ADD) VF_CASE(2, APPLY_SUB) VF_CASE(2, APPLY_RESIDUAL)
 #undef VF_CASE
@@ -202,16 +235,20 @@ void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double 
 }
 
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
-                       const uint8_t *dmask, int color, bool forward) {
+                       const uint8_t *dmask, int color, bool forward, bool chained) {
     ColorDesc col;
     if (!make_color(g, color, col)) return;
     stencil_kernel_attributes();
     const long long tot = (long long)g.ccnt[color][0] * g.ccnt[color][1] * g.ccnt[color][2];
     ProfScope ps(ctx, stencil_level_streams(g) ? PC_GS_ST : PC_GS_ST_SMALL, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
-    dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)((tot + kStencilTile - 1) / kStencilTile));
+    const int spt = stencil_slots_per_thread();
+    dim3 block(kStencilTile, (g.N == 3 ? 27 : 9) / spt), grid((unsigned)((tot + kStencilTile - 1) / kStencilTile));
     const long long tile0 = g.cbase[color] / kStencilTile;
-    if (g.N == 3) k_stencil_tile<3, true, APPLY_SET><<<grid, block, 0, ctx.stream>>>(g, tile0, S, u, b, dmask, u, forward ? 1 : 0);
-    else          k_stencil_tile<2, true, APPLY_SET><<<grid, block, 0, ctx.stream>>>(g, tile0, S, u, b, dmask, u, forward ? 1 : 0);
+    const int fl = (forward ? 1 : 0) | (chained ? 2 : 0);
+    if (g.N == 3 && spt == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
+    else if (g.N == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
+    else if (spt == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
+    else                      VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
     VF_KERNEL_CHECK();
 }
 
@@ -539,6 +576,7 @@ void launch_symmetrize_lower(const LaunchCtx &ctx, double *A, int n) {
 
 // y = A x for a dense symmetric row-major A: one warp per row, coalesced along the row.
 __global__ void __launch_bounds__(256) k_dense_symv(const double *__restrict__ A, int n, const double *__restrict__ x, double *__restrict__ y) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
     const double *row = A + (size_t)warp * n;
@@ -551,13 +589,14 @@ void launch_dense_symv(const LaunchCtx &ctx, const double *A, int n, const doubl
     ProfScope ps(ctx, PC_COARSE_SOLVE, (double)n * n);
     if (n == 0) return;
     dim3 block(256), grid((unsigned)(((size_t)n * 32 + 255) / 256));
-    k_dense_symv<<<grid, block, 0, ctx.stream>>>(A, n, x, y);
+    VF_LAUNCH((k_dense_symv), grid, block, 0, ctx.stream, A, n, x, y);
     VF_KERNEL_CHECK();
 }
 
 // y = tril(A) x or triu(A) x for a row-major matrix: one warp per row over the row's triangular part only
 template<bool LOWER>
 __global__ void __launch_bounds__(256) k_dense_trmv(const double *__restrict__ A, int n, const double *__restrict__ x, double *__restrict__ y) {
+    pdl_prologue();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= n) return;
     const double *a = A + (size_t)row * n;
@@ -571,12 +610,13 @@ void launch_dense_trmv(const LaunchCtx &ctx, const double *A, int n, const doubl
     ProfScope ps(ctx, PC_COARSE_SOLVE, (double)n * n / 2);
     if (n == 0) return;
     dim3 block(256), grid((unsigned)(((size_t)n * 32 + 255) / 256));
-    if (lower) k_dense_trmv<true><<<grid, block, 0, ctx.stream>>>(A, n, x, y);
-    else       k_dense_trmv<false><<<grid, block, 0, ctx.stream>>>(A, n, x, y);
+    if (lower) VF_LAUNCH((k_dense_trmv<true>), grid, block, 0, ctx.stream, A, n, x, y);
+    else       VF_LAUNCH((k_dense_trmv<false>), grid, block, 0, ctx.stream, A, n, x, y);
     VF_KERNEL_CHECK();
 }
 
 __global__ void k_gather_free(const double *__restrict__ f, const int *__restrict__ freeDofs, int nfree, long long numNodes, int N, double *__restrict__ rhs) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nfree) return;
     const int dof = freeDofs[i];
@@ -585,10 +625,11 @@ __global__ void k_gather_free(const double *__restrict__ f, const int *__restric
 void launch_gather_free(const LaunchCtx &ctx, const double *f, const int *freeDofs, int nfree, long long numNodes, int N, double *rhs) {
     ProfScope ps(ctx, PC_COARSE_SOLVE, (double)nfree);
     if (nfree == 0) return;
-    k_gather_free<<<(nfree + 255) / 256, 256, 0, ctx.stream>>>(f, freeDofs, nfree, numNodes, N, rhs);
+    VF_LAUNCH((k_gather_free), (nfree + 255) / 256, 256, 0, ctx.stream, f, freeDofs, nfree, numNodes, N, rhs);
     VF_KERNEL_CHECK();
 }
 __global__ void k_scatter_free(const double *__restrict__ y, const int *__restrict__ freeDofs, int nfree, long long numNodes, int N, double *__restrict__ x) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nfree) return;
     const int dof = freeDofs[i];
@@ -597,7 +638,7 @@ __global__ void k_scatter_free(const double *__restrict__ y, const int *__restri
 void launch_scatter_free(const LaunchCtx &ctx, const double *y, const int *freeDofs, int nfree, long long numNodes, int N, double *x) {
     ProfScope ps(ctx, PC_COARSE_SOLVE, (double)nfree);
     if (nfree == 0) return;
-    k_scatter_free<<<(nfree + 255) / 256, 256, 0, ctx.stream>>>(y, freeDofs, nfree, numNodes, N, x);
+    VF_LAUNCH((k_scatter_free), (nfree + 255) / 256, 256, 0, ctx.stream, y, freeDofs, nfree, numNodes, N, x);
     VF_KERNEL_CHECK();
 }
 

@@ -5,9 +5,15 @@
 // Masked vector ops: TensorProductSimulator.hh:413-459; PCG updates: MultigridSolver.hh:1108-1143,
 // ParallelVectorOps.hh:28-84.
 #include "vf_internal.cuh"
+#include <cstdlib>
 #include "vf_reduce.cuh"
 
 namespace vf {
+
+bool pdl_enabled() {
+    static const bool v = [] { const char *e = std::getenv("VF_PDL"); return !(e && e[0] == '0'); }();
+    return v;
+}
 
 static inline dim3 node_block(const GridDesc &g) { return (g.N == 3) ? dim3(32, 4, 2) : dim3(32, 8, 1); }
 static inline dim3 node_grid(const GridDesc &g, dim3 b) { return dim3((g.nn[2] + b.x - 1) / b.x, (g.nn[1] + b.y - 1) / b.y, (g.nn[0] + b.z - 1) / b.z); }
@@ -16,6 +22,7 @@ static inline dim3 node_grid(const GridDesc &g, dim3 b) { return dim3((g.nn[2] +
 template<int N>
 __global__ void __launch_bounds__(256)
 k_restrict(const __grid_constant__ GridDesc gf, const __grid_constant__ GridDesc gc, const double *__restrict__ fine, double *__restrict__ coarse) {
+    pdl_prologue();
     constexpr int A0 = Dims<N>::A0, NS = Dims<N>::NS;
     const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
     const int c1 = blockIdx.y * blockDim.y + threadIdx.y;
@@ -57,8 +64,8 @@ k_restrict(const __grid_constant__ GridDesc gf, const __grid_constant__ GridDesc
 void launch_restrict(const LaunchCtx &ctx, const GridDesc &gf, const GridDesc &gc, const double *fine, double *coarse) {
     ProfScope ps(ctx, PC_RESTRICT, (double)gf.numNodes);
     dim3 b = node_block(gc), g = node_grid(gc, b);
-    if (gc.N == 3) k_restrict<3><<<g, b, 0, ctx.stream>>>(gf, gc, fine, coarse);
-    else           k_restrict<2><<<g, b, 0, ctx.stream>>>(gf, gc, fine, coarse);
+    if (gc.N == 3) VF_LAUNCH((k_restrict<3>), g, b, 0, ctx.stream, gf, gc, fine, coarse);
+    else           VF_LAUNCH((k_restrict<2>), g, b, 0, ctx.stream, gf, gc, fine, coarse);
     VF_KERNEL_CHECK();
 }
 
@@ -66,6 +73,7 @@ void launch_restrict(const LaunchCtx &ctx, const GridDesc &gf, const GridDesc &g
 template<int N, bool ACC>
 __global__ void __launch_bounds__(256)
 k_prolong(const __grid_constant__ GridDesc gf, const __grid_constant__ GridDesc gc, const double *__restrict__ coarse, double *__restrict__ fine) {
+    pdl_prologue();
     constexpr int A0 = Dims<N>::A0, NPE = Dims<N>::NPE;
     const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
     const int c1 = blockIdx.y * blockDim.y + threadIdx.y;
@@ -106,8 +114,8 @@ k_prolong(const __grid_constant__ GridDesc gf, const __grid_constant__ GridDesc 
 void launch_prolong(const LaunchCtx &ctx, const GridDesc &gf, const GridDesc &gc, const double *coarse, double *fine, bool accumulate) {
     ProfScope ps(ctx, PC_PROLONG, (double)gf.numNodes);
     dim3 b = node_block(gf), g = node_grid(gf, b);
-    if (gf.N == 3) { if (accumulate) k_prolong<3, true><<<g, b, 0, ctx.stream>>>(gf, gc, coarse, fine); else k_prolong<3, false><<<g, b, 0, ctx.stream>>>(gf, gc, coarse, fine); }
-    else           { if (accumulate) k_prolong<2, true><<<g, b, 0, ctx.stream>>>(gf, gc, coarse, fine); else k_prolong<2, false><<<g, b, 0, ctx.stream>>>(gf, gc, coarse, fine); }
+    if (gf.N == 3) { if (accumulate) VF_LAUNCH((k_prolong<3, true>), g, b, 0, ctx.stream, gf, gc, coarse, fine); else VF_LAUNCH((k_prolong<3, false>), g, b, 0, ctx.stream, gf, gc, coarse, fine); }
+    else           { if (accumulate) VF_LAUNCH((k_prolong<2, true>), g, b, 0, ctx.stream, gf, gc, coarse, fine); else VF_LAUNCH((k_prolong<2, false>), g, b, 0, ctx.stream, gf, gc, coarse, fine); }
     VF_KERNEL_CHECK();
 }
 
@@ -128,6 +136,7 @@ __device__ __forceinline__ bool node_active(const GridDesc &g, long long n, int 
 static inline int flat_blocks(long long n) { long long b = (n + 255) / 256; const long long cap = 148LL * 16; return (int)(b < cap ? (b > 0 ? b : 1) : cap); }
 
 __global__ void __launch_bounds__(256) k_zero_dirichlet(const __grid_constant__ GridDesc g, const uint8_t *__restrict__ dmask, double *__restrict__ u) {
+    pdl_prologue();
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < g.numNodes; n += (long long)gridDim.x * blockDim.x) {
         const unsigned dm = dmask[n];
         if (dm) { for (int c = 0; c < g.N; ++c) if ((dm >> c) & 1u) u[c * g.numNodes + n] = 0.0; }
@@ -135,11 +144,12 @@ __global__ void __launch_bounds__(256) k_zero_dirichlet(const __grid_constant__ 
 }
 void launch_zero_dirichlet(const LaunchCtx &ctx, const GridDesc &g, const uint8_t *dmask, double *u) {
     ProfScope ps(ctx, PC_VEC, (double)g.numNodes);
-    k_zero_dirichlet<<<flat_blocks(g.numNodes), 256, 0, ctx.stream>>>(g, dmask, u);
+    VF_LAUNCH((k_zero_dirichlet), flat_blocks(g.numNodes), 256, 0, ctx.stream, g, dmask, u);
     VF_KERNEL_CHECK();
 }
 
 __global__ void k_enforce_dirichlet(long long numNodes, int N, int ndir, const long long *__restrict__ nodes, const uint8_t *__restrict__ masks, const double *__restrict__ vals, double *__restrict__ u) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ndir) return;
     const long long n = nodes[i]; const unsigned dm = masks[i];
@@ -148,40 +158,44 @@ __global__ void k_enforce_dirichlet(long long numNodes, int N, int ndir, const l
 void launch_enforce_dirichlet(const LaunchCtx &ctx, long long numNodes, int N, int ndir, const long long *nodes, const uint8_t *masks, const double *vals, double *u) {
     if (ndir == 0) return;
     ProfScope ps(ctx, PC_VEC, (double)ndir);
-    k_enforce_dirichlet<<<(ndir + 255) / 256, 256, 0, ctx.stream>>>(numNodes, N, ndir, nodes, masks, vals, u);
+    VF_LAUNCH((k_enforce_dirichlet), (ndir + 255) / 256, 256, 0, ctx.stream, numNodes, N, ndir, nodes, masks, vals, u);
     VF_KERNEL_CHECK();
 }
 
 __global__ void __launch_bounds__(256) k_masked_zero(const __grid_constant__ GridDesc g, double *__restrict__ u, int limit) {
+    pdl_prologue();
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < g.numNodes; n += (long long)gridDim.x * blockDim.x)
         if (node_active(g, n, limit)) for (int c = 0; c < g.N; ++c) u[c * g.numNodes + n] = 0.0;
 }
 void launch_masked_zero(const LaunchCtx &ctx, const GridDesc &g, double *u, int margin) {
     ProfScope ps(ctx, PC_VEC, (double)g.numNodes);
-    k_masked_zero<<<flat_blocks(g.numNodes), 256, 0, ctx.stream>>>(g, u, g.nActive + margin);
+    VF_LAUNCH((k_masked_zero), flat_blocks(g.numNodes), 256, 0, ctx.stream, g, u, g.nActive + margin);
     VF_KERNEL_CHECK();
 }
 __global__ void __launch_bounds__(256) k_detached_zero(const __grid_constant__ GridDesc g, double *__restrict__ u) {
+    pdl_prologue();
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < g.numNodes; n += (long long)gridDim.x * blockDim.x)
         if (!node_active(g, n, g.nActive)) for (int c = 0; c < g.N; ++c) u[c * g.numNodes + n] = 0.0;
 }
 void launch_detached_zero(const LaunchCtx &ctx, const GridDesc &g, double *u) {
     if (g.nActive >= g.nn[g.bd]) return;
     ProfScope ps(ctx, PC_VEC, (double)g.numNodes);
-    k_detached_zero<<<flat_blocks(g.numNodes), 256, 0, ctx.stream>>>(g, u);
+    VF_LAUNCH((k_detached_zero), flat_blocks(g.numNodes), 256, 0, ctx.stream, g, u);
     VF_KERNEL_CHECK();
 }
 __global__ void __launch_bounds__(256) k_masked_copy(const __grid_constant__ GridDesc g, const double *__restrict__ in, double *__restrict__ out, int limit) {
+    pdl_prologue();
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < g.numNodes; n += (long long)gridDim.x * blockDim.x)
         if (node_active(g, n, limit)) for (int c = 0; c < g.N; ++c) out[c * g.numNodes + n] = in[c * g.numNodes + n];
 }
 void launch_masked_copy(const LaunchCtx &ctx, const GridDesc &g, const double *in, double *out, int margin) {
     ProfScope ps(ctx, PC_VEC, (double)g.numNodes);
-    k_masked_copy<<<flat_blocks(g.numNodes), 256, 0, ctx.stream>>>(g, in, out, g.nActive + margin);
+    VF_LAUNCH((k_masked_copy), flat_blocks(g.numNodes), 256, 0, ctx.stream, g, in, out, g.nActive + margin);
     VF_KERNEL_CHECK();
 }
 
 __global__ void __launch_bounds__(256) k_masked_dot(const __grid_constant__ GridDesc g, const double *__restrict__ a, const double *__restrict__ b, double *result, double *scratch) {
+    pdl_prologue();
     double s = 0.0;
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < g.numNodes; n += (long long)gridDim.x * blockDim.x)
         if (node_active(g, n, g.nActive) && node_owned(g, n)) for (int c = 0; c < g.N; ++c) s = fma(a[c * g.numNodes + n], b[c * g.numNodes + n], s);
@@ -189,11 +203,12 @@ __global__ void __launch_bounds__(256) k_masked_dot(const __grid_constant__ Grid
 }
 void launch_masked_dot(const LaunchCtx &ctx, const GridDesc &g, const double *a, const double *b, double *result, double *scratch) {
     ProfScope ps(ctx, PC_VEC, (double)g.numNodes);
-    k_masked_dot<<<flat_blocks(g.numNodes), 256, 0, ctx.stream>>>(g, a, b, result, scratch);
+    VF_LAUNCH((k_masked_dot), flat_blocks(g.numNodes), 256, 0, ctx.stream, g, a, b, result, scratch);
     VF_KERNEL_CHECK();
 }
 
 __global__ void __launch_bounds__(256) k_cg_direction(const __grid_constant__ GridDesc g, const double *__restrict__ s, double *__restrict__ d, const double *num, const double *den, int first) {
+    pdl_prologue();
     const double beta = first ? 0.0 : (*num / *den);
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < g.numNodes; n += (long long)gridDim.x * blockDim.x) {
         if (!node_active(g, n, g.nActive)) continue;
@@ -205,12 +220,13 @@ __global__ void __launch_bounds__(256) k_cg_direction(const __grid_constant__ Gr
 }
 void launch_cg_direction(const LaunchCtx &ctx, const GridDesc &g, const double *s, double *d, const double *num, const double *den, bool first) {
     ProfScope ps(ctx, PC_VEC, (double)g.numNodes);
-    k_cg_direction<<<flat_blocks(g.numNodes), 256, 0, ctx.stream>>>(g, s, d, num, den, first ? 1 : 0);
+    VF_LAUNCH((k_cg_direction), flat_blocks(g.numNodes), 256, 0, ctx.stream, g, s, d, num, den, first ? 1 : 0);
     VF_KERNEL_CHECK();
 }
 
 __global__ void __launch_bounds__(256) k_cg_update(const __grid_constant__ GridDesc g, double *__restrict__ x, const double *__restrict__ d, double *__restrict__ r, const double *__restrict__ Ad,
                                                    const double *rMr, const double *dAd, double *rsq, double *scratch) {
+    pdl_prologue();
     const double alpha = *rMr / *dAd;
     double s = 0.0;
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < g.numNodes; n += (long long)gridDim.x * blockDim.x) {
@@ -229,7 +245,7 @@ __global__ void __launch_bounds__(256) k_cg_update(const __grid_constant__ GridD
 void launch_cg_update(const LaunchCtx &ctx, const GridDesc &g, double *x, const double *d, double *r, const double *Ad,
                       const double *rMr, const double *dAd, double *rsq, double *scratch) {
     ProfScope ps(ctx, PC_VEC, (double)g.numNodes);
-    k_cg_update<<<flat_blocks(g.numNodes), 256, 0, ctx.stream>>>(g, x, d, r, Ad, rMr, dAd, rsq, scratch);
+    VF_LAUNCH((k_cg_update), flat_blocks(g.numNodes), 256, 0, ctx.stream, g, x, d, r, Ad, rMr, dAd, rsq, scratch);
     VF_KERNEL_CHECK();
 }
 
