@@ -1,9 +1,10 @@
 /* voxelfem_b200.h -- C ABI of the B200-native VoxelFEM hot path.
  *
  * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The C++
- * host classes in voxelfem_b200/host/ (TensorProductSimulator, MultigridSolver,
- * TopologyOptimizationProblem, ...) and the pyVoxelFEM pybind11 module are thin veneers
- * over these entry points; tests/ call them directly through ctypes.
+ * host classes in voxelfem_b200/host/VoxelFEM.hh (TensorProductSimulator, MultigridSolver,
+ * TopologyOptimizationProblem, ...) and the pyVoxelFEM / pyOptimizer modules in
+ * voxelfem_b200/compat/ are thin veneers over these entry points; tests/ also call them
+ * directly through ctypes.
  *
  * Every entry point names the reference interface it replaces (paths relative to the
  * VoxelFEM reference tree).  All functions return 0 on success and a non-zero status on

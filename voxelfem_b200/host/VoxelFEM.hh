@@ -1,0 +1,449 @@
+// VoxelFEM.hh -- C++ host classes of the B200-native VoxelFEM hot path.
+//
+// Header-only veneer over the C ABI (include/voxelfem_b200.h) with the reference's class and method names, so that C++
+// code written against the reference's headers for the MG-PCG / topopt path recompiles against this one:
+//   TensorProductSimulator<double, 1, 1[, 1]>     TensorProductSimulator.hh:170-2182
+//   MultigridSolver<double, 1, 1[, 1]>            MultigridSolver.hh:23-1176
+//   Filter / SmoothingFilter / ProjectionFilter   TopologyOptimizationFilter.hh:20-400
+//   TotalVolumeConstraint                         TopologyOptimizationConstraint.hh:24-40
+//   MultigridComplianceObjective                  TopologyOptimizationObjective.hh:60-105
+//   TopologyOptimizationProblem                   TopologyOptimizationProblem.hh:17-155
+//   OCOptimizer                                   OptimalityCriterion.hh:38-149
+//   LayerByLayerEvaluator                         LayerByLayer.hh:25-309
+//   MMA                                           MethodOfMovingAsymptotes.hh:28-470
+// Eigen is not available here, so the Eigen types of the reference's signatures are replaced by two minimal owning
+// arrays with the same storage order: VField (numNodes x N, column-major == the C ABI's component-major VField,
+// TensorProductSimulator.hh:180) and VXd (std::vector<double>).
+// Every method is one C-ABI call; all arithmetic runs in CUDA kernels of libvoxelfem_b200.so.  Errors arrive as a
+// status + vf_last_error() and are rethrown as the exception types the reference throws (std::runtime_error, and
+// std::logic_error for the PCG's NaN guard, MultigridSolver.hh:1083).
+#pragma once
+#include <array>
+#include <cctype>
+#include <cmath>
+#include <cstdint>
+#include <fstream>
+#include <functional>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/voxelfem_b200.h"
+
+namespace voxelfem_b200 {
+
+inline void check(int rc) {
+    if (rc == 0) return;
+    const std::string msg = vf_last_error();
+    if (msg.rfind("NaN encountered", 0) == 0) throw std::logic_error(msg);
+    throw std::runtime_error(msg);
+}
+
+using VXd = std::vector<double>;
+
+// (rows x N) column-major nodal vector field
+class VField {
+public:
+    VField() = default;
+    VField(size_t rows, size_t cols) : m_rows(rows), m_cols(cols), m_d(rows * cols, 0.0) {}
+    void setZero(size_t rows, size_t cols) { m_rows = rows; m_cols = cols; m_d.assign(rows * cols, 0.0); }
+    void setZero() { std::fill(m_d.begin(), m_d.end(), 0.0); }
+    size_t rows() const { return m_rows; }
+    size_t cols() const { return m_cols; }
+    size_t size() const { return m_d.size(); }
+    double &operator()(size_t i, size_t c) { return m_d[c * m_rows + i]; }
+    double operator()(size_t i, size_t c) const { return m_d[c * m_rows + i]; }
+    double *data() { return m_d.data(); }
+    const double *data() const { return m_d.data(); }
+    double squaredNorm() const { double s = 0; for (double v : m_d) s += v * v; return s; }
+    double norm() const { return std::sqrt(squaredNorm()); }
+    double dot(const VField &o) const { double s = 0; for (size_t i = 0; i < m_d.size(); ++i) s += m_d[i] * o.m_d[i]; return s; }
+private:
+    size_t m_rows = 0, m_cols = 0;
+    std::vector<double> m_d;
+};
+
+enum class InterpolationLaw { SIMP = VF_LAW_SIMP, RAMP = VF_LAW_RAMP };
+
+namespace detail {
+// Minimal reader for the .bc files the voxel simulator accepts (MeshFEM BoundaryConditions.cc:219-380 restricted to
+// "dirichlet[xyz]*" / "force" box regions, TensorProductSimulator.hh:600-652): {"regions": [{"type", "value", "box%"|"box"}]}
+struct BCRegion { int kind = 0, cmask = 7; double value[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; bool relative = false; };
+class MiniJSON {
+public:
+    explicit MiniJSON(const std::string &s) : m_s(s) {}
+    std::vector<BCRegion> regions() {
+        std::vector<BCRegion> out;
+        expect('{');
+        while (true) {
+            const std::string key = str(); expect(':');
+            if (key == "regions") {
+                expect('[');
+                if (peek() == ']') { ++m_p; }
+                else while (true) { out.push_back(region()); if (peek() == ',') { ++m_p; continue; } expect(']'); break; }
+            } else skipValue();
+            if (peek() == ',') { ++m_p; continue; }
+            expect('}'); break;
+        }
+        return out;
+    }
+private:
+    const std::string &m_s; size_t m_p = 0;
+    char peek() { while (m_p < m_s.size() && std::isspace((unsigned char)m_s[m_p])) ++m_p; if (m_p >= m_s.size()) throw std::runtime_error("unexpected end of .bc file"); return m_s[m_p]; }
+    void expect(char c) { if (peek() != c) throw std::runtime_error(std::string("malformed .bc file: expected '") + c + "'"); ++m_p; }
+    std::string str() { expect('"'); std::string r; while (m_p < m_s.size() && m_s[m_p] != '"') r += m_s[m_p++]; ++m_p; return r; }
+    double num() { peek(); size_t used = 0; const double v = std::stod(m_s.substr(m_p), &used); m_p += used; return v; }
+    void vec(double (&v)[3]) { expect('['); int i = 0; if (peek() == ']') { ++m_p; return; } while (true) { const double x = num(); if (i < 3) v[i++] = x; if (peek() == ',') { ++m_p; continue; } expect(']'); break; } }
+    void skipValue() {
+        const char c = peek();
+        if (c == '"') { str(); return; }
+        if (c == '{' || c == '[') { int depth = 0; do { const char d = m_s[m_p++]; if (d == '{' || d == '[') ++depth; else if (d == '}' || d == ']') --depth; else if (d == '"') { while (m_s[m_p] != '"') ++m_p; ++m_p; } } while (depth > 0); return; }
+        while (m_p < m_s.size() && m_s[m_p] != ',' && m_s[m_p] != '}' && m_s[m_p] != ']') ++m_p;
+    }
+    void box(BCRegion &r) {
+        expect('{');
+        while (true) {
+            const std::string k = str(); expect(':');
+            if (k == "minCorner") vec(r.lo); else if (k == "maxCorner") vec(r.hi); else skipValue();
+            if (peek() == ',') { ++m_p; continue; } expect('}'); break;
+        }
+    }
+    BCRegion region() {
+        BCRegion r; bool haveBox = false;
+        expect('{');
+        while (true) {
+            const std::string k = str(); expect(':');
+            if (k == "type") {
+                const std::string t = str();
+                if (t.rfind("dirichlet", 0) == 0) {
+                    r.kind = 0; const std::string comp = t.substr(9);
+                    if (!comp.empty()) { r.cmask = 0; for (char ch : comp) { if (ch < 'x' || ch > 'z') throw std::runtime_error("Invalid type '" + t + "'"); r.cmask |= 1 << (ch - 'x'); } }
+                } else if (t == "force") r.kind = 1;
+                else throw std::runtime_error("Illegal constraint type, only \"dirichlet\" and \"force\" accepted");
+            } else if (k == "value") vec(r.value);
+            else if (k == "box%") { r.relative = true; box(r); haveBox = true; }
+            else if (k == "box") { r.relative = false; box(r); haveBox = true; }
+            else skipValue();
+            if (peek() == ',') { ++m_p; continue; } expect('}'); break;
+        }
+        if (!haveBox) throw std::runtime_error("only box / box% regions are supported");
+        return r;
+    }
+};
+} // namespace detail
+
+template<typename Real_, size_t... Degrees> class MultigridSolver;
+
+// ---------------------------------------------------------------------------------------------------------------------
+template<typename Real_, size_t... Degrees>
+class TensorProductSimulator {
+public:
+    static constexpr size_t N = sizeof...(Degrees);
+    static_assert(std::is_same<Real_, double>::value, "only the double instantiations exist (python_bindings/VoxelFEM.cc:301-308)");
+    static_assert((N == 2 || N == 3) && ((Degrees == 1) && ...), "only Q1 elements in 2D and 3D are instantiated");
+    using Scalar = Real_;
+    using VNd = std::array<double, N>;
+    using EigenNDIndex = std::array<size_t, N>;
+    using VField = voxelfem_b200::VField;
+    using VXd = voxelfem_b200::VXd;
+    struct BBoxN { VNd minCorner, maxCorner; };
+
+    TensorProductSimulator(const BBoxN &domain, const EigenNDIndex &elementsPerDimension) : m_domain(domain), m_ne(elementsPerDimension) {
+        int64_t ne[3] = {1, 1, 1}; double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+        for (size_t d = 0; d < N; ++d) { ne[d] = (int64_t)m_ne[d]; lo[d] = domain.minCorner[d]; hi[d] = domain.maxCorner[d]; }
+        check(vf_sim_create((int)N, ne, lo, hi, &m_h));
+    }
+    ~TensorProductSimulator() { if (m_h) vf_sim_destroy(m_h); }
+    TensorProductSimulator(const TensorProductSimulator &) = delete;
+    TensorProductSimulator &operator=(const TensorProductSimulator &) = delete;
+
+    size_t numNodes() const { return (size_t)vf_sim_num_nodes(m_h); }
+    size_t numElements() const { return (size_t)vf_sim_num_elements(m_h); }
+    const EigenNDIndex &NbElementsPerDimension() const { return m_ne; }
+    EigenNDIndex NbNodesPerDimension() const { EigenNDIndex r = m_ne; for (auto &v : r) ++v; return r; }
+    const BBoxN &domain() const { return m_domain; }
+
+    // material: isotropic ETensor(E, nu) (MeshFEM ElasticityTensor.hh:100-115) or the flattened (N(N+1)/2)^2 tensor
+    void setIsotropicETensor(double E, double nu) { check(vf_sim_set_isotropic(m_h, E, nu)); }
+    void setETensor(const std::vector<double> &flattened) { check(vf_sim_set_elasticity_tensor(m_h, flattened.data())); }
+    void readMaterial(const std::string &materialPath) {   // isotropic_material files (MeshFEM Materials.cc:291-311)
+        std::ifstream f(materialPath); if (!f) throw std::runtime_error("Couldn't open material " + materialPath);
+        std::stringstream ss; ss << f.rdbuf(); const std::string s = ss.str();
+        auto field = [&](const char *k) { const size_t p = s.find(std::string("\"") + k + "\""); if (p == std::string::npos) throw std::runtime_error(std::string("material file lacks ") + k); return std::stod(s.substr(s.find(':', p) + 1)); };
+        if (s.find("isotropic_material") == std::string::npos) throw std::runtime_error("only isotropic_material files are supported");
+        setIsotropicETensor(field("young"), field("poisson"));
+    }
+    std::vector<double> fullDensityElementStiffnessMatrix() const { const size_t k = N << N; std::vector<double> r(k * k); check(vf_sim_get_K0(m_h, r.data())); return r; }
+
+    InterpolationLaw interpolationLaw() const { return m_law; }
+    double E_0() const { return m_E0; }  double E_min() const { return m_Emin; }
+    double SIMPExponent() const { return m_gamma; }  double RAMPFactor() const { return m_q; }
+    void setInterpolationLaw(InterpolationLaw law) { m_law = law; pushInterp(); }
+    void setE_0(double v) { m_E0 = v; pushInterp(); }        void setE_min(double v) { m_Emin = v; pushInterp(); }
+    void setSIMPExponent(double v) { m_gamma = v; pushInterp(); }  void setRAMPFactor(double v) { m_q = v; pushInterp(); }
+    void setGravity(const VNd &g) { double v[3] = {0, 0, 0}; for (size_t d = 0; d < N; ++d) v[d] = g[d]; m_gravity = g; check(vf_sim_set_gravity(m_h, v)); }
+    const VNd &getGravity() const { return m_gravity; }
+
+    void setDensities(const VXd &rho) { if (rho.size() != numElements()) throw std::runtime_error("Density vector size mismatch"); check(vf_sim_set_densities(m_h, rho.data())); }
+    void setUniformDensities(double density) { check(vf_sim_set_uniform_density(m_h, density)); }
+    VXd getDensities() const { VXd r(numElements()); check(vf_sim_get_densities(m_h, r.data())); return r; }
+    VXd getYoungModulusScaleFactor() const { VXd r(numElements()); check(vf_sim_get_young_moduli(m_h, r.data())); return r; }
+    void setFabricationMaskHeightByLayer(size_t l) { check(vf_sim_set_mask_layer(m_h, (int64_t)l)); }
+
+    void applyDisplacementsAndLoadsFromFile(const std::string &bcPath) {
+        std::ifstream f(bcPath); if (!f) throw std::runtime_error("Couldn't open " + bcPath);
+        std::stringstream ss; ss << f.rdbuf(); const std::string s = ss.str();
+        const auto regs = detail::MiniJSON(s).regions();
+        std::vector<int32_t> kind, cmask; std::vector<double> val, lo, hi;
+        for (const auto &r : regs) {
+            kind.push_back(r.kind); cmask.push_back(r.cmask);
+            for (int d = 0; d < 3; ++d) {
+                val.push_back(r.value[d]);
+                const bool act = d < (int)N;
+                const double a = act ? m_domain.minCorner[d] : 0.0, b = act ? m_domain.maxCorner[d] : 0.0;
+                lo.push_back(r.relative && act ? a + r.lo[d] * (b - a) : r.lo[d]);
+                hi.push_back(r.relative && act ? a + r.hi[d] * (b - a) : r.hi[d]);
+            }
+        }
+        check(vf_sim_apply_bc_regions(m_h, (int)regs.size(), kind.data(), cmask.data(), val.data(), lo.data(), hi.data()));
+    }
+    void addDirichletCondition(const VNd &u, const VNd &minCorner, const VNd &maxCorner, const std::string &componentMask = "xyz") {
+        double uu[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; int cm = 0;
+        for (size_t d = 0; d < N; ++d) { uu[d] = u[d]; lo[d] = minCorner[d]; hi[d] = maxCorner[d]; }
+        for (char c : componentMask) cm |= 1 << (std::tolower(c) - 'x');
+        check(vf_sim_add_dirichlet_box(m_h, uu, lo, hi, cm));
+    }
+    std::vector<uint8_t> getDirichletMask() const { std::vector<uint8_t> m(numNodes()); check(vf_sim_get_dirichlet_mask(m_h, m.data())); return m; }
+    VField buildLoadVector() const { VField f(numNodes(), N); check(vf_sim_build_load_vector(m_h, f.data())); return f; }
+
+    VField applyK(const VField &u) const { VField r(numNodes(), N); check(vf_sim_apply_K(m_h, u.data(), r.data(), 1, 0)); return r; }
+    template<bool ZeroInit = true, bool Negate = false>
+    void applyK(const VField &u, VField &result) const { if (ZeroInit) result.setZero(numNodes(), N); check(vf_sim_apply_K(m_h, u.data(), result.data(), ZeroInit, Negate)); }
+    VField solve(const VField &f) const { VField u(numNodes(), N); check(vf_sim_solve(m_h, f.data(), u.data())); return u; }
+    VXd complianceGradientFlattened(const VField &u) const { VXd g(numElements()); check(vf_sim_compliance_gradient(m_h, u.data(), g.data(), 0)); return g; }
+    VXd elementEnergyDensity(const VField &u) const { VXd e(numElements()); check(vf_sim_element_energy_density(m_h, u.data(), e.data())); return e; }
+
+    vf_sim *handle() const { return m_h; }
+private:
+    void pushInterp() { check(vf_sim_set_interpolation(m_h, (int)m_law, m_E0, m_Emin, m_gamma, m_q)); }
+    BBoxN m_domain; EigenNDIndex m_ne; vf_sim *m_h = nullptr; VNd m_gravity{};
+    InterpolationLaw m_law = InterpolationLaw::SIMP; double m_E0 = 1, m_Emin = 1e-4, m_gamma = 3, m_q = 3;   // TensorProductSimulator.hh:2160-2166
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+template<typename Real_, size_t... Degrees>
+class MultigridSolver {
+public:
+    using TPS = TensorProductSimulator<Real_, Degrees...>;
+    static constexpr size_t N = TPS::N;
+    using VField = voxelfem_b200::VField;
+    using PCGCallback = std::function<void(size_t, const VField &, const VField &)>;   // (it, x, r), MultigridSolver.hh:1043-1045
+    using MGCallback = std::function<void(size_t, const VField &)>;
+
+    MultigridSolver(std::shared_ptr<TPS> fineSimulator, size_t numCoarseningLevels) : m_fine(std::move(fineSimulator)) {
+        check(vf_mg_create(m_fine->handle(), (int)numCoarseningLevels, &m_h));
+    }
+    ~MultigridSolver() { if (m_h) vf_mg_destroy(m_h); }
+    MultigridSolver(const MultigridSolver &) = delete;
+    MultigridSolver &operator=(const MultigridSolver &) = delete;
+
+    TPS &getSimulator(size_t l = 0) { if (l != 0) throw std::runtime_error("coarse-level simulators live on the device; use numNodes(l)"); return *m_fine; }
+    std::shared_ptr<TPS> getSimulatorPtr() const { return m_fine; }
+    size_t numLevels() const { return (size_t)vf_mg_num_levels(m_h); }
+    size_t numNodes(size_t l) const { return (size_t)vf_mg_level_num_nodes(m_h, (int)l); }
+
+    void updateStiffnessMatrices() { check(vf_mg_update_stiffness_matrices(m_h)); }
+    void setSymmetricGaussSeidel(bool symmetric) { check(vf_mg_set_symmetric_gauss_seidel(m_h, symmetric)); }
+    void setFabricationMaskHeightByLayer(size_t l) { check(vf_mg_set_mask_layer(m_h, (int64_t)l)); }
+    void decrementFabricationMaskHeightByLayer(size_t inc) { check(vf_mg_decrement_mask(m_h, (int)inc)); }
+
+    VField applyK(size_t l, const VField &u) { VField r(numNodes(l), N); check(vf_mg_apply_K(m_h, (int)l, u.data(), r.data())); return r; }
+    void computeResidual(size_t l, const VField &u, const VField &b, VField &r) { r.setZero(numNodes(l), N); check(vf_mg_compute_residual(m_h, (int)l, u.data(), b.data(), r.data())); }
+
+    // solve (:546-573); the callback sees the iterate after every cycle
+    VField solve(const VField &u, const VField &f, size_t numSteps, size_t numSmoothingSteps, bool stiffnessUpdated = false, bool zeroDirichlet = false,
+                 MGCallback it_callback = nullptr, bool fmg = false) {
+        VField x(u.rows(), u.cols());
+        if (!it_callback) { check(vf_mg_solve(m_h, u.data(), f.data(), (int)numSteps, (int)numSmoothingSteps, stiffnessUpdated, zeroDirichlet, fmg, x.data())); return x; }
+        VField cur = u;
+        for (size_t i = 0; i < numSteps; ++i) {
+            check(vf_mg_solve(m_h, cur.data(), f.data(), 1, (int)numSmoothingSteps, stiffnessUpdated || i > 0, zeroDirichlet, fmg && i == 0, x.data()));
+            it_callback(i, x); cur = x;
+        }
+        return x;
+    }
+
+    // preconditionedConjugateGradient (:1047-1152): x is the initial guess on entry and the solution on exit
+    void preconditionedConjugateGradient(VField &x, const VField &b, size_t maxIter, double tol, PCGCallback cb = nullptr,
+                                         size_t mgIterations = 1, size_t mgSmoothingIterations = 1, bool fmg = false) {
+        struct Tramp { MultigridSolver *self; PCGCallback *cb; size_t n; } t{this, &cb, x.rows()};
+        auto call = [](int it, double, void *user) {
+            Tramp &tr = *static_cast<Tramp *>(user);
+            VField xi(tr.n, N), ri(tr.n, N);   // the fields are fetched only because a callback asked for them
+            check(vf_mg_get_pcg_iterate(tr.self->m_h, xi.data())); check(vf_mg_get_pcg_residual(tr.self->m_h, ri.data()));
+            (*tr.cb)((size_t)it, xi, ri);
+        };
+        int iters = 0;
+        check(vf_mg_pcg(m_h, x.data(), b.data(), (int)maxIter, tol, (int)mgIterations, (int)mgSmoothingIterations, fmg, 0, &iters, nullptr,
+                        cb ? static_cast<vf_pcg_callback>(call) : nullptr, &t));
+        m_lastIters = (size_t)iters;
+    }
+    size_t lastPCGIterations() const { return m_lastIters; }
+    VField pcgResidual() { VField r(numNodes(0), N); check(vf_mg_get_pcg_residual(m_h, r.data())); return r; }
+
+    vf_mg *handle() const { return m_h; }
+private:
+    std::shared_ptr<TPS> m_fine; vf_mg *m_h = nullptr; size_t m_lastIters = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Filters and constraints: descriptors consumed by TopologyOptimizationProblem (the chain itself runs on the device)
+template<typename Real_> struct Filter { virtual ~Filter() = default; virtual std::array<double, 4> spec() const = 0; };
+template<typename Real_> struct SmoothingFilter : Filter<Real_> {   // TopologyOptimizationFilter.hh:283-400
+    enum class Type { Const = VF_SMOOTH_CONST, Linear = VF_SMOOTH_LINEAR };
+    SmoothingFilter(size_t r = 1, Type t = Type::Const) : radius(r), type(t) {}
+    size_t radius; Type type;
+    std::array<double, 4> spec() const override { return {double(VF_FILTER_SMOOTH), double(radius), double(int(type)), 0.0}; }
+};
+template<typename Real_> struct ProjectionFilter : Filter<Real_> {  // TopologyOptimizationFilter.hh:189-245
+    explicit ProjectionFilter(Real_ beta = 1) { setBeta(beta); }
+    Real_ getBeta() const { return m_beta; }
+    void setBeta(Real_ beta) { if (beta <= 0) throw std::runtime_error("Beta parameter has to be positive (received beta = " + std::to_string(beta) + ")"); m_beta = beta; }
+    Real_ invert(Real_ filteredValue) const {
+        if (filteredValue > 1.0 || filteredValue < 0.0) throw std::runtime_error("ProjectionFilter::invert domain error: target density for inversion is outside [0, 1].");
+        return std::atanh((2 * filteredValue - 1) * std::tanh(0.5 * m_beta)) / m_beta + 0.5;
+    }
+    std::array<double, 4> spec() const override { return {double(VF_FILTER_PROJECT), 0.0, 0.0, double(m_beta)}; }
+private:
+    Real_ m_beta = 1;
+};
+template<typename Real_> struct Constraint { virtual ~Constraint() = default; };
+template<typename Real_> struct TotalVolumeConstraint : Constraint<Real_> {   // TopologyOptimizationConstraint.hh:24-40
+    explicit TotalVolumeConstraint(Real_ volumeFraction) : m_volumeFraction(volumeFraction) {}
+    Real_ m_volumeFraction;
+};
+
+template<typename Sim> struct Objective { virtual ~Objective() = default; };
+template<typename Sim>
+struct MultigridComplianceObjective : Objective<Sim> {            // TopologyOptimizationObjective.hh:60-105
+    template<typename MGS> explicit MultigridComplianceObjective(std::shared_ptr<MGS> mg_) : m_handle(mg_->handle()), m_keep(mg_) {}
+    size_t cgIter = 100; double tol = 1e-5; size_t mgIterations = 1, mgSmoothingIterations = 2; bool fullMultigrid = true, zeroInit = false;
+    vf_mg *mgHandle() const { return m_handle; }
+private:
+    vf_mg *m_handle; std::shared_ptr<void> m_keep;
+};
+
+template<typename Sim>
+class TopologyOptimizationProblem {                               // TopologyOptimizationProblem.hh:17-155
+public:
+    using VXd = voxelfem_b200::VXd;
+    using ObjectivePtr = std::shared_ptr<MultigridComplianceObjective<Sim>>;
+    using ConstraintsList = std::vector<std::shared_ptr<Constraint<double>>>;
+    using FiltersList = std::vector<std::shared_ptr<Filter<double>>>;
+    TopologyOptimizationProblem(Sim &simulator, ObjectivePtr objective, const ConstraintsList &constraints, const FiltersList &filters)
+        : m_sim(simulator), m_objective(std::move(objective)), m_constraints(constraints), m_filters(filters) {
+        if (constraints.size() != 1) throw std::runtime_error("exactly one TotalVolumeConstraint is supported (OptimalityCriterion.hh:43-45)");
+        auto tvc = std::dynamic_pointer_cast<TotalVolumeConstraint<double>>(constraints[0]);
+        if (!tvc) throw std::runtime_error("exactly one TotalVolumeConstraint is supported (OptimalityCriterion.hh:43-45)");
+        std::vector<double> spec;
+        for (const auto &f : filters) { const auto s = f->spec(); spec.insert(spec.end(), s.begin(), s.end()); }
+        if (spec.empty()) spec.push_back(0.0);
+        check(vf_top_create(m_objective->mgHandle(), (int)filters.size(), spec.data(), tvc->m_volumeFraction, &m_h));
+    }
+    ~TopologyOptimizationProblem() { if (m_h) vf_top_destroy(m_h); }
+    TopologyOptimizationProblem(const TopologyOptimizationProblem &) = delete;
+    TopologyOptimizationProblem &operator=(const TopologyOptimizationProblem &) = delete;
+
+    size_t numVars() const { return m_sim.numElements(); }
+    bool setVars(const VXd &x, bool /* forceUpdate */ = false) { syncSolver(); if (x.size() != numVars()) throw std::runtime_error("Size mismatch"); check(vf_top_set_vars(m_h, x.data())); return true; }
+    VXd getVars() const { VXd r(numVars()); check(vf_top_get_vars(m_h, 0, r.data())); return r; }
+    VXd getDensities() const { VXd r(numVars()); check(vf_top_get_vars(m_h, 1, r.data())); return r; }
+    double evaluateObjective() const { double v = 0; check(vf_top_compliance(m_h, &v)); return v; }
+    VXd evaluateObjectiveGradientAndReturn() const { VXd g(numVars()); check(vf_top_objective_gradient(m_h, g.data())); return g; }
+    VXd evaluateConstraints() const { double v = 0; check(vf_top_constraint(m_h, &v)); return VXd(1, v); }
+    VXd evaluateConstraintsJacobianAndReturn() const { VXd g(numVars()); check(vf_top_constraint_jacobian(m_h, g.data())); return g; }
+    VField displacement() const { VField u(m_sim.numNodes(), Sim::N); check(vf_top_get_u(m_h, u.data())); return u; }
+    int lastPCGIterations() const { return vf_top_last_pcg_iterations(m_h); }
+    ObjectivePtr getObjective() const { return m_objective; }
+    const FiltersList &getFilters() const { return m_filters; }
+    const ConstraintsList &getConstraints() const { return m_constraints; }
+    void syncSolver() const {
+        const auto &o = *m_objective;
+        check(vf_top_set_solver(m_h, (int)o.cgIter, o.tol, (int)o.mgIterations, (int)o.mgSmoothingIterations, o.fullMultigrid, o.zeroInit));
+    }
+    vf_top *handle() const { return m_h; }
+private:
+    Sim &m_sim; ObjectivePtr m_objective; ConstraintsList m_constraints; FiltersList m_filters; vf_top *m_h = nullptr;
+};
+
+template<typename Problem>
+class OCOptimizer {                                               // OptimalityCriterion.hh:38-149
+public:
+    explicit OCOptimizer(Problem &p) : m_p(p) {}
+    void step(double m = 0.2, double p = 0.5, double ctol = 1e-6, bool inplace = true) {
+        if (!inplace) throw std::runtime_error("OCOptimizer::step(inplace = false) is not supported");
+        m_p.syncSolver(); int evals = 0; check(vf_top_oc_step(m_p.handle(), m, p, ctol, &evals)); m_lastEvals = evals;
+    }
+    int lastConstraintEvaluations() const { return m_lastEvals; }
+private:
+    Problem &m_p; int m_lastEvals = 0;
+};
+
+template<typename TPS>
+class LayerByLayerEvaluator {                                     // LayerByLayer.hh:25-309
+public:
+    using VXd = voxelfem_b200::VXd;
+    using LBLCallback = std::function<void(size_t, double, size_t)>;   // (layer, compliance, PCG iterations)
+    explicit LayerByLayerEvaluator(std::shared_ptr<TPS> lblSim) : m_sim(std::move(lblSim)) {}
+    ~LayerByLayerEvaluator() { if (m_h) vf_lbl_destroy(m_h); }
+    void selectInitMethod(const std::string &method) { m_method = method; if (m_h) check(vf_lbl_select_init_method(m_h, method.c_str())); }
+    template<typename MG>
+    void run(MG &solver, bool zeroInit, size_t layerIncrement, size_t maxIter, double tol, std::nullptr_t /* it_callback */ = nullptr,
+             size_t mgIterations = 1, size_t mgSmoothingIterations = 1, bool fullMultigrid = false, bool /* verbose */ = false, LBLCallback lblCallback = nullptr) {
+        if (!m_h || m_mg != solver.handle()) {
+            if (m_h) vf_lbl_destroy(m_h);
+            m_h = nullptr; check(vf_lbl_create(solver.handle(), &m_h)); m_mg = solver.handle();
+            check(vf_lbl_select_init_method(m_h, m_method.c_str()));
+        }
+        auto call = [](int64_t layer, double c, int its, void *user) { (*static_cast<LBLCallback *>(user))((size_t)layer, c, (size_t)its); };
+        check(vf_lbl_run(m_h, zeroInit, (int64_t)layerIncrement, (int)maxIter, tol, (int)mgIterations, (int)mgSmoothingIterations, fullMultigrid,
+                         lblCallback ? static_cast<vf_lbl_callback>(call) : nullptr, &lblCallback));
+    }
+    double objective() const { double v = 0; check(vf_lbl_objective(m_h, &v)); return v; }
+    VXd gradient() const { VXd g(m_sim->numElements()); check(vf_lbl_gradient(m_h, g.data())); return g; }
+private:
+    std::shared_ptr<TPS> m_sim; vf_lbl *m_h = nullptr; vf_mg *m_mg = nullptr; std::string m_method = "N=3";
+};
+
+class MMA {                                                       // MethodOfMovingAsymptotes.hh:28-470
+public:
+    using VXd = voxelfem_b200::VXd;
+    using F = std::function<VXd(const VXd &)>;      // m + 1 values
+    using DF = std::function<VXd(const VXd &)>;     // (m + 1) x n, row-major
+    MMA(int numVars, int numConstr, const VXd &xmin, const VXd &xmax, F f, DF df_dx) : m_n(numVars), m_m(numConstr), m_f(std::move(f)), m_df(std::move(df_dx)) {
+        check(vf_mma_create(numVars, numConstr, xmin.data(), xmax.data(), &m_h));
+    }
+    ~MMA() { if (m_h) vf_mma_destroy(m_h); }
+    MMA(const MMA &) = delete;
+    MMA &operator=(const MMA &) = delete;
+    void enableGCMMA(bool enable) { check(vf_mma_enable_gcmma(m_h, enable)); }
+    void setInitialVar(const VXd &x0) { check(vf_mma_set_initial_var(m_h, x0.data())); }
+    void step() {
+        auto f = [](const double *x, double *out, void *user) -> int {
+            MMA &s = *static_cast<MMA *>(user);
+            try { const VXd v = s.m_f(VXd(x, x + s.m_n)); std::copy(v.begin(), v.end(), out); return 0; } catch (...) { return 1; }
+        };
+        auto df = [](const double *x, double *out, void *user) -> int {
+            MMA &s = *static_cast<MMA *>(user);
+            try { const VXd v = s.m_df(VXd(x, x + s.m_n)); std::copy(v.begin(), v.end(), out); return 0; } catch (...) { return 1; }
+        };
+        check(vf_mma_step(m_h, f, df, this, 0));
+    }
+    VXd getOptimalVar() const { VXd x(m_n); check(vf_mma_get_optimal_var(m_h, x.data())); return x; }
+private:
+    int m_n, m_m; F m_f; DF m_df; vf_mma *m_h = nullptr;
+};
+
+} // namespace voxelfem_b200
