@@ -199,6 +199,21 @@ int vf_filter_smooth(int dim, const int64_t *sizes, int radius, int type, const 
 int vf_filter_project(int64_t n, double beta, const double *in, double *out);                                 /* ProjectionFilter::apply (:199-210) */
 int vf_filter_project_backprop(int64_t n, double beta, const double *in, const double *vars, double *out);  /* ProjectionFilter::backprop (:212-225) */
 
+/* ---- Device-pointer building blocks (slab-partitioned topology optimization) -------------
+ * Same kernels as the filters / OC update / sensitivities above, on arrays that already live in HBM and on the
+ * simulator's stream: the host side (voxelfem_b200/capi.py: SlabProblem) exchanges the filter halos between slabs
+ * and all-reduces the scalars between these calls.  sizes / n describe the array passed in (e.g. a slab plus its halo). */
+int vf_dev_filter_smooth(vf_sim *s, int dim, const int64_t *sizes, int radius, int type, const double *in_dev, double *out_dev);
+int vf_dev_filter_project(vf_sim *s, int64_t n, double beta, const double *in_dev, double *out_dev);
+int vf_dev_filter_project_backprop(vf_sim *s, int64_t n, double beta, const double *g_dev, const double *vars_dev, double *out_dev);
+/* OCOptimizer update rule (OptimalityCriterion.hh:64-83) for one multiplier value. */
+int vf_dev_oc_update(vf_sim *s, int64_t n, const double *x0_dev, const double *dJ_dev, const double *dc_dev, double lambda, double m, double p, double *out_dev);
+int vf_dev_sum(vf_sim *s, int64_t n, const double *x_dev, double *result_host);
+int vf_sim_set_densities_dev(vf_sim *s, const double *rho_dev);                 /* setDensities (:785-790), window-sized */
+int vf_sim_compliance_gradient_dev(vf_sim *s, const double *u_dev, double *g_dev, int accumulate); /* (:1008-1040) */
+void *vf_sim_stream(vf_sim *s);
+int vf_sim_synchronize(vf_sim *s);
+
 /* ---- Topology optimization problem ------------------------------------------------ */
 /* filter_spec: 4 doubles per filter (kind, radius, smoothing type, beta). */
 int vf_top_create(vf_mg *mg, int num_filters, const double *filter_spec, double volume_fraction, vf_top **out);

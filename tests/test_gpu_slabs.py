@@ -95,3 +95,41 @@ def test_slab_mbb_partial_dirichlet(capi, data_dir):
     u, it, _ = solve_slabs(capi, ne, dom, bc, levels, 2, 2, rho, 1e-5, f, pcg)
     assert it == it_ref
     assert np.linalg.norm(u - u_ref) <= 1e-9 * np.linalg.norm(u_ref)
+
+
+@pytest.mark.parametrize("ne,levels,first_rep,nparts,radius", [((32, 8, 8), 2, 2, 2, 2), ((48, 16, 8), 2, 1, 3, 3), ((32, 16, 16), 3, 2, 4, 1)])
+def test_slab_topopt_matches_undivided_problem(capi, data_dir, ne, levels, first_rep, nparts, radius):
+    """Config-4 style loop (filters + partitioned MG-PCG compliance + volume constraint + OC) on a local slab group against the
+    undivided device problem: same compliance, sensitivities, bisection path and design variables, iteration by iteration."""
+    dom = (ne[0] / 8.0, ne[1] / 8.0, ne[2] / 8.0)
+    bc = os.path.join(data_dir, "bcs", "3D", "cantilever_flexion_E.bc")
+    V = 0.3
+    filters = [("smooth", radius, 1), ("project", 1.0)]
+    x0 = np.full(int(np.prod(ne)), 0.5 + np.arctanh((2 * V - 1) * np.tanh(0.5)))
+    x0 = x0 * (1 + 0.05 * np.sin(np.arange(x0.size)))                    # break the uniformity so that halos matter
+    s, mg, _ = build_reference(capi, ne, dom, bc, levels, np.ones(int(np.prod(ne))), 1e-4)
+    ref = capi.Problem(mg, filters, V)
+    ref.set_solver(200, 1e-12, 1, 2, True, False)      # tight solves: what remains is the difference of the two code paths
+    ref.set_vars(x0)
+
+    sims, mgs = [], []
+    for (a, b) in capi.slab_ranges(ne[0], nparts, 2 ** first_rep):
+        ps = capi.SlabSim(np.array(ne), np.zeros(3), np.array(dom), a, b, share_stream_with=sims[0] if sims else None)
+        ps.set_isotropic(1.0, 0.3); ps.set_interp(0, 1.0, 1e-4, 3.0, 3.0); ps.apply_bc_file(bc)
+        ps.set_densities(ps.window_of_elements(np.ones(int(np.prod(ne)))))
+        sims.append(ps); mgs.append(capi.SlabMG(ps, levels, first_rep))
+    grp = capi.SlabGroup(mgs)
+    top = capi.SlabProblem(list(zip(sims, mgs)), grp, filters, V)
+    top.set_solver(200, 1e-12, 1, 2, True, False)
+    top.set_vars(x0)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    for it in range(3):
+        assert rel(top.physical_vars(), ref.physical_vars()) < (1e-13 if it == 0 else 1e-6)
+        assert abs(top.compliance() - ref.compliance()) < 1e-8 * abs(ref.compliance()), it
+        assert abs(top.constraint() - ref.constraint()) < 1e-12
+        assert rel(top.objective_gradient(), ref.objective_gradient()) < 1e-7
+        assert rel(top.constraint_jacobian(), ref.constraint_jacobian()) < 1e-12
+        na, nb = top.oc_step(), ref.oc_step()
+        assert na == nb and abs(top.last_pcg_iters - ref.last_pcg_iters()) <= 2
+        assert rel(top.design_vars(), ref.design_vars()) < 1e-6
+    grp.close()

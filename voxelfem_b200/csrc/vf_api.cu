@@ -1602,6 +1602,40 @@ int vf_filter_project_backprop(int64_t n, double beta, const double *in, const d
     h2d(a.p, in, n, c.stream); h2d(v.p, vars, n, c.stream); launch_filter_project_backprop(c, n, beta, a.p, v.p, b.p); d2h(out, b.p, n, c.stream); VF_CATCH
 }
 
+// ---- device-pointer variants (element arrays stay in HBM; kernels run on the simulator's stream) ------------------------
+// Building blocks of a topology-optimization iteration whose element arrays are partitioned into slabs (one per GPU): the
+// host side exchanges filter halos and all-reduces scalars between these calls (voxelfem_b200/capi.py: SlabProblem).
+int vf_dev_filter_smooth(vf_sim *s, int dim, const int64_t *sizes, int radius, int type, const double *in_dev, double *out_dev) {
+    VF_TRY int sz[3] = {1, 1, 1}; for (int d = 0; d < dim; ++d) sz[d] = (int)sizes[d];
+    launch_filter_smooth(s->ctx, dim, sz, radius, type, in_dev, out_dev); VF_CATCH
+}
+int vf_dev_filter_project(vf_sim *s, int64_t n, double beta, const double *in_dev, double *out_dev) {
+    VF_TRY launch_filter_project(s->ctx, n, beta, in_dev, out_dev); VF_CATCH
+}
+int vf_dev_filter_project_backprop(vf_sim *s, int64_t n, double beta, const double *g_dev, const double *vars_dev, double *out_dev) {
+    VF_TRY launch_filter_project_backprop(s->ctx, n, beta, g_dev, vars_dev, out_dev); VF_CATCH
+}
+int vf_dev_oc_update(vf_sim *s, int64_t n, const double *x0_dev, const double *dJ_dev, const double *dc_dev, double lambda, double m, double p, double *out_dev) {
+    VF_TRY launch_oc_update(s->ctx, n, x0_dev, dJ_dev, dc_dev, lambda, m, p, out_dev); VF_CATCH
+}
+int vf_dev_sum(vf_sim *s, int64_t n, const double *x_dev, double *result) {
+    VF_TRY
+    if (s->scratch.n < reduce_scratch_doubles()) s->scratch.alloc(reduce_scratch_doubles(), true);
+    if (s->scalars.n < 8) s->scalars.alloc(8, true);
+    launch_sum(s->ctx, n, x_dev, s->scalars.p, s->scratch.p);
+    d2h(result, s->scalars.p, 1, s->stream);
+    VF_CATCH
+}
+int vf_sim_set_densities_dev(vf_sim *s, const double *rho_dev) {
+    VF_TRY if (rho_dev != s->rho.p) VF_CUDA(cudaMemcpyAsync(s->rho.p, rho_dev, sizeof(double) * s->g.numElems, cudaMemcpyDeviceToDevice, s->stream));
+    s->updateModuli(); VF_CATCH
+}
+int vf_sim_compliance_gradient_dev(vf_sim *s, const double *u_dev, double *g_dev, int accumulate) {
+    VF_TRY launch_compliance_gradient(s->ctx, s->g, s->K0p, u_dev, s->rho.p, g_dev, s->law, s->E0, s->Emin, s->gamma, s->q, s->gravity, s->elemVolume(), accumulate != 0); VF_CATCH
+}
+void *vf_sim_stream(vf_sim *s) { return (void *)s->stream; }
+int vf_sim_synchronize(vf_sim *s) { VF_TRY VF_CUDA(cudaStreamSynchronize(s->stream)); VF_CATCH }
+
 } // extern "C"
 
 // ---------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 // host_smoke.cpp -- the reference's C++ workflow for the hot path, written against the reference's class names
-// (VoxelFEM.hh), compiled by __graft_entry__.build() and run on the GPU by tests/test_gpu_host_api.py, which compares
-// the printed numbers with the CPU oracle:
+// (VoxelFEM.hh), compiled by __graft_entry__.build() and run on the GPU by tests/test_gpu_host_api.py, which checks
+// the printed numbers against the CPU restatement kept under tests/:
 //   1. python/CoarseningLevelBenchmark.py:76-100 in C++: one MG-PCG solve with an iteration callback (2D and 3D),
 //   2. python/3DTopoptDemo.ipynb cells 1, 5: filters + MultigridComplianceObjective + TotalVolumeConstraint + OCOptimizer,
 //   3. error behaviour: the exception the reference throws for a grid that cannot be coarsened (MultigridSolver.hh:52).
