@@ -163,7 +163,9 @@ def main():
         # the CPU restatement of its algorithm (oracle/) with all host threads.  Rank 0 only.
         if rank != 0:
             return
-        wl = args.workload or args.cpu_workload
+        # same workload as the GPU arm (256^3); each step is a bounded sample of it: the PCG capped at 2 iterations (about 20-40 s
+        # per step on the box's host cores); warm-up capped at one step so that the default --steps/--warmup ends within minutes
+        wl = args.workload or workload
         cb = cpu_sample(wl, max(1, args.steps), max(0, min(args.warmup, 1)))
         line = {"impl": "reference", "metric": "MG-PCG DOF*iterations per second (3D Q1, FMG-PCG, tol 1e-10)", "value": cb["value"], "unit": "DOF*iters/s",
                 "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
