@@ -258,18 +258,19 @@ def main():
     # end-to-end through the host-pointer C ABI call (what the reference's binding does: copy u and f in, x out)
     xh = torch.zeros(ndof, dtype=torch.float64).pin_memory().numpy()
     bh = torch.zeros(ndof, dtype=torch.float64).pin_memory().numpy()
+    u0h = torch.zeros(ndof, dtype=torch.float64).pin_memory().numpy()   # zero initial guess, as in python/CoarseningLevelBenchmark.py
     bh[:] = b.download()
     import ctypes as C
 
     def e2e_step():
-        xh[:] = 0.0
         if grp is not None:  # this rank's window: host -> device, partitioned solve, device -> host
-            capi._check(L.vf_dev_upload(x.ptr, xh, ndof)); capi._check(L.vf_dev_upload(b.ptr, bh, ndof))
+            capi._check(L.vf_dev_upload(x.ptr, u0h, ndof)); capi._check(L.vf_dev_upload(b.ptr, bh, ndof))
             it_, _ = grp.pcg_dev([x], [b], **PCG)
             capi._check(L.vf_dev_download(xh, x.ptr, ndof))
             return it_
         itc = C.c_int(0)
-        capi._check(L.vf_mg_pcg(mg.h, xh, bh, PCG["max_iter"], PCG["tol"], PCG["mg_iterations"], PCG["mg_smoothing"], int(PCG["fmg"]), 0, C.byref(itc), np.zeros(PCG["max_iter"] + 1), capi.PCG_CALLBACK(), None))
+        # the reference binding's call shape: initial guess and load in (pinned host arrays), solution out (pinned host array)
+        capi._check(L.vf_mg_pcg_io(mg.h, u0h, bh, xh, PCG["max_iter"], PCG["tol"], PCG["mg_iterations"], PCG["mg_smoothing"], int(PCG["fmg"]), 0, C.byref(itc), np.zeros(PCG["max_iter"] + 1), capi.PCG_CALLBACK(), None))
         return itc.value
     e2e_step()
     barrier()

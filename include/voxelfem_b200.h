@@ -133,6 +133,11 @@ typedef void (*vf_pcg_callback)(int iteration, double residual_norm, void *user)
 int vf_mg_pcg(vf_mg *mg, double *x, const double *b, int max_iter, double tol, int mg_iterations,
               int mg_smoothing_iterations, int fmg, int dirichlet_already_satisfied,
               int *out_iterations, double *residual_norms, vf_pcg_callback cb, void *user);
+/* Out-of-place form of vf_mg_pcg, as the reference's Python binding uses the solver (VoxelFEM.cc:174-186): u0 (initial guess)
+ * and b are read, the solution is written to x_out. */
+int vf_mg_pcg_io(vf_mg *mg, const double *u0, const double *b, double *x_out, int max_iter, double tol, int mg_iterations,
+                 int mg_smoothing_iterations, int fmg, int dirichlet_already_satisfied,
+                 int *out_iterations, double *residual_norms, vf_pcg_callback cb, void *user);
 int vf_mg_get_pcg_residual(vf_mg *mg, double *r);                         /* pcgResidual (:1156) */
 /* Current iterate x of the running PCG: valid inside cb (the reference's it_callback receives (it, x, r),
  * MultigridSolver.hh:1043-1045, 1146-1147) and until the buffers passed to the last solve are released. */

@@ -91,6 +91,7 @@ def lib():
         "vf_mg_coarse_solve": (ci, [vp, _dp, _dp]),
         "vf_mg_solve": (ci, [vp, _dp, _dp, ci, ci, ci, ci, ci, _dp]),
         "vf_mg_pcg": (ci, [vp, _dp, _dp, ci, cd, ci, ci, ci, ci, C.POINTER(ci), _dp, PCG_CALLBACK, vp]),
+        "vf_mg_pcg_io": (ci, [vp, _dp, _dp, _dp, ci, cd, ci, ci, ci, ci, C.POINTER(ci), _dp, PCG_CALLBACK, vp]),
         "vf_mg_get_pcg_iterate": (ci, [vp, _dp]),
         "vf_dev_filter_smooth": (ci, [vp, ci, _ip, ci, ci, vp, vp]),
         "vf_dev_filter_project": (ci, [vp, i64, cd, vp, vp]),
@@ -473,11 +474,12 @@ class MG(_Owned):
         return from_soa(out, self.N)
 
     def pcg(self, u, b, max_iter, tol, mg_iterations=1, mg_smoothing=1, fmg=False, dirichlet_ok=False, callback=None):
-        x = to_soa(u)
+        u0 = to_soa(u)
+        x = np.empty_like(u0)
         it = C.c_int(0)
         res = np.zeros(max(max_iter, 1) + 1)
         cb = PCG_CALLBACK(lambda i, r, _u: callback(i, r)) if callback else PCG_CALLBACK()
-        _check(self.L.vf_mg_pcg(self.h, x, to_soa(b), max_iter, tol, mg_iterations, mg_smoothing, int(fmg), int(dirichlet_ok), C.byref(it), res, cb, None))
+        _check(self.L.vf_mg_pcg_io(self.h, u0, to_soa(b), x, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), int(dirichlet_ok), C.byref(it), res, cb, None))
         return from_soa(x, self.N), it.value, res[:it.value]
 
     def pcg_dev(self, x_dev, b_dev, max_iter, tol, mg_iterations=1, mg_smoothing=1, fmg=False, dirichlet_ok=False):

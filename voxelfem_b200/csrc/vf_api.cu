@@ -1494,6 +1494,20 @@ int vf_mg_pcg(vf_mg *mg, double *x, const double *b, int maxIter, double tol, in
     if (resNorms) std::copy(mg->lastResiduals.begin(), mg->lastResiduals.end(), resNorms);
     VF_CATCH
 }
+// Out-of-place form, as the reference's Python binding calls it (VoxelFEM.cc:174-186: `VField x = u; pcg(x, ...); return x`):
+// the initial guess u0 is read, the solution is written to x_out; neither host buffer needs preparing between solves.
+int vf_mg_pcg_io(vf_mg *mg, const double *u0, const double *b, double *x_out, int maxIter, double tol, int mgIt, int mgSmooth, int fmg, int dirichletOK,
+                 int *outIters, double *resNorms, vf_pcg_callback cb, void *user) {
+    VF_TRY const size_t len = (size_t)mg->grid(0).numNodes * mg->N;
+    double *dx = mg_tmp(mg, 0, len), *db = mg_tmp(mg, 1, len);
+    VF_CUDA(cudaMemcpyAsync(dx, u0, len * sizeof(double), cudaMemcpyHostToDevice, mg->ctx.stream));
+    VF_CUDA(cudaMemcpyAsync(db, b, len * sizeof(double), cudaMemcpyHostToDevice, mg->ctx.stream));
+    mg_pcg(*mg, dx, db, maxIter, tol, mgIt, mgSmooth, fmg != 0, dirichletOK != 0, cb, user);
+    d2h(x_out, dx, len, mg->ctx.stream);
+    if (outIters) *outIters = mg->lastIters;
+    if (resNorms) std::copy(mg->lastResiduals.begin(), mg->lastResiduals.end(), resNorms);
+    VF_CATCH
+}
 int vf_mg_get_pcg_residual(vf_mg *mg, double *r) { VF_TRY d2h(r, lb(*mg, 0), (size_t)mg->grid(0).numNodes * mg->N, mg->ctx.stream); VF_CATCH }
 int vf_mg_get_pcg_iterate(vf_mg *mg, double *x) {
     VF_TRY if (!mg->pcgX) throw std::runtime_error("no PCG solve has run on this solver");
