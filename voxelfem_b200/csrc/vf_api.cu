@@ -492,9 +492,10 @@ struct vf_mg {
     DevBuf<double> stage[2];                          // staging buffers of the slab exchanges
     // The preconditioner application (one FMG / V-cycle: a fixed sequence of ~350 launches, most of them tiny coarse-level
     // kernels) is captured once into a CUDA graph and replayed every PCG iteration.
-    struct PrecondGraph { cudaGraphExec_t exec = nullptr; uint64_t version = 0; int nActive = -1, mgIt = 0, nsmooth = 0; bool fmg = false, sym = true; long long launches = 0; } pg;
+    struct PrecondGraph { cudaGraphExec_t exec = nullptr; uint64_t version = 0; int nActive = -1, mgIt = 0, nsmooth = 0; bool fmg = false, sym = true; long long launches = 0; } pg, sg;   // sg: V-cycle over the replicated levels of an NCCL rank
+    bool inSubCapture = false;
     bool useGraphs = true;
-    ~vf_mg() { if (hostScalars) cudaFreeHost(hostScalars); if (pg.exec) cudaGraphExecDestroy(pg.exec); }
+    ~vf_mg() { if (hostScalars) cudaFreeHost(hostScalars); if (pg.exec) cudaGraphExecDestroy(pg.exec); if (sg.exec) cudaGraphExecDestroy(sg.exec); }
     int numLevels() const { return (int)lv.size(); }
     const uint8_t *dmask(int l) const { return l == 0 ? sim->dmaskDev.p : lv[l]->dmask.p; }
     const GridDesc &grid(int l) const { return l == 0 ? sim->g : lv[l]->g; }
@@ -815,6 +816,35 @@ void mg_prolong(vf_mg &lead, int l, Field coarse, Field fine, bool accumulate) {
 void mg_vcycle(vf_mg &lead, int l, int nsmooth, bool residualSystem) {
     const int coarsest = lead.numLevels() - 1;
     if (l == coarsest) { mg_coarse_solve(lead, fb(l), fx(l)); return; }
+    // NCCL rank: the V-cycle over the replicated levels (first replicated level downwards) needs no communication and is entered
+    // firstRep + 1 times per FMG cycle with ~100 tiny launches each: replay it as a captured CUDA graph.  (The windowed levels stay
+    // eager: capturing the NCCL ghost-plane exchanges deadlocked, see mg_pcg.)
+    if (lead.grp && lead.grp->comm && l == lead.firstRep && l > 0 && residualSystem && !lead.inSubCapture && lead.useGraphs &&
+        !(lead.ctx.prof && lead.ctx.prof->enabled) && parts_of(lead).size() == 1) {
+        static const bool enabled = [] { const char *e = std::getenv("VF_SUBGRAPH"); return !(e && e[0] == '0'); }();
+        if (enabled) {
+            mg_update_stiffness(lead);
+            vf_mg::PrecondGraph &sg = lead.sg;
+            const bool valid = sg.exec && sg.version == lead.sim->structVersion && sg.nActive == lead.sim->g.nActive && sg.nsmooth == nsmooth && sg.sym == lead.symmetricGS;
+            if (!valid) {
+                if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+                const long long before = g_launches.load();
+                cudaGraph_t graph = nullptr;
+                lead.inSubCapture = true;
+                VF_CUDA(cudaStreamBeginCapture(lead.ctx.stream, cudaStreamCaptureModeThreadLocal));
+                try { mg_vcycle(lead, l, nsmooth, true); } catch (...) { lead.inSubCapture = false; cudaStreamEndCapture(lead.ctx.stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+                lead.inSubCapture = false;
+                VF_CUDA(cudaStreamEndCapture(lead.ctx.stream, &graph));
+                VF_CUDA(cudaGraphInstantiate(&sg.exec, graph, 0));
+                cudaGraphDestroy(graph);
+                sg.launches = g_launches.load() - before; g_launches.fetch_sub(sg.launches);
+                sg.version = lead.sim->structVersion; sg.nActive = lead.sim->g.nActive; sg.nsmooth = nsmooth; sg.sym = lead.symmetricGS;
+            }
+            VF_CUDA(cudaGraphLaunch(sg.exec, lead.ctx.stream));
+            g_launches.fetch_add(sg.launches);
+            return;
+        }
+    }
     mg_enforce_dirichlet(lead, l, fx(l), residualSystem);
     for (int i = 0; i < nsmooth; ++i) mg_smooth(lead, l, fx(l), fb(l), true);
     mg_residual(lead, l, fx(l), fb(l), fr(l));
