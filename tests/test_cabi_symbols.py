@@ -52,3 +52,19 @@ def test_product_does_not_reference_oracle():
                 if "oracle" in txt.lower() and fn != "__init__.py":
                     bad.append(os.path.join(dirpath, fn))
     assert not bad, bad
+
+
+def test_handle_tree_destroys_dependents_first():
+    """The ctypes layer owns C-ABI handles in a tree (simulator -> solvers -> problems): whichever wrapper is finalised first,
+    dependents are destroyed before what they point into, and every handle is destroyed exactly once."""
+    from voxelfem_b200.capi import _Handle
+    log = []
+    sim = _Handle(lambda h: log.append(("sim", h)), 1)
+    mg1, mg2 = _Handle(lambda h: log.append(("mg", h)), 2), _Handle(lambda h: log.append(("mg", h)), 3)
+    top = _Handle(lambda h: log.append(("top", h)), 4)
+    sim.adopt(mg1); sim.adopt(mg2); mg1.adopt(top)
+    mg2.close()                                  # a solver dropped on its own
+    sim.close()                                  # the simulator goes first (cycle collector order): subtree first
+    top.close(); mg1.close(); sim.close()        # late finalisers find their handles closed
+    assert log == [("mg", 3), ("top", 4), ("mg", 2), ("sim", 1)]
+    assert sim.h is None and mg1.h is None and top.h is None
