@@ -69,12 +69,16 @@ void launch_restrict(const LaunchCtx &ctx, const GridDesc &gf, const GridDesc &g
     VF_KERNEL_CHECK();
 }
 
-// fine_n (=, +=) sum over the <= 2^N coarse nodes around it of the multilinear weights
+// fine_n (=, +=) sum over the <= 2^N coarse nodes around it of the multilinear weights.
+// The weight prod_a (odd_a ? 1/2 : 1) does not depend on which of the surrounding coarse nodes is visited and is a power of two, so
+// the coarse values are summed (same order as the reference's row visit, MultigridSolver.hh:162-176) and scaled once: bit-identical
+// to accumulating w * value, with a third of the instructions (the first version spent 357 instructions per fine node and was
+// issue-bound at 0.29 / 0.46 ms for the 256^3 grid).  x and y parities are warp-uniform, so even rows skip their absent neighbours.
 template<int N, bool ACC>
 __global__ void __launch_bounds__(256)
 k_prolong(const __grid_constant__ GridDesc gf, const __grid_constant__ GridDesc gc, const double *__restrict__ coarse, double *__restrict__ fine) {
     pdl_prologue();
-    constexpr int A0 = Dims<N>::A0, NPE = Dims<N>::NPE;
+    constexpr int A0 = Dims<N>::A0;
     const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
     const int c1 = blockIdx.y * blockDim.y + threadIdx.y;
     const int c0 = blockIdx.z * blockDim.z + threadIdx.z;
@@ -82,32 +86,39 @@ k_prolong(const __grid_constant__ GridDesc gf, const __grid_constant__ GridDesc 
     const int cc[3] = {c0, c1, c2};
     if (ACC && ((gf.bd == 1) ? c1 : c2) >= gf.nActive) return; // accum_interpolation visits non-detached nodes only (:192)
     const long long n = (long long)c0 * gf.ns[0] + (long long)c1 * gf.ns[1] + c2;
+    long long base = 0; bool ok0[3] = {true, true, true}, ok1[3] = {false, false, false}; double w = 1.0;
+    #pragma unroll
+    for (int a = A0; a < 3; ++a) {
+        const int fa = cc[a] - (a == 0 ? xshift(gf, gc) : 0);   // fine index relative to coarse plane 0 (may be negative in a window)
+        const int q = fa >> 1;                                  // arithmetic shift = floor division
+        const bool odd = fa & 1;
+        ok0[a] = q >= 0 && q < gc.nn[a];                        // outside the coarse window: only for ghost planes, which are received
+        ok1[a] = odd && q + 1 >= 0 && q + 1 < gc.nn[a];         // even fine index: single coarse node
+        base += (long long)q * gc.ns[a];
+        if (odd) w *= 0.5;
+    }
     double acc[N];
     #pragma unroll
     for (int c = 0; c < N; ++c) acc[c] = 0.0;
+    const long long NC = gc.numNodes;
     #pragma unroll
-    for (int k = 0; k < NPE; ++k) {
-        bool use = true; long long ci = 0; double w = 1.0;
+    for (int b0 = 0; b0 < (N == 3 ? 2 : 1); ++b0) {
+        if (!(b0 ? ok1[0] : ok0[0])) continue;
         #pragma unroll
-        for (int a = A0; a < 3; ++a) {
-            const int bit = (k >> (2 - a)) & 1;
-            const int fa = cc[a] - (a == 0 ? xshift(gf, gc) : 0);   // fine index relative to coarse plane 0 (may be negative in a window)
-            const int odd = fa & 1;
-            // even fine index: single coarse node (bit 0 only); odd: both neighbours with weight 1/2
-            use = use && (odd || bit == 0);
-            const int q = (fa >> 1) + bit;                          // arithmetic shift = floor division
-            use = use && q >= 0 && q < gc.nn[a];                    // outside the coarse window: only for ghost planes, which are received
-            ci += (long long)q * gc.ns[a];
-            w *= odd ? 0.5 : 1.0;
-        }
-        if (use) {
+        for (int b1 = 0; b1 < 2; ++b1) {
+            if (!(b1 ? ok1[1] : ok0[1])) continue;
+            const long long row = base + (b0 ? gc.ns[0] : 0) + (b1 ? gc.ns[1] : 0);
             #pragma unroll
-            for (int c = 0; c < N; ++c) acc[c] = fma(w, coarse[c * gc.numNodes + ci], acc[c]);
+            for (int b2 = 0; b2 < 2; ++b2) {
+                if (!(b2 ? ok1[2] : ok0[2])) continue;
+                #pragma unroll
+                for (int c = 0; c < N; ++c) acc[c] += coarse[c * NC + row + b2];
+            }
         }
     }
     #pragma unroll
     for (int c = 0; c < N; ++c) {
-        if (ACC) fine[c * gf.numNodes + n] += acc[c]; else fine[c * gf.numNodes + n] = acc[c];
+        if (ACC) fine[c * gf.numNodes + n] += w * acc[c]; else fine[c * gf.numNodes + n] = w * acc[c];
     }
 }
 
