@@ -42,19 +42,21 @@ k_restrict(const __grid_constant__ GridDesc gf, const __grid_constant__ GridDesc
             { int r = s;
               #pragma unroll
               for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+            // branch-free: an out-of-range neighbour is read at a clamped (valid, non-detached) index with weight 0, so all
+            // 3^N * N loads are independent and in flight together (the branchy version serialised on load latency: 11 us for
+            // a 17^3 coarse grid)
             bool valid = true; long long fi = 0; double w = 1.0;
             #pragma unroll
             for (int a = A0; a < 3; ++a) {
                 const int q = 2 * cc[a] + d[a] + (a == 0 ? xshift(gf, gc) : 0);
                 const int lim = (a == gf.bd) ? gf.nActive : gf.nn[a];
                 valid = valid && q >= 0 && q < lim;
-                fi += (long long)q * gf.ns[a];
+                fi += (long long)min(max(q, 0), lim - 1) * gf.ns[a];
                 w *= (d[a] == 0) ? 1.0 : 0.5;
             }
-            if (valid) {
-                #pragma unroll
-                for (int c = 0; c < N; ++c) acc[c] = fma(w, fine[c * gf.numNodes + fi], acc[c]);
-            }
+            w = valid ? w : 0.0;
+            #pragma unroll
+            for (int c = 0; c < N; ++c) acc[c] = fma(w, fine[c * gf.numNodes + fi], acc[c]);
         }
     }
     #pragma unroll
