@@ -131,7 +131,10 @@ def setup_slab(capi, rank, world, data_dir):
     ne = np.array([256 * world, 256, 256])
     dmax = np.array([float(world), 1.0, 1.0])
     levels = 5 if world <= 2 else 6          # keeps the replicated coarsest grid at <= 4,131 DOF
-    first_rep = int(os.environ.get("VF_BENCH_FIRST_REP", "3"))   # levels 0..2 are windowed per GPU, the rest is replicated (3 vs 4: 240 vs 251 ms at 2 GPUs)
+    # first replicated level: the levels below it are windowed per GPU (ghost-plane exchange after every colour pass), the rest is
+    # replicated on every rank (no communication, replayed as a CUDA graph).  Replicating level 3 as well pays while the replicated
+    # grid is small (2 GPUs: 240 vs 251 ms, 4 GPUs: 231 vs 242 ms per solve); at 8 slabs level 3 has 280k nodes and stays windowed.
+    first_rep = int(os.environ.get("VF_BENCH_FIRST_REP", "3" if world <= 4 else "4"))
     a, b = capi.slab_ranges(int(ne[0]), world, 2 ** first_rep)[rank]
     s = capi.SlabSim(ne, np.zeros(3), dmax, a, b)
     s.set_isotropic(MATERIAL["E"], MATERIAL["nu"])
