@@ -68,3 +68,37 @@ def test_owned_reduction_and_ghost_exchange_gloo_world2():
     port = 29000 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, ne, out), nprocs=world, join=True)
     assert dict(out) == {0: 1, 1: 1}
+
+
+def _halo_worker(rank, world, port, ne, R, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from voxelfem_b200 import capi
+    field = np.random.default_rng(5).normal(size=ne)                                # same global element field on every rank
+    sb, se = capi.slab_ranges(ne[0], world, 4)[rank]
+    ext = capi.slab_halo_exchange([torch.from_numpy(np.ascontiguousarray(field[sb:se]))], [(sb, se)], ne[0], R, dist)[0]
+    elo, ehi = capi.slab_halo_range(sb, se, ne[0], R)
+    out[rank] = 1 if np.array_equal(ext.numpy(), field[elo:ehi]) else 0
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,R", [(2, 3), (3, 4)])
+def test_filter_halo_exchange_gloo(world, R):
+    """The filter halos of the slab-partitioned topology optimization (capi.SlabProblem): after the exchange every rank holds
+    exactly the global field's layers [sb - R, se + R) clipped at the grid -- over torch.distributed (gloo here, NCCL on GPUs)."""
+    ne = (8 * world, 3, 5)
+    out = mp.get_context("spawn").Manager().dict()
+    port = 31000 + (os.getpid() % 2000) + world
+    mp.spawn(_halo_worker, args=(world, port, ne, R, out), nprocs=world, join=True)
+    assert dict(out) == {r: 1 for r in range(world)}
+
+
+def test_filter_halo_exchange_local_parts():
+    from voxelfem_b200 import capi
+    ne, R = (24, 2, 3), 5
+    field = np.random.default_rng(6).normal(size=ne)
+    slabs = capi.slab_ranges(ne[0], 3, 8)
+    ext = capi.slab_halo_exchange([torch.from_numpy(np.ascontiguousarray(field[a:b])) for a, b in slabs], slabs, ne[0], R, None)
+    for (a, b), e in zip(slabs, ext):
+        lo, hi = capi.slab_halo_range(a, b, ne[0], R)
+        assert np.array_equal(e.numpy(), field[lo:hi])

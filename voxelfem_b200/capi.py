@@ -771,6 +771,48 @@ class _Ptr:
         self.t, self.ptr = t, C.c_void_p(t.data_ptr())
 
 
+def slab_halo_range(sb, se, ne0, R):
+    """Element layers [elo, ehi) a slab owning [sb, se) holds once R halo layers per neighbour are attached (clipped at the grid)."""
+    return max(0, sb - R), min(ne0, se + R)
+
+
+def slab_halo_exchange(owned, slabs, ne0, R, dist=None):
+    """Arrays over the slab + halo layers of every local part: owned layers from `owned` (torch tensors, layer axis first, any
+    device), halo layers from the neighbouring slabs' owned layers.  `slabs`: the (sb, se) element-layer ranges of the local parts.
+    dist is None: all slabs of the grid are local and ordered (device copies); else the single local part is rank dist.get_rank()
+    of an initialised torch.distributed group (NCCL on GPUs, gloo in the CPU tests) and halos travel as batched isend / irecv."""
+    import torch
+    ext = []
+    for (sb, se), o in zip(slabs, owned):
+        elo, ehi = slab_halo_range(sb, se, ne0, R)
+        e = torch.zeros((ehi - elo,) + tuple(o.shape[1:]), dtype=o.dtype, device=o.device)
+        e[sb - elo:se - elo] = o
+        ext.append(e)
+    if dist is None:
+        for i, (sb, se) in enumerate(slabs):
+            elo, ehi = slab_halo_range(sb, se, ne0, R)
+            if i > 0:
+                k = sb - elo; ext[i][:k] = owned[i - 1][owned[i - 1].shape[0] - k:]
+            if i + 1 < len(slabs):
+                k = ehi - se; ext[i][se - elo:] = owned[i + 1][:k]
+        return ext
+    (sb, se), o, e = slabs[0], owned[0], ext[0]
+    elo, ehi = slab_halo_range(sb, se, ne0, R)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ops, kl, kr = [], sb - elo, ehi - se
+    assert o.shape[0] >= R, "a slab must hold at least R element layers"
+    lo_send = o[:R].contiguous(); hi_send = o[o.shape[0] - R:].contiguous()
+    lo_recv = torch.empty((kl,) + tuple(o.shape[1:]), dtype=o.dtype, device=o.device) if kl else None
+    hi_recv = torch.empty((kr,) + tuple(o.shape[1:]), dtype=o.dtype, device=o.device) if kr else None
+    if rank > 0: ops += [dist.P2POp(dist.isend, lo_send, rank - 1), dist.P2POp(dist.irecv, lo_recv, rank - 1)]
+    if rank + 1 < world: ops += [dist.P2POp(dist.isend, hi_send, rank + 1), dist.P2POp(dist.irecv, hi_recv, rank + 1)]
+    if ops:
+        for r in dist.batch_isend_irecv(ops): r.wait()
+    if kl: e[:kl] = lo_recv
+    if kr: e[se - elo:] = hi_recv
+    return ext
+
+
 class SlabProblem:
     """Compliance topology optimization (TopologyOptimizationProblem + MultigridComplianceObjective + TotalVolumeConstraint +
     OCOptimizer, TopologyOptimizationProblem.hh:17-155, OptimalityCriterion.hh:38-149) on a grid partitioned into slabs along axis 0
@@ -828,32 +870,7 @@ class SlabProblem:
 
     def _with_halo(self, owned):
         """Slab + halo arrays: owned layers from `owned` (one tensor per local part), halo layers from the neighbouring slabs."""
-        torch = self.torch
-        ext = []
-        for st, o in zip(self.st, owned):
-            e = torch.zeros((st["ehi"] - st["elo"], self.gne[1], self.gne[2]), dtype=torch.float64, device=self.dev)
-            e[st["sb"] - st["elo"]:st["se"] - st["elo"]] = o
-            ext.append(e)
-        if self.local:
-            for i, st in enumerate(self.st):
-                if i > 0:
-                    k = st["sb"] - st["elo"]; ext[i][:k] = owned[i - 1][owned[i - 1].shape[0] - k:]
-                if i + 1 < len(self.st):
-                    k = st["ehi"] - st["se"]; ext[i][st["se"] - st["elo"]:] = owned[i + 1][:k]
-        else:
-            st, o, e = self.st[0], owned[0], ext[0]
-            rank, world = self.dist.get_rank(), self.dist.get_world_size()
-            ops, kl, kr = [], st["sb"] - st["elo"], st["ehi"] - st["se"]
-            lo_send = o[:self.R].contiguous(); hi_send = o[o.shape[0] - self.R:].contiguous()
-            lo_recv = torch.empty((kl,) + tuple(o.shape[1:]), dtype=torch.float64, device=self.dev) if kl else None
-            hi_recv = torch.empty((kr,) + tuple(o.shape[1:]), dtype=torch.float64, device=self.dev) if kr else None
-            if rank > 0: ops += [self.dist.P2POp(self.dist.isend, lo_send, rank - 1), self.dist.P2POp(self.dist.irecv, lo_recv, rank - 1)]
-            if rank + 1 < world: ops += [self.dist.P2POp(self.dist.isend, hi_send, rank + 1), self.dist.P2POp(self.dist.irecv, hi_recv, rank + 1)]
-            if ops:
-                for r in self.dist.batch_isend_irecv(ops): r.wait()
-            if kl: e[:kl] = lo_recv
-            if kr: e[st["se"] - st["elo"]:] = hi_recv
-        return ext
+        return slab_halo_exchange(owned, [(st["sb"], st["se"]) for st in self.st], self.gne[0], self.R, None if self.local else self.dist)
 
     def _apply_filter(self, st, f, a):
         out = self.torch.empty_like(a)
