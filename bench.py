@@ -169,7 +169,8 @@ def main():
         # same workload as the GPU arm (256^3); each step is a bounded sample of it: the PCG capped at 2 iterations (about 20-40 s
         # per step on the box's host cores); warm-up capped at one step so that the default --steps/--warmup ends within minutes
         wl = args.workload or workload
-        cb = cpu_sample(wl, max(1, args.steps), max(0, min(args.warmup, 1)))
+        # all host threads, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+        cb = cpu_sample(wl, max(1, args.steps), max(0, min(args.warmup, 1)), threads=os.cpu_count())
         line = {"impl": "reference", "metric": "MG-PCG DOF*iterations per second (3D Q1, FMG-PCG, tol 1e-10)", "value": cb["value"], "unit": "DOF*iters/s",
                 "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -330,8 +331,8 @@ def main():
         print("  timed pass %.3f ms, instrumented pass %.3f ms (%d steps each)" % (ms, ms_prof, args.steps), file=sys.stderr)
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
-        cpu_baseline = cpu_sample(args.cpu_workload, 1, 1)
+    if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only
+        cpu_baseline = cpu_sample(args.cpu_workload, 1, 1, threads=os.cpu_count())
         cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     value = work / (ms * 1e-3)
