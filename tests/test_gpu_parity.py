@@ -310,3 +310,44 @@ def test_topopt_oc_iterations(capi, ne, dom, bc, data_dir):
         assert rel(gp.design_vars(), op.design_vars()) < 1e-6
         assert abs(gp.constraint()) <= 1e-6 + 1e-9            # OC postcondition (invariant 8)
     assert rel_l2(gp.u(), op.u()) < 1e-6
+
+
+def _voigt_rotation_z(theta):
+    """6x6 transformation of a Voigt-flattened (xx, yy, zz, yz, xz, xy; engineering shear) elasticity tensor under a rotation
+    about z: D' = T D T^T with T built from the rotation of the strain tensor."""
+    c, s = np.cos(theta), np.sin(theta)
+    R = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    idx = [(0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1)]
+    T = np.zeros((6, 6))
+    for a, (i, j) in enumerate(idx):
+        for b, (k, l) in enumerate(idx):
+            T[a, b] = R[i, k] * R[j, l] if k == l else R[i, k] * R[j, l] + R[i, l] * R[j, k]
+    return T
+
+
+@pytest.mark.parametrize("kind", ["orthotropic", "rotated"])
+def test_applyK_general_elasticity_tensor(capi, kind):
+    """setETensor with a non-isotropic material: an axis-aligned orthotropic tensor keeps the voxel's mirror symmetry (symmetry-
+    adapted kernel, general 3x3 blocks), the same tensor rotated by 30 degrees about z does not (dense kernel).  Both must apply
+    exactly the matrix assembled from the library's own K0 and moduli (independent numpy assembly, tests/npref.py)."""
+    import npref
+    D = np.diag([3.0, 2.0, 1.5, 0.6, 0.5, 0.4])
+    D[0, 1] = D[1, 0] = 0.7; D[0, 2] = D[2, 0] = 0.5; D[1, 2] = D[2, 1] = 0.4
+    if kind == "rotated":
+        T = _voigt_rotation_z(np.pi / 6)
+        D = T @ D @ T.T
+    ne = np.array([6, 4, 5])
+    g = capi.Sim(ne, np.zeros(3), np.array([1.5, 0.8, 1.0]))
+    g.set_elasticity_tensor(D)
+    g.set_interp(0, 1.0, 1e-3, 3.0, 3.0)
+    g.set_densities(RNG.uniform(0.1, 1.0, int(np.prod(ne))))
+    K0 = g.K0()
+    assert np.abs(K0 - K0.T).max() < 1e-14 * np.abs(K0).max()
+    t = np.tile(np.eye(3), (8, 1))                                     # the three rigid translations of an element
+    assert np.abs(K0 @ t).max() < 1e-13 * np.abs(K0).max()
+    K = npref.assemble_K(ne, K0, g.E())
+    u = RNG.normal(size=(g.num_nodes, 3))
+    ref = npref.dof_to_field(K @ npref.field_to_dof(u), 3)
+    assert rel(g.apply_K(u), ref) < 1e-12
+    b = RNG.normal(size=u.shape)
+    assert rel(g.apply_K(u, out=b, zero_init=False, negate=True), b - ref) < 1e-12
