@@ -26,9 +26,10 @@ def elasticity_D(N, E, nu):
     return D
 
 
-def k0_reference(N, h, E=1.0, nu=0.0):
-    """K0 = int_e B^T D B with B in engineering strains, 3-point Gauss (over-integrated on purpose)."""
-    D = elasticity_D(N, E, nu)
+def k0_reference(N, h, E=1.0, nu=0.0, D=None):
+    """K0 = int_e B^T D B with B in engineering strains, 3-point Gauss (over-integrated on purpose).  D: Voigt matrix in MeshFEM's
+    flattening order (xx, yy[, zz, yz, xz], xy), entries C_ijkl; default isotropic (E, nu)."""
+    D = elasticity_D(N, E, nu) if D is None else np.asarray(D, dtype=float)
     gp, gw = np.polynomial.legendre.leggauss(3)
     gp = 0.5 * (gp + 1)
     gw = 0.5 * gw

@@ -233,6 +233,7 @@ class OracleSim:
     def nn(self): return self.ne + 1
 
     def set_isotropic(self, E, nu): self.L.vfo_sim_set_isotropic(self.h, E, nu)
+    def set_elasticity_tensor(self, D): self.L.vfo_sim_set_D(self.h, np.ascontiguousarray(D, dtype=np.float64))   # setETensor (TensorProductSimulator.hh:343-347)
 
     def K0(self):
         ke = self.N * 2 ** self.N

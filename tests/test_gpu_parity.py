@@ -342,6 +342,8 @@ def test_applyK_general_elasticity_tensor(capi, kind):
     g.set_interp(0, 1.0, 1e-3, 3.0, 3.0)
     g.set_densities(RNG.uniform(0.1, 1.0, int(np.prod(ne))))
     K0 = g.K0()
+    o = OracleSim(ne, np.zeros(3), np.array([1.5, 0.8, 1.0])); o.set_elasticity_tensor(D)
+    assert rel(K0, o.K0()) < 1e-14                                    # same quadrature as the oracle (pinned on CPU against an independent one)
     assert np.abs(K0 - K0.T).max() < 1e-14 * np.abs(K0).max()
     t = np.tile(np.eye(3), (8, 1))                                     # the three rigid translations of an element
     assert np.abs(K0 @ t).max() < 1e-13 * np.abs(K0).max()

@@ -254,3 +254,29 @@ def test_vcycle_is_symmetric_operator(data_dir):
     Ma = mg.solve(z, a, 1, 1, True, True, False)
     Mb = mg.solve(z, b, 1, 1, True, True, False)
     assert abs((Ma * b).sum() - (Mb * a).sum()) < 1e-10 * abs((Ma * b).sum())
+
+
+@pytest.mark.parametrize("N,h", [(3, (0.25, 0.5, 0.125)), (2, (0.5, 0.25))])
+def test_K0_general_elasticity_tensor(N, h):
+    """setETensor with an orthotropic and with a fully populated symmetric positive-definite tensor: the oracle's 2-point Gauss K0
+    (exact for Q1 on a box) against an independent over-integrated B^T D B quadrature; K0 stays symmetric, annihilates rigid
+    translations, and reduces to the isotropic matrix for an isotropic D."""
+    ne = np.full(N, 4)
+    dom = np.array(h) * ne
+    fl = 6 if N == 3 else 3
+    rng = np.random.default_rng(8)
+    A = rng.normal(size=(fl, fl))
+    tensors = {"orthotropic": np.diag(rng.uniform(0.4, 3.0, fl)), "full": A @ A.T + fl * np.eye(fl), "isotropic": npref.elasticity_D(N, 1.3, 0.25)}
+    tensors["orthotropic"][:N, :N] += 0.3
+    for name, D in tensors.items():
+        s = OracleSim(ne, np.zeros(N), dom)
+        s.set_elasticity_tensor(D)
+        K0 = s.K0()
+        ref = npref.k0_reference(N, h, D=D)
+        assert np.abs(K0 - ref).max() < 1e-13 * np.abs(ref).max(), name
+        assert np.abs(K0 - K0.T).max() < 1e-15 * np.abs(K0).max()
+        t = np.tile(np.eye(N), (2 ** N, 1))
+        assert np.abs(K0 @ t).max() < 1e-13 * np.abs(K0).max()
+    s = OracleSim(ne, np.zeros(N), dom); s.set_isotropic(1.3, 0.25)
+    s2 = OracleSim(ne, np.zeros(N), dom); s2.set_elasticity_tensor(tensors["isotropic"])
+    assert np.abs(s.K0() - s2.K0()).max() == 0
