@@ -280,3 +280,37 @@ def test_K0_general_elasticity_tensor(N, h):
     s = OracleSim(ne, np.zeros(N), dom); s.set_isotropic(1.3, 0.25)
     s2 = OracleSim(ne, np.zeros(N), dom); s2.set_elasticity_tensor(tensors["isotropic"])
     assert np.abs(s.K0() - s2.K0()).max() == 0
+
+
+def test_fabrication_mask_arithmetic_and_masked_operator():
+    """Mask bookkeeping of the layer-by-layer path (TensorProductSimulator.hh:290-331, MultigridSolver.hh:1022-1036): with the mask
+    at fine element layer l, firstMaskedElementLayer = ceil(h / dy - 1e-10) = l and firstDetachedNodeLayer = l + 1; the coarse
+    levels get the same physical height, so a partially covered coarse element counts as unmasked; the masked operator equals the
+    operator of the same grid with zero moduli above the mask on every attached node and produces zeros on detached nodes."""
+    ne = np.array([4, 8, 4])
+    s = OracleSim(ne, np.zeros(3), ne.astype(float))
+    s.set_isotropic(1.0, 0.3); s.set_interp(0, 1.0, 1e-3, 3.0, 3.0)
+    rho = np.random.default_rng(9).uniform(0.2, 1.0, int(np.prod(ne)))
+    s.set_densities(rho)
+    mg = OracleMG(s, 2)
+    u = np.random.default_rng(10).normal(size=(s.num_nodes, 3))
+    for layer in (8, 5, 4, 1):
+        mg.set_mask_layer(layer)
+        assert s.mask_info() == (layer, layer + 1)
+        for lev in (1, 2):
+            fm = int(np.ceil(layer / 2 ** lev - 1e-10))
+            assert mg.get_sim(lev).mask_info() == (fm, fm + 1), (layer, lev)
+        # reference: same grid, no mask, zero moduli above the mask
+        E = s.E().reshape(tuple(ne))
+        assert (E[:, layer:] == 0).all() and (E[:, :layer] > 0).all()
+        K = npref.assemble_K(ne, s.K0(), E.ravel())
+        ref = npref.dof_to_field(K @ npref.field_to_dof(u), 3).reshape(5, 9, 5, 3)
+        got = s.apply_K(u).reshape(5, 9, 5, 3)
+        det = min(layer + 1, 9)
+        assert np.abs(got[:, :det] - ref[:, :det]).max() < 1e-13 * np.abs(ref).max()
+        assert (got[:, det:] == 0).all()
+    mg.set_mask_layer(8)
+    mg.decrement_mask(3)
+    assert s.mask_info() == (5, 6)
+    with pytest.raises(Exception):
+        mg.decrement_mask(6)
