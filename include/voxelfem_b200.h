@@ -55,6 +55,28 @@ int vf_version(void);
  * (bench.py reports it as gpu_launches). */
 int64_t vf_kernel_launch_count(void);
 void vf_reset_kernel_launch_count(void);
+/* Measured FP64 fused-multiply-add throughput of the current device in 1e12 DFMA/s (register-resident independent chains on
+ * every SM): the denominator of the FP64-pipe roofline bench.py reports next to the HBM one ("FP64 peak to be
+ * measured by the builder").  No reference equivalent. */
+int vf_measure_fp64_peak(double *tera_dfma_per_s);
+
+/* ---- section timers / tracing ----------------------------------------------------
+ * MeshFEM's global benchmark timer (3rdParty/MeshFEM/src/lib/MeshFEM/GlobalBenchmark.hh, Timer.hh) as bound by
+ * 3rdParty/MeshFEM/src/python_bindings/benchmark.cc:9-13.  Sections nest ("outer:inner"); the library opens the sections the
+ * reference opens around the same steps (CG Iterations, Preamble, V Cycle <l>, updateStiffnessMatrices, OC step, Bisection,
+ * setVars, Build load, Update load, Construct initial guess, Compute compliance, Compute gradient) and emits NVTX ranges of
+ * the same names.  Timing is off by default (a section drains the device when it closes): vf_benchmark_enable(1) or
+ * VF_BENCHMARK=1 turns it on. */
+void vf_benchmark_enable(int on);
+int vf_benchmark_enabled(void);
+void vf_benchmark_reset(void);
+void vf_benchmark_start_timer_section(const char *name);
+void vf_benchmark_stop_timer_section(const char *name);
+void vf_benchmark_start_timer(const char *name);
+void vf_benchmark_stop_timer(const char *name);
+void vf_benchmark_add_message(const char *msg);
+/* one line per section / timer: "path<TAB>seconds<TAB>(invocations)"; returns the length needed (excluding the 0) */
+size_t vf_benchmark_report(int include_messages, char *buf, size_t capacity);
 
 /* ---- TensorProductSimulator ------------------------------------------------------ */
 /* ctor, TensorProductSimulator.hh:209-279.  dim = 2 or 3. */
@@ -88,6 +110,7 @@ int vf_sim_add_dirichlet_box(vf_sim *s, const double *u, const double *box_min, 
 int vf_sim_apply_symmetry_conditions(vf_sim *s, int axes_mask, int max_face_mask);
 int vf_sim_get_dirichlet_mask(const vf_sim *s, uint8_t *mask_per_node);  /* getDirichletMask (:675-682), bit c = component c */
 int64_t vf_sim_num_force_nodes(const vf_sim *s);
+int64_t vf_sim_num_nonzero_dirichlet_values(const vf_sim *s);  /* prescribed non-zero displacements (getIntermediateFabricationShape validates them, :1893-1895) */
 int vf_sim_build_load_vector(vf_sim *s, double *f);                      /* buildLoadVector (:1269-1288) */
 /* applyK<ZeroInit,Negate> (:1410-1438 -> TPSStencils.hh:231-396, 431-728).
  * zero_init=1: out = K u; zero_init=0: out +=/-= K u (out is read). */
@@ -234,6 +257,12 @@ int vf_top_constraint_jacobian(vf_top *t, double *g);             /* evaluateCon
 int vf_top_get_u(vf_top *t, double *u);
 int vf_top_last_pcg_iterations(vf_top *t);
 int vf_top_oc_step(vf_top *t, double m, double p, double ctol, int *num_constraint_evals); /* OCOptimizer::step (OptimalityCriterion.hh:51-134) */
+/* Search half of OCOptimizer::step for problems whose virtual methods are overridden on the host (trampoline,
+ * python_bindings/VoxelFEM.cc:58-66; step(inplace = false), OptimalityCriterion.hh:57-60): dJ (host, numVars; NULL = the
+ * problem's own compliance gradient) is the caller's evaluateObjectiveGradientAndReturn(); the bracket/bisection (:95-129) runs
+ * on the device against the problem's own filter chain and constraint (evaluateOCConstraintAtVars is not virtual); the stepped
+ * variables come back in `stepped` (host) and are NOT set -- the caller invokes its own setVars (:133). */
+int vf_top_oc_search(vf_top *t, const double *dJ, double m, double p, double ctol, double *stepped, int *num_constraint_evals);
 int vf_top_get_lambda_bracket(vf_top *t, double *lo, double *hi);
 
 /* ---- Layer-by-layer evaluator ------------------------------------------------------ */
@@ -241,8 +270,14 @@ int vf_lbl_create(vf_mg *mg, vf_lbl **out);                       /* LayerByLaye
 int vf_lbl_destroy(vf_lbl *l);
 int vf_lbl_select_init_method(vf_lbl *l, const char *method);    /* selectInitMethod (:214-220): "zero", "constant", "fd", "N=k" */
 typedef void (*vf_lbl_callback)(int64_t layer, double compliance, int pcg_iterations, void *user);
+/* run (:223-296).  cb is the reference's lblCallback(l, compliance, grad_compliance, u) (:222, 277-279): the two arrays are not
+ * pushed through the callback but fetched on demand from inside it with vf_lbl_get_layer_gradient / vf_lbl_get_layer_u (no copy
+ * when the callback does not look at them).  pcg_cb is the it_callback handed to every layer's PCG (:265); inside it
+ * vf_mg_get_pcg_iterate / vf_mg_get_pcg_residual give (x, r) as for vf_mg_pcg. */
 int vf_lbl_run(vf_lbl *l, int zero_init, int64_t layer_increment, int max_iter, double tol, int mg_iterations,
-               int mg_smoothing_iterations, int fmg, vf_lbl_callback cb, void *user); /* run (:223-296) */
+               int mg_smoothing_iterations, int fmg, vf_lbl_callback cb, void *user, vf_pcg_callback pcg_cb, void *pcg_user);
+int vf_lbl_get_layer_u(vf_lbl *l, double *u);                     /* u of the layer just solved, component-major (numNodes x N) */
+int vf_lbl_get_layer_gradient(vf_lbl *l, double *g);              /* complianceGradientFlattened(u) of that layer (:278) */
 int vf_lbl_objective(vf_lbl *l, double *out);                     /* objective (:299) */
 int vf_lbl_gradient(vf_lbl *l, double *g);                        /* gradient (:300) */
 

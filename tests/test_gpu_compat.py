@@ -106,9 +106,19 @@ def test_layer_by_layer_flow(vf):
     mg = lbl_sim.multigridSolver(1)
     ev = vf.LayerByLayerEvaluator(lbl_sim)
     ev.selectInitMethod("N=3")
-    layers = []
-    ev.run(mg, True, 1, maxIter=50, tol=1e-8, it_callback=None, mgIterations=1, mgSmoothingIterations=1, fullMultigrid=False,
-           lblCallback=lambda layer, c, its: layers.append((layer, c, its)))
+    layers, pcg_its = [], []
+    # the reference's callback shapes: lblCallback(l, compliance, grad_compliance, u) (LayerByLayer.hh:222, 277-279) and the PCG
+    # it_callback(it, x, r) handed to every layer's solve (:265)
+    def lbl_cb(layer, c, grad, u):
+        assert grad.shape == (lbl_sim.numElements(),) and u.shape == (lbl_sim.numNodes(), 3)
+        assert np.abs(grad - lbl_sim.complianceGradient(u)).max() <= 1e-12 * np.abs(grad).max()
+        layers.append((layer, c, 0.5 * float((u * 0).sum())))
+    def it_cb(it, x, r):
+        assert x.shape == r.shape == (lbl_sim.numNodes(), 3)
+        pcg_its.append(it)
+    assert ev.run(mg, True, 1, maxIter=50, tol=1e-8, it_callback=it_cb, mgIterations=1, mgSmoothingIterations=1, fullMultigrid=False,
+                  lblCallback=lbl_cb) is None
+    assert len(pcg_its) >= 8 and pcg_its[0] == 1
     o = OracleSim(np.array(ne), np.zeros(3), np.array([1.0, 1.0, 0.5]))
     o.set_isotropic(1.0, 0.0); o.set_interp(1, 1.0, 1e-4, 3.0, 3.0)    # default material ETensor(1, 0)
     o.add_dirichlet([0, 0, 0], [-1, -1e-9, -1], [100, 1e-9, 100], 7); o.set_gravity(np.array([0, -1.0, 0])); o.set_densities(rho)

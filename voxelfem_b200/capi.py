@@ -30,6 +30,28 @@ class VoxelFEMError(RuntimeError):
     pass
 
 
+def _guarded(ctype, fn):
+    """ctypes prints and swallows exceptions raised inside callbacks: catch the first one here so that the caller can re-raise it
+    once the C call has returned (and skip the remaining invocations)."""
+    failed = []
+    if fn is None:
+        return ctype(), failed
+
+    def wrapper(*a):
+        if failed:
+            return
+        try:
+            fn(*a)
+        except BaseException as e:   # noqa: BLE001 -- re-raised by _reraise
+            failed.append(e)
+    return ctype(wrapper), failed
+
+
+def _reraise(failed):
+    if failed:
+        raise failed[0]
+
+
 def lib():
     """Load libvoxelfem_b200.so; fails loudly if the extension has not been built."""
     global _lib
@@ -48,6 +70,16 @@ def lib():
         "vf_version": (ci, []),
         "vf_kernel_launch_count": (i64, []),
         "vf_reset_kernel_launch_count": (None, []),
+        "vf_measure_fp64_peak": (ci, [C.POINTER(cd)]),
+        "vf_benchmark_enable": (None, [ci]),
+        "vf_benchmark_enabled": (ci, []),
+        "vf_benchmark_reset": (None, []),
+        "vf_benchmark_start_timer_section": (None, [C.c_char_p]),
+        "vf_benchmark_stop_timer_section": (None, [C.c_char_p]),
+        "vf_benchmark_start_timer": (None, [C.c_char_p]),
+        "vf_benchmark_stop_timer": (None, [C.c_char_p]),
+        "vf_benchmark_add_message": (None, [C.c_char_p]),
+        "vf_benchmark_report": (sz, [ci, C.c_char_p, sz]),
         "vf_sim_create": (ci, [ci, _ip, _dp, _dp, pvp]),
         "vf_sim_destroy": (ci, [vp]),
         "vf_sim_num_nodes": (i64, [vp]),
@@ -66,6 +98,7 @@ def lib():
         "vf_sim_apply_symmetry_conditions": (ci, [vp, ci, ci]),
         "vf_sim_get_dirichlet_mask": (ci, [vp, _u8p]),
         "vf_sim_num_force_nodes": (i64, [vp]),
+        "vf_sim_num_nonzero_dirichlet_values": (i64, [vp]),
         "vf_sim_build_load_vector": (ci, [vp, _dp]),
         "vf_sim_build_load_vector_dev": (ci, [vp, vp]),
         "vf_sim_apply_K": (ci, [vp, _dp, _dp, ci, ci]),
@@ -149,7 +182,10 @@ def lib():
         "vf_lbl_create": (ci, [vp, pvp]),
         "vf_lbl_destroy": (ci, [vp]),
         "vf_lbl_select_init_method": (ci, [vp, C.c_char_p]),
-        "vf_lbl_run": (ci, [vp, ci, i64, ci, cd, ci, ci, ci, LBL_CALLBACK, vp]),
+        "vf_lbl_run": (ci, [vp, ci, i64, ci, cd, ci, ci, ci, LBL_CALLBACK, vp, PCG_CALLBACK, vp]),
+        "vf_lbl_get_layer_u": (ci, [vp, _dp]),
+        "vf_lbl_get_layer_gradient": (ci, [vp, _dp]),
+        "vf_top_oc_search": (ci, [vp, vp, cd, cd, cd, _dp, C.POINTER(ci)]),
         "vf_lbl_objective": (ci, [vp, C.POINTER(cd)]),
         "vf_lbl_gradient": (ci, [vp, _dp]),
         "vf_mma_create": (ci, [i64, ci, _dp, _dp, pvp]),
@@ -383,6 +419,9 @@ class Sim(_Owned):
     def dirichlet_mask(self):
         out = np.zeros(self.num_nodes, dtype=np.uint8); _check(self.L.vf_sim_get_dirichlet_mask(self.h, out)); return out
 
+    def num_force_nodes(self): return int(self.L.vf_sim_num_force_nodes(self.h))
+    def has_nonzero_dirichlet_values(self): return int(self.L.vf_sim_num_nonzero_dirichlet_values(self.h)) != 0
+
     def build_load(self):
         f = np.zeros(self.num_nodes * self.N); _check(self.L.vf_sim_build_load_vector(self.h, f)); return from_soa(f, self.N)
 
@@ -478,8 +517,9 @@ class MG(_Owned):
         x = np.empty_like(u0)
         it = C.c_int(0)
         res = np.zeros(max(max_iter, 1) + 1)
-        cb = PCG_CALLBACK(lambda i, r, _u: callback(i, r)) if callback else PCG_CALLBACK()
+        cb, failed = _guarded(PCG_CALLBACK, (lambda i, r, _u: callback(i, r)) if callback else None)
         _check(self.L.vf_mg_pcg_io(self.h, u0, to_soa(b), x, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), int(dirichlet_ok), C.byref(it), res, cb, None))
+        _reraise(failed)
         return from_soa(x, self.N), it.value, res[:it.value]
 
     def pcg_dev(self, x_dev, b_dev, max_iter, tol, mg_iterations=1, mg_smoothing=1, fmg=False, dirichlet_ok=False):
@@ -487,6 +527,9 @@ class MG(_Owned):
         res = np.zeros(max(max_iter, 1) + 1)
         _check(self.L.vf_mg_pcg_dev(self.h, x_dev.ptr, b_dev.ptr, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), int(dirichlet_ok), C.byref(it), res, PCG_CALLBACK(), None))
         return it.value, res[:it.value]
+
+    def pcg_iterate(self):
+        out = np.zeros(self.nn(0) * self.N); _check(self.L.vf_mg_get_pcg_iterate(self.h, out)); return from_soa(out, self.N)
 
     def pcg_residual(self):
         out = np.zeros(self.nn(0) * self.N); _check(self.L.vf_mg_get_pcg_residual(self.h, out)); return from_soa(out, self.N)
@@ -664,6 +707,14 @@ class Problem(_Owned):
     def oc_step(self, m=0.2, p=0.5, ctol=1e-6):
         n = C.c_int(0); _check(self.L.vf_top_oc_step(self.h, m, p, ctol, C.byref(n))); return n.value
 
+    def oc_search(self, dJ=None, m=0.2, p=0.5, ctol=1e-6):
+        """Bracket + bisection of OCOptimizer::step with a caller-supplied objective gradient; returns the stepped variables
+        without setting them (vf_top_oc_search)."""
+        n = C.c_int(0); out = np.zeros(self.mg.sim.num_elements)
+        g = None if dJ is None else np.ascontiguousarray(dJ, dtype=np.float64).ravel()
+        _check(self.L.vf_top_oc_search(self.h, None if g is None else g.ctypes.data_as(C.c_void_p), m, p, ctol, out, C.byref(n)))
+        return out, n.value
+
     def lambda_bracket(self):
         a, b = C.c_double(), C.c_double(); _check(self.L.vf_top_get_lambda_bracket(self.h, C.byref(a), C.byref(b))); return a.value, b.value
 
@@ -696,16 +747,28 @@ class LBL(_Owned):
 
     def select_init_method(self, m): _check(self.L.vf_lbl_select_init_method(self.h, m.encode()))
 
-    def run(self, zero_init=True, layer_increment=1, max_iter=50, tol=1e-5, mg_iterations=1, mg_smoothing=1, fmg=False, callback=None):
+    def run(self, zero_init=True, layer_increment=1, max_iter=50, tol=1e-5, mg_iterations=1, mg_smoothing=1, fmg=False, callback=None,
+            pcg_callback=None):
+        """callback(layer, compliance, pcg_iterations) per layer -- layer_u() / layer_gradient() are valid inside it;
+        pcg_callback(it, residual_norm) per PCG iteration of every layer (mg.pcg_iterate() / mg.pcg_residual() valid inside)."""
         its, cs = [], []
 
         def _cb(layer, compliance, iters, _):
             its.append(iters); cs.append(compliance)
             if callback is not None:
                 callback(layer, compliance, iters)
-        cb = LBL_CALLBACK(_cb)
-        _check(self.L.vf_lbl_run(self.h, int(zero_init), layer_increment, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), cb, None))
+        cb, failed = _guarded(LBL_CALLBACK, _cb)
+        pcb, pfailed = _guarded(PCG_CALLBACK, (lambda i, r, _u: pcg_callback(i, r)) if pcg_callback else None)
+        _check(self.L.vf_lbl_run(self.h, int(zero_init), layer_increment, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), cb, None, pcb, None))
+        _reraise(failed); _reraise(pfailed)
         return np.array(its, dtype=np.int32), np.array(cs)
+
+    def layer_u(self):
+        n = self.mg.nn(0) * self.mg.N
+        out = np.zeros(n); _check(self.L.vf_lbl_get_layer_u(self.h, out)); return from_soa(out, self.mg.N)
+
+    def layer_gradient(self):
+        g = np.zeros(self.mg.sim.num_elements); _check(self.L.vf_lbl_get_layer_gradient(self.h, g)); return g
 
     def objective(self):
         v = C.c_double(0); _check(self.L.vf_lbl_objective(self.h, C.byref(v))); return v.value

@@ -178,12 +178,19 @@ class _TPS:
         if not 0 <= yfrac <= 1: raise RuntimeError("hfrac is out of bounds")
         ne = self._s.ne.copy(); full = int(ne[1]); nh = int(round(yfrac * full))
         if abs(yfrac * full - nh) > 1e-10: raise RuntimeError("hfrac chops off a noninteger number of element layers")
-        if validateBoundaryConditions and not np.any(self._gravity):
-            raise RuntimeError("Original simulator has unexpected boundary conditions for layer-by-layer simulation")
+        unexpected = RuntimeError("Original simulator has unexpected boundary conditions for layer-by-layer simulation")
+        if validateBoundaryConditions:      # TensorProductSimulator.hh:1885-1907
+            if not np.any(self._gravity): raise unexpected
+            if self._s.num_force_nodes() != 0: raise unexpected
+            m = self._s.dirichlet_mask().reshape(tuple(self._s.ne + 1))
+            full = (1 << self._N) - 1
+            base = np.take(m, 0, axis=1)
+            if np.any(base != full) or np.any(np.delete(m, 0, axis=1) != 0) or self._s.has_nonzero_dirichlet_values(): raise unexpected
         ne[1] = nh
         dmax = self._dmax.copy(); dmax[1] = self._dmin[1] + yfrac * (self._dmax[1] - self._dmin[1])
         r = _TPS((self._dmin, dmax), ne)
-        r._interp = dict(self._interp); r._interp["law"] = int(law); r._push_interp()
+        # law from the argument; E_min, E_0, gamma from the parent; the RAMP factor keeps its default (:1877-1883)
+        r._interp = dict(r._interp, law=int(law), Emin=self._interp["Emin"], E0=self._interp["E0"], gamma=self._interp["gamma"]); r._push_interp()
         r.ETensor = self._et
         self.transferDensitiesToIntermediateFabricationShape(r)
         g = self._gravity.copy()
@@ -275,8 +282,7 @@ class _MG:
             n = m.nn(0) * m.N
 
             def cb(it, rnorm):     # the reference hands (it, x, r) to the callback (MultigridSolver.hh:1043-1045, 1146-1147)
-                x = np.zeros(n); capi._check(m.L.vf_mg_get_pcg_iterate(m.h, x))
-                it_callback(it, capi.from_soa(x, m.N), m.pcg_residual())
+                it_callback(it, m.pcg_iterate(), m.pcg_residual())
         x, _, _ = m.pcg(u, b, int(maxIter), float(tol), int(mgIterations), int(mgSmoothingIterations), bool(fullMultigrid), False, cb)
         return x
 
@@ -289,7 +295,8 @@ def TensorProductSimulator(degreesPerDimension, domainBBox, elementsPerDimension
 
 
 def getClassName(simulator, name):
-    return "pyVoxelFEM.detail." + name + "_".join([""] + ["1"] * simulator._N)
+    # nameMangler (VoxelFEM.cc:33-35, 251-253): name + "1_1[_1]" (+ "" for double)
+    return "pyVoxelFEM.detail." + name + "_".join(["1"] * simulator._N)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -467,9 +474,16 @@ def TopologyOptimizationProblem(simulator, objective, constraints, filters): ret
 class _OCOptimizer:                      # OptimalityCriterion.hh:38-149
     def __init__(self, problem): self._pr = problem
     def step(self, m=0.2, p=0.5, ctol=1e-6, inplace=True):
-        if not inplace: raise NotImplementedError("OCOptimizer.step(inplace=False)")
-        self._pr._sync_solver()
-        self._pr._p.oc_step(m, p, ctol)
+        pr = self._pr
+        pr._sync_solver()
+        overridden = any(getattr(type(pr), n) is not getattr(_TOProblem, n) for n in ("setVars", "evaluateObjective", "evaluateObjectiveGradient"))
+        if inplace and not overridden:       # everything stays on the device (vf_top_oc_step)
+            pr._p.oc_step(m, p, ctol); return
+        # A Python subclass overrides the problem's virtual methods (trampoline, VoxelFEM.cc:58-66) or the caller asked for the
+        # out-of-place variant (:57-60): the objective gradient comes from the (possibly overridden) method, the multiplier search
+        # runs on the device against the problem's own chain and constraint, and the result goes through setVars (:133).
+        stepped, _ = pr._p.oc_search(pr.evaluateObjectiveGradient(), m, p, ctol)
+        pr.setVars(stepped)
 
 
 def OCOptimizer(problem): return _OCOptimizer(problem)
@@ -482,15 +496,18 @@ class _LBL:                              # LayerByLayer.hh:25-309
         if self._l is not None: self._l.select_init_method(method)
     def run(self, solver, zeroInit, layerIncrement, maxIter, tol, it_callback=None, mgIterations=1, mgSmoothingIterations=1,
             fullMultigrid=False, verbose=False, lblCallback=None):
-        if it_callback is not None: raise NotImplementedError("per-PCG-iteration callbacks inside LayerByLayerEvaluator.run")
         if self._l is None or self._l.mg is not solver._m:
             self._l = capi.LBL(solver._m); self._l.select_init_method(self._method)
-        cb = None
+        lbl, m = self._l, solver._m
+        cb = pcb = None
         if lblCallback is not None or verbose:
             def cb(layer, compliance, iters):
-                if verbose: print("layer %d: compliance %.10e, %d PCG iterations" % (layer, compliance, iters))
-                if lblCallback is not None: lblCallback(layer, compliance, iters)
-        return self._l.run(bool(zeroInit), int(layerIncrement), int(maxIter), float(tol), int(mgIterations), int(mgSmoothingIterations), bool(fullMultigrid), cb)
+                if verbose: print("Layer %d: %s" % (layer, repr(compliance)))        # LayerByLayer.hh:275-276
+                if lblCallback is not None: lblCallback(layer, compliance, lbl.layer_gradient(), lbl.layer_u())   # cb(l, compliance, grad_compliance, u) (:222, 277-279)
+        if it_callback is not None:
+            def pcb(it, rnorm): it_callback(it, m.pcg_iterate(), m.pcg_residual())      # (it, x, r), MultigridSolver.hh:1043-1045
+        self._its, self._compliances = lbl.run(bool(zeroInit), int(layerIncrement), int(maxIter), float(tol), int(mgIterations), int(mgSmoothingIterations),
+                                               bool(fullMultigrid), cb, pcb)             # the reference's run returns nothing
     def objective(self): return self._l.objective()
     def gradient(self): return self._l.gradient()
 

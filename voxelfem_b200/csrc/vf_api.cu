@@ -82,12 +82,15 @@ template<class T> struct DevBuf {
     DevBuf(const DevBuf &) = delete; DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    // The solver streams are non-blocking, i.e. NOT ordered against the legacy default stream the memset runs on: the memset is
+    // completed on the host side before anything else can be enqueued that touches the buffer.
+    static void zero_now(void *q, size_t bytes) { VF_CUDA(cudaMemset(q, 0, bytes)); VF_CUDA(cudaStreamSynchronize(0)); }
     void alloc(size_t count, bool zero = true) {
-        if (count == n && p) { if (zero) VF_CUDA(cudaMemset(p, 0, n * sizeof(T))); return; }
+        if (count == n && p) { if (zero) zero_now(p, n * sizeof(T)); return; }
         release();
         if (count == 0) return;
         VF_CUDA(cudaMalloc(&p, count * sizeof(T))); n = count;
-        if (zero) VF_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+        if (zero) zero_now(p, count * sizeof(T));
     }
     void upload(const T *h, size_t count, cudaStream_t s) { VF_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }
     void download(T *h, size_t count, cudaStream_t s) const { VF_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s)); VF_CUDA(cudaStreamSynchronize(s)); }
@@ -690,6 +693,7 @@ void mg_update_stiffness(vf_mg &lead, bool force = false) {
     bool stale = force;
     for (vf_mg *m : P) { mg_sync_level_masks(*m); stale = stale || m->stiffnessVersion != m->sim->version; }
     if (!stale) return;
+    TraceScope ts("updateStiffnessMatrices");                  // MultigridSolver.hh:854
     const int nl = lead.numLevels();
     const int T = lead.grp ? lead.firstRep : 0;   // levels 1..T are sub-assembled per part, then completed
     // A pending banded update recomputes only the coarse rows whose support meets the changed fine element layers: the range
@@ -774,6 +778,23 @@ void mg_residual(vf_mg &lead, int l, Field u, Field b, Field r) {
 void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward) {
     const int nc = 1 << lead.N;
     if (l > 0) mg_update_stiffness(lead);
+    if (l == 0 && lead.N == 3) {
+        // row-unit kernel (vf_gs0.cu): one launch per (x, y) parity class, both z-colours of a row inside the launch -- the same
+        // visiting order.  All parts of a group share the material and the z extent, so they take the same path.
+        bool rows = true;
+        for (vf_mg *mp : parts_of(lead)) rows = rows && gs_rows_supported(mp->grid(0), mp->sim->K0p);
+        if (rows) {
+            for (int i = 0; i < 4; ++i) {
+                const int gcls = forward ? i : 3 - i;          // global (x parity, y parity) class
+                for (vf_mg *mp : parts_of(lead)) {
+                    vf_mg &mg = *mp; const GridDesc &g = mg.grid(0);
+                    launch_gs_rows_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), gcls ^ ((g.xoff & 1) << 1), forward);
+                }
+                if (i & 1) grp_exchange(lead, l, u, (gcls >> 1) & 1);   // all planes of this x parity are final
+            }
+            return;
+        }
+    }
     for (int i = 0; i < nc; ++i) {
         const int color = forward ? i : (nc - 1 - i);
         for (vf_mg *mp : parts_of(lead)) {
@@ -820,7 +841,7 @@ void mg_vcycle(vf_mg &lead, int l, int nsmooth, bool residualSystem) {
     // firstRep + 1 times per FMG cycle with ~100 tiny launches each: replay it as a captured CUDA graph.  (The windowed levels stay
     // eager: capturing the NCCL ghost-plane exchanges deadlocked, see mg_pcg.)
     if (lead.grp && lead.grp->comm && l == lead.firstRep && l > 0 && residualSystem && !lead.inSubCapture && lead.useGraphs &&
-        !(lead.ctx.prof && lead.ctx.prof->enabled) && parts_of(lead).size() == 1) {
+        !(lead.ctx.prof && lead.ctx.prof->enabled) && !trace_enabled() && parts_of(lead).size() == 1) {
         static const bool enabled = [] { const char *e = std::getenv("VF_SUBGRAPH"); return !(e && e[0] == '0'); }();
         if (enabled) {
             mg_update_stiffness(lead);
@@ -845,6 +866,7 @@ void mg_vcycle(vf_mg &lead, int l, int nsmooth, bool residualSystem) {
             return;
         }
     }
+    TraceScope ts("V Cycle " + std::to_string(l));             // MultigridSolver.hh:618
     mg_enforce_dirichlet(lead, l, fx(l), residualSystem);
     for (int i = 0; i < nsmooth; ++i) mg_smooth(lead, l, fx(l), fb(l), true);
     mg_residual(lead, l, fx(l), fb(l), fr(l));
@@ -866,6 +888,7 @@ void mg_fmg(vf_mg &lead, int l, int nsmooth, bool residualSystem) {
 // solve (:546-573) operating on lv[0].x (initial guess already there) and lv[0].b
 void mg_solve_inplace(vf_mg &lead, int numSteps, int nsmooth, bool zeroDirichlet, bool fmg) {
     if (numSteps == 0) return;
+    TraceScope ts("MG Solver");                                // MultigridSolver.hh:549
     int start = 0;
     if (fmg) { mg_fmg(lead, 0, nsmooth, zeroDirichlet); start = 1; }
     for (int i = start; i < numSteps; ++i) mg_vcycle(lead, 0, nsmooth, zeroDirichlet);
@@ -909,6 +932,8 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
         if (cb) cb(1, rn, user);
         return;
     }
+    TraceScope tsCG("CG Iterations");                          // MultigridSolver.hh:1067
+    trace_push("Preamble");                                    // (:1077)
     for (vf_mg *m : P) {
         if (!dirichletOK) launch_enforce_dirichlet(m->ctx, m->sim->g.numNodes, N, (int)m->sim->dirNodes.size(), m->sim->dirNodesDev.p, m->sim->dirMaskDev.p, m->sim->dirValsDev.p, X(*m));
         launch_masked_dot(m->ctx, m->sim->g, B(*m), B(*m), m->scalars.p + SC_BSQ, m->scratch.p);
@@ -919,6 +944,7 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
     mg_dot(lead, r, r, SC_RSQ);
     const double bsq = read_scalar(lead, SC_BSQ);
     double rsq = read_scalar(lead, SC_RSQ);
+    trace_pop("Preamble");
     if (std::isnan(rsq)) throw std::logic_error("NaN encountered");
     int i = 0; bool first = true; int cur = SC_RMR_A, old = SC_RMR_B;
     while ((i++ < maxIter) && (rsq > tol * tol * bsq)) {
@@ -931,7 +957,7 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
             };
             // Slab groups stay eager: capturing the NCCL ghost-plane send/recv pairs of one rank into the graph deadlocked on
             // 2 GPUs (round 1), so the partitioned solve pays the launch latency of the small levels.
-            const bool graphable = lead.useGraphs && !lead.grp && !(lead.ctx.prof && lead.ctx.prof->enabled);
+            const bool graphable = lead.useGraphs && !lead.grp && !(lead.ctx.prof && lead.ctx.prof->enabled) && !trace_enabled();   // section timers drain the device: not capturable
             vf_mg::PrecondGraph &pg = lead.pg;
             const bool valid = pg.exec && pg.version == lead.sim->structVersion && pg.nActive == lead.sim->g.nActive && pg.mgIt == mgIterations &&
                                pg.nsmooth == mgSmoothing && pg.fmg == fmg && pg.sym == lead.symmetricGS;
@@ -957,9 +983,12 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
         }
         for (vf_mg *m : P) launch_zero_dirichlet(m->ctx, m->sim->g, m->dmask(0), s(*m));            // (:1122)
         std::swap(cur, old);
+        trace_push("CG direction");                                                                 // (:1121)
         mg_dot(lead, r, s, cur);                                                                    // r_Minv_r (:1124)
         for (vf_mg *m : P) launch_cg_direction(m->ctx, m->sim->g, s(*m), m->d.p, m->scalars.p + cur, m->scalars.p + old, first); // d = s + beta d (:1125-1126)
-        first = false;
+ first = false;
+        trace_pop("CG direction");
+        trace_push("CG update");                                                                    // (:1133)
         mg_apply_K(lead, 0, d, d, Ad, APPLY_SET, true);                                             // Ad = K d, zero Dirichlet (:1129-1130)
         mg_dot(lead, d, Ad, SC_DAD);                                                                // d . Ad (:1134); a reduction fused into the apply kernel measured slower (1.79 vs 1.10 + 0.11 ms at 256^3)
         grp_exchange(lead, 0, Ad);                                                                  // keeps r consistent on the ghost planes (r feeds the next restriction)
@@ -968,7 +997,8 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
         rsq = read_scalar(lead, SC_RSQ);
         if (std::isnan(rsq)) throw std::logic_error("NaN encountered at iteration" + std::to_string(i));
         lead.lastIters = i; lead.lastResiduals.push_back(std::sqrt(rsq));
-        if (cb) cb(i, std::sqrt(rsq), user);
+        trace_pop("CG update");
+        if (cb) { TraceScope tcb("Callback"); cb(i, std::sqrt(rsq), user); }                        // (:1148)
     }
 }
 void mg_pcg(vf_mg &mg, double *x, const double *b, int maxIter, double tol, int mgIterations, int mgSmoothing, bool fmg, bool dirichletOK,
@@ -1045,6 +1075,7 @@ int vf_device_count(int *count) { VF_TRY VF_CUDA(cudaGetDeviceCount(count)); VF_
 int vf_set_device(int device) { VF_TRY VF_CUDA(cudaSetDevice(device)); VF_CATCH }
 int64_t vf_kernel_launch_count(void) { return vf::g_launches.load(); }
 void vf_reset_kernel_launch_count(void) { vf::g_launches.store(0); }
+int vf_measure_fp64_peak(double *tera_dfma_per_s) { VF_TRY ensure_device(); *tera_dfma_per_s = vf::measure_dfma_peak(nullptr); VF_CATCH }
 
 // ---- simulator ----------------------------------------------------------------------------
 static vf_sim *sim_create_common(int dim, const int64_t *gne, const double *dmin, const double *dmax, bool window, int64_t slabBegin, int64_t slabEnd, vf_sim *share) {
@@ -1159,6 +1190,12 @@ int vf_sim_apply_symmetry_conditions(vf_sim *s, int axes_mask, int max_face_mask
         }
     }
     b.apply(); VF_CATCH
+}
+// number of Dirichlet components with a non-zero prescribed value (m_dirichletNodeDisplacements, TensorProductSimulator.hh:575-593)
+int64_t vf_sim_num_nonzero_dirichlet_values(const vf_sim *s) {
+    int64_t n = 0;
+    for (size_t k = 0; k < s->dirNodes.size(); ++k) for (int c = 0; c < s->N; ++c) if (((s->dirMask[k] >> c) & 1) && s->dirVals[k * s->N + c] != 0) ++n;
+    return n;
 }
 int vf_sim_get_dirichlet_mask(const vf_sim *s, uint8_t *m) { VF_TRY std::copy(s->nodeMask.begin(), s->nodeMask.end(), m); VF_CATCH }
 int64_t vf_sim_num_force_nodes(const vf_sim *s) { return (int64_t)s->forceNodes.size(); }
@@ -1579,11 +1616,12 @@ int vf_mg_debug_multicolor_visit(vf_mg *mg, int32_t *order) {
     VF_CATCH
 }
 
-int vf_dev_alloc(size_t n, double **out) { VF_TRY ensure_device(); VF_CUDA(cudaMalloc(out, n * sizeof(double))); VF_CUDA(cudaMemset(*out, 0, n * sizeof(double))); VF_CATCH }
+// Device-buffer helpers: complete on return (they run on the legacy default stream, which the non-blocking solver streams are not ordered against).
+int vf_dev_alloc(size_t n, double **out) { VF_TRY ensure_device(); VF_CUDA(cudaMalloc(out, n * sizeof(double))); VF_CUDA(cudaMemset(*out, 0, n * sizeof(double))); VF_CUDA(cudaStreamSynchronize(0)); VF_CATCH }
 int vf_dev_free(double *p) { VF_TRY VF_CUDA(cudaFree(p)); VF_CATCH }
-int vf_dev_upload(double *dev, const double *host, size_t n) { VF_TRY VF_CUDA(cudaMemcpy(dev, host, n * sizeof(double), cudaMemcpyHostToDevice)); VF_CATCH }
-int vf_dev_download(double *host, const double *dev, size_t n) { VF_TRY VF_CUDA(cudaMemcpy(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost)); VF_CATCH }
-int vf_dev_memset_zero(double *dev, size_t n) { VF_TRY VF_CUDA(cudaMemset(dev, 0, n * sizeof(double))); VF_CATCH }
+int vf_dev_upload(double *dev, const double *host, size_t n) { VF_TRY VF_CUDA(cudaMemcpy(dev, host, n * sizeof(double), cudaMemcpyHostToDevice)); VF_CUDA(cudaStreamSynchronize(0)); VF_CATCH }
+int vf_dev_download(double *host, const double *dev, size_t n) { VF_TRY VF_CUDA(cudaDeviceSynchronize()); VF_CUDA(cudaMemcpy(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost)); VF_CATCH }
+int vf_dev_memset_zero(double *dev, size_t n) { VF_TRY VF_CUDA(cudaMemset(dev, 0, n * sizeof(double))); VF_CUDA(cudaStreamSynchronize(0)); VF_CATCH }
 void *vf_mg_stream(vf_mg *mg) { return (void *)mg->ctx.stream; }
 int vf_mg_synchronize(vf_mg *mg) { VF_TRY VF_CUDA(cudaStreamSynchronize(mg->ctx.stream)); VF_CATCH }
 
@@ -1717,6 +1755,7 @@ struct vf_top {
         lastPcgIters = mg->lastIters;
     }
     void setVarsDev() { // FilterChain::setDesignVars (:142-152) + updateCache
+        TraceScope ts("setVars");                              // TopologyOptimizationProblem.hh:42
         for (size_t i = 0; i < filters.size(); ++i) applyFilter(filters[i], vars[i]->p, vars[i + 1]->p);
         updateCache(vars.back()->p);
     }
@@ -1730,10 +1769,12 @@ struct vf_top {
         if (a != g.p) VF_CUDA(cudaMemcpyAsync(g.p, a, sizeof(double) * ne(), cudaMemcpyDeviceToDevice, mg->ctx.stream));
     }
     void objectiveGradient() { // into dJ
+        TraceScope ts("evaluateObjectiveGradient");            // TopologyOptimizationProblem.hh:78
         launch_compliance_gradient(mg->ctx, sim->g, sim->K0p, u.p, sim->rho.p, dJ.p, sim->law, sim->E0, sim->Emin, sim->gamma, sim->q, sim->gravity, sim->elemVolume(), false);
         backprop(dJ, tmp);
     }
     void constraintJacobian() { // into dc (TopologyOptimizationConstraint.hh:34-36)
+        TraceScope ts("evaluateConstraintsJacobian");          // TopologyOptimizationProblem.hh:107
         launch_fill(mg->ctx, ne(), -1.0 / (volFrac * double(ne())), dc.p);
         backprop(dc, tmp);
     }
@@ -1781,9 +1822,8 @@ int vf_top_get_u(vf_top *t, double *u) { VF_TRY d2h(u, t->u.p, t->u.n, t->mg->ct
 int vf_top_last_pcg_iterations(vf_top *t) { return t->lastPcgIters; }
 int vf_top_get_lambda_bracket(vf_top *t, double *lo, double *hi) { *lo = t->lamMin; *hi = t->lamMax; return 0; }
 // OCOptimizer::step (OptimalityCriterion.hh:51-134)
-int vf_top_oc_step(vf_top *t, double m, double p, double ctol, int *nevalsOut) {
-    VF_TRY
-    t->objectiveGradient(); t->constraintJacobian();
+static int oc_bisect(vf_top *t, double m, double p, double ctol) {   // bracket + bisection of OCOptimizer::step (:95-129) on t->dJ, t->dc; result in t->stepped
+    TraceScope ts("Bisection");                                // OptimalityCriterion.hh:91
     int nevals = 0;
     auto ceval = [&](double lam) { ++nevals; return t->ceval(lam, m, p); };
     const double dilation = 32;
@@ -1804,10 +1844,31 @@ int vf_top_oc_step(vf_top *t, double m, double p, double ctol, int *nevalsOut) {
         if (violation < 0) t->lamMin = mid;
         if (violation > 0) t->lamMax = mid;
     } while (true);
+    return nevals;
+}
+int vf_top_oc_step(vf_top *t, double m, double p, double ctol, int *nevalsOut) {
+    VF_TRY
+    TraceScope ts("OC step");                                  // OptimalityCriterion.hh:52
+    t->objectiveGradient(); t->constraintJacobian();
+    const int nevals = oc_bisect(t, m, p, ctol);
     // m_p.setVars(m_steppedVars) (:133)
     VF_CUDA(cudaMemcpyAsync(t->vars[0]->p, t->stepped.p, sizeof(double) * t->ne(), cudaMemcpyDeviceToDevice, t->mg->ctx.stream));
     t->setVarsDev();
     VF_CUDA(cudaStreamSynchronize(t->mg->ctx.stream));
+    if (nevalsOut) *nevalsOut = nevals;
+    VF_CATCH
+}
+// The search half of OCOptimizer::step for problems whose virtual methods are overridden on the host (the trampoline of
+// python_bindings/VoxelFEM.cc:58-66; step(inplace = false), OptimalityCriterion.hh:57-60): the objective gradient comes from the
+// caller (evaluateObjectiveGradientAndReturn), the constraint is the problem's own (evaluateOCConstraintAtVars is not virtual), and
+// the stepped variables are returned instead of being set -- the caller then invokes its (possibly overridden) setVars (:133).
+int vf_top_oc_search(vf_top *t, const double *dJ, double m, double p, double ctol, double *stepped, int *nevalsOut) {
+    VF_TRY
+    TraceScope ts("OC step");
+    if (dJ) h2d(t->dJ.p, dJ, (size_t)t->ne(), t->mg->ctx.stream); else t->objectiveGradient();
+    t->constraintJacobian();
+    const int nevals = oc_bisect(t, m, p, ctol);
+    d2h(stepped, t->stepped.p, (size_t)t->ne(), t->mg->ctx.stream);
     if (nevalsOut) *nevalsOut = nevals;
     VF_CATCH
 }
@@ -1827,7 +1888,7 @@ struct vf_lbl {
     int method = 2; // 0 zero, 1 FD, 2 subspace
     size_t maxHist = 3;
     std::vector<std::unique_ptr<DevBuf<double>>> hist; // front = most recent
-    DevBuf<double> f, u, uFull, w, totalGrad, scalar, scratch;
+    DevBuf<double> f, u, uFull, w, totalGrad, layerGrad, scalar, scratch;
     bool uValid = false, uFullValid = false;
     double totalCompliance = 0; long long layersAccumulated = 0;
     double *hostScalar = nullptr;
@@ -1922,7 +1983,8 @@ int vf_lbl_select_init_method(vf_lbl *l, const char *method) { // selectInitMeth
     l->hist.clear(); VF_CATCH
 }
 // LayerByLayerEvaluator::run (:223-296)
-int vf_lbl_run(vf_lbl *l, int zeroInit, int64_t layerIncrement, int maxIter, double tol, int mgIt, int mgSmooth, int fmg, vf_lbl_callback cb, void *user) {
+int vf_lbl_run(vf_lbl *l, int zeroInit, int64_t layerIncrement, int maxIter, double tol, int mgIt, int mgSmooth, int fmg, vf_lbl_callback cb, void *user,
+               vf_pcg_callback pcgCb, void *pcgUser) {
     VF_TRY
     vf_mg &mg = *l->mg; vf_sim &sim = *l->sim;
     const int64_t numLayers = sim.ne[1];
@@ -1933,24 +1995,30 @@ int vf_lbl_run(vf_lbl *l, int zeroInit, int64_t layerIncrement, int maxIter, dou
     l->hist.clear();                                           // m_initGen->reset() (:237)
     l->layersAccumulated = 0; l->totalCompliance = 0; l->layerIters.clear();
     l->totalGrad.alloc(sim.g.numElems, true);
-    if (int rc = vf_mg_set_mask_layer(&mg, numLayers)) return rc; // (:244)
+    trace_push("Build load");                                  // (:243)
+    if (int rc = vf_mg_set_mask_layer(&mg, numLayers)) { trace_pop("Build load"); return rc; } // (:244)
     if (l->f.n != len) l->f.alloc(len, true);
     sim_build_load_dev(sim, l->f.p);                           // (:245)
+    trace_pop("Build load");
     for (int64_t layer = numLayers; layer > 0; layer -= std::min(layerIncrement, layer)) {
         if (layer < numLayers) {
             if (int rc = vf_mg_decrement_mask(&mg, (int)layerIncrement)) return rc;               // (:250)
             const double g2 = sim.gravity[0] * sim.gravity[0] + sim.gravity[1] * sim.gravity[1] + sim.gravity[2] * sim.gravity[2];
             if (g2 == 0 || std::abs(g2 - sim.gravity[1] * sim.gravity[1]) > 1e-10) throw std::runtime_error("Unexpected gravity vector");
+            TraceScope tl("Update load");                                                        // (:251)
             launch_self_weight_load(mg.ctx, sim.g, sim.rho.p, sim.gravity, sim.elemVolume(), l->f.p, (int)layer, (int)(layer + layerIncrement), -1.0); // (:252)
         }
-        if (layer < numLayers || !l->uValid) l->constructGuess();                                  // (:259-260)
+        if (layer < numLayers || !l->uValid) { TraceScope tg("Construct initial guess"); l->constructGuess(); } // (:258-260)
         try {
-            mg_pcg(mg, l->u.p, l->f.p, maxIter, tol, mgIt, mgSmooth, fmg != 0, /* dirichletAlreadySatisfied */ true, nullptr, nullptr); // (:265)
+            mg_pcg(mg, l->u.p, l->f.p, maxIter, tol, mgIt, mgSmooth, fmg != 0, /* dirichletAlreadySatisfied */ true, pcgCb, pcgUser); // (:265)
         } catch (const std::exception &e) { throw std::runtime_error(std::string("PCG exception ") + e.what() + " at l = " + std::to_string(layer)); }
         l->layerIters.push_back(mg.lastIters);
+        trace_push("Compute compliance");                                                          // (:272)
         const double compliance = l->maskedDot(l->f.p, l->u.p);                                    // (:273)
+        trace_pop("Compute compliance");
         if (cb) cb(layer, compliance, mg.lastIters, user);
         l->totalCompliance += compliance;
+        TraceScope tgr("Compute gradient");                                                        // (:282)
         launch_compliance_gradient(mg.ctx, sim.g, sim.K0p, l->u.p, sim.rho.p, l->totalGrad.p, sim.law, sim.E0, sim.Emin, sim.gamma, sim.q, sim.gravity, sim.elemVolume(), true); // (:283)
         ++l->layersAccumulated;
         if (layer == numLayers) { if (l->uFull.n != len) l->uFull.alloc(len, false); VF_CUDA(cudaMemcpyAsync(l->uFull.p, l->u.p, sizeof(double) * len, cudaMemcpyDeviceToDevice, mg.ctx.stream)); l->uFullValid = true; }
@@ -1958,6 +2026,15 @@ int vf_lbl_run(vf_lbl *l, int zeroInit, int64_t layerIncrement, int maxIter, dou
     }
     VF_CUDA(cudaStreamSynchronize(mg.ctx.stream));
     VF_CATCH
+}
+// Inside a vf_lbl_callback: the layer's displacement and its compliance gradient, the last two arguments of the reference's
+// lblCallback(l, compliance, grad_compliance, u) (LayerByLayer.hh:222, 277-279) -- fetched only when the callback asks for them.
+int vf_lbl_get_layer_u(vf_lbl *l, double *u) { VF_TRY d2h(u, l->u.p, l->len(), l->mg->ctx.stream); VF_CATCH }
+int vf_lbl_get_layer_gradient(vf_lbl *l, double *g) {
+    VF_TRY vf_sim &sim = *l->sim; vf_mg &mg = *l->mg;
+    if (l->layerGrad.n != (size_t)sim.g.numElems) l->layerGrad.alloc(sim.g.numElems, false);
+    launch_compliance_gradient(mg.ctx, sim.g, sim.K0p, l->u.p, sim.rho.p, l->layerGrad.p, sim.law, sim.E0, sim.Emin, sim.gamma, sim.q, sim.gravity, sim.elemVolume(), false); // complianceGradientFlattened(u)
+    d2h(g, l->layerGrad.p, (size_t)sim.g.numElems, mg.ctx.stream); VF_CATCH
 }
 int vf_lbl_objective(vf_lbl *l, double *out) { *out = 0.5 * l->totalCompliance / double(l->layersAccumulated); return 0; } // (:299)
 int vf_lbl_gradient(vf_lbl *l, double *g) { // (:300)

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <mutex>
 
 namespace vf {
 
@@ -78,6 +79,10 @@ struct K0Param {
     double kh[8][3][3];
     int walsh;      // 1 if K0 is block diagonal in that basis (orthotropic material aligned with the grid)
     int sparse7;    // 1 if additionally the trilinear mode (s = 7) of a component only couples with itself
+    // The same mirror symmetry in the nodal basis: K0[(m,c),(m^D,d)] = s(m,c,d) vt[D][3c+d] with s = +1 for c == d and
+    // (-1)^(m_c + m_d) otherwise (m_a = coordinate of local node m along axis a): 72 numbers instead of 576, each shared by the
+    // 8 incident elements of a node.  Rows padded to 10 doubles so that constant-bank pairs are 16-byte aligned.
+    double vt[8][10];
 };
 // Passed by value to the Walsh-basis kernels (constant-bank operands).
 struct KhatParam { double v[8][3][3]; };
@@ -169,6 +174,16 @@ struct ProfScope {
     ~ProfScope() { prof_end(c, cat); }
 };
 
+// vf_trace.cu: section timers + NVTX ranges under the reference's section names (GlobalBenchmark.hh, Timer.hh)
+void trace_push(const char *name);
+void trace_pop(const char *name);
+bool trace_enabled();
+struct TraceScope {   // BENCHMARK_SCOPED_TIMER_SECTION
+    std::string name;
+    explicit TraceScope(std::string n) : name(std::move(n)) { trace_push(name.c_str()); }
+    ~TraceScope() { trace_pop(name.c_str()); }
+};
+
 inline void cuda_check(cudaError_t e, const char *what, const char *file, int line) {
     if (e != cudaSuccess) {
         throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" + std::to_string(line) + ")");
@@ -176,6 +191,20 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
 }
 #define VF_CUDA(x) ::vf::cuda_check((x), #x, __FILE__, __LINE__)
 #define VF_KERNEL_CHECK() ::vf::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+
+// Per-device one-time setup (function attributes, lookup tables): kernels' attributes and device allocations belong to ONE device,
+// and a process may drive several (vf_set_device).  first_use_on_device(flags) is true exactly once per device and flag array.
+constexpr int kMaxDevices = 64;
+struct PerDeviceFlags { bool done[kMaxDevices] = {}; std::mutex m; };
+inline int current_device() { int d = 0; cuda_check(cudaGetDevice(&d), "cudaGetDevice", __FILE__, __LINE__); return d; }
+inline bool first_use_on_device(PerDeviceFlags &f) {
+    const int d = current_device();
+    std::lock_guard<std::mutex> lock(f.m);
+    if (d < 0 || d >= kMaxDevices) return true;
+    if (f.done[d]) return false;
+    f.done[d] = true;
+    return true;
+}
 
 // ---------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  Kernels of the solve path start with pdl_prologue(): griddepcontrol.launch_dependents
@@ -218,6 +247,17 @@ void launch_apply_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, 
 // One colour pass of the block Gauss-Seidel smoother at level 0.
 void launch_gs_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, double *u, const double *b, const double *E,
                   const uint8_t *dmask, int color, bool forward);
+
+// --- vf_gs0.cu: level-0 smoother on row units (3D, mirror-symmetric K0)
+// One smoothing sweep (all 8 colours in the reference order) as 4 launches: one per (x, y) parity class of node rows; a thread block
+// stages the 9 neighbouring u rows, b and the 4 adjacent modulus rows of one z-row in shared memory (cp.async, parity-split) and
+// runs both z-colours of the row.  gs_rows_supported(): whether the kernel covers this grid / material.
+bool gs_rows_supported(const GridDesc &g, const K0Param &K);
+// cls: 0..3, the (x parity, y parity) = (cls >> 1, cls & 1) class in LOCAL parities of the window
+void launch_gs_rows_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, double *u, const double *b, const double *E,
+                       const uint8_t *dmask, int cls, bool forward);
+// measured FP64 FMA throughput (T DFMA/s) of the device: independent register-resident DFMA chains on every SM
+double measure_dfma_peak(cudaStream_t stream);
 
 // One colour pass, two nodes per thread (3D only).
 void launch_gs3_color_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K, double *u, const double *b, const double *E,

@@ -485,6 +485,14 @@ void finalize_k0_param(K0Param &K, int N) {
         K.kh[s1 ^ (4 >> c1)][c1][c2] = v;
         if (c1 != c2 && (s1 == 7 || s2 == 7) && std::fabs(v) > tol) s7 = false;
     }
+    // nodal form of the same symmetry (used by the row-unit smoother, vf_gs0.cu); valid whenever the Walsh form is block diagonal
+    std::memset(K.vt, 0, sizeof(K.vt));
+    for (int D = 0; D < 8; ++D) for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) K.vt[D][3 * c + d] = K.v[c * 24 + 3 * D + d];
+    for (int e = 0; e < 8 && blockDiag; ++e) for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) for (int D = 0; D < 8; ++D) {
+        const int ec = (e >> (2 - c)) & 1, ed = (e >> (2 - d)) & 1;
+        const double sg = (c == d || ((ec + ed) & 1) == 0) ? 1.0 : -1.0;
+        if (std::fabs(K.v[(3 * e + c) * 24 + 3 * (e ^ D) + d] - sg * K.vt[D][3 * c + d]) > 64 * tol) blockDiag = false;
+    }
     const char *env = std::getenv("VF_L0_DENSE");
     K.walsh = blockDiag && !(env && env[0] == '1');
     K.sparse7 = s7;

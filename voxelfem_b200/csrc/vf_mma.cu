@@ -223,7 +223,7 @@ __global__ void k_mma_step_eval(Ptrs P, double t, double eps, Small lam, RedSpec
 template<class T> struct Buf {
     T *p = nullptr; size_t n = 0;
     ~Buf() { if (p) cudaFree(p); }
-    void alloc(size_t cnt) { if (p) cudaFree(p); p = nullptr; n = cnt; if (cnt) { VF_CUDA(cudaMalloc(&p, cnt * sizeof(T))); VF_CUDA(cudaMemset(p, 0, cnt * sizeof(T))); } }
+    void alloc(size_t cnt) { if (p) cudaFree(p); p = nullptr; n = cnt; if (cnt) { VF_CUDA(cudaMalloc(&p, cnt * sizeof(T))); VF_CUDA(cudaMemset(p, 0, cnt * sizeof(T))); VF_CUDA(cudaStreamSynchronize(0)); } }   // complete before the (non-blocking) optimizer stream touches it
 };
 
 } // namespace

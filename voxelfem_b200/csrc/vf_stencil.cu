@@ -207,15 +207,14 @@ template<typename Kern> static void prefer_shared(Kern k) {
     VF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 }
 static void stencil_kernel_attributes() {
-    static bool done = false;
-    if (done) return;
+    static PerDeviceFlags done;
+    if (!first_use_on_device(done)) return;
 #define VF_ATTR(NN_, M) prefer_shared(k_stencil_tile<NN_, false, M, 1>); prefer_shared(k_stencil_tile<NN_, false, M, 3>);
     VF_ATTR(3, APPLY_SET) VF_ATTR(3, APPLY_ADD) VF_ATTR(3, APPLY_SUB) VF_ATTR(3, APPLY_RESIDUAL)
     VF_ATTR(2, APPLY_SET) VF_ATTR(2, APPLY_ADD) VF_ATTR(2, APPLY_SUB) VF_ATTR(2, APPLY_RESIDUAL)
 #undef VF_ATTR
     prefer_shared(k_stencil_tile<3, true, APPLY_SET, 1>); prefer_shared(k_stencil_tile<2, true, APPLY_SET, 1>);
     prefer_shared(k_stencil_tile<3, true, APPLY_SET, 3>); prefer_shared(k_stencil_tile<2, true, APPLY_SET, 3>);
-    done = true;
 }
 
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,

@@ -254,10 +254,13 @@ k_filter_smooth3_tiled(const __grid_constant__ FilterDesc fd, const FilterTap *_
         if (cx < fd.sz[0]) out[((long long)cx * fd.sz[1] + cy) * fd.sz[2] + cz] = acc[k] * fd.invTotalWeight;
     }
 }
-struct FilterTapCache { int radius = -1, type = -1, n = 0; FilterTap *dev = nullptr; };
+struct FilterTapCache { int radius = -1, type = -1, n = 0, device = -1; FilterTap *dev = nullptr; };
 static const FilterTap *filter_taps3(int radius, int type, int &ntaps, cudaStream_t stream) {
-    static FilterTapCache cache[8];
-    for (auto &c : cache) if (c.radius == radius && c.type == type) { ntaps = c.n; return c.dev; }
+    static FilterTapCache cache[32];          // keyed by (device, radius, type): the table lives in that device's memory
+    static std::mutex cacheMutex;
+    std::lock_guard<std::mutex> lock(cacheMutex);
+    const int device = current_device();
+    for (auto &c : cache) if (c.radius == radius && c.type == type && c.device == device) { ntaps = c.n; return c.dev; }
     FilterTapCache *slot = nullptr;
     for (auto &c : cache) if (c.radius < 0) { slot = &c; break; }
     if (!slot) return nullptr;
@@ -271,7 +274,7 @@ static const FilterTap *filter_taps3(int radius, int type, int &ntaps, cudaStrea
     VF_CUDA(cudaMalloc(&slot->dev, h.size() * sizeof(FilterTap)));
     VF_CUDA(cudaMemcpyAsync(slot->dev, h.data(), h.size() * sizeof(FilterTap), cudaMemcpyHostToDevice, stream));
     VF_CUDA(cudaStreamSynchronize(stream));
-    slot->radius = radius; slot->type = type; slot->n = (int)h.size();
+    slot->radius = radius; slot->type = type; slot->n = (int)h.size(); slot->device = device;
     ntaps = slot->n;
     return slot->dev;
 }
@@ -296,8 +299,8 @@ void launch_filter_smooth(const LaunchCtx &ctx, int N, const int *sizes, int rad
         const FilterTap *taps = filter_taps3(radius, type, ntaps, ctx.stream);
         if (taps) {
             const size_t tile = (size_t)(kFtX + 2 * radius) * (kFtY + 2 * radius) * (kFtZ + 2 * radius) * sizeof(double);
-            static bool attr = false;
-            if (!attr) { VF_CUDA(cudaFuncSetAttribute(k_filter_smooth3_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+            static PerDeviceFlags attr;
+            if (first_use_on_device(attr)) VF_CUDA(cudaFuncSetAttribute(k_filter_smooth3_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             dim3 bt(32, 4, 2), gt((fd.sz[2] + kFtZ - 1) / kFtZ, (fd.sz[1] + kFtY - 1) / kFtY, (fd.sz[0] + kFtX - 1) / kFtX);
             k_filter_smooth3_tiled<<<gt, bt, tile, ctx.stream>>>(fd, taps, ntaps, in, out);
             VF_KERNEL_CHECK();

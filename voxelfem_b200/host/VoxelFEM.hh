@@ -24,6 +24,8 @@
 #include <cstdint>
 #include <fstream>
 #include <functional>
+#include <iostream>
+#include <exception>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -352,16 +354,18 @@ public:
         if (spec.empty()) spec.push_back(0.0);
         check(vf_top_create(m_objective->mgHandle(), (int)filters.size(), spec.data(), tvc->m_volumeFraction, &m_h));
     }
-    ~TopologyOptimizationProblem() { if (m_h) vf_top_destroy(m_h); }
+    virtual ~TopologyOptimizationProblem() { if (m_h) vf_top_destroy(m_h); }
+    // true for subclasses that override setVars / evaluateObjective / evaluateObjectiveGradientAndReturn on the host (the python trampoline)
+    virtual bool hasHostOverrides() const { return false; }
     TopologyOptimizationProblem(const TopologyOptimizationProblem &) = delete;
     TopologyOptimizationProblem &operator=(const TopologyOptimizationProblem &) = delete;
 
     size_t numVars() const { return m_sim.numElements(); }
-    bool setVars(const VXd &x, bool /* forceUpdate */ = false) { syncSolver(); if (x.size() != numVars()) throw std::runtime_error("Size mismatch"); check(vf_top_set_vars(m_h, x.data())); return true; }
+    virtual bool setVars(const VXd &x, bool /* forceUpdate */ = false) { syncSolver(); if (x.size() != numVars()) throw std::runtime_error("Size mismatch"); check(vf_top_set_vars(m_h, x.data())); return true; }
     VXd getVars() const { VXd r(numVars()); check(vf_top_get_vars(m_h, 0, r.data())); return r; }
     VXd getDensities() const { VXd r(numVars()); check(vf_top_get_vars(m_h, 1, r.data())); return r; }
-    double evaluateObjective() const { double v = 0; check(vf_top_compliance(m_h, &v)); return v; }
-    VXd evaluateObjectiveGradientAndReturn() const { VXd g(numVars()); check(vf_top_objective_gradient(m_h, g.data())); return g; }
+    virtual double evaluateObjective() const { double v = 0; check(vf_top_compliance(m_h, &v)); return v; }
+    virtual VXd evaluateObjectiveGradientAndReturn() const { VXd g(numVars()); check(vf_top_objective_gradient(m_h, g.data())); return g; }
     VXd evaluateConstraints() const { double v = 0; check(vf_top_constraint(m_h, &v)); return VXd(1, v); }
     VXd evaluateConstraintsJacobianAndReturn() const { VXd g(numVars()); check(vf_top_constraint_jacobian(m_h, g.data())); return g; }
     VField displacement() const { VField u(m_sim.numNodes(), Sim::N); check(vf_top_get_u(m_h, u.data())); return u; }
@@ -382,9 +386,19 @@ template<typename Problem>
 class OCOptimizer {                                               // OptimalityCriterion.hh:38-149
 public:
     explicit OCOptimizer(Problem &p) : m_p(p) {}
+    // inplace: gradient, multiplier search and setVars all stay on the device (vf_top_oc_step).  !inplace (:57-60): the gradient comes
+    // from the problem's virtual evaluateObjectiveGradientAndReturn(), the search runs on the device, and the stepped variables go
+    // through the problem's virtual setVars (:133) -- the path a subclassed problem (trampoline, VoxelFEM.cc:58-66) needs.
     void step(double m = 0.2, double p = 0.5, double ctol = 1e-6, bool inplace = true) {
-        if (!inplace) throw std::runtime_error("OCOptimizer::step(inplace = false) is not supported");
-        m_p.syncSolver(); int evals = 0; check(vf_top_oc_step(m_p.handle(), m, p, ctol, &evals)); m_lastEvals = evals;
+        m_p.syncSolver(); int evals = 0;
+        if (inplace && !m_p.hasHostOverrides()) check(vf_top_oc_step(m_p.handle(), m, p, ctol, &evals));
+        else {
+            const auto dJ = m_p.evaluateObjectiveGradientAndReturn();
+            std::vector<double> stepped(m_p.numVars());
+            check(vf_top_oc_search(m_p.handle(), dJ.data(), m, p, ctol, stepped.data(), &evals));
+            m_p.setVars(stepped);
+        }
+        m_lastEvals = evals;
     }
     int lastConstraintEvaluations() const { return m_lastEvals; }
 private:
@@ -395,21 +409,47 @@ template<typename TPS>
 class LayerByLayerEvaluator {                                     // LayerByLayer.hh:25-309
 public:
     using VXd = voxelfem_b200::VXd;
-    using LBLCallback = std::function<void(size_t, double, size_t)>;   // (layer, compliance, PCG iterations)
+    using VField = voxelfem_b200::VField;
+    using LBLCallback = std::function<void(size_t, double, const VXd &, const VField &)>;   // cb(l, compliance, grad_compliance, u) (:222)
     explicit LayerByLayerEvaluator(std::shared_ptr<TPS> lblSim) : m_sim(std::move(lblSim)) {}
     ~LayerByLayerEvaluator() { if (m_h) vf_lbl_destroy(m_h); }
     void selectInitMethod(const std::string &method) { m_method = method; if (m_h) check(vf_lbl_select_init_method(m_h, method.c_str())); }
+    // run (:223-296); it_callback(it, x, r) is handed to every layer's PCG (:265)
     template<typename MG>
-    void run(MG &solver, bool zeroInit, size_t layerIncrement, size_t maxIter, double tol, std::nullptr_t /* it_callback */ = nullptr,
-             size_t mgIterations = 1, size_t mgSmoothingIterations = 1, bool fullMultigrid = false, bool /* verbose */ = false, LBLCallback lblCallback = nullptr) {
+    void run(MG &solver, bool zeroInit, size_t layerIncrement, size_t maxIter, double tol, typename MG::PCGCallback it_callback = nullptr,
+             size_t mgIterations = 1, size_t mgSmoothingIterations = 1, bool fullMultigrid = false, bool verbose = false, LBLCallback lblCallback = nullptr) {
         if (!m_h || m_mg != solver.handle()) {
             if (m_h) vf_lbl_destroy(m_h);
             m_h = nullptr; check(vf_lbl_create(solver.handle(), &m_h)); m_mg = solver.handle();
             check(vf_lbl_select_init_method(m_h, m_method.c_str()));
         }
-        auto call = [](int64_t layer, double c, int its, void *user) { (*static_cast<LBLCallback *>(user))((size_t)layer, c, (size_t)its); };
+        struct Ctx { LayerByLayerEvaluator *self; LBLCallback *cb; bool verbose; typename MG::PCGCallback *pcg; vf_mg *mg; size_t nn; std::exception_ptr err; }
+            ctx{this, &lblCallback, verbose, &it_callback, solver.handle(), m_sim->numNodes(), nullptr};
+        auto layerCb = [](int64_t layer, double c, int, void *user) {
+            Ctx &x = *static_cast<Ctx *>(user);
+            if (x.err) return;
+            try {
+                if (x.verbose) std::cout << "Layer " << layer << ": " << c << std::endl;   // (:275-276)
+                if (*x.cb) {   // the two fields cross the bus only because a callback asked for them
+                    VXd g(x.self->m_sim->numElements()); VField u(x.nn, TPS::N);
+                    check(vf_lbl_get_layer_gradient(x.self->m_h, g.data())); check(vf_lbl_get_layer_u(x.self->m_h, u.data()));
+                    (*x.cb)((size_t)layer, c, g, u);
+                }
+            } catch (...) { x.err = std::current_exception(); }
+        };
+        auto pcgCb = [](int it, double, void *user) {
+            Ctx &x = *static_cast<Ctx *>(user);
+            if (x.err) return;
+            try {
+                VField xi(x.nn, TPS::N), ri(x.nn, TPS::N);
+                check(vf_mg_get_pcg_iterate(x.mg, xi.data())); check(vf_mg_get_pcg_residual(x.mg, ri.data()));
+                (*x.pcg)((size_t)it, xi, ri);
+            } catch (...) { x.err = std::current_exception(); }
+        };
         check(vf_lbl_run(m_h, zeroInit, (int64_t)layerIncrement, (int)maxIter, tol, (int)mgIterations, (int)mgSmoothingIterations, fullMultigrid,
-                         lblCallback ? static_cast<vf_lbl_callback>(call) : nullptr, &lblCallback));
+                         (lblCallback || verbose) ? static_cast<vf_lbl_callback>(layerCb) : nullptr, &ctx,
+                         it_callback ? static_cast<vf_pcg_callback>(pcgCb) : nullptr, &ctx));
+        if (ctx.err) std::rethrow_exception(ctx.err);
     }
     double objective() const { double v = 0; check(vf_lbl_objective(m_h, &v)); return v; }
     VXd gradient() const { VXd g(m_sim->numElements()); check(vf_lbl_gradient(m_h, g.data())); return g; }
