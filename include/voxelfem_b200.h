@@ -43,6 +43,10 @@ typedef struct vf_group vf_group; /* a MultigridSolver partitioned into slabs al
 #define VF_LAW_RAMP 1
 #define VF_FILTER_SMOOTH 0   /* SmoothingFilter  (TopologyOptimizationFilter.hh:285-400) */
 #define VF_FILTER_PROJECT 1  /* ProjectionFilter (TopologyOptimizationFilter.hh:189-245) */
+#define VF_FILTER_UPSAMPLE 2        /* UpsampleFilter      (:418-523); spec {2, factor, 0, 0} */
+#define VF_FILTER_VERTEX_TO_CELL 3  /* VertexToCellFilter  (:528-598); spec {3, 0, 0, 0} */
+#define VF_FILTER_LANGELAAR 4       /* LangelaarFilter     (:601-712); spec {4, 0, 0, 0} */
+#define VF_FILTER_PYTHON 5          /* PythonFilter        (:247-275); spec {5, 0, 0, 0} + vf_top_set_python_filter */
 #define VF_SMOOTH_CONST 0
 #define VF_SMOOTH_LINEAR 1
 
@@ -226,6 +230,17 @@ int vf_group_pcg_dev(vf_group *g, double *const *x_dev, const double *const *b_d
 int vf_filter_smooth(int dim, const int64_t *sizes, int radius, int type, const double *in, double *out); /* SmoothingFilter::apply == backprop (:297-310) */
 int vf_filter_project(int64_t n, double beta, const double *in, double *out);                                 /* ProjectionFilter::apply (:199-210) */
 int vf_filter_project_backprop(int64_t n, double beta, const double *in, const double *vars, double *out);  /* ProjectionFilter::backprop (:212-225) */
+/* UpsampleFilter::apply / backprop (:418-523): a vertex grid of coarse_sizes <-> (coarse_sizes - 1) * factor + 1 */
+int vf_filter_upsample(int dim, const int64_t *coarse_sizes, int factor, const double *in, double *out);
+int vf_filter_upsample_backprop(int dim, const int64_t *coarse_sizes, int factor, const double *d_dout, double *d_din);
+/* VertexToCellFilter::apply / backprop (:528-598): vertex_sizes <-> vertex_sizes - 1 */
+int vf_filter_vertex_to_cell(int dim, const int64_t *vertex_sizes, const double *in, double *out);
+int vf_filter_vertex_to_cell_backprop(int dim, const int64_t *vertex_sizes, const double *d_dout, double *d_din);
+/* LangelaarFilter::apply / backprop (:601-712).  `out` is IN/OUT (in 3D a voxel's support, NDVector.hh:211-229, holds the voxel
+ * itself: the previous content of the output array is read); smax (may be NULL) receives m_cachedSmax.  backprop takes the
+ * filter's input (vars), its last output (filtered = m_cachedFiltered) and that smax. */
+int vf_filter_langelaar(int dim, const int64_t *sizes, const double *in, double *out, double *smax);
+int vf_filter_langelaar_backprop(int dim, const int64_t *sizes, const double *d_dout, const double *vars, const double *filtered, const double *smax, double *d_din);
 
 /* ---- Device-pointer building blocks (slab-partitioned topology optimization) -------------
  * Same kernels as the filters / OC update / sensitivities above, on arrays that already live in HBM and on the
@@ -244,7 +259,17 @@ int vf_sim_synchronize(vf_sim *s);
 
 /* ---- Topology optimization problem ------------------------------------------------ */
 /* filter_spec: 4 doubles per filter (kind, radius, smoothing type, beta). */
+/* PythonFilter callbacks (:253-254): apply(in, out), backprop(d_dout, vars, d_din); return non-zero to abort */
+typedef int (*vf_filter_apply_cb)(const double *in, int64_t n_in, double *out, int64_t n_out, void *user);
+typedef int (*vf_filter_backprop_cb)(const double *d_dout, int64_t n_out, const double *vars, int64_t n_in, double *d_din, void *user);
 int vf_top_create(vf_mg *mg, int num_filters, const double *filter_spec, double volume_fraction, vf_top **out);
+int64_t vf_top_num_vars(const vf_top *t);                       /* FilterChain::numVars (:134): design variables (differs from numElements with Upsample / VertexToCell filters) */
+int64_t vf_top_num_physical_vars(const vf_top *t);              /* numPhysicalVars (:138) */
+int vf_top_get_grid_dims(const vf_top *t, int physical, int64_t *dims); /* gridDims / physicalGridDims (:136, 139) */
+int vf_top_set_python_filter(vf_top *t, int filter_index, vf_filter_apply_cb apply_cb, vf_filter_backprop_cb backprop_cb, void *user);
+/* MultigridComplianceObjective::residual_cb (TopologyOptimizationObjective.hh:93, 104): called after every PCG iteration of the
+ * solves setVars / the OC step run, with the iteration number and residual norm; inside it vf_mg_get_pcg_residual gives r. */
+int vf_top_set_residual_callback(vf_top *t, vf_pcg_callback cb, void *user);
 int vf_top_destroy(vf_top *t);
 /* MultigridComplianceObjective attributes (TopologyOptimizationObjective.hh:99-103). */
 int vf_top_set_solver(vf_top *t, int cg_iter, double tol, int mg_iterations, int mg_smoothing_iterations, int fmg, int zero_init);

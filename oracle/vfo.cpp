@@ -1110,6 +1110,9 @@ struct MG {
         return x[0];
     }
     // preconditionedConjugateGradient (:1047-1152)
+    // stiffnessPrebuilt: test/bench infrastructure only -- skip the per-call hierarchy rebuild of the reference (:1104-1107) when the
+    // caller knows the operators are current (bench.py times the rebuild and the iterations separately).
+    bool stiffnessPrebuilt = false;
     void pcg(double *xx, const double *bb, int maxIter, double tol, int mgIterations, int mgSmoothing, bool fmg, bool dirichletOK,
              const std::function<void(int, const double *, const double *)> &cb = nullptr) {
         Sim &fine = *sims[0];
@@ -1129,7 +1132,7 @@ struct MG {
         if (Ad.size() != len) Ad.assign(len, 0.0);
         if (dvec.size() != len) dvec.assign(len, 0.0);
         double bNormSq, rSq, rMr = 0;
-        bool stiffUpdated = false;
+        bool stiffUpdated = stiffnessPrebuilt;
         if (!dirichletOK) fine.enforceDirichlet(xx);
         bNormSq = fine.maskedDot(bb, bb);
         computeResidual(0, xx, bb, rr);
@@ -1203,6 +1206,143 @@ static void projectionBackprop(idx n, double beta, const double *in, const doubl
     #pragma omp parallel for schedule(static)
     for (idx i = 0; i < n; ++i) { double t = std::tanh(beta * (vars[i] - 0.5)); out[i] = in[i] * (1.0 - t * t) * scale; }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// UpsampleFilter / VertexToCellFilter / LangelaarFilter (TopologyOptimizationFilter.hh:418-712), restated loop for loop.
+// Flat row-major arrays, last axis fastest (NDVector.hh:256-264).
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace filt {
+static idx flat(int N, const idx *sz, const idx *c) { idx r = 0; for (int d = 0; d < N; ++d) r = r * sz[d] + c[d]; return r; }
+static void unflat(int N, const idx *sz, idx i, idx *c) { for (int d = N - 1; d >= 0; --d) { c[d] = i % sz[d]; i /= sz[d]; } }
+static idx total(int N, const idx *sz) { idx n = 1; for (int d = 0; d < N; ++d) n *= sz[d]; return n; }
+
+// UpsampleFilter::ApplyImpl (:463-489): every coarse entry that is the min corner of a cell samples that cell's multilinear
+// interpolant at the (factor + 1)^N fine nodes of the cell (faces shared with the next cell are written twice with the same value)
+static void upsample(int N, const idx *cs, int factor, const double *in, double *out) {
+    idx fs[3]; for (int d = 0; d < N; ++d) fs[d] = (cs[d] - 1) * factor + 1;
+    const idx nc = total(N, cs);
+    for (idx i = 0; i < nc; ++i) {
+        idx mc[3]; unflat(N, cs, i, mc);
+        bool valid = true; for (int d = 0; d < N; ++d) if (mc[d] + 1 >= cs[d]) valid = false;
+        if (!valid) continue;
+        double coeff[8];
+        for (int b = 0; b < (1 << N); ++b) { idx q[3]; for (int d = 0; d < N; ++d) q[d] = mc[d] + ((b >> (N - 1 - d)) & 1); coeff[b] = in[flat(N, cs, q)]; }
+        idx li[3] = {0, 0, 0};
+        const idx per = factor + 1; idx cnt = 1; for (int d = 0; d < N; ++d) cnt *= per;
+        for (idx k = 0; k < cnt; ++k) {
+            idx r = k; for (int d = N - 1; d >= 0; --d) { li[d] = r % per; r /= per; }
+            double v = 0.0;
+            for (int b = 0; b < (1 << N); ++b) {
+                double w = 1.0;
+                for (int d = 0; d < N; ++d) { const double t = double(li[d]) / factor; w *= ((b >> (N - 1 - d)) & 1) ? t : 1.0 - t; }
+                v += coeff[b] * w;
+            }
+            idx q[3]; for (int d = 0; d < N; ++d) q[d] = mc[d] * factor + li[d];
+            out[flat(N, fs, q)] = v;
+        }
+    }
+}
+// UpsampleFilter::BackpropImpl (:497-523)
+static void upsampleBackprop(int N, const idx *cs, int factor, const double *dout, double *din) {
+    idx fs[3]; for (int d = 0; d < N; ++d) fs[d] = (cs[d] - 1) * factor + 1;
+    const idx nc = total(N, cs);
+    for (idx i = 0; i < nc; ++i) {
+        idx n_c[3]; unflat(N, cs, i, n_c);
+        idx n_f[3], lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+        for (int d = 0; d < N; ++d) {
+            n_f[d] = factor * n_c[d]; lo[d] = n_f[d]; hi[d] = n_f[d] + 1;
+            if (n_c[d] > 0) lo[d] -= (factor - 1);
+            if (n_c[d] < cs[d] - 1) hi[d] += (factor - 1);
+        }
+        double acc = 0.0;
+        idx q[3];
+        for (q[0] = lo[0]; q[0] < hi[0]; ++q[0]) for (q[1] = lo[1]; q[1] < hi[1]; ++q[1]) for (q[2] = (N == 3 ? lo[2] : 0); q[2] < (N == 3 ? hi[2] : 1); ++q[2]) {
+            double phi = 1.0;
+            for (int d = 0; d < N; ++d) phi *= 1.0 - double(std::max(q[d], n_f[d]) - std::min(q[d], n_f[d])) / factor;
+            acc += phi * dout[flat(N, fs, q)];
+        }
+        din[i] = acc;
+    }
+}
+// VertexToCellFilter (:543-584)
+static void v2c(int N, const idx *vs, const double *in, double *out) {
+    idx es[3]; for (int d = 0; d < N; ++d) es[d] = vs[d] - 1;
+    const double weight = std::pow(2.0, -N); const idx ne = total(N, es);
+    for (idx e = 0; e < ne; ++e) {
+        idx mc[3]; unflat(N, es, e, mc);
+        double a = 0.0;
+        for (int b = 0; b < (1 << N); ++b) { idx q[3]; for (int d = 0; d < N; ++d) q[d] = mc[d] + ((b >> (N - 1 - d)) & 1); a += in[flat(N, vs, q)]; }
+        out[e] = a * weight;
+    }
+}
+static void v2cBackprop(int N, const idx *vs, const double *dout, double *din) {
+    idx es[3]; for (int d = 0; d < N; ++d) es[d] = vs[d] - 1;
+    const double weight = std::pow(2.0, -N); const idx nv = total(N, vs);
+    for (idx v = 0; v < nv; ++v) {
+        idx c[3]; unflat(N, vs, v, c);
+        double a = 0.0;
+        for (int b = 0; b < (1 << N); ++b) {
+            bool ok = true; idx q[3];
+            for (int d = 0; d < N; ++d) { const idx e = c[d] - 1 + ((b >> (N - 1 - d)) & 1); if (e < 0 || e >= es[d]) ok = false; q[d] = e; }
+            if (ok) a += dout[flat(N, es, q)];
+        }
+        din[v] = a * weight;
+    }
+}
+// NDVector::visitLayer (NDVector.hh:187-209) and visitSupportingRegion (:211-229) -- note the loop over the FIRST N - 1 axes
+template<class F> static void visitLayer(int N, const idx *sz, idx layer, F &&cb) {
+    if (N == 2) { for (idx i = 0; i < sz[0]; ++i) { idx c[2] = {i, layer}; cb(flat(2, sz, c)); } }
+    else { for (idx i = 0; i < sz[0]; ++i) for (idx j = 0; j < sz[2]; ++j) { idx c[3] = {i, layer, j}; cb(flat(3, sz, c)); } }
+}
+template<class F> static void visitSupport(int N, const idx *sz, const idx *voxel, F &&cb) {
+    idx center[3] = {0, 0, 0}; for (int d = 0; d < N; ++d) center[d] = voxel[d];
+    center[1] -= 1;
+    cb(flat(N, sz, center));
+    for (int d = 0; d < N - 1; ++d) {
+        idx cur[3] = {center[0], center[1], center[2]};
+        cur[d] -= 1;
+        bool in = true; for (int a = 0; a < N; ++a) if (cur[a] < 0 || cur[a] >= sz[a]) in = false;
+        if (in) cb(flat(N, sz, cur));
+        cur[d] += 2;
+        in = true; for (int a = 0; a < N; ++a) if (cur[a] < 0 || cur[a] >= sz[a]) in = false;
+        if (in) cb(flat(N, sz, cur));
+    }
+}
+static const double LG_P = 40, LG_Q = 40 - 1.58, LG_EPS = 1e-4;   // (:703-711)
+static double lgSmin(double x1, double x2) { return 0.5 * (x1 + x2 - std::pow((x1 - x2) * (x1 - x2) + LG_EPS, 0.5) + std::pow(LG_EPS, 0.5)); }
+static double lgDsminDx1(double x1, double x2) { return 0.5 * (1 - (x1 - x2) * std::pow((x1 - x2) * (x1 - x2) + LG_EPS, -0.5)); }
+static double lgDsminDx2(double x1, double x2) { return 0.5 * (1 + (x1 - x2) * std::pow((x1 - x2) * (x1 - x2) + LG_EPS, -0.5)); }
+// LangelaarFilter::apply (:609-623): out is in/out (see visitSupport), smaxCache = m_cachedSmax
+static void langelaar(int N, const idx *sz, const double *in, double *out, double *smaxCache) {
+    visitLayer(N, sz, 0, [&](idx i) { out[i] = in[i]; });
+    for (idx layer = 1; layer < sz[1]; ++layer)
+        visitLayer(N, sz, layer, [&](idx i) {
+            idx c[3]; unflat(N, sz, i, c);
+            double sum = 0; visitSupport(N, sz, c, [&](idx k) { sum += std::pow(out[k], LG_P); });
+            smaxCache[i] = std::pow(sum, 1 / LG_Q);
+            out[i] = lgSmin(in[i], smaxCache[i]);
+        });
+}
+// LangelaarFilter::backprop (:625-634) with computeLagrangeMultipliers (:643-661)
+static void langelaarBackprop(int N, const idx *sz, const double *in, const double *vars, const double *filtered, const double *smaxCache, double *out) {
+    const idx n = total(N, sz);
+    std::vector<double> lambdas(n, 0.0);
+    auto smaxDerivative = [&](const idx *indices, idx der) {
+        double sum = 0; visitSupport(N, sz, indices, [&](idx i) { sum += std::pow(filtered[i], LG_P); });
+        return LG_P * std::pow(filtered[der], LG_P - 1) / LG_Q * std::pow(sum, 1 / LG_Q - 1);
+    };
+    for (idx layer = sz[1] - 1; layer >= 0; --layer) {
+        visitLayer(N, sz, layer, [&](idx i) { lambdas[i] = in[i]; });
+        if (layer < sz[1] - 1)
+            visitLayer(N, sz, layer + 1, [&](idx i) {
+                idx c[3]; unflat(N, sz, i, c);
+                visitSupport(N, sz, c, [&](idx k) { lambdas[k] += lambdas[i] * (lgDsminDx2(vars[i], smaxCache[i]) * smaxDerivative(c, k)); });
+            });
+    }
+    visitLayer(N, sz, 0, [&](idx i) { out[i] = lambdas[i]; });
+    for (idx layer = 1; layer < sz[1]; ++layer) visitLayer(N, sz, layer, [&](idx i) { out[i] = lambdas[i] * lgDsminDx1(vars[i], smaxCache[i]); });
+}
+} // namespace filt
 
 // A filter chain restricted to the in-scope filters: kind 0 = Smoothing(radius, type), 1 = Projection(beta)
 struct FilterSpec { int kind; int radius; int type; double beta; };
@@ -1793,6 +1933,7 @@ int vfo_mg_get_stencil(void *h, int l, double *out) {
 int vfo_mg_coarse_solve(void *h, const double *f, double *x) { VFO_TRY MG &mg = M(h); mg.sims.back()->solve(f, x); VFO_CATCH }
 int vfo_mg_solve(void *h, const double *u, const double *f, int numSteps, int nsmooth, int stiffnessUpdated, int zeroDirichlet, int fmg, double *out) {
     VFO_TRY const auto &res = M(h).solve(u, f, numSteps, nsmooth, stiffnessUpdated != 0, zeroDirichlet != 0, fmg != 0); std::copy(res.begin(), res.end(), out); VFO_CATCH }
+void vfo_mg_set_stiffness_prebuilt(void *h, int on) { M(h).stiffnessPrebuilt = on != 0; }
 int vfo_mg_pcg(void *h, double *x, const double *b, int maxIter, double tol, int mgIt, int mgSmooth, int fmg, int dirichletOK, int *outIters, double *outResiduals) {
     VFO_TRY MG &mg = M(h); mg.pcg(x, b, maxIter, tol, mgIt, mgSmooth, fmg != 0, dirichletOK != 0);
     if (outIters) *outIters = mg.lastIters;
@@ -1808,6 +1949,12 @@ void vfo_mg_debug_multicolor_visit(void *h, int32_t *out) { MG &mg = M(h); const
 void vfo_smoothing_filter(int N, const int64_t *sizes, int radius, int type, const double *in, double *out) { smoothingFilter(N, sizes, radius, type, in, out); }
 void vfo_projection_apply(int64_t n, double beta, const double *in, double *out) { projectionApply(n, beta, in, out); }
 void vfo_projection_backprop(int64_t n, double beta, const double *in, const double *vars, double *out) { projectionBackprop(n, beta, in, vars, out); }
+void vfo_filter_upsample(int N, const int64_t *cs, int factor, const double *in, double *out) { filt::upsample(N, cs, factor, in, out); }
+void vfo_filter_upsample_backprop(int N, const int64_t *cs, int factor, const double *dout, double *din) { filt::upsampleBackprop(N, cs, factor, dout, din); }
+void vfo_filter_v2c(int N, const int64_t *vs, const double *in, double *out) { filt::v2c(N, vs, in, out); }
+void vfo_filter_v2c_backprop(int N, const int64_t *vs, const double *dout, double *din) { filt::v2cBackprop(N, vs, dout, din); }
+void vfo_filter_langelaar(int N, const int64_t *sz, const double *in, double *out, double *smax) { filt::langelaar(N, sz, in, out, smax); }
+void vfo_filter_langelaar_backprop(int N, const int64_t *sz, const double *in, const double *vars, const double *filtered, const double *smax, double *out) { filt::langelaarBackprop(N, sz, in, vars, filtered, smax, out); }
 
 // filters: flat array of (kind, radius, type, beta) quadruples as doubles
 void *vfo_problem_create(void *mgh, int nfilters, const double *fspec, double volFrac) {

@@ -94,6 +94,12 @@ def lib():
         "vfo_smoothing_filter": (None, [ci, _ip, ci, ci, _dp, _dp]),
         "vfo_projection_apply": (None, [i64, cd, _dp, _dp]),
         "vfo_projection_backprop": (None, [i64, cd, _dp, _dp, _dp]),
+        "vfo_filter_upsample": (None, [ci, _ip, ci, _dp, _dp]),
+        "vfo_filter_upsample_backprop": (None, [ci, _ip, ci, _dp, _dp]),
+        "vfo_filter_v2c": (None, [ci, _ip, _dp, _dp]),
+        "vfo_filter_v2c_backprop": (None, [ci, _ip, _dp, _dp]),
+        "vfo_filter_langelaar": (None, [ci, _ip, _dp, _dp, _dp]),
+        "vfo_filter_langelaar_backprop": (None, [ci, _ip, _dp, _dp, _dp, _dp, _dp]),
         "vfo_problem_create": (vp, [vp, ci, _dp, cd]),
         "vfo_problem_destroy": (None, [vp]),
         "vfo_problem_set_solver": (None, [vp, ci, cd, ci, ci, ci, ci]),
@@ -380,6 +386,11 @@ class OracleMG:
         _check(self.L.vfo_mg_pcg(self.h, x, to_soa(b), max_iter, tol, mg_iterations, mg_smoothing, int(fmg), int(dirichlet_ok), C.byref(it), res))
         return from_soa(x, self.N), it.value, res[:it.value]
 
+    def set_stiffness_prebuilt(self, on):
+        """bench infrastructure: skip the per-call hierarchy rebuild inside pcg (the caller has called update_stiffness)."""
+        self.L.vfo_mg_set_stiffness_prebuilt.argtypes = [C.c_void_p, C.c_int]; self.L.vfo_mg_set_stiffness_prebuilt.restype = None
+        self.L.vfo_mg_set_stiffness_prebuilt(self.h, int(on))
+
     def pcg_residual(self):
         out = np.zeros(self.nn(0) * self.N)
         self.L.vfo_mg_get_pcg_residual(self.h, out)
@@ -471,6 +482,42 @@ def projection_apply(x, beta):
 def projection_backprop(g, vars_, beta):
     g = np.ascontiguousarray(g, dtype=np.float64).ravel(); out = np.zeros_like(g)
     lib().vfo_projection_backprop(len(g), beta, g, np.ascontiguousarray(vars_, dtype=np.float64).ravel(), out); return out
+
+
+def _f(a): return np.ascontiguousarray(a, dtype=np.float64).ravel()
+def _s(shape): return np.ascontiguousarray(shape, dtype=np.int64)
+
+
+def upsample(x, coarse_shape, factor):
+    cs = _s(coarse_shape); out = np.zeros(int(np.prod((cs - 1) * factor + 1)))
+    lib().vfo_filter_upsample(len(cs), cs, factor, _f(x), out); return out
+
+
+def upsample_backprop(g, coarse_shape, factor):
+    cs = _s(coarse_shape); out = np.zeros(int(np.prod(cs)))
+    lib().vfo_filter_upsample_backprop(len(cs), cs, factor, _f(g), out); return out
+
+
+def vertex_to_cell(x, vertex_shape):
+    vs = _s(vertex_shape); out = np.zeros(int(np.prod(vs - 1)))
+    lib().vfo_filter_v2c(len(vs), vs, _f(x), out); return out
+
+
+def vertex_to_cell_backprop(g, vertex_shape):
+    vs = _s(vertex_shape); out = np.zeros(int(np.prod(vs)))
+    lib().vfo_filter_v2c_backprop(len(vs), vs, _f(g), out); return out
+
+
+def langelaar(x, shape, out_prev=None):
+    """returns (filtered, smax); out_prev = previous content of the output array (zeros on a fresh filter)."""
+    sz = _s(shape); n = int(np.prod(sz))
+    out = np.zeros(n) if out_prev is None else _f(out_prev).copy(); smax = np.zeros(n)
+    lib().vfo_filter_langelaar(len(sz), sz, _f(x), out, smax); return out, smax
+
+
+def langelaar_backprop(g, vars_, filtered, smax, shape):
+    sz = _s(shape); out = np.zeros(int(np.prod(sz)))
+    lib().vfo_filter_langelaar_backprop(len(sz), sz, _f(g), _f(vars_), _f(filtered), _f(smax), out); return out
 
 
 class OracleLBL:

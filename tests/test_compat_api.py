@@ -9,6 +9,51 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "voxelfem_b200", "compat"))
+
+
+def test_pybind11_modules_expose_the_reference_surface():
+    """The pybind11 extension modules built from host/VoxelFEM.hh (voxelfem_b200/pybind): same names as python_bindings/VoxelFEM.cc and
+    Optimizer.cc register.  Loaded in a subprocess: the module names collide with the pure-Python flavour imported by the other tests."""
+    import subprocess
+    code = r'''
+import json, os, sys
+sys.path.insert(0, os.path.join(sys.argv[1], "voxelfem_b200", "pybind"))
+import pyVoxelFEM as m, pyOptimizer
+assert m.__file__.endswith(".so") and pyOptimizer.__file__.endswith(".so")
+API = json.load(open(os.path.join(sys.argv[1], "tests", "golden", "pyvoxelfem_api.json")))
+d = m.detail
+cls = {"TensorProductSimulator": d.TensorProductSimulator1_1_1, "MultigridSolver": d.MultigridSolver1_1_1, "TopologyOptimizationProblem": d.TopologyOptimizationProblem1_1_1,
+       "MultigridComplianceObjective": d.MultigridComplianceObjective1_1_1, "LayerByLayerEvaluator": d.LayerByLayerEvaluator1_1_1, "OCOptimizer": d.OCOptimizer1_1_1,
+       "FilterChain": m.FilterChain, "ProjectionFilter": m.ProjectionFilter, "SmoothingFilter": m.SmoothingFilter, "Filter": m.SmoothingFilter,
+       "TotalVolumeConstraint": m.TotalVolumeConstraint, "PythonFilter": m.PythonFilter}
+missing = {k: [n for n in API[k] if not hasattr(c, n)] for k, c in cls.items()}
+missing["module"] = [n for n in API["module"] if not hasattr(m, n)]
+missing["MMA"] = [n for n in API["pyOptimizer.MMA"] if not hasattr(pyOptimizer.MMA, n)]
+assert not any(missing.values()), missing
+assert d.TensorProductSimulator1_1 is not d.TensorProductSimulator1_1_1 and m.InterpolationLaw.SIMP == m.SIMP
+class Sub(d.TopologyOptimizationProblem1_1_1):        # python-subclassable (trampoline, VoxelFEM.cc:58-66)
+    def evaluateObjective(self): return 0.0
+pf = m.ProjectionFilter(4.0)
+assert abs(pf.invert(0.5) - 0.5) < 1e-15
+up = m.UpsampleFilter(2); up.setOutputDimensions([9, 5]); assert list(up.inputDimensions) == [5, 3]
+try:
+    m.TensorProductSimulator([2, 2], [[0, 0], [1, 1]], [4, 4])
+except RuntimeError as e:
+    assert "No template instantiation" in str(e)
+else:
+    raise AssertionError("Q2 factory call did not raise")
+import torch
+if not torch.cuda.is_available():
+    try:
+        m.TensorProductSimulator([1, 1], [[0, 0], [2, 1]], [8, 4])
+    except RuntimeError as e:
+        assert "no CPU fallback" in str(e)      # the extension fails loudly without a device
+    else:
+        raise AssertionError("constructor succeeded without a GPU")
+print("ok")
+'''
+    r = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
 API = json.load(open(os.path.join(ROOT, "tests", "golden", "pyvoxelfem_api.json")))
 
 
@@ -48,9 +93,15 @@ def test_mma_surface():
 
 def test_out_of_scope_names_fail_loudly():
     import pyVoxelFEM as m
-    for name in ("PythonFilter", "UpsampleFilter", "VertexToCellFilter", "LangelaarFilter"):
-        with pytest.raises(NotImplementedError, match=name):
-            getattr(m, name)()
+    for name in ("PythonFilter", "UpsampleFilter", "VertexToCellFilter", "LangelaarFilter"):   # built since round 2
+        f = getattr(m, name)()
+        f.setOutputDimensions([9, 9])
+        assert list(f.outputDimensions) == [9, 9]
+    assert hasattr(m.PythonFilter(), "apply_cb") and hasattr(m.PythonFilter(), "backprop_cb")
+    up = m.UpsampleFilter(2); up.setOutputDimensions([9, 5]); assert list(up.inputDimensions) == [5, 3]
+    with pytest.raises(RuntimeError, match="not divisible"):
+        m.UpsampleFilter(2).setOutputDimensions([8, 8])
+    v2c = m.VertexToCellFilter(); v2c.setOutputDimensions([8, 4]); assert list(v2c.inputDimensions) == [9, 5]
     with pytest.raises(NotImplementedError, match="MultigridComplianceObjective"):
         m.ComplianceObjective(None)
     with pytest.raises(NotImplementedError, match="getK"):

@@ -13,13 +13,25 @@ from oracle import OracleLBL, OracleMG, OracleProblem, OracleSim
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "voxelfem_b200", "compat"))
+DRIVER_MODULES = ("pyVoxelFEM", "pyOptimizer", "benchmark", "parallelism", "MeshFEM", "mesh")
 
 
-@pytest.fixture(scope="module")
-def vf():
-    import pyVoxelFEM
-    return pyVoxelFEM
+@pytest.fixture(scope="module", params=["pybind11", "python-shim"])
+def vf(request):
+    """pyVoxelFEM in both flavours: the pybind11 extension built from host/VoxelFEM.hh (voxelfem_b200/pybind) and the pure-Python
+    module over the ctypes layer (voxelfem_b200/compat).  Whichever directory is on sys.path provides `pyVoxelFEM`, `pyOptimizer`,
+    `benchmark`, ... under the names the reference's drivers import."""
+    d = os.path.join(ROOT, "voxelfem_b200", "pybind" if request.param == "pybind11" else "compat")
+    saved = {k: sys.modules.pop(k) for k in DRIVER_MODULES if k in sys.modules}
+    sys.path.insert(0, d)
+    import importlib
+    m = importlib.import_module("pyVoxelFEM")
+    assert os.path.dirname(os.path.abspath(m.__file__)) == d
+    yield m
+    sys.path.remove(d)
+    for k in DRIVER_MODULES:
+        sys.modules.pop(k, None)
+    sys.modules.update(saved)
 
 
 def rel_l2(a, b): return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
@@ -138,6 +150,7 @@ def test_layer_by_layer_flow(vf):
 
 def test_mma_module(vf):
     import pyOptimizer
+    assert os.path.dirname(os.path.abspath(pyOptimizer.__file__)) == os.path.dirname(os.path.abspath(vf.__file__))
     from mma_problems import svanberg_toy
     n, m, lo, hi, f, df, x0, xstar = svanberg_toy()
     opt = pyOptimizer.MMA(n, m, lo, hi, f, df)
@@ -145,3 +158,102 @@ def test_mma_module(vf):
     for _ in range(12):
         opt.step()
     assert np.abs(opt.getOptimalVar() - xstar).max() < 2e-6
+
+
+def _lbl_optimization_problem_class(vf, benchmark, tps):
+    """python/LayerByLayerOptimization.py:54-79 (getClass) restated: a python subclass of the problem class named by getClassName."""
+    baseClass = eval(vf.getClassName(tps, "TopologyOptimizationProblem"), {"pyVoxelFEM": vf})
+
+    class LayerByLayerOptimizationProblem(baseClass):
+        def __init__(self, tps, optObj, constraints, filters, layObj, weight):
+            super().__init__(tps, optObj, constraints, filters)
+            self.optObj, self.layObj, self.weight, self.skipLayers, self.opt_obj, self.lbl_obj = optObj, layObj, weight, 1, 0, 0
+        def setVars(self, x, verbose=False):
+            benchmark.start_timer_section('Optimization setVars')
+            super().setVars(x)
+            benchmark.stop_timer_section('Optimization setVars')
+            self.layObj.setVars(self.getDensities(), self.skipLayers, verbose)
+        def evaluateObjective(self):
+            self.opt_obj = super().evaluateObjective()
+            self.lbl_obj = self.layObj.energy()
+            return self.opt_obj + self.weight * self.lbl_obj
+        def evaluateObjectiveGradient(self):
+            return super().evaluateObjectiveGradient() + self.weight * self.filterChain.backprop(self.layObj.gradient())
+    return LayerByLayerOptimizationProblem
+
+
+class _LayObj:
+    """python/LayerByLayerObjective.py:75-139 restated (no downsampling, no symmetry): the layer-by-layer objective of a design."""
+    def __init__(self, vf, tps, levels, pcgVars):
+        self.vf, self.tps, self.pcgVars = vf, tps, pcgVars
+        self.sim = tps.getIntermediateFabricationShape(1, False, vf.InterpolationLaw.RAMP)
+        self.sim.q = 3
+        self.mg = self.sim.multigridSolver(levels)
+        self.ev = None
+    def setVars(self, x, skipLayers=1, verbose=False):
+        self.tps.downsampleDensityFieldTo(x, self.sim)
+        if self.ev is None: self.ev = self.vf.LayerByLayerEvaluator(self.sim)
+        self.ev.selectInitMethod("N=3")
+        self.ev.run(self.mg, True, skipLayers, **self.pcgVars, verbose=verbose, lblCallback=None)
+    def energy(self): return self.ev.objective()
+    def gradient(self): return self.ev.gradient()
+
+
+def test_layer_by_layer_optimization_flow(vf, data_dir):
+    """python/LayerByLayerOptimization.py:56-79, 180-200 + its MMA / OC drivers (:13-38): a python-SUBCLASSED problem
+    (trampoline) whose objective adds the layer-by-layer energy, driven by pyOptimizer.MMA and by OCOptimizer.step."""
+    import benchmark
+    import pyOptimizer
+    benchmark.reset()
+    grid, maxVolume, weight = [16, 8], 0.6, 0.1
+    filters = [vf.SmoothingFilter(radius=2, type=vf.SmoothingFilter.Type.Linear), vf.ProjectionFilter(beta=5)]
+    constraints = [vf.TotalVolumeConstraint(maxVolume)]
+    uniformDensity = filters[-1].invert(maxVolume)
+    tps = vf.TensorProductSimulator([1, 1], [[0, 0], [2, 1]], grid)
+    tps.setDensities(np.ones(int(np.prod(grid))) * uniformDensity)
+    tps.readMaterial(os.path.join(data_dir, "materials", "B9Creator.material"))
+    tps.applyDisplacementsAndLoadsFromFile(os.path.join(data_dir, "bcs", "mbb_N.bc"))
+    optObj = vf.MultigridComplianceObjective(tps.multigridSolver(2))
+    optObj.mgSmoothingIterations = 1
+    optObj.tol = 1e-9
+    cg = {"opt": 0, "lay": 0}
+    optObj.residual_cb = lambda i, r: cg.__setitem__("opt", cg["opt"] + 1)
+    pcgVars = {'maxIter': 50, 'tol': 1e-9, 'mgIterations': 1, 'mgSmoothingIterations': 1, 'fullMultigrid': False,
+               'it_callback': lambda i, _, r: cg.__setitem__("lay", cg["lay"] + 1)}
+    layObj = _LayObj(vf, tps, 2, pcgVars)
+    Problem = _lbl_optimization_problem_class(vf, benchmark, tps)
+    top = Problem(tps, optObj, constraints, filters, layObj, weight)
+    x0 = tps.getDensities()
+    top.setVars(x0)
+    assert cg["opt"] > 0 and cg["lay"] > 0
+    J = top.evaluateObjective()
+    assert abs(J - (top.opt_obj + weight * top.lbl_obj)) < 1e-14 * abs(J) and top.lbl_obj > 0
+    # the subclass's gradient: finite differences of the combined objective along a random direction
+    g = top.evaluateObjectiveGradient()
+    d = np.random.default_rng(0).normal(size=x0.size); h = 1e-5
+    top.setVars(x0 + h * d); Jp = top.evaluateObjective()
+    top.setVars(x0 - h * d); Jm = top.evaluateObjective()
+    assert abs((Jp - Jm) / (2 * h) - float(g @ d)) < 2e-5 * abs(float(g @ d))
+    top.setVars(x0)
+    # MMA exactly as python/LayerByLayerOptimization.py:13-38 wires it
+    n = top.numVars()
+    def gradients(x): return np.stack([top.evaluateObjectiveGradient(), -top.evaluateConstraintsJacobian()[0]])
+    def objAndConstr(x):
+        top.setVars(x)
+        return np.stack([top.evaluateObjective(), -top.evaluateConstraints()[0]])
+    mma = pyOptimizer.MMA(n, 1, np.zeros(n), np.ones(n), objAndConstr, gradients)
+    mma.setInitialVar(x0)
+    J0 = objAndConstr(x0)[0]
+    for _ in range(4): mma.step()
+    assert top.evaluateObjective() < J0 and -top.evaluateConstraints()[0] <= 1e-6       # descends, volume constraint respected
+    # OC on the subclassed problem: gradient from the override, search on the device, result through the override's setVars
+    top.setVars(x0)
+    before = dict(cg)
+    oc = vf.OCOptimizer(top)
+    oc.step()
+    assert cg["lay"] > before["lay"]                                    # the override's setVars ran the layer-by-layer simulation
+    assert abs(top.evaluateConstraints()[0]) <= 1e-6 and top.evaluateObjective() < J0
+    oc.step(inplace=False)
+    assert abs(top.evaluateConstraints()[0]) <= 1e-6
+    rep = benchmark.report
+    rep()

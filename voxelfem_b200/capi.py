@@ -20,6 +20,8 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 PCG_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_void_p)
 LBL_CALLBACK = C.CFUNCTYPE(None, C.c_int64, C.c_double, C.c_int, C.c_void_p)
+FILTER_APPLY_CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.c_int64, C.c_void_p)
+FILTER_BACKPROP_CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.c_void_p)
 MMA_F_CALLBACK = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
 MMA_DF_CALLBACK = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
 
@@ -159,6 +161,17 @@ def lib():
         "vf_filter_project": (ci, [i64, cd, _dp, _dp]),
         "vf_filter_project_backprop": (ci, [i64, cd, _dp, _dp, _dp]),
         "vf_top_create": (ci, [vp, ci, _dp, cd, pvp]),
+        "vf_top_num_vars": (i64, [vp]),
+        "vf_top_num_physical_vars": (i64, [vp]),
+        "vf_top_get_grid_dims": (ci, [vp, ci, _ip]),
+        "vf_top_set_python_filter": (ci, [vp, ci, FILTER_APPLY_CB, FILTER_BACKPROP_CB, vp]),
+        "vf_top_set_residual_callback": (ci, [vp, PCG_CALLBACK, vp]),
+        "vf_filter_upsample": (ci, [ci, _ip, ci, _dp, _dp]),
+        "vf_filter_upsample_backprop": (ci, [ci, _ip, ci, _dp, _dp]),
+        "vf_filter_vertex_to_cell": (ci, [ci, _ip, _dp, _dp]),
+        "vf_filter_vertex_to_cell_backprop": (ci, [ci, _ip, _dp, _dp]),
+        "vf_filter_langelaar": (ci, [ci, _ip, _dp, _dp, _dp]),
+        "vf_filter_langelaar_backprop": (ci, [ci, _ip, _dp, _dp, _dp, _dp, _dp]),
         "vf_top_destroy": (ci, [vp]),
         "vf_top_set_solver": (ci, [vp, ci, cd, ci, ci, ci, ci]),
         "vf_top_set_vars": (ci, [vp, _dp]),
@@ -660,29 +673,78 @@ class SlabGroup(_Owned):
 class Problem(_Owned):
     """TopologyOptimizationProblem + MultigridComplianceObjective + TotalVolumeConstraint + OCOptimizer (vf_top)."""
 
+    KINDS = {"smooth": 0, "project": 1, "upsample": 2, "vertex_to_cell": 3, "langelaar": 4, "python": 5}
+
     def __init__(self, mg, filters, vol_frac):
+        """filters: ("smooth", radius, type) | ("project", beta) | ("upsample", factor) | ("vertex_to_cell",) | ("langelaar",) |
+        ("python", apply(in) -> out, backprop(d_dout, vars) -> d_din)"""
         self.L = lib()
         self.mg = mg
-        spec = []
-        for f in filters:
-            if f[0] == "smooth":
+        spec, self._py = [], []
+        for i, f in enumerate(filters):
+            k = self.KINDS[f[0]]
+            if k == 0:
                 spec += [0, f[1], f[2], 0.0]
-            else:
+            elif k == 1:
                 spec += [1, 0, 0, f[1]]
+            elif k == 2:
+                spec += [2, f[1], 0, 0.0]
+            else:
+                spec += [k, 0, 0, 0.0]
+            if k == 5:
+                self._py.append((i, f[1], f[2]))
         spec = np.ascontiguousarray(spec if spec else [0.0], dtype=np.float64)
         h = C.c_void_p()
         _check(self.L.vf_top_create(mg.h, len(filters), spec, vol_frac, C.byref(h)))
         self._own(h, self.L.vf_top_destroy, mg)
         self.ne = mg.sim.num_elements
         self.N = mg.N
+        self.nv = int(self.L.vf_top_num_vars(self.h))
+        self._cbs, self._failed = [], []
+        for i, ap, bp in self._py:
+            def a_cb(pin, nin, pout, nout, _u, ap=ap):
+                try:
+                    np.ctypeslib.as_array(pout, (nout,))[:] = np.asarray(ap(np.ctypeslib.as_array(pin, (nin,)).copy()), dtype=np.float64).ravel(); return 0
+                except BaseException as e:   # noqa: BLE001
+                    self._failed.append(e); return 1
+
+            def b_cb(pg, nout, pv, nin, pout, _u, bp=bp):
+                try:
+                    np.ctypeslib.as_array(pout, (nin,))[:] = np.asarray(bp(np.ctypeslib.as_array(pg, (nout,)).copy(), np.ctypeslib.as_array(pv, (nin,)).copy()), dtype=np.float64).ravel(); return 0
+                except BaseException as e:   # noqa: BLE001
+                    self._failed.append(e); return 1
+            ca, cb = FILTER_APPLY_CB(a_cb), FILTER_BACKPROP_CB(b_cb)
+            self._cbs += [ca, cb]
+            _check(self.L.vf_top_set_python_filter(self.h, i, ca, cb, None))
+
+    def _call(self, rc):
+        if self._failed:
+            e = self._failed[0]; self._failed.clear(); raise e
+        _check(rc)
+
+    def set_residual_callback(self, fn):
+        """fn(iteration, residual_norm) after every PCG iteration of the problem's solves; None clears it."""
+        def guarded(i, r, _u):
+            try:
+                fn(i, r)
+            except BaseException as e:   # noqa: BLE001
+                self._failed.append(e)
+        self._res_cb = PCG_CALLBACK(guarded) if fn is not None else PCG_CALLBACK()
+        _check(self.L.vf_top_set_residual_callback(self.h, self._res_cb, None))
+
+    def grid_dims(self, physical=False):
+        d = np.zeros(self.N, dtype=np.int64); _check(self.L.vf_top_get_grid_dims(self.h, int(physical), d)); return d
 
     def set_solver(self, cg_iter=100, tol=1e-5, mg_it=1, mg_smooth=2, fmg=True, zero_init=False):
         _check(self.L.vf_top_set_solver(self.h, cg_iter, tol, mg_it, mg_smooth, int(fmg), int(zero_init)))
 
-    def set_vars(self, x): _check(self.L.vf_top_set_vars(self.h, np.ascontiguousarray(x, dtype=np.float64)))
+    def set_vars(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        if x.size != self.nv: raise VoxelFEMError("Variable size mismatch")
+        self._call(self.L.vf_top_set_vars(self.h, x))
 
     def design_vars(self):
-        o = np.zeros(self.ne); _check(self.L.vf_top_get_vars(self.h, 0, o)); return o
+        o = np.zeros(self.nv); _check(self.L.vf_top_get_vars(self.h, 0, o)); return o
 
     def physical_vars(self):
         o = np.zeros(self.ne); _check(self.L.vf_top_get_vars(self.h, 1, o)); return o
@@ -694,10 +756,10 @@ class Problem(_Owned):
         v = C.c_double(); _check(self.L.vf_top_constraint(self.h, C.byref(v))); return v.value
 
     def objective_gradient(self):
-        o = np.zeros(self.ne); _check(self.L.vf_top_objective_gradient(self.h, o)); return o
+        o = np.zeros(self.nv); self._call(self.L.vf_top_objective_gradient(self.h, o)); return o
 
     def constraint_jacobian(self):
-        o = np.zeros(self.ne); _check(self.L.vf_top_constraint_jacobian(self.h, o)); return o
+        o = np.zeros(self.nv); self._call(self.L.vf_top_constraint_jacobian(self.h, o)); return o
 
     def u(self):
         o = np.zeros(self.mg.nn(0) * self.N); _check(self.L.vf_top_get_u(self.h, o)); return from_soa(o, self.N)
@@ -705,14 +767,14 @@ class Problem(_Owned):
     def last_pcg_iters(self): return self.L.vf_top_last_pcg_iterations(self.h)
 
     def oc_step(self, m=0.2, p=0.5, ctol=1e-6):
-        n = C.c_int(0); _check(self.L.vf_top_oc_step(self.h, m, p, ctol, C.byref(n))); return n.value
+        n = C.c_int(0); self._call(self.L.vf_top_oc_step(self.h, m, p, ctol, C.byref(n))); return n.value
 
     def oc_search(self, dJ=None, m=0.2, p=0.5, ctol=1e-6):
         """Bracket + bisection of OCOptimizer::step with a caller-supplied objective gradient; returns the stepped variables
         without setting them (vf_top_oc_search)."""
-        n = C.c_int(0); out = np.zeros(self.mg.sim.num_elements)
+        n = C.c_int(0); out = np.zeros(self.nv)
         g = None if dJ is None else np.ascontiguousarray(dJ, dtype=np.float64).ravel()
-        _check(self.L.vf_top_oc_search(self.h, None if g is None else g.ctypes.data_as(C.c_void_p), m, p, ctol, out, C.byref(n)))
+        self._call(self.L.vf_top_oc_search(self.h, None if g is None else g.ctypes.data_as(C.c_void_p), m, p, ctol, out, C.byref(n)))
         return out, n.value
 
     def lambda_bracket(self):
@@ -724,6 +786,42 @@ def smoothing_filter(x, shape, radius, ftype):
     out = np.zeros(int(np.prod(shape)))
     _check(lib().vf_filter_smooth(len(shape), shape, radius, ftype, np.ascontiguousarray(x, dtype=np.float64).ravel(), out))
     return out
+
+
+def _fa(a): return np.ascontiguousarray(a, dtype=np.float64).ravel()
+def _sa(shape): return np.ascontiguousarray(shape, dtype=np.int64)
+
+
+def upsample_filter(x, coarse_shape, factor):                         # UpsampleFilter::apply
+    cs = _sa(coarse_shape); out = np.zeros(int(np.prod((cs - 1) * factor + 1)))
+    _check(lib().vf_filter_upsample(len(cs), cs, int(factor), _fa(x), out)); return out
+
+
+def upsample_filter_backprop(g, coarse_shape, factor):
+    cs = _sa(coarse_shape); out = np.zeros(int(np.prod(cs)))
+    _check(lib().vf_filter_upsample_backprop(len(cs), cs, int(factor), _fa(g), out)); return out
+
+
+def vertex_to_cell_filter(x, vertex_shape):                           # VertexToCellFilter::apply
+    vs = _sa(vertex_shape); out = np.zeros(int(np.prod(vs - 1)))
+    _check(lib().vf_filter_vertex_to_cell(len(vs), vs, _fa(x), out)); return out
+
+
+def vertex_to_cell_filter_backprop(g, vertex_shape):
+    vs = _sa(vertex_shape); out = np.zeros(int(np.prod(vs)))
+    _check(lib().vf_filter_vertex_to_cell_backprop(len(vs), vs, _fa(g), out)); return out
+
+
+def langelaar_filter(x, shape, out_prev=None):
+    """LangelaarFilter::apply -> (filtered, smax).  out_prev: previous content of the output array (zeros for a fresh filter)."""
+    sz = _sa(shape); n = int(np.prod(sz))
+    out = np.zeros(n) if out_prev is None else _fa(out_prev).copy(); smax = np.zeros(n)
+    _check(lib().vf_filter_langelaar(len(sz), sz, _fa(x), out, smax)); return out, smax
+
+
+def langelaar_filter_backprop(g, vars_, filtered, smax, shape):
+    sz = _sa(shape); out = np.zeros(int(np.prod(sz)))
+    _check(lib().vf_filter_langelaar_backprop(len(sz), sz, _fa(g), _fa(vars_), _fa(filtered), _fa(smax), out)); return out
 
 
 def projection_apply(x, beta):

@@ -346,37 +346,87 @@ class ProjectionFilter(_Filter):         # TopologyOptimizationFilter.hh:199-245
     def _spec(self): return ("project", self._beta)
 
 
-def _out_of_scope_filter(name):
-    class F(_Filter):
-        def __init__(self, *a, **k):
-            raise NotImplementedError("pyVoxelFEM.%s is not on the B200 hot path yet (SURVEY.md section 8f, rank 2)" % name)
-    F.__name__ = name
-    return F
+class UpsampleFilter(_Filter):           # TopologyOptimizationFilter.hh:418-523
+    def __init__(self, factor=2):
+        super().__init__(); self._factor = int(factor)
+    def setInputDimensions(self, gridDims):
+        d = np.asarray(gridDims, dtype=np.int64)
+        if np.any(d < 2): raise RuntimeError("Interpolation can only be applied to a 2^d grid or larger")
+        self._in = d; self._out = (d - 1) * self._factor + 1
+    def setOutputDimensions(self, gridDims):
+        d = np.asarray(gridDims, dtype=np.int64)
+        if np.any(d < 2): raise RuntimeError("Interpolation can only be applied to a 2^d grid or larger")
+        self._out = d; self._in = (d - 1) // self._factor + 1
+        if np.any((self._in - 1) * self._factor + 1 != self._out): raise RuntimeError("Output size is not divisible by factor")
+    def _apply(self, x): return capi.upsample_filter(x, self._dims(), self._factor)
+    def _backprop(self, g, vars_in): return capi.upsample_filter_backprop(g, self._dims(), self._factor)
+    def _spec(self): return ("upsample", self._factor)
 
 
-PythonFilter, UpsampleFilter, VertexToCellFilter, LangelaarFilter = (_out_of_scope_filter(n) for n in ("PythonFilter", "UpsampleFilter", "VertexToCellFilter", "LangelaarFilter"))
+class VertexToCellFilter(_Filter):       # TopologyOptimizationFilter.hh:528-598
+    def setInputDimensions(self, gridDims):
+        d = np.asarray(gridDims, dtype=np.int64)
+        if np.any(d < 2): raise RuntimeError("Input grid must be 2^d or larger.")
+        self._in = d; self._out = d - 1
+    def setOutputDimensions(self, gridDims):
+        self._out = np.asarray(gridDims, dtype=np.int64); self._in = self._out + 1
+    def _apply(self, x): return capi.vertex_to_cell_filter(x, self._dims())
+    def _backprop(self, g, vars_in): return capi.vertex_to_cell_filter_backprop(g, self._dims())
+    def _spec(self): return ("vertex_to_cell",)
+
+
+class LangelaarFilter(_Filter):          # TopologyOptimizationFilter.hh:601-712
+    def __init__(self):
+        super().__init__(); self._filtered = self._smax = None
+    def _apply(self, x):
+        prev = self._filtered if self._filtered is not None and self._filtered.size == x.size else None
+        self._filtered, self._smax = capi.langelaar_filter(x, self._dims(), out_prev=prev)   # m_cachedFiltered, m_cachedSmax (:622, 697-701)
+        return self._filtered.copy()
+    def _backprop(self, g, vars_in):
+        if self._filtered is None: raise RuntimeError("LangelaarFilter.backprop before apply")
+        return capi.langelaar_filter_backprop(g, vars_in, self._filtered, self._smax, self._dims())
+    def _spec(self): return ("langelaar",)
+
+
+class PythonFilter(_Filter):             # TopologyOptimizationFilter.hh:247-275
+    def __init__(self):
+        super().__init__(); self.apply_cb = None; self.backprop_cb = None
+    def _apply(self, x):
+        if self.apply_cb is None: raise RuntimeError("Apply callback must be configured")
+        out = np.zeros(int(np.prod(self._out))); self.apply_cb(x, out); return out          # callbacks write into `out` (Eigen::Ref)
+    def _backprop(self, g, vars_in):
+        if self.backprop_cb is None: raise RuntimeError("Backprop callback must be configured")
+        out = np.zeros(int(np.prod(self._in))); self.backprop_cb(g, vars_in, out); return out
+    def _spec(self):
+        return ("python", lambda x: self._apply(x), lambda g, v: self._backprop(g, v))
 
 
 class FilterChain:                       # TopologyOptimizationFilter.hh:90-187
     def __init__(self, filters, outGridDimensions):
-        self._filters = list(filters); self._dims = np.asarray(outGridDimensions, dtype=np.int64)
-        for f in self._filters: f.setInputDimensions(self._dims); f.setOutputDimensions(self._dims)
-        self._vars = [np.zeros(int(np.prod(self._dims)))]
+        self._filters = list(filters)
+        dims = np.asarray(outGridDimensions, dtype=np.int64)
+        self._out_dims = dims.copy()
+        for f in reversed(self._filters):            # setOutputDimensions (:117-132): from the physical grid backwards
+            f.setOutputDimensions(dims); dims = np.asarray(f.inputDimensions, dtype=np.int64)
+        self._dims = dims
+        self._vars = [np.zeros(int(np.prod(self._dims)))] + [np.zeros(int(np.prod(f.outputDimensions))) for f in self._filters]
     @property
     def filters(self): return self._filters
     def numVars(self): return int(np.prod(self._dims))
     numPhysicalVars = numVars            # the reference binds numPhysicalVars to numVars (VoxelFEM.cc:331)
     def gridDims(self): return self._dims
-    def physicalGridDims(self): return self._dims
+    def physicalGridDims(self): return self._out_dims
     def setDesignVars(self, xDesign):
-        v = [np.asarray(xDesign, dtype=np.float64).ravel().copy()]
+        x = np.asarray(xDesign, dtype=np.float64).ravel()
+        if x.size != self.numVars(): raise RuntimeError("Variable size mismatch")
+        v = [x.copy()]
         for f in self._filters: v.append(f._apply(v[-1]))
         self._vars = v
     def designVars(self): return self._vars[0].copy()
     def physicalVars(self): return self._vars[-1].copy()
     def backprop(self, g):
         g = np.asarray(g, dtype=np.float64).ravel()
-        if g.size != self.numPhysicalVars(): raise RuntimeError("Size mismatch")
+        if g.size != self._vars[-1].size: raise RuntimeError("Size mismatch")
         for i in range(len(self._filters) - 1, -1, -1): g = self._filters[i]._backprop(g, self._vars[i])
         return g
 
@@ -423,16 +473,21 @@ class _TOProblem:
         if len(constraints) != 1 or not isinstance(constraints[0], TotalVolumeConstraint):
             raise NotImplementedError("constraints must be [TotalVolumeConstraint] (the OC optimizer requires exactly that, OptimalityCriterion.hh:43-45)")
         self._sim, self._obj, self._constraints, self._filters = simulator, objective, list(constraints), list(filters)
-        dims = simulator.NbElementsPerDimension
-        for f in self._filters: f.setInputDimensions(dims); f.setOutputDimensions(dims)
+        dims = np.asarray(simulator.NbElementsPerDimension, dtype=np.int64)
+        for f in reversed(self._filters): f.setOutputDimensions(dims); dims = np.asarray(f.inputDimensions, dtype=np.int64)
         self._p = capi.Problem(objective.mg._m, [f._spec() for f in self._filters], self._constraints[0].volumeFraction)
         self._chain = _DeviceChainView(self)
+        self._res_cb_set = None
         objective._problem = weakref.ref(self)
 
     def _sync_solver(self):
         o = self._obj
+        if o.residual_cb is not self._res_cb_set:       # residual_cb(it, r) (TopologyOptimizationObjective.hh:93, 104)
+            cb = o.residual_cb
+            self._p.set_residual_callback(None if cb is None else (lambda it, rn: cb(it, o.mg._m.pcg_residual())))
+            self._res_cb_set = cb
         self._p.set_solver(int(o.cgIter), float(o.tol), int(o.mgIterations), int(o.mgSmoothingIterations), bool(o.fullMultigrid), bool(o.zeroInit))
-    def numVars(self): return self._sim.numElements()
+    def numVars(self): return self._p.nv
     def setVars(self, x, forceUpdate=False):
         self._sync_solver(); self._p.set_vars(x); return True
     def getVars(self): return self._p.design_vars()
@@ -458,13 +513,14 @@ class _DeviceChainView:
     def filters(self): return self._pr._filters
     def numVars(self): return self._pr.numVars()
     numPhysicalVars = numVars
-    def gridDims(self): return self._pr._sim.NbElementsPerDimension
-    physicalGridDims = gridDims
+    def gridDims(self): return self._pr._p.grid_dims(False)
+    def physicalGridDims(self): return self._pr._p.grid_dims(True)
     def designVars(self): return self._pr._p.design_vars()
     def physicalVars(self): return self._pr._p.physical_vars()
     def setDesignVars(self, xDesign): self._pr.setVars(xDesign)
     def backprop(self, g):
-        fc = FilterChain(self._pr._filters, self.gridDims()); fc.setDesignVars(self.designVars())
+        # back-propagation of an arbitrary physical-space gradient through the problem's filters at the current design variables
+        fc = FilterChain(self._pr._filters, self.physicalGridDims()); fc.setDesignVars(self.designVars())
         return fc.backprop(g)
 
 

@@ -1684,6 +1684,56 @@ int vf_filter_project_backprop(int64_t n, double beta, const double *in, const d
     h2d(a.p, in, n, c.stream); h2d(v.p, vars, n, c.stream); launch_filter_project_backprop(c, n, beta, a.p, v.p, b.p); d2h(out, b.p, n, c.stream); VF_CATCH
 }
 
+static long long prod_sizes(int dim, const int *sz) { long long n = 1; for (int d = 0; d < dim; ++d) n *= sz[d]; return n; }
+// UpsampleFilter (TopologyOptimizationFilter.hh:418-523): coarse_sizes -> (coarse_sizes - 1) * factor + 1
+int vf_filter_upsample(int dim, const int64_t *coarse_sizes, int factor, const double *in, double *out) {
+    VF_TRY ensure_device(); int cs[3] = {1, 1, 1}, fs[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d) { cs[d] = (int)coarse_sizes[d]; fs[d] = (cs[d] - 1) * factor + 1; if (cs[d] < 2) throw std::runtime_error("Interpolation can only be applied to a 2^d grid or larger"); }
+    const long long nc = prod_sizes(dim, cs), nf = prod_sizes(dim, fs);
+    DevBuf<double> a, b; a.alloc(nc, false); b.alloc(nf, false); LaunchCtx c = default_ctx();
+    h2d(a.p, in, nc, c.stream); launch_filter_upsample(c, dim, cs, factor, a.p, b.p); d2h(out, b.p, nf, c.stream); VF_CATCH
+}
+int vf_filter_upsample_backprop(int dim, const int64_t *coarse_sizes, int factor, const double *d_dout, double *d_din) {
+    VF_TRY ensure_device(); int cs[3] = {1, 1, 1}, fs[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d) { cs[d] = (int)coarse_sizes[d]; fs[d] = (cs[d] - 1) * factor + 1; }
+    const long long nc = prod_sizes(dim, cs), nf = prod_sizes(dim, fs);
+    DevBuf<double> a, b; a.alloc(nf, false); b.alloc(nc, false); LaunchCtx c = default_ctx();
+    h2d(a.p, d_dout, nf, c.stream); launch_filter_upsample_backprop(c, dim, cs, factor, a.p, b.p); d2h(d_din, b.p, nc, c.stream); VF_CATCH
+}
+// VertexToCellFilter (:528-598): vertex_sizes -> vertex_sizes - 1
+int vf_filter_vertex_to_cell(int dim, const int64_t *vertex_sizes, const double *in, double *out) {
+    VF_TRY ensure_device(); int vs[3] = {1, 1, 1}, es[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d) { vs[d] = (int)vertex_sizes[d]; es[d] = vs[d] - 1; if (vs[d] < 2) throw std::runtime_error("Input grid must be 2^d or larger."); }
+    const long long nv = prod_sizes(dim, vs), ne = prod_sizes(dim, es);
+    DevBuf<double> a, b; a.alloc(nv, false); b.alloc(ne, false); LaunchCtx c = default_ctx();
+    h2d(a.p, in, nv, c.stream); launch_filter_v2c(c, dim, vs, a.p, b.p); d2h(out, b.p, ne, c.stream); VF_CATCH
+}
+int vf_filter_vertex_to_cell_backprop(int dim, const int64_t *vertex_sizes, const double *d_dout, double *d_din) {
+    VF_TRY ensure_device(); int vs[3] = {1, 1, 1}, es[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d) { vs[d] = (int)vertex_sizes[d]; es[d] = vs[d] - 1; }
+    const long long nv = prod_sizes(dim, vs), ne = prod_sizes(dim, es);
+    DevBuf<double> a, b; a.alloc(ne, false); b.alloc(nv, false); LaunchCtx c = default_ctx();
+    h2d(a.p, d_dout, ne, c.stream); launch_filter_v2c_backprop(c, dim, vs, a.p, b.p); d2h(d_din, b.p, nv, c.stream); VF_CATCH
+}
+// LangelaarFilter (:601-712).  `out` is IN/OUT: in 3D the support of a voxel holds the voxel itself (NDVector.hh:211-229 walks the first
+// N - 1 axes), so the previous content of the output array is read -- pass the array the reference would be writing into.  smax
+// receives m_cachedSmax; the output itself is m_cachedFiltered.
+int vf_filter_langelaar(int dim, const int64_t *sizes, const double *in, double *out, double *smax) {
+    VF_TRY ensure_device(); int sz[3] = {1, 1, 1}; for (int d = 0; d < dim; ++d) sz[d] = (int)sizes[d];
+    const long long n = prod_sizes(dim, sz);
+    DevBuf<double> a, b, m; a.alloc(n, false); b.alloc(n, false); m.alloc(n, true); LaunchCtx c = default_ctx();
+    h2d(a.p, in, n, c.stream); h2d(b.p, out, n, c.stream); launch_filter_langelaar(c, dim, sz, a.p, b.p, m.p);
+    d2h(out, b.p, n, c.stream); if (smax) d2h(smax, m.p, n, c.stream); VF_CATCH
+}
+int vf_filter_langelaar_backprop(int dim, const int64_t *sizes, const double *d_dout, const double *vars, const double *filtered, const double *smax, double *d_din) {
+    VF_TRY ensure_device(); int sz[3] = {1, 1, 1}; for (int d = 0; d < dim; ++d) sz[d] = (int)sizes[d];
+    const long long n = prod_sizes(dim, sz);
+    DevBuf<double> g, v, f, m, scr, o; g.alloc(n, false); v.alloc(n, false); f.alloc(n, false); m.alloc(n, false); scr.alloc(3 * n, true); o.alloc(n, false);
+    LaunchCtx c = default_ctx();
+    h2d(g.p, d_dout, n, c.stream); h2d(v.p, vars, n, c.stream); h2d(f.p, filtered, n, c.stream); h2d(m.p, smax, n, c.stream);
+    launch_filter_langelaar_backprop(c, dim, sz, g.p, v.p, f.p, m.p, scr.p, o.p); d2h(d_din, o.p, n, c.stream); VF_CATCH
+}
+
 // ---- device-pointer variants (element arrays stay in HBM; kernels run on the simulator's stream) ------------------------
 // Building blocks of a topology-optimization iteration whose element arrays are partitioned into slabs (one per GPU): the
 // host side exchanges filter halos and all-reduces scalars between these calls (voxelfem_b200/capi.py: SlabProblem).
@@ -1723,23 +1773,72 @@ int vf_sim_synchronize(vf_sim *s) { VF_TRY VF_CUDA(cudaStreamSynchronize(s->stre
 // ---------------------------------------------------------------------------
 // Topology optimization problem
 // ---------------------------------------------------------------------------
-struct FilterSpec { int kind, radius, type; double beta; };
+struct FilterSpec {
+    int kind, radius, type; double beta;       // spec quadruple {kind, radius | factor, type, beta}
+    int in[3] = {1, 1, 1}, out[3] = {1, 1, 1}; // grid sizes (first N entries), set by vf_top_create from the physical grid backwards (FilterChain::setOutputDimensions, TopologyOptimizationFilter.hh:117-132)
+    long long nIn = 0, nOut = 0;
+    // LangelaarFilter state: smax of every voxel's support and the filtered values of the LAST application (m_cachedSmax, m_cachedFiltered, :697-701)
+    std::unique_ptr<DevBuf<double>> smaxCache, filteredCache, lgScratch;
+    // PythonFilter (:247-275): host callbacks
+    vf_filter_apply_cb applyCb = nullptr; vf_filter_backprop_cb backpropCb = nullptr; void *user = nullptr;
+};
 struct vf_top {
     vf_mg *mg; vf_sim *sim;
     std::vector<FilterSpec> filters; double volFrac;
     std::vector<std::unique_ptr<DevBuf<double>>> vars; // m_vars of FilterChain (TopologyOptimizationFilter.hh:111-132)
     DevBuf<double> u, f, dJ, dc, stepped, xv, tmp, scalar, scratch;
+    std::vector<double> hostA, hostB, hostC;           // staging for PythonFilter callbacks
+    vf_pcg_callback residualCb = nullptr; void *residualUser = nullptr;   // MultigridComplianceObjective::residual_cb
     int cgIter = 100; double tol = 1e-5; int mgIt = 1, mgSmooth = 2; bool fmg = true, zeroInit = false; // TopologyOptimizationObjective.hh:99-103
     double lamMin = 1, lamMax = 2; // OptimalityCriterion.hh:46-49
     int lastPcgIters = 0;
     double *hostScalar = nullptr;
     ~vf_top() { if (hostScalar) cudaFreeHost(hostScalar); }
-    long long ne() const { return sim->g.numElems; }
-    int sizes3[3];
-    void applyFilter(const FilterSpec &fs, const double *in, double *out) {
-        int sz[3] = {(int)sim->ne[0], (int)sim->ne[1], (int)sim->ne[2]};
-        if (fs.kind == VF_FILTER_SMOOTH) launch_filter_smooth(mg->ctx, sim->N, sz, fs.radius, fs.type, in, out);
-        else launch_filter_project(mg->ctx, ne(), fs.beta, in, out);
+    long long ne() const { return sim->g.numElems; }                              // physical variables (one per element)
+    long long nDesign() const { return filters.empty() ? ne() : filters.front().nIn; }
+    long long nMax() const { long long m = ne(); for (const auto &fs : filters) m = std::max(m, std::max(fs.nIn, fs.nOut)); return m; }
+    // Filter::apply; `out` is in/out for the Langelaar filter (in 3D a voxel's support holds the voxel itself: its previous value is read)
+    void applyFilter(FilterSpec &fs, const double *in, double *out) {
+        const int N = sim->N;
+        switch (fs.kind) {
+            case VF_FILTER_SMOOTH:  launch_filter_smooth(mg->ctx, N, fs.in, fs.radius, fs.type, in, out); break;
+            case VF_FILTER_PROJECT: launch_filter_project(mg->ctx, fs.nIn, fs.beta, in, out); break;
+            case VF_FILTER_UPSAMPLE: launch_filter_upsample(mg->ctx, N, fs.in, fs.radius, in, out); break;
+            case VF_FILTER_VERTEX_TO_CELL: launch_filter_v2c(mg->ctx, N, fs.in, in, out); break;
+            case VF_FILTER_LANGELAAR:
+                launch_filter_langelaar(mg->ctx, N, fs.in, in, out, fs.smaxCache->p);
+                VF_CUDA(cudaMemcpyAsync(fs.filteredCache->p, out, sizeof(double) * fs.nOut, cudaMemcpyDeviceToDevice, mg->ctx.stream));
+                break;
+            case VF_FILTER_PYTHON: {
+                if (!fs.applyCb) throw std::runtime_error("Apply callback must be configured");
+                hostA.resize(fs.nIn); hostB.assign(fs.nOut, 0.0);
+                d2h(hostA.data(), in, fs.nIn, mg->ctx.stream);
+                if (fs.applyCb(hostA.data(), fs.nIn, hostB.data(), fs.nOut, fs.user)) throw std::runtime_error("PythonFilter apply callback failed");
+                h2d(out, hostB.data(), fs.nOut, mg->ctx.stream); VF_CUDA(cudaStreamSynchronize(mg->ctx.stream));
+                break;
+            }
+            default: throw std::runtime_error("unknown filter kind");
+        }
+    }
+    // Filter::backprop(in = dJ/d(out), vars = the filter's input, out = dJ/d(in))
+    void backpropFilter(FilterSpec &fs, const double *g, const double *vars_, double *out) {
+        const int N = sim->N;
+        switch (fs.kind) {
+            case VF_FILTER_SMOOTH:  launch_filter_smooth(mg->ctx, N, fs.in, fs.radius, fs.type, g, out); break;     // symmetric operator (:297-310)
+            case VF_FILTER_PROJECT: launch_filter_project_backprop(mg->ctx, fs.nIn, fs.beta, g, vars_, out); break;
+            case VF_FILTER_UPSAMPLE: launch_filter_upsample_backprop(mg->ctx, N, fs.in, fs.radius, g, out); break;
+            case VF_FILTER_VERTEX_TO_CELL: launch_filter_v2c_backprop(mg->ctx, N, fs.in, g, out); break;
+            case VF_FILTER_LANGELAAR: launch_filter_langelaar_backprop(mg->ctx, N, fs.in, g, vars_, fs.filteredCache->p, fs.smaxCache->p, fs.lgScratch->p, out); break;
+            case VF_FILTER_PYTHON: {
+                if (!fs.backpropCb) throw std::runtime_error("Backprop callback must be configured");
+                hostA.resize(fs.nOut); hostB.resize(fs.nIn); hostC.assign(fs.nIn, 0.0);
+                d2h(hostA.data(), g, fs.nOut, mg->ctx.stream); d2h(hostB.data(), vars_, fs.nIn, mg->ctx.stream);
+                if (fs.backpropCb(hostA.data(), fs.nOut, hostB.data(), fs.nIn, hostC.data(), fs.user)) throw std::runtime_error("PythonFilter backprop callback failed");
+                h2d(out, hostC.data(), fs.nIn, mg->ctx.stream); VF_CUDA(cudaStreamSynchronize(mg->ctx.stream));
+                break;
+            }
+            default: throw std::runtime_error("unknown filter kind");
+        }
     }
     double readScalar() {
         VF_CUDA(cudaMemcpyAsync(hostScalar, scalar.p, sizeof(double), cudaMemcpyDeviceToHost, mg->ctx.stream));
@@ -1751,7 +1850,7 @@ struct vf_top {
         if (xPhysDev != sim->rho.p) VF_CUDA(cudaMemcpyAsync(sim->rho.p, xPhysDev, sizeof(double) * ne(), cudaMemcpyDeviceToDevice, mg->ctx.stream));
         sim->updateModuli();
         if (zeroInit) VF_CUDA(cudaMemsetAsync(u.p, 0, sizeof(double) * u.n, mg->ctx.stream));
-        mg_pcg(*mg, u.p, f.p, cgIter, tol, mgIt, mgSmooth, fmg, false, nullptr, nullptr);
+        mg_pcg(*mg, u.p, f.p, cgIter, tol, mgIt, mgSmooth, fmg, false, residualCb, residualUser);   // residual_cb (TopologyOptimizationObjective.hh:93, 104)
         lastPcgIters = mg->lastIters;
     }
     void setVarsDev() { // FilterChain::setDesignVars (:142-152) + updateCache
@@ -1759,14 +1858,10 @@ struct vf_top {
         for (size_t i = 0; i < filters.size(); ++i) applyFilter(filters[i], vars[i]->p, vars[i + 1]->p);
         updateCache(vars.back()->p);
     }
-    void backprop(DevBuf<double> &g, DevBuf<double> &scr) { // FilterChain::backprop (:162-170); result left in g
+    void backprop(DevBuf<double> &g, DevBuf<double> &scr) { // FilterChain::backprop (:162-170); g: physical size in, design size out
         double *a = g.p, *b = scr.p;
-        for (size_t i = filters.size(); i-- > 0;) {
-            if (filters[i].kind == VF_FILTER_SMOOTH) { int sz[3] = {(int)sim->ne[0], (int)sim->ne[1], (int)sim->ne[2]}; launch_filter_smooth(mg->ctx, sim->N, sz, filters[i].radius, filters[i].type, a, b); }
-            else launch_filter_project_backprop(mg->ctx, ne(), filters[i].beta, a, vars[i]->p, b);
-            std::swap(a, b);
-        }
-        if (a != g.p) VF_CUDA(cudaMemcpyAsync(g.p, a, sizeof(double) * ne(), cudaMemcpyDeviceToDevice, mg->ctx.stream));
+        for (size_t i = filters.size(); i-- > 0;) { backpropFilter(filters[i], a, vars[i]->p, b); std::swap(a, b); }
+        if (a != g.p) VF_CUDA(cudaMemcpyAsync(g.p, a, sizeof(double) * nDesign(), cudaMemcpyDeviceToDevice, mg->ctx.stream));
     }
     void objectiveGradient() { // into dJ
         TraceScope ts("evaluateObjectiveGradient");            // TopologyOptimizationProblem.hh:78
@@ -1783,9 +1878,9 @@ struct vf_top {
         return 1.0 - (readScalar() / double(ne())) / volFrac;
     }
     double ceval(double lambda, double m, double p) { // OptimalityCriterion.hh:64-83 + TopologyOptimizationProblem.hh:58-66
-        launch_oc_update(mg->ctx, ne(), vars[0]->p, dJ.p, dc.p, lambda, m, p, stepped.p);
+        launch_oc_update(mg->ctx, nDesign(), vars[0]->p, dJ.p, dc.p, lambda, m, p, stepped.p);
         const double *cur = stepped.p; double *a = xv.p, *b = tmp.p;
-        for (const auto &fs : filters) { applyFilter(fs, cur, a); cur = a; std::swap(a, b); }
+        for (auto &fs : filters) { applyFilter(fs, cur, a); cur = a; std::swap(a, b); }   // FilterChain::applyInPlace (:154-160)
         return constraintOf(cur);
     }
 };
@@ -1795,11 +1890,36 @@ int vf_top_create(vf_mg *mg, int nf, const double *spec, double volFrac, vf_top 
     VF_TRY
     auto t = std::make_unique<vf_top>();
     t->mg = mg; t->sim = mg->sim; t->volFrac = volFrac;
-    for (int i = 0; i < nf; ++i) t->filters.push_back({(int)spec[4 * i], (int)spec[4 * i + 1], (int)spec[4 * i + 2], spec[4 * i + 3]});
-    const long long ne = t->ne(); const size_t len = (size_t)t->sim->g.numNodes * t->sim->N;
-    for (int i = 0; i <= nf; ++i) { t->vars.push_back(std::make_unique<DevBuf<double>>()); t->vars.back()->alloc(ne, true); }
+    const int N = t->sim->N;
+    for (int i = 0; i < nf; ++i) { FilterSpec fs; fs.kind = (int)spec[4 * i]; fs.radius = (int)spec[4 * i + 1]; fs.type = (int)spec[4 * i + 2]; fs.beta = spec[4 * i + 3]; t->filters.push_back(std::move(fs)); }
+    // grid sizes from the physical grid backwards (FilterChain::setOutputDimensions, TopologyOptimizationFilter.hh:117-132)
+    int dims[3] = {1, 1, 1}; for (int a = 0; a < N; ++a) dims[a] = (int)t->sim->ne[a];
+    for (int i = nf - 1; i >= 0; --i) {
+        FilterSpec &fs = t->filters[i];
+        for (int a = 0; a < 3; ++a) fs.out[a] = fs.in[a] = dims[a];
+        if (fs.kind == VF_FILTER_UPSAMPLE) {                       // m_setOutputDimensions (:448-454)
+            const int f = fs.radius;
+            if (f < 1) throw std::runtime_error("UpsampleFilter factor must be positive");
+            for (int a = 0; a < N; ++a) {
+                if (dims[a] < 2) throw std::runtime_error("Interpolation can only be applied to a 2^d grid or larger");
+                fs.in[a] = (dims[a] - 1) / f + 1;
+                if ((fs.in[a] - 1) * f + 1 != dims[a]) throw std::runtime_error("Output size is not divisible by factor");
+            }
+        } else if (fs.kind == VF_FILTER_VERTEX_TO_CELL) {          // (:593-596)
+            for (int a = 0; a < N; ++a) fs.in[a] = dims[a] + 1;
+        } else if (fs.kind < 0 || fs.kind > VF_FILTER_PYTHON) throw std::runtime_error("unknown filter kind");
+        fs.nIn = fs.nOut = 1;
+        for (int a = 0; a < N; ++a) { fs.nIn *= fs.in[a]; fs.nOut *= fs.out[a]; dims[a] = fs.in[a]; }
+        if (fs.kind == VF_FILTER_LANGELAAR) {
+            fs.smaxCache = std::make_unique<DevBuf<double>>(); fs.smaxCache->alloc(fs.nIn, true);
+            fs.filteredCache = std::make_unique<DevBuf<double>>(); fs.filteredCache->alloc(fs.nIn, true);
+            fs.lgScratch = std::make_unique<DevBuf<double>>(); fs.lgScratch->alloc(3 * fs.nIn, true);
+        }
+    }
+    const long long ne = t->ne(), nmax = t->nMax(); const size_t len = (size_t)t->sim->g.numNodes * t->sim->N;
+    for (int i = 0; i <= nf; ++i) { t->vars.push_back(std::make_unique<DevBuf<double>>()); t->vars.back()->alloc(i < nf ? t->filters[i].nIn : ne, true); }
     t->u.alloc(len, true); t->f.alloc(len, true);
-    t->dJ.alloc(ne, true); t->dc.alloc(ne, true); t->stepped.alloc(ne, true); t->xv.alloc(ne, true); t->tmp.alloc(ne, true);
+    t->dJ.alloc(nmax, true); t->dc.alloc(nmax, true); t->stepped.alloc(t->nDesign(), true); t->xv.alloc(nmax, true); t->tmp.alloc(nmax, true);
     t->scalar.alloc(1, true); t->scratch.alloc(reduce_scratch_doubles(), true);
     VF_CUDA(cudaMallocHost(&t->hostScalar, sizeof(double)));
     sim_build_load_dev(*t->sim, t->f.p);      // ComplianceObjective ctor (TopologyOptimizationObjective.hh:32-35)
@@ -1808,16 +1928,30 @@ int vf_top_create(vf_mg *mg, int nf, const double *spec, double volFrac, vf_top 
     *out = t.release();
     VF_CATCH
 }
+int64_t vf_top_num_vars(const vf_top *t) { return t->nDesign(); }                 /* FilterChain::numVars (:134) */
+int64_t vf_top_num_physical_vars(const vf_top *t) { return t->ne(); }             /* numPhysicalVars (:138) */
+int vf_top_get_grid_dims(const vf_top *t, int physical, int64_t *dims) {          /* gridDims / physicalGridDims (:136, 139) */
+    const int N = t->sim->N;
+    for (int a = 0; a < N; ++a) dims[a] = (physical || t->filters.empty()) ? (int64_t)t->sim->ne[a] : t->filters.front().in[a];
+    return 0;
+}
+int vf_top_set_residual_callback(vf_top *t, vf_pcg_callback cb, void *user) { t->residualCb = cb; t->residualUser = user; return 0; }
+int vf_top_set_python_filter(vf_top *t, int index, vf_filter_apply_cb apply_cb, vf_filter_backprop_cb backprop_cb, void *user) {
+    VF_TRY
+    if (index < 0 || index >= (int)t->filters.size() || t->filters[index].kind != VF_FILTER_PYTHON) throw std::runtime_error("filter " + std::to_string(index) + " is not a PythonFilter");
+    t->filters[index].applyCb = apply_cb; t->filters[index].backpropCb = backprop_cb; t->filters[index].user = user;
+    VF_CATCH
+}
 int vf_top_destroy(vf_top *t) { VF_TRY if (t) { cudaStreamSynchronize(t->mg->ctx.stream); delete t; } VF_CATCH }
 int vf_top_set_solver(vf_top *t, int cgIter, double tol, int mgIt, int mgSmooth, int fmg, int zeroInit) { t->cgIter = cgIter; t->tol = tol; t->mgIt = mgIt; t->mgSmooth = mgSmooth; t->fmg = fmg != 0; t->zeroInit = zeroInit != 0; return 0; }
-int vf_top_set_vars(vf_top *t, const double *x) { VF_TRY h2d(t->vars[0]->p, x, t->ne(), t->mg->ctx.stream); t->setVarsDev(); VF_CUDA(cudaStreamSynchronize(t->mg->ctx.stream)); VF_CATCH }
-int vf_top_get_vars(vf_top *t, int which, double *out) { VF_TRY d2h(out, which == 0 ? t->vars.front()->p : t->vars.back()->p, t->ne(), t->mg->ctx.stream); VF_CATCH }
+int vf_top_set_vars(vf_top *t, const double *x) { VF_TRY h2d(t->vars[0]->p, x, t->nDesign(), t->mg->ctx.stream); t->setVarsDev(); VF_CUDA(cudaStreamSynchronize(t->mg->ctx.stream)); VF_CATCH }
+int vf_top_get_vars(vf_top *t, int which, double *out) { VF_TRY d2h(out, which == 0 ? t->vars.front()->p : t->vars.back()->p, which == 0 ? t->nDesign() : t->ne(), t->mg->ctx.stream); VF_CATCH }
 int vf_top_compliance(vf_top *t, double *out) {
     VF_TRY launch_dot_plain(t->mg->ctx, (long long)t->u.n, t->f.p, t->u.p, t->scalar.p, t->scratch.p); *out = 0.5 * t->readScalar(); VF_CATCH
 }
 int vf_top_constraint(vf_top *t, double *out) { VF_TRY *out = t->constraintOf(t->vars.back()->p); VF_CATCH }
-int vf_top_objective_gradient(vf_top *t, double *g) { VF_TRY t->objectiveGradient(); d2h(g, t->dJ.p, t->ne(), t->mg->ctx.stream); VF_CATCH }
-int vf_top_constraint_jacobian(vf_top *t, double *g) { VF_TRY t->constraintJacobian(); d2h(g, t->dc.p, t->ne(), t->mg->ctx.stream); VF_CATCH }
+int vf_top_objective_gradient(vf_top *t, double *g) { VF_TRY t->objectiveGradient(); d2h(g, t->dJ.p, t->nDesign(), t->mg->ctx.stream); VF_CATCH }
+int vf_top_constraint_jacobian(vf_top *t, double *g) { VF_TRY t->constraintJacobian(); d2h(g, t->dc.p, t->nDesign(), t->mg->ctx.stream); VF_CATCH }
 int vf_top_get_u(vf_top *t, double *u) { VF_TRY d2h(u, t->u.p, t->u.n, t->mg->ctx.stream); VF_CATCH }
 int vf_top_last_pcg_iterations(vf_top *t) { return t->lastPcgIters; }
 int vf_top_get_lambda_bracket(vf_top *t, double *lo, double *hi) { *lo = t->lamMin; *hi = t->lamMax; return 0; }
@@ -1852,7 +1986,7 @@ int vf_top_oc_step(vf_top *t, double m, double p, double ctol, int *nevalsOut) {
     t->objectiveGradient(); t->constraintJacobian();
     const int nevals = oc_bisect(t, m, p, ctol);
     // m_p.setVars(m_steppedVars) (:133)
-    VF_CUDA(cudaMemcpyAsync(t->vars[0]->p, t->stepped.p, sizeof(double) * t->ne(), cudaMemcpyDeviceToDevice, t->mg->ctx.stream));
+    VF_CUDA(cudaMemcpyAsync(t->vars[0]->p, t->stepped.p, sizeof(double) * t->nDesign(), cudaMemcpyDeviceToDevice, t->mg->ctx.stream));
     t->setVarsDev();
     VF_CUDA(cudaStreamSynchronize(t->mg->ctx.stream));
     if (nevalsOut) *nevalsOut = nevals;
@@ -1865,10 +1999,10 @@ int vf_top_oc_step(vf_top *t, double m, double p, double ctol, int *nevalsOut) {
 int vf_top_oc_search(vf_top *t, const double *dJ, double m, double p, double ctol, double *stepped, int *nevalsOut) {
     VF_TRY
     TraceScope ts("OC step");
-    if (dJ) h2d(t->dJ.p, dJ, (size_t)t->ne(), t->mg->ctx.stream); else t->objectiveGradient();
+    if (dJ) h2d(t->dJ.p, dJ, (size_t)t->nDesign(), t->mg->ctx.stream); else t->objectiveGradient();
     t->constraintJacobian();
     const int nevals = oc_bisect(t, m, p, ctol);
-    d2h(stepped, t->stepped.p, (size_t)t->ne(), t->mg->ctx.stream);
+    d2h(stepped, t->stepped.p, (size_t)t->nDesign(), t->mg->ctx.stream);
     if (nevalsOut) *nevalsOut = nevals;
     VF_CATCH
 }

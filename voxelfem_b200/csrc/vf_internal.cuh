@@ -323,6 +323,14 @@ void launch_self_weight_load(const LaunchCtx &ctx, const GridDesc &g, const doub
 void launch_filter_smooth(const LaunchCtx &ctx, int N, const int *sizes, int radius, int type, const double *in, double *out);
 void launch_filter_project(const LaunchCtx &ctx, long long n, double beta, const double *in, double *out);
 void launch_filter_project_backprop(const LaunchCtx &ctx, long long n, double beta, const double *in, const double *vars, double *out);
+// --- vf_filters.cu: UpsampleFilter, VertexToCellFilter, LangelaarFilter (TopologyOptimizationFilter.hh:418-712); sizes: first N entries
+void launch_filter_upsample(const LaunchCtx &ctx, int N, const int *coarseSizes, int factor, const double *in, double *out);
+void launch_filter_upsample_backprop(const LaunchCtx &ctx, int N, const int *coarseSizes, int factor, const double *dout, double *din);
+void launch_filter_v2c(const LaunchCtx &ctx, int N, const int *vertexSizes, const double *in, double *out);
+void launch_filter_v2c_backprop(const LaunchCtx &ctx, int N, const int *vertexSizes, const double *dout, double *din);
+void launch_filter_langelaar(const LaunchCtx &ctx, int N, const int *sizes, const double *in, double *out, double *smaxCache);
+void launch_filter_langelaar_backprop(const LaunchCtx &ctx, int N, const int *sizes, const double *g_in, const double *vars, const double *filtered,
+                                      const double *smaxCache, double *scratch, double *out);
 // OC update (OptimalityCriterion.hh:64-83): out = clamp(x0 * (dJ / (dc*lambda))^p, x0 -+ m, [0,1]); non-finite -> x0
 void launch_oc_update(const LaunchCtx &ctx, long long n, const double *x0, const double *dJ, const double *dc, double lambda, double m, double p, double *out);
 void launch_sum(const LaunchCtx &ctx, long long n, const double *x, double *result, double *scratch);

@@ -168,8 +168,8 @@ public:
     const BBoxN &domain() const { return m_domain; }
 
     // material: isotropic ETensor(E, nu) (MeshFEM ElasticityTensor.hh:100-115) or the flattened (N(N+1)/2)^2 tensor
-    void setIsotropicETensor(double E, double nu) { check(vf_sim_set_isotropic(m_h, E, nu)); }
-    void setETensor(const std::vector<double> &flattened) { check(vf_sim_set_elasticity_tensor(m_h, flattened.data())); }
+    void setIsotropicETensor(double E, double nu) { check(vf_sim_set_isotropic(m_h, E, nu)); m_et = ETensorState{true, E, nu, {}}; }
+    void setETensor(const std::vector<double> &flattened) { check(vf_sim_set_elasticity_tensor(m_h, flattened.data())); m_et = ETensorState{false, 0, 0, flattened}; }
     void readMaterial(const std::string &materialPath) {   // isotropic_material files (MeshFEM Materials.cc:291-311)
         std::ifstream f(materialPath); if (!f) throw std::runtime_error("Couldn't open material " + materialPath);
         std::stringstream ss; ss << f.rdbuf(); const std::string s = ss.str();
@@ -227,8 +227,105 @@ public:
     VXd complianceGradientFlattened(const VField &u) const { VXd g(numElements()); check(vf_sim_compliance_gradient(m_h, u.data(), g.data(), 0)); return g; }
     VXd elementEnergyDensity(const VField &u) const { VXd e(numElements()); check(vf_sim_element_energy_density(m_h, u.data(), e.data())); return e; }
 
+    // ---- element / node bookkeeping (TensorProductSimulator.hh:1532-1651; NDVector.hh:249-275) ----
+    VNd getStretchings() const { VNd r; for (size_t d = 0; d < N; ++d) r[d] = (m_domain.maxCorner[d] - m_domain.minCorner[d]) / double(m_ne[d]); return r; }
+    double elementVolume(size_t /* ei */ = 0) const { double v = 1; for (double h : getStretchings()) v *= h; return v; }
+    EigenNDIndex unflattenNode(size_t ni) const { EigenNDIndex r; for (size_t d = N; d-- > 0;) { r[d] = ni % (m_ne[d] + 1); ni /= (m_ne[d] + 1); } return r; }
+    EigenNDIndex unflattenElement(size_t ei) const { EigenNDIndex r; for (size_t d = N; d-- > 0;) { r[d] = ei % m_ne[d]; ei /= m_ne[d]; } return r; }
+    VNd nodePosition(size_t ni) const { const auto c = unflattenNode(ni); const auto h = getStretchings(); VNd p; for (size_t d = 0; d < N; ++d) p[d] = m_domain.minCorner[d] + double(c[d]) * h[d]; return p; }
+    size_t elementIndexForGridCell(const EigenNDIndex &cellIdxs) const { size_t r = 0; for (size_t d = 0; d < N; ++d) r = r * m_ne[d] + cellIdxs[d]; return r; }
+    size_t elemNodeGlobalIndex(size_t ei, size_t n) const {
+        const auto e = unflattenElement(ei); size_t r = 0;
+        for (size_t d = 0; d < N; ++d) r = r * (m_ne[d] + 1) + e[d] + ((n >> (N - 1 - d)) & 1);
+        return r;
+    }
+    std::vector<size_t> elementNodes(size_t ei) const { std::vector<size_t> r(size_t(1) << N); for (size_t n = 0; n < r.size(); ++n) r[n] = elemNodeGlobalIndex(ei, n); return r; }
+    double elementDensity(size_t ei) const { return getDensities().at(ei); }
+    double elementYoungModulusScaleFactor(size_t ei) const { return getYoungModulusScaleFactor().at(ei); }
+    std::vector<double> elementStiffnessMatrix(size_t ei) const { auto K = fullDensityElementStiffnessMatrix(); const double E = elementYoungModulusScaleFactor(ei); for (double &v : K) v *= E; return K; }
+    void setDensity(size_t ei, double value) { auto rho = getDensities(); rho.at(ei) = value; setDensities(rho); }
+    void setDensitiesFromCoarseGrid(size_t upscalingFactor, const VXd &rho) {   // (:309-320 of the reference's density setters)
+        EigenNDIndex cs; size_t nc = 1; for (size_t d = 0; d < N; ++d) { cs[d] = m_ne[d] / upscalingFactor; nc *= cs[d]; }
+        if (rho.size() != nc) throw std::runtime_error("Density vector size mismatch");
+        VXd fine(numElements());
+        for (size_t e = 0; e < fine.size(); ++e) { const auto c = unflattenElement(e); size_t ci = 0; for (size_t d = 0; d < N; ++d) ci = ci * cs[d] + c[d] / upscalingFactor; fine[e] = rho[ci]; }
+        setDensities(fine);
+    }
+    double getFabricationMaskHeight() const { int64_t a = 0, b = 0; double h = 0; check(vf_sim_get_mask_info(m_h, &a, &b, &h)); return h; }
+    void applySymmetryConditions(const std::array<bool, N> &symmetry_axes, const std::array<bool, N> &minMaxFace = {}) {
+        int axes = 0, faces = 0; for (size_t d = 0; d < N; ++d) { axes |= int(symmetry_axes[d]) << d; faces |= int(minMaxFace[d]) << d; }
+        check(vf_sim_apply_symmetry_conditions(m_h, axes, faces));
+    }
+    // material as set (needed to configure derived simulators)
+    struct ETensorState { bool isotropic = true; double E = 1, nu = 0; std::vector<double> D; };
+    const ETensorState &getETensor() const { return m_et; }
+    void setETensor(const ETensorState &et) { if (et.isotropic) setIsotropicETensor(et.E, et.nu); else setETensor(et.D); }
+
+    // ---- layer-by-layer helpers (:1852-1923) and downsampling (:1926-1992) ----
+    static constexpr size_t BUILD_DIRECTION = 1;
+    std::shared_ptr<TensorProductSimulator> getIntermediateFabricationShape(double hfrac, bool validateBoundaryConditions = true, InterpolationLaw law = InterpolationLaw::SIMP) const {
+        if (hfrac < 0 || hfrac > 1) throw std::runtime_error("hfrac is out of bounds");
+        const size_t full = m_ne[BUILD_DIRECTION]; const size_t nh = (size_t)std::llround(hfrac * double(full));
+        if (std::abs(hfrac * double(full) - double(nh)) > 1e-10) throw std::runtime_error("hfrac chops off a noninteger number of element layers");
+        auto ne = m_ne; ne[BUILD_DIRECTION] = nh;
+        auto sub = m_domain; sub.maxCorner[BUILD_DIRECTION] = sub.minCorner[BUILD_DIRECTION] + hfrac * (sub.maxCorner[BUILD_DIRECTION] - sub.minCorner[BUILD_DIRECTION]);
+        auto r = std::make_shared<TensorProductSimulator>(sub, ne);
+        r->setInterpolationLaw(law);
+        r->setETensor(m_et);
+        transferDensitiesToIntermediateFabricationShape(*r);
+        r->setE_min(m_Emin); r->setE_0(m_E0); r->setSIMPExponent(m_gamma);           // the RAMP factor keeps its default (:1881-1883)
+        const std::runtime_error unexpectedBC("Original simulator has unexpected boundary conditions for layer-by-layer simulation");
+        double g2 = 0; for (double g : m_gravity) g2 += g * g;
+        if (g2 == 0) { if (validateBoundaryConditions) throw unexpectedBC; VNd g{}; g[BUILD_DIRECTION] = -1; r->setGravity(g); }
+        else r->setGravity(m_gravity);
+        if (validateBoundaryConditions) {                                                // (:1893-1907)
+            if (vf_sim_num_force_nodes(m_h) != 0 || vf_sim_num_nonzero_dirichlet_values(m_h) != 0) throw unexpectedBC;
+            const auto mask = getDirichletMask(); const uint8_t fullMask = uint8_t((1u << N) - 1u);
+            for (size_t ni = 0; ni < mask.size(); ++ni) { const bool base = unflattenNode(ni)[BUILD_DIRECTION] == 0; if (base ? mask[ni] != fullMask : mask[ni] != 0) throw unexpectedBC; }
+        }
+        double ext = 0; for (size_t d = 0; d < N; ++d) ext = std::max(ext, sub.maxCorner[d] - sub.minCorner[d]);
+        VNd lo = sub.minCorner, hi = sub.maxCorner, zero{}; const double eps = 1e-9 * ext;
+        for (size_t d = 0; d < N; ++d) { lo[d] -= eps; hi[d] += eps; }
+        hi[BUILD_DIRECTION] = sub.minCorner[BUILD_DIRECTION] + eps;
+        r->addDirichletCondition(zero, lo, hi);                                          // build platform fully clamped (:1913-1920)
+        return r;
+    }
+    void transferDensitiesToIntermediateFabricationShape(TensorProductSimulator &inter) const {
+        const auto rho = getDensities(); VXd out(inter.numElements());
+        for (size_t e = 0; e < out.size(); ++e) out[e] = rho[elementIndexForGridCell(inter.unflattenElement(e))];
+        inter.setDensities(out);
+    }
+    std::shared_ptr<TensorProductSimulator> downsample(size_t downsamplingLevels) const {
+        const size_t f = size_t(1) << downsamplingLevels; auto ne = m_ne;
+        for (auto &n : ne) { if (n % f) throw std::runtime_error("Grid size must be divisible by 2^downsamplingLevels"); n /= f; }
+        auto r = std::make_shared<TensorProductSimulator>(m_domain, ne);
+        r->setETensor(m_et); r->setE_min(m_Emin); r->setE_0(m_E0); r->setSIMPExponent(m_gamma);
+        return r;
+    }
+    size_t downsamplingFactor(const TensorProductSimulator &coarse) const {
+        const size_t f = m_ne[0] / coarse.m_ne[0];
+        for (size_t d = 0; d < N; ++d) if (coarse.m_ne[d] * f != m_ne[d]) throw std::runtime_error("Invalid downsampled simulator");
+        return f;
+    }
+    void downsampleDensityFieldTo(const VXd &densities, TensorProductSimulator &coarse) const {
+        const size_t f = downsamplingFactor(coarse);
+        if (densities.size() != numElements()) throw std::runtime_error("Invalid input densities size (" + std::to_string(densities.size()) + " vs " + std::to_string(numElements()) + ")");
+        VXd c(coarse.numElements(), 0.0); const double w = 1.0 / std::pow(double(f), double(N));
+        for (size_t e = 0; e < densities.size(); ++e) { auto q = unflattenElement(e); for (auto &v : q) v /= f; c[coarse.elementIndexForGridCell(q)] += densities[e]; }
+        for (double &v : c) v *= w;
+        coarse.setDensities(c);
+    }
+    VXd upsampleDensityGradientFrom(const TensorProductSimulator &coarse, const VXd &g_coarse) const {
+        const size_t f = downsamplingFactor(coarse);
+        if (g_coarse.size() != coarse.numElements()) throw std::runtime_error("Invalid coarse gradient size");
+        VXd g(numElements()); const double w = 1.0 / std::pow(double(f), double(N));
+        for (size_t e = 0; e < g.size(); ++e) { auto q = unflattenElement(e); for (auto &v : q) v /= f; g[e] = g_coarse[coarse.elementIndexForGridCell(q)] * w; }
+        return g;
+    }
+
     vf_sim *handle() const { return m_h; }
 private:
+    ETensorState m_et{true, 1.0, 0.0, {}};                         // ETensor(1, 0), TensorProductSimulator.hh:2114
     void pushInterp() { check(vf_sim_set_interpolation(m_h, (int)m_law, m_E0, m_Emin, m_gamma, m_q)); }
     BBoxN m_domain; EigenNDIndex m_ne; vf_sim *m_h = nullptr; VNd m_gravity{};
     InterpolationLaw m_law = InterpolationLaw::SIMP; double m_E0 = 1, m_Emin = 1e-4, m_gamma = 3, m_q = 3;   // TensorProductSimulator.hh:2160-2166
@@ -295,21 +392,58 @@ public:
     size_t lastPCGIterations() const { return m_lastIters; }
     VField pcgResidual() { VField r(numNodes(0), N); check(vf_mg_get_pcg_residual(m_h, r.data())); return r; }
 
+    // zeroOutDirichletComponents (:511-524) on a host field of level l
+    void zeroOutDirichletComponents(size_t l, VField &u) const {
+        std::vector<uint8_t> m(numNodes(l)); check(vf_mg_level_dirichlet_mask(m_h, (int)l, m.data()));
+        for (size_t n = 0; n < m.size(); ++n) for (size_t c = 0; c < N; ++c) if ((m[n] >> c) & 1) u(n, c) = 0.0;
+    }
+    std::vector<uint8_t> levelDirichletMask(size_t l) const { std::vector<uint8_t> m(numNodes(l)); check(vf_mg_level_dirichlet_mask(m_h, (int)l, m.data())); return m; }
+    VField debug_get_x(size_t l) { VField r(numNodes(l), N); check(vf_mg_debug_get(m_h, 0, (int)l, r.data())); return r; }
+    VField debug_get_b(size_t l) { VField r(numNodes(l), N); check(vf_mg_debug_get(m_h, 1, (int)l, r.data())); return r; }
+    std::vector<int32_t> debugMulticolorVisit() { std::vector<int32_t> r(numNodes(0)); check(vf_mg_debug_multicolor_visit(m_h, r.data())); return r; }
+
     vf_mg *handle() const { return m_h; }
 private:
     std::shared_ptr<TPS> m_fine; vf_mg *m_h = nullptr; size_t m_lastIters = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Filters and constraints: descriptors consumed by TopologyOptimizationProblem (the chain itself runs on the device)
-template<typename Real_> struct Filter { virtual ~Filter() = default; virtual std::array<double, 4> spec() const = 0; };
+// Filters (TopologyOptimizationFilter.hh:17-712).  A filter maps a flat row-major grid array to another; inside a
+// TopologyOptimizationProblem the chain runs on the device (vf_top_*, described there by spec()); apply / backprop here are the
+// stand-alone host-array entry points (vf_filter_*), which is what FilterChain and the python bindings use.
+using GridDims = std::vector<size_t>;
+template<typename Real_> struct Filter {
+    using VXd = voxelfem_b200::VXd;
+    virtual ~Filter() = default;
+    virtual std::array<double, 4> spec() const = 0;
+    virtual VXd apply(const VXd &in) = 0;                                       // Filter::apply (:25)
+    virtual VXd backprop(const VXd &d_dout, const VXd &vars) const = 0;        // Filter::backprop (:31)
+    const GridDims &inputDimensions() const { return m_inputDims; }
+    const GridDims &outputDimensions() const { return m_outputDims; }
+    void setInputDimensions(const GridDims &dims) { m_setInputDimensions(dims); m_gridDimsAreSet = true; }
+    void setOutputDimensions(const GridDims &dims) { m_setOutputDimensions(dims); m_gridDimsAreSet = true; }
+    void checkGridDimensionsAreSet() const { if (!m_gridDimsAreSet) throw std::runtime_error("Filter grid dimensions not set. Initialize a TopologyOptimizationProblem object with this filter before using it."); }
+    static size_t numEntries(const GridDims &d) { size_t n = 1; for (size_t v : d) n *= v; return n; }
+protected:
+    virtual void m_setInputDimensions(const GridDims &dims) { m_inputDims = m_outputDims = dims; }
+    virtual void m_setOutputDimensions(const GridDims &dims) { m_inputDims = m_outputDims = dims; }
+    std::vector<int64_t> dims64(const GridDims &d) const { return std::vector<int64_t>(d.begin(), d.end()); }
+    void checkIn(const VXd &x, const GridDims &d) const { checkGridDimensionsAreSet(); if (x.size() != numEntries(d)) throw std::runtime_error("Input dimension mismatch"); }
+    GridDims m_inputDims, m_outputDims; bool m_gridDimsAreSet = false;
+};
 template<typename Real_> struct SmoothingFilter : Filter<Real_> {   // TopologyOptimizationFilter.hh:283-400
+    using VXd = voxelfem_b200::VXd;
     enum class Type { Const = VF_SMOOTH_CONST, Linear = VF_SMOOTH_LINEAR };
     SmoothingFilter(size_t r = 1, Type t = Type::Const) : radius(r), type(t) {}
     size_t radius; Type type;
     std::array<double, 4> spec() const override { return {double(VF_FILTER_SMOOTH), double(radius), double(int(type)), 0.0}; }
+    VXd apply(const VXd &in) override { this->checkIn(in, this->m_inputDims); VXd out(in.size()); const auto d = this->dims64(this->m_inputDims);
+        check(vf_filter_smooth((int)d.size(), d.data(), (int)radius, int(type), in.data(), out.data())); return out; }
+    VXd backprop(const VXd &g, const VXd &) const override { this->checkIn(g, this->m_outputDims); VXd out(g.size()); const auto d = this->dims64(this->m_inputDims);
+        check(vf_filter_smooth((int)d.size(), d.data(), (int)radius, int(type), g.data(), out.data())); return out; }   // symmetric operator (:297-310)
 };
 template<typename Real_> struct ProjectionFilter : Filter<Real_> {  // TopologyOptimizationFilter.hh:189-245
+    using VXd = voxelfem_b200::VXd;
     explicit ProjectionFilter(Real_ beta = 1) { setBeta(beta); }
     Real_ getBeta() const { return m_beta; }
     void setBeta(Real_ beta) { if (beta <= 0) throw std::runtime_error("Beta parameter has to be positive (received beta = " + std::to_string(beta) + ")"); m_beta = beta; }
@@ -318,8 +452,92 @@ template<typename Real_> struct ProjectionFilter : Filter<Real_> {  // TopologyO
         return std::atanh((2 * filteredValue - 1) * std::tanh(0.5 * m_beta)) / m_beta + 0.5;
     }
     std::array<double, 4> spec() const override { return {double(VF_FILTER_PROJECT), 0.0, 0.0, double(m_beta)}; }
+    VXd apply(const VXd &in) override { this->checkIn(in, this->m_inputDims); VXd out(in.size()); check(vf_filter_project((int64_t)in.size(), m_beta, in.data(), out.data())); return out; }
+    VXd backprop(const VXd &g, const VXd &vars) const override { VXd out(g.size()); check(vf_filter_project_backprop((int64_t)g.size(), m_beta, g.data(), vars.data(), out.data())); return out; }
 private:
     Real_ m_beta = 1;
+};
+template<typename Real_> struct UpsampleFilter : Filter<Real_> {    // TopologyOptimizationFilter.hh:418-523
+    using VXd = voxelfem_b200::VXd;
+    explicit UpsampleFilter(size_t factor = 2) : m_factor(factor) {}
+    std::array<double, 4> spec() const override { return {double(VF_FILTER_UPSAMPLE), double(m_factor), 0.0, 0.0}; }
+    VXd apply(const VXd &in) override { this->checkIn(in, this->m_inputDims); VXd out(this->numEntries(this->m_outputDims)); const auto d = this->dims64(this->m_inputDims);
+        check(vf_filter_upsample((int)d.size(), d.data(), (int)m_factor, in.data(), out.data())); return out; }
+    VXd backprop(const VXd &g, const VXd &) const override { this->checkIn(g, this->m_outputDims); VXd out(this->numEntries(this->m_inputDims)); const auto d = this->dims64(this->m_inputDims);
+        check(vf_filter_upsample_backprop((int)d.size(), d.data(), (int)m_factor, g.data(), out.data())); return out; }
+protected:
+    void m_setInputDimensions(const GridDims &dims) override {
+        for (size_t v : dims) if (v < 2) throw std::runtime_error("Interpolation can only be applied to a 2^d grid or larger");
+        this->m_inputDims = dims; this->m_outputDims = dims; for (auto &v : this->m_outputDims) v = (v - 1) * m_factor + 1;
+    }
+    void m_setOutputDimensions(const GridDims &dims) override {
+        for (size_t v : dims) if (v < 2) throw std::runtime_error("Interpolation can only be applied to a 2^d grid or larger");
+        this->m_outputDims = dims; this->m_inputDims = dims;
+        for (size_t d = 0; d < dims.size(); ++d) { this->m_inputDims[d] = (dims[d] - 1) / m_factor + 1; if ((this->m_inputDims[d] - 1) * m_factor + 1 != dims[d]) throw std::runtime_error("Output size is not divisible by factor"); }
+    }
+private:
+    size_t m_factor;
+};
+template<typename Real_> struct VertexToCellFilter : Filter<Real_> {   // TopologyOptimizationFilter.hh:528-598
+    using VXd = voxelfem_b200::VXd;
+    std::array<double, 4> spec() const override { return {double(VF_FILTER_VERTEX_TO_CELL), 0.0, 0.0, 0.0}; }
+    VXd apply(const VXd &in) override { this->checkIn(in, this->m_inputDims); VXd out(this->numEntries(this->m_outputDims)); const auto d = this->dims64(this->m_inputDims);
+        check(vf_filter_vertex_to_cell((int)d.size(), d.data(), in.data(), out.data())); return out; }
+    VXd backprop(const VXd &g, const VXd &) const override { this->checkIn(g, this->m_outputDims); VXd out(this->numEntries(this->m_inputDims)); const auto d = this->dims64(this->m_inputDims);
+        check(vf_filter_vertex_to_cell_backprop((int)d.size(), d.data(), g.data(), out.data())); return out; }
+protected:
+    void m_setInputDimensions(const GridDims &dims) override { for (size_t v : dims) if (v < 2) throw std::runtime_error("Input grid must be 2^d or larger."); this->m_inputDims = dims; this->m_outputDims = dims; for (auto &v : this->m_outputDims) v -= 1; }
+    void m_setOutputDimensions(const GridDims &dims) override { this->m_outputDims = dims; this->m_inputDims = dims; for (auto &v : this->m_inputDims) v += 1; }
+};
+template<typename Real_> struct LangelaarFilter : Filter<Real_> {      // TopologyOptimizationFilter.hh:601-712
+    using VXd = voxelfem_b200::VXd;
+    std::array<double, 4> spec() const override { return {double(VF_FILTER_LANGELAAR), 0.0, 0.0, 0.0}; }
+    VXd apply(const VXd &in) override {
+        this->checkIn(in, this->m_inputDims); const auto d = this->dims64(this->m_inputDims);
+        if (m_cachedFiltered.size() != in.size()) { m_cachedFiltered.assign(in.size(), 0.0); m_cachedSmax.assign(in.size(), 0.0); }
+        check(vf_filter_langelaar((int)d.size(), d.data(), in.data(), m_cachedFiltered.data(), m_cachedSmax.data()));   // output array is in/out (header note)
+        return m_cachedFiltered;
+    }
+    VXd backprop(const VXd &g, const VXd &vars) const override {
+        if (m_cachedFiltered.size() != g.size()) throw std::runtime_error("LangelaarFilter::backprop before apply");
+        VXd out(g.size()); const auto d = this->dims64(this->m_inputDims);
+        check(vf_filter_langelaar_backprop((int)d.size(), d.data(), g.data(), vars.data(), m_cachedFiltered.data(), m_cachedSmax.data(), out.data())); return out;
+    }
+private:
+    VXd m_cachedFiltered, m_cachedSmax;
+};
+template<typename Real_> struct PythonFilter : Filter<Real_> {         // TopologyOptimizationFilter.hh:247-275
+    using VXd = voxelfem_b200::VXd;
+    using ApplyCallback = std::function<void(const VXd &in, VXd &out)>;
+    using BackpropCallback = std::function<void(const VXd &in, const VXd &vars, VXd &out)>;
+    std::array<double, 4> spec() const override { return {double(VF_FILTER_PYTHON), 0.0, 0.0, 0.0}; }
+    VXd apply(const VXd &in) override { if (!apply_cb) throw std::runtime_error("Apply callback must be configured"); VXd out(this->numEntries(this->m_outputDims), 0.0); apply_cb(in, out); return out; }
+    VXd backprop(const VXd &g, const VXd &vars) const override { if (!backprop_cb) throw std::runtime_error("Backprop callback must be configured"); VXd out(this->numEntries(this->m_inputDims), 0.0); backprop_cb(g, vars, out); return out; }
+    ApplyCallback apply_cb; BackpropCallback backprop_cb;
+};
+// FilterChain (TopologyOptimizationFilter.hh:90-187) on host arrays
+template<typename Real_> struct FilterChain {
+    using VXd = voxelfem_b200::VXd;
+    using Filters = std::vector<std::shared_ptr<Filter<Real_>>>;
+    FilterChain(const Filters &f, const GridDims &outGridDims) : m_filters(f) {
+        GridDims dims = outGridDims;
+        for (size_t i = m_filters.size(); i-- > 0;) { m_filters[i]->setOutputDimensions(dims); dims = m_filters[i]->inputDimensions(); }
+        m_inDims = dims; m_outDims = outGridDims;
+        m_vars.assign(m_filters.size() + 1, VXd());
+        m_vars[0].assign(Filter<Real_>::numEntries(dims), 0.0);
+        for (size_t i = 0; i < m_filters.size(); ++i) m_vars[i + 1].assign(Filter<Real_>::numEntries(m_filters[i]->outputDimensions()), 0.0);
+    }
+    size_t numVars() const { return m_vars.front().size(); }
+    size_t numPhysicalVars() const { return m_vars.back().size(); }
+    const GridDims &gridDims() const { return m_inDims; }
+    const GridDims &physicalGridDims() const { return m_outDims; }
+    void setDesignVars(const VXd &x) { if (x.size() != numVars()) throw std::runtime_error("Variable size mismatch"); m_vars[0] = x; for (size_t i = 0; i < m_filters.size(); ++i) m_vars[i + 1] = m_filters[i]->apply(m_vars[i]); }
+    VXd backprop(VXd g) const { if (g.size() != numPhysicalVars()) throw std::runtime_error("Size mismatch"); for (size_t i = m_filters.size(); i-- > 0;) g = m_filters[i]->backprop(g, m_vars[i]); return g; }
+    const VXd &designVars() const { return m_vars.front(); }
+    const VXd &physicalVars() const { return m_vars.back(); }
+    const Filters &filters() const { return m_filters; }
+private:
+    Filters m_filters; std::vector<VXd> m_vars; GridDims m_inDims, m_outDims;
 };
 template<typename Real_> struct Constraint { virtual ~Constraint() = default; };
 template<typename Real_> struct TotalVolumeConstraint : Constraint<Real_> {   // TopologyOptimizationConstraint.hh:24-40
@@ -328,13 +546,23 @@ template<typename Real_> struct TotalVolumeConstraint : Constraint<Real_> {   //
 };
 
 template<typename Sim> struct Objective { virtual ~Objective() = default; };
+template<typename Sim> class TopologyOptimizationProblem;
 template<typename Sim>
 struct MultigridComplianceObjective : Objective<Sim> {            // TopologyOptimizationObjective.hh:60-105
     template<typename MGS> explicit MultigridComplianceObjective(std::shared_ptr<MGS> mg_) : m_handle(mg_->handle()), m_keep(mg_) {}
     size_t cgIter = 100; double tol = 1e-5; size_t mgIterations = 1, mgSmoothingIterations = 2; bool fullMultigrid = true, zeroInit = false;
+    std::function<void(size_t, const VField &)> residual_cb;       // (:104) invoked per PCG iteration of updateCache with (it, r)
     vf_mg *mgHandle() const { return m_handle; }
+    std::shared_ptr<void> mgHolder() const { return m_keep; }
+    // compliance / u / f / gradient of the attached problem (ComplianceObjective, :27-57)
+    double compliance() const { return problem().TopologyOptimizationProblem<Sim>::evaluateObjective(); }
+    VField u() const { return problem().displacement(); }
+    VField f() const { return problem().getSimulator().buildLoadVector(); }
+    VXd gradient() const { return problem().getSimulator().complianceGradientFlattened(u()); }   // dJ/d(rho_phys) (:45-47)
+    void attach(const TopologyOptimizationProblem<Sim> *p) { m_problem = p; }
 private:
-    vf_mg *m_handle; std::shared_ptr<void> m_keep;
+    const TopologyOptimizationProblem<Sim> &problem() const { if (!m_problem) throw std::runtime_error("objective is not attached to a TopologyOptimizationProblem yet"); return *m_problem; }
+    vf_mg *m_handle; std::shared_ptr<void> m_keep; const TopologyOptimizationProblem<Sim> *m_problem = nullptr;
 };
 
 template<typename Sim>
@@ -349,10 +577,24 @@ public:
         if (constraints.size() != 1) throw std::runtime_error("exactly one TotalVolumeConstraint is supported (OptimalityCriterion.hh:43-45)");
         auto tvc = std::dynamic_pointer_cast<TotalVolumeConstraint<double>>(constraints[0]);
         if (!tvc) throw std::runtime_error("exactly one TotalVolumeConstraint is supported (OptimalityCriterion.hh:43-45)");
+        GridDims dims(simulator.NbElementsPerDimension().begin(), simulator.NbElementsPerDimension().end());
+        for (size_t i = filters.size(); i-- > 0;) { filters[i]->setOutputDimensions(dims); dims = filters[i]->inputDimensions(); }   // FilterChain::setOutputDimensions (:117-132)
         std::vector<double> spec;
-        for (const auto &f : filters) { const auto s = f->spec(); spec.insert(spec.end(), s.begin(), s.end()); }
+        for (const auto &f : filters) { const auto sp = f->spec(); spec.insert(spec.end(), sp.begin(), sp.end()); }
         if (spec.empty()) spec.push_back(0.0);
         check(vf_top_create(m_objective->mgHandle(), (int)filters.size(), spec.data(), tvc->m_volumeFraction, &m_h));
+        for (size_t i = 0; i < filters.size(); ++i) {              // PythonFilter: host callbacks inside the device chain
+            auto *pf = dynamic_cast<PythonFilter<double> *>(filters[i].get());
+            if (!pf) continue;
+            auto ap = [](const double *in, int64_t nin, double *out, int64_t nout, void *user) -> int {
+                try { auto &f = *static_cast<PythonFilter<double> *>(user); if (!f.apply_cb) throw std::runtime_error("Apply callback must be configured");
+                      VXd o((size_t)nout, 0.0); f.apply_cb(VXd(in, in + nin), o); std::copy(o.begin(), o.end(), out); return 0; } catch (...) { s_pending() = std::current_exception(); return 1; } };
+            auto bp = [](const double *g, int64_t nout, const double *vars, int64_t nin, double *out, void *user) -> int {
+                try { auto &f = *static_cast<PythonFilter<double> *>(user); if (!f.backprop_cb) throw std::runtime_error("Backprop callback must be configured");
+                      VXd o((size_t)nin, 0.0); f.backprop_cb(VXd(g, g + nout), VXd(vars, vars + nin), o); std::copy(o.begin(), o.end(), out); return 0; } catch (...) { s_pending() = std::current_exception(); return 1; } };
+            check(vf_top_set_python_filter(m_h, (int)i, ap, bp, pf));
+        }
+        m_objective->attach(this);
     }
     virtual ~TopologyOptimizationProblem() { if (m_h) vf_top_destroy(m_h); }
     // true for subclasses that override setVars / evaluateObjective / evaluateObjectiveGradientAndReturn on the host (the python trampoline)
@@ -360,25 +602,40 @@ public:
     TopologyOptimizationProblem(const TopologyOptimizationProblem &) = delete;
     TopologyOptimizationProblem &operator=(const TopologyOptimizationProblem &) = delete;
 
-    size_t numVars() const { return m_sim.numElements(); }
-    virtual bool setVars(const VXd &x, bool /* forceUpdate */ = false) { syncSolver(); if (x.size() != numVars()) throw std::runtime_error("Size mismatch"); check(vf_top_set_vars(m_h, x.data())); return true; }
+    size_t numVars() const { return (size_t)vf_top_num_vars(m_h); }
+    size_t numPhysicalVars() const { return (size_t)vf_top_num_physical_vars(m_h); }
+    virtual bool setVars(const VXd &x, bool /* forceUpdate */ = false) { syncSolver(); if (x.size() != numVars()) throw std::runtime_error("Size mismatch"); call(vf_top_set_vars(m_h, x.data())); return true; }
     VXd getVars() const { VXd r(numVars()); check(vf_top_get_vars(m_h, 0, r.data())); return r; }
-    VXd getDensities() const { VXd r(numVars()); check(vf_top_get_vars(m_h, 1, r.data())); return r; }
+    VXd getDensities() const { VXd r(numPhysicalVars()); check(vf_top_get_vars(m_h, 1, r.data())); return r; }
     virtual double evaluateObjective() const { double v = 0; check(vf_top_compliance(m_h, &v)); return v; }
-    virtual VXd evaluateObjectiveGradientAndReturn() const { VXd g(numVars()); check(vf_top_objective_gradient(m_h, g.data())); return g; }
+    virtual VXd evaluateObjectiveGradientAndReturn() const { VXd g(numVars()); call(vf_top_objective_gradient(m_h, g.data())); return g; }
     VXd evaluateConstraints() const { double v = 0; check(vf_top_constraint(m_h, &v)); return VXd(1, v); }
-    VXd evaluateConstraintsJacobianAndReturn() const { VXd g(numVars()); check(vf_top_constraint_jacobian(m_h, g.data())); return g; }
+    VXd evaluateConstraintsJacobianAndReturn() const { VXd g(numVars()); call(vf_top_constraint_jacobian(m_h, g.data())); return g; }
     VField displacement() const { VField u(m_sim.numNodes(), Sim::N); check(vf_top_get_u(m_h, u.data())); return u; }
     int lastPCGIterations() const { return vf_top_last_pcg_iterations(m_h); }
     ObjectivePtr getObjective() const { return m_objective; }
     const FiltersList &getFilters() const { return m_filters; }
     const ConstraintsList &getConstraints() const { return m_constraints; }
+    GridDims gridDims(bool physical = false) const { std::vector<int64_t> d(Sim::N); check(vf_top_get_grid_dims(m_h, physical, d.data())); return GridDims(d.begin(), d.end()); }
+    // back-propagation of an arbitrary physical-space gradient through the problem's filters at the current design variables
+    VXd backpropThroughFilters(const VXd &g) const { FilterChain<double> fc(m_filters, gridDims(true)); fc.setDesignVars(getVars()); return fc.backprop(g); }
+    Sim &getSimulator() const { return m_sim; }
     void syncSolver() const {
         const auto &o = *m_objective;
+        auto rcb = [](int it, double, void *user) {                  // residual_cb(it, r): the residual is fetched only because a callback is set
+            const auto &self = *static_cast<const TopologyOptimizationProblem *>(user);
+            if (!self.m_objective->residual_cb) return;
+            VField r(self.m_sim.numNodes(), Sim::N); check(vf_mg_get_pcg_residual(self.m_objective->mgHandle(), r.data()));
+            try { self.m_objective->residual_cb((size_t)it, r); } catch (...) { s_pending() = std::current_exception(); }
+        };
+        check(vf_top_set_residual_callback(m_h, o.residual_cb ? static_cast<vf_pcg_callback>(rcb) : nullptr, const_cast<TopologyOptimizationProblem *>(this)));
         check(vf_top_set_solver(m_h, (int)o.cgIter, o.tol, (int)o.mgIterations, (int)o.mgSmoothingIterations, o.fullMultigrid, o.zeroInit));
     }
     vf_top *handle() const { return m_h; }
+    // a C-ABI call during which PythonFilter callbacks may run: their exception (if any) is rethrown instead of the generic status
+    static void call(int rc) { if (s_pending()) { auto e = s_pending(); s_pending() = nullptr; std::rethrow_exception(e); } check(rc); }
 private:
+    static std::exception_ptr &s_pending() { static thread_local std::exception_ptr p; return p; }
     Sim &m_sim; ObjectivePtr m_objective; ConstraintsList m_constraints; FiltersList m_filters; vf_top *m_h = nullptr;
 };
 
@@ -391,11 +648,11 @@ public:
     // through the problem's virtual setVars (:133) -- the path a subclassed problem (trampoline, VoxelFEM.cc:58-66) needs.
     void step(double m = 0.2, double p = 0.5, double ctol = 1e-6, bool inplace = true) {
         m_p.syncSolver(); int evals = 0;
-        if (inplace && !m_p.hasHostOverrides()) check(vf_top_oc_step(m_p.handle(), m, p, ctol, &evals));
+        if (inplace && !m_p.hasHostOverrides()) Problem::call(vf_top_oc_step(m_p.handle(), m, p, ctol, &evals));
         else {
             const auto dJ = m_p.evaluateObjectiveGradientAndReturn();
             std::vector<double> stepped(m_p.numVars());
-            check(vf_top_oc_search(m_p.handle(), dJ.data(), m, p, ctol, stepped.data(), &evals));
+            Problem::call(vf_top_oc_search(m_p.handle(), dJ.data(), m, p, ctol, stepped.data(), &evals));
             m_p.setVars(stepped);
         }
         m_lastEvals = evals;
