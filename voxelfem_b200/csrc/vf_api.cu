@@ -773,7 +773,7 @@ void mg_residual(vf_mg &lead, int l, Field u, Field b, Field r) {
 }
 
 // smoothingMulticoloredGS (:452-458): 2^N colour passes, colours reversed for backward sweeps (:417).  In a slab window the
-// colour of a node is the parity class of its GLOBAL index; after a pass that updated the parity of the ghost planes those
+// colour of a node is the parity class of its GLOBAL index; after the passes that updated the parity of the ghost planes those
 // planes are received from the neighbours.
 void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward) {
     const int nc = 1 << lead.N;
@@ -804,7 +804,9 @@ void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward) {
             else if (l == 0)         launch_gs_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), lc, forward);
             else                     launch_gs_stencil(mg.ctx, g, mg.lv[l]->S.p, u(mg), b(mg), mg.dmask(l), lc, forward, /* chained */ i > 0 && !lead.grp);
         }
-        if (lead.N == 3) grp_exchange(lead, l, u, (color >> 2) & 1);
+        // The four passes of one x parity only read planes of the other parity besides their own plane, so a ghost plane (one parity)
+        // has to be current only when the passes of the OTHER parity start: one exchange per parity group instead of one per pass.
+        if (lead.N == 3 && (i & 3) == 3) grp_exchange(lead, l, u, (color >> 2) & 1);
     }
 }
 // coarsest-level solve on the replicated coarsest grid

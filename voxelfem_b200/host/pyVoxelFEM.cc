@@ -187,8 +187,11 @@ void addTPSBindings(py::module &m, py::module &detail) {
     using ObjectivePtr = typename TOProblem::ObjectivePtr;
     using PCV = ProblemChainView<TPS>;
 
-    m.def("TopologyOptimizationProblem", [](TPS &s, ObjectivePtr o, ConstraintsList c, FiltersList f) { return std::make_unique<TOProblem>(s, o, c, f); },
-          py::arg("simulator"), py::arg("objective"), py::arg("constraints"), py::arg("filters"), py::keep_alive<0, 1>());
+    // "Constructor" function (VoxelFEM.cc:236-240): forwards to the class registered for this simulator type, so that the object is built
+    // by the class's own py::init (one construction path for the factory, the mangled class and python subclasses of it)
+    m.def("TopologyOptimizationProblem", [detail](std::shared_ptr<TPS> s, py::object o, py::object c, py::object f) {
+              return detail.attr(NM::mangle("TopologyOptimizationProblem").c_str())(s, o, c, f); },
+          py::arg("simulator"), py::arg("objective"), py::arg("constraints"), py::arg("filters"));
     m.def("MultigridComplianceObjective", [](std::shared_ptr<MG> mg) { return std::make_shared<MGCO>(mg); }, py::arg("mg_solver"));
     m.def("ComplianceObjective", [](TPS &) -> py::object { PyErr_SetString(PyExc_NotImplementedError, "ComplianceObjective (CHOLMOD direct solve of the fine system) is not on the B200 path; use MultigridComplianceObjective(tps.multigridSolver(levels))"); throw py::error_already_set(); }, py::arg("simulator"));
 
@@ -251,7 +254,9 @@ void addTPSBindings(py::module &m, py::module &detail) {
     py::class_<OCO>(detail, NM::mangle("OCOptimizer").c_str())
         .def(py::init<TOProblem &>(), py::arg("problem"), py::keep_alive<1, 2>())
         .def("step", &OCO::step, py::arg("m") = 0.2, py::arg("p") = 0.5, py::arg("ctol") = 1e-6, py::arg("inplace") = true);
-    m.def("OCOptimizer", [](TOProblem &p) { return std::make_unique<OCO>(p); }, py::keep_alive<0, 1>());
+    m.def("OCOptimizer", [detail](py::object p) {
+              if (!py::isinstance<TOProblem>(p)) throw py::reference_cast_error();   // not this simulator type: try the next overload
+              return detail.attr(NM::mangle("OCOptimizer").c_str())(p); }, py::arg("problem"));
 }
 
 PYBIND11_MODULE(pyVoxelFEM, m) {
