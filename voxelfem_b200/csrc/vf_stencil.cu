@@ -389,7 +389,7 @@ void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const Grid
 // traffic for level 2 of a 256^3 grid where the one-shot kernel above issues 43 GB of cache-resident re-reads (14.7 ms).
 // Intermediates are SoA (T[entry][node]); the first pass reads and the last pass writes the colour-tiled layout.
 // ---------------------------------------------------------------------------
-struct AxisPass { int inNN[3], outNN[3]; int axis; long long inNodes, outNodes; };
+struct AxisPass { int inNN[3], outNN[3]; int axis; long long inNodes, outNodes; int shift; };   // shift: fine index = 2 * coarse index + al + shift (slab windows, axis 0)
 
 template<bool IN_TILED, bool OUT_TILED>
 __global__ void __launch_bounds__(128)
@@ -404,7 +404,7 @@ k_coarsen_axis(const __grid_constant__ AxisPass P, const __grid_constant__ GridD
     double acc[3] = {0.0, 0.0, 0.0};
     #pragma unroll
     for (int al = -1; al <= 1; ++al) {
-        const int f = 2 * c[a] + al;
+        const int f = 2 * c[a] + al + P.shift;
         if (f < 0 || f >= P.inNN[a]) continue;
         const double wa = al == 0 ? 1.0 : 0.5;
         int fc[3] = {c[0], c[1], c[2]}; fc[a] = f;
@@ -444,7 +444,7 @@ void launch_coarsen_stencil_separable(const LaunchCtx &ctx, const GridDesc &gc, 
     AxisPass P[3];
     int cur[3] = {gf.nn[0], gf.nn[1], gf.nn[2]};
     for (int a = 0; a < 3; ++a) {
-        P[a].axis = a;
+        P[a].axis = a; P[a].shift = a == 0 ? xshift(gf, gc) : 0;
         for (int k = 0; k < 3; ++k) { P[a].inNN[k] = cur[k]; }
         cur[a] = gc.nn[a];
         for (int k = 0; k < 3; ++k) { P[a].outNN[k] = cur[k]; }
