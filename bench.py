@@ -42,7 +42,7 @@ PCG = dict(max_iter=100, tol=1e-10, mg_iterations=1, mg_smoothing=1, fmg=True)
 # these grids; log: profiles/r03f_pytest_baseline_configs.log): the CPU arm times a bounded sample and scales it to the full solve
 ORACLE_ITERATIONS = {"C3_pcg_256^3": 14, "C3_pcg_128^3": 14, "C1_pcg_256x128": 16}
 # executed FP64 instructions per unit of the level-0 kernels: the FP64-pipe view of the roofline
-FP64_OPS = {"gs_l0": 670.0, "apply_l0": 185.0, "residual_l0": 188.0}
+FP64_OPS = {"gs_l0": 414.0, "apply_l0": 185.0, "residual_l0": 188.0}   # gs_l0: neighbour form (331 DFMA + 59 DADD + 24 DMUL per node, SASS of k_gs3_nbt)
 
 # algorithmic bytes per unit of work (SURVEY.md section 8d / DESIGN.md): fp64, 3D Q1
 ALG_BYTES = {"gs_l0": 80.0, "apply_l0": 56.0, "residual_l0": 80.0, "gs_stencil": 80.0 + 27 * 9 * 8.0,

@@ -487,6 +487,210 @@ k_gs3_nb(const __grid_constant__ GridDesc g, const __grid_constant__ VtabParam V
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// TMA-staged neighbour form.  k_gs3_nb above is bound by the shared-memory instruction path (ncu: 27 % of the warp samples issue the
+// 34 x 257 eight-byte cp.async of a row unit, mio_throttle is the second stall reason): the parity-split rows need one LDGSTS per
+// element.  Here every row arrives RAW (z order) by ONE bulk copy (cp.async.bulk + mbarrier, no LSU instruction at all), and the
+// lanes -- which still own every other node of the row -- fetch what they need as 16-byte aligned pairs: a pair holds two of the
+// three z-neighbours (z - 1, z, z + 1) of a (row, component), the third is a second load.  Which pair is aligned depends on the
+// parity of the row's first element in global memory and on the colour; with odd node counts per axis (any grid that can be
+// coarsened) that parity is (px + py + plane + row + component) mod 2 -- a compile-time constant per launch class (template Q).
+// A row starts at element P + o of its buffer (o: parity of its global offset, P = 2): copies start and end on 16-byte boundaries,
+// and the slots of z = -1 / z = nz that no copy covers are zeroed by hand (a covered slot holds a neighbouring row's value: finite,
+// and always multiplied by a zero modulus).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int kRawP = 2;
+template<int RS> __host__ __device__ constexpr int raw_u(int p, int r, int c) { return ((p * 3 + r) * 3 + c) * RS; }
+template<int RS> __host__ __device__ constexpr int raw_b(int c) { return (27 + c) * RS; }
+template<int RS> __host__ __device__ constexpr int raw_e(int lx, int ly) { return (30 + lx * 2 + ly) * RS; }
+
+// values at z - 1, z, z + 1 of a raw row whose element z' sits at row[kRawP + O + z']; z = 2 i + PZ
+template<int O, int PZ>
+__device__ __forceinline__ void raw_load3(const double *row, int i, double (&v)[3]) {
+    if (((PZ + O) & 1) == 0) {
+        const double2 a = *reinterpret_cast<const double2 *>(row + kRawP + O + PZ + 2 * i);        // (z, z + 1)
+        v[1] = a.x; v[2] = a.y; v[0] = row[kRawP + O + PZ + 2 * i - 1];
+    } else {
+        const double2 a = *reinterpret_cast<const double2 *>(row + kRawP + O + PZ + 2 * i - 1);    // (z - 1, z)
+        v[0] = a.x; v[1] = a.y; v[2] = row[kRawP + O + PZ + 2 * i + 1];
+    }
+}
+
+template<int RS, int Q, int PZ>
+__device__ __forceinline__ void gs_nbt_node(const VtabParam &V, const double *S, int i, int z, int nz, double (&Ku)[3], double (&uself)[3], double (&M)[3][3]) {
+    // stage 1 (axis 2): T1[v2][a0][a1]; a_k = 1: the element on the - side of the node along axis k
+    double T1[4][2][2];
+    #pragma unroll
+    for (int a0 = 0; a0 < 2; ++a0) {
+        #pragma unroll
+        for (int a1 = 0; a1 < 2; ++a1) {
+            const double *row = S + raw_e<RS>(1 - a0, 1 - a1) + kRawP;   // element layers have even row offsets: o = 0
+            double ep, em;
+            if (PZ == 1) { const double2 a = *reinterpret_cast<const double2 *>(row + 2 * i); em = a.x; ep = a.y; }   // elements z - 1 = 2 i, z
+            else { em = row[2 * i - 1]; ep = row[2 * i]; }
+            T1[0][a0][a1] = ep; T1[1][a0][a1] = em; T1[2][a0][a1] = ep + em; T1[3][a0][a1] = ep - em;
+        }
+    }
+    double T2[4][4][2];
+    #pragma unroll
+    for (int v2 = 0; v2 < 4; ++v2) {
+        #pragma unroll
+        for (int a0 = 0; a0 < 2; ++a0) {
+            const double ep = T1[v2][a0][0], em = T1[v2][a0][1];
+            T2[0][v2][a0] = ep; T2[1][v2][a0] = em; T2[2][v2][a0] = ep + em; T2[3][v2][a0] = ep - em;
+        }
+    }
+    double A[3][10];
+    #pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        #pragma unroll
+        for (int k = 0; k < 10; ++k) A[c][k] = 0.0;
+    }
+    #pragma unroll
+    for (int d0 = -1; d0 <= 1; ++d0) {
+        #pragma unroll
+        for (int d1 = -1; d1 <= 1; ++d1) {
+            double un[3][3];                                     // [component][d2 + 1]
+            if ((Q + d0 + d1) & 1) { raw_load3<1, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 0), i, un[0]); raw_load3<0, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 1), i, un[1]); raw_load3<1, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 2), i, un[2]); }
+            else                   { raw_load3<0, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 0), i, un[0]); raw_load3<1, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 1), i, un[1]); raw_load3<0, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 2), i, un[2]); }
+            #pragma unroll
+            for (int d2 = -1; d2 <= 1; ++d2) {
+                const int D = ((d0 != 0) << 2) | ((d1 != 0) << 1) | (d2 != 0);
+                double Sv[4]; bool sneg[4];
+                #pragma unroll
+                for (int si = 0; si < 4; ++si) {
+                    const int s0 = nb_sbit(si, 0), s1 = nb_sbit(si, 1), s2 = nb_sbit(si, 2);
+                    const int v0 = nb_variant(d0, s0), v1 = nb_variant(d1, s1), v2 = nb_variant(d2, s2);
+                    Sv[si] = v0 < 2 ? T2[v1][v2][v0] : (v0 == 2 ? T2[v1][v2][0] + T2[v1][v2][1] : T2[v1][v2][0] - T2[v1][v2][1]);
+                    sneg[si] = ((d0 < 0 && s0) != (d1 < 0 && s1)) != (d2 < 0 && s2);
+                }
+                #pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    #pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const int si = c == d ? 0 : c + d;
+                        const bool neg = sneg[si] != gs_vneg(D, c, d);
+                        const int k = gs_vclass(D, c, d);
+                        A[c][k] = fma(neg ? -Sv[si] : Sv[si], un[d][d2 + 1], A[c][k]);
+                    }
+                }
+                if (D == 0) {
+                    #pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        uself[c] = un[c][1];
+                        #pragma unroll
+                        for (int c2 = c; c2 < 3; ++c2) {
+                            const double k = V.mag[gs_vclass(0, c, c2)];
+                            M[c][c2] = (gs_vneg(0, c, c2) ? -k : k) * Sv[c == c2 ? 0 : c + c2];
+                            M[c2][c] = M[c][c2];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    #pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double acc = 0.0;
+        #pragma unroll
+        for (int k = 0; k < 10; ++k) acc = fma(V.mag[k], A[c][k], acc);
+        Ku[c] = acc;
+    }
+}
+
+template<bool FWD, int RS, int Q, int PZ>
+__device__ __forceinline__ void gs_nbt_phase(const GridDesc &g, const VtabParam &V, double *S, double *u, const uint8_t *__restrict__ dmask, long long nrow, int tid, unsigned dmFirst) {
+    const int nz = g.nn[2];
+    const long long NN = g.numNodes;
+    const int cnt = (nz + 1 - PZ) >> 1;
+    #pragma unroll 1
+    for (int i = tid; i < cnt; i += kNbThreads) {
+        const int z = 2 * i + PZ;
+        const unsigned dm = i == tid ? dmFirst : (unsigned)dmask[nrow + z];   // first trip: fetched while the rows were in flight
+        if (dm == 7u) continue;                           // hasFullDirichlet nodes are skipped (MultigridSolver.hh:350)
+        double Ku[3], uself[3], M[3][3], rhs[3], du[3];
+        gs_nbt_node<RS, Q, PZ>(V, S, i, z, nz, Ku, uself, M);
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) rhs[c] = S[raw_b<RS>(c) + kRawP + ((Q + c) & 1) + z] - Ku[c];
+        gs_node_update<3>(M, rhs, dm, FWD, du);
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double v = uself[c] + du[c];
+            u[c * NN + nrow + z] = v;
+            S[raw_u<RS>(1, 1, c) + kRawP + ((Q + c) & 1) + z] = v;
+        }
+    }
+}
+
+template<bool FWD, int RS, int Q>
+__global__ void __launch_bounds__(kNbThreads, 3)
+k_gs3_nbt(const __grid_constant__ GridDesc g, const __grid_constant__ VtabParam V, const __grid_constant__ RowPass rp,
+          double *u, const double *__restrict__ b, const double *__restrict__ E, const uint8_t *__restrict__ dmask) {
+    extern __shared__ __align__(16) double S[];
+    __shared__ alignas(8) unsigned long long mbar;
+    pdl_prologue();
+    const int tid = threadIdx.x;
+    const int x = rp.px + 2 * (int)blockIdx.y, y = rp.py + 2 * (int)blockIdx.x;
+    if (x < g.cmpLo || x >= g.cmpHi) return;              // ghost planes of a slab window are received, not computed
+    const int nx = g.nn[0], ny = g.nn[1], nz = g.nn[2];
+    const long long NN = g.numNodes;
+    const long long nrow = (long long)x * g.ns[0] + (long long)y * g.ns[1];
+    if (tid == 0) mbar_init(&mbar, kRowArrays);
+    __syncthreads();
+    if (tid < kRowArrays) {
+        // one bulk copy per row.  Rows of u outside the grid are mirrored back into it (keeps the parity of the row offset; their
+        // values only ever meet zero moduli); element rows outside the grid are zero-filled below.
+        const double *base; long long e0, total; int len; bool valid = true;
+        if (tid < 27) {
+            const int p = tid / 9, r = (tid / 3) % 3, c = tid % 3;
+            int xx = x + p - 1, yy = y + r - 1;
+            if (xx < 0 || xx >= nx) xx = x - (p - 1);
+            if (yy < 0 || yy >= ny) yy = y - (r - 1);
+            base = u; e0 = c * NN + (long long)xx * g.ns[0] + (long long)yy * g.ns[1]; total = 3 * NN; len = nz;
+        } else if (tid < 30) {
+            base = b; e0 = (tid - 27) * NN + nrow; total = 3 * NN; len = nz;
+        } else {
+            const int ex = x - 1 + ((tid - 30) >> 1), ey = y - 1 + ((tid - 30) & 1);
+            valid = ex >= 0 && ex < g.ne[0] && ey >= 0 && ey < g.ne[1];
+            base = E; e0 = valid ? (long long)ex * g.es[0] + (long long)ey * g.es[1] : 0; total = g.numElems; len = g.ne[2];
+        }
+        double *row = S + tid * RS;
+        row[kRawP - 1] = 0.0;                             // z = -1 of a row with o = 0 (never covered by a copy)
+        if (valid) {
+            const int o = (int)(e0 & 1);
+            const long long start = e0 - o;
+            int cnt = (o + len + 1) & ~1;
+            row[kRawP + cnt] = 0.0;                       // z = len of a row with o + len even
+            if (start + cnt > total) {                    // the very last row of the array: the rounded-up copy would leave the allocation
+                cnt -= 2;
+                row[kRawP + cnt] = base[start + cnt];
+                row[kRawP + cnt + 1] = 0.0;
+            }
+            tma_load_1d(row + kRawP, base + start, (unsigned)cnt * 8u, &mbar);
+        } else mbar_arrive(&mbar);
+    }
+    #pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ex = x - 1 + (j >> 1), ey = y - 1 + (j & 1);
+        if (!(ex >= 0 && ex < g.ne[0] && ey >= 0 && ey < g.ne[1]))
+            for (int k = tid; k < RS; k += kNbThreads) S[(30 + j) * RS + k] = 0.0;
+    }
+    // Dirichlet masks of this thread's first node of either colour: fetched while the rows are in flight
+    const int zA = 2 * tid + (FWD ? 0 : 1), zB = 2 * tid + (FWD ? 1 : 0);
+    const unsigned dmA = zA < nz ? dmask[nrow + zA] : 7u, dmB = zB < nz ? dmask[nrow + zB] : 7u;
+    mbar_wait(&mbar, 0);
+    __syncthreads();                                      // hand-written pad / tail slots
+    if (FWD) {
+        gs_nbt_phase<FWD, RS, Q, 0>(g, V, S, u, dmask, nrow, tid, dmA);
+        __syncthreads();                                  // the second colour reads the first colour's new values of this row
+        gs_nbt_phase<FWD, RS, Q, 1>(g, V, S, u, dmask, nrow, tid, dmB);
+    } else {
+        gs_nbt_phase<FWD, RS, Q, 1>(g, V, S, u, dmask, nrow, tid, dmA);
+        __syncthreads();
+        gs_nbt_phase<FWD, RS, Q, 0>(g, V, S, u, dmask, nrow, tid, dmB);
+    }
+}
+
 static int gs_rows_hp(const GridDesc &g) {
     const int need = g.nn[2] / 2 + 2;
     if (need <= 36) return 36;
@@ -514,6 +718,37 @@ static void gs_nb_launch(const LaunchCtx &ctx, const GridDesc &g, const VtabPara
     dim3 grid(rp.cntY, rp.cntX), block(kNbThreads);
     if (forward) VF_LAUNCH((k_gs3_nb<true, HP>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
     else         VF_LAUNCH((k_gs3_nb<false, HP>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
+    VF_KERNEL_CHECK();
+}
+
+// raw-row buffer length (doubles) for rows of nz nodes: elements -1 .. nz at offsets kRawP + o + z, one spare pair for the unused half of a load
+static int gs_nbt_rs(const GridDesc &g) {
+    const int need = g.nn[2] + 5;
+    if (need <= 76) return 76;
+    if (need <= 140) return 140;
+    if (need <= 262) return 262;
+    return 0;
+}
+// the TMA-staged kernel needs 16-byte aligned arrays and odd node counts per axis (compile-time pair alignment, see above)
+static bool gs_nbt_usable(const GridDesc &g, const double *u, const double *b, const double *E) {
+    static const bool off = [] { const char *e = std::getenv("VF_GS_TMA"); return e && e[0] == '0'; }();
+    if (off || gs_nbt_rs(g) == 0) return false;
+    if (!(g.nn[0] & 1) || !(g.nn[1] & 1) || !(g.nn[2] & 1) || g.ns[2] != 1 || g.ns[1] != g.nn[2] || g.ns[0] != (long long)g.nn[1] * g.nn[2]) return false;
+    if ((g.es[1] & 1) || (g.es[0] & 1)) return false;
+    return (((uintptr_t)u | (uintptr_t)b | (uintptr_t)E) & 15) == 0;
+}
+template<int RS, int Q>
+static void gs_nbt_launch(const LaunchCtx &ctx, const GridDesc &g, const VtabParam &V, const RowPass &rp, double *u, const double *b,
+                          const double *E, const uint8_t *dmask, bool forward) {
+    const size_t smem = (size_t)kRowArrays * RS * sizeof(double);
+    static PerDeviceFlags attr;
+    if (first_use_on_device(attr)) {
+        VF_CUDA(cudaFuncSetAttribute(k_gs3_nbt<true, RS, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VF_CUDA(cudaFuncSetAttribute(k_gs3_nbt<false, RS, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    dim3 grid(rp.cntY, rp.cntX), block(kNbThreads);
+    if (forward) VF_LAUNCH((k_gs3_nbt<true, RS, Q>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
+    else         VF_LAUNCH((k_gs3_nbt<false, RS, Q>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
     VF_KERNEL_CHECK();
 }
 
@@ -564,6 +799,12 @@ void launch_gs_rows_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K
     for (double &m : V.mag) m = 0.0;
     const bool iso = gs_rows_iso(K, V);
     static const bool nbForm = [] { const char *e = std::getenv("VF_GS_NB"); return !(e && e[0] == '0'); }();   // 0: element form (gs_row_half)
+    if (iso && nbForm && gs_nbt_usable(g, u, b, E)) {
+        const int q = (rp.px + rp.py) & 1;
+#define VF_NBT_CASE(RS_) case RS_: if (q) gs_nbt_launch<RS_, 1>(ctx, g, V, rp, u, b, E, dmask, forward); else gs_nbt_launch<RS_, 0>(ctx, g, V, rp, u, b, E, dmask, forward); return;
+        switch (gs_nbt_rs(g)) { VF_NBT_CASE(76) VF_NBT_CASE(140) VF_NBT_CASE(262) default: break; }
+#undef VF_NBT_CASE
+    }
 #define VF_ROWS_CASE(HP_) case HP_: if (iso && nbForm) gs_nb_launch<HP_>(ctx, g, V, rp, u, b, E, dmask, forward); \
                                     else if (iso) gs_rows_launch<HP_, true>(ctx, g, V, rp, u, b, E, dmask, forward); \
                                     else gs_rows_launch<HP_, false>(ctx, g, V, rp, u, b, E, dmask, forward); break;
