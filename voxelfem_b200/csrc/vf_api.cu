@@ -486,6 +486,7 @@ struct vf_mg {
     // the build direction changed (mask decrements), and sim->version == bandVersion (MultigridSolver.hh:907-1017).
     bool bandActive = false; int bandLo = 0, bandHi = 0; uint64_t bandVersion = 0;
     DevBuf<double> coarsenScratch;   // intermediates of the separable Galerkin product
+    DevBuf<unsigned> gridBar;        // arrival counter + generation of the persistent small-level sweep (k_stencil_sweep)
     DevBuf<double> Ad, d, scalars, scratch, tmpA, tmpB, tmpC;
     double *hostScalars = nullptr; // pinned
     std::vector<double> lastResiduals; int lastIters = 0; const double *pcgX = nullptr; // device iterate of the running / last PCG
@@ -989,6 +990,14 @@ void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward) {
             }
             return;
         }
+    }
+    if (l > 0 && (!lead.grp || l >= lead.firstRep) && stencil_sweep_fused(lead.grid(l))) {
+        // small level without ghost planes: the 2^N colour passes in one persistent launch (grid barrier between the colours)
+        for (vf_mg *mp : parts_of(lead)) {
+            vf_mg &mg = *mp; const GridDesc &g = mg.grid(l);
+            launch_gs_stencil_sweep(mg.ctx, g, mg.lv[l]->S.p, u(mg), b(mg), mg.dmask(l), forward, g.xoff & 1, mg.gridBar.p);
+        }
+        return;
     }
     for (int i = 0; i < nc; ++i) {
         const int color = forward ? i : (nc - 1 - i);
@@ -1563,7 +1572,7 @@ static vf_mg *mg_create_common(vf_sim *fine, int levels, int firstRep) {
     VF_CUDA(cudaStreamSynchronize(fine->stream));
     const size_t len0 = (size_t)fine->g.numNodes * N;
     mg->Ad.alloc(len0, true); mg->d.alloc(len0, true);
-    mg->scalars.alloc(SC_COUNT, true); mg->scratch.alloc(reduce_scratch_doubles(), true);
+    mg->scalars.alloc(SC_COUNT, true); mg->scratch.alloc(reduce_scratch_doubles(), true); mg->gridBar.alloc(2, true);
     VF_CUDA(cudaMallocHost(&mg->hostScalars, SC_COUNT * sizeof(double)));
     mg_sync_level_masks(*mg);
     return mg.release();

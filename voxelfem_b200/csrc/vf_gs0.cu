@@ -493,13 +493,17 @@ k_gs3_nb(const __grid_constant__ GridDesc g, const __grid_constant__ VtabParam V
 // element.  Here every row arrives RAW (z order) by ONE bulk copy (cp.async.bulk + mbarrier, no LSU instruction at all), and the
 // lanes -- which still own every other node of the row -- fetch what they need as 16-byte aligned pairs: a pair holds two of the
 // three z-neighbours (z - 1, z, z + 1) of a (row, component), the third is a second load.  Which pair is aligned depends on the
-// parity of the row's first element in global memory and on the colour; with odd node counts per axis (any grid that can be
-// coarsened) that parity is (px + py + plane + row + component) mod 2 -- a compile-time constant per launch class (template Q).
+// parity of the row's first element in global memory and on the colour; with odd node counts along axes 1 and 2 (any grid that can
+// be coarsened) that parity is (px + py + plane + row + CN * component) mod 2, CN = numNodes mod 2 (0 for a slab window with an even
+// number of planes) -- compile-time constants per launch class (templates Q, CN).
 // A row starts at element P + o of its buffer (o: parity of its global offset, P = 2): copies start and end on 16-byte boundaries,
 // and the slots of z = -1 / z = nz that no copy covers are zeroed by hand (a covered slot holds a neighbouring row's value: finite,
 // and always multiplied by a zero modulus).
 // ---------------------------------------------------------------------------------------------------------------------------------
 constexpr int kRawP = 2;
+// threads / resident blocks per SM by row-buffer length: a colour of a row has (nz + 1) / 2 nodes
+__host__ __device__ constexpr int nbt_threads(int RS) { return RS > 140 ? 160 : (RS > 76 ? 96 : 64); }
+__host__ __device__ constexpr int nbt_blocks(int RS) { return RS > 140 ? 3 : (RS > 76 ? 5 : 8); }
 template<int RS> __host__ __device__ constexpr int raw_u(int p, int r, int c) { return ((p * 3 + r) * 3 + c) * RS; }
 template<int RS> __host__ __device__ constexpr int raw_b(int c) { return (27 + c) * RS; }
 template<int RS> __host__ __device__ constexpr int raw_e(int lx, int ly) { return (30 + lx * 2 + ly) * RS; }
@@ -516,7 +520,7 @@ __device__ __forceinline__ void raw_load3(const double *row, int i, double (&v)[
     }
 }
 
-template<int RS, int Q, int PZ>
+template<int RS, int Q, int CN, int PZ>
 __device__ __forceinline__ void gs_nbt_node(const VtabParam &V, const double *S, int i, int z, int nz, double (&Ku)[3], double (&uself)[3], double (&M)[3][3]) {
     // stage 1 (axis 2): T1[v2][a0][a1]; a_k = 1: the element on the - side of the node along axis k
     double T1[4][2][2];
@@ -551,8 +555,9 @@ __device__ __forceinline__ void gs_nbt_node(const VtabParam &V, const double *S,
         #pragma unroll
         for (int d1 = -1; d1 <= 1; ++d1) {
             double un[3][3];                                     // [component][d2 + 1]
-            if ((Q + d0 + d1) & 1) { raw_load3<1, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 0), i, un[0]); raw_load3<0, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 1), i, un[1]); raw_load3<1, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 2), i, un[2]); }
-            else                   { raw_load3<0, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 0), i, un[0]); raw_load3<1, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 1), i, un[1]); raw_load3<0, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 2), i, un[2]); }
+            // parity of the row's global offset: (Q + plane + row + CN * component) mod 2
+            if ((Q + d0 + d1) & 1) { raw_load3<1, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 0), i, un[0]); raw_load3<1 ^ CN, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 1), i, un[1]); raw_load3<1, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 2), i, un[2]); }
+            else                   { raw_load3<0, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 0), i, un[0]); raw_load3<0 ^ CN, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 1), i, un[1]); raw_load3<0, PZ>(S + raw_u<RS>(d0 + 1, d1 + 1, 2), i, un[2]); }
             #pragma unroll
             for (int d2 = -1; d2 <= 1; ++d2) {
                 const int D = ((d0 != 0) << 2) | ((d1 != 0) << 1) | (d2 != 0);
@@ -598,32 +603,32 @@ __device__ __forceinline__ void gs_nbt_node(const VtabParam &V, const double *S,
     }
 }
 
-template<bool FWD, int RS, int Q, int PZ>
+template<bool FWD, int RS, int Q, int CN, int PZ>
 __device__ __forceinline__ void gs_nbt_phase(const GridDesc &g, const VtabParam &V, double *S, double *u, const uint8_t *__restrict__ dmask, long long nrow, int tid, unsigned dmFirst) {
     const int nz = g.nn[2];
     const long long NN = g.numNodes;
     const int cnt = (nz + 1 - PZ) >> 1;
     #pragma unroll 1
-    for (int i = tid; i < cnt; i += kNbThreads) {
+    for (int i = tid; i < cnt; i += nbt_threads(RS)) {
         const int z = 2 * i + PZ;
         const unsigned dm = i == tid ? dmFirst : (unsigned)dmask[nrow + z];   // first trip: fetched while the rows were in flight
         if (dm == 7u) continue;                           // hasFullDirichlet nodes are skipped (MultigridSolver.hh:350)
         double Ku[3], uself[3], M[3][3], rhs[3], du[3];
-        gs_nbt_node<RS, Q, PZ>(V, S, i, z, nz, Ku, uself, M);
+        gs_nbt_node<RS, Q, CN, PZ>(V, S, i, z, nz, Ku, uself, M);
         #pragma unroll
-        for (int c = 0; c < 3; ++c) rhs[c] = S[raw_b<RS>(c) + kRawP + ((Q + c) & 1) + z] - Ku[c];
+        for (int c = 0; c < 3; ++c) rhs[c] = S[raw_b<RS>(c) + kRawP + ((Q + CN * c) & 1) + z] - Ku[c];
         gs_node_update<3>(M, rhs, dm, FWD, du);
         #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double v = uself[c] + du[c];
             u[c * NN + nrow + z] = v;
-            S[raw_u<RS>(1, 1, c) + kRawP + ((Q + c) & 1) + z] = v;
+            S[raw_u<RS>(1, 1, c) + kRawP + ((Q + CN * c) & 1) + z] = v;
         }
     }
 }
 
-template<bool FWD, int RS, int Q>
-__global__ void __launch_bounds__(kNbThreads, 3)
+template<bool FWD, int RS, int Q, int CN>
+__global__ void __launch_bounds__(nbt_threads(RS), nbt_blocks(RS))
 k_gs3_nbt(const __grid_constant__ GridDesc g, const __grid_constant__ VtabParam V, const __grid_constant__ RowPass rp,
           double *u, const double *__restrict__ b, const double *__restrict__ E, const uint8_t *__restrict__ dmask) {
     extern __shared__ __align__(16) double S[];
@@ -673,7 +678,7 @@ k_gs3_nbt(const __grid_constant__ GridDesc g, const __grid_constant__ VtabParam 
     for (int j = 0; j < 4; ++j) {
         const int ex = x - 1 + (j >> 1), ey = y - 1 + (j & 1);
         if (!(ex >= 0 && ex < g.ne[0] && ey >= 0 && ey < g.ne[1]))
-            for (int k = tid; k < RS; k += kNbThreads) S[(30 + j) * RS + k] = 0.0;
+            for (int k = tid; k < RS; k += nbt_threads(RS)) S[(30 + j) * RS + k] = 0.0;
     }
     // Dirichlet masks of this thread's first node of either colour: fetched while the rows are in flight
     const int zA = 2 * tid + (FWD ? 0 : 1), zB = 2 * tid + (FWD ? 1 : 0);
@@ -681,13 +686,13 @@ k_gs3_nbt(const __grid_constant__ GridDesc g, const __grid_constant__ VtabParam 
     mbar_wait(&mbar, 0);
     __syncthreads();                                      // hand-written pad / tail slots
     if (FWD) {
-        gs_nbt_phase<FWD, RS, Q, 0>(g, V, S, u, dmask, nrow, tid, dmA);
+        gs_nbt_phase<FWD, RS, Q, CN, 0>(g, V, S, u, dmask, nrow, tid, dmA);
         __syncthreads();                                  // the second colour reads the first colour's new values of this row
-        gs_nbt_phase<FWD, RS, Q, 1>(g, V, S, u, dmask, nrow, tid, dmB);
+        gs_nbt_phase<FWD, RS, Q, CN, 1>(g, V, S, u, dmask, nrow, tid, dmB);
     } else {
-        gs_nbt_phase<FWD, RS, Q, 1>(g, V, S, u, dmask, nrow, tid, dmA);
+        gs_nbt_phase<FWD, RS, Q, CN, 1>(g, V, S, u, dmask, nrow, tid, dmA);
         __syncthreads();
-        gs_nbt_phase<FWD, RS, Q, 0>(g, V, S, u, dmask, nrow, tid, dmB);
+        gs_nbt_phase<FWD, RS, Q, CN, 0>(g, V, S, u, dmask, nrow, tid, dmB);
     }
 }
 
@@ -699,11 +704,17 @@ static int gs_rows_hp(const GridDesc &g) {
     return 0;
 }
 
+static bool gs_rows_iso(const K0Param &K, VtabParam &V);
 bool gs_rows_supported(const GridDesc &g, const K0Param &K) {
     static const int mode = [] { const char *e = std::getenv("VF_GS_ROWS"); return e ? std::atoi(e) : 1; }();
     if (mode == 0 || g.N != 3 || !K.walsh || g.bd != 1) return false;
-    if (g.nn[2] < 200 && mode != 2) return false;   // a 256-thread block covers 128 nodes of a colour per trip: shorter rows leave it half idle (measured: 128^3 0.35 vs 0.26 ms per sweep) -- keep the per-colour kernel
-    return gs_rows_hp(g) != 0;
+    if (gs_rows_hp(g) == 0) return false;
+    if (mode == 2 || g.nn[2] >= 200) return true;
+    // Shorter rows: the element form leaves its 256-thread block half idle (128^3: 0.35 vs 0.26 ms per sweep for the per-colour kernel),
+    // the neighbour form with its row-length dependent block size does not (128^3: 0.145 ms, 64^3: 0.042 vs 0.085 ms).
+    static const bool nbOff = [] { const char *e = std::getenv("VF_GS_NB"); return e && e[0] == '0'; }();
+    VtabParam V;
+    return !nbOff && g.nn[2] >= 9 && gs_rows_iso(K, V);
 }
 
 template<int HP>
@@ -733,22 +744,22 @@ static int gs_nbt_rs(const GridDesc &g) {
 static bool gs_nbt_usable(const GridDesc &g, const double *u, const double *b, const double *E) {
     static const bool off = [] { const char *e = std::getenv("VF_GS_TMA"); return e && e[0] == '0'; }();
     if (off || gs_nbt_rs(g) == 0) return false;
-    if (!(g.nn[0] & 1) || !(g.nn[1] & 1) || !(g.nn[2] & 1) || g.ns[2] != 1 || g.ns[1] != g.nn[2] || g.ns[0] != (long long)g.nn[1] * g.nn[2]) return false;
+    if (!(g.nn[1] & 1) || !(g.nn[2] & 1) || g.ns[2] != 1 || g.ns[1] != g.nn[2] || g.ns[0] != (long long)g.nn[1] * g.nn[2]) return false;
     if ((g.es[1] & 1) || (g.es[0] & 1)) return false;
     return (((uintptr_t)u | (uintptr_t)b | (uintptr_t)E) & 15) == 0;
 }
-template<int RS, int Q>
+template<int RS, int Q, int CN>
 static void gs_nbt_launch(const LaunchCtx &ctx, const GridDesc &g, const VtabParam &V, const RowPass &rp, double *u, const double *b,
                           const double *E, const uint8_t *dmask, bool forward) {
     const size_t smem = (size_t)kRowArrays * RS * sizeof(double);
     static PerDeviceFlags attr;
     if (first_use_on_device(attr)) {
-        VF_CUDA(cudaFuncSetAttribute(k_gs3_nbt<true, RS, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VF_CUDA(cudaFuncSetAttribute(k_gs3_nbt<false, RS, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VF_CUDA(cudaFuncSetAttribute(k_gs3_nbt<true, RS, Q, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VF_CUDA(cudaFuncSetAttribute(k_gs3_nbt<false, RS, Q, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    dim3 grid(rp.cntY, rp.cntX), block(kNbThreads);
-    if (forward) VF_LAUNCH((k_gs3_nbt<true, RS, Q>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
-    else         VF_LAUNCH((k_gs3_nbt<false, RS, Q>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
+    dim3 grid(rp.cntY, rp.cntX), block(nbt_threads(RS));
+    if (forward) VF_LAUNCH((k_gs3_nbt<true, RS, Q, CN>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
+    else         VF_LAUNCH((k_gs3_nbt<false, RS, Q, CN>), grid, block, smem, ctx.stream, g, V, rp, u, b, E, dmask);
     VF_KERNEL_CHECK();
 }
 
@@ -801,7 +812,9 @@ void launch_gs_rows_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param &K
     static const bool nbForm = [] { const char *e = std::getenv("VF_GS_NB"); return !(e && e[0] == '0'); }();   // 0: element form (gs_row_half)
     if (iso && nbForm && gs_nbt_usable(g, u, b, E)) {
         const int q = (rp.px + rp.py) & 1;
-#define VF_NBT_CASE(RS_) case RS_: if (q) gs_nbt_launch<RS_, 1>(ctx, g, V, rp, u, b, E, dmask, forward); else gs_nbt_launch<RS_, 0>(ctx, g, V, rp, u, b, E, dmask, forward); return;
+        const int cn = (int)(g.numNodes & 1);                 // does the component offset change the parity of a row's global offset?
+#define VF_NBT_CASE(RS_) case RS_: if (q && cn) gs_nbt_launch<RS_, 1, 1>(ctx, g, V, rp, u, b, E, dmask, forward); else if (cn) gs_nbt_launch<RS_, 0, 1>(ctx, g, V, rp, u, b, E, dmask, forward); \
+                                   else if (q) gs_nbt_launch<RS_, 1, 0>(ctx, g, V, rp, u, b, E, dmask, forward); else gs_nbt_launch<RS_, 0, 0>(ctx, g, V, rp, u, b, E, dmask, forward); return;
         switch (gs_nbt_rs(g)) { VF_NBT_CASE(76) VF_NBT_CASE(140) VF_NBT_CASE(262) default: break; }
 #undef VF_NBT_CASE
     }

@@ -288,6 +288,9 @@ void launch_gs3_color_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param 
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
                           const uint8_t *dmask, double *out, int mode);
 // chained: the previous kernel on the stream is a colour pass of the same sweep (nothing in flight writes S)
+bool stencil_sweep_fused(const GridDesc &g);   // small level: all colour passes of a sweep in one persistent launch
+void launch_gs_stencil_sweep(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b, const uint8_t *dmask,
+                             bool forward, int xparity, unsigned *bar);
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
                        const uint8_t *dmask, int color, bool forward, bool chained = false);
 // Galerkin coarsening (MultigridSolver.hh:711-819): level-1 stencil from the fine Young's moduli and the 2^N

@@ -201,6 +201,158 @@ static void stencil_kernel_attributes() {
     prefer_shared(k_stencil_tile<3, true, APPLY_SET, 3>); prefer_shared(k_stencil_tile<2, true, APPLY_SET, 3>);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// One smoothing sweep of a SMALL stored-stencil level in one launch.  A colour pass of a level that fits the L2 (level >= 3 of the
+// 256^3 hierarchy: <= 36k nodes) is a 2-3 us kernel behind ~8 us of launch / dependency latency, and a sweep is 2^N of them
+// (13 % of the solve in round 1).  Here a persistent grid (every block resident) runs the 2^N colour passes back to back with a
+// grid-wide barrier in between (sense-reversing counter in global memory; release / acquire at gpu scope) and loops over the tiles
+// of a colour.  Displacements are read with ld.global.cg: other blocks wrote them one colour earlier in the same launch, and L1 is
+// not coherent.  Same tile arithmetic, same visiting order (MultigridSolver.hh:408-442) as k_stencil_tile<GS>.
+// ---------------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_gpu_u32(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// bar[0]: arrivals of the current generation, bar[1]: generation.  All blocks of the grid must be resident.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned gen = ld_acquire_gpu_u32(bar + 1);
+        __threadfence();
+        if (atomicAdd(bar, 1u) == nblocks - 1) { bar[0] = 0u; __threadfence(); st_release_gpu_u32(bar + 1, gen + 1); }
+        else while (ld_acquire_gpu_u32(bar + 1) == gen) { }
+    }
+    __syncthreads();
+}
+
+template<int N>
+__global__ void __launch_bounds__(kStencilTile * Dims<N>::NS, N == 3 ? 4 : 8)
+k_stencil_sweep(const __grid_constant__ GridDesc g, const double *__restrict__ S, double *u, const double *__restrict__ b,
+                const uint8_t *__restrict__ dmask, int forward, int xparity, unsigned *bar) {
+    pdl_prologue();
+    constexpr int NS = Dims<N>::NS, A0 = Dims<N>::A0, NN = N * N, NE = Dims<N>::NE, NC = 1 << N;
+    __shared__ TileShared<N, 1> sh;
+    const int tx = threadIdx.x, s = threadIdx.y;
+    if (tx == 0 && s == 0) mbar_init(&sh.mbar, 1);
+    __syncthreads();
+    unsigned phase = 0;
+    int d[3] = {0, 0, 0};
+    { int r = s;
+      #pragma unroll
+      for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+    #pragma unroll 1
+    for (int ci = 0; ci < NC; ++ci) {
+        const int gcol = forward ? ci : NC - 1 - ci;
+        const int color = N == 3 ? (gcol ^ (xparity << 2)) : gcol;     // local parity class of this global colour (slab windows)
+        const long long tile0 = g.cbase[color] / kStencilTile;
+        const long long tot = (long long)g.ccnt[color][0] * g.ccnt[color][1] * g.ccnt[color][2];
+        const int ntile = (int)((tot + kStencilTile - 1) / kStencilTile);
+        #pragma unroll 1
+        for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
+            const long long tile = tile0 + t;
+            const long long pos = tile * kStencilTile + tx;
+            int c[3] = {0, 0, 0};
+            const bool inRange = pos_coords<N>(g, pos, c);
+            const long long n = (long long)c[0] * g.ns[0] + (long long)c[1] * g.ns[1] + c[2];
+            const bool detached = inRange && (((g.bd == 1) ? c[1] : c[2]) >= g.nActive);
+            const bool active = inRange && !detached && !(c[0] < g.cmpLo || c[0] >= g.cmpHi);
+            const int anyActive = __syncthreads_or(active ? 1 : 0);   // also: everybody is done with the previous tile's shared data
+            if (!anyActive) continue;
+            if (tx == 0 && s == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the previous tile was read through the generic proxy
+                tma_load_1d(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+            }
+            double acc[N], un[N];
+            #pragma unroll
+            for (int a = 0; a < N; ++a) { acc[a] = 0.0; un[a] = 0.0; }
+            bool valid = false;
+            if (active) {
+                if (s < N) sh.bs[s][tx] = b[s * g.numNodes + n];
+                if (s == N) sh.dm[tx] = dmask ? dmask[n] : 0u;
+                bool v = true; long long off = 0;
+                #pragma unroll
+                for (int a = A0; a < 3; ++a) { const int qq = c[a] + d[a]; v = v && qq >= 0 && qq < g.nn[a]; off += (long long)d[a] * g.ns[a]; }
+                valid = v;
+                if (v) {
+                    #pragma unroll
+                    for (int k = 0; k < N; ++k) un[k] = __ldcg(u + k * g.numNodes + n + off);
+                    if (s == NS / 2) {
+                        #pragma unroll
+                        for (int k = 0; k < N; ++k) sh.us[k][tx] = un[k];
+                    }
+                }
+            }
+            mbar_wait(&sh.mbar, phase); phase ^= 1u;
+            if (valid) {
+                #pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    #pragma unroll
+                    for (int k = 0; k < N; ++k) acc[a] = fma(sh.S[(s * NN + a * N + k) * kStencilTile + tx], un[k], acc[a]);
+                }
+            }
+            #pragma unroll
+            for (int a = 0; a < N; ++a) sh.red[a][s][tx] = acc[a];
+            __syncthreads();
+            if (s < N) {   // thread row a = s sums the slot contributions of component a (fixed order -> deterministic)
+                double tsum = 0.0;
+                #pragma unroll
+                for (int k = 0; k < NS; ++k) tsum += sh.red[s][k][tx];
+                sh.red[s][0][tx] = tsum;
+            }
+            __syncthreads();
+            if (s == 0 && active) {
+                const unsigned dm = sh.dm[tx];
+                if (dm != (unsigned)((1 << N) - 1)) {      // hasFullDirichlet nodes are skipped (MultigridSolver.hh:350)
+                    double rhs[N], M[N][N], du[N];
+                    #pragma unroll
+                    for (int a = 0; a < N; ++a) {
+                        rhs[a] = sh.bs[a][tx] - sh.red[a][0][tx];
+                        #pragma unroll
+                        for (int k = 0; k < N; ++k) M[a][k] = sh.S[((NS / 2) * NN + a * N + k) * kStencilTile + tx];
+                    }
+                    gs_node_update<N>(M, rhs, dm, forward != 0, du);
+                    #pragma unroll
+                    for (int a = 0; a < N; ++a) u[a * g.numNodes + n] = sh.us[a][tx] + du[a];
+                }
+            }
+        }
+        if (ci + 1 < NC) grid_barrier(bar, gridDim.x);
+    }
+}
+
+// whether launch_gs_stencil_sweep() handles this level.  OFF by default: measured on B200 (profiles/r04f_bench_fused_sweep.log) the
+// persistent sweep LOSES to the 2^N programmatic-dependent-launch chained colour passes replayed from the CUDA graph -- 256^3
+// solve 175.4 ms (chained) vs 177.9 ms (levels <= 5k nodes fused) vs 180.7 ms (levels <= 70k nodes fused): inside a graph a chained
+// colour pass costs ~4 us, less than a grid barrier plus an exposed TMA round trip.  VF_SWEEP_FUSED_NODES=<n> enables it for levels
+// of up to n nodes (the parity tests run with it on and off).
+bool stencil_sweep_fused(const GridDesc &g) {
+    static const long long limit = [] { const char *e = std::getenv("VF_SWEEP_FUSED_NODES"); return e ? std::atoll(e) : 0LL; }();
+    return g.numNodes <= limit;
+}
+void launch_gs_stencil_sweep(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b, const uint8_t *dmask,
+                             bool forward, int xparity, unsigned *bar) {
+    stencil_kernel_attributes();
+    static PerDeviceFlags once; static int maxBlocks[2] = {0, 0};
+    if (first_use_on_device(once)) {
+        int dev = 0, sms = 0, occ3 = 0, occ2 = 0;
+        VF_CUDA(cudaGetDevice(&dev)); VF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        prefer_shared(k_stencil_sweep<3>); prefer_shared(k_stencil_sweep<2>);
+        VF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_stencil_sweep<3>, kStencilTile * 27, 0));
+        VF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_stencil_sweep<2>, kStencilTile * 9, 0));
+        maxBlocks[1] = sms * std::max(occ3, 1); maxBlocks[0] = sms * std::max(occ2, 1);
+    }
+    long long ntileMax = 1, nodes = 0;
+    for (int c = 0; c < (1 << g.N); ++c) {
+        const long long tot = (long long)g.ccnt[c][0] * g.ccnt[c][1] * g.ccnt[c][2];
+        ntileMax = std::max(ntileMax, (tot + kStencilTile - 1) / kStencilTile); nodes += tot;
+    }
+    ProfScope ps(ctx, PC_GS_ST_SMALL, (double)nodes);
+    // every block must be resident (grid barrier): never more blocks than fit, and not the whole machine for a handful of tiles
+    const int blocks = (int)std::min<long long>(ntileMax, maxBlocks[g.N == 3 ? 1 : 0]);
+    dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)blocks);
+    if (g.N == 3) VF_LAUNCH((k_stencil_sweep<3>), grid, block, 0, ctx.stream, g, S, u, b, dmask, forward ? 1 : 0, xparity, bar);
+    else          VF_LAUNCH((k_stencil_sweep<2>), grid, block, 0, ctx.stream, g, S, u, b, dmask, forward ? 1 : 0, xparity, bar);
+    VF_KERNEL_CHECK();
+}
+
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
                           const uint8_t *dmask, double *out, int mode) {
     stencil_kernel_attributes();
