@@ -8,7 +8,6 @@
 #include "vf_internal.cuh"
 #include "../../include/voxelfem_b200.h"
 
-#include <cusolverDn.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -132,29 +131,17 @@ static void set_mask_limits(GridDesc &g, int firstMasked, int firstDetached) {
 }
 
 // ---------------------------------------------------------------------------
-// Dense SPD solver on the GPU (stands in for CHOLMOD): Cholesky factor by cuSOLVER potrf, then the explicit inverse of
-// the triangular factor (trtri) -- NOT the full inverse (potri's lauum/trmm stage costs as much as everything else
-// together).  A solve is two bandwidth-bound triangular mat-vecs  x = L^-T (L^-1 b)  on a matrix that stays L2-resident,
-// so the coarse solve on the V-cycle's critical path is two small kernels with no dependent-block latency chain.
+// Dense SPD solver on the GPU (stands in for CHOLMOD, TensorProductSimulator.hh:1198-1230): Cholesky factor L and the explicit
+// inverse of the TRIANGULAR FACTOR -- not the full inverse.  A solve is two bandwidth-bound triangular mat-vecs
+// x = L^-T (L^-1 b) on a matrix that stays L2-resident, so the coarse solve on the V-cycle's critical path is two small kernels
+// with no dependent-block latency chain.  The factorization runs on this library's own kernels (vf_dense.cu: a tiled FP64 matrix
+// product and a single-block Cholesky + inversion of 64 x 64 diagonal blocks); no cuSOLVER / cuBLAS.
 // ---------------------------------------------------------------------------
 struct DenseSolver {
-    cusolverDnHandle_t handle = nullptr; cublasHandle_t blas = nullptr;
-    DevBuf<double> A, W, Lip, Tbuf, work, rhs, y; DevBuf<int> info, red, freeDofs; std::vector<char> hostWork;
+    DevBuf<double> A, W, Lb, Lip, Tbuf, work, rhs, y; DevBuf<int> info, red, freeDofs;
     int nfree = 0; bool ok = false;
-    ~DenseSolver() { if (handle) cusolverDnDestroy(handle); if (blas) cublasDestroy(blas); }
-    void init_handle(cudaStream_t s) {
-        if (!handle) {
-            if (cusolverDnCreate(&handle) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("cusolverDnCreate failed");
-        }
-        cusolverDnSetStream(handle, s);
-        if (!blas) {
-            if (cublasCreate(&blas) != CUBLAS_STATUS_SUCCESS) throw std::runtime_error("cublasCreate failed");
-        }
-        cublasSetStream(blas, s);
-    }
     // fixed: per-DOF flags in (node*N + c) order
     void factor(const LaunchCtx &ctx, const GridDesc &g, const double *S, const std::vector<uint8_t> &fixed) {
-        init_handle(ctx.stream);
         const long long ndof = g.numNodes * g.N;
         // Free DOFs are numbered plane by plane along the longest grid axis: nodes of non-adjacent planes do not couple, so the
         // matrix of the free DOFs is block tridiagonal with one block per node plane (blockOff).
@@ -175,91 +162,87 @@ struct DenseSolver {
         VF_CUDA(cudaStreamSynchronize(ctx.stream)); // redH / freeH are stack-owned
         if (nfree == 0) { ok = true; return; }
         if (A.n != (size_t)nfree * nfree) A.alloc((size_t)nfree * nfree, false);   // A.p stays put: captured CUDA graphs hold it
-        VF_CUDA(cudaMemsetAsync(A.p, 0, sizeof(double) * A.n, ctx.stream));
+        if (W.n != (size_t)nfree * nfree) W.alloc((size_t)nfree * nfree, false);
+        VF_CUDA(cudaMemsetAsync(A.p, 0, sizeof(double) * A.n, ctx.stream));       // receives L^-1: zeros above the diagonal
+        VF_CUDA(cudaMemsetAsync(W.p, 0, sizeof(double) * W.n, ctx.stream));
         rhs.alloc(nfree, true); y.alloc(nfree, true);
+        info.alloc(1, true);
         int maxBlock = 0, nBlocks = 0;
         for (size_t b = 0; b + 1 < blockOff.size(); ++b) { const int m = blockOff[b + 1] - blockOff[b]; maxBlock = std::max(maxBlock, m); nBlocks += m > 0; }
         static const bool noBlockTri = [] { const char *e = std::getenv("VF_COARSE_DENSE"); return e && e[0] == '1'; }();
-        if (!noBlockTri && nBlocks >= 3 && maxBlock >= 96) {
-            if (W.n != (size_t)nfree * nfree) W.alloc((size_t)nfree * nfree, false);
-            VF_CUDA(cudaMemsetAsync(W.p, 0, sizeof(double) * W.n, ctx.stream));
-            launch_stencil_to_dense(ctx, g, S, red.p, nfree, W.p);
-            factor_block_tridiagonal(ctx, blockOff, maxBlock);
-        } else {
-            launch_stencil_to_dense(ctx, g, S, red.p, nfree, A.p);
-            factor_dense(ctx);
-        }
-        // cuSOLVER / cuBLAS (column-major, lower) hold L^-1(r, c), r >= c, at A[c * n + r]: in our row-major reading that is row c,
-        // column r -- the upper triangle, i.e. L^-T.  Mirror it so that the lower triangle holds L^-1 row by row.
+        launch_stencil_to_dense(ctx, g, S, red.p, nfree, W.p);
+        if (!noBlockTri && nBlocks >= 3 && maxBlock >= 96) factor_block_tridiagonal(ctx, blockOff, maxBlock);
+        else factor_dense(ctx);
+        check_info(ctx);
+        // The factorization is written in column-major terms: L^-1(r, c), r >= c, sits at A[c * n + r] -- in our row-major reading
+        // that is row c, column r: the upper triangle, i.e. L^-T.  Mirror it so that the lower triangle holds L^-1 row by row.
         launch_symmetrize_upper_to_lower(ctx);
         ok = true;
     }
-    void check_info(const LaunchCtx &ctx, int count) {
-        std::vector<int> h(count, 0); info.download(h.data(), count, ctx.stream);
-        for (int i = 0; i < count; ++i)
-            if (h[i] != 0) throw std::runtime_error("Cholesky factorization failed: coarse stiffness matrix is not positive definite (info = " + std::to_string(h[i]) + ")");
+    void check_info(const LaunchCtx &ctx) {
+        int h = 0; info.download(&h, 1, ctx.stream);
+        if (h != 0) throw std::runtime_error("Cholesky factorization failed: coarse stiffness matrix is not positive definite (pivot " + std::to_string(h - 1) + ")");
     }
-    // Dense path: potrf + trtri on the whole matrix (small or unstructured coarse grids).
+    // Dense path (small or unstructured coarse grids): blocked Cholesky + inversion of the whole matrix.
     void factor_dense(const LaunchCtx &ctx) {
-        int lwork1 = 0; size_t wdev = 0, whost = 0;
-        info.alloc(1, true);
-        // Row-major symmetric == column-major symmetric; factor the "lower" triangle in cuSOLVER's column-major view.
-        if (cusolverDnDpotrf_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, &lwork1) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf_bufferSize failed");
-        if (cusolverDnXtrtri_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, nfree, CUDA_R_64F, A.p, nfree, &wdev, &whost) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("trtri_bufferSize failed");
-        const size_t lwork = std::max((size_t)lwork1, (wdev + sizeof(double) - 1) / sizeof(double));
-        if (lwork > work.n) work.alloc(lwork, false);
-        if (whost > hostWork.size()) hostWork.resize(whost);
-        count_launch();
-        if (cusolverDnDpotrf(handle, CUBLAS_FILL_MODE_LOWER, nfree, A.p, nfree, work.p, lwork1, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf failed");
-        check_info(ctx, 1);
-        count_launch();
-        if (cusolverDnXtrtri(handle, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, nfree, CUDA_R_64F, A.p, nfree, work.p, wdev, hostWork.data(), whost, info.p) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("trtri failed");
+        const int n = nfree;
+        if (Lb.n < (size_t)n * n) Lb.alloc((size_t)n * n, false);
+        if (work.n < (size_t)kDiagBlockHost * n) work.alloc((size_t)kDiagBlockHost * n, false);
+        potrf_inv_blocked(ctx, W.p, n, n, Lb.p, n, A.p, n, work.p, info.p, 0);
     }
-    // Block-tridiagonal path (stands in for CHOLMOD's sparse factorization, TensorProductSimulator.hh:1198-1230): block Cholesky
+    // Block-tridiagonal path: block Cholesky
     //   L_ii L_ii^T = A_ii - L_ip L_ip^T,  L_ip = A_ip L_pp^-T   (p = i - 1)
     // followed by the block forward substitution L X = I, X_ii = L_ii^-1, X_i,: = -L_ii^-1 L_ip X_p,: , which leaves the dense
     // lower-triangular L^-1 that solve() applies as two bandwidth-bound triangular mat-vecs.  n bw^2 + n^2 bw flops in
-    // GEMM-shaped calls instead of the 2/3 n^3 of a dense potrf + trtri.  All in cuBLAS column-major terms on the symmetric A.
+    // matrix products instead of the 2/3 n^3 of a dense factorization + inversion.
+    // The factor chain (L_ip, Schur update, factorization + inversion of the diagonal block) is sequential over the blocks; the block
+    // rows of L^-1 left of the diagonal only feed the NEXT block row, so they run on a side stream behind the chain (forked / joined
+    // with events; L_ip and the product buffer are double-buffered between the two streams).
+    cudaStream_t side = nullptr; cudaEvent_t evChain[2] = {nullptr, nullptr}, evRow[2] = {nullptr, nullptr}, evJoin = nullptr;
+    ~DenseSolver() {
+        for (cudaEvent_t e : {evChain[0], evChain[1], evRow[0], evRow[1], evJoin}) if (e) cudaEventDestroy(e);
+        if (side) cudaStreamDestroy(side);
+    }
     void factor_block_tridiagonal(const LaunchCtx &ctx, const std::vector<int> &off, int maxBlock) {
-        const int n = nfree, nb = (int)off.size() - 1;   // W: the matrix, overwritten by its block factor; A: receives L^-1
-        info.alloc(nb, true);
-        int lwork = 0;
-        if (cusolverDnDpotrf_bufferSize(handle, CUBLAS_FILL_MODE_LOWER, maxBlock, W.p, n, &lwork) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf_bufferSize failed");
-        if ((size_t)lwork > work.n) work.alloc(lwork, false);
+        const int n = nfree, nb = (int)off.size() - 1;   // W: the matrix (lower triangle), A: receives L^-1
         auto M = [&](int i, int j) { return W.p + (size_t)off[j] * n + off[i]; };   // block (i, j), leading dimension n
         auto X = [&](int i, int j) { return A.p + (size_t)off[j] * n + off[i]; };
-        const double one = 1.0, mone = -1.0, zero = 0.0;
-        auto chk = [](cublasStatus_t st, const char *what) { if (st != CUBLAS_STATUS_SUCCESS) throw std::runtime_error(std::string("cuBLAS ") + what + " failed"); };
-        // Triangular solves against wide right-hand sides are replaced by products with the explicit L_ii^-1 (GEMM-shaped).
-        if (Lip.n < (size_t)maxBlock * maxBlock) Lip.alloc((size_t)maxBlock * maxBlock, false);
+        if (Lip.n < (size_t)2 * maxBlock * maxBlock) Lip.alloc((size_t)2 * maxBlock * maxBlock, false);
+        if (Lb.n < (size_t)maxBlock * maxBlock) Lb.alloc((size_t)maxBlock * maxBlock, false);
         if (Tbuf.n < (size_t)maxBlock * n) Tbuf.alloc((size_t)maxBlock * n, false);
-        int prev = -1;
+        if (work.n < (size_t)kDiagBlockHost * maxBlock) work.alloc((size_t)kDiagBlockHost * maxBlock, false);
+        if (!side) {
+            VF_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+            for (cudaEvent_t *e : {&evChain[0], &evChain[1], &evRow[0], &evRow[1], &evJoin}) VF_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        }
+        LaunchCtx sctx = ctx; sctx.stream = side; sctx.prof = nullptr;
+        // the side stream starts behind everything the chain's stream has done so far (the memsets of A, the assembly of W)
+        VF_CUDA(cudaEventRecord(evJoin, ctx.stream)); VF_CUDA(cudaStreamWaitEvent(side, evJoin, 0));
+        int prev = -1, step = 0; bool rowPending[2] = {false, false};
         for (int i = 0; i < nb; ++i) {
             const int m = off[i + 1] - off[i];
             if (m == 0) continue;
             const bool coupled = prev == i - 1 && prev >= 0;
             const int mp = coupled ? off[prev + 1] - off[prev] : 0;
+            const int slot = step & 1;
+            double *lip = Lip.p + (size_t)slot * maxBlock * maxBlock;
             if (coupled) {   // L_ip = A_ip L_pp^-T = A_ip X_pp^T;  A_ii -= L_ip L_ip^T
-                count_launch();
-                chk(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, m, mp, mp, &one, M(i, prev), n, X(prev, prev), n, &zero, Lip.p, m), "gemm");
-                chk(cublasDsyrk(blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, m, mp, &mone, Lip.p, m, &one, M(i, i), n), "syrk");
+                if (rowPending[slot]) { VF_CUDA(cudaStreamWaitEvent(ctx.stream, evRow[slot], 0)); rowPending[slot] = false; }   // the row update two steps back still reads this L_ip buffer
+                launch_dgemm(ctx, true, m, mp, mp, 1.0, M(i, prev), n, X(prev, prev), n, 0.0, lip, m, false);
+                launch_dgemm(ctx, true, m, m, mp, -1.0, lip, m, lip, m, 1.0, M(i, i), n, true);
             }
-            count_launch();
-            if (cusolverDnDpotrf(handle, CUBLAS_FILL_MODE_LOWER, m, M(i, i), n, work.p, lwork, info.p + i) != CUSOLVER_STATUS_SUCCESS) throw std::runtime_error("potrf failed");
-            // X_ii = L_ii^-1 (solve against the identity), then the block row left of the diagonal: X_i,: = -X_ii (L_ip X_p,:)
-            launch_set_identity(ctx, X(i, i), m, n);
-            chk(cublasDtrsm(blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, m, m, &one, M(i, i), n, X(i, i), n), "trsm");
-            if (coupled && off[i] > 0) {
-                const int w = off[i];   // all columns left of block i
-                count_launch();
-                chk(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, m, w, mp, &one, Lip.p, m, X(prev, 0), n, &zero, Tbuf.p, m), "gemm");
-                chk(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, m, w, m, &mone, X(i, i), n, Tbuf.p, m, &zero, X(i, 0), n), "gemm");
+            potrf_inv_blocked(ctx, M(i, i), n, m, Lb.p, maxBlock, X(i, i), n, work.p, info.p, off[i]);
+            if (coupled && off[i] > 0) {   // the block row left of the diagonal: X_i,: = -X_ii (L_ip X_p,:)
+                const int w = off[i];
+                VF_CUDA(cudaEventRecord(evChain[slot], ctx.stream)); VF_CUDA(cudaStreamWaitEvent(side, evChain[slot], 0));
+                launch_dgemm(sctx, false, m, w, mp, 1.0, lip, m, X(prev, 0), n, 0.0, Tbuf.p, m, false);
+                launch_dgemm(sctx, false, m, w, m, -1.0, X(i, i), n, Tbuf.p, m, 0.0, X(i, 0), n, false);
+                VF_CUDA(cudaEventRecord(evRow[slot], side)); rowPending[slot] = true;
             }
-            prev = i;
+            prev = i; ++step;
         }
-        check_info(ctx, nb);
+        VF_CUDA(cudaEventRecord(evJoin, side)); VF_CUDA(cudaStreamWaitEvent(ctx.stream, evJoin, 0));
     }
-    void launch_set_identity(const LaunchCtx &ctx, double *B, int m, int ld);
     void launch_symmetrize_upper_to_lower(const LaunchCtx &ctx);
     // x = A^-1 f on free DOFs, zero on fixed DOFs (TensorProductSimulator.hh:1227-1229, 1243-1252)
     void solve(const LaunchCtx &ctx, const GridDesc &g, const double *f, double *x) {
@@ -279,16 +262,7 @@ __global__ void k_sym_upper_to_lower(double *A, int n) { // row-major: copy A[i]
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i < n && j < n && j > i) A[(size_t)j * n + i] = A[(size_t)i * n + j];
 }
-__global__ void k_set_identity(double *B, int m, int ld) { // column-major block, leading dimension ld
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i < m && j < m) B[(size_t)j * ld + i] = i == j ? 1.0 : 0.0;
-}
 namespace vf {
-void DenseSolver::launch_set_identity(const LaunchCtx &ctx, double *B, int m, int ld) {
-    dim3 block(32, 8), grid((m + 31) / 32, (m + 7) / 8);
-    k_set_identity<<<grid, block, 0, ctx.stream>>>(B, m, ld);
-    VF_KERNEL_CHECK();
-}
 void DenseSolver::launch_symmetrize_upper_to_lower(const LaunchCtx &ctx) {
     // cuSOLVER (column-major, FILL_MODE_LOWER) holds element (r, c), r >= c, at A[c * n + r]; in our row-major reading
     // that is row c, column r >= c: the upper triangle.  Mirror it into the lower triangle.

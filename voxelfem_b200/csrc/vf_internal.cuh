@@ -317,6 +317,15 @@ void launch_dense_trmv(const LaunchCtx &ctx, const double *A, int n, const doubl
 void launch_gather_free(const LaunchCtx &ctx, const double *f, const int *freeDofs, int nfree, long long numNodes, int N, double *rhs);
 void launch_scatter_free(const LaunchCtx &ctx, const double *y, const int *freeDofs, int nfree, long long numNodes, int N, double *x);
 
+// --- vf_dense.cu: dense FP64 kernels of the coarsest-level direct solver (column-major, leading dimensions)
+constexpr int kDiagBlockHost = 64;   // panel width of the blocked factorization (== kDiagBlock of vf_dense.cu)
+// C (m x n) = alpha * A (m x k) * op(B) + beta * C;  transB: B is n x k;  lowerOnly: skip the tiles strictly above the diagonal
+void launch_dgemm(const LaunchCtx &ctx, bool transB, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb,
+                  double beta, double *C, int ldc, bool lowerOnly);
+// M (m x m SPD, lower triangle read, trailing part overwritten) -> Lb = L (scratch), X = L^-1 (zeros above the diagonal must be there);
+// tmp: kDiagBlockHost * m doubles; *info (zero-initialised) receives infoBase + 1 + index of the first non-positive pivot
+void potrf_inv_blocked(const LaunchCtx &ctx, double *M, int ld, int m, double *Lb, int ldl, double *X, int ldx, double *tmp, int *info, int infoBase);
+
 // --- vf_vec.cu: transfers and PCG vector kernels
 // Grid transfers between two windows: fine plane index = 2 * coarse plane index + xshift(gf, gc) along embedded axis 0.
 VF_HD int xshift(const GridDesc &gf, const GridDesc &gc) { return 2 * gc.xoff - gf.xoff; }
