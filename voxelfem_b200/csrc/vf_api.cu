@@ -523,10 +523,11 @@ constexpr int kNcclDouble = 8, kNcclSum = 0; // ncclFloat64, ncclSum (nccl.h)
 // Every rank owns, per neighbour, a ring of kP2PSlots MAILBOXES in its own HBM plus two words: `ready` (written by the neighbour:
 // sequence number of the last message it deposited) and `consumed` (written by the neighbour: sequence number of the last message
 // of MINE it has unpacked).  Mailboxes and words are exported with CUDA IPC, so the neighbour's kernels store into them directly
-// over NVLink.  An exchange is two kernels per side on the solver's stream and NO host-side communication call:
-//   k_p2p_send: waits (rarely) until the slot it is about to overwrite has been consumed, packs the boundary plane straight into the
+// over NVLink.  An exchange is ONE kernel (k_p2p_exchange) on the solver's stream and NO host-side communication call; its blocks play
+// up to four roles:
+//   send:       waits (rarely) until the slot it is about to overwrite has been consumed, packs the boundary plane straight into the
 //               neighbour's mailbox, fences at system scope and publishes `ready = seq`;
-//   k_p2p_recv: spins on the local `ready` word, copies the mailbox into the ghost plane and publishes `consumed = seq` to the sender.
+//   receive:    spins on the local `ready` word, copies the mailbox into the ghost plane and publishes `consumed = seq` to the sender.
 // Sequence numbers live in device memory, so the kernels replay unchanged from a captured CUDA graph.  A spin that lasts longer
 // than kP2PTimeoutNs sets an error word instead of hanging the device.  NCCL remains the transport of the all-reduces (PCG
 // scalars, replicated coarse fields) and the fallback of the exchange (VF_P2P=0).
@@ -625,79 +626,103 @@ __device__ __forceinline__ bool p2p_wait(const unsigned long long *word, unsigne
     while (ld_acquire_sys(word) < target) { if (global_timer_ns() - t0 > kP2PTimeoutNs) return false; __nanosleep(200); }
     return true;
 }
-// pack N component planes (n doubles each, component stride compStride) into the neighbour's mailbox slot and publish it
-__global__ void __launch_bounds__(256) k_p2p_send(const double *__restrict__ src, long long compStride, long long n, int ncomp,
-                                                  double *peerBox, size_t slotDoubles, P2PWords *mine, P2PWords *peer) {
+// One ghost-plane exchange of a rank = ONE kernel: its blocks are split into up to four roles (send to / receive from the lower and
+// the upper neighbour).  The send blocks never wait for this rank's receive blocks (only, rarely, for a free mailbox slot), the
+// receive blocks spin on the neighbour's `ready` word; all blocks of the launch are resident (<= 256 blocks), so no role starves.
+struct P2PRole {
+    double *field;            // send: first component plane to pack; receive: first ghost component plane to fill
+    double *box;              // send: the neighbour's mailbox ring; receive: my mailbox ring
+    P2PWords *mine, *peer;
+    long long compStride, n; size_t slotDoubles; int ncomp, nblocks, recv;
+};
+struct P2PExchange { P2PRole role[4]; int nroles; };
+// pack ncomp component planes (n doubles each, component stride compStride) into the neighbour's mailbox slot and publish it
+__device__ __forceinline__ void p2p_send_body(const P2PRole &R, int blk) {
     __shared__ unsigned long long s_seq; __shared__ int s_ok;
     if (threadIdx.x == 0) {
-        const unsigned long long seq = mine->sendSeq[0] + 1;
+        const unsigned long long seq = R.mine->sendSeq[0] + 1;
         s_seq = seq;
         // the slot is free once the neighbour has unpacked the message that used it last (kP2PSlots messages ago)
-        s_ok = (seq <= (unsigned long long)kP2PSlots) || p2p_wait(&mine->consumed[0], seq - kP2PSlots);
-        if (!s_ok) mine->error[0] = 1;
+        s_ok = (seq <= (unsigned long long)kP2PSlots) || p2p_wait(&R.mine->consumed[0], seq - kP2PSlots);
+        if (!s_ok) R.mine->error[0] = 1;
     }
     __syncthreads();
     const unsigned long long seq = s_seq;
-    double *dst = peerBox + (size_t)(seq % kP2PSlots) * slotDoubles;
+    double *dst = R.box + (size_t)(seq % kP2PSlots) * R.slotDoubles;
     if (s_ok) {
-        const long long total = n * ncomp;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-            const long long c = i / n, k = i - c * n;
-            dst[i] = src[c * compStride + k];
+        const long long total = R.n * R.ncomp;
+        for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < total; i += (long long)R.nblocks * blockDim.x) {
+            const long long c = i / R.n, k = i - c * R.n;
+            dst[i] = R.field[c * R.compStride + k];
         }
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned long long done = atomicAdd(&mine->sendDone[0], 1ULL) + 1;
-        if (done == gridDim.x) {                       // last block: everything of this message is visible system-wide
-            mine->sendDone[0] = 0;
+        const unsigned long long done = atomicAdd(&R.mine->sendDone[0], 1ULL) + 1;
+        if (done == (unsigned long long)R.nblocks) {   // last block: everything of this message is visible system-wide
+            R.mine->sendDone[0] = 0;
             __threadfence_system();
-            st_release_sys(&peer->ready[0], seq);
-            mine->sendSeq[0] = seq;
+            st_release_sys(&R.peer->ready[0], seq);
+            R.mine->sendSeq[0] = seq;
         }
     }
 }
-__global__ void __launch_bounds__(256) k_p2p_recv(double *__restrict__ dstField, long long compStride, long long n, int ncomp,
-                                                  const double *myBox, size_t slotDoubles, P2PWords *mine, P2PWords *peer) {
-    __shared__ unsigned long long s_seq; __shared__ int s_ok;
+__device__ __forceinline__ void p2p_recv_body(const P2PRole &R, int blk) {
+    __shared__ unsigned long long r_seq; __shared__ int r_ok;
     if (threadIdx.x == 0) {
-        const unsigned long long seq = mine->recvSeq[0] + 1;
-        s_seq = seq;
-        s_ok = p2p_wait(&mine->ready[0], seq);
-        if (!s_ok) mine->error[0] = 2;
+        const unsigned long long seq = R.mine->recvSeq[0] + 1;
+        r_seq = seq;
+        r_ok = p2p_wait(&R.mine->ready[0], seq);
+        if (!r_ok) R.mine->error[0] = 2;
     }
     __syncthreads();
-    const unsigned long long seq = s_seq;
-    const double *box = myBox + (size_t)(seq % kP2PSlots) * slotDoubles;
-    if (s_ok) {
-        const long long total = n * ncomp;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-            const long long c = i / n, k = i - c * n;
-            dstField[c * compStride + k] = __ldcg(box + i);     // written by the neighbour: bypass L1
+    const unsigned long long seq = r_seq;
+    const double *box = R.box + (size_t)(seq % kP2PSlots) * R.slotDoubles;
+    if (r_ok) {
+        const long long total = R.n * R.ncomp;
+        for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < total; i += (long long)R.nblocks * blockDim.x) {
+            const long long c = i / R.n, k = i - c * R.n;
+            R.field[c * R.compStride + k] = __ldcg(box + i);     // written by the neighbour: bypass L1
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned long long done = atomicAdd(&mine->recvDone[0], 1ULL) + 1;
-        if (done == gridDim.x) {
-            mine->recvDone[0] = 0;
+        const unsigned long long done = atomicAdd(&R.mine->recvDone[0], 1ULL) + 1;
+        if (done == (unsigned long long)R.nblocks) {
+            R.mine->recvDone[0] = 0;
             __threadfence_system();
-            st_release_sys(&peer->consumed[0], seq);
-            mine->recvSeq[0] = seq;
+            st_release_sys(&R.peer->consumed[0], seq);
+            R.mine->recvSeq[0] = seq;
         }
+    }
+}
+__global__ void __launch_bounds__(256) k_p2p_exchange(const __grid_constant__ P2PExchange X) {
+    int blk = blockIdx.x;
+    #pragma unroll 1
+    for (int r = 0; r < X.nroles; ++r) {
+        if (blk < X.role[r].nblocks) { if (X.role[r].recv) p2p_recv_body(X.role[r], blk); else p2p_send_body(X.role[r], blk); return; }
+        blk -= X.role[r].nblocks;
     }
 }
 static int p2p_blocks(long long n, int ncomp) { return (int)std::min<long long>((n * ncomp + 255) / 256, 64); }
-static void p2p_send_side(vf_group &G, int side, const double *sendPlane, long long compStride, long long n, int ncomp, cudaStream_t stream) {
-    P2PLink &L = G.link[side];
-    if ((size_t)(n * ncomp) > L.slotDoubles) throw std::runtime_error("ghost plane larger than the peer mailbox");
-    k_p2p_send<<<p2p_blocks(n, ncomp), 256, 0, stream>>>(sendPlane, compStride, n, ncomp, L.peerBox, L.slotDoubles, L.myWords, L.peerWords);
-    VF_KERNEL_CHECK();
-}
-static void p2p_recv_side(vf_group &G, int side, double *recvPlane, long long compStride, long long n, int ncomp, cudaStream_t stream) {
-    P2PLink &L = G.link[side];
-    k_p2p_recv<<<p2p_blocks(n, ncomp), 256, 0, stream>>>(recvPlane, compStride, n, ncomp, L.myBox, L.slotDoubles, L.myWords, L.peerWords);
+// sendL / sendR: first component plane to send to the lower / upper neighbour (nullptr: none); recvL / recvR: ghost planes to fill
+static void p2p_exchange(vf_group &G, double *sendL, double *sendR, double *recvL, double *recvR, long long compStride, long long n, int ncomp, cudaStream_t stream) {
+    P2PExchange X; X.nroles = 0;
+    int total = 0;
+    auto add = [&](int side, double *field, bool recv) {
+        if (!field) return;
+        P2PLink &L = G.link[side];
+        if ((size_t)(n * ncomp) > L.slotDoubles) throw std::runtime_error("ghost plane larger than the peer mailbox");
+        P2PRole &R = X.role[X.nroles++];
+        R.field = field; R.box = recv ? L.myBox : L.peerBox; R.mine = L.myWords; R.peer = L.peerWords;
+        R.compStride = compStride; R.n = n; R.slotDoubles = L.slotDoubles; R.ncomp = ncomp; R.nblocks = p2p_blocks(n, ncomp); R.recv = recv ? 1 : 0;
+        total += R.nblocks;
+    };
+    // sends first in block order: they are scheduled no later than the receives of the same launch
+    add(0, sendL, false); add(1, sendR, false); add(0, recvL, true); add(1, recvR, true);
+    if (!X.nroles) return;
+    k_p2p_exchange<<<total, 256, 0, stream>>>(X);
     VF_KERNEL_CHECK();
 }
 // a timed-out wait leaves an error word behind: turned into an exception at the solver's synchronisation points
@@ -778,11 +803,8 @@ template<class Sel> void grp_exchange(vf_mg &lead, int l, Sel sel, int parity = 
         if (!doLeft && !doRight) return;
         if (G.p2p) {   // device-initiated: the neighbour's kernels deposit the planes in this rank's mailboxes (see P2PLink)
             count_launch();
-            // both sends first: no rank's send ever waits behind a receive, so there is no chain of waits along the slabs
-            if (doLeft)  p2p_send_side(G, 0, planePtr(m, 0, L.sb + 1), g.numNodes, g.ns[0], N, lead.ctx.stream);
-            if (doRight) p2p_send_side(G, 1, planePtr(m, 0, L.se - 1), g.numNodes, g.ns[0], N, lead.ctx.stream);
-            if (doLeft)  p2p_recv_side(G, 0, planePtr(m, 0, L.sb - 1), g.numNodes, g.ns[0], N, lead.ctx.stream);
-            if (doRight) p2p_recv_side(G, 1, planePtr(m, 0, L.se + 1), g.numNodes, g.ns[0], N, lead.ctx.stream);
+            p2p_exchange(G, doLeft ? planePtr(m, 0, L.sb + 1) : nullptr, doRight ? planePtr(m, 0, L.se - 1) : nullptr,
+                         doLeft ? planePtr(m, 0, L.sb - 1) : nullptr, doRight ? planePtr(m, 0, L.se + 1) : nullptr, g.numNodes, g.ns[0], N, lead.ctx.stream);
             return;
         }
         NcclApi &A = NcclApi::get();
