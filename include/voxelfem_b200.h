@@ -115,6 +115,12 @@ int vf_sim_add_dirichlet_box(vf_sim *s, const double *u, const double *box_min, 
 int vf_sim_apply_symmetry_conditions(vf_sim *s, int axes_mask, int max_face_mask);
 int vf_sim_get_dirichlet_mask(const vf_sim *s, uint8_t *mask_per_node);  /* getDirichletMask (:675-682), bit c = component c */
 int64_t vf_sim_num_force_nodes(const vf_sim *s);
+int64_t vf_sim_num_dirichlet_nodes(const vf_sim *s);
+/* m_dirichletNodes / m_dirichletComponents / m_dirichletNodeDisplacements (getDirichletVarsAndValues, TensorProductSimulator.hh:1790-1835;
+ * getBCIndicatorField :697-712): nodes[n], masks[n] (bit c = component c constrained), values[n * N] */
+int vf_sim_get_dirichlet_conditions(const vf_sim *s, int64_t *nodes, uint8_t *masks, double *values);
+/* m_forceNodes / m_forceNodeForces (getForceMask :685-695): nodes[n], forces[n * N], n = vf_sim_num_force_nodes() */
+int vf_sim_get_force_nodes(const vf_sim *s, int64_t *nodes, double *forces);
 int64_t vf_sim_num_nonzero_dirichlet_values(const vf_sim *s);  /* prescribed non-zero displacements (getIntermediateFabricationShape validates them, :1893-1895) */
 int vf_sim_build_load_vector(vf_sim *s, double *f);                      /* buildLoadVector (:1269-1288) */
 /* applyK<ZeroInit,Negate> (:1410-1438 -> TPSStencils.hh:231-396, 431-728).

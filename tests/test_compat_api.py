@@ -104,8 +104,11 @@ def test_out_of_scope_names_fail_loudly():
     v2c = m.VertexToCellFilter(); v2c.setOutputDimensions([8, 4]); assert list(v2c.inputDimensions) == [9, 5]
     with pytest.raises(NotImplementedError, match="MultigridComplianceObjective"):
         m.ComplianceObjective(None)
-    with pytest.raises(NotImplementedError, match="getK"):
-        m._TPS.getK(object.__new__(m._TPS))
+    # the export / post-processing methods are built since round 2 (compat/tps_extras.py); nothing of the
+    # simulator's bound surface is left raising NotImplementedError
+    for name in ("getK", "constantStrainLoad", "solveWithImposedLoads", "getDirichletVarsAndValues", "getForceMask", "getBCIndicatorField", "sampleNodalField",
+                 "getMesh", "debugMulticolorElementVisit", "transferVFieldToIntermediateFabricationShape", "accumElementScalarFieldFromIntermediateFabricationShape"):
+        assert callable(getattr(m._TPS, name)) and getattr(m._TPS, name).__name__ == name
     with pytest.raises(RuntimeError, match="No template instantiation"):
         m.TensorProductSimulator([2, 2], [[0, 0], [1, 1]], [4, 4])
 

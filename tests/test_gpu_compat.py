@@ -257,3 +257,79 @@ def test_layer_by_layer_optimization_flow(vf, data_dir):
     assert abs(top.evaluateConstraints()[0]) <= 1e-6
     rep = benchmark.report
     rep()
+
+
+@pytest.mark.parametrize("dim,grid,corner", [(2, [8, 6], [4.0, 3.0]), (3, [6, 4, 4], [3.0, 2.0, 2.0])])
+def test_export_and_postprocessing_methods(vf, data_dir, dim, grid, corner, tmp_path):
+    """getK, getMesh, sampleNodalField, getDirichletVarsAndValues, getForceMask, getBCIndicatorField,
+    constantStrainLoad, solveWithImposedLoads, debugMulticolorElementVisit, the intermediate-shape transfers and .msh output --
+    checked against the operators of the solve path and against closed forms."""
+    bc = os.path.join(data_dir, "bcs", "3D" if dim == 3 else "", "cantilever_flexion_E.bc")
+    tps = vf.TensorProductSimulator([1] * dim, [[0] * dim, corner], grid)
+    tps.readMaterial(os.path.join(data_dir, "materials", "B9Creator.material"))
+    tps.applyDisplacementsAndLoadsFromFile(bc)
+    tps.E_min = 0.0; tps.gamma = 1.0                                      # E(rho) = rho: constantStrainLoad scales by the DENSITY
+    rng = np.random.default_rng(11)
+    rho = rng.uniform(0.2, 1.0, tps.numElements())
+    tps.setDensities(rho)
+    nn = tps.numNodes()
+    # getK: the upper triangle of the assembled matrix reproduces the matrix-free operator
+    K = tps.getK()
+    Kfull = K + K.T - __import__("scipy.sparse", fromlist=["diags"]).diags(K.diagonal())
+    u = rng.normal(size=(nn, dim))
+    assert rel_l2((Kfull @ u.ravel()).reshape(nn, dim), tps.applyK(u)) < 1e-13
+    assert (K - __import__("scipy.sparse", fromlist=["triu"]).triu(K)).nnz == 0
+    # Dirichlet / force bookkeeping
+    mask = tps.getDirichletMask()
+    dvars, dvals = tps.getDirichletVarsAndValues()
+    assert sorted(dvars) == sorted(np.flatnonzero(mask.ravel()).tolist()) and all(v == 0 for v in dvals)
+    f = tps.buildLoadVector()
+    assert np.array_equal(np.asarray(tps.getForceMask()), f != 0)
+    ind = np.asarray(tps.getBCIndicatorField())
+    bits = (mask * (1 << np.arange(dim))).sum(axis=1) + (1 << dim) * ((f != 0) * (1 << np.arange(dim))).sum(axis=1)
+    assert np.array_equal(ind, bits.astype(float))
+    # mesh + sampling: nodal values at the vertices, the mean of the corner values at element centroids, clamping outside
+    V, F = tps.getMesh()
+    assert V.shape == (nn, 3) and F.shape == (tps.numElements(), 2 ** dim)
+    assert np.allclose(V[:, :dim], np.array([tps.nodePosition(i) for i in range(nn)]))
+    assert rel_l2(np.asarray(tps.sampleNodalField(u, V[:, :dim])), u) < 1e-13
+    cent = V[F].mean(axis=1)[:, :dim]
+    assert rel_l2(np.asarray(tps.sampleNodalField(u, cent)), u[F].mean(axis=1)) < 1e-13
+    far = np.array([[-5.0] * dim, [1e3] * dim])
+    assert np.allclose(np.asarray(tps.sampleNodalField(u, far)), u[[0, nn - 1]])
+    # constant-strain load: multilinear elements reproduce u(x) = eps x, so the load is K u_lin when E(rho) = rho
+    eps = rng.normal(size=(dim, dim)); eps = 0.5 * (eps + eps.T)
+    assert rel_l2(np.asarray(tps.constantStrainLoad(eps)), tps.applyK(V[:, :dim] @ eps.T)) < 1e-12
+    flat = [eps[i, i] for i in range(dim)] + ([eps[0, 1]] if dim == 2 else [eps[1, 2], eps[0, 2], eps[0, 1]])
+    assert rel_l2(np.asarray(tps.constantStrainLoad(flat)), np.asarray(tps.constantStrainLoad(eps))) < 1e-15
+    # direct solve with the imposed loads
+    us = np.asarray(tps.solveWithImposedLoads())
+    assert rel_l2(us, tps.solve(f)) < 1e-12 and np.all(us[mask] == 0)
+    # multicoloured element visit: a permutation, colour by colour (2^N parity classes, axis 0 outermost)
+    rank = np.asarray(tps.debugMulticolorElementVisit()).astype(int).reshape(grid)
+    assert sorted(rank.ravel().tolist()) == list(range(tps.numElements()))
+    par = lambda r: tuple(int(v) % 2 for v in np.unravel_index(int(np.flatnonzero(rank.ravel() == r)[0]), grid))
+    cols = [par(r) for r in range(tps.numElements())]
+    assert cols == sorted(cols)
+    # intermediate fabrication shape transfers
+    tps2 = vf.TensorProductSimulator([1] * dim, [[0] * dim, corner], grid)
+    tps2.readMaterial(os.path.join(data_dir, "materials", "B9Creator.material")); tps2.setDensities(rho)
+    g = np.zeros(dim); g[1] = -1.0; tps2.gravity = g
+    lo = [-1e-9] * dim; hi = [c + 1e-9 for c in corner]; hi[1] = 1e-9
+    tps2.addDirichletCondition([0.0] * dim, lo, hi, "xyz"[:dim])
+    inter = tps2.getIntermediateFabricationShape(0.5)
+    ui = np.asarray(tps2.transferVFieldToIntermediateFabricationShape(inter, u))
+    shp = tuple(np.array(grid) + 1)
+    assert np.array_equal(ui, u.reshape(shp + (dim,))[:, :grid[1] // 2 + 1].reshape(-1, dim))
+    acc = np.ones(tps2.numElements())
+    gi = rng.normal(size=inter.numElements())
+    tps2.accumElementScalarFieldFromIntermediateFabricationShape(inter, gi, acc)
+    exp = np.ones(grid); exp[:, :grid[1] // 2] += gi.reshape(tuple(inter.NbElementsPerDimension))
+    assert np.array_equal(acc, exp.ravel())
+    # .msh output of the simulator's fields and reading it back
+    sys.path.insert(0, ROOT)
+    from voxelfem_b200.compat import msh
+    path = str(tmp_path / "out.msh")
+    msh.write_fields(tps, path, element_fields={"density": rho}, node_fields={"u": u})
+    assert np.array_equal(msh.densities_from_msh(tps, path), rho)
+    assert np.array_equal(msh.MSHFieldParser(path).vectorField("u"), u)

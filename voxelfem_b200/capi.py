@@ -100,6 +100,9 @@ def lib():
         "vf_sim_apply_symmetry_conditions": (ci, [vp, ci, ci]),
         "vf_sim_get_dirichlet_mask": (ci, [vp, _u8p]),
         "vf_sim_num_force_nodes": (i64, [vp]),
+        "vf_sim_num_dirichlet_nodes": (i64, [vp]),
+        "vf_sim_get_dirichlet_conditions": (ci, [vp, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), _dp]),
+        "vf_sim_get_force_nodes": (ci, [vp, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), _dp]),
         "vf_sim_num_nonzero_dirichlet_values": (i64, [vp]),
         "vf_sim_build_load_vector": (ci, [vp, _dp]),
         "vf_sim_build_load_vector_dev": (ci, [vp, vp]),
@@ -446,6 +449,20 @@ class Sim(_Owned):
         out = np.zeros(self.num_nodes, dtype=np.uint8); _check(self.L.vf_sim_get_dirichlet_mask(self.h, out)); return out
 
     def num_force_nodes(self): return int(self.L.vf_sim_num_force_nodes(self.h))
+
+    def dirichlet_conditions(self):
+        """(nodes, component masks, values (n, N)) of the stored Dirichlet conditions, ascending node index."""
+        n = int(self.L.vf_sim_num_dirichlet_nodes(self.h))
+        nodes, masks, vals = np.zeros(max(n, 1), dtype=np.int64), np.zeros(max(n, 1), dtype=np.uint8), np.zeros(max(n, 1) * self.N)
+        _check(self.L.vf_sim_get_dirichlet_conditions(self.h, nodes, masks, vals))
+        return nodes[:n], masks[:n], vals[:n * self.N].reshape(n, self.N)
+
+    def force_nodes(self):
+        """(nodes, forces (n, N)) of the stored nodal forces."""
+        n = self.num_force_nodes()
+        nodes, f = np.zeros(max(n, 1), dtype=np.int64), np.zeros(max(n, 1) * self.N)
+        _check(self.L.vf_sim_get_force_nodes(self.h, nodes, f))
+        return nodes[:n], f[:n * self.N].reshape(n, self.N)
     def has_nonzero_dirichlet_values(self): return int(self.L.vf_sim_num_nonzero_dirichlet_values(self.h)) != 0
 
     def build_load(self):

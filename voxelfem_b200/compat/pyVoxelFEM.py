@@ -22,6 +22,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))   # repo root
 from voxelfem_b200 import capi  # noqa: E402
+from voxelfem_b200.compat import tps_extras  # noqa: E402
 
 
 class InterpolationLaw(enum.IntEnum):          # VoxelFEM.cc:407-410
@@ -229,11 +230,21 @@ class _TPS:
         for d in range(self._N): g = np.repeat(g, f, axis=d)
         return g.ravel() * (1.0 / f ** self._N)
 
-    for _n in ("getK", "constantStrainLoad", "solveWithImposedLoads", "getDirichletVarsAndValues", "getForceMask", "getBCIndicatorField",
-               "sampleNodalField", "getMesh", "debugMulticolorElementVisit", "transferVFieldToIntermediateFabricationShape",
-               "accumElementScalarFieldFromIntermediateFabricationShape"):
-        locals()[_n] = _unsupported(_n)
-    del _n
+    # ---- export / post-processing next to the solve path: compat/tps_extras.py ----
+    def _dirichletConditions(self): return self._s.dirichlet_conditions()
+    def _forceNodes(self): return self._s.force_nodes()
+    def getK(self): return tps_extras.getK(self)
+    def constantStrainLoad(self, eps): return tps_extras.constantStrainLoad(self, eps)
+    def solveWithImposedLoads(self): return tps_extras.solveWithImposedLoads(self)
+    def getDirichletVarsAndValues(self): return tps_extras.getDirichletVarsAndValues(self)
+    def getForceMask(self): return tps_extras.getForceMask(self)
+    def getBCIndicatorField(self): return tps_extras.getBCIndicatorField(self)
+    def sampleNodalField(self, u, p): return tps_extras.sampleNodalField(self, u, p)
+    def getMesh(self): return tps_extras.getMesh(self)
+    def debugMulticolorElementVisit(self): return tps_extras.debugMulticolorElementVisit(self)
+    def transferVFieldToIntermediateFabricationShape(self, intermediateTPS, u): return tps_extras.transferVFieldToIntermediateFabricationShape(self, intermediateTPS, u)
+    def accumElementScalarFieldFromIntermediateFabricationShape(self, intermediateTPS, rho_in, rho_accum):
+        tps_extras.accumElementScalarFieldFromIntermediateFabricationShape(self, intermediateTPS, rho_in, rho_accum)
 
 
 class _LevelSim:

@@ -1407,6 +1407,20 @@ int64_t vf_sim_num_nonzero_dirichlet_values(const vf_sim *s) {
 }
 int vf_sim_get_dirichlet_mask(const vf_sim *s, uint8_t *m) { VF_TRY std::copy(s->nodeMask.begin(), s->nodeMask.end(), m); VF_CATCH }
 int64_t vf_sim_num_force_nodes(const vf_sim *s) { return (int64_t)s->forceNodes.size(); }
+int64_t vf_sim_num_dirichlet_nodes(const vf_sim *s) { return (int64_t)s->dirNodes.size(); }
+// nodes[n], masks[n] (bit c: component c constrained), values[n * N] in the order the conditions are stored (ascending node index)
+int vf_sim_get_dirichlet_conditions(const vf_sim *s, int64_t *nodes, uint8_t *masks, double *values) {
+    VF_TRY
+    std::copy(s->dirNodes.begin(), s->dirNodes.end(), nodes); std::copy(s->dirMask.begin(), s->dirMask.end(), masks);
+    std::copy(s->dirVals.begin(), s->dirVals.end(), values);
+    VF_CATCH
+}
+// nodes[n], forces[n * N]: the per-node forces of the "force" / "traction" conditions (TensorProductSimulator.hh:617-632)
+int vf_sim_get_force_nodes(const vf_sim *s, int64_t *nodes, double *forces) {
+    VF_TRY
+    std::copy(s->forceNodes.begin(), s->forceNodes.end(), nodes); std::copy(s->forceVals.begin(), s->forceVals.end(), forces);
+    VF_CATCH
+}
 int vf_sim_build_load_vector_dev(vf_sim *s, double *f_dev) { VF_TRY sim_build_load_dev(*s, f_dev); VF_CATCH }
 int vf_sim_build_load_vector(vf_sim *s, double *f) {
     VF_TRY double *t = sim_tmp(s, 0); sim_build_load_dev(*s, t); d2h(f, t, (size_t)s->g.numNodes * s->N, s->stream); VF_CATCH

@@ -142,10 +142,26 @@ void addTPSBindings(py::module &m, py::module &detail) {
        .def("downsample", &TPS::downsample, py::arg("downsamplingLevels"))
        .def("downsampleDensityFieldTo", [](const TPS &s, const NpArr &rho, TPS &coarse) { s.downsampleDensityFieldTo(to_vxd(rho), coarse); }, py::arg("densities"), py::arg("coarseTPS"))
        .def("upsampleDensityGradientFrom", [](const TPS &s, const TPS &coarse, const NpArr &g) { return from_vxd(s.upsampleDensityGradientFrom(coarse, to_vxd(g))); }, py::arg("coarseTPS"), py::arg("g_coarse"));
+    // Export / post-processing methods next to the solve path: one host-side implementation written
+    // against the public simulator API (voxelfem_b200/compat/tps_extras.py), shared with the ctypes flavour of this module.
+    tps.def("_dirichletConditions", [](const TPS &s) {
+            const size_t n = (size_t)vf_sim_num_dirichlet_nodes(s.handle());
+            py::array_t<int64_t> nodes((py::ssize_t)n); py::array_t<uint8_t> masks((py::ssize_t)n); py::array_t<double> vals({(py::ssize_t)n, (py::ssize_t)N});
+            std::vector<int64_t> hn(std::max<size_t>(n, 1)); std::vector<uint8_t> hm(std::max<size_t>(n, 1)); std::vector<double> hv(std::max<size_t>(n, 1) * N);
+            if (vf_sim_get_dirichlet_conditions(s.handle(), hn.data(), hm.data(), hv.data()) != 0) throw std::runtime_error(vf_last_error());
+            std::copy(hn.begin(), hn.begin() + n, nodes.mutable_data()); std::copy(hm.begin(), hm.begin() + n, masks.mutable_data()); std::copy(hv.begin(), hv.begin() + n * N, vals.mutable_data());
+            return py::make_tuple(nodes, masks, vals); })
+       .def("_forceNodes", [](const TPS &s) {
+            const size_t n = (size_t)vf_sim_num_force_nodes(s.handle());
+            py::array_t<int64_t> nodes((py::ssize_t)n); py::array_t<double> f({(py::ssize_t)n, (py::ssize_t)N});
+            std::vector<int64_t> hn(std::max<size_t>(n, 1)); std::vector<double> hf(std::max<size_t>(n, 1) * N);
+            if (vf_sim_get_force_nodes(s.handle(), hn.data(), hf.data()) != 0) throw std::runtime_error(vf_last_error());
+            std::copy(hn.begin(), hn.begin() + n, nodes.mutable_data()); std::copy(hf.begin(), hf.begin() + n * N, f.mutable_data());
+            return py::make_tuple(nodes, f); });
     for (const char *name : {"getK", "constantStrainLoad", "solveWithImposedLoads", "getDirichletVarsAndValues", "getForceMask", "getBCIndicatorField", "sampleNodalField", "getMesh",
                              "debugMulticolorElementVisit", "transferVFieldToIntermediateFabricationShape", "accumElementScalarFieldFromIntermediateFabricationShape"}) {
         const std::string n = name;
-        tps.def(name, [n](py::args, py::kwargs) { not_on_path("TensorProductSimulator." + n); });
+        tps.def(name, [n](py::object self, py::args a, py::kwargs kw) { return py::module_::import("voxelfem_b200.compat.tps_extras").attr(n.c_str())(self, *a, **kw); });
     }
 
     using LSV = LevelSimView<MG>;
