@@ -318,6 +318,28 @@ int vf_group_top_last_pcg_iterations(vf_gtop *t);
 int vf_group_top_get_u(vf_gtop *t, int local_part, double *u_window);          /* displacement window of a local part, component-major */
 int vf_group_top_oc_step(vf_gtop *t, double m, double p, double ctol, int *num_constraint_evals); /* OCOptimizer::step (OptimalityCriterion.hh:51-134) */
 
+/* ---- Degree-2 (Q2) elements: TensorProductSimulator<double, 2, 2[, 2]> on the reference's generic element path ---------------
+ * (the reference's python bindings instantiate degree 1 only, python_bindings/VoxelFEM.cc:303-308).
+ * Node grid (2 ne + 1)^N; nodal fields component-major (c * numNodes + node) like everywhere in this ABI; K0 is (N 3^N)^2 with
+ * entry index N * local_node + component, local nodes row-major over 3^N (TPSStencils.hh:139).                                   */
+typedef struct vf_q2 vf_q2;
+int vf_q2_create(int dim, const int64_t *num_elements, const double *domain_min, const double *domain_max, vf_q2 **out);   /* TensorProductSimulator.hh:209-279 */
+int vf_q2_destroy(vf_q2 *s);
+int64_t vf_q2_num_nodes(const vf_q2 *s);
+int64_t vf_q2_num_elements(const vf_q2 *s);
+int vf_q2_set_isotropic(vf_q2 *s, double young, double poisson);                       /* setETensor (:343-347) */
+int vf_q2_set_elasticity_tensor(vf_q2 *s, const double *D);                            /* flattened 6x6 / 3x3, row-major */
+int vf_q2_get_K0(const vf_q2 *s, double *out);                                         /* fullDensityElementStiffnessMatrix: Element_T::Stiffness (:67-80), Gauss degree 4 per axis */
+int vf_q2_set_interpolation(vf_q2 *s, int law, double E_0, double E_min, double gamma, double q);   /* :2055-2102 */
+int vf_q2_set_densities(vf_q2 *s, const double *rho);
+int vf_q2_get_young_moduli(const vf_q2 *s, double *E);
+int vf_q2_apply_K(vf_q2 *s, const double *u, double *out, int zero_init, int negate);  /* generic applyK<ZeroInit, Negate> (TPSStencils.hh:163-185) */
+int vf_q2_element_energies(vf_q2 *s, const double *u, double *energy);                 /* u_e^T K0 u_e per element (elementEnergyDensity :1057-1073 up to the modulus) */
+/* Jacobi-preconditioned CG on the Q2 operator with the flagged components (numNodes * N bytes, component-major) clamped to zero;
+ * x: initial guess in, solution out.  Stands in for the reference's direct solve of Q2 systems (TPS::solve, :1198-1230): the
+ * reference has no multigrid instantiation for degree 2 either. */
+int vf_q2_pcg(vf_q2 *s, double *x, const double *b, const uint8_t *fixed, int max_iter, double tol, int *iters, double *rel_residual);
+
 /* ---- Layer-by-layer evaluator ------------------------------------------------------ */
 int vf_lbl_create(vf_mg *mg, vf_lbl **out);                       /* LayerByLayerEvaluator(lblSim) (LayerByLayer.hh:33-36) */
 int vf_lbl_destroy(vf_lbl *l);

@@ -208,6 +208,19 @@ def lib():
         "vf_group_top_last_pcg_iterations": (ci, [vp]),
         "vf_group_top_get_u": (ci, [vp, ci, _dp]),
         "vf_group_top_oc_step": (ci, [vp, cd, cd, cd, C.POINTER(ci)]),
+        "vf_q2_create": (ci, [ci, _ip, _dp, _dp, pvp]),
+        "vf_q2_destroy": (ci, [vp]),
+        "vf_q2_num_nodes": (i64, [vp]),
+        "vf_q2_num_elements": (i64, [vp]),
+        "vf_q2_set_isotropic": (ci, [vp, cd, cd]),
+        "vf_q2_set_elasticity_tensor": (ci, [vp, _dp]),
+        "vf_q2_get_K0": (ci, [vp, _dp]),
+        "vf_q2_set_interpolation": (ci, [vp, ci, cd, cd, cd, cd]),
+        "vf_q2_set_densities": (ci, [vp, _dp]),
+        "vf_q2_get_young_moduli": (ci, [vp, _dp]),
+        "vf_q2_apply_K": (ci, [vp, _dp, _dp, ci, ci]),
+        "vf_q2_element_energies": (ci, [vp, _dp, _dp]),
+        "vf_q2_pcg": (ci, [vp, _dp, _dp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), ci, cd, C.POINTER(ci), C.POINTER(cd)]),
         "vf_lbl_create": (ci, [vp, pvp]),
         "vf_lbl_destroy": (ci, [vp]),
         "vf_lbl_select_init_method": (ci, [vp, C.c_char_p]),
@@ -862,6 +875,48 @@ def projection_apply(x, beta):
 def projection_backprop(g, vars_, beta):
     g = np.ascontiguousarray(g, dtype=np.float64).ravel(); out = np.zeros_like(g)
     _check(lib().vf_filter_project_backprop(len(g), beta, g, np.ascontiguousarray(vars_, dtype=np.float64).ravel(), out)); return out
+
+
+class SimQ2(_Owned):
+    """TensorProductSimulator<double, 2, 2[, 2]> on the reference's generic element path (vf_q2_*, csrc/vf_q2.cu): K0, applyK, element
+    energies and a Jacobi-preconditioned CG.  Nodal fields are (numNodes, N) arrays over the (2 ne + 1)^N node grid."""
+
+    def __init__(self, ne, dmin=None, dmax=None):
+        self.L = lib()
+        self.ne = np.ascontiguousarray(ne, dtype=np.int64); self.N = len(self.ne)
+        dmin = np.zeros(self.N) if dmin is None else np.ascontiguousarray(dmin, dtype=np.float64)
+        dmax = self.ne.astype(np.float64) if dmax is None else np.ascontiguousarray(dmax, dtype=np.float64)
+        h = C.c_void_p()
+        _check(self.L.vf_q2_create(self.N, self.ne, dmin, dmax, C.byref(h)))
+        self._own(h, self.L.vf_q2_destroy)
+        self.num_nodes, self.num_elements = int(self.L.vf_q2_num_nodes(self.h)), int(self.L.vf_q2_num_elements(self.h))
+
+    def set_isotropic(self, E, nu): _check(self.L.vf_q2_set_isotropic(self.h, E, nu))
+    def set_elasticity_tensor(self, D): _check(self.L.vf_q2_set_elasticity_tensor(self.h, np.ascontiguousarray(D, dtype=np.float64)))
+    def set_interp(self, law=0, E0=1.0, Emin=1e-4, gamma=3.0, q=3.0): _check(self.L.vf_q2_set_interpolation(self.h, law, E0, Emin, gamma, q))
+    def set_densities(self, rho): _check(self.L.vf_q2_set_densities(self.h, np.ascontiguousarray(rho, dtype=np.float64).ravel()))
+
+    def K0(self):
+        k = self.N * 3 ** self.N
+        out = np.zeros((k, k)); _check(self.L.vf_q2_get_K0(self.h, out)); return out
+
+    def E(self):
+        out = np.zeros(self.num_elements); _check(self.L.vf_q2_get_young_moduli(self.h, out)); return out
+
+    def apply_K(self, u, out=None, zero_init=True, negate=False):
+        o = np.zeros(self.num_nodes * self.N) if out is None else to_soa(out)
+        _check(self.L.vf_q2_apply_K(self.h, to_soa(u), o, int(zero_init), int(negate)))
+        return from_soa(o, self.N)
+
+    def element_energies(self, u):
+        out = np.zeros(self.num_elements); _check(self.L.vf_q2_element_energies(self.h, to_soa(u), out)); return out
+
+    def pcg(self, x0, b, fixed, max_iter=2000, tol=1e-10):
+        """-> (x, iterations, relative residual); fixed: boolean (numNodes, N) mask of clamped components."""
+        x = to_soa(x0).copy(); it, rr = C.c_int(0), C.c_double(0)
+        fx = np.ascontiguousarray(np.asarray(fixed, dtype=np.uint8).T).ravel()
+        _check(self.L.vf_q2_pcg(self.h, x, to_soa(b), fx, max_iter, tol, C.byref(it), C.byref(rr)))
+        return from_soa(x, self.N), it.value, rr.value
 
 
 class LBL(_Owned):
