@@ -228,6 +228,22 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same copy with an L2 evict-first hint: for data that is streamed once per pass (stored stencils), so that it does not push
+// the re-used nodal fields out of the L2
+__device__ __forceinline__ void tma_load_1d_stream(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+// a global load that asks the L2 to keep the line (evict-last): the nodal fields of a level whose stencil streams past them
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); return pol;
+}
+__device__ __forceinline__ double ld_l2_hint(const double *p, unsigned long long pol) {
+    double v; asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
     asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
                  ::"r"(smem_u32(bar)), "r"(parity) : "memory");

@@ -77,7 +77,10 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     if (tx == 0 && s == 0) mbar_init(&sh.mbar, 1);
     const int anyActive = __syncthreads_or(active ? 1 : 0);     // also publishes the barrier initialisation
     if (!earlyTile) pdl_wait();
-    if (anyActive && tx == 0 && s == 0) tma_load_1d(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+    if (anyActive && tx == 0 && s == 0) {
+        if (flags & 4) tma_load_1d_stream(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+        else           tma_load_1d(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+    }
     if (earlyTile) pdl_wait();
     if (anyActive) {
         double acc[N], un[SPT][N];
@@ -106,8 +109,14 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
                 for (int a = A0; a < 3; ++a) { const int qq = c[a] + d[a]; v = v && qq >= 0 && qq < g.nn[a]; off += (long long)d[a] * g.ns[a]; }
                 valid[j] = v;
                 if (v) {
-                    #pragma unroll
-                    for (int k = 0; k < N; ++k) un[j][k] = uin[k * g.numNodes + n + off];
+                    if (flags & 8) {
+                        const unsigned long long keep = l2_policy_evict_last();
+                        #pragma unroll
+                        for (int k = 0; k < N; ++k) un[j][k] = ld_l2_hint(uin + k * g.numNodes + n + off, keep);
+                    } else {
+                        #pragma unroll
+                        for (int k = 0; k < N; ++k) un[j][k] = uin[k * g.numNodes + n + off];
+                    }
                     if (GS && slot == NS / 2) {
                         #pragma unroll
                         for (int k = 0; k < N; ++k) sh.us[k][tx] = un[j][k];
@@ -182,6 +191,13 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     }
 }
 
+// flags bit 2: fetch the stencil tile with an L2 evict-first hint (levels whose stencil streams from HBM; VF_ST_EVICT_FIRST=0 disables)
+static int stencil_stream_hint(const GridDesc &g) {
+    static const bool on = [] { const char *e = std::getenv("VF_ST_EVICT_FIRST"); return !(e && e[0] == '0'); }();
+    const double bytes = (double)g.numNodes * (g.N == 3 ? 1944.0 : 288.0);
+    static const bool keepU = [] { const char *e = std::getenv("VF_ST_KEEP_U"); return e && e[0] == '1'; }();
+    return (on && bytes > 64.0 * 1048576.0) ? (keepU ? 12 : 4) : 0;   // larger than half the L2: the stencil cannot stay resident between passes anyway
+}
 static int stencil_slots_per_thread() {
     static const int v = [] { const char *e = std::getenv("VF_ST_SPT"); return (e && std::atoi(e) == 3) ? 3 : 1; }();
     return v;
@@ -359,10 +375,11 @@ void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double 
     const bool big = stencil_level_streams(g);
     ProfScope ps(ctx, mode == APPLY_RESIDUAL ? (big ? PC_RESIDUAL_ST : PC_RESIDUAL_ST_SMALL) : (big ? PC_APPLY_ST : PC_APPLY_ST_SMALL), (double)g.numNodes);
     const int spt = stencil_slots_per_thread();
+    const int hint = stencil_stream_hint(g);
     dim3 block(kStencilTile, (g.N == 3 ? 27 : 9) / spt), grid((unsigned)(g.numPos / kStencilTile));
 #define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) { \
-        if (spt == 3) VF_LAUNCH((k_stencil_tile<NN_, false, M, 3>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1); \
-        else          VF_LAUNCH((k_stencil_tile<NN_, false, M, 1>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1); }
+        if (spt == 3) VF_LAUNCH((k_stencil_tile<NN_, false, M, 3>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint); \
+        else          VF_LAUNCH((k_stencil_tile<NN_, false, M, 1>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint); }
     VF_CASE(3, APPLY_SET) VF_CASE(3, APPLY_ADD) VF_CASE(3, APPLY_SUB) VF_CASE(3, APPLY_RESIDUAL)
     VF_CASE(2, APPLY_SET) VF_CASE(2, APPLY_ADD) VF_CASE(2, APPLY_SUB) VF_CASE(2, APPLY_RESIDUAL)
 #undef VF_CASE
@@ -379,7 +396,7 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
     const int spt = stencil_slots_per_thread();
     dim3 block(kStencilTile, (g.N == 3 ? 27 : 9) / spt), grid((unsigned)((tot + kStencilTile - 1) / kStencilTile));
     const long long tile0 = g.cbase[color] / kStencilTile;
-    const int fl = (forward ? 1 : 0) | (chained ? 2 : 0);
+    const int fl = (forward ? 1 : 0) | (chained ? 2 : 0) | stencil_stream_hint(g);
     if (g.N == 3 && spt == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
     else if (g.N == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
     else if (spt == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
