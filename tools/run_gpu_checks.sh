@@ -19,3 +19,6 @@ tail -3 $O/${T}_bench.err
 timeout 300 python tools/time_ops.py > $O/${T}_time_ops.log 2>&1; grep -E "level [01] |vcycle|FMG" $O/${T}_time_ops.log
 timeout 300 python tools/bench_topopt.py > $O/${T}_topopt_C2.log 2>&1; tail -1 $O/${T}_topopt_C2.log | cut -c1-300
 timeout 300 python tools/bench_lbl.py > $O/${T}_lbl_C5.log 2>&1; tail -1 $O/${T}_lbl_C5.log | cut -c1-400
+# ncu launch list of one solve capped at 1 PCG iteration (per-launch device times: shares of the step, not bench values)
+timeout 600 ncu --clock-control none --metrics gpu__time_duration.sum -c 4000 --csv --log-file $O/${T}_launches.csv python tools/profile_driver.py "C3_pcg_256^3" 1 > $O/${T}_launches.log 2>&1
+python tools/summarize_launches.py $O/${T}_launches.csv > $O/${T}_launches_summary.txt 2>&1; head -14 $O/${T}_launches_summary.txt
