@@ -2,6 +2,7 @@
 host_smoke.cpp on the GPU; every printed number is compared with the CPU oracle on the same problem."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -65,6 +66,33 @@ def test_cpp_topopt_and_errors(smoke_output, data_dir):
     assert abs(float(o["topopt_jacobian_entry"]) - op.constraint_jacobian()[0]) < 1e-12
     assert abs(float(o["mma_mean"]) - 0.2) < 1e-5                        # the volume constraint is active at the optimum
     assert o["odd_grid_error"].startswith("runtime_error") and "divisible" in o["odd_grid_error"]
+
+
+@pytest.mark.gpu
+def test_cpp_slab_problem_and_q2(smoke_output):
+    """The slab-partitioned problem (SlabTopologyOptimizationProblem over vf_group_top_*, two local slabs) reproduces the undivided
+    C++ problem iteration by iteration; the Q2 simulator reproduces the numpy restatement of the generic element path."""
+    o = smoke_output
+    for it in range(3):
+        c, cu = float(o["slab_compliance_%d" % it]), float(o["topopt_compliance_%d" % it])
+        assert abs(c - cu) < 1e-8 * abs(cu), it
+        assert abs(float(o["slab_constraint_%d" % it]) - float(o["topopt_constraint_%d" % it])) < 1e-9
+    assert abs(float(o["slab_sum_vars"]) - float(o["topopt_sum_vars"])) < 1e-7 * float(o["topopt_sum_vars"])
+    assert abs(float(o["slab_sum_gradient"]) - float(o["topopt_sum_gradient"])) < 1e-6 * abs(float(o["topopt_sum_gradient"]))
+    assert int(o["slab_halo_layers"]) == 4                                  # max(2 * 2, 2 + 1) for SmoothingFilter(2) + ProjectionFilter
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import q2ref
+    s = q2ref.Q2Sim([3, 2, 2], np.zeros(3), np.array([1.5, 1.0, 1.0])); s.set_isotropic(1.0, 0.3); s.set_interp(0, 1.0, 1e-3, 3.0, 3.0)
+    X = s.node_positions()
+    u = X * np.array([0.01, -0.003, -0.003])
+    assert int(o["q2_nodes"]) == s.num_nodes
+    assert float(o["q2_K0_asymmetry"]) == 0 and float(o["q2_K0_translation"]) < 1e-13
+    assert abs(float(o["q2_K0_trace"]) - np.trace(s.K0)) < 1e-12 * np.trace(s.K0)
+    e = s.element_energies(u).sum()
+    assert abs(float(o["q2_linear_field_energy"]) - e) < 1e-12 * e
+    assert abs(float(o["q2_uKu"]) - (u * s.apply_K(u)).sum()) < 1e-12 * e
+    # closed form: full density (E = 1), uniaxial stress state eps = (0.01, -0.003, -0.003) -> sigma_xx = 0.01, energy = vol * sigma : eps
+    assert abs(e - 1.5 * 0.01 * 0.01) < 1e-12
 
 
 def test_cpp_host_header_compiles_and_fails_loudly_without_gpu():

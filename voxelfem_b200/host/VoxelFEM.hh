@@ -136,6 +136,28 @@ private:
 };
 } // namespace detail
 
+namespace detail {
+// applyDisplacementsAndLoadsFromFile (TensorProductSimulator.hh:654-658; JSON regions of MeshFEM BoundaryConditions.cc:219-380) on a
+// simulator handle: `box%` regions are fractions of the GLOBAL domain (also for a slab window)
+inline void apply_bc_file(vf_sim *h, int N, const double *domMin, const double *domMax, const std::string &bcPath) {
+    std::ifstream f(bcPath); if (!f) throw std::runtime_error("Couldn't open " + bcPath);
+    std::stringstream ss; ss << f.rdbuf(); const std::string s = ss.str();
+    const auto regs = MiniJSON(s).regions();
+    std::vector<int32_t> kind, cmask; std::vector<double> val, lo, hi;
+    for (const auto &r : regs) {
+        kind.push_back(r.kind); cmask.push_back(r.cmask);
+        for (int d = 0; d < 3; ++d) {
+            val.push_back(r.value[d]);
+            const bool act = d < N;
+            const double a = act ? domMin[d] : 0.0, b = act ? domMax[d] : 0.0;
+            lo.push_back(r.relative && act ? a + r.lo[d] * (b - a) : r.lo[d]);
+            hi.push_back(r.relative && act ? a + r.hi[d] * (b - a) : r.hi[d]);
+        }
+    }
+    check(vf_sim_apply_bc_regions(h, (int)regs.size(), kind.data(), cmask.data(), val.data(), lo.data(), hi.data()));
+}
+} // namespace detail
+
 template<typename Real_, size_t... Degrees> class MultigridSolver;
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -195,21 +217,9 @@ public:
     void setFabricationMaskHeightByLayer(size_t l) { check(vf_sim_set_mask_layer(m_h, (int64_t)l)); }
 
     void applyDisplacementsAndLoadsFromFile(const std::string &bcPath) {
-        std::ifstream f(bcPath); if (!f) throw std::runtime_error("Couldn't open " + bcPath);
-        std::stringstream ss; ss << f.rdbuf(); const std::string s = ss.str();
-        const auto regs = detail::MiniJSON(s).regions();
-        std::vector<int32_t> kind, cmask; std::vector<double> val, lo, hi;
-        for (const auto &r : regs) {
-            kind.push_back(r.kind); cmask.push_back(r.cmask);
-            for (int d = 0; d < 3; ++d) {
-                val.push_back(r.value[d]);
-                const bool act = d < (int)N;
-                const double a = act ? m_domain.minCorner[d] : 0.0, b = act ? m_domain.maxCorner[d] : 0.0;
-                lo.push_back(r.relative && act ? a + r.lo[d] * (b - a) : r.lo[d]);
-                hi.push_back(r.relative && act ? a + r.hi[d] * (b - a) : r.hi[d]);
-            }
-        }
-        check(vf_sim_apply_bc_regions(m_h, (int)regs.size(), kind.data(), cmask.data(), val.data(), lo.data(), hi.data()));
+        double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (size_t d = 0; d < N; ++d) { lo[d] = m_domain.minCorner[d]; hi[d] = m_domain.maxCorner[d]; }
+        detail::apply_bc_file(m_h, (int)N, lo, hi, bcPath);
     }
     void addDirichletCondition(const VNd &u, const VNd &minCorner, const VNd &maxCorner, const std::string &componentMask = "xyz") {
         double uu[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; int cm = 0;
@@ -741,6 +751,119 @@ public:
     VXd getOptimalVar() const { VXd x(m_n); check(vf_mma_get_optimal_var(m_h, x.data())); return x; }
 private:
     int m_n, m_m; F m_f; DF m_df; vf_mma *m_h = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Degree-2 elements: TensorProductSimulator<double, 2, 2[, 2]> on the reference's generic element path (TPSStencils.hh:163-185),
+// vf_q2_* of the C ABI.  Node grid (2 ne + 1)^N; no multigrid (the reference has no degree-2 instantiation of it either).
+// ---------------------------------------------------------------------------------------------------------------------
+template<size_t N_>
+class TensorProductSimulatorQ2 {
+public:
+    static constexpr size_t N = N_;
+    static_assert(N == 2 || N == 3, "2D and 3D");
+    using VNd = std::array<double, N>; using EigenNDIndex = std::array<size_t, N>;
+    using VField = voxelfem_b200::VField; using VXd = voxelfem_b200::VXd;
+    struct BBoxN { VNd minCorner, maxCorner; };
+    TensorProductSimulatorQ2(const BBoxN &domain, const EigenNDIndex &elementsPerDimension) : m_ne(elementsPerDimension) {
+        int64_t ne[3] = {1, 1, 1}; double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+        for (size_t d = 0; d < N; ++d) { ne[d] = (int64_t)m_ne[d]; lo[d] = domain.minCorner[d]; hi[d] = domain.maxCorner[d]; }
+        check(vf_q2_create((int)N, ne, lo, hi, &m_h));
+    }
+    ~TensorProductSimulatorQ2() { if (m_h) vf_q2_destroy(m_h); }
+    TensorProductSimulatorQ2(const TensorProductSimulatorQ2 &) = delete;
+    TensorProductSimulatorQ2 &operator=(const TensorProductSimulatorQ2 &) = delete;
+    size_t numNodes() const { return (size_t)vf_q2_num_nodes(m_h); }
+    size_t numElements() const { return (size_t)vf_q2_num_elements(m_h); }
+    EigenNDIndex NbNodesPerDimension() const { EigenNDIndex r = m_ne; for (auto &v : r) v = 2 * v + 1; return r; }
+    void setIsotropicETensor(double E, double nu) { check(vf_q2_set_isotropic(m_h, E, nu)); }
+    void setInterpolation(InterpolationLaw law, double E_0, double E_min, double gamma, double q) { check(vf_q2_set_interpolation(m_h, (int)law, E_0, E_min, gamma, q)); }
+    void setDensities(const VXd &rho) { if (rho.size() != numElements()) throw std::runtime_error("Incorrect rho size"); check(vf_q2_set_densities(m_h, rho.data())); }
+    std::vector<double> fullDensityElementStiffnessMatrix() const { size_t k = N; for (size_t d = 0; d < N; ++d) k *= 3; std::vector<double> K(k * k); check(vf_q2_get_K0(m_h, K.data())); return K; }
+    template<bool ZeroInit = true, bool Negate = false>
+    void applyK(const VField &u, VField &result) const { if (ZeroInit) result.setZero(numNodes(), N); check(vf_q2_apply_K(m_h, u.data(), result.data(), ZeroInit, Negate)); }
+    VField applyK(const VField &u) const { VField r; applyK<true, false>(u, r); return r; }
+    VXd elementEnergies(const VField &u) const { VXd e(numElements()); check(vf_q2_element_energies(m_h, u.data(), e.data())); return e; }
+    // Jacobi-preconditioned CG with the flagged components (component-major, numNodes * N) clamped to zero; returns the iteration count
+    int solve(VField &x, const VField &b, const std::vector<uint8_t> &fixed, int maxIter, double tol, double *relResidual = nullptr) const {
+        int it = 0; check(vf_q2_pcg(m_h, x.data(), b.data(), fixed.data(), maxIter, tol, &it, relResidual)); return it;
+    }
+    vf_q2 *handle() const { return m_h; }
+private:
+    EigenNDIndex m_ne; vf_q2 *m_h = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Compliance topology optimization on a 3D grid cut into slabs along axis 0 (BASELINE.json configs[3]): TopologyOptimizationProblem +
+// MultigridComplianceObjective + TotalVolumeConstraint + OCOptimizer over vf_group_top_* (no reference equivalent: the reference is
+// single-address-space).  Local group: all slabs live in this process on the current device (one per entry of `slabs`); NCCL rank:
+// one slab per process, the 128-byte id of vf_nccl_unique_id() broadcast by the caller.  Design variables and gradients cross this
+// interface as arrays over the WHOLE grid.
+// ---------------------------------------------------------------------------------------------------------------------
+class SlabTopologyOptimizationProblem {
+public:
+    using VXd = voxelfem_b200::VXd;
+    struct Filter { int kind; int radius; int type; double beta; };      // kind 0: SmoothingFilter(radius, type), 1: ProjectionFilter(beta)
+    struct Setup {
+        std::array<double, 3> domainMin{{0, 0, 0}}, domainMax{{1, 1, 1}}; std::array<int64_t, 3> elements{{2, 2, 2}};
+        std::string bcPath; double young = 1.0, poisson = 0.3, E_0 = 1.0, E_min = 1e-4, gamma = 3.0;
+        int numCoarseningLevels = 1, firstReplicatedLevel = 1;
+        std::vector<Filter> filters; double volumeFraction = 0.3;
+    };
+    // local group over the element-layer ranges `slabs` (ordered, contiguous, multiples of 2^firstReplicatedLevel)
+    SlabTopologyOptimizationProblem(const Setup &s, const std::vector<std::pair<int64_t, int64_t>> &slabs) : m_ne(s.elements) {
+        for (const auto &r : slabs) addPart(s, r.first, r.second, m_sims.empty() ? nullptr : m_sims[0]);
+        check(vf_group_create_local((int)m_mgs.size(), m_mgs.data(), &m_grp));
+        createProblem(s);
+    }
+    // one rank of an NCCL group
+    SlabTopologyOptimizationProblem(const Setup &s, int64_t slabBegin, int64_t slabEnd, int rank, int world, const void *uniqueId128) : m_ne(s.elements) {
+        addPart(s, slabBegin, slabEnd, nullptr);
+        check(vf_group_create_nccl(m_mgs[0], rank, world, uniqueId128, &m_grp));
+        createProblem(s);
+    }
+    ~SlabTopologyOptimizationProblem() {
+        if (m_top) vf_group_top_destroy(m_top);
+        if (m_grp) vf_group_destroy(m_grp);
+        for (size_t i = m_mgs.size(); i-- > 0;) vf_mg_destroy(m_mgs[i]);
+        for (size_t i = m_sims.size(); i-- > 0;) vf_sim_destroy(m_sims[i]);      // the first part owns the stream the others share
+    }
+    SlabTopologyOptimizationProblem(const SlabTopologyOptimizationProblem &) = delete;
+    SlabTopologyOptimizationProblem &operator=(const SlabTopologyOptimizationProblem &) = delete;
+    size_t numVars() const { return (size_t)(m_ne[0] * m_ne[1] * m_ne[2]); }
+    void setSolver(int cgIter, double tol, int mgIterations, int mgSmoothingIterations, bool fullMultigrid, bool zeroInit) {
+        check(vf_group_top_set_solver(m_top, cgIter, tol, mgIterations, mgSmoothingIterations, fullMultigrid, zeroInit));
+    }
+    void setVars(const VXd &x) { if (x.size() != numVars()) throw std::runtime_error("Incorrect number of variables"); check(vf_group_top_set_vars(m_top, x.data())); }
+    VXd getVars() const { VXd x(numVars()); check(vf_group_top_get_vars(m_top, 0, x.data())); return x; }
+    VXd getDensities() const { VXd x(numVars()); check(vf_group_top_get_vars(m_top, 1, x.data())); return x; }
+    double evaluateObjective() const { double v = 0; check(vf_group_top_compliance(m_top, &v)); return v; }
+    double evaluateConstraint() const { double v = 0; check(vf_group_top_constraint(m_top, &v)); return v; }
+    VXd evaluateObjectiveGradient() const { VXd g(numVars()); check(vf_group_top_objective_gradient(m_top, g.data())); return g; }
+    VXd evaluateConstraintsJacobian() const { VXd g(numVars()); check(vf_group_top_constraint_jacobian(m_top, g.data())); return g; }
+    int ocStep(double m = 0.2, double p = 0.5, double ctol = 1e-6) { int n = 0; check(vf_group_top_oc_step(m_top, m, p, ctol, &n)); return n; }   // OCOptimizer::step; returns the constraint evaluations
+    int lastPCGIterations() const { return vf_group_top_last_pcg_iterations(m_top); }
+    int64_t filterHaloLayers() const { return vf_group_top_halo_layers(m_top); }
+private:
+    void addPart(const Setup &s, int64_t b, int64_t e, vf_sim *shareStreamWith) {
+        vf_sim *sim = nullptr;
+        check(vf_sim_create_slab(3, s.elements.data(), s.domainMin.data(), s.domainMax.data(), b, e, shareStreamWith, &sim));
+        m_sims.push_back(sim);
+        check(vf_sim_set_isotropic(sim, s.young, s.poisson));
+        check(vf_sim_set_interpolation(sim, (int)InterpolationLaw::SIMP, s.E_0, s.E_min, s.gamma, 3.0));
+        if (!s.bcPath.empty()) detail::apply_bc_file(sim, 3, s.domainMin.data(), s.domainMax.data(), s.bcPath);
+        check(vf_sim_set_uniform_density(sim, 1.0));
+        vf_mg *mg = nullptr;
+        check(vf_mg_create_slab(sim, s.numCoarseningLevels, s.firstReplicatedLevel, &mg));
+        m_mgs.push_back(mg);
+    }
+    void createProblem(const Setup &s) {
+        std::vector<double> spec;
+        for (const Filter &f : s.filters) { spec.push_back(f.kind); spec.push_back(f.radius); spec.push_back(f.type); spec.push_back(f.beta); }
+        if (spec.empty()) spec.push_back(0.0);
+        check(vf_group_top_create(m_grp, (int)s.filters.size(), spec.data(), s.volumeFraction, &m_top));
+    }
+    std::array<int64_t, 3> m_ne; std::vector<vf_sim *> m_sims; std::vector<vf_mg *> m_mgs; vf_group *m_grp = nullptr; vf_gtop *m_top = nullptr;
 };
 
 } // namespace voxelfem_b200

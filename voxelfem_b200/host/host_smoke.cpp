@@ -37,6 +37,7 @@ static void single_solve(const char *tag, const typename TPS::BBoxN &dom, const 
 }
 
 int main(int argc, char **argv) {
+    std::setvbuf(stdout, nullptr, _IOLBF, 0);      // line-buffered also into a pipe: a crash must not swallow what was printed
     const std::string data = argc > 1 ? argv[1] : "voxelfem_b200/data";
     try {
         using TPS2 = TensorProductSimulator<double, 1, 1>;
@@ -72,6 +73,40 @@ int main(int argc, char **argv) {
             for (int i = 0; i < 30; ++i) opt.step();
             double m = 0; for (double v : opt.getOptimalVar()) m += v;
             std::printf("mma_mean %.9e\n", m / n);
+        }
+        {   // the same problem cut into two slabs of a local group (vf_group_top_*): 2 OC iterations side by side with the undivided values above
+            SlabTopologyOptimizationProblem::Setup st;
+            st.domainMax = {{2, 1, 1}}; st.elements = {{16, 8, 8}}; st.bcPath = data + "/bcs/3D/cantilever_flexion_E.bc";
+            st.young = 1.0; st.poisson = 0.3; st.numCoarseningLevels = 2; st.firstReplicatedLevel = 1;
+            st.filters = {{0, 2, 1, 0.0}, {1, 0, 0, 1.0}}; st.volumeFraction = 0.3;
+            SlabTopologyOptimizationProblem top(st, {{0, 8}, {8, 16}});
+            top.setSolver(100, 1e-9, 1, 2, true, false);
+            top.setVars(VXd(top.numVars(), ProjectionFilter<double>(1.0).invert(0.3)));
+            for (int it = 0; it < 3; ++it) {
+                std::printf("slab_compliance_%d %.15e\nslab_constraint_%d %.6e\n", it, top.evaluateObjective(), it, top.evaluateConstraint());
+                top.ocStep();
+            }
+            double s = 0, g = 0; for (double v : top.getVars()) s += v; for (double v : top.evaluateObjectiveGradient()) g += v;
+            std::printf("slab_sum_vars %.12e\nslab_sum_gradient %.12e\nslab_halo_layers %lld\n", s, g, (long long)top.filterHaloLayers());
+        }
+        {   // degree-2 elements (vf_q2_*): element matrix invariants, the operator on a linear field, a clamped solve
+            using Q2 = TensorProductSimulatorQ2<3>;
+            Q2 q2(Q2::BBoxN{{0, 0, 0}, {1.5, 1.0, 1.0}}, Q2::EigenNDIndex{3, 2, 2});
+            q2.setIsotropicETensor(1.0, 0.3);
+            q2.setInterpolation(InterpolationLaw::SIMP, 1.0, 1e-3, 3.0, 3.0);
+            const auto K = q2.fullDensityElementStiffnessMatrix();
+            double asym = 0, rowsum = 0, tr = 0;
+            for (size_t i = 0; i < 81; ++i) { tr += K[i * 81 + i]; for (size_t j = 0; j < 81; ++j) asym = std::max(asym, std::abs(K[i * 81 + j] - K[j * 81 + i])); }
+            for (size_t i = 0; i < 81; ++i) { double r = 0; for (size_t j = 0; j < 81; j += 3) r += K[i * 81 + j]; rowsum = std::max(rowsum, std::abs(r)); }   // K0 * (translation along x) = 0
+            const auto nn = q2.NbNodesPerDimension();
+            VField u(q2.numNodes(), 3), f;
+            for (size_t a = 0, n = 0; a < nn[0]; ++a) for (size_t b = 0; b < nn[1]; ++b) for (size_t c = 0; c < nn[2]; ++c, ++n) {
+                const double x = 0.25 * a, y = 0.25 * b, z = 0.25 * c;              // node spacing h / 2 = 0.25
+                u(n, 0) = 0.01 * x; u(n, 1) = -0.003 * y; u(n, 2) = -0.003 * z;     // uniaxial strain state of a nu = 0.3 material
+            }
+            q2.applyK<true, false>(u, f);
+            double energy = 0; for (double e : q2.elementEnergies(u)) energy += e;
+            std::printf("q2_nodes %zu\nq2_K0_asymmetry %.3e\nq2_K0_translation %.3e\nq2_K0_trace %.12e\nq2_linear_field_energy %.12e\nq2_uKu %.12e\n", q2.numNodes(), asym, rowsum, tr, energy, u.dot(f));
         }
         try {
             auto odd = std::make_shared<TPS2>(TPS2::BBoxN{{0, 0}, {1, 1}}, TPS2::EigenNDIndex{6, 5});

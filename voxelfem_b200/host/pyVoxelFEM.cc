@@ -6,7 +6,7 @@
 // LayerByLayerEvaluator, OCOptimizer, the filters, FilterChain, TotalVolumeConstraint, InterpolationLaw, NumberType, getClassName.
 // Array conventions as there: nodal fields are (numNodes, N) float64 numpy arrays copied in and out, densities flat over
 // (ex, ey[, ez]) row-major.  Eigen is not available: the casters below convert numpy arrays to the header's VField / VXd.
-// Methods of the reference that lie outside the MG-PCG / topopt hot path raise NotImplementedError by name.
+// The export / post-processing methods next to the hot path are bound from voxelfem_b200/compat/tps_extras.py (shared with the ctypes flavour).
 #include <pybind11/functional.h>
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
@@ -35,10 +35,6 @@ template<size_t N> static std::array<double, N> to_vnd(const std::vector<double>
 template<size_t N> static std::array<size_t, N> to_idx(const std::vector<size_t> &v) { if (v.size() != N) throw std::runtime_error("expected " + std::to_string(N) + " indices"); std::array<size_t, N> r; std::copy(v.begin(), v.end(), r.begin()); return r; }
 template<class A> static py::array_t<double> np_of(const A &v) { py::array_t<double> a((py::ssize_t)v.size()); std::copy(v.begin(), v.end(), a.mutable_data()); return a; }
 template<class A> static py::array_t<int64_t> npi_of(const A &v) { py::array_t<int64_t> a((py::ssize_t)v.size()); std::copy(v.begin(), v.end(), a.mutable_data()); return a; }
-[[noreturn]] static void not_on_path(const std::string &what) {
-    PyErr_SetString(PyExc_NotImplementedError, ("pyVoxelFEM." + what + " is outside the B200 hot path (SURVEY.md section 8: out of scope)").c_str());
-    throw py::error_already_set();
-}
 
 // MeshFEM's ElasticityTensor as far as the drivers use it (ElasticityTensor.hh:100-131): setIsotropic(E, nu)
 struct PyETensor { bool isotropic = true; double E = 1, nu = 0; std::vector<double> D; void setIsotropic(double E_, double nu_) { isotropic = true; E = E_; nu = nu_; } };
