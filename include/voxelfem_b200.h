@@ -356,6 +356,20 @@ int vf_lbl_get_layer_gradient(vf_lbl *l, double *g);              /* complianceG
 int vf_lbl_objective(vf_lbl *l, double *out);                     /* objective (:299) */
 int vf_lbl_gradient(vf_lbl *l, double *g);                        /* gradient (:300) */
 
+/* ---- Layer-by-layer evaluator on a slab group (LayerByLayer.hh:25-309 with the grid partitioned along axis 0; the build direction is
+ * axis 1, so every slab holds a piece of every layer).  Every rank calls the functions with the same arguments; the gradient
+ * crosses the boundary as an array over the WHOLE element grid. */
+typedef struct vf_glbl vf_glbl;
+int vf_group_lbl_create(vf_group *g, vf_glbl **out);
+int vf_group_lbl_destroy(vf_glbl *l);
+int vf_group_lbl_select_init_method(vf_glbl *l, const char *method);            /* selectInitMethod (:214-220) */
+int vf_group_lbl_run(vf_glbl *l, int zero_init, int64_t layer_increment, int max_iter, double tol, int mg_iterations,
+                     int mg_smoothing_iterations, int fmg, vf_lbl_callback callback, void *user);   /* run (:223-296) */
+int vf_group_lbl_objective(vf_glbl *l, double *out);                            /* objective (:299) */
+int vf_group_lbl_gradient(vf_glbl *l, double *g_global);                        /* gradient (:300) */
+int vf_group_lbl_num_layer_iterations(vf_glbl *l, int *iters);                  /* PCG iterations per simulated layer; returns their number */
+
+
 /* ---- Method of Moving Asymptotes (pyOptimizer.MMA, python_bindings/Optimizer.cc:11-23) ----------------------
  * MMA(numVars, numConstr, xmin, xmax, f, df_dx) (MethodOfMovingAsymptotes.hh:34-52).  f writes the m + 1 values
  * (objective, constraints f_i(x) <= 0) and df_dx the (m + 1) x n row-major gradients; both return 0 on success.

@@ -12,7 +12,7 @@ import torch.distributed as dist
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
-from oracle import OracleMG, OracleSim  # noqa: E402
+from oracle import OracleLBL, OracleMG, OracleSim  # noqa: E402
 from voxelfem_b200 import capi  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -50,6 +50,37 @@ for ne, levels, first_rep in [((64, 32, 32), 3, 2), ((32 * world, 32, 32), 3, 3)
           % (rank, world, ne, it, it_ref, err, float((fw * w).sum()), float((fw * wref).sum()), "OK" if good else "FAIL"), flush=True)
     ok = ok and good
     grp.close()
+# layer-by-layer evaluator over NCCL (vf_group_lbl_*) against the oracle's undivided evaluator
+ne = np.array([16 * world, 8, 8]); dom = ne.astype(float) / ne[0]
+rho = np.random.default_rng(3).uniform(0.3, 1.0, int(np.prod(ne)))
+
+
+def prep(s, r):
+    s.set_isotropic(1.0, 0.3); s.set_interp(1, 1.0, 1e-4, 3.0, 3.0)
+    s.add_dirichlet([0, 0, 0], [-1, -1e-9, -1], [100, 1e-9, 100], 7)
+    s.set_gravity(np.array([0.0, -1.0, 0.0])); s.set_densities(r)
+
+
+so = OracleSim(ne, np.zeros(3), dom); prep(so, rho)
+oe = OracleLBL(OracleMG(so, 2)); oe.select_init_method("N=3")
+oi, oc = oe.run(True, 1, 200, 1e-11, 1, 1, False)
+a, b = capi.slab_ranges(int(ne[0]), world, 2)[rank]
+s = capi.SlabSim(ne, np.zeros(3), dom, a, b); prep(s, s.window_of_elements(rho))
+mg = capi.SlabMG(s, 2, 1)
+uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    uid.copy_(torch.frombuffer(bytearray(capi.SlabGroup.nccl_unique_id()), dtype=torch.uint8))
+dist.broadcast(uid, 0)
+grp = capi.SlabGroup([mg], rank=rank, world=world, unique_id=uid.cpu().numpy().tobytes())
+ge = capi.SlabLBL(grp, ne); ge.select_init_method("N=3")
+gi, gc = ge.run(True, 1, 200, 1e-11, 1, 1, False)
+eobj = abs(ge.objective() - oe.objective()) / abs(oe.objective())
+egrad = np.abs(ge.gradient() - oe.gradient()).max() / np.abs(oe.gradient()).max()
+good = len(gi) == len(oi) and np.abs(gi.astype(int) - oi.astype(int)).max() <= 1 and np.abs(gc - oc).max() < 1e-8 * np.abs(oc).max() and eobj < 1e-8 and egrad < 1e-8
+print("rank %d/%d layer-by-layer grid %s: %d layers, PCG iterations nccl=%d oracle=%d, objective rel err %.2e, gradient rel err %.2e -> %s"
+      % (rank, world, tuple(int(v) for v in ne), len(gi), int(gi.sum()), int(oi.sum()), eobj, egrad, "OK" if good else "FAIL"), flush=True)
+ok = ok and good
+ge.close(); grp.close()
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 dist.destroy_process_group()

@@ -1,5 +1,5 @@
 """Multi-GPU parity under pytest: the NCCL slab-partitioned solve (one process per GPU, ncclSend/Recv ghost planes, ncclAllReduce'd
-PCG scalars) against the oracle's undivided solve.  Needs two visible devices; on a single-GPU box the same control flow is covered
+PCG scalars) against the oracle's undivided solve, and the slab-partitioned layer-by-layer evaluator against the oracle's.  Needs two visible devices; on a single-GPU box the same control flow is covered
 by the local groups of tests/test_gpu_slabs.py and tests/test_gpu_baseline_configs.py::test_slab_partitioned_solve_matches_oracle."""
 import os
 import subprocess
@@ -21,4 +21,4 @@ def test_two_rank_nccl_solve_matches_oracle():
     env = dict(os.environ); env["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 2) // 2))
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     print(r.stdout[-4000:])
-    assert r.returncode == 0 and r.stdout.count("-> OK") == 4
+    assert r.returncode == 0 and r.stdout.count("-> OK") == 6        # 2 solves + 1 layer-by-layer run, on 2 ranks

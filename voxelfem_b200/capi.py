@@ -221,6 +221,13 @@ def lib():
         "vf_q2_apply_K": (ci, [vp, _dp, _dp, ci, ci]),
         "vf_q2_element_energies": (ci, [vp, _dp, _dp]),
         "vf_q2_pcg": (ci, [vp, _dp, _dp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), ci, cd, C.POINTER(ci), C.POINTER(cd)]),
+        "vf_group_lbl_create": (ci, [vp, pvp]),
+        "vf_group_lbl_destroy": (ci, [vp]),
+        "vf_group_lbl_select_init_method": (ci, [vp, C.c_char_p]),
+        "vf_group_lbl_run": (ci, [vp, ci, i64, ci, cd, ci, ci, ci, LBL_CALLBACK, vp]),
+        "vf_group_lbl_objective": (ci, [vp, C.POINTER(cd)]),
+        "vf_group_lbl_gradient": (ci, [vp, _dp]),
+        "vf_group_lbl_num_layer_iterations": (ci, [vp, C.POINTER(ci)]),
         "vf_lbl_create": (ci, [vp, pvp]),
         "vf_lbl_destroy": (ci, [vp]),
         "vf_lbl_select_init_method": (ci, [vp, C.c_char_p]),
@@ -958,6 +965,36 @@ class LBL(_Owned):
 
     def gradient(self):
         g = np.zeros(self.mg.sim.num_elements); _check(self.L.vf_lbl_gradient(self.h, g)); return g
+
+
+class SlabLBL(_Owned):
+    """LayerByLayerEvaluator (LayerByLayer.hh:25-309) on a slab group: vf_group_lbl_* (every slab holds a piece of every layer)."""
+
+    def __init__(self, group, ne_global):
+        self.L = lib(); self.group = group; self.ne_global = int(np.prod(ne_global))
+        h = C.c_void_p()
+        _check(self.L.vf_group_lbl_create(group.h, C.byref(h)))
+        self._own(h, self.L.vf_group_lbl_destroy, group)
+
+    def select_init_method(self, m): _check(self.L.vf_group_lbl_select_init_method(self.h, m.encode()))
+
+    def run(self, zero_init=True, layer_increment=1, max_iter=50, tol=1e-5, mg_iterations=1, mg_smoothing=1, fmg=False, callback=None):
+        """-> (PCG iterations per layer, compliance per layer); callback(layer, compliance, pcg_iterations)."""
+        its, cs = [], []
+
+        def _cb(layer, compliance, iters, _):
+            its.append(iters); cs.append(compliance)
+            if callback is not None: callback(layer, compliance, iters)
+        cb, failed = _guarded(LBL_CALLBACK, _cb)
+        _check(self.L.vf_group_lbl_run(self.h, int(zero_init), layer_increment, max_iter, tol, mg_iterations, mg_smoothing, int(fmg), cb, None))
+        _reraise(failed)
+        return np.array(its, dtype=np.int32), np.array(cs)
+
+    def objective(self):
+        v = C.c_double(0); _check(self.L.vf_group_lbl_objective(self.h, C.byref(v))); return v.value
+
+    def gradient(self):
+        g = np.zeros(self.ne_global); _check(self.L.vf_group_lbl_gradient(self.h, g)); return g
 
 
 class MMA:

@@ -2655,3 +2655,176 @@ int vf_lbl_gradient(vf_lbl *l, double *g) { // (:300)
     for (size_t i = 0; i < h.size(); ++i) g[i] = h[i] / double(l->layersAccumulated); VF_CATCH
 }
 }
+
+// ---------------------------------------------------------------------------
+// Layer-by-layer evaluator on a slab group (LayerByLayer.hh:25-309 with the grid partitioned along axis 0).  The build direction is
+// axis 1, so every slab holds a piece of every layer: the fabrication mask, the self-weight load update, the initial-guess history
+// and the compliance gradient are per-part operations on the part's window; what couples the parts is the partitioned MG-PCG
+// (vf_group_pcg), the ghost planes of the history fields before the stiffness applies of the subspace guess, and the scalar sums
+// (owned node planes only, summed over parts / all-reduced over ranks).  The coarse hierarchy is rebuilt in full for every layer
+// (the banded update of the undivided solver is not partitioned).
+// ---------------------------------------------------------------------------
+struct GLblPart {
+    vf_mg *mg = nullptr; vf_sim *sim = nullptr;
+    std::vector<std::unique_ptr<DevBuf<double>>> hist;
+    DevBuf<double> f, u, uFull, w, totalGrad, scalar, scratch;
+    size_t len() const { return (size_t)sim->g.numNodes * sim->N; }
+};
+struct vf_glbl {
+    vf_group *grp = nullptr; std::vector<std::unique_ptr<GLblPart>> parts;
+    int method = 2; size_t maxHist = 3;
+    bool uValid = false, uFullValid = false;
+    double totalCompliance = 0; long long layersAccumulated = 0; std::vector<int> layerIters;
+    DevBuf<double> gather;
+    vf_mg &lead() { return *grp->parts[0]; }
+    cudaStream_t stream() { return lead().ctx.stream; }
+    // sum over all parts / ranks of one masked dot product per part (owned node planes only)
+    template<class SelA, class SelB> double dot(SelA a, SelB b) {
+        for (auto &pp : parts) launch_masked_dot(pp->mg->ctx, pp->sim->g, a(*pp), b(*pp), pp->scalar.p, pp->scratch.p);
+        if (grp->comm) { NcclApi &A = NcclApi::get(); double *p = parts[0]->scalar.p; A.check(A.AllReduce(p, p, 1, kNcclDouble, kNcclSum, grp->comm, stream()), "ncclAllReduce"); }
+        double tot = 0;
+        for (auto &pp : parts) { double v = 0; d2h(&v, pp->scalar.p, 1, stream()); tot += v; if (grp->comm) break; }
+        return tot;
+    }
+    void addToHistory() {   // m_addToHistory (:72-84)
+        if (maxHist == 0) return;
+        for (auto &pp : parts) {
+            GLblPart &P = *pp; std::unique_ptr<DevBuf<double>> slot;
+            if (P.hist.size() == maxHist) { slot = std::move(P.hist.back()); P.hist.pop_back(); }
+            else { slot = std::make_unique<DevBuf<double>>(); slot->alloc(P.len(), true); }
+            std::swap(slot->p, P.u.p); std::swap(slot->n, P.u.n);
+            P.hist.insert(P.hist.begin(), std::move(slot));
+        }
+        uValid = false;
+    }
+    void constructGuess() {
+        const size_t s = parts[0]->hist.size();
+        for (auto &pp : parts) if (pp->u.n != pp->len()) pp->u.alloc(pp->len(), true);
+        if (method == 0 || s == 0) { for (auto &pp : parts) VF_CUDA(cudaMemsetAsync(pp->u.p, 0, sizeof(double) * pp->len(), stream())); uValid = true; return; }
+        if (method == 1) {   // InitGenFD (:95-100)
+            if (s > 2) throw std::runtime_error("Unimplemented");
+            for (auto &pp : parts) {
+                GLblPart &P = *pp;
+                VF_CUDA(cudaMemcpyAsync(P.u.p, P.hist[0]->p, sizeof(double) * P.len(), cudaMemcpyDeviceToDevice, stream()));
+                if (s == 2) { launch_scale(P.mg->ctx, (long long)P.len(), 2.0, P.u.p); launch_axpy(P.mg->ctx, (long long)P.len(), -1.0, P.hist[1]->p, P.u.p); }
+            }
+            uValid = true; return;
+        }
+        // InitGenSubspace (:110-147): A c = b with A = U^T K U, b = U^T f over the whole grid
+        const int k = (int)s;
+        std::vector<double> A((size_t)k * k, 0.0), b(k, 0.0);
+        for (auto &pp : parts) if (pp->w.n != pp->len()) pp->w.alloc(pp->len(), true);
+        for (int j = 0; j < k; ++j) {
+            b[j] = dot([&](GLblPart &P) { return P.hist[j]->p; }, [](GLblPart &P) { return P.f.p; });
+            // the stiffness apply reads the ghost planes of the history field: the solve left them current for the latest field only
+            std::vector<double *> hp; for (auto &pp : parts) hp.push_back(pp->hist[j]->p);
+            grp_exchange(lead(), 0, [&](vf_mg &m) { for (size_t q = 0; q < parts.size(); ++q) if (parts[q]->mg == &m) return hp[q]; return (double *)nullptr; });
+            for (auto &pp : parts) part_apply_K(*pp->mg, 0, pp->hist[j]->p, nullptr, pp->w.p, APPLY_SET, false);
+            for (int i = j; i < k; ++i) A[i * k + j] = A[j * k + i] = dot([&](GLblPart &P) { return P.hist[i]->p; }, [](GLblPart &P) { return P.w.p; });
+        }
+        const std::vector<double> c = vf_lbl::solveSymmetricPinv(A, b, k);
+        for (auto &pp : parts) {
+            GLblPart &P = *pp;
+            VF_CUDA(cudaMemsetAsync(P.u.p, 0, sizeof(double) * P.len(), stream()));
+            for (int i = 0; i < k; ++i) launch_axpy(P.mg->ctx, (long long)P.len(), c[i], P.hist[i]->p, P.u.p);
+            launch_detached_zero(P.mg->ctx, P.sim->g, P.u.p);
+        }
+        uValid = true;
+    }
+};
+
+extern "C" {
+int vf_group_lbl_create(vf_group *g, vf_glbl **out) {
+    VF_TRY auto l = std::make_unique<vf_glbl>(); l->grp = g;
+    if (g->parts[0]->N != 3) throw std::runtime_error("the slab-partitioned layer-by-layer evaluator is 3D");
+    for (vf_mg *m : g->parts) {
+        auto P = std::make_unique<GLblPart>(); P->mg = m; P->sim = m->sim;
+        P->scalar.alloc(1, true); P->scratch.alloc(reduce_scratch_doubles(), true);
+        l->parts.push_back(std::move(P));
+    }
+    *out = l.release(); VF_CATCH
+}
+int vf_group_lbl_destroy(vf_glbl *l) { VF_TRY if (l) { cudaStreamSynchronize(l->stream()); delete l; } VF_CATCH }
+int vf_group_lbl_select_init_method(vf_glbl *l, const char *method) {   // selectInitMethod (:214-220)
+    VF_TRY const std::string m(method);
+    if (m == "zero") { l->method = 0; l->maxHist = 0; }
+    else if (m == "constant") { l->method = 1; l->maxHist = 1; }
+    else if (m == "fd") { l->method = 1; l->maxHist = 2; }
+    else if (m.substr(0, 2) == "N=") { l->method = 2; l->maxHist = (size_t)std::stoi(m.substr(2)); }
+    else throw std::runtime_error("Unrecognized method " + m);
+    for (auto &pp : l->parts) pp->hist.clear(); VF_CATCH
+}
+// LayerByLayerEvaluator::run (:223-296) on the partitioned grid; every rank calls it with the same arguments
+int vf_group_lbl_run(vf_glbl *l, int zeroInit, int64_t layerIncrement, int maxIter, double tol, int mgIt, int mgSmooth, int fmg, vf_lbl_callback cb, void *user) {
+    VF_TRY
+    vf_mg &lead = l->lead(); vf_sim &sim0 = *lead.sim;
+    const int64_t numLayers = sim0.ne[1];
+    if (layerIncrement < 1) throw std::runtime_error("layerIncrement must be positive");
+    cudaStream_t st = l->stream();
+    l->uValid = false;
+    if (!zeroInit && l->uFullValid) {
+        for (auto &pp : l->parts) { GLblPart &P = *pp; if (P.u.n != P.len()) P.u.alloc(P.len(), false); VF_CUDA(cudaMemcpyAsync(P.u.p, P.uFull.p, sizeof(double) * P.len(), cudaMemcpyDeviceToDevice, st)); }
+        l->uValid = true;
+    }
+    l->layersAccumulated = 0; l->totalCompliance = 0; l->layerIters.clear();
+    for (auto &pp : l->parts) {
+        GLblPart &P = *pp;
+        P.hist.clear(); P.totalGrad.alloc(P.sim->g.numElems, true);
+        if (int rc = vf_mg_set_mask_layer(P.mg, numLayers)) return rc;
+        if (P.f.n != P.len()) P.f.alloc(P.len(), true);
+        sim_build_load_dev(*P.sim, P.f.p);
+    }
+    const double g2 = sim0.gravity[0] * sim0.gravity[0] + sim0.gravity[1] * sim0.gravity[1] + sim0.gravity[2] * sim0.gravity[2];
+    for (int64_t layer = numLayers; layer > 0; layer -= std::min(layerIncrement, layer)) {
+        if (layer < numLayers) {
+            if (g2 == 0 || std::abs(g2 - sim0.gravity[1] * sim0.gravity[1]) > 1e-10) throw std::runtime_error("Unexpected gravity vector");
+            for (auto &pp : l->parts) {
+                GLblPart &P = *pp;
+                if (int rc = vf_mg_decrement_mask(P.mg, (int)layerIncrement)) return rc;
+                launch_self_weight_load(P.mg->ctx, P.sim->g, P.sim->rho.p, P.sim->gravity, P.sim->elemVolume(), P.f.p, (int)layer, (int)(layer + layerIncrement), -1.0);
+            }
+        }
+        if (layer < numLayers || !l->uValid) l->constructGuess();
+        std::vector<double *> xs; std::vector<const double *> bs;
+        for (auto &pp : l->parts) { xs.push_back(pp->u.p); bs.push_back(pp->f.p); }
+        try { mg_pcg(lead, xs.data(), bs.data(), maxIter, tol, mgIt, mgSmooth, fmg != 0, /* dirichletAlreadySatisfied */ true, nullptr, nullptr); }
+        catch (const std::exception &e) { throw std::runtime_error(std::string("PCG exception ") + e.what() + " at l = " + std::to_string(layer)); }
+        l->layerIters.push_back(lead.lastIters);
+        const double compliance = l->dot([](GLblPart &P) { return P.f.p; }, [](GLblPart &P) { return P.u.p; });
+        if (cb) cb(layer, compliance, lead.lastIters, user);
+        l->totalCompliance += compliance;
+        for (auto &pp : l->parts) {
+            GLblPart &P = *pp; vf_sim &sm = *P.sim;
+            launch_compliance_gradient(P.mg->ctx, sm.g, sm.K0p, P.u.p, sm.rho.p, P.totalGrad.p, sm.law, sm.E0, sm.Emin, sm.gamma, sm.q, sm.gravity, sm.elemVolume(), true);
+            if (layer == numLayers) { if (P.uFull.n != P.len()) P.uFull.alloc(P.len(), false); VF_CUDA(cudaMemcpyAsync(P.uFull.p, P.u.p, sizeof(double) * P.len(), cudaMemcpyDeviceToDevice, st)); }
+        }
+        if (layer == numLayers) l->uFullValid = true;
+        ++l->layersAccumulated;
+        if (layer >= layerIncrement) l->addToHistory();
+    }
+    p2p_check(*l->grp, st);
+    VF_CUDA(cudaStreamSynchronize(st));
+    VF_CATCH
+}
+int vf_group_lbl_objective(vf_glbl *l, double *out) { *out = 0.5 * l->totalCompliance / double(l->layersAccumulated); return 0; }   // (:299)
+// gradient (:300) over the WHOLE grid (host array, every rank receives all of it)
+int vf_group_lbl_gradient(vf_glbl *l, double *g) {
+    VF_TRY
+    vf_sim &s0 = *l->lead().sim; cudaStream_t st = l->stream();
+    const long long layer = (long long)s0.ne[1] * s0.ne[2], neGlobal = (long long)s0.gne0 * layer;
+    if (l->gather.n != (size_t)neGlobal) l->gather.alloc(neGlobal, false);
+    VF_CUDA(cudaMemsetAsync(l->gather.p, 0, sizeof(double) * neGlobal, st));
+    for (auto &pp : l->parts) {
+        vf_sim &sm = *pp->sim;
+        VF_CUDA(cudaMemcpyAsync(l->gather.p + sm.slabBegin * layer, pp->totalGrad.p + (sm.slabBegin - sm.xoff) * layer, sizeof(double) * (sm.slabEnd - sm.slabBegin) * layer, cudaMemcpyDeviceToDevice, st));
+    }
+    if (l->grp->comm) { NcclApi &A = NcclApi::get(); A.check(A.AllReduce(l->gather.p, l->gather.p, (size_t)neGlobal, kNcclDouble, kNcclSum, l->grp->comm, st), "ncclAllReduce"); }
+    std::vector<double> h(neGlobal); d2h(h.data(), l->gather.p, (size_t)neGlobal, st);
+    for (long long i = 0; i < neGlobal; ++i) g[i] = h[i] / double(l->layersAccumulated);
+    VF_CATCH
+}
+int vf_group_lbl_num_layer_iterations(vf_glbl *l, int *iters /* one per simulated layer, may be NULL */) {
+    if (iters) std::copy(l->layerIters.begin(), l->layerIters.end(), iters);
+    return (int)l->layerIters.size();
+}
+}
