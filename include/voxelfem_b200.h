@@ -206,7 +206,8 @@ const char *vf_prof_name(int category);
 int vf_prof_get(vf_mg *mg, int category, int64_t *launches, double *total_ms, double *units);
 /* Device time (ms) of one repetition of a single multigrid operation, averaged over `reps` back-to-back
  * repetitions on the level's own fields.  op: 0 smoothing sweep (smoothingMulticoloredGS, :452-458), 1 computeResidual,
- * 2 applyK, 3 restriction, 4 accum_interpolation, 5 coarsest solve, 6 vcycle(level) (:617-658), 7 fullMultigrid(0) (:587-609). */
+ * 2 applyK, 3 restriction, 4 accum_interpolation, 5 coarsest solve, 6 vcycle(level) (:617-658), 7 fullMultigrid(0) (:587-609),
+ * 8 forward smoothing sweep that also leaves computeResidual's result (what vcycle runs on a stored-stencil level, level >= 1). */
 int vf_mg_time_op(vf_mg *mg, int op, int level, int reps, int num_smoothing_steps, double *ms_per_rep);
 
 /* ---- Slab-partitioned solver (multi-GPU) -------------------------------------------------

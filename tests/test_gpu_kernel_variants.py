@@ -1,6 +1,6 @@
 """Every kernel variant the library can select (environment switches read once per process) runs the hierarchy / V-cycle / PCG
 parity tests against the oracle in its own process: the element-form, cp.async neighbour-form and TMA-staged neighbour-form
-level-0 smoothers on short and long rows, the per-colour fallback, and the persistent small-level sweep."""
+level-0 smoothers on short and long rows, the per-colour fallback, the persistent small-level sweep, and the V-cycle with a separate residual kernel (the default takes the residual from the pre-smoothing sweep)."""
 import os
 import subprocess
 import sys
@@ -22,6 +22,8 @@ VARIANTS = {
     "dense_level0_apply": {"VF_L0_DENSE": "1"},
     "one_shot_galerkin_coarsening": {"VF_COARSEN_ONESHOT": "1"},
     "dense_coarse_factorization": {"VF_COARSE_DENSE": "1"},
+    "separate_residual_kernel": {"VF_GS_RESIDUAL": "0"},
+    "tile_coordinates_without_position_table": {"VF_ST_POSTAB": "0"},
 }
 
 

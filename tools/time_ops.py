@@ -21,6 +21,12 @@ for l in range(levels):
         gbs = bytes_per_node * nn / ms / 1e6
         rows.append((l, op, nn, ms, gbs, gbs / peak))
         print("level %d %-9s nodes %9d  %8.4f ms  %8.1f GB/s algorithmic  %5.1f%% of HBM peak" % (l, op, nn, ms, gbs, 100 * gbs / peak))
+    if l > 0:
+        try:
+            ms = mg.time_op("smooth_residual", l, reps=20)
+            print("level %d %-9s nodes %9d  %8.4f ms  (forward sweep that also emits the residual)" % (l, "smooth+r", nn, ms))
+        except RuntimeError as e:
+            print("level %d smooth+r unavailable: %s" % (l, e))
     if l < levels:
         for op in ("restrict", "prolong"):
             print("level %d %-9s %8.4f ms" % (l, op, mg.time_op(op, l, reps=20)))

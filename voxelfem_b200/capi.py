@@ -612,7 +612,7 @@ class MG(_Owned):
     def stream(self): return self.L.vf_mg_stream(self.h)
     def synchronize(self): _check(self.L.vf_mg_synchronize(self.h))
 
-    OPS = {"smooth": 0, "residual": 1, "apply": 2, "restrict": 3, "prolong": 4, "coarse_solve": 5, "vcycle": 6, "fmg": 7}
+    OPS = {"smooth": 0, "residual": 1, "apply": 2, "restrict": 3, "prolong": 4, "coarse_solve": 5, "vcycle": 6, "fmg": 7, "smooth_residual": 8}
 
     def time_op(self, op, level=0, reps=10, nsmooth=1):
         ms = C.c_double()

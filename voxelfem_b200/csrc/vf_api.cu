@@ -447,6 +447,7 @@ struct MGLevel {
     int64_t sb = 0, se = 0, gne0 = 0; bool windowed = false;
     std::vector<uint8_t> nodeMask; DevBuf<uint8_t> dmask;
     DevBuf<double> x, b, r, S;
+    DevBuf<unsigned long long> posTab;   // levels >= 1: position -> node coordinates (GridDesc::posTab)
     int firstMasked = INT_MAX, firstDetached = INT_MAX;
 };
 struct vf_mg {
@@ -967,7 +968,9 @@ void mg_residual(vf_mg &lead, int l, Field u, Field b, Field r) {
 // smoothingMulticoloredGS (:452-458): 2^N colour passes, colours reversed for backward sweeps (:417).  In a slab window the
 // colour of a node is the parity class of its GLOBAL index; after the passes that updated the parity of the ghost planes those
 // planes are received from the neighbours.
-void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward) {
+// res != nullptr (stored-stencil levels of an undivided solver, gs_residual_fusable): the sweep leaves b - K u of its final iterate
+// in *res, Dirichlet components not yet zeroed.
+void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward, const Field *res = nullptr) {
     const int nc = 1 << lead.N;
     if (l > 0) mg_update_stiffness(lead);
     if (l == 0 && lead.N == 3) {
@@ -1002,7 +1005,7 @@ void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward) {
             const int lc = (lead.N == 3) ? (color ^ ((g.xoff & 1) << 2)) : color;   // local parity class of this global colour
             if (l == 0 && mg.N == 3) launch_gs3_color_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), lc, forward);
             else if (l == 0)         launch_gs_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), lc, forward);
-            else                     launch_gs_stencil(mg.ctx, g, mg.lv[l]->S.p, u(mg), b(mg), mg.dmask(l), lc, forward, /* chained */ i > 0 && !lead.grp);
+            else                     launch_gs_stencil(mg.ctx, g, mg.lv[l]->S.p, u(mg), b(mg), mg.dmask(l), lc, forward, /* chained */ i > 0 && !lead.grp, res ? (*res)(mg) : nullptr);
         }
         // The four passes of one x parity only read planes of the other parity besides their own plane, so a ghost plane (one parity)
         // has to be current only when the passes of the OTHER parity start: one exchange per parity group instead of one per pass.
@@ -1070,8 +1073,13 @@ void mg_vcycle(vf_mg &lead, int l, int nsmooth, bool residualSystem) {
     }
     TraceScope ts("V Cycle " + std::to_string(l));             // MultigridSolver.hh:618
     mg_enforce_dirichlet(lead, l, fx(l), residualSystem);
-    for (int i = 0; i < nsmooth; ++i) mg_smooth(lead, l, fx(l), fb(l), true);
-    mg_residual(lead, l, fx(l), fb(l), fr(l));
+    // On a stored-stencil level the last pre-smoothing sweep emits the residual itself (k_stencil_tile<RES>): the stencil, 97 % of the
+    // level's bytes, is streamed twice per visit instead of three times.
+    const bool fusedRes = l > 0 && nsmooth > 0 && !lead.grp && parts_of(lead).size() == 1 && gs_residual_fusable(lead.grid(l));
+    const Field rl = fr(l);
+    for (int i = 0; i < nsmooth; ++i) mg_smooth(lead, l, fx(l), fb(l), true, (fusedRes && i == nsmooth - 1) ? &rl : nullptr);
+    if (fusedRes) launch_zero_dirichlet(lead.ctx, lead.grid(l), lead.dmask(l), lr(lead, l));   // computeResidual's mask (:538)
+    else mg_residual(lead, l, fx(l), fb(l), fr(l));
     mg_restrict(lead, l, fr(l), fb(l + 1));
     for (vf_mg *m : parts_of(lead)) launch_masked_zero(m->ctx, m->grid(l + 1), lx(*m, l + 1), 4 /* VOXELFEM_SIMD_WIDTH margin (:644) */);
     mg_vcycle(lead, l + 1, nsmooth, true);
@@ -1550,6 +1558,12 @@ static vf_mg *mg_create_common(vf_sim *fine, int levels, int firstRep) {
         else {
             coarsen_dirichlet_mask(N, *mg->lv.back(), mg->lv.back()->nodeMask, *L);
             L->dmask.alloc(L->g.numNodes, false); L->dmask.upload(L->nodeMask.data(), L->g.numNodes, fine->stream);
+            static const bool usePosTab = [] { const char *e = std::getenv("VF_ST_POSTAB"); return !(e && e[0] == '0'); }();
+            if (usePosTab && !stencil_level_streams(L->g)) {   // measured: helps the latency-bound levels, costs 2-6 % on the streaming one (profiles/r06f_ab.log)
+                L->posTab.alloc((size_t)L->g.numPos, false);
+                launch_fill_pos_table(fine->stream, L->g, L->posTab.p);
+                L->g.posTab = L->posTab.p;
+            }
             VF_CUDA(cudaStreamSynchronize(fine->stream));
         }
         mg->lv.push_back(std::move(L));
@@ -1876,6 +1890,13 @@ int vf_mg_time_op(vf_mg *mg, int op, int level, int reps, int nsmooth, double *m
             case 5: mg_coarse_solve(*mg, fb(mg->numLevels() - 1), fx(mg->numLevels() - 1)); break;
             case 6: mg_vcycle(*mg, level, nsmooth, true); break;
             case 7: mg_fmg(*mg, 0, nsmooth, true); break;
+            case 8: {   // forward sweep that also emits the residual (stored-stencil levels of an undivided solver)
+                if (!(level > 0 && !mg->grp && gs_residual_fusable(mg->grid(level)))) throw std::runtime_error("smooth_residual: not available on this level");
+                const Field rl = fr(level);
+                mg_smooth(*mg, level, fx(level), fb(level), true, &rl);
+                launch_zero_dirichlet(mg->ctx, mg->grid(level), mg->dmask(level), lr(*mg, level));
+                break;
+            }
             default: throw std::runtime_error("unknown op");
         }
     };

@@ -40,6 +40,9 @@ struct GridDesc {
     int ownLo, ownHi;   // local node planes [ownLo, ownHi) this part owns: reductions count exactly these
     int cmpLo, cmpHi;   // local node planes [cmpLo, cmpHi) the smoother updates (owned + shared planes; ghost planes are received)
     int oeLo, oeHi;     // local element layers [oeLo, oeHi) this part owns: Galerkin coarsening sub-assembles exactly these
+    // Stored-stencil levels: device table  position -> packed node coordinates  (launch_fill_pos_table), or nullptr (the tile
+    // kernels then derive the coordinates arithmetically).  Owned by the level; depends on nn / cbase / ccnt only.
+    const unsigned long long *posTab;
 };
 
 // Stored stencils are tiled: the NE = 3^N * N * N entries of kStencilTile consecutive positions form one contiguous
@@ -121,6 +124,21 @@ template<> __device__ __forceinline__ void solve_block<2>(const double (&M)[2][2
     const double id = 1.0 / (M[0][0] * M[1][1] - M[0][1] * M[1][0]);
     du[0] = (M[1][1] * r[0] - M[0][1] * r[1]) * id;
     du[1] = (M[0][0] * r[1] - M[1][0] * r[0]) * id;
+}
+// the same cofactor inverse as a matrix (one reciprocal): the stored-stencil smoother applies it to the reduced right-hand side
+template<int N> __device__ __forceinline__ void block_inverse(const double (&M)[N][N], double (&G)[N][N]);
+template<> __device__ __forceinline__ void block_inverse<3>(const double (&M)[3][3], double (&G)[3][3]) {
+    const double c00 = M[1][1] * M[2][2] - M[1][2] * M[2][1];
+    const double c01 = M[1][2] * M[2][0] - M[1][0] * M[2][2];
+    const double c02 = M[1][0] * M[2][1] - M[1][1] * M[2][0];
+    const double id = 1.0 / (M[0][0] * c00 + M[0][1] * c01 + M[0][2] * c02);
+    G[0][0] = c00 * id; G[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) * id; G[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) * id;
+    G[1][0] = c01 * id; G[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) * id; G[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) * id;
+    G[2][0] = c02 * id; G[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) * id; G[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) * id;
+}
+template<> __device__ __forceinline__ void block_inverse<2>(const double (&M)[2][2], double (&G)[2][2]) {
+    const double id = 1.0 / (M[0][0] * M[1][1] - M[0][1] * M[1][0]);
+    G[0][0] = M[1][1] * id; G[0][1] = -M[0][1] * id; G[1][0] = -M[1][0] * id; G[1][1] = M[0][0] * id;
 }
 // u_n += M^-1 (b - S') for free nodes; point Gauss-Seidel on the free components of partially
 // constrained nodes, direction following the sweep (MultigridSolver.hh:358-365).
@@ -308,7 +326,11 @@ bool stencil_sweep_fused(const GridDesc &g);   // small level: all colour passes
 void launch_gs_stencil_sweep(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b, const uint8_t *dmask,
                              bool forward, int xparity, unsigned *bar);
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
-                       const uint8_t *dmask, int color, bool forward, bool chained = false);
+                       const uint8_t *dmask, int color, bool forward, bool chained = false, double *resOut = nullptr);
+// resOut != nullptr: the pass also accumulates the residual of the sweep's final iterate (k_stencil_tile<RES>); all 2^N passes of
+// the sweep must be given the same resOut, the grid must be undivided and fully attached, Dirichlet components are left unmasked
+bool gs_residual_fusable(const GridDesc &g);
+void launch_fill_pos_table(cudaStream_t stream, const GridDesc &g, unsigned long long *tab);   // tab: g.numPos entries
 // Galerkin coarsening (MultigridSolver.hh:711-819): level-1 stencil from the fine Young's moduli and the 2^N
 // coarsened full-density matrices cK0[fi] (device, [fi][KE][KE]); level l >= 2 stencil as P^T A_{l-1} P.
 // bandLo..bandHi (inclusive, coarse node layers along the build direction): only those rows are recomputed -- the banded update of

@@ -30,9 +30,10 @@ namespace vf {
 template<int N, int SPT>
 struct TileShared {
     alignas(128) double S[Dims<N>::NE * kStencilTile];
-    double red[N][Dims<N>::NS / SPT][kStencilTile];
+    double red[N][Dims<N>::NS / SPT][kStencilTile];   // k_stencil_tile uses the first (NS / SPT + 1) / 2 rows (pairs of thread rows are pre-added by shuffle)
     double bs[N][kStencilTile];
     double us[N][kStencilTile];
+    double G[N * N][kStencilTile];   // Gauss-Seidel passes: the node's update matrix (k_stencil_tile)
     unsigned dm[kStencilTile];
     alignas(8) unsigned long long mbar;
 };
@@ -53,35 +54,73 @@ __device__ __forceinline__ bool pos_coords(const GridDesc &g, long long pos, int
 
 // SPT = stencil slots per thread: 1 (one thread row per slot, 432 threads, 4 blocks per SM in 3D) or 3 (one thread row per
 // (dx, dy) pair handling its three z-neighbours, 144 threads, 6 blocks per SM: more tiles in flight per SM).
-template<int N, bool GS, int MODE, int SPT>
+//
+// RES (Gauss-Seidel passes only): the sweep also leaves the residual  r = b - K u  of its FINAL iterate in rout, so that the V-cycle
+// needs no separate residual kernel (which would stream the whole stencil a second time: 4.2 GB at level 1 of a 256^3 grid).  Right
+// after its update a node's residual is  rhs - M du  (zero for a block solve, non-zero after the point sweep of a partially
+// constrained node); every LATER update du_j of a neighbour j changes it by  -K_ij du_j = -(K_ji)^T du_j  (the Galerkin operator is
+// symmetric), and K_ji is a slot of the row of j that the pass updating j holds in shared memory anyway.  So the thread of slot
+// (j -> i) adds  -(S_slot)^T du_j  to r_i for the neighbours i of colours visited EARLIER in this sweep (red.global.add.f64; the
+// summation order of those <= 26 contributions is not fixed, results agree with the direct residual to rounding).  Dirichlet
+// components of r are zeroed by the caller afterwards.  Only on undivided, fully attached grids (the host checks).
+//
+// Instruction economy (ncu: the tile kernels issue ~300 instructions per warp for 9 DFMA per thread and sit at 60 % issue-slot
+// utilisation with 32 registers per thread): on the levels that do not stream from HBM node coordinates come from the level's
+// position table (GridDesc::posTab, one 8-byte load instead of the divisions of pos_coords; on the streaming level the dependent
+// load costs more than the divisions), all node indices are 32-bit (3 * numNodes < 2^31 on every stored-stencil level, checked by
+// the host), the slot contributions of a warp's two thread rows are added by one shuffle before the shared-memory reduction (14
+// partial sums per component instead of 27), and a Gauss-Seidel pass has no serial 3 x 3 solve after the reduction (see G below).
+// Same-box A/B of these pieces: profiles/r06f_ab.log.
+using sidx = int;   // node indices of the stored-stencil levels (check_index_range)
+template<int N, bool GS, int MODE, int SPT, bool RES = false>
 __global__ void __launch_bounds__(kStencilTile * Dims<N>::NS / SPT, (N == 3 ? 4 : 8) * (SPT == 3 ? 3 : 2) / 2)
 k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double *__restrict__ S,
                const double *uin, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
-               double *out, int flags) {
+               double *out, int flags, double *rout) {
+    static_assert(!RES || (GS && SPT == 1), "the residual-emitting variant is a Gauss-Seidel pass with one slot per thread");
     // flags bit 0: forward sweep; bit 1: the previous kernel on the stream does not write S (a colour pass of the same sweep),
     // so the stencil tile may be requested BEFORE waiting for it -- the HBM round trip of this kernel's first wave then
     // overlaps the tail of the previous colour pass.
     pdl_trigger();
     const int forward = flags & 1;
     const bool earlyTile = (flags & 2) != 0;
-    constexpr int NS = Dims<N>::NS, A0 = Dims<N>::A0, NN = N * N, NE = Dims<N>::NE, ROWS = NS / SPT;
+    constexpr int NS = Dims<N>::NS, A0 = Dims<N>::A0, NN = N * N, NE = Dims<N>::NE, ROWS = NS / SPT, RP = (ROWS + 1) / 2;
     __shared__ TileShared<N, SPT> sh;
     const int tx = threadIdx.x, s = threadIdx.y;   // s: thread row, slots s * SPT .. s * SPT + SPT - 1
     const long long tile = tile0 + blockIdx.x;
-    const long long pos = tile * kStencilTile + tx;
+    // flags bit 4 (off by default, see stencil_stream_hint): thread 0 requests the stencil tile first of all, before any coordinate
+    // work.  (Padding tiles are zero-filled, so the request is always in bounds; a block without active nodes drains the copy before
+    // it exits; grids with tiles that are skipped as a whole -- ghost planes of a slab window, detached layers -- never do this.)
+    const bool requestFirst = (flags & 16) && !(GS && (g.cmpLo > 0 || g.cmpHi < g.nn[0])) && g.nActive >= g.nn[g.bd];
+    if (tx == 0 && s == 0) {
+        mbar_init(&sh.mbar, 1);
+        if (requestFirst) {
+            if (!earlyTile) pdl_wait();
+            if (flags & 4) tma_load_1d_stream(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+            else           tma_load_1d(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+        }
+    }
     int c[3] = {0, 0, 0};
-    const bool inRange = pos_coords<N>(g, pos, c);
-    const long long n = (long long)c[0] * g.ns[0] + (long long)c[1] * g.ns[1] + c[2];
+    bool inRange;
+    if (g.posTab) {
+        const unsigned long long e = __ldg(g.posTab + tile * kStencilTile + tx);
+        inRange = (e >> 63) == 0ull;
+        c[2] = (int)(e & 0xffffull); c[1] = (int)((e >> 16) & 0xffffull); c[0] = (int)((e >> 32) & 0xffffull);
+    } else inRange = pos_coords<N>(g, tile * kStencilTile + tx, c);
+    const sidx nnodes = (sidx)g.numNodes, ns0 = (sidx)g.ns[0], ns1 = (sidx)g.ns[1];
+    const sidx n = c[0] * ns0 + c[1] * ns1 + c[2];
     const bool detached = inRange && (((g.bd == 1) ? c[1] : c[2]) >= g.nActive);
     const bool active = inRange && !detached && !(GS && (c[0] < g.cmpLo || c[0] >= g.cmpHi)); // ghost planes of a slab window are not smoothed
-    if (tx == 0 && s == 0) mbar_init(&sh.mbar, 1);
     const int anyActive = __syncthreads_or(active ? 1 : 0);     // also publishes the barrier initialisation
-    if (!earlyTile) pdl_wait();
-    if (anyActive && tx == 0 && s == 0) {
-        if (flags & 4) tma_load_1d_stream(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
-        else           tma_load_1d(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+    if (!requestFirst) {
+        if (!earlyTile) pdl_wait();
+        if (anyActive && tx == 0 && s == 0) {
+            if (flags & 4) tma_load_1d_stream(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+            else           tma_load_1d(sh.S, S + tile * (long long)(NE * kStencilTile), NE * kStencilTile * sizeof(double), &sh.mbar);
+        }
     }
-    if (earlyTile) pdl_wait();
+    pdl_wait();
+    sidx pushTo = -1;   // RES: node index of this slot's neighbour if it receives this pass's contribution, else -1
     if (anyActive) {
         double acc[N], un[SPT][N];
         #pragma unroll
@@ -95,7 +134,7 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
         }
         if (active) {
             // stage b and the Dirichlet mask alongside so that the finalising threads have no global loads left
-            if (s < N && (GS || MODE == APPLY_RESIDUAL)) sh.bs[s][tx] = b[s * g.numNodes + n];
+            if (s < N && (GS || MODE == APPLY_RESIDUAL)) sh.bs[s][tx] = b[s * nnodes + n];
             if (s == N) sh.dm[tx] = dmask ? dmask[n] : 0u;
             #pragma unroll
             for (int j = 0; j < SPT; ++j) {
@@ -104,22 +143,29 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
                 { int r = slot;
                   #pragma unroll
                   for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
-                bool v = true; long long off = 0;
+                bool v = true;
                 #pragma unroll
-                for (int a = A0; a < 3; ++a) { const int qq = c[a] + d[a]; v = v && qq >= 0 && qq < g.nn[a]; off += (long long)d[a] * g.ns[a]; }
+                for (int a = A0; a < 3; ++a) { const int qq = c[a] + d[a]; v = v && qq >= 0 && qq < g.nn[a]; }
+                const sidx nb = n + d[0] * ns0 + d[1] * ns1 + d[2];
                 valid[j] = v;
                 if (v) {
                     if (flags & 8) {
                         const unsigned long long keep = l2_policy_evict_last();
                         #pragma unroll
-                        for (int k = 0; k < N; ++k) un[j][k] = ld_l2_hint(uin + k * g.numNodes + n + off, keep);
+                        for (int k = 0; k < N; ++k) un[j][k] = ld_l2_hint(uin + (k * nnodes + nb), keep);
                     } else {
                         #pragma unroll
-                        for (int k = 0; k < N; ++k) un[j][k] = uin[k * g.numNodes + n + off];
+                        for (int k = 0; k < N; ++k) un[j][k] = uin[k * nnodes + nb];
                     }
                     if (GS && slot == NS / 2) {
                         #pragma unroll
                         for (int k = 0; k < N; ++k) sh.us[k][tx] = un[j][k];
+                    }
+                    if (RES) {   // neighbours whose colour was visited earlier in this sweep receive -(S_slot)^T du
+                        const int cc = ((c[0] & 1) << 2) | ((c[1] & 1) << 1) | (c[2] & 1);
+                        const int m = ((d[0] != 0) << 2) | ((d[1] != 0) << 1) | (d[2] != 0);
+                        const bool visited = forward ? ((cc ^ m) < cc) : ((cc ^ m) > cc);
+                        if (visited) pushTo = nb;
                     }
                 }
             }
@@ -136,59 +182,157 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
                 }
             }
         }
-        #pragma unroll
-        for (int a = 0; a < N; ++a) sh.red[a][s][tx] = acc[a];
+        // thread rows 2w and 2w + 1 are the two halves of warp w (the last row has no partner): add them by shuffle
+        if (s != ROWS - 1) {
+            #pragma unroll
+            for (int a = 0; a < N; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);
+        }
+        if (!(s & 1)) {
+            #pragma unroll
+            for (int a = 0; a < N; ++a) sh.red[a][s >> 1][tx] = acc[a];
+        }
+
     }
     __syncthreads();
     if (!anyActive) {
         if (!GS && MODE == APPLY_SET && s == 0 && inRange) {   // applyK<ZeroInit> zero-fills the detached margin
             #pragma unroll
-            for (int a = 0; a < N; ++a) out[a * g.numNodes + n] = 0.0;
+            for (int a = 0; a < N; ++a) out[a * nnodes + n] = 0.0;
+        }
+        if (requestFirst && tx == 0 && s == 0) mbar_wait(&sh.mbar, 0);   // the requested tile must have landed before the block's shared memory is released
+        return;
+    }
+    if (s < N) { // thread row a = s sums the partial sums of component a (fixed order -> deterministic)
+        double t = 0.0;
+        #pragma unroll
+        for (int k = 0; k < RP; ++k) t += sh.red[s][k][tx];
+        sh.red[s][0][tx] = t;
+    }
+    if (GS && s == ROWS - 1) {
+        // Meanwhile the last thread row (idle during the reduction) prepares the node's update matrix G:  du = G (b - K u).
+        // G = M^-1 for a free node (cofactor inverse, as Eigen's fixed-size inverse(), MultigridSolver.hh:370), the linear map of the
+        // point Gauss-Seidel sweep over the free components for a partially constrained node (:358-365), 0 for skipped nodes (:350).
+        // The serial tail of the block after the reduction is then 9 multiply-adds instead of a 3 x 3 solve with its reciprocal.
+        double G[N][N];
+        #pragma unroll
+        for (int a = 0; a < N; ++a) {
+            #pragma unroll
+            for (int k = 0; k < N; ++k) G[a][k] = 0.0;
+        }
+        const unsigned dm = active ? sh.dm[tx] : (unsigned)((1 << N) - 1);
+        if (dm != (unsigned)((1 << N) - 1)) {
+            double M[N][N];
+            #pragma unroll
+            for (int a = 0; a < N; ++a) {
+                #pragma unroll
+                for (int k = 0; k < N; ++k) M[a][k] = sh.S[((NS / 2) * NN + a * N + k) * kStencilTile + tx];
+            }
+            if (dm == 0u) block_inverse<N>(M, G);
+            else {
+                #pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    double e[N], col[N];
+                    #pragma unroll
+                    for (int a = 0; a < N; ++a) e[a] = (a == k) ? 1.0 : 0.0;
+                    #pragma unroll
+                    for (int a = 0; a < N; ++a) col[a] = 0.0;
+                    if (forward) gs_point_sweep<N, true>(M, e, dm, col);
+                    else         gs_point_sweep<N, false>(M, e, dm, col);
+                    #pragma unroll
+                    for (int a = 0; a < N; ++a) G[a][k] = col[a];
+                }
+            }
+        }
+        #pragma unroll
+        for (int a = 0; a < N; ++a) {
+            #pragma unroll
+            for (int k = 0; k < N; ++k) sh.G[a * N + k][tx] = G[a][k];
+        }
+    }
+    __syncthreads();
+    if (GS) {
+        // every thread that needs du forms it itself from G and the reduced sums: no further barrier
+        if (!(s == 0 ? active : (RES && pushTo >= 0))) return;
+        double rhs[N], du[N];
+        #pragma unroll
+        for (int a = 0; a < N; ++a) rhs[a] = sh.bs[a][tx] - sh.red[a][0][tx];
+        #pragma unroll
+        for (int a = 0; a < N; ++a) {
+            double t = 0.0;
+            #pragma unroll
+            for (int k = 0; k < N; ++k) t = fma(sh.G[a * N + k][tx], rhs[k], t);
+            du[a] = t;
+        }
+        if (s == 0) {
+            const unsigned dm = sh.dm[tx];
+            if (dm != (unsigned)((1 << N) - 1)) {   // hasFullDirichlet nodes are skipped (:350)
+                #pragma unroll
+                for (int a = 0; a < N; ++a) out[a * nnodes + n] = sh.us[a][tx] + du[a];
+            }
+            if (RES) {   // the node's own residual after its update: the first write of r_n in this sweep, later passes add to it
+                #pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    double t = rhs[a];
+                    #pragma unroll
+                    for (int k = 0; k < N; ++k) t = fma(-sh.S[((NS / 2) * NN + a * N + k) * kStencilTile + tx], du[k], t);
+                    rout[a * nnodes + n] = ((dm >> a) & 1u) ? 0.0 : t;
+                }
+            }
+        }
+        if (RES && pushTo >= 0) {
+            #pragma unroll
+            for (int k = 0; k < N; ++k) {
+                double t = 0.0;
+                #pragma unroll
+                for (int a = 0; a < N; ++a) t = fma(sh.S[(s * NN + a * N + k) * kStencilTile + tx], du[a], t);
+                atomicAdd(rout + (k * nnodes + pushTo), -t);
+            }
         }
         return;
     }
-    if (s < N) { // thread row a = s sums the slot contributions of component a (fixed order -> deterministic)
-        double t = 0.0;
-        #pragma unroll
-        for (int k = 0; k < ROWS; ++k) t += sh.red[s][k][tx];
-        sh.red[s][0][tx] = t;
-    }
-    __syncthreads();
     if (s != 0 || !inRange) return;
-    if (GS && !active) return;
     if (detached) {
         if (!GS && MODE == APPLY_SET) {
             #pragma unroll
-            for (int a = 0; a < N; ++a) out[a * g.numNodes + n] = 0.0;
+            for (int a = 0; a < N; ++a) out[a * nnodes + n] = 0.0;
         }
         return;
     }
     const unsigned dm = sh.dm[tx];
-    if (GS) {
-        if (dm == (unsigned)((1 << N) - 1)) return; // hasFullDirichlet (MultigridSolver.hh:350)
-        double rhs[N], M[N][N], du[N];
-        #pragma unroll
-        for (int a = 0; a < N; ++a) {
-            rhs[a] = sh.bs[a][tx] - sh.red[a][0][tx];
-            #pragma unroll
-            for (int k = 0; k < N; ++k) M[a][k] = sh.S[((NS / 2) * NN + a * N + k) * kStencilTile + tx];
-        }
-        gs_node_update<N>(M, rhs, dm, forward != 0, du);
-        #pragma unroll
-        for (int a = 0; a < N; ++a) out[a * g.numNodes + n] = sh.us[a][tx] + du[a];
-    } else {
+    {
         #pragma unroll
         for (int a = 0; a < N; ++a) {
             const double av = sh.red[a][0][tx];
             double res;
             if (MODE == APPLY_SET) res = av;
-            else if (MODE == APPLY_ADD) res = out[a * g.numNodes + n] + av;
-            else if (MODE == APPLY_SUB) res = out[a * g.numNodes + n] - av;
+            else if (MODE == APPLY_ADD) res = out[a * nnodes + n] + av;
+            else if (MODE == APPLY_SUB) res = out[a * nnodes + n] - av;
             else res = sh.bs[a][tx] - av;
             if ((dm >> a) & 1u) res = 0.0;
-            out[a * g.numNodes + n] = res;
+            out[a * nnodes + n] = res;
         }
     }
+}
+
+// Position table of a stored-stencil level: entry pos = c2 | c1 << 16 | c0 << 32 of the node at position pos of the colour-major
+// numbering, bit 63 set for the padding positions of a colour's last tile.
+template<int N>
+__global__ void __launch_bounds__(256) k_fill_pos_table(const __grid_constant__ GridDesc g, unsigned long long *tab) {
+    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= g.numPos) return;
+    int c[3] = {0, 0, 0};
+    const bool ok = pos_coords<N>(g, pos, c);
+    tab[pos] = ok ? ((unsigned long long)c[2] | ((unsigned long long)c[1] << 16) | ((unsigned long long)c[0] << 32)) : (1ull << 63);
+}
+void launch_fill_pos_table(cudaStream_t stream, const GridDesc &g, unsigned long long *tab) {
+    if (g.nn[0] > 65535 || g.nn[1] > 65535 || g.nn[2] > 65535) throw std::runtime_error("stored-stencil level too large for the position table");
+    const unsigned blocks = (unsigned)((g.numPos + 255) / 256);
+    if (g.N == 3) k_fill_pos_table<3><<<blocks, 256, 0, stream>>>(g, tab);
+    else          k_fill_pos_table<2><<<blocks, 256, 0, stream>>>(g, tab);
+    VF_KERNEL_CHECK();
+}
+static void check_index_range(const GridDesc &g) {
+    if (3.0 * (double)g.numNodes >= 2147483648.0) throw std::runtime_error("stored-stencil level exceeds the 32-bit node index range of the tile kernels");
 }
 
 // flags bit 2: fetch the stencil tile with an L2 evict-first hint (levels whose stencil streams from HBM; VF_ST_EVICT_FIRST=0 disables)
@@ -196,7 +340,10 @@ static int stencil_stream_hint(const GridDesc &g) {
     static const bool on = [] { const char *e = std::getenv("VF_ST_EVICT_FIRST"); return !(e && e[0] == '0'); }();
     const double bytes = (double)g.numNodes * (g.N == 3 ? 1944.0 : 288.0);
     static const bool keepU = [] { const char *e = std::getenv("VF_ST_KEEP_U"); return e && e[0] == '1'; }();
-    return (on && bytes > 64.0 * 1048576.0) ? (keepU ? 12 : 4) : 0;   // larger than half the L2: the stencil cannot stay resident between passes anyway
+    // flags bit 4: request the tile before any coordinate work.  Measured and rejected (profiles/r06e_time_ops_early*.log: level-1 apply
+    // 0.69 -> 0.77 ms, sweep 0.93 -> 0.96 ms); VF_ST_EARLY_TMA=1 enables it.
+    static const bool early = [] { const char *e = std::getenv("VF_ST_EARLY_TMA"); return e && e[0] == '1'; }();
+    return ((on && bytes > 64.0 * 1048576.0) ? (keepU ? 12 : 4) : 0) | (early ? 16 : 0);   // larger than half the L2: the stencil cannot stay resident between passes anyway
 }
 static int stencil_slots_per_thread() {
     static const int v = [] { const char *e = std::getenv("VF_ST_SPT"); return (e && std::atoi(e) == 3) ? 3 : 1; }();
@@ -215,6 +362,7 @@ static void stencil_kernel_attributes() {
 #undef VF_ATTR
     prefer_shared(k_stencil_tile<3, true, APPLY_SET, 1>); prefer_shared(k_stencil_tile<2, true, APPLY_SET, 1>);
     prefer_shared(k_stencil_tile<3, true, APPLY_SET, 3>); prefer_shared(k_stencil_tile<2, true, APPLY_SET, 3>);
+    prefer_shared(k_stencil_tile<3, true, APPLY_SET, 1, true>); prefer_shared(k_stencil_tile<2, true, APPLY_SET, 1, true>);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -371,36 +519,49 @@ void launch_gs_stencil_sweep(const LaunchCtx &ctx, const GridDesc &g, const doub
 
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
                           const uint8_t *dmask, double *out, int mode) {
-    stencil_kernel_attributes();
+    stencil_kernel_attributes(); check_index_range(g);
     const bool big = stencil_level_streams(g);
     ProfScope ps(ctx, mode == APPLY_RESIDUAL ? (big ? PC_RESIDUAL_ST : PC_RESIDUAL_ST_SMALL) : (big ? PC_APPLY_ST : PC_APPLY_ST_SMALL), (double)g.numNodes);
     const int spt = stencil_slots_per_thread();
     const int hint = stencil_stream_hint(g);
     dim3 block(kStencilTile, (g.N == 3 ? 27 : 9) / spt), grid((unsigned)(g.numPos / kStencilTile));
 #define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) { \
-        if (spt == 3) VF_LAUNCH((k_stencil_tile<NN_, false, M, 3>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint); \
-        else          VF_LAUNCH((k_stencil_tile<NN_, false, M, 1>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint); }
+        if (spt == 3) VF_LAUNCH((k_stencil_tile<NN_, false, M, 3>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr); \
+        else          VF_LAUNCH((k_stencil_tile<NN_, false, M, 1>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr); }
     VF_CASE(3, APPLY_SET) VF_CASE(3, APPLY_ADD) VF_CASE(3, APPLY_SUB) VF_CASE(3, APPLY_RESIDUAL)
     VF_CASE(2, APPLY_SET) VF_CASE(2, APPLY_ADD) VF_CASE(2, APPLY_SUB) VF_CASE(2, APPLY_RESIDUAL)
 #undef VF_CASE
     VF_KERNEL_CHECK();
 }
 
+// VF_GS_RESIDUAL=0 keeps the separate residual kernel; VF_GS_RESIDUAL_MIN_NODES=<n> fuses only on levels of at least n nodes
+bool gs_residual_fusable(const GridDesc &g) {
+    static const bool on = [] { const char *e = std::getenv("VF_GS_RESIDUAL"); return !(e && e[0] == '0'); }();
+    static const long long minNodes = [] { const char *e = std::getenv("VF_GS_RESIDUAL_MIN_NODES"); return e ? std::atoll(e) : 0LL; }();
+    const bool undivided = g.xoff == 0 && g.cmpLo == 0 && g.cmpHi == g.nn[0] && g.ownLo == 0 && g.ownHi == g.nn[0];
+    return on && undivided && g.nActive >= g.nn[g.bd] && g.numNodes >= minNodes && !stencil_sweep_fused(g);
+}
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
-                       const uint8_t *dmask, int color, bool forward, bool chained) {
+                       const uint8_t *dmask, int color, bool forward, bool chained, double *resOut) {
     ColorDesc col;
     if (!make_color(g, color, col)) return;
-    stencil_kernel_attributes();
+    stencil_kernel_attributes(); check_index_range(g);
     const long long tot = (long long)g.ccnt[color][0] * g.ccnt[color][1] * g.ccnt[color][2];
     ProfScope ps(ctx, stencil_level_streams(g) ? PC_GS_ST : PC_GS_ST_SMALL, (double)col.cnt[0] * col.cnt[1] * col.cnt[2]);
     const int spt = stencil_slots_per_thread();
     dim3 block(kStencilTile, (g.N == 3 ? 27 : 9) / spt), grid((unsigned)((tot + kStencilTile - 1) / kStencilTile));
     const long long tile0 = g.cbase[color] / kStencilTile;
     const int fl = (forward ? 1 : 0) | (chained ? 2 : 0) | stencil_stream_hint(g);
-    if (g.N == 3 && spt == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
-    else if (g.N == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
-    else if (spt == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
-    else                      VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl);
+    double *const noRes = nullptr;
+    if (resOut) {   // residual-emitting pass: one slot per thread
+        block = dim3(kStencilTile, g.N == 3 ? 27 : 9);
+        if (g.N == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut);
+        else          VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut);
+    }
+    else if (g.N == 3 && spt == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes);
+    else if (g.N == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes);
+    else if (spt == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes);
+    else                      VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes);
     VF_KERNEL_CHECK();
 }
 
