@@ -447,7 +447,7 @@ struct MGLevel {
     int64_t sb = 0, se = 0, gne0 = 0; bool windowed = false;
     std::vector<uint8_t> nodeMask; DevBuf<uint8_t> dmask;
     DevBuf<double> x, b, r, S;
-    DevBuf<unsigned long long> posTab;   // levels >= 1: position -> node coordinates (GridDesc::posTab)
+    DevBuf<unsigned long long> posTab;   // latency-bound levels >= 1: position -> node coordinates for the tile kernels
     int firstMasked = INT_MAX, firstDetached = INT_MAX;
 };
 struct vf_mg {
@@ -951,7 +951,7 @@ Field fx(int l) { return Field{F_X, l}; } Field fb(int l) { return Field{F_B, l}
 // out (=, +=, -=) K u  or  out = b - K u  on one part
 void part_apply_K(vf_mg &mg, int l, const double *u, const double *b, double *out, int mode, bool zeroDirichlet, double *dotOut = nullptr) {
     if (l == 0) launch_apply_l0(mg.ctx, mg.sim->g, mg.sim->K0p, u, mg.sim->E.p, b, zeroDirichlet ? mg.dmask(0) : nullptr, out, mode, dotOut, mg.scratch.p);
-    else launch_apply_stencil(mg.ctx, mg.lv[l]->g, mg.lv[l]->S.p, u, b, zeroDirichlet ? mg.dmask(l) : nullptr, out, mode);
+    else launch_apply_stencil(mg.ctx, mg.lv[l]->g, mg.lv[l]->S.p, u, b, zeroDirichlet ? mg.dmask(l) : nullptr, out, mode, mg.lv[l]->posTab.p);
 }
 void mg_apply_K(vf_mg &lead, int l, Field u, Field b, Field out, int mode, bool zeroDirichlet, int dotSlot = -1) {
     if (l > 0) mg_update_stiffness(lead);
@@ -1005,7 +1005,7 @@ void mg_smooth(vf_mg &lead, int l, Field u, Field b, bool forward, const Field *
             const int lc = (lead.N == 3) ? (color ^ ((g.xoff & 1) << 2)) : color;   // local parity class of this global colour
             if (l == 0 && mg.N == 3) launch_gs3_color_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), lc, forward);
             else if (l == 0)         launch_gs_l0(mg.ctx, g, mg.sim->K0p, u(mg), b(mg), mg.sim->E.p, mg.dmask(0), lc, forward);
-            else                     launch_gs_stencil(mg.ctx, g, mg.lv[l]->S.p, u(mg), b(mg), mg.dmask(l), lc, forward, /* chained */ i > 0 && !lead.grp, res ? (*res)(mg) : nullptr);
+            else                     launch_gs_stencil(mg.ctx, g, mg.lv[l]->S.p, u(mg), b(mg), mg.dmask(l), lc, forward, /* chained */ i > 0 && !lead.grp, res ? (*res)(mg) : nullptr, mg.lv[l]->posTab.p);
         }
         // The four passes of one x parity only read planes of the other parity besides their own plane, so a ghost plane (one parity)
         // has to be current only when the passes of the OTHER parity start: one exchange per parity group instead of one per pass.
@@ -1562,7 +1562,6 @@ static vf_mg *mg_create_common(vf_sim *fine, int levels, int firstRep) {
             if (usePosTab && !stencil_level_streams(L->g)) {   // measured: helps the latency-bound levels, costs 2-6 % on the streaming one (profiles/r06f_ab.log)
                 L->posTab.alloc((size_t)L->g.numPos, false);
                 launch_fill_pos_table(fine->stream, L->g, L->posTab.p);
-                L->g.posTab = L->posTab.p;
             }
             VF_CUDA(cudaStreamSynchronize(fine->stream));
         }

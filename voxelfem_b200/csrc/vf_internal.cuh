@@ -40,9 +40,8 @@ struct GridDesc {
     int ownLo, ownHi;   // local node planes [ownLo, ownHi) this part owns: reductions count exactly these
     int cmpLo, cmpHi;   // local node planes [cmpLo, cmpHi) the smoother updates (owned + shared planes; ghost planes are received)
     int oeLo, oeHi;     // local element layers [oeLo, oeHi) this part owns: Galerkin coarsening sub-assembles exactly these
-    // Stored-stencil levels: device table  position -> packed node coordinates  (launch_fill_pos_table), or nullptr (the tile
-    // kernels then derive the coordinates arithmetically).  Owned by the level; depends on nn / cbase / ccnt only.
-    const unsigned long long *posTab;
+    // NB: the level-0 kernels are compiled at their register limit with this struct ahead of their constant-bank tables; changing its
+    // size shifted those operands and cost k_apply3w_l0 48 B of extra spills and 30 % of its speed (profiles/r06c_bench.log).
 };
 
 // Stored stencils are tiled: the NE = 3^N * N * N entries of kStencilTile consecutive positions form one contiguous
@@ -320,13 +319,16 @@ void launch_gs3_color_l0(const LaunchCtx &ctx, const GridDesc &g, const K0Param 
 // --- vf_stencil.cu: 3^N-point block-stencil levels (MultigridSolver.hh:323-334; TensorProductSimulator.hh:1500-1504)
 // Stencil layout: S[stencil_addr(stencil_pos(node), slot * N*N + a*N + b, NE)], numPos * NE doubles per level
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
-                          const uint8_t *dmask, double *out, int mode);
+                          const uint8_t *dmask, double *out, int mode, const unsigned long long *posTab = nullptr);
 // chained: the previous kernel on the stream is a colour pass of the same sweep (nothing in flight writes S)
 bool stencil_sweep_fused(const GridDesc &g);   // small level: all colour passes of a sweep in one persistent launch
 void launch_gs_stencil_sweep(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b, const uint8_t *dmask,
                              bool forward, int xparity, unsigned *bar);
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
-                       const uint8_t *dmask, int color, bool forward, bool chained = false, double *resOut = nullptr);
+                       const uint8_t *dmask, int color, bool forward, bool chained = false, double *resOut = nullptr,
+                       const unsigned long long *posTab = nullptr);
+// posTab: the level's device table  position -> packed node coordinates  (launch_fill_pos_table), or nullptr (the tile kernels
+// then derive the coordinates arithmetically)
 // resOut != nullptr: the pass also accumulates the residual of the sweep's final iterate (k_stencil_tile<RES>); all 2^N passes of
 // the sweep must be given the same resOut, the grid must be undivided and fully attached, Dirichlet components are left unmasked
 bool gs_residual_fusable(const GridDesc &g);

@@ -66,7 +66,7 @@ __device__ __forceinline__ bool pos_coords(const GridDesc &g, long long pos, int
 //
 // Instruction economy (ncu: the tile kernels issue ~300 instructions per warp for 9 DFMA per thread and sit at 60 % issue-slot
 // utilisation with 32 registers per thread): on the levels that do not stream from HBM node coordinates come from the level's
-// position table (GridDesc::posTab, one 8-byte load instead of the divisions of pos_coords; on the streaming level the dependent
+// position table (posTab, one 8-byte load instead of the divisions of pos_coords; on the streaming level the dependent
 // load costs more than the divisions), all node indices are 32-bit (3 * numNodes < 2^31 on every stored-stencil level, checked by
 // the host), the slot contributions of a warp's two thread rows are added by one shuffle before the shared-memory reduction (14
 // partial sums per component instead of 27), and a Gauss-Seidel pass has no serial 3 x 3 solve after the reduction (see G below).
@@ -76,7 +76,7 @@ template<int N, bool GS, int MODE, int SPT, bool RES = false>
 __global__ void __launch_bounds__(kStencilTile * Dims<N>::NS / SPT, (N == 3 ? 4 : 8) * (SPT == 3 ? 3 : 2) / 2)
 k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double *__restrict__ S,
                const double *uin, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
-               double *out, int flags, double *rout) {
+               double *out, int flags, double *rout, const unsigned long long *__restrict__ posTab) {
     static_assert(!RES || (GS && SPT == 1), "the residual-emitting variant is a Gauss-Seidel pass with one slot per thread");
     // flags bit 0: forward sweep; bit 1: the previous kernel on the stream does not write S (a colour pass of the same sweep),
     // so the stencil tile may be requested BEFORE waiting for it -- the HBM round trip of this kernel's first wave then
@@ -102,8 +102,8 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     }
     int c[3] = {0, 0, 0};
     bool inRange;
-    if (g.posTab) {
-        const unsigned long long e = __ldg(g.posTab + tile * kStencilTile + tx);
+    if (posTab) {
+        const unsigned long long e = __ldg(posTab + tile * kStencilTile + tx);
         inRange = (e >> 63) == 0ull;
         c[2] = (int)(e & 0xffffull); c[1] = (int)((e >> 16) & 0xffffull); c[0] = (int)((e >> 32) & 0xffffull);
     } else inRange = pos_coords<N>(g, tile * kStencilTile + tx, c);
@@ -518,7 +518,7 @@ void launch_gs_stencil_sweep(const LaunchCtx &ctx, const GridDesc &g, const doub
 }
 
 void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
-                          const uint8_t *dmask, double *out, int mode) {
+                          const uint8_t *dmask, double *out, int mode, const unsigned long long *posTab) {
     stencil_kernel_attributes(); check_index_range(g);
     const bool big = stencil_level_streams(g);
     ProfScope ps(ctx, mode == APPLY_RESIDUAL ? (big ? PC_RESIDUAL_ST : PC_RESIDUAL_ST_SMALL) : (big ? PC_APPLY_ST : PC_APPLY_ST_SMALL), (double)g.numNodes);
@@ -526,8 +526,8 @@ void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double 
     const int hint = stencil_stream_hint(g);
     dim3 block(kStencilTile, (g.N == 3 ? 27 : 9) / spt), grid((unsigned)(g.numPos / kStencilTile));
 #define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) { \
-        if (spt == 3) VF_LAUNCH((k_stencil_tile<NN_, false, M, 3>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr); \
-        else          VF_LAUNCH((k_stencil_tile<NN_, false, M, 1>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr); }
+        if (spt == 3) VF_LAUNCH((k_stencil_tile<NN_, false, M, 3>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr, posTab); \
+        else          VF_LAUNCH((k_stencil_tile<NN_, false, M, 1>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr, posTab); }
     VF_CASE(3, APPLY_SET) VF_CASE(3, APPLY_ADD) VF_CASE(3, APPLY_SUB) VF_CASE(3, APPLY_RESIDUAL)
     VF_CASE(2, APPLY_SET) VF_CASE(2, APPLY_ADD) VF_CASE(2, APPLY_SUB) VF_CASE(2, APPLY_RESIDUAL)
 #undef VF_CASE
@@ -542,7 +542,7 @@ bool gs_residual_fusable(const GridDesc &g) {
     return on && undivided && g.nActive >= g.nn[g.bd] && g.numNodes >= minNodes && !stencil_sweep_fused(g);
 }
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
-                       const uint8_t *dmask, int color, bool forward, bool chained, double *resOut) {
+                       const uint8_t *dmask, int color, bool forward, bool chained, double *resOut, const unsigned long long *posTab) {
     ColorDesc col;
     if (!make_color(g, color, col)) return;
     stencil_kernel_attributes(); check_index_range(g);
@@ -555,13 +555,13 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
     double *const noRes = nullptr;
     if (resOut) {   // residual-emitting pass: one slot per thread
         block = dim3(kStencilTile, g.N == 3 ? 27 : 9);
-        if (g.N == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut);
-        else          VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut);
+        if (g.N == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut, posTab);
+        else          VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut, posTab);
     }
-    else if (g.N == 3 && spt == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes);
-    else if (g.N == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes);
-    else if (spt == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes);
-    else                      VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes);
+    else if (g.N == 3 && spt == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab);
+    else if (g.N == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab);
+    else if (spt == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab);
+    else                      VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab);
     VF_KERNEL_CHECK();
 }
 
