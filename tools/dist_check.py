@@ -42,7 +42,7 @@ for ne, levels, first_rep, fmg in [((32, 16, 16), 3, 2, True), ((16 * world, 8, 
     it, res = grp.pcg_dev([x], [bd], 60, 1e-10, 1, 1, fmg)
     w = capi.from_soa(x.download(), 3)
     err = np.linalg.norm(w - s.window_of_nodal(u_ref)) / np.linalg.norm(u_ref)
-    good = it == it_ref and err < 1e-9 and np.allclose(res, res_ref, rtol=1e-6)
+    good = it == it_ref and err < 1e-9 and np.allclose(res, res_ref, rtol=1e-4)   # the residual-emitting sweep adds its contributions in no fixed order: rounding-level differences, amplified in the last entries of a history falling by ten orders
     print("rank %d grid %s levels %d first_rep %d fmg %s: iterations %d (undivided %d), window rel err %.2e -> %s" % (rank, ne, levels, first_rep, fmg, it, it_ref, err, "OK" if good else "FAIL"), flush=True)
     ok = ok and good
     grp.close()

@@ -1075,10 +1075,21 @@ void mg_vcycle(vf_mg &lead, int l, int nsmooth, bool residualSystem) {
     mg_enforce_dirichlet(lead, l, fx(l), residualSystem);
     // On a stored-stencil level the last pre-smoothing sweep emits the residual itself (k_stencil_tile<RES>): the stencil, 97 % of the
     // level's bytes, is streamed twice per visit instead of three times.
-    const bool fusedRes = l > 0 && nsmooth > 0 && !lead.grp && parts_of(lead).size() == 1 && gs_residual_fusable(lead.grid(l));
+    bool fusedRes = l > 0 && nsmooth > 0;
+    for (vf_mg *m : parts_of(lead)) fusedRes = fusedRes && gs_residual_fusable(m->grid(l));
     const Field rl = fr(l);
     for (int i = 0; i < nsmooth; ++i) mg_smooth(lead, l, fx(l), fb(l), true, (fusedRes && i == nsmooth - 1) ? &rl : nullptr);
-    if (fusedRes) launch_zero_dirichlet(lead.ctx, lead.grid(l), lead.dmask(l), lr(lead, l));   // computeResidual's mask (:538)
+    if (fusedRes) {
+        for (vf_mg *mp : parts_of(lead)) {
+            vf_mg &m = *mp; const GridDesc &g = m.grid(l); MGLevel &L = *m.lv[l];
+            // slab window: the shared planes next to a ghost plane did not see the neighbouring part's updates -- their residual is
+            // formed directly from the final iterate (the ghost planes are current after the sweep's last exchange)
+            if (g.cmpLo > 0)        launch_residual_stencil_plane(m.ctx, g, L.S.p, lx(m, l), lb(m, l), nullptr, lr(m, l), g.cmpLo, L.posTab.p);
+            if (g.cmpHi < g.nn[0])  launch_residual_stencil_plane(m.ctx, g, L.S.p, lx(m, l), lb(m, l), nullptr, lr(m, l), g.cmpHi - 1, L.posTab.p);
+            launch_zero_dirichlet(m.ctx, g, m.dmask(l), lr(m, l));   // computeResidual's mask (:538)
+        }
+        grp_exchange(lead, l, fr(l));   // as mg_residual: the restriction reads the ghost planes of r
+    }
     else mg_residual(lead, l, fx(l), fb(l), fr(l));
     mg_restrict(lead, l, fr(l), fb(l + 1));
     for (vf_mg *m : parts_of(lead)) launch_masked_zero(m->ctx, m->grid(l + 1), lx(*m, l + 1), 4 /* VOXELFEM_SIMD_WIDTH margin (:644) */);

@@ -330,8 +330,11 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
 // posTab: the level's device table  position -> packed node coordinates  (launch_fill_pos_table), or nullptr (the tile kernels
 // then derive the coordinates arithmetically)
 // resOut != nullptr: the pass also accumulates the residual of the sweep's final iterate (k_stencil_tile<RES>); all 2^N passes of
-// the sweep must be given the same resOut, the grid must be undivided and fully attached, Dirichlet components are left unmasked
+// the sweep must be given the same resOut, the grid must be fully attached, Dirichlet components are left unmasked and the shared
+// planes of a slab window incomplete (launch_residual_stencil_plane)
 bool gs_residual_fusable(const GridDesc &g);
+void launch_residual_stencil_plane(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
+                                   const uint8_t *dmask, double *out, int plane, const unsigned long long *posTab = nullptr);
 void launch_fill_pos_table(cudaStream_t stream, const GridDesc &g, unsigned long long *tab);   // tab: g.numPos entries
 // Galerkin coarsening (MultigridSolver.hh:711-819): level-1 stencil from the fine Young's moduli and the 2^N
 // coarsened full-density matrices cK0[fi] (device, [fi][KE][KE]); level l >= 2 stencil as P^T A_{l-1} P.

@@ -62,7 +62,9 @@ __device__ __forceinline__ bool pos_coords(const GridDesc &g, long long pos, int
 // symmetric), and K_ji is a slot of the row of j that the pass updating j holds in shared memory anyway.  So the thread of slot
 // (j -> i) adds  -(S_slot)^T du_j  to r_i for the neighbours i of colours visited EARLIER in this sweep (red.global.add.f64; the
 // summation order of those <= 26 contributions is not fixed, results agree with the direct residual to rounding).  Dirichlet
-// components of r are zeroed by the caller afterwards.  Only on undivided, fully attached grids (the host checks).
+// components of r are zeroed by the caller afterwards.  Only on fully attached grids (the host checks); in a slab window the shared
+// planes next to the ghost planes miss the contributions of the neighbouring part's updates and are recomputed by the caller
+// (launch_residual_stencil_plane).
 //
 // Instruction economy (ncu: the tile kernels issue ~300 instructions per warp for 9 DFMA per thread and sit at 60 % issue-slot
 // utilisation with 32 registers per thread): on the levels that do not stream from HBM node coordinates come from the level's
@@ -76,7 +78,8 @@ template<int N, bool GS, int MODE, int SPT, bool RES = false>
 __global__ void __launch_bounds__(kStencilTile * Dims<N>::NS / SPT, (N == 3 ? 4 : 8) * (SPT == 3 ? 3 : 2) / 2)
 k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double *__restrict__ S,
                const double *uin, const double *__restrict__ b, const uint8_t *__restrict__ dmask,
-               double *out, int flags, double *rout, const unsigned long long *__restrict__ posTab) {
+               double *out, int flags, double *rout, const unsigned long long *__restrict__ posTab, int planeSel) {
+    // planeSel >= 0 (apply / residual modes): only the nodes of local node plane planeSel are computed and written
     static_assert(!RES || (GS && SPT == 1), "the residual-emitting variant is a Gauss-Seidel pass with one slot per thread");
     // flags bit 0: forward sweep; bit 1: the previous kernel on the stream does not write S (a colour pass of the same sweep),
     // so the stencil tile may be requested BEFORE waiting for it -- the HBM round trip of this kernel's first wave then
@@ -110,7 +113,8 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
     const sidx nnodes = (sidx)g.numNodes, ns0 = (sidx)g.ns[0], ns1 = (sidx)g.ns[1];
     const sidx n = c[0] * ns0 + c[1] * ns1 + c[2];
     const bool detached = inRange && (((g.bd == 1) ? c[1] : c[2]) >= g.nActive);
-    const bool active = inRange && !detached && !(GS && (c[0] < g.cmpLo || c[0] >= g.cmpHi)); // ghost planes of a slab window are not smoothed
+    const bool active = inRange && !detached && !(GS && (c[0] < g.cmpLo || c[0] >= g.cmpHi)) // ghost planes of a slab window are not smoothed
+                        && !(!GS && planeSel >= 0 && c[0] != planeSel);
     const int anyActive = __syncthreads_or(active ? 1 : 0);     // also publishes the barrier initialisation
     if (!requestFirst) {
         if (!earlyTile) pdl_wait();
@@ -162,7 +166,7 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
                         for (int k = 0; k < N; ++k) sh.us[k][tx] = un[j][k];
                     }
                     if (RES) {   // neighbours whose colour was visited earlier in this sweep receive -(S_slot)^T du
-                        const int cc = ((c[0] & 1) << 2) | ((c[1] & 1) << 1) | (c[2] & 1);
+                        const int cc = ((((c[0] + g.xoff) & 1) << 2) | ((c[1] & 1) << 1) | (c[2] & 1));   // colour = parity class of the GLOBAL index
                         const int m = ((d[0] != 0) << 2) | ((d[1] != 0) << 1) | (d[2] != 0);
                         const bool visited = forward ? ((cc ^ m) < cc) : ((cc ^ m) > cc);
                         if (visited) pushTo = nb;
@@ -291,6 +295,7 @@ k_stencil_tile(const __grid_constant__ GridDesc g, long long tile0, const double
         return;
     }
     if (s != 0 || !inRange) return;
+    if (planeSel >= 0 && !active) return;
     if (detached) {
         if (!GS && MODE == APPLY_SET) {
             #pragma unroll
@@ -526,8 +531,8 @@ void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double 
     const int hint = stencil_stream_hint(g);
     dim3 block(kStencilTile, (g.N == 3 ? 27 : 9) / spt), grid((unsigned)(g.numPos / kStencilTile));
 #define VF_CASE(NN_, M) if (g.N == NN_ && mode == M) { \
-        if (spt == 3) VF_LAUNCH((k_stencil_tile<NN_, false, M, 3>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr, posTab); \
-        else          VF_LAUNCH((k_stencil_tile<NN_, false, M, 1>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr, posTab); }
+        if (spt == 3) VF_LAUNCH((k_stencil_tile<NN_, false, M, 3>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr, posTab, -1); \
+        else          VF_LAUNCH((k_stencil_tile<NN_, false, M, 1>), grid, block, 0, ctx.stream, g, 0, S, u, b, dmask, out, 1 | hint, nullptr, posTab, -1); }
     VF_CASE(3, APPLY_SET) VF_CASE(3, APPLY_ADD) VF_CASE(3, APPLY_SUB) VF_CASE(3, APPLY_RESIDUAL)
     VF_CASE(2, APPLY_SET) VF_CASE(2, APPLY_ADD) VF_CASE(2, APPLY_SUB) VF_CASE(2, APPLY_RESIDUAL)
 #undef VF_CASE
@@ -538,8 +543,28 @@ void launch_apply_stencil(const LaunchCtx &ctx, const GridDesc &g, const double 
 bool gs_residual_fusable(const GridDesc &g) {
     static const bool on = [] { const char *e = std::getenv("VF_GS_RESIDUAL"); return !(e && e[0] == '0'); }();
     static const long long minNodes = [] { const char *e = std::getenv("VF_GS_RESIDUAL_MIN_NODES"); return e ? std::atoll(e) : 0LL; }();
-    const bool undivided = g.xoff == 0 && g.cmpLo == 0 && g.cmpHi == g.nn[0] && g.ownLo == 0 && g.ownHi == g.nn[0];
-    return on && undivided && g.nActive >= g.nn[g.bd] && g.numNodes >= minNodes && !stencil_sweep_fused(g);
+    return on && g.nActive >= g.nn[g.bd] && g.numNodes >= minNodes && !stencil_sweep_fused(g);
+}
+// out = b - K u (Dirichlet components zeroed) on the nodes of local node plane `plane` only: one launch per colour of that x parity
+// over the tiles that hold the plane's nodes.  Completes the residual of a slab window's shared planes after a residual-emitting
+// sweep (their neighbours in the ghost planes are updated by the neighbouring part, so the pushed contributions are incomplete).
+void launch_residual_stencil_plane(const LaunchCtx &ctx, const GridDesc &g, const double *S, const double *u, const double *b,
+                                   const uint8_t *dmask, double *out, int plane, const unsigned long long *posTab) {
+    stencil_kernel_attributes(); check_index_range(g);
+    const int hint = stencil_stream_hint(g);
+    const int nc = 1 << g.N;
+    for (int c = 0; c < nc; ++c) {
+        if (g.N == 3 && ((c >> 2) & 1) != (plane & 1)) continue;
+        const long long perPlane = (long long)g.ccnt[c][1] * g.ccnt[c][2];
+        if (perPlane == 0 || (plane >> 1) >= g.ccnt[c][0]) continue;
+        const long long first = g.cbase[c] + (long long)(plane >> 1) * perPlane, last = first + perPlane - 1;
+        const long long t0 = first / kStencilTile, t1 = last / kStencilTile;
+        ProfScope ps(ctx, stencil_level_streams(g) ? PC_RESIDUAL_ST : PC_RESIDUAL_ST_SMALL, (double)perPlane);
+        dim3 block(kStencilTile, g.N == 3 ? 27 : 9), grid((unsigned)(t1 - t0 + 1));
+        if (g.N == 3) VF_LAUNCH((k_stencil_tile<3, false, APPLY_RESIDUAL, 1>), grid, block, 0, ctx.stream, g, t0, S, u, b, dmask, out, 1 | hint, nullptr, posTab, plane);
+        else          VF_LAUNCH((k_stencil_tile<2, false, APPLY_RESIDUAL, 1>), grid, block, 0, ctx.stream, g, t0, S, u, b, dmask, out, 1 | hint, nullptr, posTab, plane);
+        VF_KERNEL_CHECK();
+    }
 }
 void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S, double *u, const double *b,
                        const uint8_t *dmask, int color, bool forward, bool chained, double *resOut, const unsigned long long *posTab) {
@@ -555,13 +580,13 @@ void launch_gs_stencil(const LaunchCtx &ctx, const GridDesc &g, const double *S,
     double *const noRes = nullptr;
     if (resOut) {   // residual-emitting pass: one slot per thread
         block = dim3(kStencilTile, g.N == 3 ? 27 : 9);
-        if (g.N == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut, posTab);
-        else          VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut, posTab);
+        if (g.N == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut, posTab, -1);
+        else          VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1, true>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, resOut, posTab, -1);
     }
-    else if (g.N == 3 && spt == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab);
-    else if (g.N == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab);
-    else if (spt == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab);
-    else                      VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab);
+    else if (g.N == 3 && spt == 3) VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab, -1);
+    else if (g.N == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<3, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab, -1);
+    else if (spt == 3)        VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 3>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab, -1);
+    else                      VF_LAUNCH_PDL(chained, (k_stencil_tile<2, true, APPLY_SET, 1>), grid, block, 0, ctx.stream, g, tile0, S, u, b, dmask, u, fl, noRes, posTab, -1);
     VF_KERNEL_CHECK();
 }
 
