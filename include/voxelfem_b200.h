@@ -151,6 +151,10 @@ int vf_mg_update_stiffness_matrices(vf_mg *mg);                           /* upd
 int vf_mg_apply_K(vf_mg *mg, int level, const double *u, double *out);    /* applyK(l, u) (:464-504) */
 int vf_mg_compute_residual(vf_mg *mg, int level, const double *u, const double *b, double *r); /* computeResidual (:527-541) */
 int vf_mg_smooth(vf_mg *mg, int level, double *u, const double *b, int forward);  /* smoothingMulticoloredGS (:452-458) */
+/* smoothingMulticoloredGS followed by computeResidual (:452-458, :527-541) as the V-cycle runs them on a stored-stencil level
+ * (level >= 1, no detached layers): one sweep that also leaves r = b - K u of its final iterate (Dirichlet components zero).
+ * Fails with an error status where the fused form is not available (level 0, fabrication mask active). */
+int vf_mg_smooth_residual(vf_mg *mg, int level, double *u, const double *b, int forward, double *r);
 int vf_mg_restrict(vf_mg *mg, int fine_level, const double *fine, double *coarse);            /* restriction (:216-262) */
 int vf_mg_interpolate(vf_mg *mg, int fine_level, const double *coarse, double *fine, int accumulate); /* interpolation / accum_interpolation (:178-212) */
 /* Assembled 3^N-point block stencil of a coarse level: [node][3^N][N][N] doubles (the reference's

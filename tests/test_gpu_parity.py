@@ -128,6 +128,34 @@ def test_hierarchy_operators(capi, ne, dom, bc, levels, data_dir):
 
 
 @pytest.mark.parametrize("ne,dom,bc,levels", HIER)
+def test_residual_emitting_sweep(capi, ne, dom, bc, levels, data_dir):
+    """The sweep the V-cycle runs on stored-stencil levels (k_stencil_tile<RES>) against the oracle's smoothing sweep followed by
+    its computeResidual (MultigridSolver.hh:452-458, 527-541): same iterate, same residual, Dirichlet components exactly zero."""
+    N = len(ne)
+    rho = RNG.uniform(0.05, 1, int(np.prod(ne)))
+    g, o = make_pair(capi, ne, dom=(np.zeros(N), np.array(dom)), bc=bc, data_dir=data_dir, rho=rho)
+    gm, om = capi.MG(g, levels), OracleMG(o, levels)
+    gm.update_stiffness(); om.update_stiffness()
+    with pytest.raises(capi.VoxelFEMError):
+        gm.smooth_residual(0, np.zeros((om.nn(0), N)), np.zeros((om.nn(0), N)))   # level 0 is matrix-free: no fused form
+    for l in range(1, levels):
+        dm = om.get_sim(l).dirichlet_mask()
+        bits = (dm[:, None] >> np.arange(N)[None, :]) & 1
+        u0 = RNG.normal(size=(om.nn(l), N)); u0[bits == 1] = 0
+        b = RNG.normal(size=u0.shape)
+        for fwd in (True, False):
+            ug, rg = gm.smooth_residual(l, u0, b, fwd)
+            uo = om.smooth(l, u0, b, fwd)
+            ro = om.residual(l, uo, b)
+            assert rel(ug, uo) < 1e-11, (l, fwd)
+            assert np.isfinite(rg).all() and np.all(rg[bits == 1] == 0.0), (l, fwd)
+            # r is small where the sweep has just solved: compare on the scale of b - K u0
+            scale = np.abs(om.residual(l, u0, b)).max()
+            assert np.abs(rg - ro).max() < 1e-11 * scale, (l, fwd)
+            assert np.abs(rg - gm.residual(l, ug, b)).max() < 1e-11 * scale, (l, fwd)
+
+
+@pytest.mark.parametrize("ne,dom,bc,levels", HIER)
 @pytest.mark.parametrize("fmg", [True, False])
 def test_vcycle_matches_oracle(capi, ne, dom, bc, levels, fmg, data_dir):
     N = len(ne)

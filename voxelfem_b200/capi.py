@@ -123,6 +123,7 @@ def lib():
         "vf_mg_apply_K": (ci, [vp, ci, _dp, _dp]),
         "vf_mg_compute_residual": (ci, [vp, ci, _dp, _dp, _dp]),
         "vf_mg_smooth": (ci, [vp, ci, _dp, _dp, ci]),
+        "vf_mg_smooth_residual": (ci, [vp, ci, _dp, _dp, ci, _dp]),
         "vf_mg_restrict": (ci, [vp, ci, _dp, _dp]),
         "vf_mg_interpolate": (ci, [vp, ci, _dp, _dp, ci]),
         "vf_mg_get_stencil": (ci, [vp, ci, _dp]),
@@ -552,6 +553,12 @@ class MG(_Owned):
 
     def smooth(self, l, u, b, forward=True):
         uu = to_soa(u); _check(self.L.vf_mg_smooth(self.h, l, uu, to_soa(b), int(forward))); return from_soa(uu, self.N)
+
+    def smooth_residual(self, l, u, b, forward=True):
+        """One smoothing sweep that also returns computeResidual of its result (stored-stencil levels): (u, r)."""
+        uu = to_soa(u); r = np.zeros_like(uu)
+        _check(self.L.vf_mg_smooth_residual(self.h, l, uu, to_soa(b), int(forward), r))
+        return from_soa(uu, self.N), from_soa(r, self.N)
 
     def restrict(self, lf, fine):
         out = np.zeros(self.nn(lf + 1) * self.N); _check(self.L.vf_mg_restrict(self.h, lf, to_soa(fine), out)); return from_soa(out, self.N)

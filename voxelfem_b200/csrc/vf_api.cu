@@ -1754,6 +1754,20 @@ int vf_mg_smooth(vf_mg *mg, int l, double *u, const double *b, int forward) {
     mg_smooth(*mg, l, fu(du), fu(db), forward != 0);
     d2h(u, du, len, mg->ctx.stream); VF_CATCH
 }
+int vf_mg_smooth_residual(vf_mg *mg, int l, double *u, const double *b, int forward, double *r) {
+    VF_TRY
+    mg_sync_level_masks(*mg);
+    if (!(l > 0 && l < mg->numLevels() && !mg->grp && gs_residual_fusable(mg->grid(l)))) throw std::runtime_error("vf_mg_smooth_residual: the residual-emitting sweep is not available on this level");
+    const size_t len = (size_t)mg->grid(l).numNodes * mg->N;
+    double *du = mg_tmp(mg, 0, len), *db = mg_tmp(mg, 1, len), *dr = mg_tmp(mg, 2, len);
+    h2d(du, u, len, mg->ctx.stream); h2d(db, b, len, mg->ctx.stream);
+    VF_CUDA(cudaMemsetAsync(dr, 0xff, len * sizeof(double), mg->ctx.stream));   // NaN pattern: every entry must be written by the sweep
+    const Field rf = fu(dr);
+    mg_smooth(*mg, l, fu(du), fu(db), forward != 0, &rf);
+    launch_zero_dirichlet(mg->ctx, mg->grid(l), mg->dmask(l), dr);
+    d2h(u, du, len, mg->ctx.stream); d2h(r, dr, len, mg->ctx.stream);
+    VF_CATCH
+}
 int vf_mg_restrict(vf_mg *mg, int lf, const double *fine, double *coarse) {
     VF_TRY const size_t lenF = (size_t)mg->grid(lf).numNodes * mg->N, lenC = (size_t)mg->grid(lf + 1).numNodes * mg->N;
     double *df = mg_tmp(mg, 0, lenF), *dc = mg_tmp(mg, 1, lenC);
