@@ -181,6 +181,10 @@ int vf_mg_get_pcg_residual(vf_mg *mg, double *r);                         /* pcg
  * MultigridSolver.hh:1043-1045, 1146-1147) and until the buffers passed to the last solve are released. */
 int vf_mg_get_pcg_iterate(vf_mg *mg, double *x);
 int vf_mg_set_symmetric_gauss_seidel(vf_mg *mg, int symmetric);           /* setSymmetricGaussSeidel (:123-125) */
+/* on != 0: every preconditionedConjugateGradient call rebuilds the coarse hierarchy in its first iteration, as the reference does
+ * (stiffnessMatricesUpdated = false, MultigridSolver.hh:1104-1107); default: only when the moduli or the mask changed since the last
+ * build.  The host-buffer entry point vf_mg_pcg_io runs that rebuild while its input copies are in flight. */
+int vf_mg_set_rebuild_every_solve(vf_mg *mg, int on);
 int vf_mg_set_mask_layer(vf_mg *mg, int64_t fine_layer);                  /* setFabricationMaskHeightByLayer (:1022-1028) */
 int vf_mg_decrement_mask(vf_mg *mg, int fine_layer_increment);            /* decrementFabricationMaskHeightByLayer (:1030-1036) */
 int vf_mg_debug_get(vf_mg *mg, int which /*0 x, 1 b, 2 r*/, int level, double *out); /* debug_get_x/b (:1158-1159) */

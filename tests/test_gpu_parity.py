@@ -174,6 +174,32 @@ def test_vcycle_matches_oracle(capi, ne, dom, bc, levels, fmg, data_dir):
         assert rel_l2(gm.debug_get("x", l), om.debug_get("x", l)) < 1e-9
 
 
+def test_rebuild_every_solve_mode(capi, data_dir):
+    """vf_mg_set_rebuild_every_solve: the reference-literal mode in which every PCG call rebuilds the coarse hierarchy
+    (MultigridSolver.hh:1104-1107; through the host-buffer entry point the rebuild overlaps the input copies) gives the same
+    solution, iteration count and residual history as the version-tracked default, and really rebuilds (more kernel launches)."""
+    ne, levels = (32, 16, 16), 2
+    rho = RNG.uniform(0.1, 1, int(np.prod(ne)))
+    g, o = make_pair(capi, ne, dom=(np.zeros(3), np.array((2.0, 1.0, 1.0))), bc="3D/cantilever_flexion_E.bc", data_dir=data_dir, rho=rho)
+    gm, om = capi.MG(g, levels), OracleMG(o, levels)
+    f = g.build_load()
+    L = capi.lib()
+    u_ref, it_ref, res_ref = gm.pcg(np.zeros_like(f), f, 100, 1e-9, 1, 1, True)       # builds the hierarchy
+    L.vf_reset_kernel_launch_count()
+    u0, it0, res0 = gm.pcg(np.zeros_like(f), f, 100, 1e-9, 1, 1, True)                # up to date: no rebuild
+    n_default = L.vf_kernel_launch_count()
+    gm.set_rebuild_every_solve(True)
+    L.vf_reset_kernel_launch_count()
+    u1, it1, res1 = gm.pcg(np.zeros_like(f), f, 100, 1e-9, 1, 1, True)
+    n_rebuild = L.vf_kernel_launch_count()
+    gm.set_rebuild_every_solve(False)
+    uo, ito, _ = om.pcg(np.zeros_like(f), f, 100, 1e-9, 1, 1, True)
+    assert it0 == it_ref == it1 and abs(it1 - ito) <= 1
+    assert n_rebuild > n_default
+    assert rel_l2(u1, u_ref) < 1e-9 and rel_l2(u0, u_ref) < 1e-9 and rel_l2(u1, uo) < 1e-6
+    assert np.allclose(res1, res_ref, rtol=1e-4)
+
+
 PCG_CASES = [
     ("C1-small", (64, 32), (2.0, 1.0), "mbb_N.bc", 2, 0.5, 1e-5),
     ("C3-small", (32, 32, 32), (1.0, 1.0, 1.0), "3D/cantilever_flexion_E.bc", 2, 0.5, 1e-5),

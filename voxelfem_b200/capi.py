@@ -144,6 +144,7 @@ def lib():
         "vf_mg_pcg_dev": (ci, [vp, vp, vp, ci, cd, ci, ci, ci, ci, C.POINTER(ci), _dp, PCG_CALLBACK, vp]),
         "vf_mg_get_pcg_residual": (ci, [vp, _dp]),
         "vf_mg_set_symmetric_gauss_seidel": (ci, [vp, ci]),
+        "vf_mg_set_rebuild_every_solve": (ci, [vp, ci]),
         "vf_mg_set_mask_layer": (ci, [vp, i64]),
         "vf_mg_decrement_mask": (ci, [vp, ci]),
         "vf_mg_debug_get": (ci, [vp, ci, ci, _dp]),
@@ -605,6 +606,7 @@ class MG(_Owned):
         out = np.zeros(self.nn(0) * self.N); _check(self.L.vf_mg_get_pcg_residual(self.h, out)); return from_soa(out, self.N)
 
     def set_symmetric_gs(self, s): _check(self.L.vf_mg_set_symmetric_gauss_seidel(self.h, int(s)))
+    def set_rebuild_every_solve(self, on=True): _check(self.L.vf_mg_set_rebuild_every_solve(self.h, int(on)))
     def set_mask_layer(self, l): _check(self.L.vf_mg_set_mask_layer(self.h, l))
     def decrement_mask(self, inc): _check(self.L.vf_mg_decrement_mask(self.h, inc))
 

@@ -474,7 +474,14 @@ struct vf_mg {
     struct PrecondGraph { cudaGraphExec_t exec = nullptr; uint64_t version = 0; int nActive = -1, mgIt = 0, nsmooth = 0; bool fmg = false, sym = true; long long launches = 0; } pg, sg;   // sg: V-cycle over the replicated levels of an NCCL rank
     bool inSubCapture = false;
     bool useGraphs = true;
-    ~vf_mg() { if (hostScalars) cudaFreeHost(hostScalars); if (pg.exec) cudaGraphExecDestroy(pg.exec); if (sg.exec) cudaGraphExecDestroy(sg.exec); }
+    // Reference-literal mode (vf_mg_set_rebuild_every_solve): every PCG call rebuilds the coarse hierarchy (MultigridSolver.hh:1104-1107) instead
+    // of only when the moduli changed.  rebuiltForThisSolve: vf_mg_pcg_io already did it, overlapped with its host -> device copies.
+    bool rebuildEverySolve = false, rebuiltForThisSolve = false;
+    cudaStream_t ioStream = nullptr; cudaEvent_t ioEvA = nullptr, ioEvB = nullptr;   // copy stream of the host-buffer entry points
+    ~vf_mg() {
+        if (hostScalars) cudaFreeHost(hostScalars); if (pg.exec) cudaGraphExecDestroy(pg.exec); if (sg.exec) cudaGraphExecDestroy(sg.exec);
+        if (ioEvA) cudaEventDestroy(ioEvA); if (ioEvB) cudaEventDestroy(ioEvB); if (ioStream) cudaStreamDestroy(ioStream);
+    }
     int numLevels() const { return (int)lv.size(); }
     const uint8_t *dmask(int l) const { return l == 0 ? sim->dmaskDev.p : lv[l]->dmask.p; }
     const GridDesc &grid(int l) const { return l == 0 ? sim->g : lv[l]->g; }
@@ -1134,6 +1141,7 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
     std::vector<vf_mg *> &P = parts_of(lead);
     const int N = lead.N;
     lead.lastResiduals.clear(); lead.lastIters = 0;
+    const bool prebuilt = lead.rebuiltForThisSolve; lead.rebuiltForThisSolve = false;
     for (vf_mg *m : P) mg_sync_level_masks(*m);
     const Field r = fb(0), s = fx(0), d{F_D, 0}, Ad{F_AD, 0};
     auto X = [&](vf_mg &m) { for (size_t i = 0; i < P.size(); ++i) if (P[i] == &m) return xs[i]; return (double *)nullptr; };
@@ -1170,7 +1178,7 @@ void mg_pcg(vf_mg &lead, double *const *xs, const double *const *bs, int maxIter
     int i = 0; bool first = true; int cur = SC_RMR_A, old = SC_RMR_B;
     while ((i++ < maxIter) && (rsq > tol * tol * bsq)) {
         if (mgIterations > 0 && mgSmoothing > 0) {
-            mg_update_stiffness(lead); // lazily, first iteration (:1104-1107)
+            mg_update_stiffness(lead, lead.rebuildEverySolve && !prebuilt && i == 1); // lazily, first iteration (:1104-1107)
             // applyPreconditionerInv: zero initial guess (:577-580); the FMG cycle overwrites s by interpolation (:600)
             auto precond = [&]() {
                 if (!fmg) for (vf_mg *m : P) VF_CUDA(cudaMemsetAsync(s(*m), 0, sizeof(double) * m->sim->g.numNodes * N, m->ctx.stream));
@@ -1838,8 +1846,22 @@ int vf_mg_pcg_io(vf_mg *mg, const double *u0, const double *b, double *x_out, in
                  int *outIters, double *resNorms, vf_pcg_callback cb, void *user) {
     VF_TRY const size_t len = (size_t)mg->grid(0).numNodes * mg->N;
     double *dx = mg_tmp(mg, 0, len), *db = mg_tmp(mg, 1, len);
-    VF_CUDA(cudaMemcpyAsync(dx, u0, len * sizeof(double), cudaMemcpyHostToDevice, mg->ctx.stream));
-    VF_CUDA(cudaMemcpyAsync(db, b, len * sizeof(double), cudaMemcpyHostToDevice, mg->ctx.stream));
+    // The copies run on their own stream so that the hierarchy rebuild (which depends on the moduli only) overlaps them: at 256^3 the
+    // 6.6 ms rebuild hides behind 15 ms of PCIe traffic.
+    if (!mg->ioStream) {
+        VF_CUDA(cudaStreamCreateWithFlags(&mg->ioStream, cudaStreamNonBlocking));
+        VF_CUDA(cudaEventCreateWithFlags(&mg->ioEvA, cudaEventDisableTiming)); VF_CUDA(cudaEventCreateWithFlags(&mg->ioEvB, cudaEventDisableTiming));
+    }
+    VF_CUDA(cudaEventRecord(mg->ioEvA, mg->ctx.stream)); VF_CUDA(cudaStreamWaitEvent(mg->ioStream, mg->ioEvA, 0));   // earlier work on the buffers is done
+    VF_CUDA(cudaMemcpyAsync(dx, u0, len * sizeof(double), cudaMemcpyHostToDevice, mg->ioStream));
+    VF_CUDA(cudaMemcpyAsync(db, b, len * sizeof(double), cudaMemcpyHostToDevice, mg->ioStream));
+    VF_CUDA(cudaEventRecord(mg->ioEvB, mg->ioStream));
+    if (mgIt > 0 && mgSmooth > 0 && mg->numLevels() > 1 && !mg->grp) {
+        mg_sync_level_masks(*mg);
+        mg_update_stiffness(*mg, mg->rebuildEverySolve);
+        mg->rebuiltForThisSolve = true;
+    }
+    VF_CUDA(cudaStreamWaitEvent(mg->ctx.stream, mg->ioEvB, 0));
     mg_pcg(*mg, dx, db, maxIter, tol, mgIt, mgSmooth, fmg != 0, dirichletOK != 0, cb, user);
     d2h(x_out, dx, len, mg->ctx.stream);
     if (outIters) *outIters = mg->lastIters;
@@ -1852,6 +1874,7 @@ int vf_mg_get_pcg_iterate(vf_mg *mg, double *x) {
     d2h(x, mg->pcgX, (size_t)mg->grid(0).numNodes * mg->N, mg->ctx.stream); VF_CATCH
 }
 int vf_mg_set_symmetric_gauss_seidel(vf_mg *mg, int s) { mg->symmetricGS = s != 0; return 0; }
+int vf_mg_set_rebuild_every_solve(vf_mg *mg, int on) { mg->rebuildEverySolve = on != 0; return 0; }
 int vf_mg_set_mask_layer(vf_mg *mg, int64_t layer) { if (int rc = vf_sim_set_mask_layer(mg->sim, layer)) return rc; VF_TRY mg_sync_level_masks(*mg); VF_CATCH }
 int vf_mg_decrement_mask(vf_mg *mg, int inc) {
     VF_TRY // decrementFabricationMaskHeightByLayer (TensorProductSimulator.hh:311-324; MultigridSolver.hh:1030-1036)
