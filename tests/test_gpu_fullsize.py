@@ -82,3 +82,16 @@ def test_full_size_solve_and_transfers(capi, problem):
     a1 = mg.apply_K(1, xc)
     ref = mg.restrict(0, s.apply_K(mg.interpolate(0, xc)))
     assert np.abs(a1 - ref).max() < 1e-11 * np.abs(ref).max()
+    # The residual-emitting sweep at level 1 of the full-size hierarchy (4.2 GB stencil, the level that streams from HBM): its iterate
+    # equals the plain sweep's (same arithmetic) and its residual equals computeResidual of that iterate (MultigridSolver.hh:452-458, 527-541),
+    # for both sweep directions; Dirichlet components are exactly zero.
+    dm1 = mg.get_sim(1).dirichlet_mask()
+    bits = (dm1[:, None] >> np.arange(3)[None, :]) & 1
+    u1 = rng.standard_normal((mg.nn(1), 3)); u1[bits == 1] = 0
+    b1 = rng.standard_normal(u1.shape)
+    scale = np.abs(mg.residual(1, u1, b1)).max()
+    for fwd in (True, False):
+        us, rs = mg.smooth_residual(1, u1, b1, fwd)
+        assert np.abs(us - mg.smooth(1, u1, b1, fwd)).max() <= 1e-13 * np.abs(us).max()
+        assert np.isfinite(rs).all() and np.all(rs[bits == 1] == 0.0)
+        assert np.abs(rs - mg.residual(1, us, b1)).max() < 1e-11 * scale
