@@ -23,6 +23,7 @@ VARIANTS = {
     "one_shot_galerkin_coarsening": {"VF_COARSEN_ONESHOT": "1"},
     "dense_coarse_factorization": {"VF_COARSE_DENSE": "1"},
     "separate_residual_kernel": {"VF_GS_RESIDUAL": "0"},
+    "level1_coarsening_with_table_loads": {"VF_COARSEN_PARAMK": "0"},
     "tile_coordinates_without_position_table": {"VF_ST_POSTAB": "0"},
 }
 

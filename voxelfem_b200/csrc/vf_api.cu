@@ -910,7 +910,7 @@ void mg_update_stiffness(vf_mg &lead, bool force = false) {
         MGLevel &L = *mg.lv[l];
         const size_t len = (size_t)L.g.numPos * (mg.N == 3 ? 27 : 9) * mg.N * mg.N;
         if (L.S.n != len) L.S.alloc(len, true);
-        if (l == 1) launch_coarsen_from_moduli(mg.ctx, L.g, mg.sim->g, mg.sim->E.p, mg.cK0dev.p, L.S.p, bLo[l], bHi[l]);
+        if (l == 1) launch_coarsen_from_moduli(mg.ctx, L.g, mg.sim->g, mg.sim->E.p, mg.cK0dev.p, L.S.p, bLo[l], bHi[l], mg.cK0.data());
         else if (mg.N == 3 && !banded && !noSeparable) {
             const GridDesc &gf = mg.lv[l - 1]->g;
             const size_t need = coarsen_separable_scratch(L.g, gf);

@@ -340,7 +340,8 @@ void launch_fill_pos_table(cudaStream_t stream, const GridDesc &g, unsigned long
 // coarsened full-density matrices cK0[fi] (device, [fi][KE][KE]); level l >= 2 stencil as P^T A_{l-1} P.
 // bandLo..bandHi (inclusive, coarse node layers along the build direction): only those rows are recomputed -- the banded update of
 // updateStiffnessMatrices after a change of the fabrication mask (MultigridSolver.hh:907-1017); default: every row.
-void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc, int bandLo = 0, int bandHi = 0x7fffffff);
+void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc, int bandLo = 0, int bandHi = 0x7fffffff,
+                                const double *cK0host = nullptr);   // cK0host: host copy of cK0, enables the per-slot kernel with the blocks as kernel parameters
 void launch_coarsen_stencil(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *Sf, double *Sc, int bandLo = 0, int bandHi = 0x7fffffff);
 // P^T A P one axis at a time (3D, undivided grids, full rebuilds); scratch holds the two intermediate operators
 size_t coarsen_separable_scratch(const GridDesc &gc, const GridDesc &gf);

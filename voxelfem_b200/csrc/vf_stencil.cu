@@ -17,6 +17,7 @@
 #include "vf_reduce.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace vf {
 
@@ -649,8 +650,102 @@ k_coarsen_from_moduli(const __grid_constant__ GridDesc gc, const __grid_constant
     for (int i = 0; i < NN; ++i) Sc[stencil_addr(p, s * NN + i, Dims<N>::NE)] = acc[i];
 }
 
-void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc, int bandLo, int bandHi) {
+// The same sum with the coarsened full-density blocks as KERNEL PARAMETERS: one launch per stencil slot, and for a given slot the
+// blocks K[e][fi] = cK0[fi][rows of local node e, columns of local node m(e, slot)] (<= 4.6 KB) are warp-uniform compile-time
+// offsets into the constant bank, so the multiply-adds take them as operands directly.  The first kernel issues one global load per
+// multiply-add (the table is fetched through the load/store path although every lane reads the same entry) and is bound by that path:
+// 3.35 ms for level 1 of a 256^3 grid, whose 9.9 G multiply-adds are 0.6 ms of FP64 pipe time.  Same (e, fi, entry) summation order
+// as above: bit-identical stencils.
+template<int N> struct SlotK {
+    double k[1 << N][1 << N][N * N];   // [incident coarse element e][child fi][a * N + b]
+    int m[1 << N];                     // local node of n + delta in element e, or -1 if the element does not contain it
+};
+template<int N>
+__global__ void __launch_bounds__(128)
+k_coarsen_from_moduli_slot(const __grid_constant__ GridDesc gc, const __grid_constant__ GridDesc gf, const __grid_constant__ SlotK<N> K,
+                           const double *__restrict__ E, double *__restrict__ Sc, int s, int bandLo, int bandHi) {
+    constexpr int NPE = Dims<N>::NPE, A0 = Dims<N>::A0, NN = N * N;
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= gc.numNodes) return;
+    int c[3]; { long long r = n; c[2] = (int)(r % gc.nn[2]); r /= gc.nn[2]; c[1] = (int)(r % gc.nn[1]); c[0] = (int)(r / gc.nn[1]); }
+    { const int cb = (gc.bd == 1) ? c[1] : c[2]; if (cb < bandLo || cb > bandHi) return; }   // banded update: rows outside keep their values
+    int d[3] = {0, 0, 0};
+    { int r = s; for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+    double acc[NN];
+    #pragma unroll
+    for (int i = 0; i < NN; ++i) acc[i] = 0.0;
+    bool nbValid = true;
+    for (int a = A0; a < 3; ++a) { const int q = c[a] + d[a]; nbValid = nbValid && q >= 0 && q < gc.nn[a]; }
+    if (nbValid) {
+        const int xs = xshift(gf, gc);
+        #pragma unroll
+        for (int e = 0; e < NPE; ++e) { // incident coarse elements; node is local node ln == e
+            if (K.m[e] < 0) continue;   // warp-uniform
+            bool ok = true; int ec[3] = {0, 0, 0};
+            #pragma unroll
+            for (int a = A0; a < 3; ++a) {
+                ec[a] = c[a] - ((e >> (2 - a)) & 1);
+                ok = ok && ec[a] >= 0 && ec[a] < gc.ne[a];
+            }
+            if (!ok) continue;
+            // first child of the element; child fi adds its bits times the element strides (compile-time selection of uniform operands)
+            long long base = 0;
+            #pragma unroll
+            for (int a = A0; a < 3; ++a) base += (long long)(2 * ec[a] + (a == 0 ? xs : 0)) * gf.es[a];
+            const int q0 = 2 * ec[0] + xs;
+            #pragma unroll
+            for (int fi = 0; fi < NPE; ++fi) {
+                if (A0 == 0) { const int q = q0 + ((fi >> 2) & 1); if (q < gf.oeLo || q >= gf.oeHi) continue; }   // sub-assembly over the fine element layers this part owns
+                long long ef = base;
+                #pragma unroll
+                for (int a = A0; a < 3; ++a) if ((fi >> (2 - a)) & 1) ef += gf.es[a];
+                const double Ef = __ldg(E + ef);
+                #pragma unroll
+                for (int i = 0; i < NN; ++i) acc[i] = fma(Ef, K.k[e][fi][i], acc[i]);
+            }
+        }
+    }
+    const long long p = stencil_pos(gc, c[0], c[1], c[2]);
+    #pragma unroll
+    for (int i = 0; i < NN; ++i) Sc[stencil_addr(p, s * NN + i, Dims<N>::NE)] = acc[i];
+}
+template<int N>
+static void coarsen_from_moduli_slots(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0host, double *Sc, int bandLo, int bandHi) {
+    constexpr int NPE = Dims<N>::NPE, KE = Dims<N>::KE, A0 = Dims<N>::A0, NS = Dims<N>::NS;
+    const unsigned blocks = (unsigned)((gc.numNodes + 127) / 128);
+    for (int s = 0; s < NS; ++s) {
+        int d[3] = {0, 0, 0};
+        { int r = s; for (int a = 2; a >= A0; --a) { d[a] = r % 3 - 1; r /= 3; } }
+        SlotK<N> K; std::memset(&K, 0, sizeof(K));
+        for (int e = 0; e < NPE; ++e) {
+            bool ok = true; int m = 0;
+            for (int a = A0; a < 3; ++a) {
+                const int mb = d[a] + ((e >> (2 - a)) & 1);
+                ok = ok && (mb == 0 || mb == 1);
+                m |= (mb & 1) << (2 - a);
+            }
+            K.m[e] = ok ? m : -1;
+            if (!ok) continue;
+            for (int fi = 0; fi < NPE; ++fi)
+                for (int a = 0; a < N; ++a)
+                    for (int b = 0; b < N; ++b) K.k[e][fi][a * N + b] = cK0host[(size_t)fi * KE * KE + (size_t)(N * e + a) * KE + (N * m + b)];
+        }
+        count_launch();
+        k_coarsen_from_moduli_slot<N><<<blocks, 128, 0, ctx.stream>>>(gc, gf, K, E, Sc, s, bandLo, bandHi);
+        VF_KERNEL_CHECK();
+    }
+}
+
+// cK0host: the host copy of cK0 (the per-slot parameter form needs it); VF_COARSEN_PARAMK=0 selects the first kernel
+void launch_coarsen_from_moduli(const LaunchCtx &ctx, const GridDesc &gc, const GridDesc &gf, const double *E, const double *cK0, double *Sc, int bandLo, int bandHi,
+                                const double *cK0host) {
     ProfScope ps(ctx, PC_COARSEN, (double)gc.numNodes);
+    static const bool paramK = [] { const char *e = std::getenv("VF_COARSEN_PARAMK"); return !(e && e[0] == '0'); }();
+    if (cK0host && paramK) {
+        if (gc.N == 3) coarsen_from_moduli_slots<3>(ctx, gc, gf, E, cK0host, Sc, bandLo, bandHi);
+        else           coarsen_from_moduli_slots<2>(ctx, gc, gf, E, cK0host, Sc, bandLo, bandHi);
+        return;
+    }
     dim3 block(128), grid((unsigned)((gc.numNodes + 127) / 128), gc.N == 3 ? 27 : 9);
     if (gc.N == 3) k_coarsen_from_moduli<3><<<grid, block, 0, ctx.stream>>>(gc, gf, E, cK0, Sc, bandLo, bandHi);
     else           k_coarsen_from_moduli<2><<<grid, block, 0, ctx.stream>>>(gc, gf, E, cK0, Sc, bandLo, bandHi);
