@@ -314,3 +314,25 @@ def test_fabrication_mask_arithmetic_and_masked_operator():
     assert s.mask_info() == (5, 6)
     with pytest.raises(Exception):
         mg.decrement_mask(6)
+
+
+def test_C1_full_size_against_sparse_direct_solve(data_dir):
+    """BASELINE.json configs[0] at its real size (2D MBB, 256 x 128, rho = 0.5, E_min = 1e-5, 3 coarsening levels, FMG-PCG to 1e-10 --
+    python/CoarseningLevelBenchmark.py:76-100): the oracle's converged displacement against a sparse direct solve of an independently
+    assembled stiffness matrix, its reported residual against b - K u, and the iteration count the GPU tests and bench.py quote (16)."""
+    ne, dom, levels = (256, 128), (np.zeros(2), np.array([2.0, 1.0])), 3
+    s = make_sim(ne, dom=dom, bc="mbb_N.bc", data_dir=data_dir, emin=1e-5)
+    s.set_uniform_density(0.5)
+    mg = OracleMG(s, levels)
+    f = s.build_load()
+    u, iters, res = mg.pcg(np.zeros_like(f), f, 100, 1e-10, 1, 1, True)
+    assert iters == 16
+    assert res[-1] <= 1e-10 * np.linalg.norm(f)
+    K = npref.assemble_K(ne, s.K0(), s.E())
+    uref = npref.direct_solve(K, f, s.dirichlet_mask(), 2)
+    assert np.linalg.norm(u - uref) < 1e-7 * np.linalg.norm(uref)
+    assert abs(0.5 * (f * u).sum() - 0.5 * (f * uref).sum()) < 1e-8 * abs(0.5 * (f * uref).sum())   # compliance
+    r = npref.dof_to_field(npref.field_to_dof(f) - K @ npref.field_to_dof(u), 2)
+    bits = (s.dirichlet_mask()[:, None] >> np.arange(2)[None, :]) & 1
+    r[bits == 1] = 0
+    assert abs(np.linalg.norm(r) - res[-1]) < 1e-2 * res[-1]   # recurrence residual vs re-evaluated residual, eleven orders below ||f||
