@@ -62,7 +62,7 @@ def test_coarsening_level_benchmark_flow(vf, data_dir, dim, grid, levels):
     assert abs(len(seen) - ito) <= 1 and [s[0] for s in seen] == list(range(1, len(seen) + 1))
     assert rel_l2(u, uo) < 1e-6
     k = min(len(seen), ito)
-    assert np.allclose([s[1] for s in seen][:k], reso[:k], rtol=1e-5)
+    assert np.allclose([s[1] for s in seen][:k], reso[:k], rtol=1e-4)
     assert rel_l2(seen[-1][2], u) < 1e-14                         # the callback's iterate of the last iteration is the result
     r = mg.computeResidual(0, u, f)
     assert np.linalg.norm(r) <= 1e-10 * np.linalg.norm(f) * 1.01

